@@ -1,0 +1,157 @@
+"""ctypes binding of tapes_py_interface.so (C ABI: include/tapes_b200.h).
+
+Loading fails loudly when the library has not been built; there is no CPU fallback.
+"""
+
+import ctypes
+import os
+
+import numpy
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'tapes_py_interface.so')
+
+# every symbol include/tapes_b200.h declares
+SYMBOLS = (
+    'setup_gambit', 'cleanup_gambit', 'c_register_problems', 'c_compute_dy_dt',
+    'tapes_last_error', 'tapes_clear_error', 'tapes_alphabet_size', 'tapes_register_rules',
+    'tapes_model', 'tapes_release_model', 'tapes_rhs_device', 'tapes_rhs_profile', 'tapes_sync', 'tapes_model_info',
+    'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
+)
+
+_lib = None
+
+
+def load():
+  """Loads the shared library and declares its signatures."""
+  global _lib
+  if _lib is not None:
+    return _lib
+  if not os.path.exists(LIB_PATH):
+    raise OSError(
+        f'{LIB_PATH} is missing: build it with '
+        '`python -m chemical_kinetics_and_program_execution_b200.build_ext` '
+        '(or __graft_entry__.build()); this package has no CPU fallback.')
+  lib = ctypes.CDLL(LIB_PATH)
+  vp, i64, i32, dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_double
+  lib.setup_gambit.restype = vp
+  lib.setup_gambit.argtypes = []
+  lib.cleanup_gambit.restype = None
+  lib.cleanup_gambit.argtypes = [vp]
+  lib.c_register_problems.restype = i64
+  lib.c_register_problems.argtypes = [i64]
+  lib.c_compute_dy_dt.restype = None
+  lib.c_compute_dy_dt.argtypes = [vp, i64, i64, vp, vp]
+  lib.tapes_last_error.restype = ctypes.c_char_p
+  lib.tapes_last_error.argtypes = []
+  lib.tapes_clear_error.restype = None
+  lib.tapes_clear_error.argtypes = []
+  lib.tapes_alphabet_size.restype = i64
+  lib.tapes_alphabet_size.argtypes = [ctypes.c_char_p]
+  lib.tapes_register_rules.restype = i32
+  lib.tapes_register_rules.argtypes = [ctypes.c_char_p, i64, i64] + [vp] * 7
+  lib.tapes_model.restype = vp
+  lib.tapes_model.argtypes = [ctypes.c_char_p, i64]
+  lib.tapes_release_model.restype = i32
+  lib.tapes_release_model.argtypes = [ctypes.c_char_p, i64]
+  lib.tapes_rhs_device.restype = i32
+  lib.tapes_rhs_device.argtypes = [vp, vp, vp, vp]
+  lib.tapes_rhs_profile.restype = i32
+  lib.tapes_rhs_profile.argtypes = [vp, vp, vp, vp, vp, i32]
+  lib.tapes_sync.restype = i32
+  lib.tapes_sync.argtypes = [vp]
+  lib.tapes_model_info.restype = i32
+  lib.tapes_model_info.argtypes = [vp, vp, i32]
+  lib.tapes_model_timing.restype = i32
+  lib.tapes_model_timing.argtypes = [vp, vp, i32]
+  lib.tapes_export_csr.restype = i32
+  lib.tapes_export_csr.argtypes = [vp, vp, vp]
+  lib.tapes_export_node_weights.restype = i32
+  lib.tapes_export_node_weights.argtypes = [vp, vp]
+  lib.tapes_rule_table.restype = i64
+  lib.tapes_rule_table.argtypes = [ctypes.c_char_p, i64] + [vp] * 11
+  if hasattr(lib, 'tapes_dop853_create'):
+    lib.tapes_dop853_create.restype = vp
+    lib.tapes_dop853_create.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl]
+    lib.tapes_dop853_destroy.restype = None
+    lib.tapes_dop853_destroy.argtypes = [vp]
+    lib.tapes_dop853_step_to.restype = i32
+    lib.tapes_dop853_step_to.argtypes = [vp, dbl, vp]
+    lib.tapes_dop853_info.restype = i32
+    lib.tapes_dop853_info.argtypes = [vp, vp, i32]
+    lib.tapes_observe.restype = i32
+    lib.tapes_observe.argtypes = [vp, vp, vp, vp, i64, vp]
+  _lib = lib
+  return lib
+
+
+def last_error():
+  return load().tapes_last_error().decode()
+
+
+def check(ok, what):
+  """Raises RuntimeError carrying the library's error message when `ok` is false."""
+  if not ok:
+    msg = last_error()
+    load().tapes_clear_error()
+    raise RuntimeError(f'{what}: {msg}' if msg else what)
+
+
+MODEL_INFO_FIELDS = (
+    'n_states', 'n_nodes', 'nnz', 'n_flux_rules', 'n_levels', 'launches_per_rhs', 'n_terms',
+    'n_sum_nodes', 'worlds_walked', 'leaf_worlds', 'seeds', 'hash_inserts', 'hash_unique',
+    'alphabet', 'cl_k', 'spmv_lanes_per_row')
+
+
+def model_info(model):
+  buf = numpy.zeros(len(MODEL_INFO_FIELDS), dtype=numpy.int64)
+  n = load().tapes_model_info(model, buf.ctypes.data, buf.size)
+  return {name: int(buf[i]) for i, name in enumerate(MODEL_INFO_FIELDS[:n])}
+
+
+def model_timing(model):
+  buf = numpy.zeros(3, dtype=numpy.float64)
+  load().tapes_model_timing(model, buf.ctypes.data, 3)
+  return dict(host_enumerate_ms=float(buf[0]), device_expand_ms=float(buf[1]),
+              device_csr_ms=float(buf[2]))
+
+
+def rule_table(tag, cl_k):
+  """Host-only flux-rule table of (tag, cl_k) as a dict of numpy arrays."""
+  lib = load()
+  n_steps = ctypes.c_int64(0)
+  stats = numpy.zeros(2, dtype=numpy.int64)
+  n_rules = lib.tapes_rule_table(tag.encode(), cl_k, ctypes.addressof(n_steps), None, None, None,
+                                 None, None, None, None, None, None, stats.ctypes.data)
+  check(n_rules >= 0, 'tapes_rule_table')
+  ns = n_steps.value
+  out = dict(
+      rule_ptr=numpy.zeros(n_rules + 1, dtype=numpy.int64),
+      step_kind=numpy.zeros(ns, dtype=numpy.int32), step_len=numpy.zeros(ns, dtype=numpy.int32),
+      step_long=numpy.zeros(ns, dtype=numpy.int64), step_short=numpy.zeros(ns, dtype=numpy.int64),
+      step_prob=numpy.zeros(ns, dtype=numpy.float64),
+      seed_len=numpy.zeros((n_rules, 2), dtype=numpy.int32),
+      seed_orig=numpy.zeros((n_rules, 2), dtype=numpy.uint64),
+      seed_adj=numpy.zeros((n_rules, 2), dtype=numpy.uint64))
+  n2 = lib.tapes_rule_table(
+      tag.encode(), cl_k, ctypes.addressof(n_steps), out['rule_ptr'].ctypes.data,
+      out['step_kind'].ctypes.data, out['step_len'].ctypes.data, out['step_long'].ctypes.data,
+      out['step_short'].ctypes.data, out['step_prob'].ctypes.data, out['seed_len'].ctypes.data,
+      out['seed_orig'].ctypes.data, out['seed_adj'].ctypes.data, stats.ctypes.data)
+  check(n2 == n_rules, 'tapes_rule_table')
+  out['worlds_walked'] = int(stats[0])
+  out['leaf_worlds'] = int(stats[1])
+  return out
+
+
+def register_rules(tag, size_a, rules):
+  """Registers a rewrite-rule set (dict with keys tape, span, catalyst, pattern[R,4], repl[R,4],
+  rate, select_weight) under `tag`."""
+  i32 = lambda x: numpy.ascontiguousarray(numpy.asarray(x, dtype=numpy.int32))
+  f64 = lambda x: numpy.ascontiguousarray(numpy.asarray(x, dtype=numpy.float64))
+  arrs = (i32(rules['tape']), i32(rules['span']), i32(rules['catalyst']),
+          i32(rules['pattern']).reshape(-1, 4), i32(rules['repl']).reshape(-1, 4),
+          f64(rules['rate']), f64(rules['select_weight']))
+  rc = load().tapes_register_rules(tag.encode(), size_a, arrs[0].shape[0],
+                                   *[a.ctypes.data for a in arrs])
+  check(rc == 0, 'tapes_register_rules')

@@ -1,0 +1,271 @@
+// C ABI (include/tapes_b200.h).  The four drop-in symbols keep the names and signatures the
+// reference's ctypes layer binds (framework/markov_tapes.py:40-56).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+#include <map>
+#include <memory>
+#include <string>
+
+#include "../../include/tapes_b200.h"
+#include "engine.h"
+#include "rules.h"
+
+namespace {
+
+struct Runtime {
+  int device = -1;
+  bool cuda_ok = false;
+};
+
+std::string g_error;
+Runtime* g_runtime = nullptr;
+std::map<std::pair<std::string, int>, std::unique_ptr<tapes::Model>> g_models;
+
+void fail(const std::string& msg) {
+  g_error = msg;
+  std::fprintf(stderr, "tapes_b200: %s\n", msg.c_str());
+  std::fflush(stderr);
+}
+
+bool ensure_cuda() {
+  if (g_runtime && g_runtime->cuda_ok) return true;
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if (err != cudaSuccess || count == 0) {
+    fail(std::string("no CUDA device available (") + cudaGetErrorString(err) +
+         "); this library has no CPU fallback");
+    return false;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (const char* lr = std::getenv("LOCAL_RANK")) dev = std::atoi(lr) % count;
+  if (const char* td = std::getenv("TAPES_DEVICE")) dev = std::atoi(td) % count;
+  if (cudaSetDevice(dev) != cudaSuccess) { fail("cudaSetDevice failed"); return false; }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major < 10) {
+    fail(std::string("device '") + prop.name + "' is not sm_100; kernels are built for sm_100a only");
+    return false;
+  }
+  if (!g_runtime) g_runtime = new Runtime();
+  g_runtime->device = dev;
+  g_runtime->cuda_ok = true;
+  return true;
+}
+
+tapes::Model* get_model(const char* tag, int64_t cl_k) {
+  tapes::register_builtin_problems();
+  auto key = std::make_pair(std::string(tag), (int)cl_k);
+  auto it = g_models.find(key);
+  if (it != g_models.end()) return it->second.get();
+  const tapes::Problem* prob = tapes::find_problem(tag);
+  if (!prob) { fail(std::string("unknown problem tag: ") + tag); return nullptr; }
+  if (!ensure_cuda()) return nullptr;
+  try {
+    auto t0 = std::chrono::steady_clock::now();
+    tapes::RuleTable table = tapes::enumerate_rules(*prob, (int)cl_k);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::unique_ptr<tapes::Model> m = tapes::build_model(table, nullptr);
+    m->stats.host_enumerate_ms = ms;
+    tapes::Model* raw = m.get();
+    g_models[key] = std::move(m);
+    return raw;
+  } catch (const std::exception& ex) {
+    fail(std::string("building ") + tag + " k=" + std::to_string(cl_k) + " failed: " + ex.what());
+    return nullptr;
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* setup_gambit(void) {
+  if (!ensure_cuda()) return nullptr;
+  return (void*)g_runtime;
+}
+
+void cleanup_gambit(void* handle) {
+  (void)handle;
+  g_models.clear();
+  if (g_runtime) { delete g_runtime; g_runtime = nullptr; }
+}
+
+int64_t c_register_problems(int64_t n) {
+  tapes::register_builtin_problems();
+  std::printf("=== Registered Problems ===\n");
+  for (const std::string& tag : tapes::registered_tags()) std::printf("%s\n", tag.c_str());
+  std::printf("======\n");
+  std::fflush(stdout);
+  return n + 1;
+}
+
+void c_compute_dy_dt(const char* tag, int64_t cl_k, int64_t debug, const double* probs_in,
+                     double* probs_out) {
+  (void)debug;
+  tapes::Model* m = get_model(tag, cl_k);
+  if (!m) return;
+  try {
+    tapes::rhs_host(*m, probs_in, probs_out);
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+  }
+}
+
+const char* tapes_last_error(void) { return g_error.c_str(); }
+void tapes_clear_error(void) { g_error.clear(); }
+
+int64_t tapes_alphabet_size(const char* tag) {
+  tapes::register_builtin_problems();
+  const tapes::Problem* p = tapes::find_problem(tag);
+  return p ? p->alphabet : -1;
+}
+
+int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, const int32_t* tape,
+                         const int32_t* span, const int32_t* catalyst, const int32_t* pattern,
+                         const int32_t* replacement, const double* rate, const double* select_weight) {
+  try {
+    tapes::register_builtin_problems();
+    std::vector<tapes::RewriteRule> rules((size_t)n_rules);
+    for (int64_t i = 0; i < n_rules; ++i) {
+      tapes::RewriteRule& r = rules[(size_t)i];
+      r.tape = tape[i]; r.span = span[i]; r.catalyst = catalyst[i];
+      for (int j = 0; j < 4; ++j) { r.pattern[j] = pattern[4 * i + j]; r.replacement[j] = replacement[4 * i + j]; }
+      r.rate = rate[i]; r.select_weight = select_weight[i];
+    }
+    tapes::register_problem(tag, (int)alphabet, tapes::body_from_rewrite_rules(std::move(rules)));
+    // a re-registered tag invalidates cached structures
+    for (auto it = g_models.begin(); it != g_models.end();)
+      it = (it->first.first == tag) ? g_models.erase(it) : std::next(it);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+void* tapes_model(const char* tag, int64_t cl_k) { return (void*)get_model(tag, cl_k); }
+
+int tapes_release_model(const char* tag, int64_t cl_k) {
+  return g_models.erase(std::make_pair(std::string(tag), (int)cl_k)) ? 0 : 1;
+}
+
+int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream) {
+  if (!model) { fail("null model"); return 1; }
+  try {
+    tapes::rhs_device(*(tapes::Model*)model, d_probs_in, d_probs_out, (cudaStream_t)cuda_stream);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_rhs_profile(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream,
+                      double* phase_ms, int capacity) {
+  if (!model) { fail("null model"); return 1; }
+  try {
+    float ms[3] = {0, 0, 0};
+    tapes::rhs_device_profiled(*(tapes::Model*)model, d_probs_in, d_probs_out, (cudaStream_t)cuda_stream, ms);
+    for (int i = 0; i < 3 && i < capacity; ++i) phase_ms[i] = ms[i];
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_sync(void* model) {
+  if (!model) { fail("null model"); return 1; }
+  cudaError_t err = cudaStreamSynchronize(((tapes::Model*)model)->stream);
+  if (err != cudaSuccess) { fail(cudaGetErrorString(err)); return 1; }
+  return 0;
+}
+
+int tapes_model_info(void* model, int64_t* out, int capacity) {
+  if (!model) { fail("null model"); return 0; }
+  const tapes::Model& m = *(tapes::Model*)model;
+  const int64_t v[] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
+                       (int64_t)m.levels.size(), m.launches_per_rhs, m.stats.terms, m.stats.sum_nodes,
+                       m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
+                       m.stats.hash_unique, (int64_t)m.A, (int64_t)m.k, (int64_t)m.spmv_group};
+  int n = (int)(sizeof(v) / sizeof(v[0]));
+  if (n > capacity) n = capacity;
+  for (int i = 0; i < n; ++i) out[i] = v[i];
+  return n;
+}
+
+int tapes_model_timing(void* model, double* out, int capacity) {
+  if (!model) { fail("null model"); return 0; }
+  const tapes::Model& m = *(tapes::Model*)model;
+  const double v[] = {m.stats.host_enumerate_ms, m.stats.device_expand_ms, m.stats.device_csr_ms};
+  int n = 3 > capacity ? capacity : 3;
+  for (int i = 0; i < n; ++i) out[i] = v[i];
+  return n;
+}
+
+int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
+  if (!model) { fail("null model"); return 1; }
+  tapes::Model& m = *(tapes::Model*)model;
+  cudaStreamSynchronize(m.stream);
+  if (cudaMemcpy(row_ptr, m.row_ptr, (m.n_states + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+      (m.nnz && cudaMemcpy(entries, m.entries, m.nnz * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) {
+    fail("export_csr: copy failed");
+    return 1;
+  }
+  return 0;
+}
+
+int tapes_export_node_weights(void* model, double* weights) {
+  if (!model) { fail("null model"); return 1; }
+  tapes::Model& m = *(tapes::Model*)model;
+  cudaStreamSynchronize(m.stream);
+  if (m.n_nodes && cudaMemcpy(weights, m.node_w, m.n_nodes * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    fail("export_node_weights: copy failed");
+    return 1;
+  }
+  return 0;
+}
+
+int64_t tapes_rule_table(const char* tag, int64_t cl_k, int64_t* n_steps, int64_t* rule_ptr,
+                         int32_t* step_kind, int32_t* step_len, int64_t* step_long, int64_t* step_short,
+                         double* step_prob, int32_t* seed_len, uint64_t* seed_orig, uint64_t* seed_adj,
+                         int64_t* walk_stats) {
+  try {
+    tapes::register_builtin_problems();
+    const tapes::Problem* prob = tapes::find_problem(tag);
+    if (!prob) { fail(std::string("unknown problem tag: ") + tag); return -1; }
+    tapes::RuleTable t = tapes::enumerate_rules(*prob, (int)cl_k);
+    int64_t steps = 0;
+    for (auto& r : t.rules) steps += (int64_t)r.steps.size();
+    if (n_steps) *n_steps = steps;
+    if (walk_stats) { walk_stats[0] = t.worlds_walked; walk_stats[1] = t.leaf_worlds; }
+    if (rule_ptr) {
+      int64_t s = 0;
+      for (size_t i = 0; i < t.rules.size(); ++i) {
+        rule_ptr[i] = s;
+        for (const tapes::Step& st : t.rules[i].steps) {
+          step_kind[s] = st.kind; step_len[s] = st.length; step_long[s] = st.long_index;
+          step_short[s] = st.short_index; step_prob[s] = st.prob;
+          ++s;
+        }
+        for (int tp = 0; tp < 2; ++tp) {
+          seed_len[2 * i + tp] = t.rules[i].tape[tp].length;
+          seed_orig[2 * i + tp] = t.rules[i].tape[tp].orig;
+          seed_adj[2 * i + tp] = t.rules[i].tape[tp].adjusted;
+        }
+      }
+      rule_ptr[t.rules.size()] = s;
+    }
+    return (int64_t)t.rules.size();
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return -1;
+  }
+}
+
+}  // extern "C"

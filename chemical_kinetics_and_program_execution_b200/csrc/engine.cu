@@ -1,0 +1,755 @@
+// Device engine (sm_100a): frontier expansion of the window-extension forest, CSR assembly of the
+// flux structure, and the per-step evaluation  dy/dt = S * w(p).
+//
+// Reference behaviour being reproduced (framework/tape_multiverse.scm):
+//   lr-rec-extend-1 1249-1401   window extension, one node per (seed, window, context)
+//   get-prob-relative 1263-1269 per-node ratio  p_long / max(p_long, p_short), 0 when p_long == 0
+//   accumulate-dp/dt 1271-1301  -w at the original window index, +w at the adjusted one
+//   sp-table-marginal 362-385   last-axis marginals, sequential sums
+//   mv-state-unfold-for-tape-get 482-588, -choose 594-626   leaf-world probabilities
+#include "engine.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <type_traits>
+
+#include "primitives.cuh"
+
+namespace tapes {
+
+namespace {
+
+constexpr uint8_t FL_TERM = 1;   // contributes a flux term (window is full)
+constexpr uint8_t FL_LEFT = 2;   // expands leftwards
+constexpr uint8_t FL_RIGHT = 4;  // hands its weight to the right chain
+constexpr uint32_t kNoRank = 0xffffffffu;
+constexpr uint32_t kOutflowBit = 0x80000000u;
+constexpr int kThreads = 256;
+
+template <typename T>
+T* dalloc(size_t n, cudaStream_t st) {
+  void* p = nullptr;
+  TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st));
+  return (T*)p;
+}
+template <typename T>
+void dfree(T*& p, cudaStream_t st) {
+  if (p) cudaFreeAsync((void*)p, st);
+  p = nullptr;
+}
+
+struct Consts {
+  uint32_t A;
+  int k;
+  uint32_t M;       // A^(k-1)
+  uint32_t pw[33];  // pw[i] = A^i for i < k (fits u32 since A^k < 2^32)
+};
+
+// Build-time frontier: the nodes of one level with everything needed to expand them.
+struct Frontier {
+  uint64_t n = 0;
+  uint32_t n_plain = 0;
+  uint32_t* io = nullptr;
+  uint32_t* ia = nullptr;
+  uint32_t* seed = nullptr;
+  uint8_t* meta = nullptr;
+  uint8_t* flags = nullptr;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Expansion pass 1: classify every frontier node and hash-insert right-chain prefixes.
+// ---------------------------------------------------------------------------------------------
+__global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __restrict__ cflag,
+                                uint32_t* __restrict__ tflag, uint8_t* __restrict__ kflag) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < f.n;
+  bool haskey = false;
+  uint64_t key = 0;
+  uint32_t pa = 0;
+  if (valid) {
+    const uint8_t meta = f.meta[i], fl = f.flags[i];
+    const int kind = meta >> 6, len = meta & 63;
+    const uint32_t io = f.io[i], ia = f.ia[i];
+    uint32_t child = 0;
+    if (kind == NODE_SUM) {
+      child = 1;
+    } else if (fl & FL_LEFT) {
+      if (len < c.k) child = 1;                       // tm.scm:1340-1357
+      else if (io / c.A != ia / c.A) child = 1;       // tm.scm:1358-1379, entry test 1331
+    }
+    if (kind != NODE_SUM && (fl & FL_RIGHT)) {        // tm.scm:1393-1397 / 1319-1322
+      const uint32_t po = io % c.M;
+      pa = ia % c.M;
+      haskey = po != pa;                              // tm.scm:1308-1309
+      key = ((uint64_t)f.seed[i] << 32) | po;
+    }
+    cflag[i] = child;
+    tflag[i] = (fl & FL_TERM) ? 1u : 0u;
+    kflag[i] = haskey ? 1 : 0;
+  }
+  hash_insert_warp(hs, haskey, key, pa);
+}
+
+__global__ void slot_flag_kernel(HashSet hs, uint32_t* __restrict__ flag) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h <= hs.mask) flag[h] = hs.keys[h] != kEmptyKey ? 1u : 0u;
+}
+
+__global__ void slot_gather_kernel(HashSet hs, const uint64_t* __restrict__ rank,
+                                   uint64_t* __restrict__ out) {
+  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (h <= hs.mask) {
+    const uint64_t k = hs.keys[h];
+    if (k != kEmptyKey) out[rank[h]] = k;
+  }
+}
+
+__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t n, uint64_t key) {
+  uint32_t lo = 0, hi = n;
+  while (lo < hi) {
+    const uint32_t mid = lo + ((hi - lo) >> 1);
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Expansion pass 2: write the children (digit-major, so that consecutive threads touch
+// consecutive table entries on every later evaluation), the flux edges and the SUM ranks.
+// ---------------------------------------------------------------------------------------------
+__global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ cflag,
+                            const uint32_t* __restrict__ tflag, const uint8_t* __restrict__ kflag,
+                            const uint64_t* __restrict__ crank, const uint64_t* __restrict__ trank,
+                            uint64_t n_parents_with_children, const uint64_t* __restrict__ sorted_keys,
+                            uint32_t n_keys, Frontier next, uint32_t* __restrict__ next_parent,
+                            uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
+                            uint32_t* __restrict__ keyrank) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= f.n) return;
+  const uint8_t meta = f.meta[i];
+  const int kind = meta >> 6, len = meta & 63;
+  const uint32_t io = f.io[i], ia = f.ia[i], seed = f.seed[i];
+  const uint32_t gid = (uint32_t)(cur_base + i);
+  if (cflag[i]) {
+    const uint64_t r = crank[i];
+    uint32_t bo, ba, step;
+    uint8_t nmeta, nfl;
+    if (kind == NODE_SUM) {            // right extension of a prefix: prefix * A + x
+      bo = io * c.A; ba = ia * c.A; step = 1;
+      nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
+      nfl = FL_TERM | FL_RIGHT;
+    } else if (len < c.k) {            // left extension: x * A^len + index
+      bo = io; ba = ia; step = c.pw[len];
+      const int nl = len + 1;
+      nmeta = (uint8_t)((NODE_LEFT << 6) | nl);
+      nfl = FL_LEFT | (nl == c.k ? FL_TERM : 0) | (nl == c.k - 1 ? FL_RIGHT : 0);
+    } else {                           // left shift of a full window: x * A^(k-1) + index / A
+      bo = io / c.A; ba = ia / c.A; step = c.M;
+      nmeta = (uint8_t)((NODE_LEFT << 6) | c.k);
+      nfl = FL_TERM | FL_LEFT;
+    }
+    for (uint32_t x = 0; x < c.A; ++x) {
+      const uint64_t ci = (uint64_t)x * n_parents_with_children + r;
+      next.io[ci] = bo + x * step;
+      next.ia[ci] = ba + x * step;
+      next.seed[ci] = seed;
+      next.meta[ci] = nmeta;
+      next.flags[ci] = nfl;
+      next_parent[ci] = gid;
+    }
+  }
+  if (tflag[i]) {
+    const uint64_t e = 2 * trank[i];
+    edge_row[e] = io;     edge_val[e] = gid | kOutflowBit;   // -w at the original window
+    edge_row[e + 1] = ia; edge_val[e + 1] = gid;             // +w at the adjusted window
+  }
+  if (kflag[i]) {
+    const uint64_t key = ((uint64_t)seed << 32) | (io % c.M);
+    keyrank[i] = lower_bound_u64(sorted_keys, n_keys, key);
+  } else {
+    keyrank[i] = kNoRank;
+  }
+}
+
+__global__ void sum_nodes_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs,
+                                 Consts c, Frontier next, uint64_t first) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_keys) return;
+  const uint64_t key = sorted_keys[r];
+  const uint64_t idx = first + r;
+  next.io[idx] = (uint32_t)key;
+  next.ia[idx] = hash_lookup(hs, key);
+  next.seed[idx] = (uint32_t)(key >> 32);
+  next.meta[idx] = (uint8_t)((NODE_SUM << 6) | (c.k - 1));
+  next.flags[idx] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Grouping: (group, value) pairs -> CSR lists with ascending values inside each group.
+// ---------------------------------------------------------------------------------------------
+__global__ void group_count_kernel(const uint32_t* __restrict__ group, uint64_t n,
+                                   uint32_t* __restrict__ counts) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && group[i] != kNoRank) atomicAdd(&counts[group[i]], 1u);
+}
+
+__global__ void group_fill_ids_kernel(const uint32_t* __restrict__ group, uint64_t n, uint64_t id_base,
+                                      const uint64_t* __restrict__ ptr, uint32_t* __restrict__ cursor,
+                                      uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && group[i] != kNoRank) {
+    const uint32_t g = group[i];
+    out[ptr[g] + atomicAdd(&cursor[g], 1u)] = (uint32_t)(id_base + i);
+  }
+}
+
+__global__ void group_fill_vals_kernel(const uint32_t* __restrict__ group, const uint32_t* __restrict__ val,
+                                       uint64_t n, const uint64_t* __restrict__ ptr,
+                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const uint32_t g = group[i];
+    out[ptr[g] + atomicAdd(&cursor[g], 1u)] = val[i];
+  }
+}
+
+__global__ void group_sort_kernel(const uint64_t* __restrict__ ptr, uint64_t n_groups,
+                                  uint32_t* __restrict__ vals) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const uint64_t lo = ptr[g], hi = ptr[g + 1];
+  for (uint64_t a = lo + 1; a < hi; ++a) {  // insertion sort; groups are short
+    const uint32_t v = vals[a];
+    uint64_t b = a;
+    while (b > lo && vals[b - 1] > v) { vals[b] = vals[b - 1]; --b; }
+    vals[b] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-step kernels.
+// ---------------------------------------------------------------------------------------------
+
+// marg_{L}[i] = sum_j marg_{L+1}[i * A + j], j ascending from an exact 0 (tm.scm:378-384).
+__global__ void marginal_kernel(const double* __restrict__ src, double* __restrict__ dst, uint64_t n_out,
+                                uint32_t A) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_out) return;
+  const double* s = src + i * A;
+  double total = 0.0;
+  for (uint32_t j = 0; j < A; ++j) total = total + s[j];
+  dst[i] = total;
+}
+
+// The short tables (marg_top .. marg_0) in one block.
+__global__ void marginal_tail_kernel(const double* __restrict__ p, double* __restrict__ marg,
+                                     const uint64_t* __restrict__ off_in, int k, int top, uint32_t A) {
+  __shared__ uint64_t off[40];
+  if (threadIdx.x < 40) off[threadIdx.x] = off_in[threadIdx.x];
+  __syncthreads();
+  uint64_t n_out = 1;
+  for (int i = 0; i < top; ++i) n_out *= A;
+  for (int L = top; L >= 0; --L) {
+    const double* src = (L + 1 == k) ? p : marg + off[L + 1];
+    double* dst = marg + off[L];
+    for (uint64_t i = threadIdx.x; i < n_out; i += blockDim.x) {
+      double total = 0.0;
+      for (uint32_t j = 0; j < A; ++j) total = total + src[i * A + j];
+      dst[i] = total;
+    }
+    n_out /= A;
+    __syncthreads();
+  }
+}
+
+struct Tables {
+  const double* p;       // marg_k
+  const double* marg;    // marg_L, L < k, at marg + off[L]
+  uint64_t off[34];
+  int k;
+};
+__device__ __forceinline__ const double* table(const Tables& t, int L) {
+  return L == t.k ? t.p : t.marg + t.off[L];
+}
+
+// Leaf-world probabilities: product of unfold ratios (tm.scm:556-565) and choice
+// probabilities (tm.scm:617-618) in program order.
+__global__ void rule_weight_kernel(Tables t, uint32_t n_rules, const uint32_t* __restrict__ rule_ptr,
+                                   const uint8_t* __restrict__ kind, const uint8_t* __restrict__ len,
+                                   const uint32_t* __restrict__ ilong, const uint32_t* __restrict__ ishort,
+                                   const double* __restrict__ prob, double* __restrict__ rule_w) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rules) return;
+  double w = 1.0;
+  for (uint32_t s = rule_ptr[r]; s < rule_ptr[r + 1]; ++s) {
+    if (kind[s] == Step::UNFOLD) {
+      const int L = len[s];
+      const double p_here = fmax(0.0, table(t, L)[ilong[s]]);
+      const double p_marg = table(t, L - 1)[ishort[s]];
+      const double rel = p_here == 0.0 ? 0.0 : p_here / fmax(p_here, p_marg);
+      w = w * rel;
+      if (!(w > 0.0)) { w = 0.0; break; }  // pruned branch (tm.scm:565)
+    } else {
+      w = fmax(0.0, prob[s]) * w;
+    }
+  }
+  rule_w[r] = w;
+}
+
+__device__ __forceinline__ double relative(double p_long, double p_short) {  // tm.scm:1263-1269
+  if (p_long == 0.0) return 0.0;
+  return p_long / fmax(p_long, p_short);
+}
+
+// One level of the forest: w[node] = w[parent] * relative(...), pruned when the ratio is not > 0
+// (tm.scm:1316, 1350, 1373); SUM nodes add up their parents in ascending id order.
+__global__ void level_kernel(Tables t, Consts c, Level lv, const double* __restrict__ rule_w,
+                             double* __restrict__ w) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < lv.n_plain) {
+    const uint8_t meta = lv.meta[i];
+    const int kind = meta >> 6, len = meta & 63;
+    const uint32_t io = lv.io[i], par = lv.parent[i];
+    double out;
+    if (kind == NODE_ROOT) {
+      out = rule_w[par];
+    } else {
+      const double wp = w[par];
+      double p_long, p_short;
+      if (kind == NODE_LEFT) {
+        p_long = table(t, len)[io];
+        p_short = table(t, len - 1)[io % c.pw[len - 1]];
+      } else {
+        p_long = t.p[io];
+        p_short = table(t, c.k - 1)[io / c.A];
+      }
+      const double r = relative(p_long, p_short);
+      out = r > 0.0 ? wp * r : 0.0;
+    }
+    w[lv.base + i] = out;
+  } else if (i < (uint64_t)lv.n_plain + lv.n_sum) {
+    const uint64_t s = i - lv.n_plain;
+    double total = 0.0;
+    for (uint64_t e = lv.sum_ptr[s]; e < lv.sum_ptr[s + 1]; ++e) total += w[lv.sum_parents[e]];
+    w[lv.base + i] = total;
+  }
+}
+
+// dy/dt[row] = sum over the row's entries of +-w[node]; G lanes per row, shuffle reduction.
+template <int G>
+__global__ void spmv_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ entries,
+                            const double* __restrict__ w, double* __restrict__ out, uint64_t n_rows) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t row = t / G;
+  const int sub = (int)(t % G);
+  double acc = 0.0;
+  if (row < n_rows) {
+    const uint64_t lo = row_ptr[row], hi = row_ptr[row + 1];
+    for (uint64_t e = lo + sub; e < hi; e += G) {
+      const uint32_t v = entries[e];
+      const double x = w[v & ~kOutflowBit];
+      acc += (v & kOutflowBit) ? -x : x;
+    }
+  }
+#pragma unroll
+  for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
+  if (sub == 0 && row < n_rows) out[row] = acc;
+}
+
+double ms_since(std::chrono::steady_clock::time_point t0) {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+struct HostRoot {
+  uint32_t io, ia, seed, rule;
+  uint8_t meta, flags;
+};
+
+}  // namespace
+
+Model::~Model() {
+  cudaStream_t st = stream;
+  if (st) cudaStreamSynchronize(st);
+  auto fr = [&](auto*& p) { if (p) { cudaFree((void*)p); p = nullptr; } };
+  fr(rule_ptr); fr(step_kind); fr(step_len); fr(step_long); fr(step_short); fr(step_prob); fr(rule_w);
+  for (Level& lv : levels) { fr(lv.io); fr(lv.parent); fr(lv.meta); fr(lv.sum_ptr); fr(lv.sum_parents); }
+  fr(node_w); fr(row_ptr); fr(entries); fr(marg); fr(d_marg_off); fr(d_in); fr(d_out);
+  if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) {
+  std::unique_ptr<Model> mp(new Model());
+  Model& m = *mp;
+  m.A = table.alphabet;
+  m.k = table.cl_k;
+  if (m.k < 1 || m.k > 32) throw std::runtime_error("cl_k must be in 1..32");
+  if (m.A < 1 || m.A > 65535) throw std::runtime_error("alphabet size must be in 1..65535");
+  m.pow_a[0] = 1;
+  for (int i = 1; i <= m.k; ++i) m.pow_a[i] = m.pow_a[i - 1] * (uint64_t)m.A;
+  m.n_states = m.pow_a[m.k];
+  if (m.n_states >= (1ull << 32)) throw std::runtime_error("A^cl_k must be below 2^32");
+  if (stream) {
+    m.stream = stream;
+  } else {
+    TAPES_CUDA_CHECK(cudaStreamCreateWithFlags(&m.stream, cudaStreamNonBlocking));
+    m.own_stream = true;
+  }
+  cudaStream_t st = m.stream;
+  {
+    int dev = 0;
+    TAPES_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaMemPool_t pool;
+    TAPES_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
+    uint64_t keep = ~0ull;
+    TAPES_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+
+  Consts c;
+  c.A = (uint32_t)m.A;
+  c.k = m.k;
+  c.M = (uint32_t)m.pow_a[m.k - 1];
+  for (int i = 0; i < 33; ++i) c.pw[i] = i < m.k ? (uint32_t)m.pow_a[i] : 0u;
+  const uint64_t W = m.n_states, M = m.pow_a[m.k - 1];
+
+  m.stats.worlds_walked = table.worlds_walked;
+  m.stats.leaf_worlds = table.leaf_worlds;
+  m.stats.flux_rules = (int64_t)table.rules.size();
+
+  // ---- rule steps to the device ----
+  {
+    std::vector<uint32_t> ptr(1, 0), ilong, ishort;
+    std::vector<uint8_t> kind, len;
+    std::vector<double> prob;
+    for (const FluxRule& r : table.rules) {
+      for (const Step& s : r.steps) {
+        kind.push_back(s.kind); len.push_back(s.length);
+        ilong.push_back(s.long_index); ishort.push_back(s.short_index); prob.push_back(s.prob);
+      }
+      ptr.push_back((uint32_t)kind.size());
+    }
+    m.n_rules = (uint32_t)table.rules.size();
+    auto up = [&](auto*& dptr, const auto& h) {
+      typedef typename std::remove_reference<decltype(h[0])>::type T;
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
+      if (!h.empty())
+        TAPES_CUDA_CHECK(cudaMemcpyAsync((void*)dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    };
+    up(m.rule_ptr, ptr); up(m.step_kind, kind); up(m.step_len, len);
+    up(m.step_long, ilong); up(m.step_short, ishort); up(m.step_prob, prob);
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.rule_w, std::max<size_t>(m.n_rules, 1) * sizeof(double)));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+
+  // ---- roots (finish-fn-eval-fast-fixed, tm.scm:1416-1443; top call 1398-1401) ----
+  std::vector<HostRoot> roots;
+  uint32_t n_seeds = 0;
+  for (size_t r = 0; r < table.rules.size(); ++r) {
+    for (int t = 0; t < 2; ++t) {
+      const Seed& sd = table.rules[r].tape[t];
+      if (!sd.changed()) continue;
+      const uint32_t seed = n_seeds++;
+      uint64_t io = sd.orig, ia = sd.adjusted;
+      int len = sd.length;
+      if (len >= m.k - 1) {  // right chain starts from the right-most k-1 digits
+        const uint64_t po = io % M, pa = ia % M;
+        if (po != pa)
+          roots.push_back({(uint32_t)po, (uint32_t)pa, seed, (uint32_t)r, (uint8_t)((NODE_ROOT << 6) | (m.k - 1)), FL_RIGHT});
+      }
+      bool alive = true;
+      while (len > m.k) {  // tm.scm:1380-1390: accumulate, drop the right-most digit
+        if (io == ia) { alive = false; break; }
+        const uint64_t s = io % W, d = ia % W;
+        if (s != d)
+          roots.push_back({(uint32_t)s, (uint32_t)d, seed, (uint32_t)r, (uint8_t)((NODE_ROOT << 6) | m.k), FL_TERM});
+        io /= (uint64_t)m.A; ia /= (uint64_t)m.A; --len;
+      }
+      if (alive && io != ia) {
+        uint8_t fl = FL_LEFT;
+        if (len == m.k) fl |= FL_TERM;
+        roots.push_back({(uint32_t)io, (uint32_t)ia, seed, (uint32_t)r, (uint8_t)((NODE_ROOT << 6) | len), fl});
+      }
+    }
+  }
+  m.stats.seeds = n_seeds;
+
+  // ---- level-synchronous expansion ----
+  auto t_expand = std::chrono::steady_clock::now();
+  struct EdgeChunk { uint32_t* row; uint32_t* val; uint64_t n; };
+  std::vector<EdgeChunk> edge_chunks;
+
+  Frontier cur;
+  cur.n = roots.size();
+  cur.n_plain = (uint32_t)roots.size();
+  uint32_t* cur_parent = nullptr;
+  if (cur.n) {
+    std::vector<uint32_t> h_io(cur.n), h_ia(cur.n), h_seed(cur.n), h_rule(cur.n);
+    std::vector<uint8_t> h_meta(cur.n), h_fl(cur.n);
+    for (size_t i = 0; i < cur.n; ++i) {
+      h_io[i] = roots[i].io; h_ia[i] = roots[i].ia; h_seed[i] = roots[i].seed; h_rule[i] = roots[i].rule;
+      h_meta[i] = roots[i].meta; h_fl[i] = roots[i].flags;
+    }
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&cur.io, cur.n * 4));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&cur_parent, cur.n * 4));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&cur.meta, cur.n));
+    cur.ia = dalloc<uint32_t>(cur.n, st); cur.seed = dalloc<uint32_t>(cur.n, st); cur.flags = dalloc<uint8_t>(cur.n, st);
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.io, h_io.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.ia, h_ia.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.seed, h_seed.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur_parent, h_rule.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.meta, h_meta.data(), cur.n, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.flags, h_fl.data(), cur.n, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  Level cur_level;
+  cur_level.base = 0;
+  cur_level.n_plain = cur.n_plain;
+  cur_level.n_sum = 0;
+  cur_level.io = cur.io; cur_level.parent = cur_parent; cur_level.meta = cur.meta;
+
+  uint64_t seed_bits = 0;
+  while ((1ull << seed_bits) < std::max<uint64_t>(n_seeds, 1)) ++seed_bits;
+  uint64_t prefix_bits = 0;
+  while ((1ull << prefix_bits) < M) ++prefix_bits;
+  const uint64_t significant = ((prefix_bits ? ((1ull << prefix_bits) - 1) : 0ull)) |
+                               ((seed_bits ? ((1ull << seed_bits) - 1) : 0ull) << 32);
+
+  uint64_t total_terms = 0;
+  while (cur.n > 0) {
+    if (cur_level.base + cur.n >= 0x7fffffffull) throw std::runtime_error("extension forest exceeds 2^31 nodes");
+    m.stats.levels++;
+    const uint64_t n = cur.n;
+    // pass 1
+    uint64_t cap = 1024;
+    while (cap < 2 * n) cap <<= 1;
+    HashSet hs;
+    hs.keys = dalloc<uint64_t>(cap, st);
+    hs.vals = dalloc<uint32_t>(cap, st);
+    hs.mask = cap - 1;
+    TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
+    uint32_t* cflag = dalloc<uint32_t>(n, st);
+    uint32_t* tflag = dalloc<uint32_t>(n, st);
+    uint8_t* kflag = dalloc<uint8_t>(n, st);
+    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, cflag, tflag, kflag);
+    uint64_t* crank = dalloc<uint64_t>(n + 1, st);
+    uint64_t* trank = dalloc<uint64_t>(n + 1, st);
+    uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(std::max<uint64_t>(cap, 256ull * 1184)), st);
+    exclusive_scan_u32(cflag, n, crank, scan_tmp, st);
+    exclusive_scan_u32(tflag, n, trank, scan_tmp, st);
+    uint32_t* sflag = dalloc<uint32_t>(cap, st);
+    uint64_t* srank = dalloc<uint64_t>(cap + 1, st);
+    slot_flag_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, sflag);
+    exclusive_scan_u32(sflag, cap, srank, scan_tmp, st);
+    uint64_t h_tot[3];
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], crank + n, 8, cudaMemcpyDeviceToHost, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], trank + n, 8, cudaMemcpyDeviceToHost, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], srank + cap, 8, cudaMemcpyDeviceToHost, st));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+    const uint64_t NC = h_tot[0], NT = h_tot[1], NS = h_tot[2];
+    if (NS >= 0xffffffffull || NC * (uint64_t)m.A >= 0xffffffffull) throw std::runtime_error("level too large");
+
+    // unique right-chain prefixes in canonical (seed, prefix) order
+    uint64_t* keys_a = dalloc<uint64_t>(NS, st);
+    uint64_t* keys_b = dalloc<uint64_t>(NS, st);
+    uint64_t* sorted = keys_a;
+    if (NS) {
+      slot_gather_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, srank, keys_a);
+      const RadixPlan plan = radix_plan(NS);
+      uint32_t* rh = dalloc<uint32_t>(256ull * plan.blocks, st);
+      uint64_t* ro = dalloc<uint64_t>(256ull * plan.blocks + 1, st);
+      sorted = radix_sort_u64(keys_a, keys_b, NS, significant, rh, ro, scan_tmp, st);
+      dfree(rh, st); dfree(ro, st);
+    }
+    dfree(sflag, st); dfree(srank, st);
+
+    // pass 2
+    Frontier next;
+    next.n_plain = (uint32_t)(NC * (uint64_t)m.A);
+    next.n = (uint64_t)next.n_plain + NS;
+    uint32_t* next_parent = nullptr;
+    if (next.n) {
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&next.io, next.n * 4));
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&next.meta, next.n));
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&next_parent, std::max<uint64_t>(next.n_plain, 1) * 4));
+      next.ia = dalloc<uint32_t>(next.n, st);
+      next.seed = dalloc<uint32_t>(next.n, st);
+      next.flags = dalloc<uint8_t>(next.n, st);
+    }
+    EdgeChunk ec{nullptr, nullptr, 2 * NT};
+    if (NT) { ec.row = dalloc<uint32_t>(2 * NT, st); ec.val = dalloc<uint32_t>(2 * NT, st); }
+    uint32_t* keyrank = dalloc<uint32_t>(n, st);
+    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, cflag, tflag, kflag, crank,
+                                                          trank, NC, sorted, (uint32_t)NS, next, next_parent,
+                                                          ec.row, ec.val, keyrank);
+    Level next_level;
+    next_level.base = cur_level.base + n;
+    next_level.n_plain = next.n_plain;
+    next_level.n_sum = (uint32_t)NS;
+    next_level.io = next.io; next_level.parent = next_parent; next_level.meta = next.meta;
+    if (NS) {
+      sum_nodes_kernel<<<grid_for(NS, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NS, hs, c, next, next.n_plain);
+      // parent lists of the SUM nodes
+      uint32_t* cnt = dalloc<uint32_t>(NS, st);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NS * 4, st));
+      group_count_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cnt);
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&next_level.sum_ptr, (NS + 1) * 8));
+      exclusive_scan_u32(cnt, NS, next_level.sum_ptr, scan_tmp, st);
+      uint64_t n_par = 0;
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&n_par, next_level.sum_ptr + NS, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      next_level.n_sum_parents = n_par;
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&next_level.sum_parents, std::max<uint64_t>(n_par, 1) * 4));
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NS * 4, st));
+      group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base,
+                                                                       next_level.sum_ptr, cnt, next_level.sum_parents);
+      group_sort_kernel<<<grid_for(NS, kThreads), kThreads, 0, st>>>(next_level.sum_ptr, NS, next_level.sum_parents);
+      dfree(cnt, st);
+      m.stats.hash_inserts += (int64_t)n_par;
+      m.stats.hash_unique += (int64_t)NS;
+    }
+    TAPES_CUDA_CHECK(cudaGetLastError());
+    if (NT) edge_chunks.push_back(ec);
+    total_terms += NT;
+    m.stats.sum_nodes += (int64_t)cur_level.n_sum;
+
+    // retire the current frontier; its io/parent/meta live on in the level store
+    m.levels.push_back(cur_level);
+    dfree(cur.ia, st); dfree(cur.seed, st); dfree(cur.flags, st);
+    dfree(cflag, st); dfree(tflag, st); dfree(kflag, st); dfree(crank, st); dfree(trank, st);
+    dfree(scan_tmp, st); dfree(keys_a, st); dfree(keys_b, st); dfree(keyrank, st);
+    dfree(hs.keys, st); dfree(hs.vals, st);
+    cur = next;
+    cur_level = next_level;
+  }
+  m.n_nodes = cur_level.base;  // base of the (empty) level after the last
+  m.stats.nodes = (int64_t)m.n_nodes;
+  m.stats.terms = (int64_t)total_terms;
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  m.stats.device_expand_ms = ms_since(t_expand);
+
+  // ---- CSR assembly: count per state, scan, fill, sort inside each row ----
+  auto t_csr = std::chrono::steady_clock::now();
+  const uint64_t n = m.n_states;
+  m.nnz = 2 * total_terms;
+  {
+    uint32_t* cnt = dalloc<uint32_t>(n, st);
+    TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
+    for (const EdgeChunk& ec : edge_chunks)
+      group_count_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.n, cnt);
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.row_ptr, (n + 1) * 8));
+    uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(n), st);
+    exclusive_scan_u32(cnt, n, m.row_ptr, scan_tmp, st);
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.entries, std::max<uint64_t>(m.nnz, 1) * 4));
+    TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
+    for (EdgeChunk& ec : edge_chunks) {
+      group_fill_vals_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.val, ec.n, m.row_ptr, cnt, m.entries);
+      dfree(ec.row, st); dfree(ec.val, st);
+    }
+    group_sort_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(m.row_ptr, n, m.entries);
+    dfree(cnt, st); dfree(scan_tmp, st);
+    TAPES_CUDA_CHECK(cudaGetLastError());
+  }
+  const double per_row = n ? (double)m.nnz / (double)n : 0.0;
+  m.spmv_group = per_row > 24 ? 16 : (per_row > 10 ? 8 : (per_row > 4 ? 4 : 2));
+
+  // ---- per-step buffers ----
+  m.marg_total = 0;
+  for (int L = 0; L < m.k; ++L) { m.marg_off[L] = m.marg_total; m.marg_total += m.pow_a[L]; }
+  m.marg_off[m.k] = m.marg_total;
+  TAPES_CUDA_CHECK(cudaMalloc((void**)&m.marg, std::max<uint64_t>(m.marg_total, 1) * 8));
+  TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_marg_off, 40 * 8));
+  for (int L = m.k + 1; L < 40; ++L) m.marg_off[L] = 0;
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_marg_off, m.marg_off, 40 * 8, cudaMemcpyHostToDevice, st));
+  TAPES_CUDA_CHECK(cudaMalloc((void**)&m.node_w, std::max<uint64_t>(m.n_nodes, 1) * 8));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  m.stats.device_csr_ms = ms_since(t_csr);
+  m.launches_per_rhs = rhs_launch_count(m);
+  return mp;
+}
+
+namespace {
+// Tables with at most this many entries are produced by the single-block tail kernel.
+constexpr uint64_t kTailEntries = 4096;
+int marginal_tail_top(const Model& m) {
+  int top = -1;
+  for (int L = 0; L < m.k; ++L)
+    if (m.pow_a[L] <= kTailEntries) top = L;
+  return top;
+}
+}  // namespace
+
+int64_t rhs_launch_count(const Model& m) {
+  int64_t launches = 0;
+  const int top = marginal_tail_top(m);
+  launches += (m.k - 1 - top);          // one kernel per long marginal table
+  if (top >= 0) launches += 1;          // tail tables
+  launches += 1;                        // leaf-world probabilities
+  launches += (int64_t)m.levels.size(); // forest levels
+  launches += 1;                        // S * w
+  return launches;
+}
+
+static void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
+  Consts c;
+  c.A = (uint32_t)m.A; c.k = m.k; c.M = (uint32_t)m.pow_a[m.k - 1];
+  for (int i = 0; i < 33; ++i) c.pw[i] = i < m.k ? (uint32_t)m.pow_a[i] : 0u;
+  Tables t;
+  t.p = d_p; t.marg = m.marg; t.k = m.k;
+  for (int i = 0; i < 34; ++i) t.off[i] = i <= m.k ? m.marg_off[i] : 0;
+
+  // marginal tables, longest first
+  const int top = marginal_tail_top(m);
+  for (int L = m.k - 1; L > top; --L) {
+    const double* src = (L + 1 == m.k) ? d_p : m.marg + m.marg_off[L + 1];
+    marginal_kernel<<<grid_for(m.pow_a[L], kThreads), kThreads, 0, st>>>(src, m.marg + m.marg_off[L], m.pow_a[L], c.A);
+  }
+  if (top >= 0)
+    marginal_tail_kernel<<<1, 1024, 0, st>>>(d_p, m.marg, m.d_marg_off, m.k, top, c.A);
+  if (m.n_rules)
+    rule_weight_kernel<<<grid_for(m.n_rules, 128), 128, 0, st>>>(t, m.n_rules, m.rule_ptr, m.step_kind, m.step_len,
+                                                                m.step_long, m.step_short, m.step_prob, m.rule_w);
+  if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
+  for (const Level& lv : m.levels) {
+    const uint64_t cnt = (uint64_t)lv.n_plain + lv.n_sum;
+    if (cnt) level_kernel<<<grid_for(cnt, kThreads), kThreads, 0, st>>>(t, c, lv, m.rule_w, m.node_w);
+  }
+  if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
+  const uint64_t threads = m.n_states * (uint64_t)m.spmv_group;
+  switch (m.spmv_group) {
+    case 2: spmv_kernel<2><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
+    case 4: spmv_kernel<4><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
+    case 8: spmv_kernel<8><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
+    default: spmv_kernel<16><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
+  }
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
+  rhs_launch(m, d_p, d_out, stream ? stream : m.stream, nullptr);
+}
+
+void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_t stream, float ms[3]) {
+  cudaStream_t st = stream ? stream : m.stream;
+  cudaEvent_t ev[4];
+  for (int i = 0; i < 4; ++i) TAPES_CUDA_CHECK(cudaEventCreate(&ev[i]));
+  TAPES_CUDA_CHECK(cudaEventRecord(ev[0], st));
+  rhs_launch(m, d_p, d_out, st, ev);
+  TAPES_CUDA_CHECK(cudaEventRecord(ev[3], st));
+  TAPES_CUDA_CHECK(cudaEventSynchronize(ev[3]));
+  for (int i = 0; i < 3; ++i) TAPES_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+}
+
+void rhs_host(Model& m, const double* h_p, double* h_out) {
+  const size_t bytes = (size_t)m.n_states * 8;
+  if (!m.d_in) {
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_in, bytes));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_out, bytes));
+  }
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
+  rhs_device(m, m.d_in, m.d_out, m.stream);
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+}
+
+}  // namespace tapes

@@ -1,0 +1,274 @@
+// Device-wide building blocks used by the structure build (sm_100a): exclusive scan, stable LSD
+// radix sort of 64-bit keys, and an open-addressing hash set with warp-aggregated inserts.
+// All launches go to the caller's stream; nothing here synchronises the host.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+
+namespace tapes {
+
+#define TAPES_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                          \
+    cudaError_t err__ = (expr);                                                                 \
+    if (err__ != cudaSuccess)                                                                   \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(err__) + " at " \
+                               + __FILE__ + ":" + std::to_string(__LINE__));                    \
+  } while (0)
+
+inline unsigned grid_for(uint64_t items, unsigned block) {
+  uint64_t g = (items + block - 1) / block;
+  if (g == 0) g = 1;
+  if (g > 0x7fffffffull) throw std::runtime_error("grid too large");
+  return (unsigned)g;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exclusive scan: u32 counts -> u64 offsets.  Three kernels: tile sums, scan of the tile sums by
+// one block, tile-local scan plus tile offset.  The grand total lands in out[n].
+// ------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint64_t warp_inclusive_sum(uint64_t v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint64_t o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+
+// Block-wide exclusive prefix of one value per thread; returns the prefix and the block total.
+__device__ __forceinline__ uint64_t block_exclusive_sum(uint64_t v, uint64_t* warp_totals /*32*/,
+                                                        uint64_t* block_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  uint64_t inc = warp_inclusive_sum(v, lane);
+  if (lane == 31) warp_totals[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t t = lane < nwarps ? warp_totals[lane] : 0;
+    uint64_t ti = warp_inclusive_sum(t, lane);
+    warp_totals[lane] = ti - t;  // exclusive
+    if (lane == 31) *block_total = ti;
+  }
+  __syncthreads();
+  uint64_t res = inc - v + warp_totals[warp];
+  __syncthreads();
+  return res;
+}
+
+__global__ void scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                      uint64_t* __restrict__ tile_sums) {
+  __shared__ uint64_t wt[32];
+  __shared__ uint64_t total;
+  const uint64_t tile0 = (uint64_t)blockIdx.x * kScanTile;
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    uint64_t i = tile0 + (uint64_t)j * kScanThreads + threadIdx.x;
+    if (i < n) s += in[i];
+  }
+  (void)block_exclusive_sum(s, wt, &total);
+  if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+__global__ void scan_tile_offsets_kernel(uint64_t* __restrict__ tile_sums, uint64_t ntiles,
+                                         uint64_t* __restrict__ grand_total) {
+  __shared__ uint64_t wt[32];
+  __shared__ uint64_t total;
+  uint64_t carry = 0;
+  for (uint64_t base = 0; base < ntiles; base += blockDim.x) {
+    uint64_t i = base + threadIdx.x;
+    uint64_t v = i < ntiles ? tile_sums[i] : 0;
+    uint64_t ex = block_exclusive_sum(v, wt, &total);
+    if (i < ntiles) tile_sums[i] = carry + ex;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                  const uint64_t* __restrict__ tile_offsets,
+                                  uint64_t* __restrict__ out) {
+  __shared__ uint64_t wt[32];
+  __shared__ uint64_t total;
+  const uint64_t tile0 = (uint64_t)blockIdx.x * kScanTile;
+  // thread owns kScanItems consecutive items so that the per-thread prefix is sequential
+  const uint64_t first = tile0 + (uint64_t)threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  uint64_t s = 0;
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    uint64_t i = first + j;
+    v[j] = i < n ? in[i] : 0;
+    s += v[j];
+  }
+  uint64_t ex = block_exclusive_sum(s, wt, &total) + tile_offsets[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    uint64_t i = first + j;
+    if (i < n) out[i] = ex;
+    ex += v[j];
+  }
+}
+
+// `tmp` must hold ceil(n / kScanTile) + 1 u64; out must hold n + 1 u64 (out[n] = total).
+inline size_t scan_tmp_elems(uint64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile + 1); }
+
+inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* tmp,
+                               cudaStream_t st) {
+  if (n == 0) {
+    TAPES_CUDA_CHECK(cudaMemsetAsync(out, 0, sizeof(uint64_t), st));
+    return;
+  }
+  const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
+  scan_tile_sums_kernel<<<(unsigned)ntiles, kScanThreads, 0, st>>>(in, n, tmp);
+  scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(tmp, ntiles, out + n);
+  scan_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, st>>>(in, n, tmp, out);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------
+// Open-addressing hash set of 64-bit keys with a 32-bit value written by the first inserter.
+// Lanes of a warp that carry the same key elect one inserter (warp-aggregated insert).
+// ------------------------------------------------------------------------------------------
+constexpr uint64_t kEmptyKey = ~0ull;
+
+struct HashSet {
+  uint64_t* keys = nullptr;
+  uint32_t* vals = nullptr;
+  uint64_t mask = 0;  // capacity - 1 (capacity is a power of two)
+};
+
+__device__ __forceinline__ uint64_t hash_mix(uint64_t x) {
+  x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+  x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+  x ^= x >> 33;
+  return x;
+}
+
+// All 32 lanes must call this; `active` says whether the lane has a key.
+__device__ __forceinline__ void hash_insert_warp(const HashSet& hs, bool active, uint64_t key,
+                                                 uint32_t val) {
+  const unsigned lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, active ? key : (kEmptyKey - lane));
+  const bool leader = active && ((__ffs(peers) - 1) == (int)lane);
+  if (leader) {
+    uint64_t h = hash_mix(key) & hs.mask;
+    for (;;) {
+      unsigned long long prev =
+          atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey,
+                    (unsigned long long)key);
+      if (prev == kEmptyKey) { hs.vals[h] = val; break; }
+      if (prev == key) break;
+      h = (h + 1) & hs.mask;
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t hash_lookup(const HashSet& hs, uint64_t key) {
+  uint64_t h = hash_mix(key) & hs.mask;
+  for (;;) {
+    uint64_t k = hs.keys[h];
+    if (k == key) return hs.vals[h];
+    if (k == kEmptyKey) return 0xffffffffu;
+    h = (h + 1) & hs.mask;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stable LSD radix sort of u64 keys, 8 bits per pass, only over the byte positions the caller
+// marks as significant.  Each block owns one contiguous chunk and ranks it tile by tile.
+// ------------------------------------------------------------------------------------------
+constexpr int kSortThreads = 256;
+
+__global__ void radix_hist_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint64_t chunk,
+                                  int shift, uint32_t* __restrict__ hist /*[256][gridDim.x]*/) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint64_t lo = (uint64_t)blockIdx.x * chunk;
+  uint64_t hi = lo + chunk;
+  if (hi > n) hi = n;
+  for (uint64_t i = lo + threadIdx.x; i < hi; i += kSortThreads)
+    atomicAdd(&h[(keys[i] >> shift) & 255], 1u);
+  __syncthreads();
+  hist[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void radix_scatter_kernel(const uint64_t* __restrict__ keys, uint64_t* __restrict__ out,
+                                     uint64_t n, uint64_t chunk, int shift,
+                                     const uint64_t* __restrict__ offsets /*[256][gridDim.x]*/) {
+  __shared__ uint64_t off[256];
+  off[threadIdx.x] = offsets[(uint64_t)threadIdx.x * gridDim.x + blockIdx.x];
+  __syncthreads();
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t lo = (uint64_t)blockIdx.x * chunk;
+  uint64_t hi = lo + chunk;
+  if (hi > n) hi = n;
+  for (uint64_t t0 = lo; t0 < hi; t0 += kSortThreads) {
+    const uint64_t i = t0 + threadIdx.x;
+    const bool active = i < hi;
+    const uint64_t key = active ? keys[i] : 0;
+    const unsigned d = active ? (unsigned)((key >> shift) & 255) : (256u + lane);
+    const unsigned peers = __match_any_sync(0xffffffffu, d);
+    const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+    const int leader = __ffs(peers) - 1;
+    uint64_t base = 0;
+    // warps take turns so that earlier items get smaller positions (stability)
+    for (int w = 0; w < kSortThreads / 32; ++w) {
+      if ((int)warp == w && active && (int)lane == leader) {
+        base = off[d];
+        off[d] = base + __popc(peers);
+      }
+      __syncthreads();
+    }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (active) out[base + rank] = key;
+  }
+}
+
+// tmp_hist: 256 * blocks u32; tmp_off: 256 * blocks + 1 u64; scan_tmp per scan_tmp_elems.
+struct RadixPlan {
+  unsigned blocks = 0;
+  uint64_t chunk = 0;
+};
+inline RadixPlan radix_plan(uint64_t n) {
+  RadixPlan p;
+  uint64_t blocks = (n + 4095) / 4096;
+  if (blocks > 1184) blocks = 1184;  // 8 x 148 SMs
+  if (blocks == 0) blocks = 1;
+  p.blocks = (unsigned)blocks;
+  p.chunk = (n + blocks - 1) / blocks;
+  return p;
+}
+
+// Sorts `keys` (n items) using `alt` as ping-pong space; returns the buffer holding the result.
+inline uint64_t* radix_sort_u64(uint64_t* keys, uint64_t* alt, uint64_t n, uint64_t significant_bits,
+                                uint32_t* tmp_hist, uint64_t* tmp_off, uint64_t* scan_tmp,
+                                cudaStream_t st) {
+  if (n <= 1) return keys;
+  const RadixPlan plan = radix_plan(n);
+  uint64_t* src = keys;
+  uint64_t* dst = alt;
+  for (int byte = 0; byte < 8; ++byte) {
+    if (((significant_bits >> (8 * byte)) & 0xff) == 0) continue;
+    const int shift = 8 * byte;
+    radix_hist_kernel<<<plan.blocks, kSortThreads, 0, st>>>(src, n, plan.chunk, shift, tmp_hist);
+    exclusive_scan_u32(tmp_hist, 256ull * plan.blocks, tmp_off, scan_tmp, st);
+    radix_scatter_kernel<<<plan.blocks, kSortThreads, 0, st>>>(src, dst, n, plan.chunk, shift,
+                                                              tmp_off);
+    uint64_t* t = src; src = dst; dst = t;
+  }
+  TAPES_CUDA_CHECK(cudaGetLastError());
+  return src;
+}
+
+}  // namespace tapes

@@ -1,0 +1,190 @@
+// Host-side rule front end (see rules.h).
+#include "rules.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <stdexcept>
+
+namespace tapes {
+
+namespace {
+
+const int kMaxSide = 40;  // cells a view may extend to either side of cell 0
+
+// A contiguous symbolic view [-left, right-1] holding both the original and the adjusted symbol
+// of every uncovered cell (tm.scm:41-55 t-view, tm.scm:207-216 tv-pair).
+struct Window {
+  int left = 0, right = 0;
+  uint16_t orig[2 * kMaxSide];
+  uint16_t adj[2 * kMaxSide];
+  bool covers(int cell) const { return cell >= -left && cell < right; }
+  int width() const { return left + right; }
+  uint64_t digits(const uint16_t* a, int first, int count, int A) const {
+    uint64_t v = 0;
+    for (int i = 0; i < count; ++i) v = v * (uint64_t)A + a[kMaxSide + first + i];
+    return v;
+  }
+};
+
+struct Fork { int ways; };  // thrown when the decision list is exhausted at a split point
+
+// Runs a body against a fixed list of split decisions, recording the probability steps.
+class Replayer : public Machine {
+ public:
+  Replayer(int A, int k, const std::vector<int>& decisions) : A_(A), k_(k), decisions_(decisions) {}
+
+  int read(Tape t, int cell) override {
+    Window& w = win_[t];
+    while (!w.covers(cell)) {
+      if (cell >= kMaxSide || cell < -kMaxSide) throw std::runtime_error("tape view too long");
+      int s = next_decision(A_);
+      // One-cell unfolding toward `cell` (tm.scm:482-588): L = min(k, visible + 1), the context
+      // is the L-1 cells adjacent to the new cell, always taken from the ORIGINAL view (490).
+      const bool to_right = cell >= 0;
+      const int L = std::min(k_, w.width() + 1);
+      uint64_t context = to_right ? w.digits(w.orig, w.right - (L - 1), L - 1, A_)
+                                  : w.digits(w.orig, -w.left, L - 1, A_);
+      uint64_t pow_lm1 = 1;
+      for (int i = 0; i < L - 1; ++i) pow_lm1 *= (uint64_t)A_;
+      uint64_t extended = to_right ? context * (uint64_t)A_ + (uint64_t)s
+                                   : (uint64_t)s * pow_lm1 + context;
+      Step st;
+      st.kind = Step::UNFOLD;
+      st.length = (uint8_t)L;
+      st.long_index = (uint32_t)extended;
+      st.short_index = (uint32_t)context;
+      st.prob = 0.0;
+      steps_.push_back(st);
+      int pos = to_right ? w.right++ : -(++w.left);
+      w.orig[kMaxSide + pos] = (uint16_t)s;
+      w.adj[kMaxSide + pos] = (uint16_t)s;
+    }
+    return w.adj[kMaxSide + cell];  // programs observe their own writes (tm.scm:759)
+  }
+
+  void write(Tape t, int cell, int symbol) override {
+    (void)read(t, cell);  // a write first forces the cell to be unfolded (tm.scm:787-792)
+    win_[t].adj[kMaxSide + cell] = (uint16_t)symbol;
+  }
+
+  int pick(const double* weights, int n) override {
+    double total = 0.0;
+    for (int i = 0; i < n; ++i) total = total + weights[i];
+    int j = next_decision(n);
+    Step st;
+    st.kind = Step::CHOICE;
+    st.length = 0;
+    st.long_index = st.short_index = 0;
+    st.prob = weights[j] / total;
+    steps_.push_back(st);
+    return j;
+  }
+
+  const std::vector<Step>& steps() const { return steps_; }
+  const Window& window(int t) const { return win_[t]; }
+
+ private:
+  int next_decision(int ways) {
+    if (pos_ >= decisions_.size()) throw Fork{ways};
+    return decisions_[pos_++];
+  }
+  int A_, k_;
+  const std::vector<int>& decisions_;
+  size_t pos_ = 0;
+  Window win_[2];
+  std::vector<Step> steps_;
+};
+
+std::map<std::string, Problem>& registry() {
+  static std::map<std::string, Problem> r;
+  return r;
+}
+
+}  // namespace
+
+RuleTable enumerate_rules(const Problem& problem, int cl_k) {
+  RuleTable table;
+  table.alphabet = problem.alphabet;
+  table.cl_k = cl_k;
+  double states = 1;
+  for (int i = 0; i < cl_k; ++i) states *= problem.alphabet;
+  if (cl_k < 1 || states >= 4294967296.0)
+    throw std::runtime_error("A^cl_k must be below 2^32");
+
+  std::vector<std::vector<int>> todo;
+  todo.push_back({});
+  while (!todo.empty()) {
+    std::vector<int> decisions = std::move(todo.back());
+    todo.pop_back();
+    table.worlds_walked++;
+    Replayer m(problem.alphabet, cl_k, decisions);
+    try {
+      problem.body(m);
+    } catch (const Fork& f) {
+      for (int c = f.ways - 1; c >= 0; --c) {  // pushed high-to-low so that option 0 is walked first
+        std::vector<int> d = decisions;
+        d.push_back(c);
+        todo.push_back(std::move(d));
+      }
+      continue;
+    }
+    table.leaf_worlds++;
+    FluxRule rule;
+    bool any = false;
+    for (int t = 0; t < 2; ++t) {
+      const Window& w = m.window(t);
+      Seed& sd = rule.tape[t];
+      sd.length = w.width();
+      double bits = 0;
+      for (int i = 0; i < sd.length; ++i) bits += std::log2((double)problem.alphabet);
+      if (bits > 63.0) throw std::runtime_error("tape view index exceeds 64 bits");
+      sd.orig = w.digits(w.orig, -w.left, sd.length, problem.alphabet);
+      sd.adjusted = w.digits(w.adj, -w.left, sd.length, problem.alphabet);
+      any = any || sd.changed();
+    }
+    if (!any) continue;
+    rule.steps = m.steps();
+    table.rules.push_back(std::move(rule));
+  }
+  return table;
+}
+
+const Problem* find_problem(const std::string& tag) {
+  auto it = registry().find(tag);
+  return it == registry().end() ? nullptr : &it->second;
+}
+
+void register_problem(const std::string& tag, int alphabet, Body body) {
+  Problem p;
+  p.alphabet = alphabet;
+  p.body = std::move(body);
+  registry()[tag] = std::move(p);
+}
+
+std::vector<std::string> registered_tags() {
+  std::vector<std::string> tags;
+  for (auto& kv : registry()) tags.push_back(kv.first);
+  return tags;
+}
+
+Body body_from_rewrite_rules(std::vector<RewriteRule> rules) {
+  for (const RewriteRule& r : rules)
+    if (r.span < 1 || r.span > 4) throw std::runtime_error("rewrite rule span must be 1..4");
+  return [rules](Machine& m) {
+    std::vector<double> weights(rules.size());
+    for (size_t i = 0; i < rules.size(); ++i) weights[i] = rules[i].select_weight;
+    const RewriteRule& r = rules[(size_t)m.pick(weights.data(), (int)weights.size())];
+    const Tape own = r.tape ? DATA_TAPE : PROGRAM_TAPE;
+    const Tape other = r.tape ? PROGRAM_TAPE : DATA_TAPE;
+    if (r.catalyst >= 0 && m.read(other, 0) != r.catalyst) return;
+    for (int c = 0; c < r.span; ++c)
+      if (m.read(own, c) != r.pattern[c]) return;
+    const double accept[2] = {r.rate, 1 - r.rate};
+    if (m.pick(accept, 2) != 0) return;
+    for (int c = 0; c < r.span; ++c)
+      if (r.replacement[c] != r.pattern[c]) m.write(own, c, r.replacement[c]);
+  };
+}
+
+}  // namespace tapes

@@ -1,0 +1,72 @@
+"""Device-resident use of the library: torch tensors for memory and streams, the C ABI for the
+work.  Importing this module imports `markov_tapes` (runtime initialisation + known-answer test).
+"""
+
+import ctypes
+
+import numpy
+import torch
+
+from . import _lib
+from . import markov_tapes
+
+
+class DeviceModel:
+  """The structure of (tag, cl_k) on the current CUDA device."""
+
+  def __init__(self, tag, cl_k):
+    self.tag, self.cl_k = tag, cl_k
+    self.handle = markov_tapes.u_lib.tapes_model(tag.encode(), cl_k)
+    _lib.check(bool(self.handle), 'tapes_model')
+    self.info = _lib.model_info(self.handle)
+    self.timing = _lib.model_timing(self.handle)
+    self.n_states = self.info['n_states']
+
+  def rhs(self, p, out=None):
+    """dy/dt of a float64 CUDA tensor, asynchronously on torch's current stream."""
+    assert p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.numel() == self.n_states
+    if out is None:
+      out = torch.empty_like(p)
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = markov_tapes.u_lib.tapes_rhs_device(self.handle, p.data_ptr(), out.data_ptr(), stream)
+    _lib.check(rc == 0, 'tapes_rhs_device')
+    return out
+
+  def rhs_profile(self, p, out):
+    """One right-hand side with CUDA events between its phases; returns ms per phase
+    (marginals + leaf-world probabilities, forest levels, S*w) measured on the launch stream."""
+    stream = torch.cuda.current_stream().cuda_stream
+    ms = numpy.zeros(3, dtype=numpy.float64)
+    rc = markov_tapes.u_lib.tapes_rhs_profile(self.handle, p.data_ptr(), out.data_ptr(), stream,
+                                              ms.ctypes.data, 3)
+    _lib.check(rc == 0, 'tapes_rhs_profile')
+    return ms
+
+  def csr(self):
+    """(row_ptr[int64], entries[uint32]) copied to host."""
+    row_ptr = numpy.zeros(self.n_states + 1, dtype=numpy.int64)
+    entries = numpy.zeros(max(self.info['nnz'], 1), dtype=numpy.uint32)
+    rc = markov_tapes.u_lib.tapes_export_csr(self.handle, row_ptr.ctypes.data, entries.ctypes.data)
+    _lib.check(rc == 0, 'tapes_export_csr')
+    return row_ptr, entries[:self.info['nnz']]
+
+  def node_weights(self):
+    w = numpy.zeros(max(self.info['n_nodes'], 1), dtype=numpy.float64)
+    rc = markov_tapes.u_lib.tapes_export_node_weights(self.handle, w.ctypes.data)
+    _lib.check(rc == 0, 'tapes_export_node_weights')
+    return w[:self.info['n_nodes']]
+
+  def terms(self):
+    """Flux terms of the most recent right-hand side as (src, dst, w) arrays in node order."""
+    row_ptr, entries = self.csr()
+    w = self.node_weights()
+    rows = numpy.repeat(numpy.arange(self.n_states, dtype=numpy.int64), numpy.diff(row_ptr))
+    node = (entries & 0x7fffffff).astype(numpy.int64)
+    outflow = (entries >> 31).astype(bool)
+    src = numpy.full(len(w), -1, dtype=numpy.int64)
+    dst = numpy.full(len(w), -1, dtype=numpy.int64)
+    src[node[outflow]] = rows[outflow]
+    dst[node[~outflow]] = rows[~outflow]
+    has = src >= 0
+    assert (has == (dst >= 0)).all()
+    return src[has], dst[has], w[has]

@@ -1,0 +1,226 @@
+"""Drop-in replacement for the reference's framework/markov_tapes.py, backed by CUDA on a B200.
+
+Same public names, keyword-only signatures, return shapes and error behaviour as the reference
+module (framework/markov_tapes.py:58-374); the Gambit-C shared object behind it is replaced by
+`tapes_py_interface.so` built from csrc/ (C ABI: include/tapes_b200.h).  Like the reference,
+importing this module initialises the runtime, registers the problems and runs the load-time
+known-answer test (framework/markov_tapes.py:357-374), so it needs a GPU and raises otherwise.
+
+Differences, all documented in INTEGRATION.md:
+  * the per-call `print('DDD t=...')` (framework/markov_tapes.py:277) only happens when
+    MARKOV_TAPES_DEBUG=1;
+  * a failed library call raises RuntimeError (the reference drops into a Scheme REPL,
+    framework/tapes_py_interface.scm:42-44);
+  * additions: `get_device_dy_dt`, `ode_integrate_device`, `model_stats`, `register_rule_set`.
+"""
+
+import atexit
+import itertools
+import os
+import sys
+import types
+
+import numpy
+import scipy.integrate
+
+from . import _lib
+
+IS_DEBUG = bool(int(os.getenv('MARKOV_TAPES_DEBUG', '0')))
+
+u_lib = _lib.load()
+
+
+def init_gambit():
+  """Initialises the device runtime (name kept from the reference, markov_tapes.py:58-76)."""
+  if IS_DEBUG:
+    print('DEBUG: initializing runtime.', file=sys.stderr, flush=True)
+  runtime = u_lib.setup_gambit()
+  if not runtime:
+    _lib.check(False, 'setup_gambit')
+
+  def _cleanup_gambit():
+    if IS_DEBUG:
+      print('DEBUG: cleanup runtime.', file=sys.stderr, flush=True)
+    u_lib.cleanup_gambit(runtime)
+  atexit.register(_cleanup_gambit)
+  if IS_DEBUG:
+    print('DEBUG: registering problems.', file=sys.stderr, flush=True)
+  if 124 != u_lib.c_register_problems(123):
+    # canary: the call returns its argument plus one (markov_tapes.py:72-76)
+    raise ValueError('Registering problems failed.')
+
+
+### Helpers (host-side analysis; same semantics as markov_tapes.py:81-256)
+
+def mpp_from_spd(spd, eps=None):
+  """Markov process parameters r[prefix + (s,)] = P(s | prefix) from a subsequence table.
+
+  spd has shape B + (N,)*k.  Entries are clipped to [eps, 1] first so that an impossible prefix
+  yields a uniform continuation instead of 0/0 (default eps 1e-100).
+  """
+  if eps is None:
+    eps = 1e-100
+  clipped = numpy.clip(numpy.asarray(spd).astype(numpy.float64), eps, 1)
+  return clipped / clipped.sum(axis=-1, keepdims=True)
+
+
+def ctm_from_mpp(num_alphabet, num_context, mpp):
+  """Context transfer matrix [N**c, N**c]: entry [suffix context, prefix context]."""
+  n_ctx = num_alphabet ** num_context
+  steps = numpy.asarray(mpp).reshape([num_alphabet] * (1 + num_context))
+  # column = context (i_0..i_{c-1}), row = shifted context (i_1..i_c)
+  cols = numpy.arange(n_ctx * num_alphabet) // num_alphabet
+  rows = numpy.arange(n_ctx * num_alphabet) % n_ctx
+  result = numpy.zeros([n_ctx, n_ctx])
+  numpy.add.at(result, (rows, cols), steps.ravel())
+  return result
+
+
+def get_ctm_eigenvalue1_eigenspace(spd, eps_mpp=None, eps=1e-7):
+  """Eigenvalue-1 eigenspace of the context transfer matrix (markov_tapes.py:133-175).
+
+  Returns (deviation, eigenspace) or (marginals_distance, None) when the marginals over the
+  leading and the trailing index differ by more than eps.
+  """
+  spd = numpy.asarray(spd, dtype=numpy.float64)
+  num_alphabet = spd.shape[0]
+  num_context = spd.ndim - 1
+  right = spd.sum(axis=-1)
+  left = spd.sum(axis=0)
+  distance = numpy.linalg.norm(right.ravel() - left.ravel())
+  if not distance <= eps:
+    return distance, None
+  ctm = ctm_from_mpp(num_alphabet, num_context, mpp_from_spd(spd, eps=eps_mpp))
+  eigvals, eigvecs = numpy.linalg.eig(ctm)
+  eigenspace = eigvecs[:, abs(eigvals - 1.0) <= eps]
+  _, residuals, *_ = numpy.linalg.lstsq(eigenspace, left.ravel(), rcond=None)
+  return numpy.linalg.norm(residuals**.5), eigenspace
+
+
+def markov_entropy(spd):
+  """Entropy rate of the Markov chain described by the subsequence table."""
+  clipped = numpy.clip(numpy.asarray(spd).astype(numpy.float64), 1e-280, 1)
+  context = clipped.sum(axis=-1)
+  conditional = clipped / context[..., numpy.newaxis]
+  per_context = (-conditional * numpy.log(conditional)).sum(axis=-1)
+  return per_context.ravel().dot(context.ravel())
+
+
+def seq_prob(spd, seq, *, num_prefix_indices=0, eps=None, mpp=None, want_mpp=False):
+  """Probability of `seq` under the subsequence table (markov_tapes.py:190-233).
+
+  Returns (probability, mpp).  Sequences not longer than k are read off directly (summing the
+  leading excess axes); longer ones are extended with the Markov process parameters.
+  """
+  spd = numpy.asarray(spd, dtype=numpy.float64)
+  k = spd.ndim - num_prefix_indices
+  excess = k - len(seq)
+  if excess >= 0:
+    picked = spd[(Ellipsis,) + tuple(seq)]
+    axes = tuple(range(num_prefix_indices, num_prefix_indices + excess))
+    return picked.sum(axis=axes), (mpp_from_spd(spd, eps=eps) if want_mpp else mpp)
+  if mpp is None:
+    mpp = mpp_from_spd(spd, eps=eps)
+  current = spd[(Ellipsis,) + tuple(seq[:k])]
+  rest = seq[1:]
+  while len(rest) >= k:
+    current = mpp[(Ellipsis,) + tuple(rest[:k])] * current
+    rest = rest[1:]
+  return current, mpp
+
+
+def tprint(size_a, cl_k, adata, epsilon=1e-10, nmax=float('inf'), file=None):
+  """Prints the entries of a transition table whose magnitude is not below epsilon."""
+  n_in = cl_k - 1
+  table = numpy.asarray(adata).reshape([size_a] * (2 * n_in))
+  for n, idx in enumerate(itertools.product(range(size_a), repeat=2 * n_in)):
+    if n >= nmax:
+      print('... more entries...', file=file)
+    val = table[idx]
+    if not abs(val) < epsilon:
+      print(f'{idx[:n_in]} {idx[n_in:]}: {val}')
+
+
+### Right-hand side and integrators
+
+def _tag_buffer(tag):
+  return numpy.frombuffer(tag.encode() + b'\x00', dtype=numpy.uint8)
+
+
+def get_dy_dt(*, tag, size_a, cl_k, debug=False):
+  """Returns the (probabilities_in, t) -> d/dt probabilities function (markov_tapes.py:259-289).
+
+  Host arrays in, host array out; the work happens on the GPU through c_compute_dy_dt.
+  """
+  a_tag = _tag_buffer(tag)
+  do_debug = 1 if debug else 0
+  expected_size = size_a ** cl_k
+
+  def dy_dt(a_probs_in, t):
+    if IS_DEBUG:
+      print(f'DDD {t=:.10g}')
+    c_probs_in = numpy.ascontiguousarray(numpy.asarray(a_probs_in, dtype=numpy.float64).ravel())
+    c_probs_out = numpy.zeros_like(c_probs_in)
+    if c_probs_in.size != expected_size:
+      raise ValueError(f'probability-array should have size {expected_size}, '
+                       f'observed: {c_probs_in.size}')
+    u_lib.c_compute_dy_dt(a_tag.ctypes.data, cl_k, do_debug, c_probs_in.ctypes.data,
+                          c_probs_out.ctypes.data)
+    if u_lib.tapes_last_error():
+      _lib.check(False, 'c_compute_dy_dt')
+    return c_probs_out
+  return dy_dt
+
+
+def _checked_p0(p0, size_a, cl_k):
+  p0 = numpy.asarray(p0, dtype=numpy.float64).ravel()
+  if not (p0.size == size_a**cl_k and (0 <= p0).all() and (p0 <= 1).all()
+          and abs(p0.sum() - 1) < 1e-10):
+    raise ValueError('Parameter p0 is not a subsequence probability distribution.')
+  return p0
+
+
+def ode_integrate(*, tag, size_a, cl_k, p0, ts, odeint_kwargs=types.MappingProxyType({}),
+                  debug=False):
+  """scipy.integrate.odeint over the GPU right-hand side (markov_tapes.py:292-318)."""
+  p0 = _checked_p0(p0, size_a, cl_k)
+  dy_dt = get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k, debug=debug)
+  return scipy.integrate.odeint(dy_dt, p0, ts, **odeint_kwargs)
+
+
+def ode_integrate_ivp(*, tag, size_a, cl_k, p0, ts, ivp_kwargs=types.MappingProxyType({}),
+                      debug=False):
+  """scipy.integrate.solve_ivp over the GPU right-hand side, result shaped like odeint's
+  (markov_tapes.py:321-354)."""
+  p0 = _checked_p0(p0, size_a, cl_k)
+  dy_dt = get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k, debug=debug)
+  return scipy.integrate.solve_ivp(
+      lambda t, y: dy_dt(y, t), (ts[0], ts[-1]), p0, t_eval=ts, **ivp_kwargs).y.T
+
+
+### Additions
+
+def register_rule_set(tag, size_a, rules):
+  """Registers a rewrite-rule set under `tag` (see configs.random_rule_set)."""
+  _lib.register_rules(tag, size_a, rules)
+
+
+def model_stats(*, tag, cl_k):
+  """Builds (or fetches) the device structure for (tag, cl_k) and returns its size facts."""
+  model = u_lib.tapes_model(tag.encode(), cl_k)
+  _lib.check(bool(model), 'tapes_model')
+  stats = _lib.model_info(model)
+  stats.update(_lib.model_timing(model))
+  return stats
+
+
+def _run_validation():
+  fn_dy_dt = get_dy_dt(tag='__canary_problem_radioactive_decay', size_a=2, cl_k=3, debug=False)
+  observed = fn_dy_dt(numpy.full([8], fill_value=0.125, dtype=numpy.float64), 0.0).tolist()
+  expected = [0.375, 0.125, 0.125, -0.125, 0.125, -0.125, -0.125, -0.375]
+  if expected != observed:
+    raise RuntimeError('Load-time validation problem failed to produce the expected result.')
+
+
+init_gambit()
+_run_validation()

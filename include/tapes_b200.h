@@ -1,0 +1,105 @@
+/* C ABI of the B200 tape-multiverse library (built as tapes_py_interface.so).
+ *
+ * The first four symbols are exactly what the reference's Python layer binds with ctypes
+ * (framework/markov_tapes.py:40-56); each replaces the reference implementation cited beside
+ * it.  The tapes_* symbols are additions for device-resident use, introspection and tests.
+ *
+ * All pointers are plain host or device addresses; there are no torch types in this interface.
+ * Unless stated otherwise a function returns 0 on success and non-zero on failure, in which case
+ * tapes_last_error() describes the problem.  The library is single-threaded like the reference
+ * (global registry, framework/tapes_py_interface.scm:24).
+ */
+#ifndef TAPES_B200_H_
+#define TAPES_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- drop-in symbols ------------------------------------------------------------------- */
+
+/* Replaces setup_gambit (framework/tapes_py_interface_c_glue.c:31-40): selects the CUDA device
+ * (LOCAL_RANK modulo the device count when set, else the current device), creates the runtime
+ * and returns an opaque handle; NULL when no sm_100 device is usable. */
+void* setup_gambit(void);
+
+/* Replaces cleanup_gambit (framework/tapes_py_interface_c_glue.c:42-45): frees every cached
+ * model and the handle. */
+void cleanup_gambit(void* handle);
+
+/* Replaces c_register_problems (framework/tapes_py_interface.scm:101-112): registers the canary
+ * and the problems of framework/problems.scm under the same tags, prints the registry listing
+ * (problems.scm:631-638) and returns n + 1. */
+int64_t c_register_problems(int64_t n);
+
+/* Replaces c_compute_dy_dt (framework/tapes_py_interface.scm:115-122 -> 80-94): probs_in and
+ * probs_out are HOST buffers of A^cl_k doubles (A = alphabet of `tag`).  The structure for
+ * (tag, cl_k) is built on first use and cached.  `debug` is accepted and ignored, as in the
+ * reference's shipped configuration (framework/tape_multiverse.scm:1448-1449). */
+void c_compute_dy_dt(const char* tag, int64_t cl_k, int64_t debug, const double* probs_in,
+                     double* probs_out);
+
+/* ---- additions -------------------------------------------------------------------------- */
+
+/* Message of the most recent failure ("" when none); cleared by tapes_clear_error. */
+const char* tapes_last_error(void);
+void tapes_clear_error(void);
+
+/* Alphabet size registered for `tag`, or -1. */
+int64_t tapes_alphabet_size(const char* tag);
+
+/* Registers a rewrite-rule set as a problem (see csrc/rules.h RewriteRule).  pattern and
+ * replacement hold 4 int32 per rule. */
+int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, const int32_t* tape,
+                         const int32_t* span, const int32_t* catalyst, const int32_t* pattern,
+                         const int32_t* replacement, const double* rate,
+                         const double* select_weight);
+
+/* Builds (or fetches from the cache) the device structure for (tag, cl_k). NULL on failure. */
+void* tapes_model(const char* tag, int64_t cl_k);
+int tapes_release_model(const char* tag, int64_t cl_k);
+
+/* dy/dt for DEVICE buffers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = the model's
+ * own stream). */
+int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream);
+
+/* One right-hand side with CUDA events between its phases, recorded on the launching stream;
+ * synchronises and writes the phase durations in ms: [0] marginal tables + leaf-world
+ * probabilities, [1] forest levels, [2] S * w. */
+int tapes_rhs_profile(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream,
+                      double* phase_ms, int capacity);
+
+/* Blocks until the model's stream is idle. */
+int tapes_sync(void* model);
+
+/* Integer facts about a model, in this order: n_states, n_nodes, nnz, n_flux_rules, n_levels,
+ * kernel launches per right-hand side, n_terms, n_sum_nodes, worlds_walked, leaf_worlds, seeds,
+ * hash_inserts, hash_unique, alphabet, cl_k, spmv lanes per row.  Returns how many were written. */
+int tapes_model_info(void* model, int64_t* out, int capacity);
+
+/* Build timings in ms: host rule enumeration, device expansion, device CSR assembly. */
+int tapes_model_timing(void* model, double* out, int capacity);
+
+/* Copies the CSR flux structure to host: row_ptr has n_states + 1 entries, entries has nnz
+ * (node id | outflow << 31). */
+int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries);
+
+/* Copies the node weights of the most recent right-hand side to host (n_nodes doubles). */
+int tapes_export_node_weights(void* model, double* weights);
+
+/* Host-only (no GPU needed): the flux-rule table of (tag, cl_k).  Call with all pointers NULL to
+ * get sizes: returns the number of rules and stores the total step count in *n_steps. Arrays:
+ * rule_ptr[n_rules + 1]; per step kind, length, long_index, short_index, prob; per rule and tape
+ * (2 per rule) seed_len, seed_orig, seed_adj.  Returns -1 on failure. */
+int64_t tapes_rule_table(const char* tag, int64_t cl_k, int64_t* n_steps, int64_t* rule_ptr,
+                         int32_t* step_kind, int32_t* step_len, int64_t* step_long,
+                         int64_t* step_short, double* step_prob, int32_t* seed_len,
+                         uint64_t* seed_orig, uint64_t* seed_adj, int64_t* walk_stats);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TAPES_B200_H_ */

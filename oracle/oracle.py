@@ -46,6 +46,9 @@ def lib():
     _lib.oracle_terms.argtypes = [
         ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
         ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    _lib.oracle_worlds.restype = ctypes.c_int64
+    _lib.oracle_worlds.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_void_p,
+                                   ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]
     _lib.oracle_alphabet_size.restype = ctypes.c_int64
     _lib.oracle_alphabet_size.argtypes = [ctypes.c_char_p]
     _lib.oracle_register_rules.restype = ctypes.c_int
@@ -95,6 +98,19 @@ def terms(tag, cl_k, probs, mode=LITERAL):
   lib().oracle_terms(tag.encode(), cl_k, mode, p.ctypes.data, n, src.ctypes.data,
                      dst.ctypes.data, w.ctypes.data)
   return src, dst, w
+
+
+def worlds(tag, cl_k, probs):
+  """Leaf worlds at `probs`: (prob[n], info[n, 6]) with info = plen, p_orig, p_adj, dlen, d_orig,
+  d_adj (see oracle_worlds in tape_oracle.cpp)."""
+  p = numpy.ascontiguousarray(numpy.asarray(probs, dtype=numpy.float64).ravel())
+  n = lib().oracle_worlds(tag.encode(), cl_k, p.ctypes.data, 0, None, None)
+  if n < 0:
+    raise RuntimeError(last_error())
+  prob = numpy.zeros(n, dtype=numpy.float64)
+  info = numpy.zeros((n, 6), dtype=numpy.int64)
+  lib().oracle_worlds(tag.encode(), cl_k, p.ctypes.data, n, prob.ctypes.data, info.ctypes.data)
+  return prob, info
 
 
 def register_rules(tag, size_a, rules):

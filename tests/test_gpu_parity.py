@@ -1,0 +1,199 @@
+"""GPU parity tests: the CUDA path (called through the C ABI) against the CPU oracle.
+
+Tolerances (stated per BASELINE.json's north_star): the flux-term set is compared exactly
+(integer indices); dy/dt is compared to 1e-13 of its largest entry (sums of ~1e1..1e2 products of
+~10 doubles each, evaluated in a different order than the CPU's depth-first walk); trajectories
+driven by the same SciPy stepper are compared to 1e-12 relative.
+"""
+
+import json
+import os
+
+import numpy
+import pytest
+import scipy.integrate
+
+from conftest import dense
+
+pytestmark = pytest.mark.gpu
+
+from chemical_kinetics_and_program_execution_b200 import configs  # noqa: E402
+from test_oracle import TAGS  # noqa: E402
+
+RHS_TOL = 1e-13
+
+
+@pytest.fixture(scope='module')
+def mt():
+  from chemical_kinetics_and_program_execution_b200 import markov_tapes
+  return markov_tapes
+
+
+@pytest.fixture(scope='module')
+def device():
+  from chemical_kinetics_and_program_execution_b200 import device as dev
+  return dev
+
+
+def test_canary_exact(mt, known_answers):
+  # the reference's load-time known-answer test, framework/markov_tapes.py:357-365
+  f = mt.get_dy_dt(tag=known_answers['canary_tag'], size_a=2, cl_k=3)
+  assert f(numpy.array(known_answers['canary_p']), 0.0).tolist() == known_answers['canary_dy_dt']
+
+
+def assert_rhs_close(got, want):
+  scale = abs(want).max()
+  assert abs(got - want).max() <= RHS_TOL * scale + 1e-300, (abs(got - want).max(), scale)
+
+
+@pytest.mark.parametrize('tag,size_a,cl_k', TAGS + [('ex2-ferromagnetic-chain', 2, 2),
+                                                   ('ex2-ferromagnetic-chain', 2, 3),
+                                                   ('ex4-chemical-turing', 9, 2),
+                                                   ('ex1-radioactive-decay', 2, 1),
+                                                   ('ex3-copolymerization', 4, 6),
+                                                   ('ex5-msrtf-machine', 5, 5)])
+def test_rhs_matches_oracle(mt, oracle, tag, size_a, cl_k):
+  f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
+  for seed, make in ((1, configs.dirichlet_product_table), (2, configs.markov_table)):
+    p = make(size_a, cl_k, seed)
+    assert_rhs_close(f(p, 0.0), oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED))
+
+
+def test_rhs_matches_literal_oracle_on_shipped_p0(mt, oracle, p0_fixtures):
+  fx = p0_fixtures
+  cases = [('ex2-ferromagnetic-chain', 2, k, dense(fx[f'ex2_k{k}_idx'], fx[f'ex2_k{k}_val'], 2 ** k))
+           for k in range(3, 8)]
+  cases += [('ex3-copolymerization', 4, 6, dense(fx['ex3_k6_idx'], fx['ex3_k6_val'], 4 ** 6)),
+            ('ex3var1-copolymerization', 4, 6, dense(fx['ex3_k6_idx'], fx['ex3_k6_val'], 4 ** 6)),
+            ('ex3var2-copolymerization', 4, 6, dense(fx['ex3_k6_idx'], fx['ex3_k6_val'], 4 ** 6)),
+            ('ex4-chemical-turing', 9, 5, dense(fx['ex4_a_idx'], fx['ex4_a_val'], 9 ** 5)),
+            ('ex4var1-chemical-turing', 9, 5, dense(fx['ex4_b_idx'], fx['ex4_b_val'], 9 ** 5)),
+            ('ex4var2-chemical-turing', 10, 5, dense(fx['ex4var2_idx'], fx['ex4var2_val'], 10 ** 5)),
+            ('ex5-msrtf-machine', 5, 5, dense(fx['ex5_idx'], fx['ex5_val'], 5 ** 5)),
+            ('ex5var1-msrtf-machine', 5, 5, dense(fx['ex5_idx'], fx['ex5_val'], 5 ** 5))]
+  for tag, size_a, cl_k, p0 in cases:
+    f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
+    assert_rhs_close(f(p0, 0.0), oracle.compute_dy_dt(tag, cl_k, p0, mode=oracle.LITERAL))
+
+
+def test_rhs_on_mid_trajectory_states(mt, oracle, trajectories):
+  tr = trajectories
+  f = mt.get_dy_dt(tag='ex4-chemical-turing', size_a=9, cl_k=5)
+  for name in ('a', 'b'):
+    for tt in (10, 100, 1000):
+      p = dense(tr[f'ex4_{name}_t{tt}_idx'], tr[f'ex4_{name}_t{tt}_val'], 9 ** 5)
+      assert_rhs_close(f(p, 0.0), oracle.compute_dy_dt('ex4-chemical-turing', 5, p, mode=oracle.LITERAL))
+  f5 = mt.get_dy_dt(tag='ex5-msrtf-machine', size_a=5, cl_k=5)
+  for key in ('ex5_t50', 'ex5_end'):
+    assert_rhs_close(f5(tr[key], 0.0), oracle.compute_dy_dt('ex5-msrtf-machine', 5, tr[key], mode=oracle.MERGED))
+
+
+def test_rhs_with_slightly_negative_entries(mt, oracle):
+  # integrators feed slightly invalid tables (tm.scm:526-539); clamps must behave identically
+  rng = numpy.random.default_rng(5)
+  p = configs.dirichlet_product_table(4, 5, 3)
+  p = p + 1e-9 * rng.standard_normal(p.size) * (rng.random(p.size) < 0.05)
+  p[rng.integers(0, p.size, 40)] = 0.0
+  p[rng.integers(0, p.size, 10)] = -1e-12
+  for tag in ('ex3-copolymerization', 'ex3var2-copolymerization'):
+    f = mt.get_dy_dt(tag=tag, size_a=4, cl_k=5)
+    assert_rhs_close(f(p, 0.0), oracle.compute_dy_dt(tag, 5, p, mode=oracle.MERGED))
+
+
+@pytest.mark.parametrize('tag,size_a,cl_k', [('__canary_problem_radioactive_decay', 2, 3),
+                                            ('ex2-ferromagnetic-chain', 2, 5),
+                                            ('ex3var2-copolymerization', 4, 4),
+                                            ('ex4-chemical-turing', 9, 3),
+                                            ('ex5-msrtf-machine', 5, 4)])
+def test_flux_term_set_is_bit_exact(mt, device, oracle, tag, size_a, cl_k):
+  """State set / sparsity: the (src, dst) pairs and their weights, canonically sorted."""
+  import torch
+  model = device.DeviceModel(tag, cl_k)
+  p = configs.dirichlet_product_table(size_a, cl_k, 7)  # full support: nothing pruned
+  d_p = torch.from_numpy(p).cuda()
+  model.rhs(d_p)
+  torch.cuda.synchronize()
+  src, dst, w = model.terms()
+  osrc, odst, ow = oracle.terms(tag, cl_k, p, mode=oracle.MERGED)
+  assert model.info['n_terms'] == len(src)
+
+  def canon(s, d, ww):
+    order = numpy.lexsort((numpy.arange(len(s)), d, s))
+    keys = numpy.stack([s[order], d[order]], axis=1)
+    uniq, inv = numpy.unique(keys, axis=0, return_inverse=True)
+    tot = numpy.zeros(len(uniq))
+    numpy.add.at(tot, inv.ravel(), ww[order])
+    return uniq, tot
+  gk, gw = canon(src, dst, w)
+  ok, ow2 = canon(osrc, odst, ow)
+  assert numpy.array_equal(gk, ok)  # bit-exact sparsity
+  assert abs(gw - ow2).max() <= 1e-14 * abs(ow2).max()
+  # the CSR rows are sorted and the row pointer is monotone
+  row_ptr, entries = model.csr()
+  assert (numpy.diff(row_ptr) >= 0).all() and row_ptr[-1] == len(entries) == 2 * len(src)
+  for r in numpy.nonzero(numpy.diff(row_ptr) > 1)[0][:200]:
+    seg = entries[row_ptr[r]:row_ptr[r + 1]]
+    assert (numpy.diff(seg.astype(numpy.int64)) > 0).all()
+
+
+def test_rule_set_problem(mt, oracle):
+  rules = configs.random_rule_set(6, 9, seed=8)
+  tag = 'rt-gpu'
+  oracle.register_rules(tag, 6, rules)
+  mt.register_rule_set(tag, 6, rules)
+  for cl_k in (2, 4, 5):
+    p = configs.markov_table(6, cl_k, 9)
+    f = mt.get_dy_dt(tag=tag, size_a=6, cl_k=cl_k)
+    assert_rhs_close(f(p, 0.0), oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED))
+
+
+def test_device_rhs_equals_host_rhs(mt, device):
+  import torch
+  p = configs.markov_table(5, 5, 1)
+  host = mt.get_dy_dt(tag='ex5-msrtf-machine', size_a=5, cl_k=5)(p, 0.0)
+  model = device.DeviceModel('ex5-msrtf-machine', 5)
+  out = model.rhs(torch.from_numpy(p).cuda())
+  assert numpy.array_equal(out.cpu().numpy(), host)  # same kernels, deterministic order
+
+
+def test_errors(mt):
+  with pytest.raises(ValueError):
+    mt.get_dy_dt(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=3)(numpy.ones(5), 0.0)
+  with pytest.raises(RuntimeError):
+    mt.get_dy_dt(tag='no-such-problem', size_a=2, cl_k=3)(numpy.ones(8) / 8, 0.0)
+  with pytest.raises(ValueError):
+    mt.ode_integrate(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=3, p0=numpy.ones(8), ts=[0, 1])
+
+
+def test_ex4_end_points_match_reference(mt, known_answers, p0_fixtures):
+  """examples/ex4_chemical_turing.py:98-116 and 150-170 through the drop-in API."""
+  for name in ('a', 'b'):
+    p0 = dense(p0_fixtures[f'ex4_{name}_idx'], p0_fixtures[f'ex4_{name}_val'], 9 ** 5)
+    ys = mt.ode_integrate_ivp(tag='ex4-chemical-turing', size_a=9, cl_k=5, p0=p0,
+                              ts=numpy.linspace(0, 2000.0, 2001),
+                              ivp_kwargs=dict(rtol=1e-13, atol=1e-13, method='DOP853'))
+    assert ys.shape == (2001, 9 ** 5)
+    spd = ys[-1].reshape([9] * 5)
+    got = [mt.seq_prob(spd, s)[0] for s in known_answers['ex4_observables']]
+    for g, w in zip(got, known_answers[f'ex4_p0_{name}_t2000']):
+      assert abs(g - w) <= 1e-12 * abs(w), (name, g, w)
+
+
+def test_ex2_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
+  """examples/ex2_ferromagnet_tape.py:74-84 (odeint, rtol=atol=1e-9) for k = 3..7."""
+  for k in range(3, 8):
+    p0 = dense(p0_fixtures[f'ex2_k{k}_idx'], p0_fixtures[f'ex2_k{k}_val'], 2 ** k)
+    ys = mt.ode_integrate(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=k, p0=p0,
+                          ts=numpy.linspace(0, 60, 1001), odeint_kwargs=dict(rtol=1e-9, atol=1e-9))
+    want = trajectories[f'ex2_k{k}_end']
+    assert abs(ys[-1] - want).max() <= 1e-12 * abs(want).max()
+
+
+def test_ex5_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
+  p0 = dense(p0_fixtures['ex5_idx'], p0_fixtures['ex5_val'], 5 ** 5)
+  ys = mt.ode_integrate_ivp(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=p0,
+                            ts=numpy.linspace(0, 500.0, 4001),
+                            ivp_kwargs=dict(rtol=1e-13, atol=1e-13, method='DOP853'))
+  for key, row in (('ex5_t50', 400), ('ex5_end', 4000)):
+    want = trajectories[key]
+    assert abs(ys[row] - want).max() <= 1e-12 * abs(want).max()
