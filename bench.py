@@ -1,0 +1,359 @@
+"""Benchmark of the master-equation step  dy/dt = S * w(p)  on a synthetic random rewrite-rule
+multiverse (BASELINE.json: last config).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the CPU port of the reference path
+
+One "step" is one full right-hand side over the whole state table: marginal tables, leaf-world
+probabilities, every level of the window-extension forest (the p-dependent re-evaluation of the
+rate structure) and the CSR product S*w.  With N > 1 the rule set is dealt to the ranks
+(parallel.py) and a step also contains the flux reduce-scatter and the table all-gather.
+
+`value` is algorithmic GB/s of the whole step (bytes defined in DESIGN.md, "Algorithmic bytes"):
+  step_bytes = 28 * nnz + 24 * n + 8 * n * (1 + 2 / (A - 1))
+`roofline` describes the dominant kernel, the CSR product, against the measured HBM peak:
+  spmv_bytes = 12 * nnz + 16 * n
+Prints exactly one JSON line on rank 0.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+METRIC = 'master-eq SpMV GB/s (whole dy/dt step incl. rate re-evaluation, algorithmic bytes)'
+UNIT = 'GB/s'
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  ap.add_argument('--size-a', type=int, default=10)
+  ap.add_argument('--cl-k', type=int, default=8)
+  ap.add_argument('--rules-per-gpu', type=int, default=16)
+  ap.add_argument('--seed', type=int, default=1)
+  ap.add_argument('--e2e-steps', type=int, default=3)
+  ap.add_argument('--cpu-rules', type=int, default=2, help='rules in the CPU-baseline sample')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  return ap.parse_args()
+
+
+def step_bytes(nnz, n, size_a):
+  return 28.0 * nnz + 24.0 * n + 8.0 * n * (1.0 + 2.0 / max(size_a - 1, 1))
+
+
+def spmv_bytes(nnz, n):
+  return 12.0 * nnz + 16.0 * n
+
+
+def measured_peak():
+  path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  try:
+    with open(path) as f:
+      return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+  except Exception:
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+  """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
+  QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+           'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+           'clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.samples = []
+    self.stop = threading.Event()
+    self.thread = threading.Thread(target=self._run, daemon=True)
+
+  def _run(self):
+    while not self.stop.is_set():
+      try:
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+                              '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                             timeout=5).stdout.strip()
+        if out:
+          self.samples.append([x.strip() for x in out.split(',')])
+      except Exception:
+        pass
+      self.stop.wait(0.2)
+
+  def __enter__(self):
+    self.thread.start()
+    return self
+
+  def __exit__(self, *exc):
+    self.stop.set()
+    self.thread.join(timeout=10)
+
+  def summary(self):
+    sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+    mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    reasons = sorted({names[i] for s in self.samples for i in range(4)
+                      if len(s) >= 6 and s[2 + i].lower().startswith('active')})
+    return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
+                reasons=reasons, samples=len(self.samples))
+
+
+def make_workload(args, world, rank):
+  """The synthetic rule set (all ranks generate the same one) and this rank's share."""
+  from chemical_kinetics_and_program_execution_b200 import configs, parallel
+  total_rules = args.rules_per_gpu * world
+  rules = configs.random_rule_set(args.size_a, total_rules, seed=args.seed)
+  local = parallel.split_rule_set(rules, world, rank) if world > 1 else rules
+  tag = configs.synthetic_tag(args.size_a, total_rules, args.seed) + (f'-rank{rank}of{world}' if world > 1 else '')
+  return rules, local, tag
+
+
+def device_product_table(size_a, cl_k, seed, device):
+  """Full-support product table built on the device (Dirichlet symbol frequencies)."""
+  import torch
+  rng = numpy.random.default_rng(seed)
+  f = torch.from_numpy(rng.dirichlet(numpy.ones(size_a))).to(device)
+  table = f
+  for _ in range(cl_k - 1):
+    table = (table[:, None] * f[None, :]).reshape(-1)
+  return table.contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# CPU port (oracle) legs: the only places bench.py executes anything under oracle/.
+# --------------------------------------------------------------------------------------------
+def _cpu_worker(job):
+  tag, size_a, cl_k, rules, seed = job
+  from chemical_kinetics_and_program_execution_b200 import configs
+  from oracle import oracle
+  oracle.register_rules(tag, size_a, rules)
+  f = numpy.random.default_rng(seed).dirichlet(numpy.ones(size_a))
+  p = configs.product_table(f, cl_k)
+  t0 = time.perf_counter()
+  out, counters = oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED, want_counters=True)
+  return time.perf_counter() - t0, counters, float(abs(out).sum())
+
+
+def cpu_port_step(args, rules_subset, nnz_per_rule_state, reps=1):
+  """Times the merged-mode CPU port on `rules_subset`, one worker process per rule (the forests
+  of different rules are independent, which is the only parallelism the path offers on a CPU)."""
+  import multiprocessing as mp
+  from chemical_kinetics_and_program_execution_b200 import parallel
+  n_rules = len(rules_subset['rate'])
+  cores = min(len(os.sched_getaffinity(0)), n_rules)
+  jobs = [(f'cpu-sample-{i}', args.size_a, args.cl_k, parallel.split_rule_set(rules_subset, cores, i), args.seed + 2)
+          for i in range(cores)]
+  ctx = mp.get_context('fork')
+  times = []
+  counters = None
+  for _ in range(reps):
+    with ctx.Pool(cores) as pool:
+      res = pool.map(_cpu_worker, jobs)
+    times.append(max(r[0] for r in res))  # workers run concurrently; table set-up is not timed
+    counters = {k: sum(r[1][k] for r in res) for k in res[0][1]}
+  return min(times), cores, counters
+
+
+def run_reference(args):
+  """--impl reference: the CPU port of the reference's compute-dy/dt (oracle, merged mode; the
+  Gambit-C original cannot be built in this image) on a bounded sample of the same workload."""
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  from chemical_kinetics_and_program_execution_b200 import configs
+  from oracle import oracle
+  oracle.build()
+  n = args.size_a ** args.cl_k
+  total_rules = args.rules_per_gpu * args.gpus
+  rules = configs.random_rule_set(args.size_a, total_rules, seed=args.seed)
+  sample = {k: numpy.asarray(v)[:args.cpu_rules] for k, v in rules.items()}
+  # structural size of the sample (terms -> nnz) from the port's own term counter
+  times, cores, counters = [], 1, None
+  for _ in range(args.warmup + args.steps):
+    t, cores, counters = cpu_port_step(args, sample, None)
+    times.append(t)
+  timed = times[args.warmup:]
+  nnz = 2 * counters['acc_calls']
+  bytes_step = step_bytes(nnz, n, args.size_a)
+  ms = 1e3 * sum(timed) / len(timed)
+  value = bytes_step / (ms * 1e-3) / 1e9
+  sample_desc = (f'first {args.cpu_rules} of {total_rules} rules of the same rule set on the full '
+                 f'{n}-state table, nnz={nnz}, merged-mode port, one process per rule')
+  line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus,
+              steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
+              scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
+              config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a,
+                          cl_k=args.cl_k, n_states=n, rules_per_gpu=args.rules_per_gpu,
+                          total_rules=total_rules, seed=args.seed, sample=sample_desc),
+              cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample_desc),
+              e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+              gpu_launches=0)
+  print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA path
+# --------------------------------------------------------------------------------------------
+def run_b200(args):
+  import torch
+  import torch.distributed as dist
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  if world != args.gpus:
+    if world == 1 and args.gpus > 1:
+      raise SystemExit('launch with torch.distributed.run for --gpus > 1')
+  torch.cuda.set_device(local_rank)
+  device = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=device)
+
+  from chemical_kinetics_and_program_execution_b200 import device as dev, markov_tapes as mt, parallel
+
+  n = args.size_a ** args.cl_k
+  rules, local_rules, tag = make_workload(args, world, rank)
+  mt.register_rule_set(tag, args.size_a, local_rules)
+  t0 = time.perf_counter()
+  model = dev.DeviceModel(tag, args.cl_k)
+  torch.cuda.synchronize()
+  build_s = time.perf_counter() - t0
+  info, timing = model.info, model.timing
+
+  p = device_product_table(args.size_a, args.cl_k, args.seed + 2, device)
+  out = torch.empty_like(p)
+  sharded = None
+  if world > 1:
+    sharded = parallel.ShardedRhs(lambda pin, pout: model.rhs(pin, pout), n, device=device)
+    p_full = torch.zeros(sharded.padded, dtype=torch.float64, device=device)
+    p_full[:n] = p
+    out_full = torch.zeros_like(p_full)
+
+  def one_step():
+    if sharded is None:
+      model.rhs(p, out)
+    else:
+      sharded.rhs_full(p_full, out_full)
+
+  for _ in range(args.warmup):
+    one_step()
+  torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  with ClockSampler(local_rank) as clocks:
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+      one_step()
+    ev1.record()
+    torch.cuda.synchronize()
+  if world > 1:
+    dist.barrier()
+  ms_total = ev0.elapsed_time(ev1)
+  if world > 1:
+    t = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+  ms_step = ms_total / args.steps
+
+  # whole-job structural size
+  sizes = torch.tensor([info['nnz'], info['n_nodes'], info['n_terms'], info['launches_per_rhs']],
+                       dtype=torch.float64, device=device)
+  if world > 1:
+    dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
+  nnz_total, nodes_total, terms_total, launches_total = [float(x) for x in sizes.tolist()]
+  job_bytes = 28.0 * nnz_total + world * (24.0 * n + 8.0 * n * (1.0 + 2.0 / max(args.size_a - 1, 1)))
+  value = job_bytes / (ms_step * 1e-3) / 1e9
+
+  # per-phase device times of this rank's kernels (CUDA events on the launching stream)
+  phase = numpy.zeros(3)
+  reps = max(3, min(args.steps, 10))
+  for _ in range(reps):
+    phase += model.rhs_profile(p, out)
+  phase /= reps
+  peak, peak_src = measured_peak()
+  spmv_gbs = spmv_bytes(info['nnz'], n) / (phase[2] * 1e-3) / 1e9
+  roofline = dict(bound='hbm', kernel='spmv_kernel (S*w, CSR)', achieved=spmv_gbs, peak=peak,
+                  unit='GB/s', frac=spmv_gbs / peak, traffic=None, peak_source=peak_src,
+                  algorithmic_bytes_per_launch=spmv_bytes(info['nnz'], n),
+                  kernel_ms=float(phase[2]),
+                  phases_ms=dict(marginals_and_world_probs=float(phase[0]), forest_levels=float(phase[1]),
+                                 spmv=float(phase[2])),
+                  step_frac_of_peak=(step_bytes(info['nnz'], n, args.size_a) / (phase.sum() * 1e-3) / 1e9) / peak)
+
+  # end to end through the reference-facing C ABI call with pinned HOST buffers
+  e2e = None
+  if rank == 0 and world == 1:
+    h_in = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_out = torch.empty(n, dtype=torch.float64).pin_memory()
+    h_in.copy_(p)
+    f = mt.get_dy_dt(tag=tag, size_a=args.size_a, cl_k=args.cl_k)
+    a_tag = numpy.frombuffer(tag.encode() + b'\x00', dtype=numpy.uint8)
+    call = lambda: mt.u_lib.c_compute_dy_dt(a_tag.ctypes.data, args.cl_k, 0, h_in.data_ptr(), h_out.data_ptr())
+    call()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+      call()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.e2e_steps
+    e2e = dict(value=step_bytes(info['nnz'], n, args.size_a) / (e2e_ms * 1e-3) / 1e9, unit=UNIT,
+               h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n, ms_per_step=e2e_ms,
+               api='c_compute_dy_dt (host buffers, pinned)')
+    del f
+  elif rank == 0:
+    e2e = dict(value=None, unit=UNIT, h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
+               note='host-buffer entry point is single-GPU; measured at N=1')
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    from oracle import oracle
+    oracle.build()
+    sample = {k: numpy.asarray(v)[:args.cpu_rules] for k, v in rules.items()}
+    t_cpu, cores, counters = cpu_port_step(args, sample, None)
+    nnz_s = 2 * counters['acc_calls']
+    cpu = dict(value=step_bytes(nnz_s, n, args.size_a) / t_cpu / 1e9, unit=UNIT, cores=cores, kind='port',
+               sample=(f'first {args.cpu_rules} of {args.rules_per_gpu} rules on the full {n}-state table '
+                       f'(nnz={nnz_s}), merged-mode CPU port of compute-dy/dt, one process per rule, '
+                       f'{t_cpu:.1f} s'),
+               seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu)
+
+  if rank == 0:
+    expand_s = (timing['device_expand_ms'] + timing['host_enumerate_ms']) * 1e-3
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
+                data='synthetic',
+                config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a, cl_k=args.cl_k,
+                            n_states=n, rules_per_gpu=args.rules_per_gpu, total_rules=args.rules_per_gpu * world,
+                            seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
+                            parallelism=f'rules dealt to {world} rank(s); reduce-scatter + all-gather per step' if world > 1 else 'single GPU',
+                            l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
+                clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches_total / world) * args.steps,
+                roofline=roofline, cpu_baseline=cpu,
+                states_expanded_per_s=(info['n_nodes'] + info['worlds_walked']) / max(expand_s, 1e-9),
+                build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
+                           hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique']))
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_b200(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -11,6 +11,12 @@ from . import _lib
 from . import markov_tapes
 
 
+def _current_stream_handle():
+  """cudaStream_t of torch's current stream.  Torch reports the legacy default stream as 0,
+  which the C ABI reads as "use the model's own stream", so it is passed as cudaStreamLegacy."""
+  return torch.cuda.current_stream().cuda_stream or 1
+
+
 class DeviceModel:
   """The structure of (tag, cl_k) on the current CUDA device."""
 
@@ -27,7 +33,7 @@ class DeviceModel:
     assert p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.numel() == self.n_states
     if out is None:
       out = torch.empty_like(p)
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = _current_stream_handle()
     rc = markov_tapes.u_lib.tapes_rhs_device(self.handle, p.data_ptr(), out.data_ptr(), stream)
     _lib.check(rc == 0, 'tapes_rhs_device')
     return out
@@ -35,7 +41,7 @@ class DeviceModel:
   def rhs_profile(self, p, out):
     """One right-hand side with CUDA events between its phases; returns ms per phase
     (marginals + leaf-world probabilities, forest levels, S*w) measured on the launch stream."""
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = _current_stream_handle()
     ms = numpy.zeros(3, dtype=numpy.float64)
     rc = markov_tapes.u_lib.tapes_rhs_profile(self.handle, p.data_ptr(), out.data_ptr(), stream,
                                               ms.ctypes.data, 3)

@@ -1,0 +1,78 @@
+"""CPU tests (gloo, world_size 2) of the multi-GPU plumbing: rule dealing, flux reduce-scatter
+and table all-gather reproduce the unsplit right-hand side.  The local right-hand side is played
+by the CPU oracle here; on the GPU box bench.py plugs in the CUDA path."""
+
+import os
+import socket
+
+import numpy
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from chemical_kinetics_and_program_execution_b200 import configs, parallel
+
+SIZE_A, CL_K, N_RULES = 5, 4, 7
+
+
+def _free_port():
+  with socket.socket() as s:
+    s.bind(('127.0.0.1', 0))
+    return s.getsockname()[1]
+
+
+def _worker(rank, world, port, result_path):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from oracle import oracle
+  rules = configs.random_rule_set(SIZE_A, N_RULES, seed=6)
+  local = parallel.split_rule_set(rules, world, rank)
+  tag = f'par-test-{rank}'
+  oracle.register_rules(tag, SIZE_A, local)
+  n = SIZE_A ** CL_K
+
+  def local_rhs(p_full, out_full):
+    out_full.copy_(torch.from_numpy(oracle.compute_dy_dt(tag, CL_K, p_full.numpy(), mode=oracle.MERGED)))
+
+  sharded = parallel.ShardedRhs(local_rhs, n, device='cpu')
+  p = torch.zeros(sharded.padded, dtype=torch.float64)
+  p[:n] = torch.from_numpy(configs.markov_table(SIZE_A, CL_K, 3))
+  out = torch.zeros_like(p)
+  sharded.rhs_full(p, out)
+  if rank == 0:
+    numpy.save(result_path, out[:n].numpy())
+  dist.destroy_process_group()
+
+
+def test_split_rule_set_keeps_every_rule_once():
+  rules = configs.random_rule_set(SIZE_A, N_RULES, seed=6)
+  seen = []
+  for r in range(3):
+    part = parallel.split_rule_set(rules, 3, r)
+    assert abs(part['select_weight'].sum() - rules['select_weight'].sum()) < 1e-12
+    seen += part['rate'][:-1].tolist()  # last one is the inert rule
+    assert (part['pattern'][-1] == part['repl'][-1]).all()
+  assert sorted(seen) == sorted(rules['rate'].tolist())
+
+
+def test_block_bounds_cover_all_states():
+  for n, w in ((625, 2), (1000, 8), (7, 4)):
+    covered = []
+    for r in range(w):
+      lo, hi, block = parallel.block_bounds(n, w, r)
+      covered += list(range(lo, hi))
+      assert hi - lo <= block
+    assert covered == list(range(n))
+
+
+def test_two_rank_rhs_equals_unsplit(tmp_path, oracle):
+  result = str(tmp_path / 'dy.npy')
+  port = _free_port()
+  mp.spawn(_worker, args=(2, port, result), nprocs=2, join=True)
+  got = numpy.load(result)
+  rules = configs.random_rule_set(SIZE_A, N_RULES, seed=6)
+  oracle.register_rules('par-test-full', SIZE_A, rules)
+  p = configs.markov_table(SIZE_A, CL_K, 3)
+  want = oracle.compute_dy_dt('par-test-full', CL_K, p, mode=oracle.MERGED)
+  assert abs(got - want).max() <= 1e-14 * abs(want).max()
