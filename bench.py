@@ -26,6 +26,8 @@ import time
 
 import numpy
 
+os.environ.setdefault('MARKOV_TAPES_QUIET', '1')  # stdout carries exactly one JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)

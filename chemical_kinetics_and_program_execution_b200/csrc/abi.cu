@@ -97,10 +97,12 @@ void cleanup_gambit(void* handle) {
 
 int64_t c_register_problems(int64_t n) {
   tapes::register_builtin_problems();
-  std::printf("=== Registered Problems ===\n");
-  for (const std::string& tag : tapes::registered_tags()) std::printf("%s\n", tag.c_str());
-  std::printf("======\n");
-  std::fflush(stdout);
+  if (!std::getenv("MARKOV_TAPES_QUIET")) {  // the listing of problems.scm:631-638
+    std::printf("=== Registered Problems ===\n");
+    for (const std::string& tag : tapes::registered_tags()) std::printf("%s\n", tag.c_str());
+    std::printf("======\n");
+    std::fflush(stdout);
+  }
   return n + 1;
 }
 
