@@ -16,7 +16,7 @@ SYMBOLS = (
     'setup_gambit', 'cleanup_gambit', 'c_register_problems', 'c_compute_dy_dt',
     'tapes_last_error', 'tapes_clear_error', 'tapes_alphabet_size', 'tapes_register_rules',
     'tapes_model', 'tapes_release_model', 'tapes_rhs_device', 'tapes_rhs_profile', 'tapes_sync', 'tapes_model_info',
-    'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
+    'tapes_model_set', 'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
 )
 
 _lib = None
@@ -62,6 +62,8 @@ def load():
   lib.tapes_sync.argtypes = [vp]
   lib.tapes_model_info.restype = i32
   lib.tapes_model_info.argtypes = [vp, vp, i32]
+  lib.tapes_model_set.restype = i32
+  lib.tapes_model_set.argtypes = [vp, ctypes.c_char_p, i64]
   lib.tapes_model_timing.restype = i32
   lib.tapes_model_timing.argtypes = [vp, vp, i32]
   lib.tapes_export_csr.restype = i32

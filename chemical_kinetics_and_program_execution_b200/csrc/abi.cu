@@ -201,6 +201,18 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   return n;
 }
 
+int tapes_model_set(void* model, const char* key, int64_t value) {
+  if (!model) { fail("null model"); return 1; }
+  tapes::Model& m = *(tapes::Model*)model;
+  if (std::strcmp(key, "spmv_lanes") == 0 &&
+      (value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
+    m.spmv_group = (int)value;
+    return 0;
+  }
+  fail(std::string("unknown option or value: ") + key);
+  return 1;
+}
+
 int tapes_model_timing(void* model, double* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
   const tapes::Model& m = *(tapes::Model*)model;

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -60,8 +61,9 @@ struct Frontier {
 // ---------------------------------------------------------------------------------------------
 // Expansion pass 1: classify every frontier node and hash-insert right-chain prefixes.
 // ---------------------------------------------------------------------------------------------
-__global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __restrict__ cflag,
-                                uint32_t* __restrict__ tflag, uint8_t* __restrict__ kflag) {
+__global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __restrict__ lflag,
+                                uint32_t* __restrict__ rflag, uint32_t* __restrict__ tflag,
+                                uint8_t* __restrict__ kflag) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < f.n;
   bool haskey = false;
@@ -71,12 +73,12 @@ __global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __re
     const uint8_t meta = f.meta[i], fl = f.flags[i];
     const int kind = meta >> 6, len = meta & 63;
     const uint32_t io = f.io[i], ia = f.ia[i];
-    uint32_t child = 0;
+    uint32_t left = 0, right = 0;
     if (kind == NODE_SUM) {
-      child = 1;
+      right = 1;                                      // tm.scm:1310-1322
     } else if (fl & FL_LEFT) {
-      if (len < c.k) child = 1;                       // tm.scm:1340-1357
-      else if (io / c.A != ia / c.A) child = 1;       // tm.scm:1358-1379, entry test 1331
+      if (len < c.k) left = 1;                        // tm.scm:1340-1357
+      else if (io / c.A != ia / c.A) left = 1;        // tm.scm:1358-1379, entry test 1331
     }
     if (kind != NODE_SUM && (fl & FL_RIGHT)) {        // tm.scm:1393-1397 / 1319-1322
       const uint32_t po = io % c.M;
@@ -84,7 +86,8 @@ __global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __re
       haskey = po != pa;                              // tm.scm:1308-1309
       key = ((uint64_t)f.seed[i] << 32) | po;
     }
-    cflag[i] = child;
+    lflag[i] = left;
+    rflag[i] = right;
     tflag[i] = (fl & FL_TERM) ? 1u : 0u;
     kflag[i] = haskey ? 1 : 0;
   }
@@ -115,31 +118,43 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Expansion pass 2: write the children (digit-major, so that consecutive threads touch
-// consecutive table entries on every later evaluation), the flux edges and the SUM ranks.
+// Expansion pass 2: write the children, the flux edges and the SUM ranks.  Children are laid out
+// so that consecutive nodes have consecutive table indices on every later evaluation: a left
+// extension adds the MOST significant digit, so left children are stored digit-major
+// (x * n_left_parents + parent rank); a right extension adds the LEAST significant digit, so
+// right children are stored parent-major (parent rank * A + x) behind them.
 // ---------------------------------------------------------------------------------------------
-__global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ cflag,
-                            const uint32_t* __restrict__ tflag, const uint8_t* __restrict__ kflag,
-                            const uint64_t* __restrict__ crank, const uint64_t* __restrict__ trank,
-                            uint64_t n_parents_with_children, const uint64_t* __restrict__ sorted_keys,
+__global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ lflag,
+                            const uint32_t* __restrict__ rflag, const uint32_t* __restrict__ tflag,
+                            const uint8_t* __restrict__ kflag, const uint64_t* __restrict__ lrank,
+                            const uint64_t* __restrict__ rrank, const uint64_t* __restrict__ trank,
+                            uint64_t n_left_parents, const uint64_t* __restrict__ sorted_keys,
                             uint32_t n_keys, Frontier next, uint32_t* __restrict__ next_parent,
                             uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
                             uint32_t* __restrict__ keyrank) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.n) return;
   const uint8_t meta = f.meta[i];
-  const int kind = meta >> 6, len = meta & 63;
+  const int len = meta & 63;
   const uint32_t io = f.io[i], ia = f.ia[i], seed = f.seed[i];
   const uint32_t gid = (uint32_t)(cur_base + i);
-  if (cflag[i]) {
-    const uint64_t r = crank[i];
+  if (rflag[i]) {                      // right extension of a prefix: prefix * A + x
+    const uint64_t first = (uint64_t)c.A * n_left_parents + rrank[i] * c.A;
+    const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
+    for (uint32_t x = 0; x < c.A; ++x) {
+      const uint64_t ci = first + x;
+      next.io[ci] = io * c.A + x;
+      next.ia[ci] = ia * c.A + x;
+      next.seed[ci] = seed;
+      next.meta[ci] = nmeta;
+      next.flags[ci] = FL_TERM | FL_RIGHT;
+      next_parent[ci] = gid;
+    }
+  } else if (lflag[i]) {
+    const uint64_t r = lrank[i];
     uint32_t bo, ba, step;
     uint8_t nmeta, nfl;
-    if (kind == NODE_SUM) {            // right extension of a prefix: prefix * A + x
-      bo = io * c.A; ba = ia * c.A; step = 1;
-      nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
-      nfl = FL_TERM | FL_RIGHT;
-    } else if (len < c.k) {            // left extension: x * A^len + index
+    if (len < c.k) {                   // left extension: x * A^len + index
       bo = io; ba = ia; step = c.pw[len];
       const int nl = len + 1;
       nmeta = (uint8_t)((NODE_LEFT << 6) | nl);
@@ -150,7 +165,7 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
       nfl = FL_TERM | FL_LEFT;
     }
     for (uint32_t x = 0; x < c.A; ++x) {
-      const uint64_t ci = (uint64_t)x * n_parents_with_children + r;
+      const uint64_t ci = (uint64_t)x * n_left_parents + r;
       next.io[ci] = bo + x * step;
       next.ia[ci] = ba + x * step;
       next.seed[ci] = seed;
@@ -336,24 +351,41 @@ __global__ void level_kernel(Tables t, Consts c, Level lv, const double* __restr
   }
 }
 
-// dy/dt[row] = sum over the row's entries of +-w[node]; G lanes per row, shuffle reduction.
+// dy/dt[row] = sum over the row's entries of +-w[node].  G lanes share a row; every lane keeps
+// kSpmvUnroll independent entry loads and weight gathers in flight, then the lanes of a row are
+// combined by a shuffle reduction.  The summation order is fixed by (G, unroll), so results are
+// reproducible run to run.
+constexpr int kSpmvUnroll = 4;
+
 template <int G>
-__global__ void spmv_kernel(const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ entries,
-                            const double* __restrict__ w, double* __restrict__ out, uint64_t n_rows) {
+__global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ row_ptr,
+                                                   const uint32_t* __restrict__ entries,
+                                                   const double* __restrict__ w, double* __restrict__ out,
+                                                   uint64_t n_rows) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t row = t / G;
   const int sub = (int)(t % G);
   double acc = 0.0;
   if (row < n_rows) {
     const uint64_t lo = row_ptr[row], hi = row_ptr[row + 1];
-    for (uint64_t e = lo + sub; e < hi; e += G) {
-      const uint32_t v = entries[e];
-      const double x = w[v & ~kOutflowBit];
-      acc += (v & kOutflowBit) ? -x : x;
+    for (uint64_t e = lo + sub; e < hi; e += (uint64_t)G * kSpmvUnroll) {
+      uint32_t v[kSpmvUnroll];
+#pragma unroll
+      for (int u = 0; u < kSpmvUnroll; ++u) {
+        const uint64_t eu = e + (uint64_t)u * G;
+        v[u] = eu < hi ? entries[eu] : 0xffffffffu;
+      }
+      double x[kSpmvUnroll];
+#pragma unroll
+      for (int u = 0; u < kSpmvUnroll; ++u) x[u] = v[u] != 0xffffffffu ? w[v[u] & ~kOutflowBit] : 0.0;
+#pragma unroll
+      for (int u = 0; u < kSpmvUnroll; ++u) acc += (v[u] & kOutflowBit) ? -x[u] : x[u];
     }
   }
+  if (G > 1) {
 #pragma unroll
-  for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
+    for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
+  }
   if (sub == 0 && row < n_rows) out[row] = acc;
 }
 
@@ -527,25 +559,30 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     hs.vals = dalloc<uint32_t>(cap, st);
     hs.mask = cap - 1;
     TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
-    uint32_t* cflag = dalloc<uint32_t>(n, st);
+    uint32_t* lflag = dalloc<uint32_t>(n, st);
+    uint32_t* rflag = dalloc<uint32_t>(n, st);
     uint32_t* tflag = dalloc<uint32_t>(n, st);
     uint8_t* kflag = dalloc<uint8_t>(n, st);
-    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, cflag, tflag, kflag);
-    uint64_t* crank = dalloc<uint64_t>(n + 1, st);
+    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, rflag, tflag, kflag);
+    uint64_t* lrank = dalloc<uint64_t>(n + 1, st);
+    uint64_t* rrank = dalloc<uint64_t>(n + 1, st);
     uint64_t* trank = dalloc<uint64_t>(n + 1, st);
     uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(std::max<uint64_t>(cap, 256ull * 1184)), st);
-    exclusive_scan_u32(cflag, n, crank, scan_tmp, st);
+    exclusive_scan_u32(lflag, n, lrank, scan_tmp, st);
+    exclusive_scan_u32(rflag, n, rrank, scan_tmp, st);
     exclusive_scan_u32(tflag, n, trank, scan_tmp, st);
     uint32_t* sflag = dalloc<uint32_t>(cap, st);
     uint64_t* srank = dalloc<uint64_t>(cap + 1, st);
     slot_flag_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, sflag);
     exclusive_scan_u32(sflag, cap, srank, scan_tmp, st);
-    uint64_t h_tot[3];
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], crank + n, 8, cudaMemcpyDeviceToHost, st));
+    uint64_t h_tot[4];
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], lrank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], trank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], srank + cap, 8, cudaMemcpyDeviceToHost, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[3], rrank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-    const uint64_t NC = h_tot[0], NT = h_tot[1], NS = h_tot[2];
+    const uint64_t NL = h_tot[0], NT = h_tot[1], NS = h_tot[2], NR = h_tot[3];
+    const uint64_t NC = NL + NR;
     if (NS >= 0xffffffffull || NC * (uint64_t)m.A >= 0xffffffffull) throw std::runtime_error("level too large");
 
     // unique right-chain prefixes in canonical (seed, prefix) order
@@ -578,9 +615,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     EdgeChunk ec{nullptr, nullptr, 2 * NT};
     if (NT) { ec.row = dalloc<uint32_t>(2 * NT, st); ec.val = dalloc<uint32_t>(2 * NT, st); }
     uint32_t* keyrank = dalloc<uint32_t>(n, st);
-    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, cflag, tflag, kflag, crank,
-                                                          trank, NC, sorted, (uint32_t)NS, next, next_parent,
-                                                          ec.row, ec.val, keyrank);
+    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, rflag, tflag, kflag,
+                                                          lrank, rrank, trank, NL, sorted, (uint32_t)NS, next,
+                                                          next_parent, ec.row, ec.val, keyrank);
     Level next_level;
     next_level.base = cur_level.base + n;
     next_level.n_plain = next.n_plain;
@@ -615,7 +652,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     // retire the current frontier; its io/parent/meta live on in the level store
     m.levels.push_back(cur_level);
     dfree(cur.ia, st); dfree(cur.seed, st); dfree(cur.flags, st);
-    dfree(cflag, st); dfree(tflag, st); dfree(kflag, st); dfree(crank, st); dfree(trank, st);
+    dfree(lflag, st); dfree(rflag, st); dfree(tflag, st); dfree(kflag, st);
+    dfree(lrank, st); dfree(rrank, st); dfree(trank, st);
     dfree(scan_tmp, st); dfree(keys_a, st); dfree(keys_b, st); dfree(keyrank, st);
     dfree(hs.keys, st); dfree(hs.vals, st);
     cur = next;
@@ -650,7 +688,11 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaGetLastError());
   }
   const double per_row = n ? (double)m.nnz / (double)n : 0.0;
-  m.spmv_group = per_row > 24 ? 16 : (per_row > 10 ? 8 : (per_row > 4 ? 4 : 2));
+  m.spmv_group = per_row > 48 ? 4 : (per_row > 24 ? 2 : 1);
+  if (const char* g = std::getenv("TAPES_SPMV_LANES")) {
+    const int v = std::atoi(g);
+    if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) m.spmv_group = v;
+  }
 
   // ---- per-step buffers ----
   m.marg_total = 0;
@@ -716,6 +758,7 @@ static void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t 
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
   const uint64_t threads = m.n_states * (uint64_t)m.spmv_group;
   switch (m.spmv_group) {
+    case 1: spmv_kernel<1><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
     case 2: spmv_kernel<2><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
     case 4: spmv_kernel<4><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
     case 8: spmv_kernel<8><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;

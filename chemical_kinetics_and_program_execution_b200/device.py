@@ -28,6 +28,11 @@ class DeviceModel:
     self.timing = _lib.model_timing(self.handle)
     self.n_states = self.info['n_states']
 
+  def set_option(self, key, value):
+    rc = markov_tapes.u_lib.tapes_model_set(self.handle, key.encode(), int(value))
+    _lib.check(rc == 0, 'tapes_model_set')
+    self.info = _lib.model_info(self.handle)
+
   def rhs(self, p, out=None):
     """dy/dt of a float64 CUDA tensor, asynchronously on torch's current stream."""
     assert p.is_cuda and p.dtype == torch.float64 and p.is_contiguous() and p.numel() == self.n_states

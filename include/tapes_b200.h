@@ -79,6 +79,9 @@ int tapes_sync(void* model);
  * hash_inserts, hash_unique, alphabet, cl_k, spmv lanes per row.  Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
+/* Tuning knobs of a built model; currently "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row). */
+int tapes_model_set(void* model, const char* key, int64_t value);
+
 /* Build timings in ms: host rule enumeration, device expansion, device CSR assembly. */
 int tapes_model_timing(void* model, double* out, int capacity);
 

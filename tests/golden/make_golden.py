@@ -140,6 +140,10 @@ def make_trajectories():
     ys = scipy.integrate.odeint(f, p0, numpy.linspace(0, 60, 1001), rtol=1e-9, atol=1e-9)
     result[f'ex2_k{k}_end'] = ys[-1]
     result[f'ex2_k{k}_t6'] = ys[100]
+    # the same problem through the explicit stepper, where 1e-12 parity is meaningful
+    sol = scipy.integrate.solve_ivp(lambda t, y: f(y, t), (0.0, 60.0), p0, t_eval=[0.0, 30.0, 60.0],
+                                    rtol=1e-13, atol=1e-13, method='DOP853')
+    result[f'ex2_k{k}_dop853_end'] = sol.y[:, -1]
   numpy.savez_compressed(os.path.join(HERE, 'oracle_trajectories.npz'), **result)
   print('wrote oracle_trajectories.npz')
 

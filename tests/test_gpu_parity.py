@@ -197,13 +197,24 @@ def test_ex4_end_points_match_reference(mt, known_answers, p0_fixtures):
 
 
 def test_ex2_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
-  """examples/ex2_ferromagnet_tape.py:74-84 (odeint, rtol=atol=1e-9) for k = 3..7."""
+  """examples/ex2_ferromagnet_tape.py:74-84 for k = 3..7.
+
+  Through DOP853 (rtol=atol=1e-13) the GPU and CPU trajectories agree to 1e-12.  Through the
+  shipped odeint/LSODA call (rtol=atol=1e-9) they agree to 1e-10: LSODA differentiates the
+  right-hand side numerically for its Jacobian, which amplifies last-bit differences of dy/dt far
+  below the solver's own 1e-9 tolerance but above 1e-12.
+  """
   for k in range(3, 8):
     p0 = dense(p0_fixtures[f'ex2_k{k}_idx'], p0_fixtures[f'ex2_k{k}_val'], 2 ** k)
+    ys = mt.ode_integrate_ivp(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=k, p0=p0, ts=[0.0, 30.0, 60.0],
+                              ivp_kwargs=dict(rtol=1e-13, atol=1e-13, method='DOP853'))
+    want = trajectories[f'ex2_k{k}_dop853_end']
+    assert abs(ys[-1] - want).max() <= 1e-12 * abs(want).max()
     ys = mt.ode_integrate(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=k, p0=p0,
                           ts=numpy.linspace(0, 60, 1001), odeint_kwargs=dict(rtol=1e-9, atol=1e-9))
     want = trajectories[f'ex2_k{k}_end']
-    assert abs(ys[-1] - want).max() <= 1e-12 * abs(want).max()
+    assert ys.shape == (1001, 2 ** k)
+    assert abs(ys[-1] - want).max() <= 1e-10 * abs(want).max()
 
 
 def test_ex5_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
