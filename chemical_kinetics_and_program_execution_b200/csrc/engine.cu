@@ -39,6 +39,12 @@ void dfree(T*& p, cudaStream_t st) {
   if (p) cudaFreeAsync((void*)p, st);
   p = nullptr;
 }
+template <typename T>
+T* dkeep(size_t n) {  // allocations that live as long as the model
+  void* p = nullptr;
+  TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return (T*)p;
+}
 
 struct Consts {
   uint32_t A;
@@ -50,20 +56,18 @@ struct Consts {
 // Build-time frontier: the nodes of one level with everything needed to expand them.
 struct Frontier {
   uint64_t n = 0;
-  uint32_t n_plain = 0;
-  uint32_t* io = nullptr;
-  uint32_t* ia = nullptr;
-  uint32_t* seed = nullptr;
-  uint8_t* meta = nullptr;
-  uint8_t* flags = nullptr;
+  uint32_t* io = nullptr;    // original window index
+  uint32_t* ia = nullptr;    // adjusted window index
+  uint32_t* seed = nullptr;  // which (leaf world, tape) the node descends from
+  uint8_t* meta = nullptr;   // kind << 6 | window length
+  uint8_t* flags = nullptr;  // FL_*
 };
 
 // ---------------------------------------------------------------------------------------------
 // Expansion pass 1: classify every frontier node and hash-insert right-chain prefixes.
 // ---------------------------------------------------------------------------------------------
 __global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __restrict__ lflag,
-                                uint32_t* __restrict__ rflag, uint32_t* __restrict__ tflag,
-                                uint8_t* __restrict__ kflag) {
+                                uint32_t* __restrict__ tflag, uint8_t* __restrict__ kflag) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < f.n;
   bool haskey = false;
@@ -71,23 +75,20 @@ __global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __re
   uint32_t pa = 0;
   if (valid) {
     const uint8_t meta = f.meta[i], fl = f.flags[i];
-    const int kind = meta >> 6, len = meta & 63;
+    const int len = meta & 63;
     const uint32_t io = f.io[i], ia = f.ia[i];
-    uint32_t left = 0, right = 0;
-    if (kind == NODE_SUM) {
-      right = 1;                                      // tm.scm:1310-1322
-    } else if (fl & FL_LEFT) {
+    uint32_t left = 0;
+    if (fl & FL_LEFT) {
       if (len < c.k) left = 1;                        // tm.scm:1340-1357
       else if (io / c.A != ia / c.A) left = 1;        // tm.scm:1358-1379, entry test 1331
     }
-    if (kind != NODE_SUM && (fl & FL_RIGHT)) {        // tm.scm:1393-1397 / 1319-1322
+    if (fl & FL_RIGHT) {                              // tm.scm:1393-1397 / 1319-1322
       const uint32_t po = io % c.M;
       pa = ia % c.M;
       haskey = po != pa;                              // tm.scm:1308-1309
       key = ((uint64_t)f.seed[i] << 32) | po;
     }
     lflag[i] = left;
-    rflag[i] = right;
     tflag[i] = (fl & FL_TERM) ? 1u : 0u;
     kflag[i] = haskey ? 1 : 0;
   }
@@ -118,18 +119,17 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Expansion pass 2: write the children, the flux edges and the SUM ranks.  Children are laid out
-// so that consecutive nodes have consecutive table indices on every later evaluation: a left
+// Expansion pass 2: write the left children, the parent records the per-step evaluation reads,
+// the flux edges, and the prefix-group rank of every node that feeds the right chain.  A left
 // extension adds the MOST significant digit, so left children are stored digit-major
-// (x * n_left_parents + parent rank); a right extension adds the LEAST significant digit, so
-// right children are stored parent-major (parent rank * A + x) behind them.
+// (x * n_left_parents + parent rank): consecutive nodes then have consecutive table indices.
 // ---------------------------------------------------------------------------------------------
 __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ lflag,
-                            const uint32_t* __restrict__ rflag, const uint32_t* __restrict__ tflag,
-                            const uint8_t* __restrict__ kflag, const uint64_t* __restrict__ lrank,
-                            const uint64_t* __restrict__ rrank, const uint64_t* __restrict__ trank,
+                            const uint32_t* __restrict__ tflag, const uint8_t* __restrict__ kflag,
+                            const uint64_t* __restrict__ lrank, const uint64_t* __restrict__ trank,
                             uint64_t n_left_parents, const uint64_t* __restrict__ sorted_keys,
-                            uint32_t n_keys, Frontier next, uint32_t* __restrict__ next_parent,
+                            uint32_t n_keys, Frontier next, uint32_t* __restrict__ lp_gid,
+                            uint32_t* __restrict__ lp_io, uint8_t* __restrict__ lp_len,
                             uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
                             uint32_t* __restrict__ keyrank) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,32 +138,24 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
   const int len = meta & 63;
   const uint32_t io = f.io[i], ia = f.ia[i], seed = f.seed[i];
   const uint32_t gid = (uint32_t)(cur_base + i);
-  if (rflag[i]) {                      // right extension of a prefix: prefix * A + x
-    const uint64_t first = (uint64_t)c.A * n_left_parents + rrank[i] * c.A;
-    const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
-    for (uint32_t x = 0; x < c.A; ++x) {
-      const uint64_t ci = first + x;
-      next.io[ci] = io * c.A + x;
-      next.ia[ci] = ia * c.A + x;
-      next.seed[ci] = seed;
-      next.meta[ci] = nmeta;
-      next.flags[ci] = FL_TERM | FL_RIGHT;
-      next_parent[ci] = gid;
-    }
-  } else if (lflag[i]) {
+  if (lflag[i]) {
     const uint64_t r = lrank[i];
     uint32_t bo, ba, step;
-    uint8_t nmeta, nfl;
+    int nl;
+    uint8_t nfl;
     if (len < c.k) {                   // left extension: x * A^len + index
       bo = io; ba = ia; step = c.pw[len];
-      const int nl = len + 1;
-      nmeta = (uint8_t)((NODE_LEFT << 6) | nl);
+      nl = len + 1;
       nfl = FL_LEFT | (nl == c.k ? FL_TERM : 0) | (nl == c.k - 1 ? FL_RIGHT : 0);
     } else {                           // left shift of a full window: x * A^(k-1) + index / A
       bo = io / c.A; ba = ia / c.A; step = c.M;
-      nmeta = (uint8_t)((NODE_LEFT << 6) | c.k);
+      nl = c.k;
       nfl = FL_TERM | FL_LEFT;
     }
+    lp_gid[r] = gid;
+    lp_io[r] = bo;
+    lp_len[r] = (uint8_t)nl;
+    const uint8_t nmeta = (uint8_t)((NODE_LEFT << 6) | nl);
     for (uint32_t x = 0; x < c.A; ++x) {
       const uint64_t ci = (uint64_t)x * n_left_parents + r;
       next.io[ci] = bo + x * step;
@@ -171,7 +163,6 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
       next.seed[ci] = seed;
       next.meta[ci] = nmeta;
       next.flags[ci] = nfl;
-      next_parent[ci] = gid;
     }
   }
   if (tflag[i]) {
@@ -187,17 +178,24 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
   }
 }
 
-__global__ void sum_nodes_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs,
-                                 Consts c, Frontier next, uint64_t first) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_keys) return;
-  const uint64_t key = sorted_keys[r];
-  const uint64_t idx = first + r;
-  next.io[idx] = (uint32_t)key;
-  next.ia[idx] = hash_lookup(hs, key);
-  next.seed[idx] = (uint32_t)(key >> 32);
-  next.meta[idx] = (uint8_t)((NODE_SUM << 6) | (c.k - 1));
-  next.flags[idx] = 0;
+// The A right children of every prefix group (tm.scm:1310-1322), group-major so that consecutive
+// nodes read consecutive entries of p.
+__global__ void emit_groups_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs,
+                                   Consts c, Frontier next, uint64_t first, uint32_t* __restrict__ g_prefix) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_keys) return;
+  const uint64_t key = sorted_keys[g];
+  const uint32_t po = (uint32_t)key, pa = hash_lookup(hs, key), seed = (uint32_t)(key >> 32);
+  g_prefix[g] = po;
+  const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
+  for (uint32_t x = 0; x < c.A; ++x) {
+    const uint64_t ci = first + (uint64_t)g * c.A + x;
+    next.io[ci] = po * c.A + x;
+    next.ia[ci] = pa * c.A + x;
+    next.seed[ci] = seed;
+    next.meta[ci] = nmeta;
+    next.flags[ci] = FL_TERM | FL_RIGHT;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -312,42 +310,63 @@ __global__ void rule_weight_kernel(Tables t, uint32_t n_rules, const uint32_t* _
   rule_w[r] = w;
 }
 
-__device__ __forceinline__ double relative(double p_long, double p_short) {  // tm.scm:1263-1269
-  if (p_long == 0.0) return 0.0;
-  return p_long / fmax(p_long, p_short);
+__global__ void root_kernel(const uint32_t* __restrict__ root_rule, uint32_t n_roots,
+                            const double* __restrict__ rule_w, double* __restrict__ w) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_roots) w[i] = rule_w[root_rule[i]];
 }
 
-// One level of the forest: w[node] = w[parent] * relative(...), pruned when the ratio is not > 0
-// (tm.scm:1316, 1350, 1373); SUM nodes add up their parents in ascending id order.
-__global__ void level_kernel(Tables t, Consts c, Level lv, const double* __restrict__ rule_w,
-                             double* __restrict__ w) {
-  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < lv.n_plain) {
-    const uint8_t meta = lv.meta[i];
-    const int kind = meta >> 6, len = meta & 63;
-    const uint32_t io = lv.io[i], par = lv.parent[i];
-    double out;
-    if (kind == NODE_ROOT) {
-      out = rule_w[par];
-    } else {
-      const double wp = w[par];
-      double p_long, p_short;
-      if (kind == NODE_LEFT) {
-        p_long = table(t, len)[io];
-        p_short = table(t, len - 1)[io % c.pw[len - 1]];
-      } else {
-        p_long = t.p[io];
-        p_short = table(t, c.k - 1)[io / c.A];
-      }
-      const double r = relative(p_long, p_short);
-      out = r > 0.0 ? wp * r : 0.0;
+// w_child = w_parent * ratio, pruned when the ratio is not > 0 (tm.scm:1316, 1350, 1373).
+__device__ __forceinline__ double child_weight(double w_parent, double p_long, double p_short) {
+  if (p_long == 0.0) return 0.0;                       // tm.scm:1266
+  const double r = p_long / fmax(p_long, p_short);     // tm.scm:1267-1269
+  return r > 0.0 ? w_parent * r : 0.0;
+}
+
+// One level of the forest.  Blocks [0, left_blocks) evaluate the children of the left parents,
+// one parent per thread (the A children of consecutive parents are consecutive in memory for every
+// digit x).  The remaining blocks evaluate the right children, 32 prefix groups per warp: each
+// lane first adds up one group's parents in ascending id order, then the warp writes the 32 * A
+// children cooperatively so that the reads of p and the writes of w are contiguous.
+__global__ void __launch_bounds__(kThreads) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
+                                                         double* __restrict__ w) {
+  if (blockIdx.x < left_blocks) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= lv.n_left) return;
+    const int len = lv.lp_len[r];
+    const uint32_t bo = lv.lp_io[r];
+    const double wp = w[lv.lp_gid[r]];
+    const double* tl = table(t, len);
+    const double p_short = table(t, len - 1)[bo];
+    const uint32_t step = c.pw[len - 1];
+    double* out = w + lv.base + r;
+    for (uint32_t x = 0; x < c.A; ++x)
+      out[(uint64_t)x * lv.n_left] = child_weight(wp, tl[bo + x * step], p_short);
+  } else {
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x - left_blocks) * (kThreads / 32) + (threadIdx.x >> 5);
+    const uint64_t g0 = (uint64_t)warp * 32;
+    if (g0 >= lv.n_groups) return;
+    const uint64_t g = g0 + lane;
+    double total = 0.0, p_short = 0.0;
+    uint32_t prefix = 0;
+    if (g < lv.n_groups) {
+      const uint64_t lo = lv.g_ptr[g], hi = lv.g_ptr[g + 1];
+      for (uint64_t e = lo; e < hi; ++e) total += w[lv.g_parents[e]];
+      prefix = lv.g_prefix[g];
+      p_short = table(t, c.k - 1)[prefix];
     }
-    w[lv.base + i] = out;
-  } else if (i < (uint64_t)lv.n_plain + lv.n_sum) {
-    const uint64_t s = i - lv.n_plain;
-    double total = 0.0;
-    for (uint64_t e = lv.sum_ptr[s]; e < lv.sum_ptr[s + 1]; ++e) total += w[lv.sum_parents[e]];
-    w[lv.base + i] = total;
+    const uint32_t groups_here = (uint32_t)min((uint64_t)32, (uint64_t)lv.n_groups - g0);
+    const uint32_t children = groups_here * c.A;
+    double* out = w + lv.base + (uint64_t)c.A * lv.n_left + g0 * c.A;
+    for (uint32_t j = lane; j < ((children + 31) & ~31u); j += 32) {
+      const uint32_t gl = j < children ? j / c.A : 0;
+      const uint32_t x = j - gl * c.A;
+      const double wp = __shfl_sync(0xffffffffu, total, gl);
+      const double ps = __shfl_sync(0xffffffffu, p_short, gl);
+      const uint32_t pre = __shfl_sync(0xffffffffu, prefix, gl);
+      if (j < children) out[j] = child_weight(wp, t.p[(uint64_t)pre * c.A + x], ps);
+    }
   }
 }
 
@@ -398,6 +417,15 @@ struct HostRoot {
   uint8_t meta, flags;
 };
 
+Consts make_consts(const Model& m) {
+  Consts c;
+  c.A = (uint32_t)m.A;
+  c.k = m.k;
+  c.M = (uint32_t)m.pow_a[m.k - 1];
+  for (int i = 0; i < 33; ++i) c.pw[i] = i < m.k ? (uint32_t)m.pow_a[i] : 0u;
+  return c;
+}
+
 }  // namespace
 
 Model::~Model() {
@@ -405,7 +433,9 @@ Model::~Model() {
   if (st) cudaStreamSynchronize(st);
   auto fr = [&](auto*& p) { if (p) { cudaFree((void*)p); p = nullptr; } };
   fr(rule_ptr); fr(step_kind); fr(step_len); fr(step_long); fr(step_short); fr(step_prob); fr(rule_w);
-  for (Level& lv : levels) { fr(lv.io); fr(lv.parent); fr(lv.meta); fr(lv.sum_ptr); fr(lv.sum_parents); }
+  for (Level& lv : levels) {
+    fr(lv.root_rule); fr(lv.lp_gid); fr(lv.lp_io); fr(lv.lp_len); fr(lv.g_prefix); fr(lv.g_ptr); fr(lv.g_parents);
+  }
   fr(node_w); fr(row_ptr); fr(entries); fr(marg); fr(d_marg_off); fr(d_in); fr(d_out);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
@@ -437,11 +467,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
 
-  Consts c;
-  c.A = (uint32_t)m.A;
-  c.k = m.k;
-  c.M = (uint32_t)m.pow_a[m.k - 1];
-  for (int i = 0; i < 33; ++i) c.pw[i] = i < m.k ? (uint32_t)m.pow_a[i] : 0u;
+  const Consts c = make_consts(m);
   const uint64_t W = m.n_states, M = m.pow_a[m.k - 1];
 
   m.stats.worlds_walked = table.worlds_walked;
@@ -462,14 +488,14 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     }
     m.n_rules = (uint32_t)table.rules.size();
     auto up = [&](auto*& dptr, const auto& h) {
-      typedef typename std::remove_reference<decltype(h[0])>::type T;
-      TAPES_CUDA_CHECK(cudaMalloc((void**)&dptr, std::max<size_t>(h.size(), 1) * sizeof(T)));
+      typedef typename std::remove_const<typename std::remove_reference<decltype(h[0])>::type>::type T;
+      dptr = dkeep<T>(h.size());
       if (!h.empty())
         TAPES_CUDA_CHECK(cudaMemcpyAsync((void*)dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
     };
     up(m.rule_ptr, ptr); up(m.step_kind, kind); up(m.step_len, len);
     up(m.step_long, ilong); up(m.step_short, ishort); up(m.step_prob, prob);
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.rule_w, std::max<size_t>(m.n_rules, 1) * sizeof(double)));
+    m.rule_w = dkeep<double>(m.n_rules);
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   }
 
@@ -512,8 +538,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
 
   Frontier cur;
   cur.n = roots.size();
-  cur.n_plain = (uint32_t)roots.size();
-  uint32_t* cur_parent = nullptr;
+  Level cur_level;
+  cur_level.base = 0;
+  cur_level.n_roots = (uint32_t)roots.size();
   if (cur.n) {
     std::vector<uint32_t> h_io(cur.n), h_ia(cur.n), h_seed(cur.n), h_rule(cur.n);
     std::vector<uint8_t> h_meta(cur.n), h_fl(cur.n);
@@ -521,23 +548,17 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       h_io[i] = roots[i].io; h_ia[i] = roots[i].ia; h_seed[i] = roots[i].seed; h_rule[i] = roots[i].rule;
       h_meta[i] = roots[i].meta; h_fl[i] = roots[i].flags;
     }
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&cur.io, cur.n * 4));
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&cur_parent, cur.n * 4));
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&cur.meta, cur.n));
-    cur.ia = dalloc<uint32_t>(cur.n, st); cur.seed = dalloc<uint32_t>(cur.n, st); cur.flags = dalloc<uint8_t>(cur.n, st);
+    cur_level.root_rule = dkeep<uint32_t>(cur.n);
+    cur.io = dalloc<uint32_t>(cur.n, st); cur.ia = dalloc<uint32_t>(cur.n, st);
+    cur.seed = dalloc<uint32_t>(cur.n, st); cur.meta = dalloc<uint8_t>(cur.n, st); cur.flags = dalloc<uint8_t>(cur.n, st);
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.io, h_io.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.ia, h_ia.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.seed, h_seed.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur_parent, h_rule.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(cur_level.root_rule, h_rule.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.meta, h_meta.data(), cur.n, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.flags, h_fl.data(), cur.n, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   }
-  Level cur_level;
-  cur_level.base = 0;
-  cur_level.n_plain = cur.n_plain;
-  cur_level.n_sum = 0;
-  cur_level.io = cur.io; cur_level.parent = cur_parent; cur_level.meta = cur.meta;
 
   uint64_t seed_bits = 0;
   while ((1ull << seed_bits) < std::max<uint64_t>(n_seeds, 1)) ++seed_bits;
@@ -551,7 +572,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     if (cur_level.base + cur.n >= 0x7fffffffull) throw std::runtime_error("extension forest exceeds 2^31 nodes");
     m.stats.levels++;
     const uint64_t n = cur.n;
-    // pass 1
+    // pass 1: classify + hash-dedup of the right-chain prefixes
     uint64_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
     HashSet hs;
@@ -560,100 +581,96 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     hs.mask = cap - 1;
     TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
     uint32_t* lflag = dalloc<uint32_t>(n, st);
-    uint32_t* rflag = dalloc<uint32_t>(n, st);
     uint32_t* tflag = dalloc<uint32_t>(n, st);
     uint8_t* kflag = dalloc<uint8_t>(n, st);
-    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, rflag, tflag, kflag);
+    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, tflag, kflag);
     uint64_t* lrank = dalloc<uint64_t>(n + 1, st);
-    uint64_t* rrank = dalloc<uint64_t>(n + 1, st);
     uint64_t* trank = dalloc<uint64_t>(n + 1, st);
     uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(std::max<uint64_t>(cap, 256ull * 1184)), st);
     exclusive_scan_u32(lflag, n, lrank, scan_tmp, st);
-    exclusive_scan_u32(rflag, n, rrank, scan_tmp, st);
     exclusive_scan_u32(tflag, n, trank, scan_tmp, st);
     uint32_t* sflag = dalloc<uint32_t>(cap, st);
     uint64_t* srank = dalloc<uint64_t>(cap + 1, st);
     slot_flag_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, sflag);
     exclusive_scan_u32(sflag, cap, srank, scan_tmp, st);
-    uint64_t h_tot[4];
+    uint64_t h_tot[3];
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], lrank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], trank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], srank + cap, 8, cudaMemcpyDeviceToHost, st));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[3], rrank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-    const uint64_t NL = h_tot[0], NT = h_tot[1], NS = h_tot[2], NR = h_tot[3];
-    const uint64_t NC = NL + NR;
-    if (NS >= 0xffffffffull || NC * (uint64_t)m.A >= 0xffffffffull) throw std::runtime_error("level too large");
+    const uint64_t NL = h_tot[0], NT = h_tot[1], NG = h_tot[2];
+    if ((NL + NG) * (uint64_t)m.A >= 0xffffffffull) throw std::runtime_error("level too large");
 
     // unique right-chain prefixes in canonical (seed, prefix) order
-    uint64_t* keys_a = dalloc<uint64_t>(NS, st);
-    uint64_t* keys_b = dalloc<uint64_t>(NS, st);
+    uint64_t* keys_a = dalloc<uint64_t>(NG, st);
+    uint64_t* keys_b = dalloc<uint64_t>(NG, st);
     uint64_t* sorted = keys_a;
-    if (NS) {
+    if (NG) {
       slot_gather_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, srank, keys_a);
-      const RadixPlan plan = radix_plan(NS);
+      const RadixPlan plan = radix_plan(NG);
       uint32_t* rh = dalloc<uint32_t>(256ull * plan.blocks, st);
       uint64_t* ro = dalloc<uint64_t>(256ull * plan.blocks + 1, st);
-      sorted = radix_sort_u64(keys_a, keys_b, NS, significant, rh, ro, scan_tmp, st);
+      sorted = radix_sort_u64(keys_a, keys_b, NG, significant, rh, ro, scan_tmp, st);
       dfree(rh, st); dfree(ro, st);
     }
     dfree(sflag, st); dfree(srank, st);
 
-    // pass 2
+    // pass 2: children, parent records, flux edges
     Frontier next;
-    next.n_plain = (uint32_t)(NC * (uint64_t)m.A);
-    next.n = (uint64_t)next.n_plain + NS;
-    uint32_t* next_parent = nullptr;
+    next.n = (NL + NG) * (uint64_t)m.A;
+    Level next_level;
+    next_level.base = cur_level.base + n;
+    next_level.n_left = (uint32_t)NL;
+    next_level.n_groups = (uint32_t)NG;
     if (next.n) {
-      TAPES_CUDA_CHECK(cudaMalloc((void**)&next.io, next.n * 4));
-      TAPES_CUDA_CHECK(cudaMalloc((void**)&next.meta, next.n));
-      TAPES_CUDA_CHECK(cudaMalloc((void**)&next_parent, std::max<uint64_t>(next.n_plain, 1) * 4));
+      next.io = dalloc<uint32_t>(next.n, st);
       next.ia = dalloc<uint32_t>(next.n, st);
       next.seed = dalloc<uint32_t>(next.n, st);
+      next.meta = dalloc<uint8_t>(next.n, st);
       next.flags = dalloc<uint8_t>(next.n, st);
+    }
+    if (NL) {
+      next_level.lp_gid = dkeep<uint32_t>(NL);
+      next_level.lp_io = dkeep<uint32_t>(NL);
+      next_level.lp_len = dkeep<uint8_t>(NL);
     }
     EdgeChunk ec{nullptr, nullptr, 2 * NT};
     if (NT) { ec.row = dalloc<uint32_t>(2 * NT, st); ec.val = dalloc<uint32_t>(2 * NT, st); }
     uint32_t* keyrank = dalloc<uint32_t>(n, st);
-    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, rflag, tflag, kflag,
-                                                          lrank, rrank, trank, NL, sorted, (uint32_t)NS, next,
-                                                          next_parent, ec.row, ec.val, keyrank);
-    Level next_level;
-    next_level.base = cur_level.base + n;
-    next_level.n_plain = next.n_plain;
-    next_level.n_sum = (uint32_t)NS;
-    next_level.io = next.io; next_level.parent = next_parent; next_level.meta = next.meta;
-    if (NS) {
-      sum_nodes_kernel<<<grid_for(NS, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NS, hs, c, next, next.n_plain);
-      // parent lists of the SUM nodes
-      uint32_t* cnt = dalloc<uint32_t>(NS, st);
-      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NS * 4, st));
+    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, kflag, lrank, trank,
+                                                          NL, sorted, (uint32_t)NG, next, next_level.lp_gid,
+                                                          next_level.lp_io, next_level.lp_len, ec.row, ec.val, keyrank);
+    if (NG) {
+      next_level.g_prefix = dkeep<uint32_t>(NG);
+      emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
+                                                                     NL * (uint64_t)m.A, next_level.g_prefix);
+      // parent lists of the prefix groups
+      uint32_t* cnt = dalloc<uint32_t>(NG, st);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
       group_count_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cnt);
-      TAPES_CUDA_CHECK(cudaMalloc((void**)&next_level.sum_ptr, (NS + 1) * 8));
-      exclusive_scan_u32(cnt, NS, next_level.sum_ptr, scan_tmp, st);
+      next_level.g_ptr = dkeep<uint64_t>(NG + 1);
+      exclusive_scan_u32(cnt, NG, next_level.g_ptr, scan_tmp, st);
       uint64_t n_par = 0;
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(&n_par, next_level.sum_ptr + NS, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&n_par, next_level.g_ptr + NG, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      next_level.n_sum_parents = n_par;
-      TAPES_CUDA_CHECK(cudaMalloc((void**)&next_level.sum_parents, std::max<uint64_t>(n_par, 1) * 4));
-      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NS * 4, st));
+      next_level.n_group_parents = n_par;
+      next_level.g_parents = dkeep<uint32_t>(n_par);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
       group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base,
-                                                                       next_level.sum_ptr, cnt, next_level.sum_parents);
-      group_sort_kernel<<<grid_for(NS, kThreads), kThreads, 0, st>>>(next_level.sum_ptr, NS, next_level.sum_parents);
+                                                                       next_level.g_ptr, cnt, next_level.g_parents);
+      group_sort_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(next_level.g_ptr, NG, next_level.g_parents);
       dfree(cnt, st);
       m.stats.hash_inserts += (int64_t)n_par;
-      m.stats.hash_unique += (int64_t)NS;
+      m.stats.hash_unique += (int64_t)NG;
+      m.stats.sum_nodes += (int64_t)NG;
     }
     TAPES_CUDA_CHECK(cudaGetLastError());
     if (NT) edge_chunks.push_back(ec);
     total_terms += NT;
-    m.stats.sum_nodes += (int64_t)cur_level.n_sum;
 
-    // retire the current frontier; its io/parent/meta live on in the level store
     m.levels.push_back(cur_level);
-    dfree(cur.ia, st); dfree(cur.seed, st); dfree(cur.flags, st);
-    dfree(lflag, st); dfree(rflag, st); dfree(tflag, st); dfree(kflag, st);
-    dfree(lrank, st); dfree(rrank, st); dfree(trank, st);
+    dfree(cur.io, st); dfree(cur.ia, st); dfree(cur.seed, st); dfree(cur.meta, st); dfree(cur.flags, st);
+    dfree(lflag, st); dfree(tflag, st); dfree(kflag, st); dfree(lrank, st); dfree(trank, st);
     dfree(scan_tmp, st); dfree(keys_a, st); dfree(keys_b, st); dfree(keyrank, st);
     dfree(hs.keys, st); dfree(hs.vals, st);
     cur = next;
@@ -674,10 +691,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (const EdgeChunk& ec : edge_chunks)
       group_count_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.n, cnt);
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.row_ptr, (n + 1) * 8));
+    m.row_ptr = dkeep<uint64_t>(n + 1);
     uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(n), st);
     exclusive_scan_u32(cnt, n, m.row_ptr, scan_tmp, st);
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.entries, std::max<uint64_t>(m.nnz, 1) * 4));
+    m.entries = dkeep<uint32_t>(m.nnz);
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (EdgeChunk& ec : edge_chunks) {
       group_fill_vals_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.val, ec.n, m.row_ptr, cnt, m.entries);
@@ -698,11 +715,11 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.marg_total = 0;
   for (int L = 0; L < m.k; ++L) { m.marg_off[L] = m.marg_total; m.marg_total += m.pow_a[L]; }
   m.marg_off[m.k] = m.marg_total;
-  TAPES_CUDA_CHECK(cudaMalloc((void**)&m.marg, std::max<uint64_t>(m.marg_total, 1) * 8));
-  TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_marg_off, 40 * 8));
   for (int L = m.k + 1; L < 40; ++L) m.marg_off[L] = 0;
+  m.marg = dkeep<double>(m.marg_total);
+  m.d_marg_off = dkeep<uint64_t>(40);
   TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_marg_off, m.marg_off, 40 * 8, cudaMemcpyHostToDevice, st));
-  TAPES_CUDA_CHECK(cudaMalloc((void**)&m.node_w, std::max<uint64_t>(m.n_nodes, 1) * 8));
+  m.node_w = dkeep<double>(m.n_nodes);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
   m.launches_per_rhs = rhs_launch_count(m);
@@ -718,23 +735,9 @@ int marginal_tail_top(const Model& m) {
     if (m.pow_a[L] <= kTailEntries) top = L;
   return top;
 }
-}  // namespace
 
-int64_t rhs_launch_count(const Model& m) {
-  int64_t launches = 0;
-  const int top = marginal_tail_top(m);
-  launches += (m.k - 1 - top);          // one kernel per long marginal table
-  if (top >= 0) launches += 1;          // tail tables
-  launches += 1;                        // leaf-world probabilities
-  launches += (int64_t)m.levels.size(); // forest levels
-  launches += 1;                        // S * w
-  return launches;
-}
-
-static void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
-  Consts c;
-  c.A = (uint32_t)m.A; c.k = m.k; c.M = (uint32_t)m.pow_a[m.k - 1];
-  for (int i = 0; i < 33; ++i) c.pw[i] = i < m.k ? (uint32_t)m.pow_a[i] : 0u;
+void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
+  const Consts c = make_consts(m);
   Tables t;
   t.p = d_p; t.marg = m.marg; t.k = m.k;
   for (int i = 0; i < 34; ++i) t.off[i] = i <= m.k ? m.marg_off[i] : 0;
@@ -752,8 +755,13 @@ static void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t 
                                                                 m.step_long, m.step_short, m.step_prob, m.rule_w);
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
   for (const Level& lv : m.levels) {
-    const uint64_t cnt = (uint64_t)lv.n_plain + lv.n_sum;
-    if (cnt) level_kernel<<<grid_for(cnt, kThreads), kThreads, 0, st>>>(t, c, lv, m.rule_w, m.node_w);
+    if (lv.n_roots) {
+      root_kernel<<<grid_for(lv.n_roots, kThreads), kThreads, 0, st>>>(lv.root_rule, lv.n_roots, m.rule_w, m.node_w);
+    } else if (lv.n_left + lv.n_groups) {
+      const unsigned left_blocks = lv.n_left ? grid_for(lv.n_left, kThreads) : 0;
+      const unsigned group_blocks = lv.n_groups ? grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads) : 0;
+      level_kernel<<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, m.node_w);
+    }
   }
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
   const uint64_t threads = m.n_states * (uint64_t)m.spmv_group;
@@ -765,6 +773,19 @@ static void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t 
     default: spmv_kernel<16><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
+int64_t rhs_launch_count(const Model& m) {
+  int64_t launches = 0;
+  const int top = marginal_tail_top(m);
+  launches += (m.k - 1 - top);          // one kernel per long marginal table
+  if (top >= 0) launches += 1;          // tail tables
+  if (m.n_rules) launches += 1;         // leaf-world probabilities
+  for (const Level& lv : m.levels)
+    if (lv.n_roots || lv.n_left + lv.n_groups) launches += 1;
+  launches += 1;                        // S * w
+  return launches;
 }
 
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
@@ -786,8 +807,8 @@ void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_
 void rhs_host(Model& m, const double* h_p, double* h_out) {
   const size_t bytes = (size_t)m.n_states * 8;
   if (!m.d_in) {
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_in, bytes));
-    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_out, bytes));
+    m.d_in = dkeep<double>(m.n_states);
+    m.d_out = dkeep<double>(m.n_states);
   }
   TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
   rhs_device(m, m.d_in, m.d_out, m.stream);

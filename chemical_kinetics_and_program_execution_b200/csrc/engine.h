@@ -13,30 +13,39 @@
 
 namespace tapes {
 
-// Node kinds of the extension forest (stored in the top two bits of the per-node meta byte; the
-// low six bits hold the node's window length).
+// Node kinds of the extension forest (build-time only; the top two bits of a frontier node's
+// meta byte, the low six bits hold the node's window length).
 enum NodeKind : uint8_t {
   NODE_ROOT = 0,   // weight = probability of the leaf world that owns the seed
-  NODE_LEFT = 1,   // left extension / left shift (tm.scm:1340-1379): one parent
-  NODE_RIGHT = 2,  // right extension (tm.scm:1303-1322): parent is a SUM node
-  NODE_SUM = 3,    // sum over the dropped left-context digit of a right-chain prefix
+  NODE_LEFT = 1,   // left extension / left shift (tm.scm:1340-1379)
+  NODE_RIGHT = 2,  // right extension (tm.scm:1303-1322)
 };
 
+// One level of the forest as it is evaluated every step.  Child nodes are implicit: only their
+// parents are stored.
+//   level 0:  n_roots nodes, node i has the weight of flux rule root_rule[i].
+//   level >0: the A children of left parent r are nodes  base + x * n_left + r  (x = new, most
+//             significant digit); the A children of prefix group g are nodes
+//             base + A * n_left + g * A + x  (x = new, least significant digit).
+// A prefix group collects the right-chain nodes of the previous level that share the window
+// prefix the next right extension starts from (the literal recursion visits that prefix once per
+// dropped left-context digit, tm.scm:1319-1322); its children get  sum(parents) * ratio.
 struct Level {
-  uint64_t base = 0;       // global id of the level's first node
-  uint32_t n_plain = 0;    // ROOT / LEFT / RIGHT nodes, ids base .. base + n_plain - 1
-  uint32_t n_sum = 0;      // SUM nodes, ids base + n_plain ..
-  uint32_t* io = nullptr;       // [n_plain] index of the node's sequence in its marginal table
-  uint32_t* parent = nullptr;   // [n_plain] global id of the parent (ROOT: rule number)
-  uint8_t* meta = nullptr;      // [n_plain] kind << 6 | length
-  uint64_t* sum_ptr = nullptr;      // [n_sum + 1] offsets into sum_parents
-  uint32_t* sum_parents = nullptr;  // global ids, ascending inside each SUM node
-  uint64_t n_sum_parents = 0;
+  uint64_t base = 0;
+  uint32_t n_roots = 0, n_left = 0, n_groups = 0;
+  uint32_t* root_rule = nullptr;  // [n_roots]
+  uint32_t* lp_gid = nullptr;     // [n_left] global id of the parent node
+  uint32_t* lp_io = nullptr;      // [n_left] table index shared by the children (before adding x)
+  uint8_t* lp_len = nullptr;      // [n_left] window length of the children
+  uint32_t* g_prefix = nullptr;   // [n_groups] (k-1)-digit window prefix
+  uint64_t* g_ptr = nullptr;      // [n_groups + 1] offsets into g_parents
+  uint32_t* g_parents = nullptr;  // parent node ids, ascending inside each group
+  uint64_t n_group_parents = 0;
 };
 
 struct BuildStats {
   int64_t worlds_walked = 0, leaf_worlds = 0, flux_rules = 0, seeds = 0;
-  int64_t nodes = 0, sum_nodes = 0, terms = 0, levels = 0;
+  int64_t nodes = 0, sum_nodes = 0, terms = 0, levels = 0;  // sum_nodes = prefix groups
   int64_t hash_inserts = 0, hash_unique = 0;
   double host_enumerate_ms = 0, device_expand_ms = 0, device_csr_ms = 0;
 };
