@@ -39,7 +39,7 @@ UNIT = 'GB/s'
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--steps', type=int, default=50)
   ap.add_argument('--warmup', type=int, default=3)
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--size-a', type=int, default=10)
@@ -70,31 +70,56 @@ def measured_peak():
 
 
 class ClockSampler:
-  """Samples nvidia-smi clocks and throttle reasons while the timed region runs."""
-  QUERY = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
-           'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-           'clocks_event_reasons.sw_power_cap')
+  """Samples SM clocks and throttle reasons through NVML every 20 ms while the timed region runs
+  (the same counters as `nvidia-smi --query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.*`)."""
 
   def __init__(self, index):
     self.index = index
     self.samples = []
     self.stop = threading.Event()
     self.thread = threading.Thread(target=self._run, daemon=True)
+    self.max_mhz = None
+    self.error = None
 
   def _run(self):
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      visible = os.environ.get('CUDA_VISIBLE_DEVICES')
+      phys = int(visible.split(',')[self.index]) if visible and visible.split(',')[self.index].isdigit() else self.index
+      h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+      get_reasons = getattr(pynvml, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+          pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+      while not self.stop.is_set():
+        self.samples.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), int(get_reasons(h))))
+        self.stop.wait(0.02)
+    except Exception as ex:  # NVML binding unavailable: fall back to polling nvidia-smi
+      self.error = repr(ex)
+      self._run_smi()
+
+  def _run_smi(self):
+    query = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+    bits = [0x8, 0x40, 0x20, 0x4]
     while not self.stop.is_set():
       try:
-        out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.QUERY}',
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={query}',
                               '--format=csv,noheader,nounits'], capture_output=True, text=True,
                              timeout=5).stdout.strip()
-        if out:
-          self.samples.append([x.strip() for x in out.split(',')])
+        f = [x.strip() for x in out.split(',')]
+        if len(f) >= 6 and f[0].isdigit():
+          self.max_mhz = int(f[1])
+          mask = sum(b for b, v in zip(bits, f[2:6]) if v.lower().startswith('active'))
+          self.samples.append((int(f[0]), mask))
       except Exception:
         pass
-      self.stop.wait(0.2)
+      self.stop.wait(0.1)
 
   def __enter__(self):
     self.thread.start()
+    time.sleep(0.05)
     return self
 
   def __exit__(self, *exc):
@@ -102,13 +127,17 @@ class ClockSampler:
     self.thread.join(timeout=10)
 
   def summary(self):
-    sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-    mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-    reasons = sorted({names[i] for s in self.samples for i in range(4)
-                      if len(s) >= 6 and s[2 + i].lower().startswith('active')})
-    return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=(max(mx) if mx else None),
-                reasons=reasons, samples=len(self.samples))
+    # NVML clocks-event-reason bits
+    bits = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+    sm = sorted(s[0] for s in self.samples)
+    seen = 0
+    for s in self.samples:
+      seen |= s[1]
+    out = dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=self.max_mhz,
+               reasons=sorted(name for bit, name in bits.items() if seen & bit), samples=len(self.samples))
+    if self.error:
+      out['error'] = self.error
+    return out
 
 
 def make_workload(args, world, rank):
