@@ -72,17 +72,22 @@ def load():
   lib.tapes_export_node_weights.argtypes = [vp, vp]
   lib.tapes_rule_table.restype = i64
   lib.tapes_rule_table.argtypes = [ctypes.c_char_p, i64] + [vp] * 11
-  if hasattr(lib, 'tapes_dop853_create'):
-    lib.tapes_dop853_create.restype = vp
-    lib.tapes_dop853_create.argtypes = [vp, vp, dbl, dbl, dbl, dbl, dbl]
-    lib.tapes_dop853_destroy.restype = None
-    lib.tapes_dop853_destroy.argtypes = [vp]
-    lib.tapes_dop853_step_to.restype = i32
-    lib.tapes_dop853_step_to.argtypes = [vp, dbl, vp]
-    lib.tapes_dop853_info.restype = i32
-    lib.tapes_dop853_info.argtypes = [vp, vp, i32]
-    lib.tapes_observe.restype = i32
-    lib.tapes_observe.argtypes = [vp, vp, vp, vp, i64, vp]
+  lib.tapes_dop853_create.restype = vp
+  lib.tapes_dop853_create.argtypes = [vp, vp, vp, dbl, dbl, dbl, dbl, dbl, dbl]
+  lib.tapes_dop853_destroy.restype = None
+  lib.tapes_dop853_destroy.argtypes = [vp]
+  lib.tapes_dop853_step.restype = i32
+  lib.tapes_dop853_step.argtypes = [vp]
+  lib.tapes_dop853_dense.restype = i32
+  lib.tapes_dop853_dense.argtypes = [vp, dbl]
+  lib.tapes_dop853_fetch.restype = i32
+  lib.tapes_dop853_fetch.argtypes = [vp, i32, vp]
+  lib.tapes_dop853_observe.restype = i32
+  lib.tapes_dop853_observe.argtypes = [vp, i32, vp, vp, vp, i64, vp]
+  lib.tapes_dop853_info.restype = i32
+  lib.tapes_dop853_info.argtypes = [vp, vp]
+  lib.tapes_observe.restype = i32
+  lib.tapes_observe.argtypes = [vp, vp, vp, vp, vp, i64, vp]
   _lib = lib
   return lib
 

@@ -12,6 +12,7 @@
 
 #include "../../include/tapes_b200.h"
 #include "engine.h"
+#include "integrate.h"
 #include "rules.h"
 
 namespace {
@@ -243,6 +244,94 @@ int tapes_export_node_weights(void* model, double* weights) {
     return 1;
   }
   return 0;
+}
+
+void* tapes_dop853_create(void* model, const double* tableau, const double* y0, double t0, double t_bound,
+                          double rtol, double atol, double max_step, double first_step) {
+  if (!model) { fail("null model"); return nullptr; }
+  try {
+    tapes::Dop853Tableau tab;
+    const double* p = tableau;
+    std::memcpy(tab.A, p, sizeof(tab.A)); p += 256;
+    std::memcpy(tab.B, p, sizeof(tab.B)); p += 12;
+    std::memcpy(tab.C, p, sizeof(tab.C)); p += 16;
+    std::memcpy(tab.E3, p, sizeof(tab.E3)); p += 13;
+    std::memcpy(tab.E5, p, sizeof(tab.E5)); p += 13;
+    std::memcpy(tab.D, p, sizeof(tab.D));
+    return (void*)tapes::dop853_create(*(tapes::Model*)model, tab, y0, t0, t_bound, rtol, atol, max_step, first_step);
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return nullptr;
+  }
+}
+
+void tapes_dop853_destroy(void* solver) { tapes::dop853_destroy((tapes::Dop853*)solver); }
+
+int tapes_dop853_step(void* solver) {
+  if (!solver) { fail("null solver"); return -2; }
+  try {
+    return tapes::dop853_step((tapes::Dop853*)solver);
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return -2;
+  }
+}
+
+int tapes_dop853_dense(void* solver, double t) {
+  if (!solver) { fail("null solver"); return 1; }
+  try {
+    tapes::Dop853* s = (tapes::Dop853*)solver;
+    tapes::dop853_dense_eval(s, t, tapes::dop853_dense_buffer(s));
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_dop853_fetch(void* solver, int which, double* out) {
+  if (!solver) { fail("null solver"); return 1; }
+  tapes::Dop853* s = (tapes::Dop853*)solver;
+  const double* src = which == 0 ? tapes::dop853_state(s) : tapes::dop853_dense_buffer(s);
+  tapes::Model& m = tapes::dop853_model(s);
+  if (cudaMemcpyAsync(out, src, m.n_states * 8, cudaMemcpyDeviceToHost, m.stream) != cudaSuccess ||
+      cudaStreamSynchronize(m.stream) != cudaSuccess) {
+    fail("dop853_fetch: copy failed");
+    return 1;
+  }
+  return 0;
+}
+
+int tapes_dop853_observe(void* solver, int which, const int64_t* offset, const int64_t* stride,
+                         const int64_t* count, int64_t n_obs, double* out) {
+  if (!solver) { fail("null solver"); return 1; }
+  try {
+    tapes::Dop853* s = (tapes::Dop853*)solver;
+    const double* src = which == 0 ? tapes::dop853_state(s) : tapes::dop853_dense_buffer(s);
+    tapes::observe_strided(tapes::dop853_model(s), src, offset, stride, count, n_obs, out);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_dop853_info(void* solver, double* out6) {
+  if (!solver) { fail("null solver"); return 1; }
+  tapes::dop853_info((tapes::Dop853*)solver, out6);
+  return 0;
+}
+
+int tapes_observe(void* model, const double* d_y, const int64_t* offset, const int64_t* stride,
+                  const int64_t* count, int64_t n_obs, double* out) {
+  if (!model) { fail("null model"); return 1; }
+  try {
+    tapes::observe_strided(*(tapes::Model*)model, d_y, offset, stride, count, n_obs, out);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
 }
 
 int64_t tapes_rule_table(const char* tag, int64_t cl_k, int64_t* n_steps, int64_t* rule_ptr,

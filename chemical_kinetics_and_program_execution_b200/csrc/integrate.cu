@@ -1,0 +1,403 @@
+// Device-resident DOP853 (see integrate.h).  All vector work is elementwise fp64 streaming, bound
+// by HBM bandwidth; reductions use a fixed two-pass order so that step sizes are reproducible.
+#include "integrate.h"
+
+#include <cmath>
+#include <limits>
+#include <vector>
+
+#include "cuda_check.h"
+
+namespace tapes {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kReduceBlocks = 1184;  // 8 x 148 SMs
+
+struct Terms {  // a linear combination  sum_j coef[j] * vec[j]
+  int n = 0;
+  double coef[16];
+  const double* vec[16];
+};
+
+// out = y + (sum_j coef_j * K_j) * h        (rk_step: dy = np.dot(K[:s].T, a[:s]) * h)
+__global__ void lincomb_kernel(double* __restrict__ out, const double* __restrict__ y, Terms t, double h,
+                               uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < t.n; ++j) acc += t.vec[j][i] * t.coef[j];
+  out[i] = y[i] + acc * h;
+}
+
+// out = (sum_j coef_j * K_j) * h            (F[3:] = h * np.dot(D, K))
+__global__ void scaled_sum_kernel(double* __restrict__ out, Terms t, double h, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double acc = 0.0;
+#pragma unroll 4
+  for (int j = 0; j < t.n; ++j) acc += t.vec[j][i] * t.coef[j];
+  out[i] = h * acc;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    r = lane < (int)(blockDim.x >> 5) ? smem[lane] : 0.0;
+    for (int d = 16; d > 0; d >>= 1) r += __shfl_down_sync(0xffffffffu, r, d);
+  }
+  __syncthreads();
+  return r;  // valid in thread 0
+}
+
+// partial[b] = sum (err5/scale)^2, partial[B + b] = sum (err3/scale)^2 over the block's elements,
+// scale = atol + max(|y|, |y_new|) * rtol   (RungeKutta._step_impl, DOP853._estimate_error_norm)
+__global__ void error_partials_kernel(Terms e5, Terms e3, const double* __restrict__ y,
+                                      const double* __restrict__ y_new, double rtol, double atol, uint64_t n,
+                                      double* __restrict__ partial) {
+  __shared__ double smem[32];
+  double s5 = 0.0, s3 = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    double a5 = 0.0, a3 = 0.0;
+    for (int j = 0; j < e5.n; ++j) a5 += e5.vec[j][i] * e5.coef[j];
+    for (int j = 0; j < e3.n; ++j) a3 += e3.vec[j][i] * e3.coef[j];
+    const double scale = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+    a5 /= scale; a3 /= scale;
+    s5 += a5 * a5; s3 += a3 * a3;
+  }
+  const double b5 = block_sum(s5, smem);
+  const double b3 = block_sum(s3, smem);
+  if (threadIdx.x == 0) { partial[blockIdx.x] = b5; partial[gridDim.x + blockIdx.x] = b3; }
+}
+
+// partial[b] = sum ((a - b_or_0) / (atol + |y| rtol))^2   (select_initial_step norms)
+__global__ void scaled_norm_partials_kernel(const double* __restrict__ a, const double* __restrict__ b,
+                                            const double* __restrict__ y, double rtol, double atol, uint64_t n,
+                                            double* __restrict__ partial) {
+  __shared__ double smem[32];
+  double s = 0.0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const double v = (a[i] - (b ? b[i] : 0.0)) / (atol + fabs(y[i]) * rtol);
+    s += v * v;
+  }
+  const double r = block_sum(s, smem);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
+}
+
+__global__ void final_sum_kernel(const double* __restrict__ partial, int n_partials, int n_sums,
+                                 double* __restrict__ out) {
+  __shared__ double smem[32];
+  for (int k = 0; k < n_sums; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n_partials; i += blockDim.x) s += partial[k * n_partials + i];
+    const double r = block_sum(s, smem);
+    if (threadIdx.x == 0) out[k] = r;
+  }
+}
+
+// F[0] = y - y_old ; F[1] = h f_old - F[0] ; F[2] = 2 F[0] - h (f + f_old)
+__global__ void dense_head_kernel(double* __restrict__ F0, double* __restrict__ F1, double* __restrict__ F2,
+                                  const double* __restrict__ y, const double* __restrict__ y_old,
+                                  const double* __restrict__ f_old, const double* __restrict__ f, double h,
+                                  uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double delta = y[i] - y_old[i];
+  F0[i] = delta;
+  F1[i] = h * f_old[i] - delta;
+  F2[i] = 2 * delta - h * (f[i] + f_old[i]);
+}
+
+struct SevenVecs { const double* F[7]; };
+
+// Dop853DenseOutput._call_impl for one time point.
+__global__ void dense_eval_kernel(double* __restrict__ out, SevenVecs fv, const double* __restrict__ y_old,
+                                  double x, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double y = 0.0;
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    y += fv.F[6 - r][i];
+    y *= (r % 2 == 0) ? x : (1 - x);
+  }
+  out[i] = y + y_old[i];
+}
+
+__global__ void observe_kernel(const double* __restrict__ y, const int64_t* __restrict__ offset,
+                               const int64_t* __restrict__ stride, const int64_t* __restrict__ count,
+                               double* __restrict__ out) {
+  __shared__ double smem[32];
+  const int o = blockIdx.x;
+  const int64_t off = offset[o], st = stride[o], cnt = count[o];
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) s += y[off + j * st];
+  const double r = block_sum(s, smem);
+  if (threadIdx.x == 0) out[o] = r;
+}
+
+}  // namespace
+
+struct Dop853 {
+  Model* m = nullptr;
+  uint64_t n = 0;
+  cudaStream_t st = nullptr;
+  Dop853Tableau tab;
+  double t = 0, t_old = 0, t_bound = 0, direction = 1, h_abs = 0, h_previous = 0;
+  double rtol = 0, atol = 0, max_step = 0;
+  double* ybuf[3] = {nullptr, nullptr, nullptr};
+  int iy = 0, iy_old = 1, iy_new = 2;
+  double* K[16];
+  double* F[7];
+  bool have_F_mem = false, dense_ready = false, f_in_last = false, have_step = false;
+  double* stage = nullptr;
+  double* partial = nullptr;
+  double* d_sums = nullptr;
+  int64_t nfev = 0, n_accepted = 0, n_rejected = 0;
+  int status = 0;  // 0 running, 1 finished, -1 failed
+
+  double* y() { return ybuf[iy]; }
+  double* y_old() { return ybuf[iy_old]; }
+  double* y_new() { return ybuf[iy_new]; }
+};
+
+namespace {
+
+double* dvec(uint64_t n) {
+  void* p = nullptr;
+  TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<uint64_t>(n, 1) * sizeof(double)));
+  return (double*)p;
+}
+
+void fun(Dop853* s, const double* y, double* out) {
+  rhs_device(*s->m, y, out, s->st);
+  s->nfev++;
+}
+
+Terms terms_of(Dop853* s, const double* coef, int count) {
+  Terms t;
+  for (int j = 0; j < count; ++j)
+    if (coef[j] != 0.0) { t.coef[t.n] = coef[j]; t.vec[t.n] = s->K[j]; ++t.n; }
+  return t;
+}
+
+void read_sums(Dop853* s, int n_sums, double* out) {
+  final_sum_kernel<<<1, 1024, 0, s->st>>>(s->partial, kReduceBlocks, n_sums, s->d_sums);
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(out, s->d_sums, n_sums * sizeof(double), cudaMemcpyDeviceToHost, s->st));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(s->st));
+}
+
+// np.linalg.norm(x / scale) / sqrt(n) of (a - b) against scale(y)
+double rms_norm(Dop853* s, const double* a, const double* b, const double* y) {
+  scaled_norm_partials_kernel<<<kReduceBlocks, kThreads, 0, s->st>>>(a, b, y, s->rtol, s->atol, s->n, s->partial);
+  double sum = 0;
+  read_sums(s, 1, &sum);
+  return std::sqrt(sum) / std::sqrt((double)s->n);
+}
+
+// scipy/integrate/_ivp/common.py: select_initial_step (order = error_estimator_order = 7)
+double select_initial_step(Dop853* s) {
+  const double interval = std::fabs(s->t_bound - s->t);
+  if (interval == 0.0) return 0.0;
+  double* f0 = s->K[0];
+  const double d0 = rms_norm(s, s->y(), nullptr, s->y());
+  const double d1 = rms_norm(s, f0, nullptr, s->y());
+  double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+  h0 = std::min(h0, interval);
+  Terms t;
+  t.n = 1; t.coef[0] = 1.0; t.vec[0] = f0;
+  lincomb_kernel<<<grid_for(s->n, kThreads), kThreads, 0, s->st>>>(s->stage, s->y(), t, h0 * s->direction, s->n);
+  fun(s, s->stage, s->K[1]);
+  const double d2 = rms_norm(s, s->K[1], f0, s->y()) / h0;
+  double h1;
+  if (d1 <= 1e-15 && d2 <= 1e-15) h1 = std::max(1e-6, h0 * 1e-3);
+  else h1 = std::pow(0.01 / std::max(d1, d2), 1.0 / (7 + 1));
+  return std::min(std::min(100 * h0, h1), std::min(interval, s->max_step));
+}
+
+// rk_step + error norm for one attempted step of size h; leaves y_new and K[0..12].
+double attempt(Dop853* s, double h) {
+  const unsigned grid = grid_for(s->n, kThreads);
+  for (int st = 1; st < 12; ++st) {
+    Terms t = terms_of(s, s->tab.A[st], st);
+    lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->stage, s->y(), t, h, s->n);
+    fun(s, s->stage, s->K[st]);
+  }
+  Terms tb = terms_of(s, s->tab.B, 12);
+  lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->y_new(), s->y(), tb, h, s->n);
+  fun(s, s->y_new(), s->K[12]);
+  Terms e5 = terms_of(s, s->tab.E5, 13), e3 = terms_of(s, s->tab.E3, 13);
+  error_partials_kernel<<<kReduceBlocks, kThreads, 0, s->st>>>(e5, e3, s->y(), s->y_new(), s->rtol, s->atol, s->n,
+                                                              s->partial);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+  double sums[2];
+  read_sums(s, 2, sums);
+  const double err5 = sums[0], err3 = sums[1];
+  if (err5 == 0.0 && err3 == 0.0) return 0.0;
+  const double denom = err5 + 0.01 * err3;
+  return std::fabs(h) * err5 / std::sqrt(denom * (double)s->n);
+}
+
+}  // namespace
+
+Dop853* dop853_create(Model& m, const Dop853Tableau& tab, const double* h_y0, double t0, double t_bound,
+                      double rtol, double atol, double max_step, double first_step) {
+  Dop853* s = new Dop853();
+  try {
+    s->m = &m; s->n = m.n_states; s->st = m.stream; s->tab = tab;
+    s->t = t0; s->t_old = t0; s->t_bound = t_bound;
+    s->direction = t_bound != t0 ? (t_bound > t0 ? 1.0 : -1.0) : 1.0;
+    // validate_tol: rtol below 100 eps is raised to it
+    const double eps = std::numeric_limits<double>::epsilon();
+    s->rtol = std::max(rtol, 100 * eps); s->atol = atol;
+    s->max_step = max_step > 0 ? max_step : std::numeric_limits<double>::infinity();
+    for (int i = 0; i < 3; ++i) s->ybuf[i] = dvec(s->n);
+    for (int i = 0; i < 16; ++i) s->K[i] = dvec(s->n);
+    for (int i = 0; i < 7; ++i) s->F[i] = nullptr;
+    s->stage = dvec(s->n);
+    s->partial = dvec(2 * kReduceBlocks);
+    s->d_sums = dvec(4);
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(s->y(), h_y0, s->n * sizeof(double), cudaMemcpyHostToDevice, s->st));
+    fun(s, s->y(), s->K[0]);  // self.f = self.fun(self.t, self.y)
+    s->h_abs = first_step > 0 ? first_step : select_initial_step(s);
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(s->st));
+  } catch (...) {
+    dop853_destroy(s);
+    throw;
+  }
+  return s;
+}
+
+void dop853_destroy(Dop853* s) {
+  if (!s) return;
+  if (s->st) cudaStreamSynchronize(s->st);
+  for (double* p : s->ybuf) if (p) cudaFree(p);
+  for (double* p : s->K) if (p) cudaFree(p);
+  for (double* p : s->F) if (p) cudaFree(p);
+  if (s->stage) cudaFree(s->stage);
+  if (s->partial) cudaFree(s->partial);
+  if (s->d_sums) cudaFree(s->d_sums);
+  delete s;
+}
+
+int dop853_step(Dop853* s) {  // OdeSolver.step + RungeKutta._step_impl
+  if (s->status != 0) return s->status;
+  if (s->n == 0 || s->t == s->t_bound) {
+    s->t_old = s->t; s->t = s->t_bound; s->status = 1;
+    return s->status;
+  }
+  if (s->f_in_last) {  // K[0] = f: the derivative at the new point was the last stage
+    std::swap(s->K[0], s->K[12]);
+    s->f_in_last = false;
+  }
+  const double t = s->t;
+  const double inf = std::numeric_limits<double>::infinity();
+  const double min_step = 10 * std::fabs(std::nextafter(t, s->direction * inf) - t);
+  double h_abs = s->h_abs;
+  if (h_abs > s->max_step) h_abs = s->max_step;
+  else if (h_abs < min_step) h_abs = min_step;
+  bool accepted = false, rejected = false;
+  double h = 0, t_new = t;
+  const double MAX_FACTOR = 10, MIN_FACTOR = 0.2, SAFETY = 0.9, exponent = -1.0 / 8.0;
+  while (!accepted) {
+    if (h_abs < min_step) { s->status = -1; return s->status; }
+    h = h_abs * s->direction;
+    t_new = t + h;
+    if (s->direction * (t_new - s->t_bound) > 0) t_new = s->t_bound;
+    h = t_new - t;
+    h_abs = std::fabs(h);
+    const double err = attempt(s, h);
+    if (err < 1) {
+      double factor = err == 0 ? MAX_FACTOR : std::min(MAX_FACTOR, SAFETY * std::pow(err, exponent));
+      if (rejected) factor = std::min(1.0, factor);
+      h_abs *= factor;
+      accepted = true;
+      s->n_accepted++;
+    } else {
+      h_abs *= std::max(MIN_FACTOR, SAFETY * std::pow(err, exponent));
+      rejected = true;
+      s->n_rejected++;
+    }
+  }
+  s->h_previous = h;
+  // y_old <- y, y <- y_new
+  const int old = s->iy_old;
+  s->iy_old = s->iy; s->iy = s->iy_new; s->iy_new = old;
+  s->t_old = t; s->t = t_new; s->h_abs = h_abs;
+  s->f_in_last = true;
+  s->dense_ready = false;
+  s->have_step = true;
+  if (s->direction * (s->t - s->t_bound) >= 0) s->status = 1;
+  return s->status;
+}
+
+void dop853_dense_eval(Dop853* s, double t, double* d_out) {  // DOP853._dense_output_impl + _call_impl
+  if (!s->have_step) throw std::runtime_error("dense output needs a completed step");
+  const unsigned grid = grid_for(s->n, kThreads);
+  if (!s->dense_ready) {
+    if (!s->have_F_mem) {
+      for (int i = 0; i < 7; ++i) s->F[i] = dvec(s->n);
+      s->have_F_mem = true;
+    }
+    const double h = s->h_previous;
+    for (int st = 13; st < 16; ++st) {
+      Terms tt = terms_of(s, s->tab.A[st], st);
+      lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->stage, s->y_old(), tt, h, s->n);
+      fun(s, s->stage, s->K[st]);
+    }
+    dense_head_kernel<<<grid, kThreads, 0, s->st>>>(s->F[0], s->F[1], s->F[2], s->y(), s->y_old(), s->K[0], s->K[12],
+                                                   h, s->n);
+    for (int r = 0; r < 4; ++r) {
+      Terms td = terms_of(s, s->tab.D[r], 16);
+      scaled_sum_kernel<<<grid, kThreads, 0, s->st>>>(s->F[3 + r], td, h, s->n);
+    }
+    s->dense_ready = true;
+  }
+  SevenVecs fv;
+  for (int i = 0; i < 7; ++i) fv.F[i] = s->F[i];
+  const double x = (t - s->t_old) / s->h_previous;
+  dense_eval_kernel<<<grid, kThreads, 0, s->st>>>(d_out, fv, s->y_old(), x, s->n);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+const double* dop853_state(const Dop853* s) { return s->ybuf[s->iy]; }
+double* dop853_dense_buffer(Dop853* s) { return s->stage; }
+Model& dop853_model(Dop853* s) { return *s->m; }
+
+void dop853_info(const Dop853* s, double out[6]) {
+  out[0] = s->t; out[1] = s->t_old; out[2] = s->h_abs;
+  out[3] = (double)s->nfev; out[4] = (double)s->n_accepted; out[5] = (double)s->n_rejected;
+}
+
+void observe_strided(Model& m, const double* d_y, const int64_t* offset, const int64_t* stride,
+                     const int64_t* count, int64_t n_obs, double* h_out) {
+  if (n_obs <= 0) return;
+  int64_t* d_meta = nullptr;
+  double* d_out = nullptr;
+  TAPES_CUDA_CHECK(cudaMalloc((void**)&d_meta, 3 * n_obs * sizeof(int64_t)));
+  TAPES_CUDA_CHECK(cudaMalloc((void**)&d_out, n_obs * sizeof(double)));
+  try {
+    for (int64_t o = 0; o < n_obs; ++o)
+      if (offset[o] < 0 || stride[o] < 1 || count[o] < 0 ||
+          (count[o] > 0 && (uint64_t)(offset[o] + (count[o] - 1) * stride[o]) >= m.n_states))
+        throw std::runtime_error("observable outside the state table");
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(d_meta, offset, n_obs * 8, cudaMemcpyHostToDevice, m.stream));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(d_meta + n_obs, stride, n_obs * 8, cudaMemcpyHostToDevice, m.stream));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(d_meta + 2 * n_obs, count, n_obs * 8, cudaMemcpyHostToDevice, m.stream));
+    observe_kernel<<<(unsigned)n_obs, 1024, 0, m.stream>>>(d_y, d_meta, d_meta + n_obs, d_meta + 2 * n_obs, d_out);
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, n_obs * 8, cudaMemcpyDeviceToHost, m.stream));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+  } catch (...) {
+    cudaFree(d_meta); cudaFree(d_out);
+    throw;
+  }
+  cudaFree(d_meta); cudaFree(d_out);
+}
+
+}  // namespace tapes

@@ -53,6 +53,17 @@ class DeviceModel:
     _lib.check(rc == 0, 'tapes_rhs_profile')
     return ms
 
+  def observe(self, y, seqs):
+    """Sequence probabilities (len(seq) <= k) of a CUDA table, summed on the device."""
+    torch.cuda.current_stream().synchronize()  # the sums run on the model's stream
+    triples = [markov_tapes.sequence_observable(self.info['alphabet'], self.cl_k, s) for s in seqs]
+    cols = [numpy.ascontiguousarray(numpy.array(c, dtype=numpy.int64)) for c in zip(*triples)]
+    out = numpy.zeros(len(seqs), dtype=numpy.float64)
+    rc = markov_tapes.u_lib.tapes_observe(self.handle, y.data_ptr(), cols[0].ctypes.data, cols[1].ctypes.data,
+                                          cols[2].ctypes.data, len(seqs), out.ctypes.data)
+    _lib.check(rc == 0, 'tapes_observe')
+    return out
+
   def csr(self):
     """(row_ptr[int64], entries[uint32]) copied to host."""
     row_ptr = numpy.zeros(self.n_states + 1, dtype=numpy.int64)

@@ -11,7 +11,8 @@ Differences, all documented in INTEGRATION.md:
     MARKOV_TAPES_DEBUG=1;
   * a failed library call raises RuntimeError (the reference drops into a Scheme REPL,
     framework/tapes_py_interface.scm:42-44);
-  * additions: `get_device_dy_dt`, `ode_integrate_device`, `model_stats`, `register_rule_set`.
+  * additions: `ode_integrate_device`, `sequence_observable`, `model_stats`,
+    `register_rule_set`; device-resident dy/dt lives in device.py.
 """
 
 import atexit
@@ -212,6 +213,95 @@ def model_stats(*, tag, cl_k):
   stats = _lib.model_info(model)
   stats.update(_lib.model_timing(model))
   return stats
+
+
+def _dop853_tableau():
+  """SciPy's DOP853 coefficients, flattened in the order tapes_dop853_create expects."""
+  from scipy.integrate._ivp import dop853_coefficients as dc
+  parts = [dc.A, dc.B, dc.C, dc.E3, dc.E5, dc.D]
+  flat = numpy.concatenate([numpy.asarray(x, dtype=numpy.float64).ravel() for x in parts])
+  assert flat.size == 374
+  return numpy.ascontiguousarray(flat)
+
+
+def sequence_observable(size_a, cl_k, seq):
+  """(offset, stride, count) of the strided sum that equals seq_prob(spd, seq) for len(seq) <= k."""
+  if len(seq) > cl_k:
+    raise ValueError('device observables need len(seq) <= cl_k; use seq_prob on fetched states')
+  offset = 0
+  for s in seq:
+    offset = offset * size_a + int(s)
+  return offset, size_a ** len(seq), size_a ** (cl_k - len(seq))
+
+
+def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max_step=numpy.inf,
+                         first_step=None, observables=None, return_states=True, want_stats=False):
+  """DOP853 integration with the table resident in HBM (no per-stage host round trips).
+
+  Follows scipy.integrate.solve_ivp(method='DOP853', t_eval=ts) step for step, so the result
+  matches `ode_integrate_ivp(..., ivp_kwargs=dict(method='DOP853', rtol=..., atol=...))`.
+
+  Returns the states at `ts` shaped like odeint's output ([len(ts), size_a**cl_k]) and/or, when
+  `observables` (a list of symbol sequences, each no longer than cl_k) is given, their
+  probabilities at `ts` ([len(ts), len(observables)]), computed on the device.  With
+  return_states=False only the observables cross the host boundary.
+  """
+  p0 = _checked_p0(p0, size_a, cl_k)
+  ts = numpy.asarray(ts, dtype=numpy.float64)
+  if ts.ndim != 1 or ts.size < 2 or not ((numpy.diff(ts) > 0).all() or (numpy.diff(ts) < 0).all()):
+    raise ValueError('ts must be a strictly monotonic sequence of at least two times')
+  model = u_lib.tapes_model(tag.encode(), cl_k)
+  _lib.check(bool(model), 'tapes_model')
+  tab = _dop853_tableau()
+  solver = u_lib.tapes_dop853_create(model, tab.ctypes.data, numpy.ascontiguousarray(p0).ctypes.data,
+                                     float(ts[0]), float(ts[-1]), float(rtol), float(atol),
+                                     float(max_step) if numpy.isfinite(max_step) else -1.0,
+                                     float(first_step) if first_step else -1.0)
+  _lib.check(bool(solver), 'tapes_dop853_create')
+  n = size_a ** cl_k
+  obs = None
+  if observables is not None:
+    triples = [sequence_observable(size_a, cl_k, seq) for seq in observables]
+    obs = [numpy.ascontiguousarray(numpy.array(col, dtype=numpy.int64)) for col in zip(*triples)]
+  states = numpy.empty((ts.size, n), dtype=numpy.float64) if return_states else None
+  series = numpy.empty((ts.size, len(observables)), dtype=numpy.float64) if obs is not None else None
+  forward = ts[-1] > ts[0]
+  info = numpy.zeros(6, dtype=numpy.float64)
+  try:
+    done = 0  # number of requested times already written
+    status = None
+    while status is None:
+      code = u_lib.tapes_dop853_step(solver)
+      if code == 1:
+        status = 0
+      elif code < 0:
+        _lib.check(code != -2, 'tapes_dop853_step')
+        raise RuntimeError('Required step size is less than spacing between numbers.')
+      u_lib.tapes_dop853_info(solver, info.ctypes.data)
+      t = info[0]
+      # every requested time in (t_old, t], the one equal to t included (solve_ivp's loop)
+      if forward:
+        upto = int(numpy.searchsorted(ts, t, side='right'))
+      else:
+        upto = int(ts.size - numpy.searchsorted(ts[::-1], t, side='left'))
+      for i in range(done, upto):
+        rc = u_lib.tapes_dop853_dense(solver, float(ts[i]))
+        _lib.check(rc == 0, 'tapes_dop853_dense')
+        if states is not None:
+          _lib.check(u_lib.tapes_dop853_fetch(solver, 1, states[i].ctypes.data) == 0, 'tapes_dop853_fetch')
+        if series is not None:
+          rc = u_lib.tapes_dop853_observe(solver, 1, obs[0].ctypes.data, obs[1].ctypes.data,
+                                          obs[2].ctypes.data, len(observables), series[i].ctypes.data)
+          _lib.check(rc == 0, 'tapes_dop853_observe')
+      done = max(done, upto)
+    u_lib.tapes_dop853_info(solver, info.ctypes.data)
+  finally:
+    u_lib.tapes_dop853_destroy(solver)
+  out = tuple(x for x in (states, series) if x is not None)
+  out = out[0] if len(out) == 1 else out
+  if want_stats:
+    return out, dict(nfev=int(info[3]), accepted=int(info[4]), rejected=int(info[5]), t=float(info[0]))
+  return out
 
 
 def _run_validation():

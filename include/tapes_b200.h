@@ -92,6 +92,41 @@ int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries);
 /* Copies the node weights of the most recent right-hand side to host (n_nodes doubles). */
 int tapes_export_node_weights(void* model, double* weights);
 
+/* ---- device-resident time stepping (replaces the SciPy stepper call sites
+ * framework/markov_tapes.py:318 and 349-354 for runs that keep the table in HBM) ------------ */
+
+/* Creates a DOP853 solver that follows scipy.integrate.solve_ivp(method='DOP853') step for step.
+ * tableau: 374 doubles = A[16][16], B[12], C[16], E3[13], E5[13], D[4][16] (row-major; SciPy's
+ * dop853_coefficients).  y0: HOST buffer of n_states doubles.  max_step <= 0 means unbounded,
+ * first_step <= 0 means "select like SciPy".  NULL on failure. */
+void* tapes_dop853_create(void* model, const double* tableau, const double* y0, double t0,
+                          double t_bound, double rtol, double atol, double max_step,
+                          double first_step);
+void tapes_dop853_destroy(void* solver);
+
+/* One solver.step(): 0 running, 1 finished, -1 step size too small, -2 error. */
+int tapes_dop853_step(void* solver);
+
+/* Evaluates the dense output of the last step at time t into the solver's device buffer. */
+int tapes_dop853_dense(void* solver, double t);
+
+/* Copies the current state (which = 0) or the dense-output buffer (which = 1) to a HOST buffer. */
+int tapes_dop853_fetch(void* solver, int which, double* out);
+
+/* Strided sums of the current state (which = 0) or the dense-output buffer (which = 1), computed
+ * on the device: out[o] = sum_{j < count[o]} y[offset[o] + j * stride[o]].  A length-L sequence
+ * probability (framework/markov_tapes.py:190-222) is offset = index(seq), stride = A^L,
+ * count = A^(k-L). */
+int tapes_dop853_observe(void* solver, int which, const int64_t* offset, const int64_t* stride,
+                         const int64_t* count, int64_t n_obs, double* out);
+
+/* t, t_old, h_abs, nfev, accepted steps, rejected steps. */
+int tapes_dop853_info(void* solver, double* out6);
+
+/* Same strided sums for any DEVICE vector of n_states doubles. */
+int tapes_observe(void* model, const double* d_y, const int64_t* offset, const int64_t* stride,
+                  const int64_t* count, int64_t n_obs, double* out);
+
 /* Host-only (no GPU needed): the flux-rule table of (tag, cl_k).  Call with all pointers NULL to
  * get sizes: returns the number of rules and stores the total step count in *n_steps. Arrays:
  * rule_ptr[n_rules + 1]; per step kind, length, long_index, short_index, prob; per rule and tape

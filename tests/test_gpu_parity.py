@@ -227,3 +227,49 @@ def test_ex5_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
   for key, row in (('ex5_t50', 400), ('ex5_end', 4000)):
     want = trajectories[key]
     assert abs(ys[row] - want).max() <= 1e-12 * abs(want).max()
+
+
+def test_device_dop853_matches_scipy_dop853(mt, p0_fixtures):
+  """The HBM-resident stepper against scipy.integrate.solve_ivp(DOP853) driving the same GPU
+  right-hand side: same controller, same step sequence, results within 1e-12."""
+  p0 = dense(p0_fixtures['ex5_idx'], p0_fixtures['ex5_val'], 5 ** 5)
+  ts = numpy.linspace(0, 40.0, 81)
+  kw = dict(rtol=1e-10, atol=1e-12)
+  want = mt.ode_integrate_ivp(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=p0, ts=ts,
+                              ivp_kwargs=dict(method='DOP853', **kw))
+  f = mt.get_dy_dt(tag='ex5-msrtf-machine', size_a=5, cl_k=5)
+  sol = scipy.integrate.solve_ivp(lambda t, y: f(y, t), (ts[0], ts[-1]), p0, t_eval=ts, method='DOP853', **kw)
+  seqs = [[0], [1, 2], [2, 2, 0, 1, 1]]
+  (got, series), stats = mt.ode_integrate_device(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=p0, ts=ts,
+                                                 observables=seqs, want_stats=True, **kw)
+  assert got.shape == want.shape
+  assert stats['nfev'] == sol.nfev
+  assert abs(got - want).max() <= 1e-12 * abs(want).max()
+  for j, seq in enumerate(seqs):
+    ref = mt.seq_prob(got.reshape((len(ts),) + (5,) * 5), seq, num_prefix_indices=1)[0]
+    assert abs(series[:, j] - ref).max() <= 1e-14 * abs(ref).max()
+
+
+def test_device_dop853_reproduces_ex4_reference_end_points(mt, known_answers, p0_fixtures):
+  """examples/ex4_chemical_turing.py:150-170 with the table kept in HBM and only the eight
+  observables read back."""
+  for name in ('a', 'b'):
+    p0 = dense(p0_fixtures[f'ex4_{name}_idx'], p0_fixtures[f'ex4_{name}_val'], 9 ** 5)
+    series = mt.ode_integrate_device(tag='ex4-chemical-turing', size_a=9, cl_k=5, p0=p0,
+                                     ts=numpy.linspace(0, 2000.0, 2001), rtol=1e-13, atol=1e-13,
+                                     observables=known_answers['ex4_observables'], return_states=False)
+    assert series.shape == (2001, 8)
+    for g, w in zip(series[-1], known_answers[f'ex4_p0_{name}_t2000']):
+      assert abs(g - w) <= 1e-12 * abs(w), (name, g, w)
+
+
+def test_device_observables(mt, device):
+  import torch
+  p = configs.markov_table(4, 6, 5)
+  model = device.DeviceModel('ex3-copolymerization', 6)
+  seqs = [[1], [0, 0], [3, 1, 0], [0, 1, 2, 3, 0, 1]]
+  got = model.observe(torch.from_numpy(p).cuda(), seqs)
+  spd = p.reshape([4] * 6)
+  for g, seq in zip(got, seqs):
+    want = mt.seq_prob(spd, seq)[0]
+    assert abs(g - want) <= 1e-14 * abs(want)
