@@ -46,6 +46,7 @@ def parse_args():
   ap.add_argument('--cl-k', type=int, default=8)
   ap.add_argument('--rules-per-gpu', type=int, default=16)
   ap.add_argument('--seed', type=int, default=1)
+  ap.add_argument('--chunks', type=int, default=8, help='row chunks of the overlapped exchange (0 = no overlap)')
   ap.add_argument('--e2e-steps', type=int, default=3)
   ap.add_argument('--cpu-rules', type=int, default=2, help='rules in the CPU-baseline sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -265,7 +266,10 @@ def run_b200(args):
   out = torch.empty_like(p)
   sharded = None
   if world > 1:
-    sharded = parallel.ShardedRhs(lambda pin, pout: model.rhs(pin, pout), n, device=device)
+    if args.chunks > 0:
+      sharded = parallel.OverlappedRhs(model.weights, model.flux_rows, n, chunks=args.chunks, device=device)
+    else:
+      sharded = parallel.ShardedRhs(lambda pin, pout: model.rhs(pin, pout), n, device=device)
     p_full = torch.zeros(sharded.padded, dtype=torch.float64, device=device)
     p_full[:n] = p
     out_full = torch.zeros_like(p_full)
@@ -366,7 +370,8 @@ def run_b200(args):
                 config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a, cl_k=args.cl_k,
                             n_states=n, rules_per_gpu=args.rules_per_gpu, total_rules=args.rules_per_gpu * world,
                             seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
-                            parallelism=f'rules dealt to {world} rank(s); reduce-scatter + all-gather per step' if world > 1 else 'single GPU',
+                            parallelism=(f'rules dealt to {world} ranks; flux reduce-scatter + table all-gather per step, '
+                                         f'{args.chunks} row chunks overlapped with the product') if world > 1 else 'single GPU',
                             l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
                 clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches_total / world) * args.steps,
                 roofline=roofline, cpu_baseline=cpu,

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'tapes_py_interface.so')
 SYMBOLS = (
     'setup_gambit', 'cleanup_gambit', 'c_register_problems', 'c_compute_dy_dt',
     'tapes_last_error', 'tapes_clear_error', 'tapes_alphabet_size', 'tapes_register_rules',
-    'tapes_model', 'tapes_release_model', 'tapes_rhs_device', 'tapes_rhs_profile', 'tapes_sync', 'tapes_model_info',
+    'tapes_model', 'tapes_release_model', 'tapes_rhs_device', 'tapes_weights_device', 'tapes_flux_rows_device', 'tapes_rhs_profile', 'tapes_sync', 'tapes_model_info',
     'tapes_model_set', 'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
 )
 
@@ -56,6 +56,10 @@ def load():
   lib.tapes_release_model.argtypes = [ctypes.c_char_p, i64]
   lib.tapes_rhs_device.restype = i32
   lib.tapes_rhs_device.argtypes = [vp, vp, vp, vp]
+  lib.tapes_weights_device.restype = i32
+  lib.tapes_weights_device.argtypes = [vp, vp, vp]
+  lib.tapes_flux_rows_device.restype = i32
+  lib.tapes_flux_rows_device.argtypes = [vp, vp, i64, i64, vp]
   lib.tapes_rhs_profile.restype = i32
   lib.tapes_rhs_profile.argtypes = [vp, vp, vp, vp, vp, i32]
   lib.tapes_sync.restype = i32

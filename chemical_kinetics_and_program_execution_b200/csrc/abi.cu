@@ -168,6 +168,29 @@ int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out,
   }
 }
 
+int tapes_weights_device(void* model, const double* d_probs_in, void* cuda_stream) {
+  if (!model) { fail("null model"); return 1; }
+  try {
+    tapes::weights_device(*(tapes::Model*)model, d_probs_in, (cudaStream_t)cuda_stream);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_flux_rows_device(void* model, double* d_probs_out, int64_t row_lo, int64_t row_hi, void* cuda_stream) {
+  if (!model) { fail("null model"); return 1; }
+  try {
+    tapes::flux_rows_device(*(tapes::Model*)model, d_probs_out, (uint64_t)row_lo, (uint64_t)row_hi,
+                            (cudaStream_t)cuda_stream);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
 int tapes_rhs_profile(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream,
                       double* phase_ms, int capacity) {
   if (!model) { fail("null model"); return 1; }

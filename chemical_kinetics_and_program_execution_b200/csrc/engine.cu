@@ -736,7 +736,7 @@ int marginal_tail_top(const Model& m) {
   return top;
 }
 
-void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
+void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* ev) {
   const Consts c = make_consts(m);
   Tables t;
   t.p = d_p; t.marg = m.marg; t.k = m.k;
@@ -763,16 +763,29 @@ void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cud
       level_kernel<<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, m.node_w);
     }
   }
-  if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
-  const uint64_t threads = m.n_states * (uint64_t)m.spmv_group;
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st) {
+  if (row_hi <= row_lo) return;
+  const uint64_t rows = row_hi - row_lo;
+  const uint64_t threads = rows * (uint64_t)m.spmv_group;
+  const uint64_t* rp = m.row_ptr + row_lo;
+  double* out = d_out + row_lo;
   switch (m.spmv_group) {
-    case 1: spmv_kernel<1><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
-    case 2: spmv_kernel<2><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
-    case 4: spmv_kernel<4><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
-    case 8: spmv_kernel<8><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
-    default: spmv_kernel<16><<<grid_for(threads, kThreads), kThreads, 0, st>>>(m.row_ptr, m.entries, m.node_w, d_out, m.n_states); break;
+    case 1: spmv_kernel<1><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
+    case 2: spmv_kernel<2><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
+    case 4: spmv_kernel<4><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
+    case 8: spmv_kernel<8><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
+    default: spmv_kernel<16><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
+  launch_weights(m, d_p, st, ev);
+  if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
+  launch_flux(m, d_out, 0, m.n_states, st);
 }
 }  // namespace
 
@@ -790,6 +803,15 @@ int64_t rhs_launch_count(const Model& m) {
 
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
   rhs_launch(m, d_p, d_out, stream ? stream : m.stream, nullptr);
+}
+
+void weights_device(Model& m, const double* d_p, cudaStream_t stream) {
+  launch_weights(m, d_p, stream ? stream : m.stream, nullptr);
+}
+
+void flux_rows_device(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t stream) {
+  if (row_hi > m.n_states || row_lo > row_hi) throw std::runtime_error("row range outside the state table");
+  launch_flux(m, d_out, row_lo, row_hi, stream ? stream : m.stream);
 }
 
 void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_t stream, float ms[3]) {

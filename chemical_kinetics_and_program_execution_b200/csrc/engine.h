@@ -101,6 +101,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream);
 // model.stream (or `stream` when non-null).
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream);
 
+// The two halves of rhs_device: all p-dependent weights, then the product for a range of states.
+void weights_device(Model& m, const double* d_p, cudaStream_t stream);
+void flux_rows_device(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t stream);
+
 // Same, with CUDA events recorded on the launching stream between the phases; synchronises and
 // returns ms for (marginals + leaf-world probabilities, forest levels, S * w).
 void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_t stream, float ms[3]);

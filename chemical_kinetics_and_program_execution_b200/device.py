@@ -43,6 +43,17 @@ class DeviceModel:
     _lib.check(rc == 0, 'tapes_rhs_device')
     return out
 
+  def weights(self, p):
+    """Everything of a right-hand side that depends on p (asynchronous, current stream)."""
+    rc = markov_tapes.u_lib.tapes_weights_device(self.handle, p.data_ptr(), _current_stream_handle())
+    _lib.check(rc == 0, 'tapes_weights_device')
+
+  def flux_rows(self, out, row_lo, row_hi):
+    """dy/dt of the states row_lo <= i < row_hi from the weights of the last `weights` call."""
+    rc = markov_tapes.u_lib.tapes_flux_rows_device(self.handle, out.data_ptr(), int(row_lo), int(row_hi),
+                                                   _current_stream_handle())
+    _lib.check(rc == 0, 'tapes_flux_rows_device')
+
   def rhs_profile(self, p, out):
     """One right-hand side with CUDA events between its phases; returns ms per phase
     (marginals + leaf-world probabilities, forest levels, S*w) measured on the launch stream."""

@@ -2,10 +2,12 @@
 
 The window-extension forests of different flux rules are independent, so the rule set is dealt
 round-robin to the ranks: rank g builds and evaluates only its rules over the full state space
-and produces a partial dy/dt.  States are owned in contiguous blocks: a reduce-scatter sums the
-partial flux into each owner's block (the flux exchange), the owner applies its update, and an
-all-gather rebuilds the full table for the next right-hand side.  Nothing here touches the GPU
-directly, so the plumbing is testable with the gloo backend on CPU.
+and produces a partial dy/dt.  States are owned block-cyclically: the table is cut into row
+chunks and every chunk into one block per rank.  As soon as the product for a chunk has been
+launched, a reduce-scatter sums that chunk's partial flux into the owners' blocks (the flux
+exchange) and an all-gather returns the owners' results, both asynchronously, so the exchange of
+chunk c runs under the product of chunks c+1...  Nothing here touches the GPU directly, so the
+plumbing is testable with the gloo backend on CPU.
 """
 
 import numpy
@@ -68,3 +70,67 @@ class ShardedRhs:
 
   def rhs_full(self, p_full, out_full):
     return self.gather(self.owned_flux(p_full), out_full)
+
+
+class OverlappedRhs:
+  """dy/dt of the full problem with the exchange overlapped chunk by chunk.
+
+  local_weights(p_full) evaluates everything that depends on p; local_flux_rows(out, lo, hi)
+  writes this rank's partial dy/dt for the states lo <= i < hi.  `owner_update(block, lo, hi)`
+  (optional) is applied by the owner to its summed block before it is gathered - the place where
+  an integrator turns flux into a new table; the default leaves dy/dt in place.
+  """
+
+  def __init__(self, local_weights, local_flux_rows, n_states, chunks=8, group=None, device='cuda',
+               owner_update=None):
+    self.local_weights = local_weights
+    self.local_flux_rows = local_flux_rows
+    self.owner_update = owner_update
+    self.group = group
+    self.world = dist.get_world_size(group)
+    self.rank = dist.get_rank(group)
+    self.n = n_states
+    self.chunks = max(1, int(chunks))
+    unit = self.chunks * self.world
+    self.padded = -(-n_states // unit) * unit
+    self.chunk_len = self.padded // self.chunks
+    self.block_len = self.chunk_len // self.world
+    self.partial = torch.zeros(self.padded, dtype=torch.float64, device=device)
+    self.owned = torch.zeros(self.chunks, self.block_len, dtype=torch.float64, device=device)
+
+  def owned_range(self, chunk):
+    lo = chunk * self.chunk_len + self.rank * self.block_len
+    return lo, lo + self.block_len
+
+  def rhs_full(self, p_full, out_full):
+    """p_full, out_full: padded full-length vectors (padding stays zero)."""
+    self.local_weights(p_full[:self.n])
+    pending = []
+    for c in range(self.chunks):
+      lo = c * self.chunk_len
+      hi = min(lo + self.chunk_len, self.n)
+      if hi > lo:
+        self.local_flux_rows(self.partial, lo, hi)
+      seg = self.partial[c * self.chunk_len:(c + 1) * self.chunk_len]
+      w1 = dist.reduce_scatter_tensor(self.owned[c], seg, op=dist.ReduceOp.SUM, group=self.group,
+                                      async_op=True)
+      pending.append((c, w1))
+      if len(pending) > 1:
+        self._finish(pending.pop(0), out_full)
+    while pending:
+      self._finish(pending.pop(0), out_full)
+    for w in self._gathers:
+      w.wait()
+    self._gathers = []
+    return out_full
+
+  _gathers = []
+
+  def _finish(self, item, out_full):
+    c, w1 = item
+    w1.wait()
+    if self.owner_update is not None:
+      self.owner_update(self.owned[c], *self.owned_range(c))
+    seg = out_full[c * self.chunk_len:(c + 1) * self.chunk_len]
+    self._gathers = self._gathers + [dist.all_gather_into_tensor(seg, self.owned[c], group=self.group,
+                                                                 async_op=True)]

@@ -65,6 +65,14 @@ int tapes_release_model(const char* tag, int64_t cl_k);
  * own stream). */
 int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream);
 
+/* The two halves of tapes_rhs_device, for callers that overlap the product with communication:
+ * tapes_weights_device evaluates everything that depends on p (marginal tables, leaf-world
+ * probabilities, all forest levels); tapes_flux_rows_device then writes dy/dt for the states
+ * row_lo <= i < row_hi into d_probs_out[row_lo .. row_hi) from those weights. */
+int tapes_weights_device(void* model, const double* d_probs_in, void* cuda_stream);
+int tapes_flux_rows_device(void* model, double* d_probs_out, int64_t row_lo, int64_t row_hi,
+                           void* cuda_stream);
+
 /* One right-hand side with CUDA events between its phases, recorded on the launching stream;
  * synchronises and writes the phase durations in ms: [0] marginal tables + leaf-world
  * probabilities, [1] forest levels, [2] S * w. */

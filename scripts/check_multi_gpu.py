@@ -1,0 +1,41 @@
+"""Run under torchrun on N GPUs: the sharded, overlapped right-hand side must equal the unsplit one."""
+import os, sys
+os.environ.setdefault('MARKOV_TAPES_QUIET', '1')
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy, torch, torch.distributed as dist
+
+rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+dist.init_process_group('nccl', device_id=dev)
+from chemical_kinetics_and_program_execution_b200 import configs, device, markov_tapes as mt, parallel
+import bench
+
+A, k, R = 10, 6, 4 * world
+rules = configs.random_rule_set(A, R, seed=5)
+mt.register_rule_set('mg-full', A, rules)
+mt.register_rule_set(f'mg-part{rank}', A, parallel.split_rule_set(rules, world, rank))
+full = device.DeviceModel('mg-full', k)
+part = device.DeviceModel(f'mg-part{rank}', k)
+n = A ** k
+p = bench.device_product_table(A, k, 9, dev)
+want = full.rhs(p)
+for chunks in (1, 3, 8):
+    sh = parallel.OverlappedRhs(part.weights, part.flux_rows, n, chunks=chunks, device=dev)
+    pf = torch.zeros(sh.padded, dtype=torch.float64, device=dev); pf[:n] = p
+    out = torch.zeros_like(pf)
+    for _ in range(3):
+        sh.rhs_full(pf, out)
+    torch.cuda.synchronize()
+    err = float((out[:n] - want).abs().max() / want.abs().max())
+    print(f'rank {rank}/{world} chunks={chunks} max rel dev vs unsplit = {err:.2e}', flush=True)
+    assert err < 1e-13
+plain = parallel.ShardedRhs(lambda a, b: part.rhs(a, b), n, device=dev)
+pf = torch.zeros(plain.padded, dtype=torch.float64, device=dev); pf[:n] = p
+out = torch.zeros_like(pf)
+plain.rhs_full(pf, out)
+torch.cuda.synchronize()
+assert float((out[:n] - want).abs().max() / want.abs().max()) < 1e-13
+dist.destroy_process_group()
+if rank == 0:
+    print('multi-gpu check ok')

@@ -40,6 +40,23 @@ def _worker(rank, world, port, result_path):
   p[:n] = torch.from_numpy(configs.markov_table(SIZE_A, CL_K, 3))
   out = torch.zeros_like(p)
   sharded.rhs_full(p, out)
+
+  # the chunked, overlapped exchange must give the same vector
+  cache = {}
+
+  def local_weights(p_full):
+    cache['dy'] = torch.from_numpy(oracle.compute_dy_dt(tag, CL_K, p_full.numpy(), mode=oracle.MERGED))
+
+  def local_flux_rows(out_partial, lo, hi):
+    out_partial[lo:hi] = cache['dy'][lo:hi]
+
+  over = parallel.OverlappedRhs(local_weights, local_flux_rows, n, chunks=3, device='cpu')
+  p2 = torch.zeros(over.padded, dtype=torch.float64)
+  p2[:n] = p[:n]
+  out2 = torch.zeros_like(p2)
+  over.rhs_full(p2, out2)
+  assert torch.equal(out2[:n], out[:n])
+  assert float(out2[n:].abs().sum()) == 0.0
   if rank == 0:
     numpy.save(result_path, out[:n].numpy())
   dist.destroy_process_group()
