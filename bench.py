@@ -46,7 +46,9 @@ def parse_args():
   ap.add_argument('--cl-k', type=int, default=8)
   ap.add_argument('--rules-per-gpu', type=int, default=16)
   ap.add_argument('--seed', type=int, default=1)
-  ap.add_argument('--chunks', type=int, default=8, help='row chunks of the overlapped exchange (0 = no overlap)')
+  ap.add_argument('--chunks', type=int, default=0, help='row chunks of the overlapped exchange (0 = no overlap)')
+  ap.add_argument('--exchange', default='rs_ag', choices=['rs_ag', 'allreduce'],
+                  help='flux exchange for N > 1: reduce-scatter + all-gather, or one all-reduce')
   ap.add_argument('--e2e-steps', type=int, default=3)
   ap.add_argument('--cpu-rules', type=int, default=2, help='rules in the CPU-baseline sample')
   ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -277,6 +279,9 @@ def run_b200(args):
   def one_step():
     if sharded is None:
       model.rhs(p, out)
+    elif args.exchange == 'allreduce':
+      model.rhs(p_full[:n], out_full[:n])
+      dist.all_reduce(out_full, op=dist.ReduceOp.SUM)
     else:
       sharded.rhs_full(p_full, out_full)
 
@@ -370,8 +375,10 @@ def run_b200(args):
                 config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a, cl_k=args.cl_k,
                             n_states=n, rules_per_gpu=args.rules_per_gpu, total_rules=args.rules_per_gpu * world,
                             seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
-                            parallelism=(f'rules dealt to {world} ranks; flux reduce-scatter + table all-gather per step, '
-                                         f'{args.chunks} row chunks overlapped with the product') if world > 1 else 'single GPU',
+                            parallelism=(f'rules dealt to {world} ranks; exchange per step: '
+                                         + ('all-reduce of dy/dt' if args.exchange == 'allreduce' else
+                                            f'flux reduce-scatter + table all-gather, {args.chunks} overlapped row chunks'))
+                            if world > 1 else 'single GPU',
                             l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
                 clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches_total / world) * args.steps,
                 roofline=roofline, cpu_baseline=cpu,
