@@ -705,7 +705,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaGetLastError());
   }
   const double per_row = n ? (double)m.nnz / (double)n : 0.0;
-  m.spmv_group = per_row > 48 ? 4 : (per_row > 24 ? 2 : 1);
+  m.spmv_group = per_row > 128 ? 4 : (per_row > 64 ? 2 : 1);
   if (const char* g = std::getenv("TAPES_SPMV_LANES")) {
     const int v = std::atoi(g);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) m.spmv_group = v;
