@@ -44,7 +44,7 @@ def parse_args():
   ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   ap.add_argument('--size-a', type=int, default=10)
   ap.add_argument('--cl-k', type=int, default=8)
-  ap.add_argument('--rules-per-gpu', type=int, default=16)
+  ap.add_argument('--rules-per-gpu', type=int, default=24)
   ap.add_argument('--seed', type=int, default=1)
   ap.add_argument('--chunks', type=int, default=0, help='row chunks of the overlapped exchange (0 = no overlap)')
   ap.add_argument('--exchange', default='rs_ag', choices=['rs_ag', 'allreduce'],
@@ -148,7 +148,7 @@ def make_workload(args, world, rank):
   from chemical_kinetics_and_program_execution_b200 import configs, parallel
   total_rules = args.rules_per_gpu * world
   rules = configs.random_rule_set(args.size_a, total_rules, seed=args.seed)
-  local = parallel.split_rule_set(rules, world, rank) if world > 1 else rules
+  local = parallel.split_rule_set(rules, world, rank, args.size_a, args.cl_k) if world > 1 else rules
   tag = configs.synthetic_tag(args.size_a, total_rules, args.seed) + (f'-rank{rank}of{world}' if world > 1 else '')
   return rules, local, tag
 
@@ -307,6 +307,36 @@ def run_b200(args):
     ms_total = float(t.item())
   ms_step = ms_total / args.steps
 
+  # per-rank compute time of one step and the bare exchange, to explain the scaling
+  rank_ms, comm_ms = None, None
+  if world > 1:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+      model.rhs(p_full[:n], out_full[:n])
+    e1.record()
+    torch.cuda.synchronize()
+    mine = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=device)
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    rank_ms = [float(x.item()) for x in every]
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+      if args.exchange == 'allreduce':
+        dist.all_reduce(out_full, op=dist.ReduceOp.SUM)
+      else:
+        dist.reduce_scatter_tensor(sharded.mine if hasattr(sharded, 'mine') else sharded.owned.view(-1)[:sharded.padded // world],
+                                   out_full, op=dist.ReduceOp.SUM)
+        dist.all_gather_into_tensor(out_full, sharded.mine if hasattr(sharded, 'mine') else sharded.owned.view(-1)[:sharded.padded // world])
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    comm_ms = float(t.item())
+
   # whole-job structural size
   sizes = torch.tensor([info['nnz'], info['n_nodes'], info['n_terms'], info['launches_per_rhs']],
                        dtype=torch.float64, device=device)
@@ -381,7 +411,7 @@ def run_b200(args):
                             if world > 1 else 'single GPU',
                             l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
                 clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches_total / world) * args.steps,
-                roofline=roofline, cpu_baseline=cpu,
+                roofline=roofline, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
                 states_expanded_per_s=(info['n_nodes'] + info['worlds_walked']) / max(expand_s, 1e-9),
                 build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique']))

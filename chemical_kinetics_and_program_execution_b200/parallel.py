@@ -15,12 +15,48 @@ import torch
 import torch.distributed as dist
 
 
-def split_rule_set(rules, world_size, rank):
-  """Rules rank, rank + world_size, ... of a rule-set dict, plus one inert rule that carries the
-  selection weight of everything dealt to other ranks, so that the probability of picking a local
-  rule is the same as in the unsplit problem (gambit_macros.scm:75-86 normalises by the sum)."""
+def rule_costs(rules, size_a, cl_k):
+  """Flux terms each rule generates at (size_a, cl_k): one per length-k window that overlaps a
+  changed cell and per assignment of the window cells outside the rule's span."""
+  pattern = numpy.asarray(rules['pattern']).reshape(-1, 4)
+  repl = numpy.asarray(rules['repl']).reshape(-1, 4)
+  costs = []
+  for r, span in enumerate(numpy.asarray(rules['span'])):
+    changed = [c for c in range(int(span)) if pattern[r, c] != repl[r, c]]
+    if not changed:
+      costs.append(0.0)
+      continue
+    total = 0.0
+    for start in range(changed[0] - cl_k + 1, changed[-1] + 1):
+      inside = max(0, min(start + cl_k, int(span)) - max(start, 0))
+      total += float(size_a) ** (cl_k - inside)
+    costs.append(total)
+  return numpy.array(costs)
+
+
+def deal_rules(costs, world_size):
+  """Longest-processing-time assignment: rules in descending cost to the least loaded rank
+  (ties to the lower rank), so every rank computes the same dealing."""
+  order = sorted(range(len(costs)), key=lambda r: (-costs[r], r))
+  load = [0.0] * world_size
+  owner = [0] * len(costs)
+  for r in order:
+    g = min(range(world_size), key=lambda j: (load[j], j))
+    owner[r] = g
+    load[g] += costs[r]
+  return numpy.array(owner)
+
+
+def split_rule_set(rules, world_size, rank, size_a=None, cl_k=None):
+  """This rank's share of a rule-set dict plus one inert rule that carries the selection weight
+  of everything dealt to other ranks, so that the probability of picking a local rule is the same
+  as in the unsplit problem (gambit_macros.scm:75-86 normalises by the sum).  With size_a and
+  cl_k the rules are dealt by estimated cost (balanced), else round-robin."""
   n = len(rules['rate'])
-  mine = numpy.arange(rank, n, world_size)
+  if size_a is not None and cl_k is not None:
+    mine = numpy.nonzero(deal_rules(rule_costs(rules, size_a, cl_k), world_size) == rank)[0]
+  else:
+    mine = numpy.arange(rank, n, world_size)
   others = numpy.setdiff1d(numpy.arange(n), mine)
   out = {key: numpy.asarray(val)[mine] for key, val in rules.items()}
   if len(others):

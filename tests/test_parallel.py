@@ -73,6 +73,25 @@ def test_split_rule_set_keeps_every_rule_once():
   assert sorted(seen) == sorted(rules['rate'].tolist())
 
 
+def test_balanced_dealing_matches_term_counts(oracle):
+  rules = configs.random_rule_set(SIZE_A, N_RULES, seed=6)
+  costs = parallel.rule_costs(rules, SIZE_A, CL_K)
+  p = configs.dirichlet_product_table(SIZE_A, CL_K, 1)
+  for r in range(N_RULES):  # the cost model is exact: it counts the oracle's flux terms
+    one = {key: numpy.asarray(val)[r:r + 1] for key, val in rules.items()}
+    oracle.register_rules('cost-probe', SIZE_A, one)
+    src, _, _ = oracle.terms('cost-probe', CL_K, p, mode=oracle.MERGED)
+    assert len(src) == costs[r]
+  owner = parallel.deal_rules(costs, 3)
+  loads = [costs[owner == g].sum() for g in range(3)]
+  assert max(loads) - min(loads) <= costs.max()
+  seen = []
+  for g in range(3):
+    part = parallel.split_rule_set(rules, 3, g, SIZE_A, CL_K)
+    seen += part['rate'][:-1].tolist()
+  assert sorted(seen) == sorted(rules['rate'].tolist())
+
+
 def test_block_bounds_cover_all_states():
   for n, w in ((625, 2), (1000, 8), (7, 4)):
     covered = []
