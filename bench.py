@@ -47,7 +47,7 @@ def parse_args():
   ap.add_argument('--rules-per-gpu', type=int, default=24)
   ap.add_argument('--seed', type=int, default=1)
   ap.add_argument('--chunks', type=int, default=0, help='row chunks of the overlapped exchange (0 = no overlap)')
-  ap.add_argument('--exchange', default='rs_ag', choices=['rs_ag', 'allreduce'],
+  ap.add_argument('--exchange', default='allreduce', choices=['rs_ag', 'allreduce'],
                   help='flux exchange for N > 1: reduce-scatter + all-gather, or one all-reduce')
   ap.add_argument('--e2e-steps', type=int, default=3)
   ap.add_argument('--cpu-rules', type=int, default=2, help='rules in the CPU-baseline sample')

@@ -131,6 +131,37 @@ def random_rule_set(size_a, n_rules, seed, max_span=3, catalyst_fraction=0.5):
               rate=rate, select_weight=numpy.ones(n_rules))
 
 
+def autocatalysis_rule_set(c_form=0.01, c_auto=1.0, c_stab=0.05, c_add=0.02, c_remove=0.02):
+  """A tape restatement of the chemistry of examples/autocatalysis.py (BASELINE.json config 2).
+
+  The reference script integrates a 3-variable mean-field ODE and never touches the tape path
+  (examples/autocatalysis.py:38-44, 126-151), so this rule set is OUR definition, not a port:
+  alphabet (S M A B) = solvent, monomer, A-dimer half, B-dimer half.  Two adjacent monomers on the
+  data tape dimerise spontaneously (c_form) or catalysed by a dimer half of the same kind under
+  the program-tape head (c_auto); dimers fall apart (c_stab); monomers flow in and out
+  (c_add / c_remove).  Parity for it is against the CPU oracle only.
+  """
+  S, M, A, B = range(4)
+  rows = []  # tape, span, catalyst, pattern, repl, rate
+  for dimer in (A, B):
+    rows.append((1, 2, -1, [M, M], [dimer, dimer], c_form))
+    rows.append((1, 2, dimer, [M, M], [dimer, dimer], c_auto))
+    rows.append((1, 2, -1, [dimer, dimer], [M, M], c_stab))
+  rows.append((1, 1, -1, [S], [M], c_add))
+  rows.append((1, 1, -1, [M], [S], c_remove))
+  n = len(rows)
+  pattern = numpy.zeros((n, 4), dtype=numpy.int32)
+  repl = numpy.zeros((n, 4), dtype=numpy.int32)
+  for r, row in enumerate(rows):
+    pattern[r, :row[1]] = row[3]
+    repl[r, :row[1]] = row[4]
+  return dict(tape=numpy.array([r[0] for r in rows], dtype=numpy.int32),
+              span=numpy.array([r[1] for r in rows], dtype=numpy.int32),
+              catalyst=numpy.array([r[2] for r in rows], dtype=numpy.int32),
+              pattern=pattern, repl=repl, rate=numpy.array([r[5] for r in rows], dtype=numpy.float64),
+              select_weight=numpy.ones(n))
+
+
 def synthetic_tag(size_a, n_rules, seed, max_span=3):
   return f'synthetic-A{size_a}-R{n_rules}-s{seed}-m{max_span}'
 

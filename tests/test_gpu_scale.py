@@ -1,0 +1,87 @@
+"""GPU parity at BASELINE.json's larger configurations: oracle comparisons where the CPU port
+finishes in seconds, size-independent properties (conservation, additivity over rule shards) at
+the full 10^8-state size."""
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from chemical_kinetics_and_program_execution_b200 import configs, parallel  # noqa: E402
+
+
+@pytest.fixture(scope='module')
+def mt():
+  from chemical_kinetics_and_program_execution_b200 import markov_tapes
+  return markov_tapes
+
+
+@pytest.fixture(scope='module')
+def device():
+  from chemical_kinetics_and_program_execution_b200 import device as dev
+  return dev
+
+
+def close(got, want, tol=1e-12):
+  scale = abs(want).max()
+  assert abs(got - want).max() <= tol * scale, (abs(got - want).max(), scale)
+
+
+def test_ex3_long_chain(mt, oracle):
+  """BASELINE config 3: ex3 with cl_k = 12 (1.68e7 states)."""
+  f = mt.get_dy_dt(tag='ex3-copolymerization', size_a=4, cl_k=12)
+  p0 = configs.ex3_p0(12)  # the shipped generator at k = 12: sparse, heavily pruned
+  close(f(p0, 0.0), oracle.compute_dy_dt('ex3-copolymerization', 12, p0, mode=oracle.LITERAL))
+  p = configs.dirichlet_product_table(4, 12, 3)  # full support: every term is live
+  got = f(p, 0.0)
+  close(got, oracle.compute_dy_dt('ex3-copolymerization', 12, p, mode=oracle.MERGED))
+  assert abs(got.sum()) <= 1e-13 * abs(got).sum()
+
+
+def test_autocatalysis_tape(mt, oracle):
+  """BASELINE config 2: our tape restatement of the autocatalysis chemistry at ~10^6 states."""
+  rules = configs.autocatalysis_rule_set()
+  oracle.register_rules('autocatalysis-tape', 4, rules)
+  mt.register_rule_set('autocatalysis-tape', 4, rules)
+  f = mt.get_dy_dt(tag='autocatalysis-tape', size_a=4, cl_k=10)
+  for p in (configs.product_table([0.5, 0.3, 0.1, 0.1], 10), configs.markov_table(4, 10, 4)):
+    got = f(p, 0.0)
+    close(got, oracle.compute_dy_dt('autocatalysis-tape', 10, p, mode=oracle.MERGED))
+    assert abs(got.sum()) <= 1e-13 * abs(got).sum()
+  # a short HBM-resident integration keeps the table a probability distribution
+  p0 = configs.product_table([0.5, 0.3, 0.1, 0.1], 10)
+  seqs = [[1], [2], [3], [2, 2], [3, 3]]
+  series = mt.ode_integrate_device(tag='autocatalysis-tape', size_a=4, cl_k=10, p0=p0, ts=numpy.linspace(0, 5, 6),
+                                   rtol=1e-8, atol=1e-10, observables=seqs + [[0]], return_states=False)
+  assert (series > -1e-12).all()
+  assert abs(series[:, [0, 1, 2, 5]].sum(axis=1) - 1).max() < 1e-9  # single-symbol marginals sum to 1
+  assert series[-1, 3] > series[0, 3]  # autocatalysed A-dimers grow from the seeded A halves
+
+
+def test_full_size_synthetic_properties(mt, device, oracle):
+  """BASELINE config 5 at its full size (A = 10, k = 8, 10^8 states): conservation, additivity
+  over rule shards, and one rule against the CPU port."""
+  import torch
+  import bench
+  size_a, cl_k, n_rules = 10, 8, 3
+  rules = configs.random_rule_set(size_a, n_rules, seed=11)
+  mt.register_rule_set('scale-full', size_a, rules)
+  full = device.DeviceModel('scale-full', cl_k)
+  p = bench.device_product_table(size_a, cl_k, 5, torch.device('cuda'))
+  want = full.rhs(p).clone()
+  torch.cuda.synchronize()
+  assert float(want.sum().abs()) <= 1e-12 * float(want.abs().sum())  # every term adds +w and -w
+  total = torch.zeros_like(want)
+  for r in range(n_rules):
+    mt.register_rule_set(f'scale-part{r}', size_a, parallel.split_rule_set(rules, n_rules, r))
+    part = device.DeviceModel(f'scale-part{r}', cl_k)
+    total += part.rhs(p)
+    if r == 0:
+      oracle.register_rules('scale-part0', size_a, parallel.split_rule_set(rules, n_rules, 0))
+      cpu = oracle.compute_dy_dt('scale-part0', cl_k, p.cpu().numpy(), mode=oracle.MERGED)
+      torch.cuda.synchronize()
+      close(part.rhs(p).cpu().numpy(), cpu)
+    mt.u_lib.tapes_release_model(f'scale-part{r}'.encode(), cl_k)
+  torch.cuda.synchronize()
+  assert float((total - want).abs().max()) <= 1e-13 * float(want.abs().max())
+  mt.u_lib.tapes_release_model(b'scale-full', cl_k)

@@ -90,3 +90,14 @@ def test_rule_table_problem(oracle):
   assert abs(lit).max() > 0
   assert abs(lit - mer).max() <= 1e-13 * abs(lit).max()
   assert abs(lit.sum()) <= 1e-13 * abs(lit).sum()
+
+
+def test_autocatalysis_rule_set(oracle):
+  rules = configs.autocatalysis_rule_set()
+  oracle.register_rules('autocat-cpu', 4, rules)
+  p = configs.markov_table(4, 5, 7)
+  lit = oracle.compute_dy_dt('autocat-cpu', 5, p, mode=oracle.LITERAL)
+  mer = oracle.compute_dy_dt('autocat-cpu', 5, p, mode=oracle.MERGED)
+  assert abs(lit).max() > 0
+  assert abs(lit - mer).max() <= 1e-13 * abs(lit).max()
+  assert abs(lit.sum()) <= 1e-13 * abs(lit).sum()
