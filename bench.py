@@ -144,12 +144,16 @@ class ClockSampler:
 
 
 def make_workload(args, world, rank):
-  """The synthetic rule set (all ranks generate the same one) and this rank's share."""
+  """The synthetic rule set and this rank's share.  Weak scaling with exactly equal work per GPU:
+  the base set of `rules_per_gpu` random rules is the N = 1 workload; at N GPUs the problem is the
+  union of N copies of it with the alphabet rotated by the rank (different rules, identical
+  structure sizes), and rank g evaluates copy g."""
   from chemical_kinetics_and_program_execution_b200 import configs, parallel
-  total_rules = args.rules_per_gpu * world
-  rules = configs.random_rule_set(args.size_a, total_rules, seed=args.seed)
-  local = parallel.split_rule_set(rules, world, rank, args.size_a, args.cl_k) if world > 1 else rules
-  tag = configs.synthetic_tag(args.size_a, total_rules, args.seed) + (f'-rank{rank}of{world}' if world > 1 else '')
+  base = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)
+  rules = configs.concat_rule_sets([configs.rotated_rule_set(base, g, args.size_a) for g in range(world)])
+  r = args.rules_per_gpu
+  local = parallel.take_rules(rules, numpy.arange(rank * r, (rank + 1) * r)) if world > 1 else rules
+  tag = configs.synthetic_tag(args.size_a, r * world, args.seed) + (f'-rank{rank}of{world}' if world > 1 else '')
   return rules, local, tag
 
 
@@ -210,7 +214,7 @@ def run_reference(args):
   oracle.build()
   n = args.size_a ** args.cl_k
   total_rules = args.rules_per_gpu * args.gpus
-  rules = configs.random_rule_set(args.size_a, total_rules, seed=args.seed)
+  rules = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)  # rank 0's rules
   sample = {k: numpy.asarray(v)[:args.cpu_rules] for k, v in rules.items()}
   # structural size of the sample (terms -> nnz) from the port's own term counter
   times, cores, counters = [], 1, None

@@ -131,6 +131,24 @@ def random_rule_set(size_a, n_rules, seed, max_span=3, catalyst_fraction=0.5):
               rate=rate, select_weight=numpy.ones(n_rules))
 
 
+def rotated_rule_set(rules, shift, size_a):
+  """The same rules with every symbol s replaced by (s + shift) mod size_a: a different rule set
+  with exactly the same structure sizes (used to give every GPU of a weak-scaling run equal work)."""
+  out = {key: numpy.array(val, copy=True) for key, val in rules.items()}
+  span = numpy.asarray(rules['span'])
+  for r in range(len(span)):
+    m = int(span[r])
+    out['pattern'][r, :m] = (out['pattern'][r, :m] + shift) % size_a
+    out['repl'][r, :m] = (out['repl'][r, :m] + shift) % size_a
+    if out['catalyst'][r] >= 0:
+      out['catalyst'][r] = (out['catalyst'][r] + shift) % size_a
+  return out
+
+
+def concat_rule_sets(parts):
+  return {key: numpy.concatenate([numpy.asarray(p[key]) for p in parts]) for key in parts[0]}
+
+
 def autocatalysis_rule_set(c_form=0.01, c_auto=1.0, c_stab=0.05, c_add=0.02, c_remove=0.02):
   """A tape restatement of the chemistry of examples/autocatalysis.py (BASELINE.json config 2).
 

@@ -376,11 +376,11 @@ __global__ void __launch_bounds__(kThreads) level_kernel(Tables t, Consts c, Lev
 // reproducible run to run.
 constexpr int kSpmvUnroll = 4;
 
-template <int G>
+template <int G, bool FUSED>
 __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ row_ptr,
                                                    const uint32_t* __restrict__ entries,
                                                    const double* __restrict__ w, double* __restrict__ out,
-                                                   uint64_t n_rows) {
+                                                   uint64_t n_rows, StageUpdate up) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t row = t / G;
   const int sub = (int)(t % G);
@@ -405,7 +405,15 @@ __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ 
 #pragma unroll
     for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
   }
-  if (sub == 0 && row < n_rows) out[row] = acc;
+  if (sub == 0 && row < n_rows) {
+    out[row] = acc;
+    if (FUSED) {  // Runge-Kutta stage update for this state (same term order as the unfused kernel)
+      double a = 0.0;
+      for (int j = 0; j < up.n; ++j) a += up.vec[j][row] * up.coef[j];
+      a += acc * up.coef_self;
+      up.stage[row] = up.y[row] + a * up.h;
+    }
+  }
 }
 
 double ms_since(std::chrono::steady_clock::time_point t0) {
@@ -766,20 +774,33 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st) {
+template <bool FUSED>
+void launch_flux_impl(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
+                      const StageUpdate& up0) {
   if (row_hi <= row_lo) return;
   const uint64_t rows = row_hi - row_lo;
   const uint64_t threads = rows * (uint64_t)m.spmv_group;
   const uint64_t* rp = m.row_ptr + row_lo;
   double* out = d_out + row_lo;
+  StageUpdate up = up0;
+  if (FUSED) {  // the kernel indexes every vector by the row inside the range
+    for (int j = 0; j < up.n; ++j) up.vec[j] += row_lo;
+    up.y += row_lo;
+    up.stage += row_lo;
+  }
+  const unsigned grid = grid_for(threads, kThreads);
   switch (m.spmv_group) {
-    case 1: spmv_kernel<1><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
-    case 2: spmv_kernel<2><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
-    case 4: spmv_kernel<4><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
-    case 8: spmv_kernel<8><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
-    default: spmv_kernel<16><<<grid_for(threads, kThreads), kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows); break;
+    case 1: spmv_kernel<1, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
+    case 2: spmv_kernel<2, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
+    case 4: spmv_kernel<4, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
+    case 8: spmv_kernel<8, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
+    default: spmv_kernel<16, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st) {
+  launch_flux_impl<false>(m, d_out, row_lo, row_hi, st, StageUpdate());
 }
 
 void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
@@ -803,6 +824,12 @@ int64_t rhs_launch_count(const Model& m) {
 
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
   rhs_launch(m, d_p, d_out, stream ? stream : m.stream, nullptr);
+}
+
+void rhs_device_fused(Model& m, const double* d_p, double* d_out, const StageUpdate& up, cudaStream_t stream) {
+  cudaStream_t st = stream ? stream : m.stream;
+  launch_weights(m, d_p, st, nullptr);
+  launch_flux_impl<true>(m, d_out, 0, m.n_states, st, up);
 }
 
 void weights_device(Model& m, const double* d_p, cudaStream_t stream) {

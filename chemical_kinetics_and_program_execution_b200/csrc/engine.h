@@ -101,6 +101,21 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream);
 // model.stream (or `stream` when non-null).
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream);
 
+// Runge-Kutta stage update fused into the product: after dy/dt[i] has been summed, the same thread
+// forms  stage[i] = y[i] + h * (sum_j coef[j] * vec[j][i] + coef_self * dy/dt[i])  (terms in this
+// order), which is the argument of the next stage.  Saves one pass over the newest stage vector
+// and one launch per stage.
+struct StageUpdate {
+  int n = 0;
+  double coef[12];
+  const double* vec[12];
+  double coef_self = 0.0;
+  const double* y = nullptr;
+  double* stage = nullptr;
+  double h = 0.0;
+};
+void rhs_device_fused(Model& m, const double* d_p, double* d_out, const StageUpdate& up, cudaStream_t stream);
+
 // The two halves of rhs_device: all p-dependent weights, then the product for a range of states.
 void weights_device(Model& m, const double* d_p, cudaStream_t stream);
 void flux_rows_device(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t stream);

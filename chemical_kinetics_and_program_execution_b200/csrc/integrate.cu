@@ -3,6 +3,7 @@
 #include "integrate.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <vector>
 
@@ -156,6 +157,7 @@ struct Dop853 {
   double* K[16];
   double* F[7];
   bool have_F_mem = false, dense_ready = false, f_in_last = false, have_step = false;
+  bool fused = true;  // stage updates fused into the product kernel
   double* stage = nullptr;
   double* partial = nullptr;
   double* d_sums = nullptr;
@@ -221,16 +223,41 @@ double select_initial_step(Dop853* s) {
   return std::min(std::min(100 * h0, h1), std::min(interval, s->max_step));
 }
 
+// The stage update that follows stage `done`: coefficients of K[0..done-1] plus the coefficient of
+// the stage being computed, in ascending stage order like np.dot(K[:s].T, a[:s]).
+StageUpdate update_after(Dop853* s, const double* coef, int done, double* target, double h) {
+  StageUpdate up;
+  for (int j = 0; j < done; ++j)
+    if (coef[j] != 0.0) { up.coef[up.n] = coef[j]; up.vec[up.n] = s->K[j]; ++up.n; }
+  up.coef_self = coef[done];
+  up.y = s->y();
+  up.stage = target;
+  up.h = h;
+  return up;
+}
+
 // rk_step + error norm for one attempted step of size h; leaves y_new and K[0..12].
 double attempt(Dop853* s, double h) {
   const unsigned grid = grid_for(s->n, kThreads);
-  for (int st = 1; st < 12; ++st) {
-    Terms t = terms_of(s, s->tab.A[st], st);
-    lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->stage, s->y(), t, h, s->n);
-    fun(s, s->stage, s->K[st]);
+  if (s->fused) {
+    // stage 1 argument from K[0] alone; afterwards every product writes the next argument itself
+    Terms t1 = terms_of(s, s->tab.A[1], 1);
+    lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->stage, s->y(), t1, h, s->n);
+    for (int st = 1; st < 12; ++st) {
+      const StageUpdate up = st < 11 ? update_after(s, s->tab.A[st + 1], st, s->stage, h)
+                                     : update_after(s, s->tab.B, 11, s->y_new(), h);
+      rhs_device_fused(*s->m, s->stage, s->K[st], up, s->st);
+      s->nfev++;
+    }
+  } else {
+    for (int st = 1; st < 12; ++st) {
+      Terms t = terms_of(s, s->tab.A[st], st);
+      lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->stage, s->y(), t, h, s->n);
+      fun(s, s->stage, s->K[st]);
+    }
+    Terms tb = terms_of(s, s->tab.B, 12);
+    lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->y_new(), s->y(), tb, h, s->n);
   }
-  Terms tb = terms_of(s, s->tab.B, 12);
-  lincomb_kernel<<<grid, kThreads, 0, s->st>>>(s->y_new(), s->y(), tb, h, s->n);
   fun(s, s->y_new(), s->K[12]);
   Terms e5 = terms_of(s, s->tab.E5, 13), e3 = terms_of(s, s->tab.E3, 13);
   error_partials_kernel<<<kReduceBlocks, kThreads, 0, s->st>>>(e5, e3, s->y(), s->y_new(), s->rtol, s->atol, s->n,
@@ -257,6 +284,7 @@ Dop853* dop853_create(Model& m, const Dop853Tableau& tab, const double* h_y0, do
     const double eps = std::numeric_limits<double>::epsilon();
     s->rtol = std::max(rtol, 100 * eps); s->atol = atol;
     s->max_step = max_step > 0 ? max_step : std::numeric_limits<double>::infinity();
+    if (const char* f = std::getenv("TAPES_RK_FUSED")) s->fused = std::atoi(f) != 0;
     for (int i = 0; i < 3; ++i) s->ybuf[i] = dvec(s->n);
     for (int i = 0; i < 16; ++i) s->K[i] = dvec(s->n);
     for (int i = 0; i < 7; ++i) s->F[i] = nullptr;

@@ -47,16 +47,12 @@ def deal_rules(costs, world_size):
   return numpy.array(owner)
 
 
-def split_rule_set(rules, world_size, rank, size_a=None, cl_k=None):
-  """This rank's share of a rule-set dict plus one inert rule that carries the selection weight
-  of everything dealt to other ranks, so that the probability of picking a local rule is the same
-  as in the unsplit problem (gambit_macros.scm:75-86 normalises by the sum).  With size_a and
-  cl_k the rules are dealt by estimated cost (balanced), else round-robin."""
+def take_rules(rules, mine):
+  """The rules with indices `mine` plus one inert rule that carries the selection weight of all
+  the others, so that the probability of picking a kept rule is the same as in the full problem
+  (gambit_macros.scm:75-86 normalises by the sum of the weights)."""
   n = len(rules['rate'])
-  if size_a is not None and cl_k is not None:
-    mine = numpy.nonzero(deal_rules(rule_costs(rules, size_a, cl_k), world_size) == rank)[0]
-  else:
-    mine = numpy.arange(rank, n, world_size)
+  mine = numpy.asarray(mine, dtype=numpy.int64)
   others = numpy.setdiff1d(numpy.arange(n), mine)
   out = {key: numpy.asarray(val)[mine] for key, val in rules.items()}
   if len(others):
@@ -67,6 +63,17 @@ def split_rule_set(rules, world_size, rank, size_a=None, cl_k=None):
     out = {key: numpy.concatenate([numpy.asarray(out[key]), numpy.asarray(inert[key], dtype=numpy.asarray(out[key]).dtype)])
            for key in out}
   return out
+
+
+def split_rule_set(rules, world_size, rank, size_a=None, cl_k=None):
+  """This rank's share of a rule-set dict (see take_rules).  With size_a and cl_k the rules are
+  dealt by estimated cost (balanced), else round-robin."""
+  n = len(rules['rate'])
+  if size_a is not None and cl_k is not None:
+    mine = numpy.nonzero(deal_rules(rule_costs(rules, size_a, cl_k), world_size) == rank)[0]
+  else:
+    mine = numpy.arange(rank, n, world_size)
+  return take_rules(rules, mine)
 
 
 def block_bounds(n_states, world_size, rank):

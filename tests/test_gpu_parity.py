@@ -273,3 +273,17 @@ def test_device_observables(mt, device):
   for g, seq in zip(got, seqs):
     want = mt.seq_prob(spd, seq)[0]
     assert abs(g - want) <= 1e-14 * abs(want)
+
+
+def test_fused_stage_update_is_bit_identical(mt, p0_fixtures, monkeypatch):
+  """The Runge-Kutta stage update fused into the product kernel keeps the term order of the
+  separate kernel, so both integrators produce the same bits."""
+  p0 = dense(p0_fixtures['ex5_idx'], p0_fixtures['ex5_val'], 5 ** 5)
+  ts = numpy.linspace(0, 20.0, 11)
+  runs = []
+  for flag in ('1', '0'):
+    monkeypatch.setenv('TAPES_RK_FUSED', flag)
+    runs.append(mt.ode_integrate_device(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=p0, ts=ts,
+                                        rtol=1e-10, atol=1e-12, want_stats=True))
+  assert runs[0][1] == runs[1][1]
+  assert numpy.array_equal(runs[0][0], runs[1][0])

@@ -92,6 +92,18 @@ def test_balanced_dealing_matches_term_counts(oracle):
   assert sorted(seen) == sorted(rules['rate'].tolist())
 
 
+def test_rotated_rule_sets_have_equal_cost():
+  base = configs.random_rule_set(SIZE_A, N_RULES, seed=6)
+  want = parallel.rule_costs(base, SIZE_A, CL_K)
+  for shift in (1, 3):
+    rot = configs.rotated_rule_set(base, shift, SIZE_A)
+    assert (parallel.rule_costs(rot, SIZE_A, CL_K) == want).all()
+    assert (rot['pattern'] != base['pattern']).any()
+  both = configs.concat_rule_sets([base, configs.rotated_rule_set(base, 1, SIZE_A)])
+  part = parallel.take_rules(both, numpy.arange(N_RULES, 2 * N_RULES))
+  assert part['select_weight'][-1] == N_RULES and len(part['rate']) == N_RULES + 1
+
+
 def test_block_bounds_cover_all_states():
   for n, w in ((625, 2), (1000, 8), (7, 4)):
     covered = []
