@@ -111,7 +111,8 @@ def check(ok, what):
 MODEL_INFO_FIELDS = (
     'n_states', 'n_nodes', 'nnz', 'n_flux_rules', 'n_levels', 'launches_per_rhs', 'n_terms',
     'n_sum_nodes', 'worlds_walked', 'leaf_worlds', 'seeds', 'hash_inserts', 'hash_unique',
-    'alphabet', 'cl_k', 'spmv_lanes_per_row')
+    'alphabet', 'cl_k', 'spmv_lanes_per_row', 'flux_format', 'n_slices', 'slice_words', 'runs',
+    'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll')
 
 
 def model_info(model):
@@ -121,10 +122,10 @@ def model_info(model):
 
 
 def model_timing(model):
-  buf = numpy.zeros(3, dtype=numpy.float64)
-  load().tapes_model_timing(model, buf.ctypes.data, 3)
+  buf = numpy.zeros(4, dtype=numpy.float64)
+  load().tapes_model_timing(model, buf.ctypes.data, 4)
   return dict(host_enumerate_ms=float(buf[0]), device_expand_ms=float(buf[1]),
-              device_csr_ms=float(buf[2]))
+              device_csr_ms=float(buf[2]), device_slices_ms=float(buf[3]))
 
 
 def rule_table(tag, cl_k):

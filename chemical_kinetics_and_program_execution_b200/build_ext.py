@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'tapes_py_interface.so')
-SOURCES = ['abi.cu', 'engine.cu', 'integrate.cu', 'rules.cpp', 'problems.cpp']
+SOURCES = ['abi.cu', 'engine.cu', 'flux.cu', 'integrate.cu', 'rules.cpp', 'problems.cpp']
 HEADERS = ['engine.h', 'rules.h', 'primitives.cuh', 'integrate.h',
            os.path.join('..', '..', 'include', 'tapes_b200.h')]
 

@@ -8,6 +8,7 @@
 #include <chrono>
 #include <map>
 #include <memory>
+#include <stdexcept>
 #include <string>
 
 #include "../../include/tapes_b200.h"
@@ -218,7 +219,10 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   const int64_t v[] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
                        (int64_t)m.levels.size(), m.launches_per_rhs, m.stats.terms, m.stats.sum_nodes,
                        m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
-                       m.stats.hash_unique, (int64_t)m.A, (int64_t)m.k, (int64_t)m.spmv_group};
+                       m.stats.hash_unique, (int64_t)m.A, (int64_t)m.k, (int64_t)m.spmv_group,
+                       (int64_t)m.flux_format, (int64_t)m.slices.n_slices, (int64_t)m.slices.n_words,
+                       (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
+                       (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll};
   int n = (int)(sizeof(v) / sizeof(v[0]));
   if (n > capacity) n = capacity;
   for (int i = 0; i < n; ++i) out[i] = v[i];
@@ -233,6 +237,10 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
     m.spmv_group = (int)value;
     return 0;
   }
+  if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {
+    m.level_unroll = (int)value;
+    return 0;
+  }
   fail(std::string("unknown option or value: ") + key);
   return 1;
 }
@@ -240,8 +248,9 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
 int tapes_model_timing(void* model, double* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
   const tapes::Model& m = *(tapes::Model*)model;
-  const double v[] = {m.stats.host_enumerate_ms, m.stats.device_expand_ms, m.stats.device_csr_ms};
-  int n = 3 > capacity ? capacity : 3;
+  const double v[] = {m.stats.host_enumerate_ms, m.stats.device_expand_ms, m.stats.device_csr_ms,
+                      m.stats.device_slices_ms};
+  int n = 4 > capacity ? capacity : 4;
   for (int i = 0; i < n; ++i) out[i] = v[i];
   return n;
 }
@@ -250,11 +259,24 @@ int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
   if (!model) { fail("null model"); return 1; }
   tapes::Model& m = *(tapes::Model*)model;
   cudaStreamSynchronize(m.stream);
-  if (cudaMemcpy(row_ptr, m.row_ptr, (m.n_states + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-      (m.nnz && cudaMemcpy(entries, m.entries, m.nnz * 4, cudaMemcpyDeviceToHost) != cudaSuccess)) {
-    fail("export_csr: copy failed");
+  uint32_t* d_entries = m.entries;
+  uint32_t* rebuilt = nullptr;
+  try {
+    if (!d_entries && m.nnz) {  // only the sliced form is resident: expand it back
+      if (cudaMalloc((void**)&rebuilt, m.nnz * 4) != cudaSuccess) throw std::runtime_error("out of device memory");
+      tapes::expand_flux_slices(m, rebuilt, m.stream);
+      if (cudaStreamSynchronize(m.stream) != cudaSuccess) throw std::runtime_error("expansion failed");
+      d_entries = rebuilt;
+    }
+    if (cudaMemcpy(row_ptr, m.row_ptr, (m.n_states + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        (m.nnz && cudaMemcpy(entries, d_entries, m.nnz * 4, cudaMemcpyDeviceToHost) != cudaSuccess))
+      throw std::runtime_error("copy failed");
+  } catch (const std::exception& ex) {
+    if (rebuilt) cudaFree(rebuilt);
+    fail(std::string("export_csr: ") + ex.what());
     return 1;
   }
+  if (rebuilt) cudaFree(rebuilt);
   return 0;
 }
 

@@ -328,20 +328,31 @@ __device__ __forceinline__ double child_weight(double w_parent, double p_long, d
 // digit x).  The remaining blocks evaluate the right children, 32 prefix groups per warp: each
 // lane first adds up one group's parents in ascending id order, then the warp writes the 32 * A
 // children cooperatively so that the reads of p and the writes of w are contiguous.
+// Loads are issued U at a time before the divisions and stores that depend on them: the kernel is
+// bound by HBM latency x bandwidth, and one load in flight per thread reaches ~60 % of peak only
+// (profiles/r01_c_*).  wr and ww are the same vector: reads touch earlier levels only.
+template <int U>
 __global__ void __launch_bounds__(kThreads) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
-                                                         double* __restrict__ w) {
+                                                         uint32_t warp_step_q, uint32_t warp_step_r,
+                                                         const double* __restrict__ wr, double* __restrict__ ww) {
   if (blockIdx.x < left_blocks) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= lv.n_left) return;
     const int len = lv.lp_len[r];
     const uint32_t bo = lv.lp_io[r];
-    const double wp = w[lv.lp_gid[r]];
-    const double* tl = table(t, len);
+    const double wp = wr[lv.lp_gid[r]];
+    const double* __restrict__ tl = table(t, len);
     const double p_short = table(t, len - 1)[bo];
     const uint32_t step = c.pw[len - 1];
-    double* out = w + lv.base + r;
-    for (uint32_t x = 0; x < c.A; ++x)
-      out[(uint64_t)x * lv.n_left] = child_weight(wp, tl[bo + x * step], p_short);
+    double* out = ww + lv.base + r;
+    for (uint32_t x0 = 0; x0 < c.A; x0 += U) {
+      double p_long[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) p_long[u] = x0 + u < c.A ? tl[bo + (x0 + u) * step] : 0.0;
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (x0 + u < c.A) out[(uint64_t)(x0 + u) * lv.n_left] = child_weight(wp, p_long[u], p_short);
+    }
   } else {
     const unsigned lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x - left_blocks) * (kThreads / 32) + (threadIdx.x >> 5);
@@ -352,20 +363,48 @@ __global__ void __launch_bounds__(kThreads) level_kernel(Tables t, Consts c, Lev
     uint32_t prefix = 0;
     if (g < lv.n_groups) {
       const uint64_t lo = lv.g_ptr[g], hi = lv.g_ptr[g + 1];
-      for (uint64_t e = lo; e < hi; ++e) total += w[lv.g_parents[e]];
       prefix = lv.g_prefix[g];
       p_short = table(t, c.k - 1)[prefix];
+      for (uint64_t e = lo; e < hi; e += U) {
+        uint32_t id[U];
+        double v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) id[u] = e + u < hi ? lv.g_parents[e + u] : kNoRank;
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = id[u] != kNoRank ? wr[id[u]] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u) total += v[u];  // ascending id order; + 0.0 leaves the sum as it is
+      }
     }
     const uint32_t groups_here = (uint32_t)min((uint64_t)32, (uint64_t)lv.n_groups - g0);
     const uint32_t children = groups_here * c.A;
-    double* out = w + lv.base + (uint64_t)c.A * lv.n_left + g0 * c.A;
-    for (uint32_t j = lane; j < ((children + 31) & ~31u); j += 32) {
-      const uint32_t gl = j < children ? j / c.A : 0;
-      const uint32_t x = j - gl * c.A;
-      const double wp = __shfl_sync(0xffffffffu, total, gl);
-      const double ps = __shfl_sync(0xffffffffu, p_short, gl);
-      const uint32_t pre = __shfl_sync(0xffffffffu, prefix, gl);
-      if (j < children) out[j] = child_weight(wp, t.p[(uint64_t)pre * c.A + x], ps);
+    double* out = ww + lv.base + (uint64_t)c.A * lv.n_left + g0 * c.A;
+    const double* __restrict__ p = t.p;
+    // child j = group gl, digit x with j = gl * A + x; a step of 32 children advances (gl, x) by
+    // (warp_step_q, warp_step_r) = divmod(32, A) with a carry
+    uint32_t gl = lane / c.A, x = lane - gl * c.A;
+    for (uint32_t j = lane; j < ((children + 31) & ~31u); j += 32 * U) {
+      uint32_t gu[U], xu[U];
+      double p_long[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        gu[u] = gl; xu[u] = x;
+        gl += warp_step_q; x += warp_step_r;
+        if (x >= c.A) { x -= c.A; ++gl; }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const bool live = j + 32 * u < children;
+        if (!live) gu[u] = 0;
+        const uint32_t pre = __shfl_sync(0xffffffffu, prefix, gu[u]);
+        p_long[u] = live ? p[(uint64_t)pre * c.A + xu[u]] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const double wp = __shfl_sync(0xffffffffu, total, gu[u]);
+        const double ps = __shfl_sync(0xffffffffu, p_short, gu[u]);
+        if (j + 32 * u < children) out[j + 32 * u] = child_weight(wp, p_long[u], ps);
+      }
     }
   }
 }
@@ -445,6 +484,7 @@ Model::~Model() {
     fr(lv.root_rule); fr(lv.lp_gid); fr(lv.lp_io); fr(lv.lp_len); fr(lv.g_prefix); fr(lv.g_ptr); fr(lv.g_parents);
   }
   fr(node_w); fr(row_ptr); fr(entries); fr(marg); fr(d_marg_off); fr(d_in); fr(d_out);
+  fr(slices.slice_ptr); fr(slices.slice_runs); fr(slices.words);
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -718,6 +758,21 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     const int v = std::atoi(g);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) m.spmv_group = v;
   }
+  m.level_unroll = m.A <= 2 ? 2 : 4;  // measured on B200 (A = 10): 1: 7.15, 2: 6.49, 4: 6.02, 5: 6.56, 8: 7.17 ms
+  if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  m.stats.device_csr_ms = ms_since(t_csr);
+
+  // ---- the form the product kernel streams: slices of 32 states (flux.cu) ----
+  m.flux_format = 1;
+  if (const char* f = std::getenv("TAPES_FLUX_FORMAT")) m.flux_format = std::strcmp(f, "csr") == 0 ? 0 : 1;
+  if (m.flux_format == 1) {
+    int min_lanes = 32;  // measured (n = 1e8, 24 rules): 32: 4.22, 16: 4.23, 8: 4.54, 4: 4.76, 2: 6.97 ms; CSR 6.10 ms
+    if (const char* g = std::getenv("TAPES_RUN_MIN_LANES")) min_lanes = std::atoi(g);
+    build_flux_slices(m, min_lanes, st);
+    cudaFree(m.entries);  // tapes_export_csr rebuilds the plain entries from the slices
+    m.entries = nullptr;
+  }
 
   // ---- per-step buffers ----
   m.marg_total = 0;
@@ -729,7 +784,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_marg_off, m.marg_off, 40 * 8, cudaMemcpyHostToDevice, st));
   m.node_w = dkeep<double>(m.n_nodes);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-  m.stats.device_csr_ms = ms_since(t_csr);
   m.launches_per_rhs = rhs_launch_count(m);
   return mp;
 }
@@ -768,7 +822,18 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
     } else if (lv.n_left + lv.n_groups) {
       const unsigned left_blocks = lv.n_left ? grid_for(lv.n_left, kThreads) : 0;
       const unsigned group_blocks = lv.n_groups ? grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads) : 0;
-      level_kernel<<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, m.node_w);
+      const uint32_t q = 32u / c.A, r = 32u % c.A;
+      // loads in flight per thread: all A children at once when A is small, else batches
+      if (m.level_unroll >= 8)
+        level_kernel<8><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
+      else if (m.level_unroll >= 5)
+        level_kernel<5><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
+      else if (m.level_unroll >= 4)
+        level_kernel<4><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
+      else if (m.level_unroll >= 2)
+        level_kernel<2><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
+      else
+        level_kernel<1><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
     }
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
@@ -778,6 +843,10 @@ template <bool FUSED>
 void launch_flux_impl(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
                       const StageUpdate& up0) {
   if (row_hi <= row_lo) return;
+  if (m.flux_format == 1) {
+    launch_flux_slices(m, d_out, row_lo, row_hi, st, FUSED ? &up0 : nullptr);
+    return;
+  }
   const uint64_t rows = row_hi - row_lo;
   const uint64_t threads = rows * (uint64_t)m.spmv_group;
   const uint64_t* rp = m.row_ptr + row_lo;

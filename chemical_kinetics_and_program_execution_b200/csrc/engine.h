@@ -43,11 +43,28 @@ struct Level {
   uint64_t n_group_parents = 0;
 };
 
+// The flux structure cut into slices of 32 consecutive states, one warp lane per state.  Consecutive
+// states gather consecutive forest nodes, so most of a slice is "runs":
+// (first node id | sign << 31, lane mask) meaning lane l, if its mask bit is set, holds the entry
+// first + popcount(mask below l).  Entries outside long enough runs are stored as padded columns of
+// 32 (0xffffffff = none).  Words of slice s start at words[slice_ptr[s]]: slice_runs[s] run pairs
+// (padded to an even count), then the columns.
+struct FluxSlices {
+  uint64_t n_slices = 0;
+  uint64_t* slice_ptr = nullptr;   // [n_slices + 1]
+  uint32_t* slice_runs = nullptr;  // [n_slices]
+  uint32_t* words = nullptr;
+  uint64_t n_words = 0;
+  // facts about the encoding
+  uint64_t runs = 0, run_entries = 0, column_entries = 0, column_slots = 0;
+  int min_run_lanes = 0;
+};
+
 struct BuildStats {
   int64_t worlds_walked = 0, leaf_worlds = 0, flux_rules = 0, seeds = 0;
   int64_t nodes = 0, sum_nodes = 0, terms = 0, levels = 0;  // sum_nodes = prefix groups
   int64_t hash_inserts = 0, hash_unique = 0;
-  double host_enumerate_ms = 0, device_expand_ms = 0, device_csr_ms = 0;
+  double host_enumerate_ms = 0, device_expand_ms = 0, device_csr_ms = 0, device_slices_ms = 0;
 };
 
 struct Model {
@@ -75,8 +92,14 @@ struct Model {
   // flux structure S (n_states x n_nodes, entries +-1) in CSR by state
   uint64_t nnz = 0;
   uint64_t* row_ptr = nullptr;     // [n_states + 1]
-  uint32_t* entries = nullptr;     // [nnz] node id | sign << 31 (1 = outflow)
-  int spmv_group = 8;              // lanes per row
+  uint32_t* entries = nullptr;     // [nnz] node id | sign << 31 (1 = outflow); freed once the sliced
+                                   // form below exists (tapes_export_csr rebuilds it on demand)
+  int spmv_group = 8;              // lanes per row of the CSR kernel
+
+  // the same structure in the form the product kernel streams (flux.cu): slices of 32 states
+  FluxSlices slices;
+  int flux_format = 1;             // 1 = slices, 0 = plain CSR
+  int level_unroll = 4;            // loads in flight per thread in level_kernel
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;
@@ -129,5 +152,16 @@ void rhs_host(Model& m, const double* h_p, double* h_out);
 
 // Number of device kernels launched by one rhs_device call.
 int64_t rhs_launch_count(const Model& m);
+
+// flux.cu ---------------------------------------------------------------------------------------
+// Encodes m.row_ptr / m.entries as slices (runs need at least min_run_lanes lanes).
+void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st);
+// dy/dt for the states row_lo <= i < row_hi from the node weights of the last weights pass; `up`
+// (may be null) fuses a Runge-Kutta stage update into the same pass.
+void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
+                        const StageUpdate* up);
+// Rebuilds the canonical CSR entries (ascending inside each row) from the slices into a device
+// buffer of nnz words.
+void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st);
 
 }  // namespace tapes

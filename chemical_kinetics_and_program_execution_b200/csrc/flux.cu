@@ -1,0 +1,289 @@
+// Sliced flux structure (sm_100a): the product  dy/dt = S * w  of the master-equation step.
+//
+// Reference behaviour being reproduced: accumulate-dp/dt (framework/tape_multiverse.scm:1271-1301)
+// adds -w at the original and +w at the adjusted window index of every flux term.  Here every
+// state gathers its terms instead (no atomics, fixed summation order).
+//
+// Why slices: with one lane per state and plain CSR, a warp's entry loads are 32 separate sectors
+// (ncu: 17 sectors per request, L1 throughput 88 %, profiles/r01_c_*).  Consecutive states gather
+// consecutive forest nodes, so 32 states are cut into runs "lane l holds first + rank(l)" that cost
+// 8 bytes per run instead of 4 bytes per entry, and the gathers of a run are one contiguous
+// segment of the weight vector.  What does not fall into runs is stored column-major (coalesced).
+#include <algorithm>
+#include <chrono>
+
+#include "engine.h"
+#include "primitives.cuh"
+
+namespace tapes {
+
+namespace {
+
+constexpr uint32_t kNone = 0xffffffffu;  // node ids stay below 2^31 - 1, so this is never an entry
+constexpr uint32_t kSignBit = 0x80000000u;
+constexpr int kThreads = 256;
+constexpr int kWarpsPerBlock = kThreads / 32;
+constexpr int kUnroll = 4;
+
+template <typename T>
+T* dalloc(size_t n, cudaStream_t st) {
+  void* p = nullptr;
+  TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st));
+  return (T*)p;
+}
+template <typename T>
+T* dkeep(size_t n) {
+  void* p = nullptr;
+  TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+  return (T*)p;
+}
+
+// One warp merges the (ascending) rows of its 32 states into one ascending stream and cuts it into
+// runs: a run continues while the next entry is the previous one + 1 and sits in a higher lane.
+// Runs with at least min_lanes lanes are kept as (first, mask); the entries of shorter ones go to
+// the lane's column list.  FILL = false counts, FILL = true writes.
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads) encode_slices_kernel(
+    const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ entries, uint64_t n_rows,
+    uint64_t n_slices, int min_lanes, uint32_t* __restrict__ slice_runs, uint32_t* __restrict__ slice_cols,
+    const uint64_t* __restrict__ slice_ptr, uint32_t* __restrict__ words) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t s = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  const uint64_t row = s * 32 + lane;
+  uint64_t cur = 0, end = 0;
+  if (row < n_rows) { cur = row_ptr[row]; end = row_ptr[row + 1]; }
+  uint32_t head = cur < end ? entries[cur] : kNone;
+  uint32_t next = cur + 1 < end ? entries[cur + 1] : kNone;  // one entry ahead hides the load latency
+
+  uint64_t run_at = 0, col_at = 0;
+  if (FILL) {
+    run_at = slice_ptr[s];
+    col_at = run_at + 2ull * ((slice_runs[s] + 1u) & ~1u);
+  }
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t n_runs = 0, my_cols = 0;
+  uint32_t first = 0, mask = 0, prev = 0;
+  int prev_lane = -1;
+
+  auto close = [&]() {
+    if (mask == 0) return;
+    if (__popc(mask) >= min_lanes) {
+      if (FILL && lane == 0) { words[run_at + 2ull * n_runs] = first; words[run_at + 2ull * n_runs + 1] = mask; }
+      ++n_runs;
+    } else if ((mask >> lane) & 1u) {
+      if (FILL) words[col_at + 32ull * my_cols + lane] = first + __popc(mask & below);
+      ++my_cols;
+    }
+  };
+
+  for (;;) {
+    const uint32_t m = __reduce_min_sync(0xffffffffu, head);
+    if (m == kNone) break;
+    const int win = __ffs(__ballot_sync(0xffffffffu, head == m)) - 1;  // entries are unique
+    const bool extend = mask != 0 && m == prev + 1 && ((m ^ prev) & kSignBit) == 0 && win > prev_lane;
+    if (!extend) { close(); first = m; mask = 0; }
+    mask |= 1u << win;
+    prev = m;
+    prev_lane = win;
+    if ((int)lane == win) {
+      ++cur;
+      head = next;
+      next = cur + 1 < end ? entries[cur + 1] : kNone;
+    }
+  }
+  close();
+
+  if (!FILL) {
+    const uint32_t cols = __reduce_max_sync(0xffffffffu, my_cols);
+    if (lane == 0) { slice_runs[s] = n_runs; slice_cols[s] = cols; }
+  } else {
+    if (lane == 0 && (n_runs & 1u)) {  // pad to an even number of run pairs (16-byte alignment)
+      words[run_at + 2ull * n_runs] = 0; words[run_at + 2ull * n_runs + 1] = 0;
+    }
+  }
+}
+
+__global__ void slice_sizes_kernel(const uint32_t* __restrict__ slice_runs, const uint32_t* __restrict__ slice_cols,
+                                   uint64_t n_slices, uint32_t* __restrict__ sizes) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n_slices) sizes[s] = 2u * ((slice_runs[s] + 1u) & ~1u) + 32u * slice_cols[s];
+}
+
+// Totals for the encoding facts: [0] runs, [1] entries held by runs, [2] run pairs incl. padding.
+__global__ void run_facts_kernel(const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
+                                 const uint32_t* __restrict__ words, uint64_t n_slices,
+                                 unsigned long long* __restrict__ facts) {
+  const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long runs = 0, held = 0, pairs = 0;
+  if (s < n_slices) {
+    const uint64_t at = slice_ptr[s];
+    runs = slice_runs[s];
+    pairs = (runs + 1ull) & ~1ull;
+    for (uint32_t j = 0; j < runs; ++j) held += __popc(words[at + 2ull * j + 1]);
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    runs += __shfl_down_sync(0xffffffffu, runs, d);
+    held += __shfl_down_sync(0xffffffffu, held, d);
+    pairs += __shfl_down_sync(0xffffffffu, pairs, d);
+  }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&facts[0], runs); atomicAdd(&facts[1], held); atomicAdd(&facts[2], pairs); }
+}
+
+// dy/dt for one slice per warp.  Every lane sums its state's terms in the order runs, then
+// columns; kUnroll gathers are in flight per lane.
+template <bool FUSED>
+__global__ void __launch_bounds__(kThreads) flux_slices_kernel(
+    const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
+    const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
+    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t s = slice_lo + (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (s >= slice_hi) return;
+  const uint64_t at = slice_ptr[s], stop = slice_ptr[s + 1];
+  const uint32_t n_runs = slice_runs[s];
+  const uint32_t n_pairs = (n_runs + 1u) & ~1u;
+  const uint2* __restrict__ runs = (const uint2*)(words + at);
+  const uint32_t* __restrict__ cols = words + at + 2ull * n_pairs;
+  const uint32_t n_cols = (uint32_t)((stop - at - 2ull * n_pairs) >> 5);
+  const uint32_t below = (1u << lane) - 1u;
+  double acc = 0.0;
+
+  for (uint32_t j0 = 0; j0 < n_runs; j0 += 32) {
+    const uint2 mine = j0 + lane < n_runs ? runs[j0 + lane] : make_uint2(0u, 0u);
+    const uint32_t here = min(32u, n_runs - j0);
+    for (uint32_t jj = 0; jj < here; jj += kUnroll) {  // lanes past `here` hold the empty run
+      uint32_t first[kUnroll], mask[kUnroll];
+      double x[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        first[u] = __shfl_sync(0xffffffffu, mine.x, (jj + u) & 31);
+        mask[u] = __shfl_sync(0xffffffffu, mine.y, (jj + u) & 31);
+      }
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u)
+        x[u] = ((mask[u] >> lane) & 1u) ? w[(first[u] & ~kSignBit) + __popc(mask[u] & below)] : 0.0;
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) acc += (first[u] & kSignBit) ? -x[u] : x[u];
+    }
+  }
+  for (uint32_t c0 = 0; c0 < n_cols; c0 += kUnroll) {
+    uint32_t v[kUnroll];
+    double x[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) v[u] = c0 + u < n_cols ? cols[32ull * (c0 + u) + lane] : kNone;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) x[u] = v[u] != kNone ? w[v[u] & ~kSignBit] : 0.0;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) acc += (v[u] & kSignBit) ? -x[u] : x[u];
+  }
+
+  const uint64_t row = s * 32 + lane;
+  if (row >= row_lo && row < row_hi) {
+    out[row] = acc;
+    if (FUSED) {  // Runge-Kutta stage update for this state (terms in tableau order)
+      double a = 0.0;
+      for (int j = 0; j < up.n; ++j) a += up.vec[j][row] * up.coef[j];
+      a += acc * up.coef_self;
+      up.stage[row] = up.y[row] + a * up.h;
+    }
+  }
+}
+
+// Writes every lane's entries back to CSR positions (runs, then columns) and sorts the row.
+__global__ void __launch_bounds__(kThreads) expand_slices_kernel(
+    const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
+    const uint32_t* __restrict__ words, const uint64_t* __restrict__ row_ptr, uint64_t n_rows,
+    uint64_t n_slices, uint32_t* __restrict__ entries) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t s = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  const uint64_t row = s * 32 + lane;
+  if (row >= n_rows) return;
+  const uint64_t at = slice_ptr[s], stop = slice_ptr[s + 1];
+  const uint32_t n_runs = slice_runs[s];
+  const uint32_t n_pairs = (n_runs + 1u) & ~1u;
+  const uint32_t n_cols = (uint32_t)((stop - at - 2ull * n_pairs) >> 5);
+  const uint32_t below = (1u << lane) - 1u;
+  const uint64_t lo = row_ptr[row];
+  uint64_t pos = lo;
+  for (uint32_t j = 0; j < n_runs; ++j) {
+    const uint32_t first = words[at + 2ull * j], mask = words[at + 2ull * j + 1];
+    if ((mask >> lane) & 1u) entries[pos++] = first + __popc(mask & below);
+  }
+  for (uint32_t c = 0; c < n_cols; ++c) {
+    const uint32_t v = words[at + 2ull * n_pairs + 32ull * c + lane];
+    if (v != kNone) entries[pos++] = v;
+  }
+  for (uint64_t a = lo + 1; a < pos; ++a) {  // insertion sort: canonical ascending order
+    const uint32_t v = entries[a];
+    uint64_t b = a;
+    while (b > lo && entries[b - 1] > v) { entries[b] = entries[b - 1]; --b; }
+    entries[b] = v;
+  }
+}
+
+}  // namespace
+
+void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
+  auto t0 = std::chrono::steady_clock::now();
+  FluxSlices& fs = m.slices;
+  const uint64_t n = m.n_states;
+  fs.n_slices = (n + 31) / 32;
+  fs.min_run_lanes = std::max(1, std::min(32, min_run_lanes));
+  const uint64_t S = fs.n_slices;
+  const unsigned grid = grid_for(S * 32, kThreads);
+  fs.slice_runs = dkeep<uint32_t>(S);
+  uint32_t* cols = dalloc<uint32_t>(S, st);
+  uint32_t* sizes = dalloc<uint32_t>(S, st);
+  encode_slices_kernel<false><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
+                                                        fs.slice_runs, cols, nullptr, nullptr);
+  slice_sizes_kernel<<<grid_for(S, kThreads), kThreads, 0, st>>>(fs.slice_runs, cols, S, sizes);
+  fs.slice_ptr = dkeep<uint64_t>(S + 1);
+  uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(S), st);
+  exclusive_scan_u32(sizes, S, fs.slice_ptr, scan_tmp, st);
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(&fs.n_words, fs.slice_ptr + S, 8, cudaMemcpyDeviceToHost, st));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  fs.words = dkeep<uint32_t>(fs.n_words);
+  TAPES_CUDA_CHECK(cudaMemsetAsync(fs.words, 0xff, fs.n_words * 4, st));  // columns default to "none"
+  encode_slices_kernel<true><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
+                                                       fs.slice_runs, cols, fs.slice_ptr, fs.words);
+  unsigned long long* facts = dalloc<unsigned long long>(3, st);
+  TAPES_CUDA_CHECK(cudaMemsetAsync(facts, 0, 24, st));
+  run_facts_kernel<<<grid_for(S, kThreads), kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, S, facts);
+  unsigned long long h_facts[3] = {0, 0, 0};
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(h_facts, facts, 24, cudaMemcpyDeviceToHost, st));
+  TAPES_CUDA_CHECK(cudaGetLastError());
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  fs.runs = h_facts[0];
+  fs.run_entries = h_facts[1];
+  fs.column_entries = m.nnz - fs.run_entries;
+  fs.column_slots = fs.n_words - 2 * h_facts[2];
+  cudaFreeAsync(cols, st); cudaFreeAsync(sizes, st); cudaFreeAsync(scan_tmp, st); cudaFreeAsync(facts, st);
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  m.stats.device_slices_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+}
+
+void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
+                        const StageUpdate* up) {
+  if (row_hi <= row_lo) return;
+  const FluxSlices& fs = m.slices;
+  const uint64_t slice_lo = row_lo / 32, slice_hi = (row_hi + 31) / 32;
+  const unsigned grid = grid_for((slice_hi - slice_lo) * 32, kThreads);
+  if (up)
+    flux_slices_kernel<true><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, d_out,
+                                                       slice_lo, slice_hi, row_lo, row_hi, *up);
+  else
+    flux_slices_kernel<false><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, d_out,
+                                                        slice_lo, slice_hi, row_lo, row_hi, StageUpdate());
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st) {
+  const FluxSlices& fs = m.slices;
+  expand_slices_kernel<<<grid_for(fs.n_slices * 32, kThreads), kThreads, 0, st>>>(
+      fs.slice_ptr, fs.slice_runs, fs.words, m.row_ptr, m.n_states, fs.n_slices, d_entries);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace tapes

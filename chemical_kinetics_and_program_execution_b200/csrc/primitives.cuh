@@ -12,6 +12,7 @@
 #include "cuda_check.h"
 
 namespace tapes {
+namespace {  // kernels here have internal linkage: every translation unit gets its own copy
 
 // ------------------------------------------------------------------------------------------
 // Exclusive scan: u32 counts -> u64 offsets.  Three kernels: tile sums, scan of the tile sums by
@@ -258,4 +259,5 @@ inline uint64_t* radix_sort_u64(uint64_t* keys, uint64_t* alt, uint64_t n, uint6
   return src;
 }
 
+}  // namespace
 }  // namespace tapes

@@ -84,17 +84,22 @@ int tapes_sync(void* model);
 
 /* Integer facts about a model, in this order: n_states, n_nodes, nnz, n_flux_rules, n_levels,
  * kernel launches per right-hand side, n_terms, n_sum_nodes, worlds_walked, leaf_worlds, seeds,
- * hash_inserts, hash_unique, alphabet, cl_k, spmv lanes per row.  Returns how many were written. */
+ * hash_inserts, hash_unique, alphabet, cl_k, CSR-kernel lanes per row, flux format (1 = slices of
+ * 32 states, 0 = plain CSR), slices, 32-bit words of the sliced form, runs, entries held by runs,
+ * entries held by columns, column slots incl. padding, minimum lanes of a run, loads in flight per
+ * thread of the level kernel.  Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
-/* Tuning knobs of a built model; currently "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row). */
+/* Tuning knobs of a built model: "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row of the plain-CSR
+ * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel). */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
-/* Build timings in ms: host rule enumeration, device expansion, device CSR assembly. */
+/* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing. */
 int tapes_model_timing(void* model, double* out, int capacity);
 
 /* Copies the CSR flux structure to host: row_ptr has n_states + 1 entries, entries has nnz
- * (node id | outflow << 31). */
+ * (node id | outflow << 31), ascending inside each row (rebuilt from the sliced form when that is
+ * the only resident one). */
 int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries);
 
 /* Copies the node weights of the most recent right-hand side to host (n_nodes doubles). */
