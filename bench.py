@@ -11,8 +11,14 @@ rate structure) and the CSR product S*w.  With N > 1 the rule set is dealt to th
 
 `value` is algorithmic GB/s of the whole step (bytes defined in DESIGN.md, "Algorithmic bytes"):
   step_bytes = 28 * nnz + 24 * n + 8 * n * (1 + 2 / (A - 1))
-`roofline` describes the dominant kernel, the CSR product, against the measured HBM peak:
+`roofline` describes the dominant kernel, the product S*w (flux_slices_kernel, 4.3 ms per launch;
+the 13 level_kernel launches of a step are at most 1 ms each and are summarised in
+`roofline_levels`), against the measured HBM peak, with the survey's CSR byte count
   spmv_bytes = 12 * nnz + 16 * n
+The kernel streams a compressed form of the CSR (runs of 32 states), so its DRAM traffic
+(`traffic`, from the ncu capture recorded in profiles/ncu_traffic.json) is below that figure and
+`frac` can exceed 1; `dram_frac` = traffic / time / peak is the fraction of the HBM roofline the
+kernel actually occupies.
 Prints exactly one JSON line on rank 0.
 """
 
@@ -50,7 +56,8 @@ def parse_args():
   ap.add_argument('--exchange', default='allreduce', choices=['rs_ag', 'allreduce'],
                   help='flux exchange for N > 1: reduce-scatter + all-gather, or one all-reduce')
   ap.add_argument('--e2e-steps', type=int, default=3)
-  ap.add_argument('--cpu-rules', type=int, default=2, help='rules in the CPU-baseline sample')
+  ap.add_argument('--cpu-rules', type=int, default=0,
+                  help='rules in the CPU-baseline sample (0 = one per usable host core, at most all)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   return ap.parse_args()
 
@@ -61,6 +68,40 @@ def step_bytes(nnz, n, size_a):
 
 def spmv_bytes(nnz, n):
   return 12.0 * nnz + 16.0 * n
+
+
+def level_bytes(info):
+  """Algorithmic bytes of all level_kernel launches of one step: 16 B per
+  child node (table read + weight write), 25 B per left-parent record, and per prefix group 24 B
+  (prefix, short marginal, parent progression) plus 8 B per parent weight."""
+  children = info['n_nodes']
+  return 16.0 * children + 25.0 * info.get('left_parents', 0) + 24.0 * info['hash_unique'] + 8.0 * info['hash_inserts']
+
+
+def recorded_traffic(kernel, info, args):
+  """DRAM bytes per launch (or per step for level_kernel) of `kernel` from the committed ncu
+  capture, when that capture was taken on this very structure; else None."""
+  try:
+    with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+      rec = json.load(f)
+    same = all(rec['config'].get(k) == v for k, v in
+               dict(size_a=args.size_a, cl_k=args.cl_k, rules=args.rules_per_gpu, seed=args.seed,
+                    nnz=info['nnz'], n_nodes=info['n_nodes']).items())
+    return float(rec['kernels'][kernel]['dram_bytes']) if same else None
+  except Exception:
+    return None
+
+
+def usable_cpu_workers(n_states, wanted):
+  """Worker processes for the CPU port: one per rule and core, bounded by host memory (each worker
+  holds the table, its marginals, the result and the accumulators: about 5 tables)."""
+  cores = len(os.sched_getaffinity(0))
+  try:
+    import psutil
+    by_mem = int(psutil.virtual_memory().available * 0.6 // (5 * 8 * n_states + (1 << 28)))
+  except Exception:
+    by_mem = 4
+  return max(1, min(cores, wanted, by_mem))
 
 
 def measured_peak():
@@ -189,8 +230,9 @@ def cpu_port_step(args, rules_subset, nnz_per_rule_state, reps=1):
   import multiprocessing as mp
   from chemical_kinetics_and_program_execution_b200 import parallel
   n_rules = len(rules_subset['rate'])
-  cores = min(len(os.sched_getaffinity(0)), n_rules)
-  jobs = [(f'cpu-sample-{i}', args.size_a, args.cl_k, parallel.split_rule_set(rules_subset, cores, i), args.seed + 2)
+  cl_k = getattr(args, 'cpu_cl_k', None) or args.cl_k
+  cores = usable_cpu_workers(args.size_a ** cl_k, n_rules)
+  jobs = [(f'cpu-sample-{i}', args.size_a, cl_k, parallel.split_rule_set(rules_subset, cores, i), args.seed + 2)
           for i in range(cores)]
   ctx = mp.get_context('fork')
   times = []
@@ -205,18 +247,32 @@ def cpu_port_step(args, rules_subset, nnz_per_rule_state, reps=1):
 
 def run_reference(args):
   """--impl reference: the CPU port of the reference's compute-dy/dt (oracle, merged mode; the
-  Gambit-C original cannot be built in this image) on a bounded sample of the same workload."""
+  Gambit-C original cannot be built in this image) with one worker process per rule on all usable
+  host cores.  Each step is a bounded sample of the bench workload: as many of rank 0's rules as
+  there are workers, on the full table when (warmup + steps) of those fit in about three minutes,
+  else on the same rule set with a shorter window (smaller cl_k; same per-term work)."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   from chemical_kinetics_and_program_execution_b200 import configs
   from oracle import oracle
   oracle.build()
-  n = args.size_a ** args.cl_k
   total_rules = args.rules_per_gpu * args.gpus
   rules = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)  # rank 0's rules
-  sample = {k: numpy.asarray(v)[:args.cpu_rules] for k, v in rules.items()}
-  # structural size of the sample (terms -> nnz) from the port's own term counter
+  n_sample = args.cpu_rules or usable_cpu_workers(args.size_a ** args.cl_k, args.rules_per_gpu)
+  sample = {k: numpy.asarray(v)[:n_sample] for k, v in rules.items()}
+  # calibrate on a short window, then pick the longest window whose run fits the time budget
+  budget_s = 170.0 / max(1, args.warmup + args.steps)
+  args.cpu_cl_k = min(args.cl_k, 5)
+  t_cal, _, _ = cpu_port_step(args, sample, None)
+  k_use, est = args.cpu_cl_k, t_cal
+  while k_use < args.cl_k:
+    nxt = est * args.size_a * (k_use + 1) / k_use  # terms per rule grow like k * A^(k-1)
+    if nxt > budget_s:
+      break
+    k_use, est = k_use + 1, nxt
+  args.cpu_cl_k = k_use
+  n = args.size_a ** k_use
   times, cores, counters = [], 1, None
   for _ in range(args.warmup + args.steps):
     t, cores, counters = cpu_port_step(args, sample, None)
@@ -226,13 +282,14 @@ def run_reference(args):
   bytes_step = step_bytes(nnz, n, args.size_a)
   ms = 1e3 * sum(timed) / len(timed)
   value = bytes_step / (ms * 1e-3) / 1e9
-  sample_desc = (f'first {args.cpu_rules} of {total_rules} rules of the same rule set on the full '
-                 f'{n}-state table, nnz={nnz}, merged-mode port, one process per rule')
+  sample_desc = (f'first {n_sample} of {total_rules} rules of the same rule set on the '
+                 f'{n}-state table (cl_k={k_use}; bench workload cl_k={args.cl_k}), nnz={nnz}, '
+                 f'merged-mode CPU port of compute-dy/dt, {cores} worker processes')
   line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus,
               steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
               scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
               config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a,
-                          cl_k=args.cl_k, n_states=n, rules_per_gpu=args.rules_per_gpu,
+                          cl_k=args.cl_k, n_states=args.size_a ** args.cl_k, rules_per_gpu=args.rules_per_gpu,
                           total_rules=total_rules, seed=args.seed, sample=sample_desc),
               cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample_desc),
               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
@@ -358,13 +415,23 @@ def run_b200(args):
   phase /= reps
   peak, peak_src = measured_peak()
   spmv_gbs = spmv_bytes(info['nnz'], n) / (phase[2] * 1e-3) / 1e9
-  roofline = dict(bound='hbm', kernel='spmv_kernel (S*w, CSR)', achieved=spmv_gbs, peak=peak,
-                  unit='GB/s', frac=spmv_gbs / peak, traffic=None, peak_source=peak_src,
+  flux_kernel = 'flux_slices_kernel' if info.get('flux_format', 0) == 1 else 'spmv_kernel'
+  traffic = recorded_traffic(flux_kernel, info, args)
+  roofline = dict(bound='hbm', kernel=flux_kernel + ' (S*w, one launch per step)', achieved=spmv_gbs, peak=peak,
+                  unit='GB/s', frac=spmv_gbs / peak, traffic=traffic,
+                  dram_frac=(traffic / (phase[2] * 1e-3) / 1e9 / peak) if traffic else None,
+                  peak_source=peak_src,
                   algorithmic_bytes_per_launch=spmv_bytes(info['nnz'], n),
                   kernel_ms=float(phase[2]),
                   phases_ms=dict(marginals_and_world_probs=float(phase[0]), forest_levels=float(phase[1]),
                                  spmv=float(phase[2])),
                   step_frac_of_peak=(step_bytes(info['nnz'], n, args.size_a) / (phase.sum() * 1e-3) / 1e9) / peak)
+  lv_gbs = level_bytes(info) / (phase[1] * 1e-3) / 1e9
+  lv_traffic = recorded_traffic('level_kernel', info, args)
+  roofline_levels = dict(bound='hbm', kernel=f'level_kernel ({info["n_levels"] - 1} launches per step, summed)',
+                         achieved=lv_gbs, peak=peak, unit='GB/s', frac=lv_gbs / peak, traffic=lv_traffic,
+                         dram_frac=(lv_traffic / (phase[1] * 1e-3) / 1e9 / peak) if lv_traffic else None,
+                         algorithmic_bytes_per_step=level_bytes(info), kernel_ms=float(phase[1]))
 
   # end to end through the reference-facing C ABI call with pinned HOST buffers
   e2e = None
@@ -392,12 +459,13 @@ def run_b200(args):
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import oracle
     oracle.build()
-    sample = {k: numpy.asarray(v)[:args.cpu_rules] for k, v in rules.items()}
+    n_sample = args.cpu_rules or usable_cpu_workers(n, args.rules_per_gpu)
+    sample = {k: numpy.asarray(v)[:n_sample] for k, v in rules.items()}
     t_cpu, cores, counters = cpu_port_step(args, sample, None)
     nnz_s = 2 * counters['acc_calls']
     cpu = dict(value=step_bytes(nnz_s, n, args.size_a) / t_cpu / 1e9, unit=UNIT, cores=cores, kind='port',
-               sample=(f'first {args.cpu_rules} of {args.rules_per_gpu} rules on the full {n}-state table '
-                       f'(nnz={nnz_s}), merged-mode CPU port of compute-dy/dt, one process per rule, '
+               sample=(f'first {n_sample} of {args.rules_per_gpu} rules on the full {n}-state table '
+                       f'(nnz={nnz_s}), merged-mode CPU port of compute-dy/dt, {cores} worker processes, '
                        f'{t_cpu:.1f} s'),
                seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu)
 
@@ -415,10 +483,12 @@ def run_b200(args):
                             if world > 1 else 'single GPU',
                             l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
                 clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches_total / world) * args.steps,
-                roofline=roofline, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
+                roofline=roofline, roofline_levels=roofline_levels, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
                 states_expanded_per_s=(info['n_nodes'] + info['worlds_walked']) / max(expand_s, 1e-9),
                 build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
-                           hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique']))
+                           hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],
+                           flux_slices={k: info.get(k) for k in ('n_slices', 'slice_words', 'runs', 'run_entries',
+                                                                  'column_entries', 'column_slots')}))
     print(json.dumps(line), flush=True)
   if world > 1:
     dist.destroy_process_group()

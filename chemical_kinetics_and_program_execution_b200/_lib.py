@@ -112,7 +112,8 @@ MODEL_INFO_FIELDS = (
     'n_states', 'n_nodes', 'nnz', 'n_flux_rules', 'n_levels', 'launches_per_rhs', 'n_terms',
     'n_sum_nodes', 'worlds_walked', 'leaf_worlds', 'seeds', 'hash_inserts', 'hash_unique',
     'alphabet', 'cl_k', 'spmv_lanes_per_row', 'flux_format', 'n_slices', 'slice_words', 'runs',
-    'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll')
+    'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll',
+    'irregular_levels', 'left_parents')
 
 
 def model_info(model):

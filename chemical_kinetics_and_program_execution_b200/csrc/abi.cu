@@ -222,7 +222,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                        m.stats.hash_unique, (int64_t)m.A, (int64_t)m.k, (int64_t)m.spmv_group,
                        (int64_t)m.flux_format, (int64_t)m.slices.n_slices, (int64_t)m.slices.n_words,
                        (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
-                       (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll};
+                       (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
+                       m.stats.irregular_levels, m.stats.left_parents};
   int n = (int)(sizeof(v) / sizeof(v[0]));
   if (n > capacity) n = capacity;
   for (int i = 0; i < n; ++i) out[i] = v[i];
@@ -235,6 +236,10 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
   if (std::strcmp(key, "spmv_lanes") == 0 &&
       (value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
     m.spmv_group = (int)value;
+    return 0;
+  }
+  if (std::strcmp(key, "flux_unroll") == 0 && (value == 4 || value == 6 || value == 8)) {
+    m.flux_unroll = (int)value;
     return 0;
   }
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {

@@ -46,6 +46,42 @@ T* dkeep(size_t n) {  // allocations that live as long as the model
   return (T*)p;
 }
 
+// Scratch for one phase of a level: sizes are declared first, then one cudaMalloc backs them all.
+struct Slab {
+  char* base = nullptr;
+  size_t bytes = 0;
+  std::vector<size_t> offsets;
+  Slab() {}
+  Slab(const Slab&) = delete;
+  Slab& operator=(const Slab&) = delete;
+  Slab& operator=(Slab&& o) {
+    if (this != &o) {
+      release();
+      base = o.base; bytes = o.bytes; offsets = std::move(o.offsets);
+      o.base = nullptr; o.bytes = 0; o.offsets.clear();
+    }
+    return *this;
+  }
+  ~Slab() { release(); }
+  size_t want(size_t b) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    offsets.push_back(bytes);
+    bytes += std::max<size_t>(b, 1);
+    return offsets.size() - 1;
+  }
+  void commit() {
+    void* p = nullptr;
+    TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+    base = (char*)p;
+  }
+  template <typename T>
+  T* at(size_t i) const { return (T*)(base + offsets[i]); }
+  void release() {
+    if (base) cudaFree(base);
+    base = nullptr; bytes = 0; offsets.clear();
+  }
+};
+
 struct Consts {
   uint32_t A;
   int k;
@@ -66,8 +102,10 @@ struct Frontier {
 // ---------------------------------------------------------------------------------------------
 // Expansion pass 1: classify every frontier node and hash-insert right-chain prefixes.
 // ---------------------------------------------------------------------------------------------
-__global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __restrict__ lflag,
-                                uint32_t* __restrict__ tflag, uint8_t* __restrict__ kflag) {
+__global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c, HashSet hs,
+                                                            uint32_t* __restrict__ lflag, uint32_t* __restrict__ tflag,
+                                                            uint8_t* __restrict__ kflag, uint64_t* __restrict__ unique,
+                                                            unsigned long long* __restrict__ n_unique) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < f.n;
   bool haskey = false;
@@ -92,30 +130,16 @@ __global__ void classify_kernel(Frontier f, Consts c, HashSet hs, uint32_t* __re
     tflag[i] = (fl & FL_TERM) ? 1u : 0u;
     kflag[i] = haskey ? 1 : 0;
   }
-  hash_insert_warp(hs, haskey, key, pa);
+  // keys seen for the first time are compacted into the new frontier's group list as they are
+  // inserted (block scan, one atomic per block); the list is put in canonical order afterwards
+  const bool fresh = hash_insert_warp(hs, haskey, key, pa);
+  block_append_u64(fresh, key, unique, n_unique);
 }
 
-__global__ void slot_flag_kernel(HashSet hs, uint32_t* __restrict__ flag) {
-  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h <= hs.mask) flag[h] = hs.keys[h] != kEmptyKey ? 1u : 0u;
-}
-
-__global__ void slot_gather_kernel(HashSet hs, const uint64_t* __restrict__ rank,
-                                   uint64_t* __restrict__ out) {
-  const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (h <= hs.mask) {
-    const uint64_t k = hs.keys[h];
-    if (k != kEmptyKey) out[rank[h]] = k;
-  }
-}
-
-__device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t n, uint64_t key) {
-  uint32_t lo = 0, hi = n;
-  while (lo < hi) {
-    const uint32_t mid = lo + ((hi - lo) >> 1);
-    if (a[mid] < key) lo = mid + 1; else hi = mid;
-  }
-  return lo;
+// ranks[slot of sorted_keys[g]] = g
+__global__ void rank_slots_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs) {
+  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_keys) hs.ranks[hash_slot(hs, sorted_keys[g])] = g;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -127,8 +151,7 @@ __device__ __forceinline__ uint32_t lower_bound_u64(const uint64_t* a, uint32_t 
 __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ lflag,
                             const uint32_t* __restrict__ tflag, const uint8_t* __restrict__ kflag,
                             const uint64_t* __restrict__ lrank, const uint64_t* __restrict__ trank,
-                            uint64_t n_left_parents, const uint64_t* __restrict__ sorted_keys,
-                            uint32_t n_keys, Frontier next, uint32_t* __restrict__ lp_gid,
+                            uint64_t n_left_parents, HashSet hs, Frontier next, uint32_t* __restrict__ lp_gid,
                             uint32_t* __restrict__ lp_io, uint8_t* __restrict__ lp_len,
                             uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
                             uint32_t* __restrict__ keyrank) {
@@ -172,7 +195,7 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
   }
   if (kflag[i]) {
     const uint64_t key = ((uint64_t)seed << 32) | (io % c.M);
-    keyrank[i] = lower_bound_u64(sorted_keys, n_keys, key);
+    keyrank[i] = hs.ranks[hash_slot(hs, key)];
   } else {
     keyrank[i] = kNoRank;
   }
@@ -185,7 +208,7 @@ __global__ void emit_groups_kernel(const uint64_t* __restrict__ sorted_keys, uin
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_keys) return;
   const uint64_t key = sorted_keys[g];
-  const uint32_t po = (uint32_t)key, pa = hash_lookup(hs, key), seed = (uint32_t)(key >> 32);
+  const uint32_t po = (uint32_t)key, pa = hs.vals[hash_slot(hs, key)], seed = (uint32_t)(key >> 32);
   g_prefix[g] = po;
   const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
   for (uint32_t x = 0; x < c.A; ++x) {
@@ -238,6 +261,25 @@ __global__ void group_sort_kernel(const uint64_t* __restrict__ ptr, uint64_t n_g
     while (b > lo && vals[b - 1] > v) { vals[b] = vals[b - 1]; --b; }
     vals[b] = v;
   }
+}
+
+// Parent lists are almost always arithmetic progressions of node ids (the parents of a prefix group
+// differ in the dropped, most significant digit only): store (first, stride, count) and count the
+// groups that are not.
+__global__ void group_progression_kernel(const uint64_t* __restrict__ ptr, const uint32_t* __restrict__ parents,
+                                         uint64_t n_groups, uint32_t* __restrict__ first,
+                                         uint32_t* __restrict__ stride, uint32_t* __restrict__ count,
+                                         unsigned long long* __restrict__ irregular) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const uint64_t lo = ptr[g], hi = ptr[g + 1];
+  const uint32_t n = (uint32_t)(hi - lo);
+  const uint32_t f = n ? parents[lo] : 0u;
+  const uint32_t d = n > 1 ? parents[lo + 1] - f : 0u;
+  bool ok = true;
+  for (uint64_t e = lo + 2; e < hi; ++e) ok = ok && (parents[e] - parents[e - 1] == d);
+  first[g] = f; stride[g] = d; count[g] = n;
+  if (!ok) atomicAdd(irregular, 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -331,8 +373,8 @@ __device__ __forceinline__ double child_weight(double w_parent, double p_long, d
 // Loads are issued U at a time before the divisions and stores that depend on them: the kernel is
 // bound by HBM latency x bandwidth, and one load in flight per thread reaches ~60 % of peak only
 // (profiles/r01_c_*).  wr and ww are the same vector: reads touch earlier levels only.
-template <int U>
-__global__ void __launch_bounds__(kThreads) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
+template <int U, bool PROGRESSIONS>
+__global__ void __launch_bounds__(kThreads, 5) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
                                                          uint32_t warp_step_q, uint32_t warp_step_r,
                                                          const double* __restrict__ wr, double* __restrict__ ww) {
   if (blockIdx.x < left_blocks) {
@@ -362,18 +404,29 @@ __global__ void __launch_bounds__(kThreads) level_kernel(Tables t, Consts c, Lev
     double total = 0.0, p_short = 0.0;
     uint32_t prefix = 0;
     if (g < lv.n_groups) {
-      const uint64_t lo = lv.g_ptr[g], hi = lv.g_ptr[g + 1];
       prefix = lv.g_prefix[g];
       p_short = table(t, c.k - 1)[prefix];
-      for (uint64_t e = lo; e < hi; e += U) {
-        uint32_t id[U];
-        double v[U];
+      if (PROGRESSIONS) {  // parents first, first + stride, ...
+        const uint32_t first = lv.g_first[g], stride = lv.g_stride[g], n = lv.g_count[g];
+        for (uint32_t e = 0; e < n; e += U) {
+          double v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) id[u] = e + u < hi ? lv.g_parents[e + u] : kNoRank;
+          for (int u = 0; u < U; ++u) v[u] = e + u < n ? wr[first + (e + u) * stride] : 0.0;  // node ids stay below 2^31
 #pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = id[u] != kNoRank ? wr[id[u]] : 0.0;
+          for (int u = 0; u < U; ++u) total += v[u];  // ascending id order; + 0.0 leaves the sum as it is
+        }
+      } else {
+        const uint64_t lo = lv.g_ptr[g], hi = lv.g_ptr[g + 1];
+        for (uint64_t e = lo; e < hi; e += U) {
+          uint32_t id[U];
+          double v[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) total += v[u];  // ascending id order; + 0.0 leaves the sum as it is
+          for (int u = 0; u < U; ++u) id[u] = e + u < hi ? lv.g_parents[e + u] : kNoRank;
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = id[u] != kNoRank ? wr[id[u]] : 0.0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) total += v[u];
+        }
       }
     }
     const uint32_t groups_here = (uint32_t)min((uint64_t)32, (uint64_t)lv.n_groups - g0);
@@ -482,9 +535,14 @@ Model::~Model() {
   fr(rule_ptr); fr(step_kind); fr(step_len); fr(step_long); fr(step_short); fr(step_prob); fr(rule_w);
   for (Level& lv : levels) {
     fr(lv.root_rule); fr(lv.lp_gid); fr(lv.lp_io); fr(lv.lp_len); fr(lv.g_prefix); fr(lv.g_ptr); fr(lv.g_parents);
+    fr(lv.g_first); fr(lv.g_stride); fr(lv.g_count);
   }
   fr(node_w); fr(row_ptr); fr(entries); fr(marg); fr(d_marg_off); fr(d_in); fr(d_out);
   fr(slices.slice_ptr); fr(slices.slice_runs); fr(slices.words);
+  if (copy_stream) {
+    cudaStreamDestroy(copy_stream);
+    for (cudaEvent_t e : copy_events) if (e) cudaEventDestroy(e);
+  }
   if (own_stream && stream) cudaStreamDestroy(stream);
 }
 
@@ -580,6 +638,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.stats.seeds = n_seeds;
 
   // ---- level-synchronous expansion ----
+  // Scratch memory comes in two slabs per level (one sized before the level's counts are known,
+  // one after): growing the stream-ordered pool by hundreds of small requests cost 2.9 s of a
+  // 3.2 s first build (profiles/r01_e_*).
   auto t_expand = std::chrono::steady_clock::now();
   struct EdgeChunk { uint32_t* row; uint32_t* val; uint64_t n; };
   std::vector<EdgeChunk> edge_chunks;
@@ -589,6 +650,15 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   Level cur_level;
   cur_level.base = 0;
   cur_level.n_roots = (uint32_t)roots.size();
+  Slab cur_slab;  // owns the arrays of `cur`
+  auto plan_frontier = [](Slab& slab, uint64_t n, size_t idx[5]) {
+    idx[0] = slab.want(n * 4); idx[1] = slab.want(n * 4); idx[2] = slab.want(n * 4);
+    idx[3] = slab.want(n); idx[4] = slab.want(n);
+  };
+  auto bind_frontier = [](const Slab& slab, const size_t idx[5], Frontier& f) {
+    f.io = slab.at<uint32_t>(idx[0]); f.ia = slab.at<uint32_t>(idx[1]); f.seed = slab.at<uint32_t>(idx[2]);
+    f.meta = slab.at<uint8_t>(idx[3]); f.flags = slab.at<uint8_t>(idx[4]);
+  };
   if (cur.n) {
     std::vector<uint32_t> h_io(cur.n), h_ia(cur.n), h_seed(cur.n), h_rule(cur.n);
     std::vector<uint8_t> h_meta(cur.n), h_fl(cur.n);
@@ -597,8 +667,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       h_meta[i] = roots[i].meta; h_fl[i] = roots[i].flags;
     }
     cur_level.root_rule = dkeep<uint32_t>(cur.n);
-    cur.io = dalloc<uint32_t>(cur.n, st); cur.ia = dalloc<uint32_t>(cur.n, st);
-    cur.seed = dalloc<uint32_t>(cur.n, st); cur.meta = dalloc<uint8_t>(cur.n, st); cur.flags = dalloc<uint8_t>(cur.n, st);
+    size_t fi[5];
+    plan_frontier(cur_slab, cur.n, fi);
+    cur_slab.commit();
+    bind_frontier(cur_slab, fi, cur);
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.io, h_io.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.ia, h_ia.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(cur.seed, h_seed.data(), cur.n * 4, cudaMemcpyHostToDevice, st));
@@ -620,48 +692,40 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     if (cur_level.base + cur.n >= 0x7fffffffull) throw std::runtime_error("extension forest exceeds 2^31 nodes");
     m.stats.levels++;
     const uint64_t n = cur.n;
+
     // pass 1: classify + hash-dedup of the right-chain prefixes
     uint64_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
+    Slab s1;
+    const size_t i_keys = s1.want(cap * 8), i_vals = s1.want(cap * 4), i_ranks = s1.want(cap * 4);
+    const size_t i_lflag = s1.want(n * 4), i_tflag = s1.want(n * 4), i_kflag = s1.want(n);
+    const size_t i_lrank = s1.want((n + 1) * 8), i_trank = s1.want((n + 1) * 8);
+    const size_t i_scan = s1.want(scan_tmp_elems(std::max<uint64_t>(n, 256ull * 1184)) * 8);
+    const size_t i_unique = s1.want(n * 8), i_counters = s1.want(16);
+    s1.commit();
     HashSet hs;
-    hs.keys = dalloc<uint64_t>(cap, st);
-    hs.vals = dalloc<uint32_t>(cap, st);
+    hs.keys = s1.at<uint64_t>(i_keys); hs.vals = s1.at<uint32_t>(i_vals); hs.ranks = s1.at<uint32_t>(i_ranks);
     hs.mask = cap - 1;
+    uint32_t* lflag = s1.at<uint32_t>(i_lflag);
+    uint32_t* tflag = s1.at<uint32_t>(i_tflag);
+    uint8_t* kflag = s1.at<uint8_t>(i_kflag);
+    uint64_t* lrank = s1.at<uint64_t>(i_lrank);
+    uint64_t* trank = s1.at<uint64_t>(i_trank);
+    uint64_t* scan_tmp = s1.at<uint64_t>(i_scan);
+    uint64_t* keys_a = s1.at<uint64_t>(i_unique);
+    unsigned long long* counters = s1.at<unsigned long long>(i_counters);  // [0] unique keys, [1] irregular groups
     TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
-    uint32_t* lflag = dalloc<uint32_t>(n, st);
-    uint32_t* tflag = dalloc<uint32_t>(n, st);
-    uint8_t* kflag = dalloc<uint8_t>(n, st);
-    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, tflag, kflag);
-    uint64_t* lrank = dalloc<uint64_t>(n + 1, st);
-    uint64_t* trank = dalloc<uint64_t>(n + 1, st);
-    uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(std::max<uint64_t>(cap, 256ull * 1184)), st);
+    TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, tflag, kflag, keys_a, counters);
     exclusive_scan_u32(lflag, n, lrank, scan_tmp, st);
     exclusive_scan_u32(tflag, n, trank, scan_tmp, st);
-    uint32_t* sflag = dalloc<uint32_t>(cap, st);
-    uint64_t* srank = dalloc<uint64_t>(cap + 1, st);
-    slot_flag_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, sflag);
-    exclusive_scan_u32(sflag, cap, srank, scan_tmp, st);
     uint64_t h_tot[3];
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], lrank + n, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], trank + n, 8, cudaMemcpyDeviceToHost, st));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], srank + cap, 8, cudaMemcpyDeviceToHost, st));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], counters, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
     const uint64_t NL = h_tot[0], NT = h_tot[1], NG = h_tot[2];
     if ((NL + NG) * (uint64_t)m.A >= 0xffffffffull) throw std::runtime_error("level too large");
-
-    // unique right-chain prefixes in canonical (seed, prefix) order
-    uint64_t* keys_a = dalloc<uint64_t>(NG, st);
-    uint64_t* keys_b = dalloc<uint64_t>(NG, st);
-    uint64_t* sorted = keys_a;
-    if (NG) {
-      slot_gather_kernel<<<grid_for(cap, kThreads), kThreads, 0, st>>>(hs, srank, keys_a);
-      const RadixPlan plan = radix_plan(NG);
-      uint32_t* rh = dalloc<uint32_t>(256ull * plan.blocks, st);
-      uint64_t* ro = dalloc<uint64_t>(256ull * plan.blocks + 1, st);
-      sorted = radix_sort_u64(keys_a, keys_b, NG, significant, rh, ro, scan_tmp, st);
-      dfree(rh, st); dfree(ro, st);
-    }
-    dfree(sflag, st); dfree(srank, st);
 
     // pass 2: children, parent records, flux edges
     Frontier next;
@@ -670,12 +734,22 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     next_level.base = cur_level.base + n;
     next_level.n_left = (uint32_t)NL;
     next_level.n_groups = (uint32_t)NG;
-    if (next.n) {
-      next.io = dalloc<uint32_t>(next.n, st);
-      next.ia = dalloc<uint32_t>(next.n, st);
-      next.seed = dalloc<uint32_t>(next.n, st);
-      next.meta = dalloc<uint8_t>(next.n, st);
-      next.flags = dalloc<uint8_t>(next.n, st);
+    const RadixPlan plan = radix_plan(std::max<uint64_t>(NG, 1));
+    Slab s2;  // owns `next`; lives until the end of the next level
+    size_t fi[5];
+    plan_frontier(s2, next.n, fi);
+    const size_t i_keys_b = s2.want(NG * 8), i_rh = s2.want(256ull * plan.blocks * 4);
+    const size_t i_ro = s2.want((256ull * plan.blocks + 1) * 8), i_keyrank = s2.want(n * 4), i_cnt = s2.want(NG * 4);
+    s2.commit();
+    bind_frontier(s2, fi, next);
+    uint32_t* keyrank = s2.at<uint32_t>(i_keyrank);
+
+    // unique right-chain prefixes in canonical (seed, prefix) order, and their rank by slot
+    uint64_t* sorted = keys_a;
+    if (NG) {
+      sorted = radix_sort_u64(keys_a, s2.at<uint64_t>(i_keys_b), NG, significant, s2.at<uint32_t>(i_rh),
+                              s2.at<uint64_t>(i_ro), scan_tmp, st);
+      rank_slots_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs);
     }
     if (NL) {
       next_level.lp_gid = dkeep<uint32_t>(NL);
@@ -683,17 +757,16 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       next_level.lp_len = dkeep<uint8_t>(NL);
     }
     EdgeChunk ec{nullptr, nullptr, 2 * NT};
-    if (NT) { ec.row = dalloc<uint32_t>(2 * NT, st); ec.val = dalloc<uint32_t>(2 * NT, st); }
-    uint32_t* keyrank = dalloc<uint32_t>(n, st);
+    if (NT) { ec.row = dkeep<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT; }  // one allocation for both
     emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, kflag, lrank, trank,
-                                                          NL, sorted, (uint32_t)NG, next, next_level.lp_gid,
-                                                          next_level.lp_io, next_level.lp_len, ec.row, ec.val, keyrank);
+                                                          NL, hs, next, next_level.lp_gid, next_level.lp_io,
+                                                          next_level.lp_len, ec.row, ec.val, keyrank);
     if (NG) {
       next_level.g_prefix = dkeep<uint32_t>(NG);
       emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
                                                                      NL * (uint64_t)m.A, next_level.g_prefix);
       // parent lists of the prefix groups
-      uint32_t* cnt = dalloc<uint32_t>(NG, st);
+      uint32_t* cnt = s2.at<uint32_t>(i_cnt);
       TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
       group_count_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cnt);
       next_level.g_ptr = dkeep<uint64_t>(NG + 1);
@@ -707,23 +780,39 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base,
                                                                        next_level.g_ptr, cnt, next_level.g_parents);
       group_sort_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(next_level.g_ptr, NG, next_level.g_parents);
-      dfree(cnt, st);
+      next_level.g_first = dkeep<uint32_t>(NG);
+      next_level.g_stride = dkeep<uint32_t>(NG);
+      next_level.g_count = dkeep<uint32_t>(NG);
+      group_progression_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
+          next_level.g_ptr, next_level.g_parents, NG, next_level.g_first, next_level.g_stride,
+          next_level.g_count, counters + 1);
+      unsigned long long h_irregular = 0;
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_irregular, counters + 1, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      auto drop = [](auto*& q) { cudaFree((void*)q); q = nullptr; };
+      if (h_irregular == 0 && !std::getenv("TAPES_KEEP_PARENT_LISTS")) {
+        drop(next_level.g_ptr); drop(next_level.g_parents);
+      } else {
+        drop(next_level.g_first); drop(next_level.g_stride); drop(next_level.g_count);
+        m.stats.irregular_levels++;
+      }
       m.stats.hash_inserts += (int64_t)n_par;
       m.stats.hash_unique += (int64_t)NG;
       m.stats.sum_nodes += (int64_t)NG;
     }
     TAPES_CUDA_CHECK(cudaGetLastError());
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
     if (NT) edge_chunks.push_back(ec);
     total_terms += NT;
+    m.stats.left_parents += (int64_t)NL;
 
     m.levels.push_back(cur_level);
-    dfree(cur.io, st); dfree(cur.ia, st); dfree(cur.seed, st); dfree(cur.meta, st); dfree(cur.flags, st);
-    dfree(lflag, st); dfree(tflag, st); dfree(kflag, st); dfree(lrank, st); dfree(trank, st);
-    dfree(scan_tmp, st); dfree(keys_a, st); dfree(keys_b, st); dfree(keyrank, st);
-    dfree(hs.keys, st); dfree(hs.vals, st);
+    s1.release();
+    cur_slab = std::move(s2);  // ownership of `next` moves with the frontier
     cur = next;
     cur_level = next_level;
   }
+  cur_slab.release();
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
   m.stats.nodes = (int64_t)m.n_nodes;
   m.stats.terms = (int64_t)total_terms;
@@ -746,7 +835,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (EdgeChunk& ec : edge_chunks) {
       group_fill_vals_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.val, ec.n, m.row_ptr, cnt, m.entries);
-      dfree(ec.row, st); dfree(ec.val, st);
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      cudaFree(ec.row);  // row and val share one allocation
+      ec.row = ec.val = nullptr;
     }
     group_sort_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(m.row_ptr, n, m.entries);
     dfree(cnt, st); dfree(scan_tmp, st);
@@ -758,8 +849,11 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     const int v = std::atoi(g);
     if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) m.spmv_group = v;
   }
-  m.level_unroll = m.A <= 2 ? 2 : 4;  // measured on B200 (A = 10): 1: 7.15, 2: 6.49, 4: 6.02, 5: 6.56, 8: 7.17 ms
+  // batch size that wastes the fewest slots of the last batch; measured on B200 (A = 10, n = 1e8,
+  // 24 rules): 1: 7.79, 2: 6.29, 4: 6.05, 5: 5.48, 8: 6.40 ms
+  m.level_unroll = m.A <= 2 ? 2 : ((m.A + 4) / 5 * 5 - m.A <= (m.A + 3) / 4 * 4 - m.A ? 5 : 4);
   if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
+  if (const char* g = std::getenv("TAPES_FLUX_UNROLL")) m.flux_unroll = std::atoi(g);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
 
@@ -823,17 +917,17 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       const unsigned left_blocks = lv.n_left ? grid_for(lv.n_left, kThreads) : 0;
       const unsigned group_blocks = lv.n_groups ? grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads) : 0;
       const uint32_t q = 32u / c.A, r = 32u % c.A;
-      // loads in flight per thread: all A children at once when A is small, else batches
-      if (m.level_unroll >= 8)
-        level_kernel<8><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
-      else if (m.level_unroll >= 5)
-        level_kernel<5><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
-      else if (m.level_unroll >= 4)
-        level_kernel<4><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
-      else if (m.level_unroll >= 2)
-        level_kernel<2><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
-      else
-        level_kernel<1><<<left_blocks + group_blocks, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w);
+      const unsigned grid = left_blocks + group_blocks;
+      const bool prog = lv.g_first != nullptr;
+#define TAPES_LEVEL(U_)                                                                                   \
+  (prog ? level_kernel<U_, true><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
+        : level_kernel<U_, false><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
+      if (m.level_unroll >= 8) TAPES_LEVEL(8);
+      else if (m.level_unroll >= 5) TAPES_LEVEL(5);
+      else if (m.level_unroll >= 4) TAPES_LEVEL(4);
+      else if (m.level_unroll >= 2) TAPES_LEVEL(2);
+      else TAPES_LEVEL(1);
+#undef TAPES_LEVEL
     }
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
@@ -923,14 +1017,34 @@ void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_
 }
 
 void rhs_host(Model& m, const double* h_p, double* h_out) {
-  const size_t bytes = (size_t)m.n_states * 8;
+  const uint64_t n = m.n_states;
+  const size_t bytes = (size_t)n * 8;
   if (!m.d_in) {
-    m.d_in = dkeep<double>(m.n_states);
-    m.d_out = dkeep<double>(m.n_states);
+    m.d_in = dkeep<double>(n);
+    m.d_out = dkeep<double>(n);
+    TAPES_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t& e : m.copy_events) TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
-  rhs_device(m, m.d_in, m.d_out, m.stream);
-  TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
+  // large tables: the result goes back in row blocks while the product of the next block runs
+  const int blocks = n >= (1ull << 22) ? Model::kCopyBlocks : 1;
+  if (blocks == 1) {
+    rhs_device(m, m.d_in, m.d_out, m.stream);
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+    return;
+  }
+  launch_weights(m, m.d_in, m.stream, nullptr);
+  const uint64_t per = ((n + blocks - 1) / blocks + 31) & ~31ull;
+  for (int b = 0; b < blocks; ++b) {
+    const uint64_t lo = std::min<uint64_t>(n, per * b), hi = std::min<uint64_t>(n, lo + per);
+    if (hi <= lo) break;
+    launch_flux(m, m.d_out, lo, hi, m.stream);
+    TAPES_CUDA_CHECK(cudaEventRecord(m.copy_events[b], m.stream));
+    TAPES_CUDA_CHECK(cudaStreamWaitEvent(m.copy_stream, m.copy_events[b], 0));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out + lo, m.d_out + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, m.copy_stream));
+  }
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(m.copy_stream));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
 }
 

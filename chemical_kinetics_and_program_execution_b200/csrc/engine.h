@@ -41,6 +41,11 @@ struct Level {
   uint64_t* g_ptr = nullptr;      // [n_groups + 1] offsets into g_parents
   uint32_t* g_parents = nullptr;  // parent node ids, ascending inside each group
   uint64_t n_group_parents = 0;
+  // when every parent list of the level is an arithmetic progression (the usual case) the lists
+  // are replaced by first + j * stride, j < count, and g_ptr / g_parents are null
+  uint32_t* g_first = nullptr;
+  uint32_t* g_stride = nullptr;
+  uint32_t* g_count = nullptr;
 };
 
 // The flux structure cut into slices of 32 consecutive states, one warp lane per state.  Consecutive
@@ -64,6 +69,8 @@ struct BuildStats {
   int64_t worlds_walked = 0, leaf_worlds = 0, flux_rules = 0, seeds = 0;
   int64_t nodes = 0, sum_nodes = 0, terms = 0, levels = 0;  // sum_nodes = prefix groups
   int64_t hash_inserts = 0, hash_unique = 0;
+  int64_t irregular_levels = 0;  // levels whose parent lists are kept explicitly
+  int64_t left_parents = 0;      // parent records of left extensions / left shifts, all levels
   double host_enumerate_ms = 0, device_expand_ms = 0, device_csr_ms = 0, device_slices_ms = 0;
 };
 
@@ -100,6 +107,7 @@ struct Model {
   FluxSlices slices;
   int flux_format = 1;             // 1 = slices, 0 = plain CSR
   int level_unroll = 4;            // loads in flight per thread in level_kernel
+  int flux_unroll = 8;             // gathers in flight per lane in flux_slices_kernel
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;
@@ -108,8 +116,11 @@ struct Model {
   uint64_t marg_total = 0;
 
   // staging for the host-buffer entry point
+  static constexpr int kCopyBlocks = 8;
   double* d_in = nullptr;
   double* d_out = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t copy_events[kCopyBlocks] = {};
 
   BuildStats stats;
   int64_t launches_per_rhs = 0;
@@ -147,7 +158,8 @@ void flux_rows_device(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi,
 // returns ms for (marginals + leaf-world probabilities, forest levels, S * w).
 void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_t stream, float ms[3]);
 
-// Host-buffer variant (the c_compute_dy_dt path): H2D, rhs_device, D2H, synchronise.
+// Host-buffer variant (the c_compute_dy_dt path): H2D, weights, then the product in row blocks
+// with the D2H copy of each block overlapping the product of the next; synchronises.
 void rhs_host(Model& m, const double* h_p, double* h_out);
 
 // Number of device kernels launched by one rhs_device call.

@@ -23,7 +23,6 @@ constexpr uint32_t kNone = 0xffffffffu;  // node ids stay below 2^31 - 1, so thi
 constexpr uint32_t kSignBit = 0x80000000u;
 constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
-constexpr int kUnroll = 4;
 
 template <typename T>
 T* dalloc(size_t n, cudaStream_t st) {
@@ -104,6 +103,65 @@ __global__ void __launch_bounds__(kThreads) encode_slices_kernel(
   }
 }
 
+// The same encoding for min_lanes = 32, where a run is exactly "value v in lane 0 and v + l in every
+// lane l": only lane 0's entries have to be visited (tens of steps instead of one per entry of the
+// slice).  Every lane walks its own ascending row once; the entries it matched are remembered in a
+// bit mask (rows longer than 128 entries keep their tail in columns).
+template <bool FILL>
+__global__ void __launch_bounds__(kThreads) encode_full_runs_kernel(
+    const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ entries, uint64_t n_rows,
+    uint64_t n_slices, uint32_t* __restrict__ slice_runs, uint32_t* __restrict__ slice_cols,
+    const uint64_t* __restrict__ slice_ptr, uint32_t* __restrict__ words) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t s = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  const uint64_t row = s * 32 + lane;
+  uint64_t lo = 0, hi = 0;
+  if (row < n_rows) { lo = row_ptr[row]; hi = row_ptr[row + 1]; }
+  const uint32_t len = (uint32_t)(hi - lo);
+  const uint32_t len0 = __shfl_sync(0xffffffffu, len, 0);
+
+  uint64_t run_at = 0, col_at = 0;
+  if (FILL) {
+    run_at = slice_ptr[s];
+    col_at = run_at + 2ull * ((slice_runs[s] + 1u) & ~1u);
+  }
+  uint64_t used_lo = 0, used_hi = 0;  // entries of this lane that went into runs
+  uint32_t n_runs = 0, at = 0;        // at: first entry of the row not yet passed
+  uint32_t head = at < len ? entries[lo + at] : kNone;
+  for (uint32_t j = 0; j < len0; ++j) {
+    uint32_t v0 = lane == 0 ? entries[lo + j] : 0u;
+    v0 = __shfl_sync(0xffffffffu, v0, 0);
+    const uint32_t want = v0 + lane;
+    while (head < want) {  // kNone is larger than any entry
+      ++at;
+      head = at < len ? entries[lo + at] : kNone;
+    }
+    const bool match = head == want && ((want ^ v0) & kSignBit) == 0 && at < 128;
+    if (__all_sync(0xffffffffu, match)) {
+      if (at < 64) used_lo |= 1ull << at; else used_hi |= 1ull << (at - 64);
+      if (FILL && lane == 0) { words[run_at + 2ull * n_runs] = v0; words[run_at + 2ull * n_runs + 1] = 0xffffffffu; }
+      ++n_runs;
+      ++at;
+      head = at < len ? entries[lo + at] : kNone;
+    }
+  }
+  const uint32_t my_cols = len - (uint32_t)__popcll(used_lo) - (uint32_t)__popcll(used_hi);
+  if (!FILL) {
+    const uint32_t cols = __reduce_max_sync(0xffffffffu, my_cols);
+    if (lane == 0) { slice_runs[s] = n_runs; slice_cols[s] = cols; }
+  } else {
+    uint32_t c = 0;
+    for (uint32_t e = 0; e < len; ++e) {
+      const bool used = e < 64 ? (used_lo >> e) & 1ull : (e < 128 ? (used_hi >> (e - 64)) & 1ull : 0ull);
+      if (!used) { words[col_at + 32ull * c + lane] = entries[lo + e]; ++c; }
+    }
+    if (lane == 0 && (n_runs & 1u)) {
+      words[run_at + 2ull * n_runs] = 0; words[run_at + 2ull * n_runs + 1] = 0;
+    }
+  }
+}
+
 __global__ void slice_sizes_kernel(const uint32_t* __restrict__ slice_runs, const uint32_t* __restrict__ slice_cols,
                                    uint64_t n_slices, uint32_t* __restrict__ sizes) {
   const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -131,8 +189,11 @@ __global__ void run_facts_kernel(const uint64_t* __restrict__ slice_ptr, const u
 }
 
 // dy/dt for one slice per warp.  Every lane sums its state's terms in the order runs, then
-// columns; kUnroll gathers are in flight per lane.
-template <bool FUSED>
+// columns.  The kernel is bound by memory latency x bandwidth (ncu, profiles/r01_f_*: 67 % of the
+// HBM peak with 4 gathers per lane and one dependent load phase per batch), so U gathers are in
+// flight per lane and the column words of the next batch are loaded while the current one is
+// gathered.
+template <int U, bool FUSED>
 __global__ void __launch_bounds__(kThreads) flux_slices_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
@@ -144,38 +205,46 @@ __global__ void __launch_bounds__(kThreads) flux_slices_kernel(
   const uint32_t n_runs = slice_runs[s];
   const uint32_t n_pairs = (n_runs + 1u) & ~1u;
   const uint2* __restrict__ runs = (const uint2*)(words + at);
-  const uint32_t* __restrict__ cols = words + at + 2ull * n_pairs;
+  const uint32_t* __restrict__ cols = words + at + 2ull * n_pairs + lane;
   const uint32_t n_cols = (uint32_t)((stop - at - 2ull * n_pairs) >> 5);
   const uint32_t below = (1u << lane) - 1u;
   double acc = 0.0;
 
-  for (uint32_t j0 = 0; j0 < n_runs; j0 += 32) {
-    const uint2 mine = j0 + lane < n_runs ? runs[j0 + lane] : make_uint2(0u, 0u);
-    const uint32_t here = min(32u, n_runs - j0);
-    for (uint32_t jj = 0; jj < here; jj += kUnroll) {  // lanes past `here` hold the empty run
-      uint32_t first[kUnroll], mask[kUnroll];
-      double x[kUnroll];
+  uint2 mine = lane < n_runs ? runs[lane] : make_uint2(0u, 0u);
+  uint32_t v[U];  // column words of the batch about to be gathered
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) {
+  for (int u = 0; u < U; ++u) v[u] = (uint32_t)u < n_cols ? cols[32u * u] : kNone;
+
+  for (uint32_t j0 = 0; j0 < n_runs; j0 += 32) {
+    const uint32_t here = min(32u, n_runs - j0);
+    for (uint32_t jj = 0; jj < here; jj += U) {  // lanes past `here` hold the empty run
+      uint32_t first[U], mask[U];
+      double x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
         first[u] = __shfl_sync(0xffffffffu, mine.x, (jj + u) & 31);
         mask[u] = __shfl_sync(0xffffffffu, mine.y, (jj + u) & 31);
+        if (32 % U != 0 && jj + u >= 32) mask[u] = 0;
       }
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u)
+      for (int u = 0; u < U; ++u)
         x[u] = ((mask[u] >> lane) & 1u) ? w[(first[u] & ~kSignBit) + __popc(mask[u] & below)] : 0.0;
 #pragma unroll
-      for (int u = 0; u < kUnroll; ++u) acc += (first[u] & kSignBit) ? -x[u] : x[u];
+      for (int u = 0; u < U; ++u) acc += (first[u] & kSignBit) ? -x[u] : x[u];
     }
+    if (j0 + 32 < n_runs) mine = j0 + 32 + lane < n_runs ? runs[j0 + 32 + lane] : make_uint2(0u, 0u);
   }
-  for (uint32_t c0 = 0; c0 < n_cols; c0 += kUnroll) {
-    uint32_t v[kUnroll];
-    double x[kUnroll];
+  for (uint32_t c0 = 0; c0 < n_cols; c0 += U) {
+    uint32_t ahead[U];
+    double x[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) v[u] = c0 + u < n_cols ? cols[32ull * (c0 + u) + lane] : kNone;
+    for (int u = 0; u < U; ++u) ahead[u] = c0 + U + u < n_cols ? cols[32u * (c0 + U + u)] : kNone;
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) x[u] = v[u] != kNone ? w[v[u] & ~kSignBit] : 0.0;
+    for (int u = 0; u < U; ++u) x[u] = v[u] != kNone ? w[v[u] & ~kSignBit] : 0.0;
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) acc += (v[u] & kSignBit) ? -x[u] : x[u];
+    for (int u = 0; u < U; ++u) acc += (v[u] & kSignBit) ? -x[u] : x[u];
+#pragma unroll
+    for (int u = 0; u < U; ++u) v[u] = ahead[u];
   }
 
   const uint64_t row = s * 32 + lane;
@@ -236,8 +305,13 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
   fs.slice_runs = dkeep<uint32_t>(S);
   uint32_t* cols = dalloc<uint32_t>(S, st);
   uint32_t* sizes = dalloc<uint32_t>(S, st);
-  encode_slices_kernel<false><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
-                                                        fs.slice_runs, cols, nullptr, nullptr);
+  const bool full_only = fs.min_run_lanes == 32;
+  if (full_only)
+    encode_full_runs_kernel<false><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.slice_runs, cols,
+                                                             nullptr, nullptr);
+  else
+    encode_slices_kernel<false><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
+                                                          fs.slice_runs, cols, nullptr, nullptr);
   slice_sizes_kernel<<<grid_for(S, kThreads), kThreads, 0, st>>>(fs.slice_runs, cols, S, sizes);
   fs.slice_ptr = dkeep<uint64_t>(S + 1);
   uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(S), st);
@@ -246,8 +320,12 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   fs.words = dkeep<uint32_t>(fs.n_words);
   TAPES_CUDA_CHECK(cudaMemsetAsync(fs.words, 0xff, fs.n_words * 4, st));  // columns default to "none"
-  encode_slices_kernel<true><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
-                                                       fs.slice_runs, cols, fs.slice_ptr, fs.words);
+  if (full_only)
+    encode_full_runs_kernel<true><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.slice_runs, cols,
+                                                            fs.slice_ptr, fs.words);
+  else
+    encode_slices_kernel<true><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
+                                                         fs.slice_runs, cols, fs.slice_ptr, fs.words);
   unsigned long long* facts = dalloc<unsigned long long>(3, st);
   TAPES_CUDA_CHECK(cudaMemsetAsync(facts, 0, 24, st));
   run_facts_kernel<<<grid_for(S, kThreads), kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, S, facts);
@@ -270,12 +348,15 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   const FluxSlices& fs = m.slices;
   const uint64_t slice_lo = row_lo / 32, slice_hi = (row_hi + 31) / 32;
   const unsigned grid = grid_for((slice_hi - slice_lo) * 32, kThreads);
-  if (up)
-    flux_slices_kernel<true><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, d_out,
-                                                       slice_lo, slice_hi, row_lo, row_hi, *up);
-  else
-    flux_slices_kernel<false><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, d_out,
-                                                        slice_lo, slice_hi, row_lo, row_hi, StageUpdate());
+#define TAPES_FLUX(U_)                                                                                      \
+  (up ? flux_slices_kernel<U_, true><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
+                                                               d_out, slice_lo, slice_hi, row_lo, row_hi, *up)  \
+      : flux_slices_kernel<U_, false><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
+                                                                d_out, slice_lo, slice_hi, row_lo, row_hi, StageUpdate()))
+  if (m.flux_unroll >= 8) TAPES_FLUX(8);
+  else if (m.flux_unroll >= 6) TAPES_FLUX(6);
+  else TAPES_FLUX(4);
+#undef TAPES_FLUX
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 

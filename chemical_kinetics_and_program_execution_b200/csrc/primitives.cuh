@@ -124,7 +124,8 @@ inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint64_t* out, ui
 }
 
 // ------------------------------------------------------------------------------------------
-// Open-addressing hash set of 64-bit keys with a 32-bit value written by the first inserter.
+// Open-addressing hash set of 64-bit keys in HBM.  The first inserter of a key also stores a
+// 32-bit value; `ranks` is filled later with the position of the key in the sorted key list.
 // Lanes of a warp that carry the same key elect one inserter (warp-aggregated insert).
 // ------------------------------------------------------------------------------------------
 constexpr uint64_t kEmptyKey = ~0ull;
@@ -132,6 +133,7 @@ constexpr uint64_t kEmptyKey = ~0ull;
 struct HashSet {
   uint64_t* keys = nullptr;
   uint32_t* vals = nullptr;
+  uint32_t* ranks = nullptr;
   uint64_t mask = 0;  // capacity - 1 (capacity is a power of two)
 };
 
@@ -142,33 +144,52 @@ __device__ __forceinline__ uint64_t hash_mix(uint64_t x) {
   return x;
 }
 
-// All 32 lanes must call this; `active` says whether the lane has a key.
-__device__ __forceinline__ void hash_insert_warp(const HashSet& hs, bool active, uint64_t key,
+// All 32 lanes must call this; `active` says whether the lane has a key.  Returns true in the
+// lane that claimed an empty slot for a key not seen before.
+__device__ __forceinline__ bool hash_insert_warp(const HashSet& hs, bool active, uint64_t key,
                                                  uint32_t val) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned peers = __match_any_sync(0xffffffffu, active ? key : (kEmptyKey - lane));
   const bool leader = active && ((__ffs(peers) - 1) == (int)lane);
+  bool fresh = false;
   if (leader) {
     uint64_t h = hash_mix(key) & hs.mask;
     for (;;) {
       unsigned long long prev =
           atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey,
                     (unsigned long long)key);
-      if (prev == kEmptyKey) { hs.vals[h] = val; break; }
+      if (prev == kEmptyKey) { hs.vals[h] = val; fresh = true; break; }
       if (prev == key) break;
       h = (h + 1) & hs.mask;
     }
   }
+  return fresh;
 }
 
-__device__ __forceinline__ uint32_t hash_lookup(const HashSet& hs, uint64_t key) {
+// Slot of a key that is known to be present.
+__device__ __forceinline__ uint64_t hash_slot(const HashSet& hs, uint64_t key) {
   uint64_t h = hash_mix(key) & hs.mask;
-  for (;;) {
-    uint64_t k = hs.keys[h];
-    if (k == key) return hs.vals[h];
-    if (k == kEmptyKey) return 0xffffffffu;
-    h = (h + 1) & hs.mask;
+  while (hs.keys[h] != key) h = (h + 1) & hs.mask;
+  return h;
+}
+
+// Block-wide compaction: every thread with `take` appends `item` to `list`; one atomic per block
+// on the shared counter.  All threads of the block must call this.
+__device__ __forceinline__ void block_append_u64(bool take, uint64_t item, uint64_t* __restrict__ list,
+                                                 unsigned long long* __restrict__ counter) {
+  __shared__ uint32_t warp_count[32];
+  __shared__ unsigned long long block_base;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned takers = __ballot_sync(0xffffffffu, take);
+  if (lane == 0) warp_count[warp] = __popc(takers);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (unsigned w = 0; w < (blockDim.x + 31) / 32; ++w) { const uint32_t c = warp_count[w]; warp_count[w] = total; total += c; }
+    block_base = total ? atomicAdd(counter, (unsigned long long)total) : 0ull;
   }
+  __syncthreads();
+  if (take) list[block_base + warp_count[warp] + __popc(takers & ((1u << lane) - 1u))] = item;
 }
 
 // ------------------------------------------------------------------------------------------

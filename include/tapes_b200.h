@@ -87,11 +87,14 @@ int tapes_sync(void* model);
  * hash_inserts, hash_unique, alphabet, cl_k, CSR-kernel lanes per row, flux format (1 = slices of
  * 32 states, 0 = plain CSR), slices, 32-bit words of the sliced form, runs, entries held by runs,
  * entries held by columns, column slots incl. padding, minimum lanes of a run, loads in flight per
- * thread of the level kernel.  Returns how many were written. */
+ * thread of the level kernel, forest levels whose parent lists are not arithmetic progressions,
+ * left-parent records of all levels.
+ * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
 /* Tuning knobs of a built model: "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row of the plain-CSR
- * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel). */
+ * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel), "flux_unroll"
+ * (4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
 /* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing. */
