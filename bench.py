@@ -52,7 +52,7 @@ def parse_args():
   ap.add_argument('--cl-k', type=int, default=8)
   ap.add_argument('--rules-per-gpu', type=int, default=24)
   ap.add_argument('--seed', type=int, default=1)
-  ap.add_argument('--chunks', type=int, default=0, help='row chunks of the overlapped exchange (0 = no overlap)')
+  ap.add_argument('--chunks', type=int, default=8, help='row blocks of the overlapped exchange (0 = no overlap)')
   ap.add_argument('--exchange', default='allreduce', choices=['rs_ag', 'allreduce'],
                   help='flux exchange for N > 1: reduce-scatter + all-gather, or one all-reduce')
   ap.add_argument('--e2e-steps', type=int, default=3)
@@ -72,10 +72,13 @@ def spmv_bytes(nnz, n):
 
 def level_bytes(info):
   """Algorithmic bytes of all level_kernel launches of one step: 16 B per
-  child node (table read + weight write), 25 B per left-parent record, and per prefix group 24 B
-  (prefix, short marginal, parent progression) plus 8 B per parent weight."""
+  child node (table read + weight write), 25 B per left-parent record, per prefix group 24 B
+  (prefix, short marginal, parent progression), 8 B per parent weight that is gathered (parents a
+  group evaluates itself are not read back) and 16 B per group sum handed to the next level."""
   children = info['n_nodes']
-  return 16.0 * children + 25.0 * info.get('left_parents', 0) + 24.0 * info['hash_unique'] + 8.0 * info['hash_inserts']
+  gathered = info['hash_inserts'] - info.get('owned_parents', 0)
+  return (16.0 * children + 25.0 * info.get('left_parents', 0) + 24.0 * info['hash_unique'] + 8.0 * gathered
+          + 16.0 * info.get('deferred_groups', 0))
 
 
 def recorded_traffic(kernel, info, args):
@@ -329,20 +332,22 @@ def run_b200(args):
   out = torch.empty_like(p)
   sharded = None
   if world > 1:
-    if args.chunks > 0:
+    if args.exchange == 'allreduce':
+      sharded = parallel.OverlappedAllReduceRhs(model.weights, model.flux_rows, n, chunks=max(args.chunks, 1))
+      padded = n
+    elif args.chunks > 0:
       sharded = parallel.OverlappedRhs(model.weights, model.flux_rows, n, chunks=args.chunks, device=device)
+      padded = sharded.padded
     else:
       sharded = parallel.ShardedRhs(lambda pin, pout: model.rhs(pin, pout), n, device=device)
-    p_full = torch.zeros(sharded.padded, dtype=torch.float64, device=device)
+      padded = sharded.padded
+    p_full = torch.zeros(padded, dtype=torch.float64, device=device)
     p_full[:n] = p
     out_full = torch.zeros_like(p_full)
 
   def one_step():
     if sharded is None:
       model.rhs(p, out)
-    elif args.exchange == 'allreduce':
-      model.rhs(p_full[:n], out_full[:n])
-      dist.all_reduce(out_full, op=dist.ReduceOp.SUM)
     else:
       sharded.rhs_full(p_full, out_full)
 
@@ -478,7 +483,8 @@ def run_b200(args):
                             n_states=n, rules_per_gpu=args.rules_per_gpu, total_rules=args.rules_per_gpu * world,
                             seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
                             parallelism=(f'rules dealt to {world} ranks; exchange per step: '
-                                         + ('all-reduce of dy/dt' if args.exchange == 'allreduce' else
+                                         + (f'all-reduce of dy/dt in {max(args.chunks, 1)} row blocks overlapped with the product'
+                                            if args.exchange == 'allreduce' else
                                             f'flux reduce-scatter + table all-gather, {args.chunks} overlapped row chunks'))
                             if world > 1 else 'single GPU',
                             l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),

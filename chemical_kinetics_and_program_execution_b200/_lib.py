@@ -113,7 +113,7 @@ MODEL_INFO_FIELDS = (
     'n_sum_nodes', 'worlds_walked', 'leaf_worlds', 'seeds', 'hash_inserts', 'hash_unique',
     'alphabet', 'cl_k', 'spmv_lanes_per_row', 'flux_format', 'n_slices', 'slice_words', 'runs',
     'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll',
-    'irregular_levels', 'left_parents')
+    'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups')
 
 
 def model_info(model):
@@ -123,10 +123,10 @@ def model_info(model):
 
 
 def model_timing(model):
-  buf = numpy.zeros(4, dtype=numpy.float64)
-  load().tapes_model_timing(model, buf.ctypes.data, 4)
+  buf = numpy.zeros(5, dtype=numpy.float64)
+  load().tapes_model_timing(model, buf.ctypes.data, 5)
   return dict(host_enumerate_ms=float(buf[0]), device_expand_ms=float(buf[1]),
-              device_csr_ms=float(buf[2]), device_slices_ms=float(buf[3]))
+              device_csr_ms=float(buf[2]), device_slices_ms=float(buf[3]), expand_alloc_ms=float(buf[4]))
 
 
 def rule_table(tag, cl_k):

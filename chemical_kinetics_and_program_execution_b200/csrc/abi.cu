@@ -223,7 +223,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                        (int64_t)m.flux_format, (int64_t)m.slices.n_slices, (int64_t)m.slices.n_words,
                        (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
                        (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
-                       m.stats.irregular_levels, m.stats.left_parents};
+                       m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
+                       m.stats.owned_parents, m.stats.deferred_groups};
   int n = (int)(sizeof(v) / sizeof(v[0]));
   if (n > capacity) n = capacity;
   for (int i = 0; i < n; ++i) out[i] = v[i];
@@ -238,8 +239,16 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
     m.spmv_group = (int)value;
     return 0;
   }
-  if (std::strcmp(key, "flux_unroll") == 0 && (value == 4 || value == 6 || value == 8)) {
+  if (std::strcmp(key, "flux_unroll") == 0 && value >= 2 && value <= 8) {
     m.flux_unroll = (int)value;
+    return 0;
+  }
+  if (std::strcmp(key, "level_own_unroll") == 0 && value >= 1 && value <= 8) {
+    m.level_own_unroll = (int)value;
+    return 0;
+  }
+  if (std::strcmp(key, "level_min_blocks") == 0 && value >= 1 && value <= 8) {
+    m.level_min_blocks = (int)value;
     return 0;
   }
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {
@@ -254,8 +263,8 @@ int tapes_model_timing(void* model, double* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
   const tapes::Model& m = *(tapes::Model*)model;
   const double v[] = {m.stats.host_enumerate_ms, m.stats.device_expand_ms, m.stats.device_csr_ms,
-                      m.stats.device_slices_ms};
-  int n = 4 > capacity ? capacity : 4;
+                      m.stats.device_slices_ms, m.stats.expand_alloc_ms};
+  int n = 5 > capacity ? capacity : 5;
   for (int i = 0; i < n; ++i) out[i] = v[i];
   return n;
 }

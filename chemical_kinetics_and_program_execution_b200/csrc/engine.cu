@@ -39,30 +39,36 @@ void dfree(T*& p, cudaStream_t st) {
   if (p) cudaFreeAsync((void*)p, st);
   p = nullptr;
 }
+double g_alloc_ms = 0;  // host time spent in cudaMalloc / cudaFree during the current build
+struct AllocTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~AllocTimer() { g_alloc_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 template <typename T>
 T* dkeep(size_t n) {  // allocations that live as long as the model
+  AllocTimer timer;
   void* p = nullptr;
   TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
   return (T*)p;
 }
 
 // Scratch for one phase of a level: sizes are declared first, then one cudaMalloc backs them all.
+// The allocation is kept and reused by later levels as long as it is large enough (the deep
+// levels of a forest have similar sizes), so the driver is asked for memory a handful of times.
 struct Slab {
   char* base = nullptr;
-  size_t bytes = 0;
+  size_t capacity = 0, bytes = 0;
   std::vector<size_t> offsets;
   Slab() {}
   Slab(const Slab&) = delete;
   Slab& operator=(const Slab&) = delete;
-  Slab& operator=(Slab&& o) {
-    if (this != &o) {
-      release();
-      base = o.base; bytes = o.bytes; offsets = std::move(o.offsets);
-      o.base = nullptr; o.bytes = 0; o.offsets.clear();
-    }
-    return *this;
-  }
   ~Slab() { release(); }
+  void swap(Slab& o) {
+    std::swap(base, o.base); std::swap(capacity, o.capacity); std::swap(bytes, o.bytes);
+    offsets.swap(o.offsets);
+  }
+  void reset() { bytes = 0; offsets.clear(); }  // forget the layout, keep the memory
   size_t want(size_t b) {
     bytes = (bytes + 255) & ~(size_t)255;
     offsets.push_back(bytes);
@@ -70,15 +76,21 @@ struct Slab {
     return offsets.size() - 1;
   }
   void commit() {
+    if (bytes <= capacity) return;
+    AllocTimer timer;
+    if (base) cudaFree(base);
+    base = nullptr; capacity = 0;
     void* p = nullptr;
     TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
     base = (char*)p;
+    capacity = std::max<size_t>(bytes, 256);
   }
   template <typename T>
   T* at(size_t i) const { return (T*)(base + offsets[i]); }
   void release() {
+    AllocTimer timer;
     if (base) cudaFree(base);
-    base = nullptr; bytes = 0; offsets.clear();
+    base = nullptr; capacity = 0; reset();
   }
 };
 
@@ -282,6 +294,49 @@ __global__ void group_progression_kernel(const uint64_t* __restrict__ ptr, const
   if (!ok) atomicAdd(irregular, 1ull);
 }
 
+// Fused right chain, build side.  A group may own its parents when they are right children of the
+// previous level, A apart in group index (stride % A == 0, so all are the same digit x of their
+// groups).  consumed[g'] counts how many children of previous-level group g' found such an owner.
+__global__ void mark_owned_parents_kernel(const uint32_t* __restrict__ first, const uint32_t* __restrict__ stride,
+                                          uint32_t* __restrict__ count, const uint32_t* __restrict__ prefix,
+                                          const uint32_t* __restrict__ prev_prefix, uint64_t n_groups,
+                                          uint64_t prev_right_base, uint32_t A, uint32_t M,
+                                          uint32_t* __restrict__ consumed) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const uint32_t n = count[g] & Level::kCountMask, f = first[g], d = stride[g];
+  if (n == 0 || f < prev_right_base || (n > 1 && d % A != 0)) return;
+  const uint32_t rel = f - (uint32_t)prev_right_base;
+  bool all_digits = n == A;  // parent j is the group with prefix  j * M / A + prefix / A ?
+  for (uint32_t j = 0; j < n; ++j) {
+    const uint32_t gp = (rel + j * d) / A;
+    atomicAdd(&consumed[gp], 1u);
+    all_digits = all_digits && prev_prefix[gp] == j * (M / A) + prefix[g] / A;
+  }
+  count[g] = n | Level::kOwnsParents | (all_digits ? Level::kAllDigits : 0u);
+}
+
+// Every previous-level group must have all A children owned, or none.
+__global__ void check_consumed_kernel(const uint32_t* __restrict__ consumed, uint64_t n_prev_groups, uint32_t A,
+                                      unsigned long long* __restrict__ partial) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_prev_groups && consumed[g] != 0 && consumed[g] != A) atomicAdd(partial, 1ull);
+}
+
+__global__ void clear_owned_parents_kernel(uint32_t* __restrict__ count, uint64_t n_groups) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_groups) count[g] &= Level::kCountMask;
+}
+
+__global__ void mark_deferred_kernel(uint32_t* __restrict__ prev_count, const uint32_t* __restrict__ consumed,
+                                     uint64_t n_prev_groups, uint32_t A, unsigned long long* __restrict__ n_deferred) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < n_prev_groups && consumed[g] == A) {
+    prev_count[g] |= Level::kChildrenDeferred;
+    atomicAdd(n_deferred, 1ull);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-step kernels.
 // ---------------------------------------------------------------------------------------------
@@ -365,6 +420,50 @@ __device__ __forceinline__ double child_weight(double w_parent, double p_long, d
   return r > 0.0 ? w_parent * r : 0.0;
 }
 
+// A group that owns its parents (fused right chain, engine.h Level): evaluates parent j = child
+// x_prev of previous-level group g_prev + j * g_step from that group's sum, stores it at its node
+// and returns the sum over j in ascending order.  DIRECT: the parents are the A values of the
+// dropped digit in order, so their table indices follow from the group's own prefix.
+template <int UO, bool DIRECT>
+__device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, const double* __restrict__ p,
+                                              const double* __restrict__ short_table, double* __restrict__ ww,
+                                              uint64_t g, uint32_t first, uint32_t stride, uint32_t n,
+                                              uint32_t g_prev, uint32_t g_step, uint32_t x_prev) {
+  double total = 0.0;
+  const uint32_t mine = DIRECT ? lv.g_prefix[g] : 0u;
+  const uint32_t mine_short = mine / c.A, short_step = c.M / c.A;
+  for (uint32_t e = 0; e < n; e += UO) {
+    uint32_t i_short[UO];
+    uint64_t i_long[UO];
+    double sum_prev[UO], p_long[UO], p_marg[UO];
+#pragma unroll
+    for (int u = 0; u < UO; ++u) {
+      const uint32_t gp = g_prev + (e + u) * g_step;
+      if (DIRECT) {
+        i_long[u] = (uint64_t)(e + u) * c.M + mine;
+        i_short[u] = (e + u) * short_step + mine_short;
+      } else {
+        const uint32_t pre = e + u < n ? lv.prev_prefix[gp] : 0u;
+        i_long[u] = (uint64_t)pre * c.A + x_prev;
+        i_short[u] = pre;
+      }
+      sum_prev[u] = e + u < n ? lv.prev_total[gp] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UO; ++u) {
+      p_long[u] = e + u < n ? p[i_long[u]] : 0.0;
+      p_marg[u] = e + u < n ? short_table[i_short[u]] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < UO; ++u) {
+      const double v = e + u < n ? child_weight(sum_prev[u], p_long[u], p_marg[u]) : 0.0;
+      if (e + u < n) ww[first + (e + u) * stride] = v;
+      total += v;
+    }
+  }
+  return total;
+}
+
 // One level of the forest.  Blocks [0, left_blocks) evaluate the children of the left parents,
 // one parent per thread (the A children of consecutive parents are consecutive in memory for every
 // digit x).  The remaining blocks evaluate the right children, 32 prefix groups per warp: each
@@ -373,8 +472,8 @@ __device__ __forceinline__ double child_weight(double w_parent, double p_long, d
 // Loads are issued U at a time before the divisions and stores that depend on them: the kernel is
 // bound by HBM latency x bandwidth, and one load in flight per thread reaches ~60 % of peak only
 // (profiles/r01_c_*).  wr and ww are the same vector: reads touch earlier levels only.
-template <int U, bool PROGRESSIONS>
-__global__ void __launch_bounds__(kThreads, 5) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
+template <int U, int UO, bool PROGRESSIONS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
                                                          uint32_t warp_step_q, uint32_t warp_step_r,
                                                          const double* __restrict__ wr, double* __restrict__ ww) {
   if (blockIdx.x < left_blocks) {
@@ -403,19 +502,35 @@ __global__ void __launch_bounds__(kThreads, 5) level_kernel(Tables t, Consts c, 
     const uint64_t g = g0 + lane;
     double total = 0.0, p_short = 0.0;
     uint32_t prefix = 0;
+    bool deferred = true;  // lanes without a group have no children to write
+    const double* __restrict__ p = t.p;
     if (g < lv.n_groups) {
-      prefix = lv.g_prefix[g];
-      p_short = table(t, c.k - 1)[prefix];
       if (PROGRESSIONS) {  // parents first, first + stride, ...
-        const uint32_t first = lv.g_first[g], stride = lv.g_stride[g], n = lv.g_count[g];
-        for (uint32_t e = 0; e < n; e += U) {
-          double v[U];
+        const uint32_t first = lv.g_first[g], stride = lv.g_stride[g], packed = lv.g_count[g];
+        const uint32_t n = packed & Level::kCountMask;
+        deferred = (packed & Level::kChildrenDeferred) != 0;
+        if (packed & Level::kOwnsParents) {
+          // the parents are children x_prev of the previous level's groups g_prev, g_prev + g_step, ...:
+          // evaluate and store them here (tm.scm:1310-1318 for the previous shift), then add them up
+          const uint32_t rel = first - (uint32_t)lv.prev_right_base;
+          const uint32_t g_prev = rel / c.A, x_prev = rel - g_prev * c.A, g_step = stride / c.A;
+          const double* __restrict__ short_table = table(t, c.k - 1);
+          if (packed & Level::kAllDigits)
+            total = own_parents<UO, true>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
+          else
+            total = own_parents<UO, false>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
+        } else {
+          for (uint32_t e = 0; e < n; e += U) {
+            double v[U];
 #pragma unroll
-          for (int u = 0; u < U; ++u) v[u] = e + u < n ? wr[first + (e + u) * stride] : 0.0;  // node ids stay below 2^31
+            for (int u = 0; u < U; ++u) v[u] = e + u < n ? wr[first + (e + u) * stride] : 0.0;  // node ids stay below 2^31
 #pragma unroll
-          for (int u = 0; u < U; ++u) total += v[u];  // ascending id order; + 0.0 leaves the sum as it is
+            for (int u = 0; u < U; ++u) total += v[u];  // ascending id order; + 0.0 leaves the sum as it is
+          }
         }
+        if (deferred) lv.g_total[g] = total;
       } else {
+        deferred = false;
         const uint64_t lo = lv.g_ptr[g], hi = lv.g_ptr[g + 1];
         for (uint64_t e = lo; e < hi; e += U) {
           uint32_t id[U];
@@ -428,17 +543,23 @@ __global__ void __launch_bounds__(kThreads, 5) level_kernel(Tables t, Consts c, 
           for (int u = 0; u < U; ++u) total += v[u];
         }
       }
+      if (!deferred) {
+        prefix = lv.g_prefix[g];
+        p_short = table(t, c.k - 1)[prefix];
+      }
     }
+    const uint32_t skip = __ballot_sync(0xffffffffu, deferred);  // bit gl: children of group gl are not ours
+    if (skip == 0xffffffffu) return;
     const uint32_t groups_here = (uint32_t)min((uint64_t)32, (uint64_t)lv.n_groups - g0);
     const uint32_t children = groups_here * c.A;
     double* out = ww + lv.base + (uint64_t)c.A * lv.n_left + g0 * c.A;
-    const double* __restrict__ p = t.p;
     // child j = group gl, digit x with j = gl * A + x; a step of 32 children advances (gl, x) by
     // (warp_step_q, warp_step_r) = divmod(32, A) with a carry
     uint32_t gl = lane / c.A, x = lane - gl * c.A;
     for (uint32_t j = lane; j < ((children + 31) & ~31u); j += 32 * U) {
       uint32_t gu[U], xu[U];
       double p_long[U];
+      bool live[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         gu[u] = gl; xu[u] = x;
@@ -447,16 +568,17 @@ __global__ void __launch_bounds__(kThreads, 5) level_kernel(Tables t, Consts c, 
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const bool live = j + 32 * u < children;
-        if (!live) gu[u] = 0;
+        live[u] = j + 32 * u < children;
+        if (!live[u]) gu[u] = 0;
+        live[u] = live[u] && !((skip >> gu[u]) & 1u);
         const uint32_t pre = __shfl_sync(0xffffffffu, prefix, gu[u]);
-        p_long[u] = live ? p[(uint64_t)pre * c.A + xu[u]] : 0.0;
+        p_long[u] = live[u] ? p[(uint64_t)pre * c.A + xu[u]] : 0.0;
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const double wp = __shfl_sync(0xffffffffu, total, gu[u]);
         const double ps = __shfl_sync(0xffffffffu, p_short, gu[u]);
-        if (j + 32 * u < children) out[j + 32 * u] = child_weight(wp, p_long[u], ps);
+        if (live[u]) out[j + 32 * u] = child_weight(wp, p_long[u], ps);
       }
     }
   }
@@ -535,7 +657,7 @@ Model::~Model() {
   fr(rule_ptr); fr(step_kind); fr(step_len); fr(step_long); fr(step_short); fr(step_prob); fr(rule_w);
   for (Level& lv : levels) {
     fr(lv.root_rule); fr(lv.lp_gid); fr(lv.lp_io); fr(lv.lp_len); fr(lv.g_prefix); fr(lv.g_ptr); fr(lv.g_parents);
-    fr(lv.g_first); fr(lv.g_stride); fr(lv.g_count);
+    fr(lv.g_first); fr(lv.g_stride); fr(lv.g_count); fr(lv.g_total);
   }
   fr(node_w); fr(row_ptr); fr(entries); fr(marg); fr(d_marg_off); fr(d_in); fr(d_out);
   fr(slices.slice_ptr); fr(slices.slice_runs); fr(slices.words);
@@ -637,6 +759,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   }
   m.stats.seeds = n_seeds;
 
+  g_alloc_ms = 0;
   // ---- level-synchronous expansion ----
   // Scratch memory comes in two slabs per level (one sized before the level's counts are known,
   // one after): growing the stream-ordered pool by hundreds of small requests cost 2.9 s of a
@@ -650,7 +773,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   Level cur_level;
   cur_level.base = 0;
   cur_level.n_roots = (uint32_t)roots.size();
-  Slab cur_slab;  // owns the arrays of `cur`
+  Slab cur_slab;    // owns the arrays of `cur`
+  Slab s1, s2;      // scratch sized before / after the counts of a level are known; s2 owns `next`
   auto plan_frontier = [](Slab& slab, uint64_t n, size_t idx[5]) {
     idx[0] = slab.want(n * 4); idx[1] = slab.want(n * 4); idx[2] = slab.want(n * 4);
     idx[3] = slab.want(n); idx[4] = slab.want(n);
@@ -696,7 +820,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     // pass 1: classify + hash-dedup of the right-chain prefixes
     uint64_t cap = 1024;
     while (cap < 2 * n) cap <<= 1;
-    Slab s1;
+    s1.reset();
     const size_t i_keys = s1.want(cap * 8), i_vals = s1.want(cap * 4), i_ranks = s1.want(cap * 4);
     const size_t i_lflag = s1.want(n * 4), i_tflag = s1.want(n * 4), i_kflag = s1.want(n);
     const size_t i_lrank = s1.want((n + 1) * 8), i_trank = s1.want((n + 1) * 8);
@@ -735,11 +859,13 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     next_level.n_left = (uint32_t)NL;
     next_level.n_groups = (uint32_t)NG;
     const RadixPlan plan = radix_plan(std::max<uint64_t>(NG, 1));
-    Slab s2;  // owns `next`; lives until the end of the next level
+    s2.reset();  // owns `next` until the end of the next level; the memory of the level before is reused
     size_t fi[5];
     plan_frontier(s2, next.n, fi);
     const size_t i_keys_b = s2.want(NG * 8), i_rh = s2.want(256ull * plan.blocks * 4);
     const size_t i_ro = s2.want((256ull * plan.blocks + 1) * 8), i_keyrank = s2.want(n * 4), i_cnt = s2.want(NG * 4);
+    const size_t i_consumed = s2.want((size_t)cur_level.n_groups * 4);
+    const size_t i_gptr = s2.want((NG + 1) * 8), i_gparents = s2.want(n * 4);  // parent lists (at most n parents)
     s2.commit();
     bind_frontier(s2, fi, next);
     uint32_t* keyrank = s2.at<uint32_t>(i_keyrank);
@@ -769,32 +895,68 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       uint32_t* cnt = s2.at<uint32_t>(i_cnt);
       TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
       group_count_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cnt);
-      next_level.g_ptr = dkeep<uint64_t>(NG + 1);
-      exclusive_scan_u32(cnt, NG, next_level.g_ptr, scan_tmp, st);
-      uint64_t n_par = 0;
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(&n_par, next_level.g_ptr + NG, 8, cudaMemcpyDeviceToHost, st));
-      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      next_level.n_group_parents = n_par;
-      next_level.g_parents = dkeep<uint32_t>(n_par);
+      uint64_t* g_ptr = s2.at<uint64_t>(i_gptr);
+      uint32_t* g_parents = s2.at<uint32_t>(i_gparents);
+      exclusive_scan_u32(cnt, NG, g_ptr, scan_tmp, st);
       TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
-      group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base,
-                                                                       next_level.g_ptr, cnt, next_level.g_parents);
-      group_sort_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(next_level.g_ptr, NG, next_level.g_parents);
+      group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base, g_ptr, cnt, g_parents);
+      group_sort_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(g_ptr, NG, g_parents);
       next_level.g_first = dkeep<uint32_t>(NG);
       next_level.g_stride = dkeep<uint32_t>(NG);
       next_level.g_count = dkeep<uint32_t>(NG);
       group_progression_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
-          next_level.g_ptr, next_level.g_parents, NG, next_level.g_first, next_level.g_stride,
-          next_level.g_count, counters + 1);
-      unsigned long long h_irregular = 0;
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_irregular, counters + 1, 8, cudaMemcpyDeviceToHost, st));
+          g_ptr, g_parents, NG, next_level.g_first, next_level.g_stride, next_level.g_count, counters + 1);
+      unsigned long long h_counts[2] = {0, 0};  // parents, irregular groups
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_counts[0], g_ptr + NG, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_counts[1], counters + 1, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      auto drop = [](auto*& q) { cudaFree((void*)q); q = nullptr; };
-      if (h_irregular == 0 && !std::getenv("TAPES_KEEP_PARENT_LISTS")) {
-        drop(next_level.g_ptr); drop(next_level.g_parents);
-      } else {
+      const uint64_t n_par = h_counts[0];
+      next_level.n_group_parents = n_par;
+      if (h_counts[1] != 0 || std::getenv("TAPES_KEEP_PARENT_LISTS")) {
+        // some list is not a progression: this level keeps its explicit lists
+        auto drop = [](auto*& q) { AllocTimer timer; cudaFree((void*)q); q = nullptr; };
         drop(next_level.g_first); drop(next_level.g_stride); drop(next_level.g_count);
+        next_level.g_ptr = dkeep<uint64_t>(NG + 1);
+        next_level.g_parents = dkeep<uint32_t>(n_par);
+        TAPES_CUDA_CHECK(cudaMemcpyAsync(next_level.g_ptr, g_ptr, (NG + 1) * 8, cudaMemcpyDeviceToDevice, st));
+        TAPES_CUDA_CHECK(cudaMemcpyAsync(next_level.g_parents, g_parents, n_par * 4, cudaMemcpyDeviceToDevice, st));
         m.stats.irregular_levels++;
+      }
+      m.stats.hash_inserts += (int64_t)n_par;
+      m.stats.hash_unique += (int64_t)NG;
+      m.stats.sum_nodes += (int64_t)NG;
+      // fused right chain: groups whose parents are right children of this level take them over
+      const bool fuse = !(std::getenv("TAPES_LEVEL_FUSE") && std::atoi(std::getenv("TAPES_LEVEL_FUSE")) == 0);
+      if (fuse && next_level.g_first && cur_level.g_first && cur_level.n_groups) {
+        const uint64_t PG = cur_level.n_groups;
+        const uint64_t right_base = cur_level.base + (uint64_t)m.A * cur_level.n_left;
+        uint32_t* consumed = s2.at<uint32_t>(i_consumed);
+        TAPES_CUDA_CHECK(cudaMemsetAsync(consumed, 0, PG * 4, st));
+        TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
+        mark_owned_parents_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
+            next_level.g_first, next_level.g_stride, next_level.g_count, next_level.g_prefix, cur_level.g_prefix,
+            NG, right_base, (uint32_t)m.A, c.M, consumed);
+        check_consumed_kernel<<<grid_for(PG, kThreads), kThreads, 0, st>>>(consumed, PG, (uint32_t)m.A, counters);
+        unsigned long long h_partial = 0;
+        TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_partial, counters, 8, cudaMemcpyDeviceToHost, st));
+        TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+        if (h_partial != 0) {  // some group would be half taken over: leave this pair of levels as it is
+          clear_owned_parents_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(next_level.g_count, NG);
+        } else {
+          mark_deferred_kernel<<<grid_for(PG, kThreads), kThreads, 0, st>>>(cur_level.g_count, consumed, PG,
+                                                                           (uint32_t)m.A, counters + 1);
+          unsigned long long h_deferred = 0;
+          TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_deferred, counters + 1, 8, cudaMemcpyDeviceToHost, st));
+          TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+          if (h_deferred) {
+            cur_level.g_total = dkeep<double>(PG);
+            next_level.prev_right_base = right_base;
+            next_level.prev_prefix = cur_level.g_prefix;
+            next_level.prev_total = cur_level.g_total;
+            m.stats.deferred_groups += (int64_t)h_deferred;
+            m.stats.owned_parents += (int64_t)h_deferred * m.A;
+          }
+        }
       }
       m.stats.hash_inserts += (int64_t)n_par;
       m.stats.hash_unique += (int64_t)NG;
@@ -807,17 +969,17 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.stats.left_parents += (int64_t)NL;
 
     m.levels.push_back(cur_level);
-    s1.release();
-    cur_slab = std::move(s2);  // ownership of `next` moves with the frontier
+    cur_slab.swap(s2);  // ownership of `next` moves with the frontier; the old frontier's memory becomes scratch
     cur = next;
     cur_level = next_level;
   }
-  cur_slab.release();
+  cur_slab.release(); s1.release(); s2.release();
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
   m.stats.nodes = (int64_t)m.n_nodes;
   m.stats.terms = (int64_t)total_terms;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_expand_ms = ms_since(t_expand);
+  m.stats.expand_alloc_ms = g_alloc_ms;
 
   // ---- CSR assembly: count per state, scan, fill, sort inside each row ----
   auto t_csr = std::chrono::steady_clock::now();
@@ -853,6 +1015,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   // 24 rules): 1: 7.79, 2: 6.29, 4: 6.05, 5: 5.48, 8: 6.40 ms
   m.level_unroll = m.A <= 2 ? 2 : ((m.A + 4) / 5 * 5 - m.A <= (m.A + 3) / 4 * 4 - m.A ? 5 : 4);
   if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
+  if (const char* g = std::getenv("TAPES_LEVEL_OWN_UNROLL")) m.level_own_unroll = std::max(1, std::atoi(g));
+  if (const char* g = std::getenv("TAPES_LEVEL_MIN_BLOCKS")) m.level_min_blocks = std::max(1, std::atoi(g));
   if (const char* g = std::getenv("TAPES_FLUX_UNROLL")) m.flux_unroll = std::atoi(g);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
@@ -919,14 +1083,20 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       const uint32_t q = 32u / c.A, r = 32u % c.A;
       const unsigned grid = left_blocks + group_blocks;
       const bool prog = lv.g_first != nullptr;
-#define TAPES_LEVEL(U_)                                                                                   \
-  (prog ? level_kernel<U_, true><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
-        : level_kernel<U_, false><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
-      if (m.level_unroll >= 8) TAPES_LEVEL(8);
-      else if (m.level_unroll >= 5) TAPES_LEVEL(5);
-      else if (m.level_unroll >= 4) TAPES_LEVEL(4);
-      else if (m.level_unroll >= 2) TAPES_LEVEL(2);
-      else TAPES_LEVEL(1);
+#define TAPES_LEVEL(U_, UO_, B_)                                                                             \
+  (prog ? level_kernel<U_, UO_, true, B_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
+        : level_kernel<U_, 1, false, 5><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
+      const int uo = m.level_own_unroll, mb = m.level_min_blocks;
+      if (m.level_unroll >= 8) TAPES_LEVEL(8, 4, 4);
+      else if (m.level_unroll >= 5) {
+        if (mb <= 4) { if (uo >= 5) TAPES_LEVEL(5, 5, 4); else TAPES_LEVEL(5, 3, 4); }
+        else if (uo >= 5) TAPES_LEVEL(5, 5, 5);
+        else if (uo >= 3) TAPES_LEVEL(5, 3, 5);
+        else TAPES_LEVEL(5, 2, 5);
+      } else if (m.level_unroll >= 4) {
+        if (uo >= 4) TAPES_LEVEL(4, 4, 5); else TAPES_LEVEL(4, 2, 5);
+      } else if (m.level_unroll >= 2) TAPES_LEVEL(2, 2, 5);
+      else TAPES_LEVEL(1, 1, 5);
 #undef TAPES_LEVEL
     }
   }

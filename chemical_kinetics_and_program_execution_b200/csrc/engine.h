@@ -45,7 +45,22 @@ struct Level {
   // are replaced by first + j * stride, j < count, and g_ptr / g_parents are null
   uint32_t* g_first = nullptr;
   uint32_t* g_stride = nullptr;
-  uint32_t* g_count = nullptr;
+  uint32_t* g_count = nullptr;    // low 29 bits: parents; flag bits kOwnsParents, kChildrenDeferred, kAllDigits
+  // Fused right chain.  A right child is written once and gathered again by the group sum of the
+  // next level; when the parents of a group are right children of the previous level, the group
+  // computes and stores them itself (flag kOwnsParents: parent j is child  (first - prev_right_base
+  // + j * stride) % A  of previous-level group  (first - prev_right_base + j * stride) / A), from
+  // that group's sum in prev_total, and the previous level skips the children of such groups
+  // (flag kChildrenDeferred) and leaves their sum in g_total instead.  Same values, same order of
+  // additions; one 8-byte read per right child less.
+  // kAllDigits (with kOwnsParents): the A parents are the A values of the dropped digit in order,
+  // so parent j reads table index j * A^(k-1) + prefix and no previous-level prefix is needed.
+  static constexpr uint32_t kOwnsParents = 0x80000000u, kChildrenDeferred = 0x40000000u,
+                            kAllDigits = 0x20000000u, kCountMask = 0x1fffffffu;
+  double* g_total = nullptr;            // [n_groups] sums of the groups whose children are deferred
+  uint64_t prev_right_base = 0;         // node id of the previous level's first right child
+  const uint32_t* prev_prefix = nullptr;  // previous level's g_prefix
+  const double* prev_total = nullptr;     // previous level's g_total
 };
 
 // The flux structure cut into slices of 32 consecutive states, one warp lane per state.  Consecutive
@@ -71,7 +86,10 @@ struct BuildStats {
   int64_t hash_inserts = 0, hash_unique = 0;
   int64_t irregular_levels = 0;  // levels whose parent lists are kept explicitly
   int64_t left_parents = 0;      // parent records of left extensions / left shifts, all levels
+  int64_t owned_parents = 0;     // right children computed by the group they feed (fused right chain)
+  int64_t deferred_groups = 0;   // groups whose children are computed by the next level
   double host_enumerate_ms = 0, device_expand_ms = 0, device_csr_ms = 0, device_slices_ms = 0;
+  double expand_alloc_ms = 0;  // part of device_expand_ms spent inside cudaMalloc / cudaFree
 };
 
 struct Model {
@@ -107,7 +125,9 @@ struct Model {
   FluxSlices slices;
   int flux_format = 1;             // 1 = slices, 0 = plain CSR
   int level_unroll = 4;            // loads in flight per thread in level_kernel
-  int flux_unroll = 8;             // gathers in flight per lane in flux_slices_kernel
+  int level_own_unroll = 3;        // parents evaluated at a time by a group that owns them
+  int level_min_blocks = 5;        // resident blocks per SM the level kernel is compiled for
+  int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;

@@ -115,6 +115,37 @@ class ShardedRhs:
     return self.gather(self.owned_flux(p_full), out_full)
 
 
+class OverlappedAllReduceRhs:
+  """dy/dt of the full problem on every rank: partial flux summed by all-reduce, row block by row
+  block, so that the exchange of one block runs while the product of the next is computed.
+
+  local_weights(p) evaluates everything that depends on p; local_flux_rows(out, lo, hi) writes this
+  rank's partial dy/dt for the states lo <= i < hi.  Blocks start at multiples of 32 states (the
+  slices of the product kernel).
+  """
+
+  def __init__(self, local_weights, local_flux_rows, n_states, chunks=8, group=None):
+    self.local_weights = local_weights
+    self.local_flux_rows = local_flux_rows
+    self.group = group
+    self.n = n_states
+    chunks = max(1, int(chunks))
+    per = -(-n_states // chunks)
+    per = -(-per // 32) * 32
+    self.bounds = [(lo, min(lo + per, n_states)) for lo in range(0, n_states, per)]
+
+  def rhs_full(self, p_full, out_full):
+    """p_full, out_full: vectors of at least n_states doubles; out_full[:n] receives the sum."""
+    self.local_weights(p_full[:self.n])
+    pending = []
+    for lo, hi in self.bounds:
+      self.local_flux_rows(out_full, lo, hi)
+      pending.append(dist.all_reduce(out_full[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+    for work in pending:
+      work.wait()
+    return out_full
+
+
 class OverlappedRhs:
   """dy/dt of the full problem with the exchange overlapped chunk by chunk.
 

@@ -88,7 +88,8 @@ int tapes_sync(void* model);
  * 32 states, 0 = plain CSR), slices, 32-bit words of the sliced form, runs, entries held by runs,
  * entries held by columns, column slots incl. padding, minimum lanes of a run, loads in flight per
  * thread of the level kernel, forest levels whose parent lists are not arithmetic progressions,
- * left-parent records of all levels.
+ * left-parent records of all levels, gathers in flight per lane of the product kernel, right
+ * children evaluated by the group they feed, groups whose children are evaluated by the next level.
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
@@ -97,7 +98,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity);
  * (4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
-/* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing. */
+/* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing, and
+ * the part of the expansion spent inside cudaMalloc / cudaFree. */
 int tapes_model_timing(void* model, double* out, int capacity);
 
 /* Copies the CSR flux structure to host: row_ptr has n_states + 1 entries, entries has nnz

@@ -30,6 +30,15 @@ for chunks in (1, 3, 8):
     err = float((out[:n] - want).abs().max() / want.abs().max())
     print(f'rank {rank}/{world} chunks={chunks} max rel dev vs unsplit = {err:.2e}', flush=True)
     assert err < 1e-13
+for chunks in (1, 5):
+    ar = parallel.OverlappedAllReduceRhs(part.weights, part.flux_rows, n, chunks=chunks)
+    out = torch.zeros(n, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        ar.rhs_full(p, out)
+    torch.cuda.synchronize()
+    err = float((out - want).abs().max() / want.abs().max())
+    print(f'rank {rank}/{world} all-reduce blocks={chunks} max rel dev vs unsplit = {err:.2e}', flush=True)
+    assert err < 1e-13
 plain = parallel.ShardedRhs(lambda a, b: part.rhs(a, b), n, device=dev)
 pf = torch.zeros(plain.padded, dtype=torch.float64, device=dev); pf[:n] = p
 out = torch.zeros_like(pf)

@@ -33,10 +33,17 @@ for fmt in formats:
   mt.u_lib.tapes_release_model(tag.encode(), k)
   if fmt == 'csr':
     os.environ['TAPES_FLUX_FORMAT'] = 'csr'
-  else:
+  else:  # sNN: slices with runs of at least NN lanes; nNN: the same without the fused right chain
     os.environ['TAPES_FLUX_FORMAT'] = 'slices'
     os.environ['TAPES_RUN_MIN_LANES'] = fmt[1:]
+    os.environ['TAPES_LEVEL_FUSE'] = '0' if fmt[0] == 'n' else '1'
+
   m = device.DeviceModel(tag, k)
+  if fmt != 'csr':
+    for fu in (4,):
+      m.set_option('flux_unroll', fu)
+      print(f'format={fmt} flux_unroll={fu} flux_ms={phases(m)[2]:.3f}', flush=True)
+    m.set_option('flux_unroll', 4)
   ph = phases(m)
   o = out.cpu().numpy()
   if ref is None:
@@ -50,10 +57,12 @@ for fmt in formats:
         f'dev_vs_first={dev:.1e} words_per_nnz={facts["slice_words"] / max(nnz, 1):.3f} {facts} timing={m.timing}',
         flush=True)
 
-for unroll in (1, 2, 4, 5, 8):
+for unroll, own, blocks in ((5, 3, 5), (5, 2, 5), (5, 5, 5), (5, 3, 4), (5, 5, 4), (4, 2, 5), (4, 4, 5), (8, 4, 4), (2, 2, 5)):
   m.set_option('level_unroll', unroll)
+  m.set_option('level_own_unroll', own)
+  m.set_option('level_min_blocks', blocks)
   ph = phases(m)
   o = out.cpu().numpy()
-  print(f'level_unroll={unroll} levels_ms={ph[1]:.3f} flux_ms={ph[2]:.3f} marg_ms={ph[0]:.3f} '
-        f'bitwise_equal_to_last_format={bool((o == ref).all()) if fmt == formats[0] else "n/a"} '
-        f'dev={abs(o - ref).max() / abs(ref).max():.1e}', flush=True)
+  print(f'level_unroll={unroll} own={own} min_blocks={blocks} levels_ms={ph[1]:.3f} flux_ms={ph[2]:.3f} marg_ms={ph[0]:.3f} '
+        f'dev={abs(o - ref).max() / abs(ref).max():.1e} owned_parents={m.info["owned_parents"]} '
+        f'deferred_groups={m.info["deferred_groups"]}', flush=True)

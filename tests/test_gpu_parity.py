@@ -173,6 +173,114 @@ def test_device_rhs_equals_host_rhs(mt, device):
   assert numpy.array_equal(out.cpu().numpy(), host)  # same kernels, deterministic order
 
 
+def test_flux_row_ranges_and_gather_depths(mt, device):
+  """Row blocks that do not start at slice boundaries, every gather depth of the product kernel
+  and every load batching of the level kernel give the same bits as one full evaluation."""
+  import torch
+  p = torch.from_numpy(configs.markov_table(9, 5, 2)).cuda()
+  model = device.DeviceModel('ex4-chemical-turing', 5)
+  assert model.info['flux_format'] == 1 and model.info['runs'] > 0
+  want = model.rhs(p).cpu().numpy()
+  n = model.n_states
+  out = torch.full((n,), float('nan'), dtype=torch.float64, device='cuda')
+  model.weights(p)
+  cuts = [0, 1, 31, 32, 1000, 1057, n // 2 + 5, n - 1, n]
+  for lo, hi in zip(cuts[:-1], cuts[1:]):
+    model.flux_rows(out, lo, hi)
+  assert numpy.array_equal(out.cpu().numpy(), want)
+  guard = torch.full((n,), 7.0, dtype=torch.float64, device='cuda')
+  model.flux_rows(guard, 40, 50)  # nothing outside the range is written
+  g = guard.cpu().numpy()
+  assert (g[:40] == 7.0).all() and (g[50:] == 7.0).all() and numpy.array_equal(g[40:50], want[40:50])
+  for key, values in (('flux_unroll', (2, 3, 4, 5, 6, 8)), ('level_unroll', (1, 2, 4, 5, 8)),
+                      ('level_own_unroll', (1, 2, 3, 5)), ('level_min_blocks', (4, 5))):
+    keep = model.info.get(key, None)
+    for v in values:
+      model.set_option(key, v)
+      assert numpy.array_equal(model.rhs(p).cpu().numpy(), want), (key, v)
+    if keep:
+      model.set_option(key, keep)
+  mt.u_lib.tapes_release_model(b'ex4-chemical-turing', 5)  # later tests get a model with default options
+
+
+@pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex5-msrtf-machine', 5, 5),
+                                             ('ex3-copolymerization', 4, 7), ('ex2-ferromagnetic-chain', 2, 7),
+                                             ('synthetic', 10, 5), ('synthetic', 3, 6)])
+def test_fused_right_chain_is_bit_identical(mt, device, monkeypatch, tag, size_a, cl_k):
+  """Letting a prefix group evaluate the right children it sums (instead of gathering them after
+  the previous level wrote them) changes neither a node weight nor dy/dt by a single bit."""
+  import torch
+  if tag == 'synthetic':
+    tag = f'fuse-test-{size_a}'
+    mt.register_rule_set(tag, size_a, configs.random_rule_set(size_a, 9, seed=4))
+  p = torch.from_numpy(configs.markov_table(size_a, cl_k, 8)).cuda()
+  got = {}
+  for fuse in ('0', '1'):
+    monkeypatch.setenv('TAPES_LEVEL_FUSE', fuse)
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+    model = device.DeviceModel(tag, cl_k)
+    dy = model.rhs(p).cpu().numpy()
+    got[fuse] = (dy, model.node_weights(), dict(model.info))
+  monkeypatch.delenv('TAPES_LEVEL_FUSE')
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  assert got['0'][2]['owned_parents'] == 0 and got['0'][2]['deferred_groups'] == 0
+  assert got['1'][2]['owned_parents'] == got['1'][2]['deferred_groups'] * size_a
+  if cl_k >= 5 and size_a >= 3:
+    assert got['1'][2]['owned_parents'] > 0
+  assert numpy.array_equal(got['0'][1], got['1'][1])
+  assert numpy.array_equal(got['0'][0], got['1'][0])
+
+
+def test_explicit_parent_lists_are_bit_identical(mt, device, monkeypatch):
+  """The general form of a level (explicit parent lists) and the usual one (arithmetic
+  progressions of parent ids) evaluate the same sums in the same order."""
+  import torch
+  tag, size_a, cl_k = 'ex4-chemical-turing', 9, 5
+  p = torch.from_numpy(configs.markov_table(size_a, cl_k, 11)).cuda()
+  got = {}
+  for keep in (False, True):
+    if keep:
+      monkeypatch.setenv('TAPES_KEEP_PARENT_LISTS', '1')
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+    model = device.DeviceModel(tag, cl_k)
+    got[keep] = (model.rhs(p).cpu().numpy(), model.node_weights(), dict(model.info))
+  monkeypatch.delenv('TAPES_KEEP_PARENT_LISTS')
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  assert got[False][2]['irregular_levels'] == 0 and got[True][2]['irregular_levels'] > 0
+  assert got[True][2]['owned_parents'] == 0
+  assert numpy.array_equal(got[False][1], got[True][1])
+  assert numpy.array_equal(got[False][0], got[True][0])
+
+
+def test_csr_export_round_trip(mt, device, monkeypatch):
+  """The sliced form expands back to the same canonical CSR the plain build keeps, for both
+  encoders (full runs only; masked runs from a merge of the 32 rows)."""
+  import torch
+  tag, cl_k = 'ex3-copolymerization', 6
+  results = {}
+  for name, env in (('csr', dict(TAPES_FLUX_FORMAT='csr')), ('full', dict(TAPES_RUN_MIN_LANES='32')),
+                    ('masked', dict(TAPES_RUN_MIN_LANES='3'))):
+    for k_, v_ in env.items():
+      monkeypatch.setenv(k_, v_)
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+    model = device.DeviceModel(tag, cl_k)
+    p = torch.from_numpy(configs.markov_table(4, cl_k, 5)).cuda()
+    results[name] = (model.csr(), model.rhs(p).cpu().numpy(), dict(model.info))
+    for k_ in env:
+      monkeypatch.delenv(k_)
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  (rp, en), dy, info = results['csr']
+  assert info['flux_format'] == 0
+  for name in ('full', 'masked'):
+    (rp2, en2), dy2, info2 = results[name]
+    assert info2['flux_format'] == 1
+    assert info2['run_entries'] + info2['column_entries'] == info2['nnz']
+    assert numpy.array_equal(rp, rp2) and numpy.array_equal(en, en2)
+    scale = abs(dy).max()
+    assert abs(dy2 - dy).max() <= 1e-14 * scale
+  assert results['masked'][2]['run_entries'] >= results['full'][2]['run_entries']
+
+
 def test_errors(mt):
   with pytest.raises(ValueError):
     mt.get_dy_dt(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=3)(numpy.ones(5), 0.0)

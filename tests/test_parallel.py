@@ -57,6 +57,14 @@ def _worker(rank, world, port, result_path):
   over.rhs_full(p2, out2)
   assert torch.equal(out2[:n], out[:n])
   assert float(out2[n:].abs().sum()) == 0.0
+
+  # the default exchange of bench.py: all-reduce in row blocks that start at multiples of 32
+  summed = parallel.OverlappedAllReduceRhs(local_weights, local_flux_rows, n, chunks=3)
+  assert [lo % 32 for lo, _ in summed.bounds] == [0] * len(summed.bounds)
+  assert summed.bounds[0][0] == 0 and summed.bounds[-1][1] == n
+  out3 = torch.zeros(n, dtype=torch.float64)
+  summed.rhs_full(p[:n].clone(), out3)
+  assert torch.equal(out3, out[:n])
   if rank == 0:
     numpy.save(result_path, out[:n].numpy())
   dist.destroy_process_group()
