@@ -53,8 +53,9 @@ def parse_args():
   ap.add_argument('--rules-per-gpu', type=int, default=24)
   ap.add_argument('--seed', type=int, default=1)
   ap.add_argument('--chunks', type=int, default=8, help='row blocks of the overlapped exchange (0 = no overlap)')
-  ap.add_argument('--exchange', default='allreduce', choices=['rs_ag', 'allreduce'],
-                  help='flux exchange for N > 1: reduce-scatter + all-gather, or one all-reduce')
+  ap.add_argument('--exchange', default='peer', choices=['peer', 'rs_ag', 'allreduce'],
+                  help='flux exchange for N > 1: fused into the product over NVLink peer memory, '
+                       'NCCL reduce-scatter + all-gather, or NCCL all-reduce in row blocks')
   ap.add_argument('--e2e-steps', type=int, default=3)
   ap.add_argument('--cpu-rules', type=int, default=0,
                   help='rules in the CPU-baseline sample (0 = one per usable host core, at most all)')
@@ -315,6 +316,9 @@ def run_b200(args):
   torch.cuda.set_device(local_rank)
   device = torch.device('cuda', local_rank)
   if world > 1:
+    # the exchange runs beside the memory-bound product kernel: give NCCL's stream priority so its
+    # few blocks are placed as soon as slots free up instead of queueing behind the product's grid
+    os.environ.setdefault('TORCH_NCCL_HIGH_PRIORITY', '1')
     dist.init_process_group('nccl', device_id=device)
 
   from chemical_kinetics_and_program_execution_b200 import device as dev, markov_tapes as mt, parallel
@@ -332,7 +336,10 @@ def run_b200(args):
   out = torch.empty_like(p)
   sharded = None
   if world > 1:
-    if args.exchange == 'allreduce':
+    if args.exchange == 'peer':
+      sharded = parallel.PeerExchangeRhs(model)
+      padded = n
+    elif args.exchange == 'allreduce':
       sharded = parallel.OverlappedAllReduceRhs(model.weights, model.flux_rows, n, chunks=max(args.chunks, 1))
       padded = n
     elif args.chunks > 0:
@@ -348,6 +355,8 @@ def run_b200(args):
   def one_step():
     if sharded is None:
       model.rhs(p, out)
+    elif args.exchange == 'peer':
+      sharded.rhs_full(p_full)
     else:
       sharded.rhs_full(p_full, out_full)
 
@@ -391,7 +400,12 @@ def run_b200(args):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(5):
-      if args.exchange == 'allreduce':
+      if args.exchange == 'peer':  # the exposed part: barrier, owner sums + broadcast, barrier
+        sharded._barrier()
+        mt.u_lib.tapes_sum_slots_broadcast(model.handle, sharded.staging, sharded._result_table, world, rank,
+                                           sharded.block, dev._current_stream_handle())
+        sharded._barrier()
+      elif args.exchange == 'allreduce':
         dist.all_reduce(out_full, op=dist.ReduceOp.SUM)
       else:
         dist.reduce_scatter_tensor(sharded.mine if hasattr(sharded, 'mine') else sharded.owned.view(-1)[:sharded.padded // world],
@@ -483,7 +497,10 @@ def run_b200(args):
                             n_states=n, rules_per_gpu=args.rules_per_gpu, total_rules=args.rules_per_gpu * world,
                             seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
                             parallelism=(f'rules dealt to {world} ranks; exchange per step: '
-                                         + (f'all-reduce of dy/dt in {max(args.chunks, 1)} row blocks overlapped with the product'
+                                         + ('fused into the product kernel: partial flux stored into the owner\'s slots '
+                                            'over NVLink peer memory, owners sum and broadcast; 2 barriers'
+                                            if args.exchange == 'peer' else
+                                            f'all-reduce of dy/dt in {max(args.chunks, 1)} row blocks overlapped with the product'
                                             if args.exchange == 'allreduce' else
                                             f'flux reduce-scatter + table all-gather, {args.chunks} overlapped row chunks'))
                             if world > 1 else 'single GPU',

@@ -192,6 +192,83 @@ int tapes_flux_rows_device(void* model, double* d_probs_out, int64_t row_lo, int
   }
 }
 
+void* tapes_peer_alloc(int64_t n_doubles, void* ipc_handle64) {
+  if (!ensure_cuda()) return nullptr;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handles are exchanged as 64 bytes");
+  void* p = nullptr;
+  if (n_doubles < 0 || cudaMalloc(&p, (size_t)(n_doubles > 0 ? n_doubles : 1) * 8) != cudaSuccess) {
+    fail("peer_alloc: cudaMalloc failed");
+    return nullptr;
+  }
+  cudaMemset(p, 0, (size_t)(n_doubles > 0 ? n_doubles : 1) * 8);
+  cudaIpcMemHandle_t h;
+  cudaError_t err = cudaIpcGetMemHandle(&h, p);
+  if (err != cudaSuccess) {
+    fail(std::string("peer_alloc: cudaIpcGetMemHandle: ") + cudaGetErrorString(err));
+    cudaFree(p);
+    return nullptr;
+  }
+  if (ipc_handle64) std::memcpy(ipc_handle64, &h, 64);
+  return p;
+}
+
+void* tapes_peer_open(const void* ipc_handle64) {
+  if (!ensure_cuda() || !ipc_handle64) return nullptr;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, ipc_handle64, 64);
+  void* p = nullptr;
+  cudaError_t err = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (err != cudaSuccess) {
+    fail(std::string("peer_open: cudaIpcOpenMemHandle: ") + cudaGetErrorString(err));
+    return nullptr;
+  }
+  return p;
+}
+
+int tapes_peer_close(void* d_ptr) {
+  if (d_ptr && cudaIpcCloseMemHandle(d_ptr) != cudaSuccess) { fail("peer_close failed"); return 1; }
+  return 0;
+}
+
+int tapes_peer_free(void* d_ptr) {
+  if (d_ptr && cudaFree(d_ptr) != cudaSuccess) { fail("peer_free failed"); return 1; }
+  return 0;
+}
+
+int tapes_flux_scatter_device(void* model, void* const* staging, int world, int rank, int64_t block,
+                              void* cuda_stream) {
+  if (!model || !staging) { fail("null model or staging table"); return 1; }
+  try {
+    tapes::Model& m = *(tapes::Model*)model;
+    if (world < 1 || world > tapes::PeerPointers::kMax) throw std::runtime_error("world size out of range");
+    tapes::PeerPointers pp;
+    for (int i = 0; i < world; ++i) pp.ptr[i] = (double*)staging[i];
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m.stream;
+    tapes::launch_flux_scatter(m, pp, world, rank, (uint64_t)block, st);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_sum_slots_broadcast(void* model, const double* d_slots, void* const* result, int world, int rank,
+                              int64_t block, void* cuda_stream) {
+  if (!model || !d_slots || !result) { fail("null argument"); return 1; }
+  try {
+    tapes::Model& m = *(tapes::Model*)model;
+    if (world < 1 || world > tapes::PeerPointers::kMax) throw std::runtime_error("world size out of range");
+    tapes::PeerPointers pp;
+    for (int i = 0; i < world; ++i) pp.ptr[i] = (double*)result[i];
+    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m.stream;
+    tapes::launch_sum_slots_broadcast(d_slots, pp, world, rank, (uint64_t)block, m.n_states, st);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return 1;
+  }
+}
+
 int tapes_rhs_profile(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream,
                       double* phase_ms, int capacity) {
   if (!model) { fail("null model"); return 1; }

@@ -433,18 +433,17 @@ __device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, 
   const uint32_t mine = DIRECT ? lv.g_prefix[g] : 0u;
   const uint32_t mine_short = mine / c.A, short_step = c.M / c.A;
   for (uint32_t e = 0; e < n; e += UO) {
-    uint32_t i_short[UO];
-    uint64_t i_long[UO];
+    uint32_t i_short[UO], i_long[UO];  // table indices stay below A^k < 2^32
     double sum_prev[UO], p_long[UO], p_marg[UO];
 #pragma unroll
     for (int u = 0; u < UO; ++u) {
       const uint32_t gp = g_prev + (e + u) * g_step;
       if (DIRECT) {
-        i_long[u] = (uint64_t)(e + u) * c.M + mine;
+        i_long[u] = (e + u) * c.M + mine;
         i_short[u] = (e + u) * short_step + mine_short;
       } else {
         const uint32_t pre = e + u < n ? lv.prev_prefix[gp] : 0u;
-        i_long[u] = (uint64_t)pre * c.A + x_prev;
+        i_long[u] = pre * c.A + x_prev;
         i_short[u] = pre;
       }
       sum_prev[u] = e + u < n ? lv.prev_total[gp] : 0.0;
@@ -572,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
         if (!live[u]) gu[u] = 0;
         live[u] = live[u] && !((skip >> gu[u]) & 1u);
         const uint32_t pre = __shfl_sync(0xffffffffu, prefix, gu[u]);
-        p_long[u] = live[u] ? p[(uint64_t)pre * c.A + xu[u]] : 0.0;
+        p_long[u] = live[u] ? p[pre * c.A + xu[u]] : 0.0;  // index below A^k < 2^32
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {

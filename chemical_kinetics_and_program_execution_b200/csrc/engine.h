@@ -192,6 +192,20 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st);
 // (may be null) fuses a Runge-Kutta stage update into the same pass.
 void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
                         const StageUpdate* up);
+// Multi-GPU exchange fused into the product (flux.cu).  Device pointers into the memory of the
+// ranks of one NVLink domain, opened through CUDA IPC by the caller.
+struct PeerPointers {
+  static constexpr int kMax = 16;
+  double* ptr[kMax] = {};
+};
+// This rank's partial dy/dt of every state, stored into the owner's staging slot `rank`
+// (staging.ptr[o]: world * block doubles in rank o's memory; state i belongs to rank i / block).
+void launch_flux_scatter(Model& m, const PeerPointers& staging, int world, int rank, uint64_t block, cudaStream_t st);
+// Owner side: sums the world slots of its block in rank order and stores the result into every
+// rank's full vector (result.ptr[q]: n_rows doubles in rank q's memory).
+void launch_sum_slots_broadcast(const double* d_slots, const PeerPointers& result, int world, int rank,
+                                uint64_t block, uint64_t n_rows, cudaStream_t st);
+
 // Rebuilds the canonical CSR entries (ascending inside each row) from the slices into a device
 // buffer of nnz words.
 void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st);

@@ -193,14 +193,11 @@ __global__ void run_facts_kernel(const uint64_t* __restrict__ slice_ptr, const u
 // HBM peak with 4 gathers per lane and one dependent load phase per batch), so U gathers are in
 // flight per lane and the column words of the next batch are loaded while the current one is
 // gathered.
-template <int U, bool FUSED, int MIN_BLOCKS>
-__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
-    const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
-    const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
-    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up) {
-  const unsigned lane = threadIdx.x & 31;
-  const uint64_t s = slice_lo + (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (s >= slice_hi) return;
+template <int U>
+__device__ __forceinline__ double slice_sum(const uint64_t* __restrict__ slice_ptr,
+                                            const uint32_t* __restrict__ slice_runs,
+                                            const uint32_t* __restrict__ words, const double* __restrict__ w,
+                                            uint64_t s, unsigned lane) {
   const uint64_t at = slice_ptr[s], stop = slice_ptr[s + 1];
   const uint32_t n_runs = slice_runs[s];
   const uint32_t n_pairs = (n_runs + 1u) & ~1u;
@@ -246,7 +243,18 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
 #pragma unroll
     for (int u = 0; u < U; ++u) v[u] = ahead[u];
   }
+  return acc;
+}
 
+template <int U, bool FUSED, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
+    const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
+    const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
+    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up) {
+  const unsigned lane = threadIdx.x & 31;
+  const uint64_t s = slice_lo + (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (s >= slice_hi) return;
+  const double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
   const uint64_t row = s * 32 + lane;
   if (row >= row_lo && row < row_hi) {
     out[row] = acc;
@@ -257,6 +265,48 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
       up.stage[row] = up.y[row] + a * up.h;
     }
   }
+}
+
+// The product fused with the flux exchange of a multi-GPU run: states are owned in contiguous
+// blocks of `block` states (a multiple of 32, so a slice has one owner), and this rank's partial
+// dy/dt of a state goes straight into the owner's staging memory, slot `rank`, with peer stores
+// over NVLink while the rest of the kernel computes.  staging.ptr[o] is owner o's buffer of
+// world * block doubles.
+template <int U>
+__global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
+    const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
+    const uint32_t* __restrict__ words, const double* __restrict__ w,
+    const __grid_constant__ PeerPointers staging, uint32_t rank,
+    uint64_t block, uint64_t rotate, uint64_t n_slices, uint64_t n_rows) {
+  const unsigned lane = threadIdx.x & 31;
+  // Every rank starts with the slices of a different owner (rank r with owner r + 1, then r + 2,
+  // ...): started in the same order, all ranks would store into one owner's memory at a time and
+  // queue up at its NVLink ingress (measured at 8 GPUs: +1.5 ms on a 3.6 ms kernel).
+  uint64_t s = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (s >= n_slices) return;
+  s += rotate;
+  if (s >= n_slices) s -= n_slices;
+  const double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
+  const uint64_t first_row = s * 32;
+  const uint64_t owner = first_row / block;
+  const uint64_t row = first_row + lane;
+  if (row < n_rows) staging.ptr[owner][(uint64_t)rank * block + (row - owner * block)] = acc;
+}
+
+// The owner's half of the exchange: adds the world slots of its block in rank order (so every
+// rank of a run, and every run, gets the same bits) and stores the sums into the full vector of
+// every rank (peer stores).  result.ptr[q] is rank q's full dy/dt vector.
+__global__ void __launch_bounds__(kThreads) sum_slots_broadcast_kernel(const double* __restrict__ slots,
+                                                                       const __grid_constant__ PeerPointers result,
+                                                                       uint32_t world,
+                                                                       uint32_t rank, uint64_t block,
+                                                                       uint64_t n_rows) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t row = (uint64_t)rank * block + j;
+  if (j >= block || row >= n_rows) return;
+  double total = 0.0;
+  for (uint32_t r = 0; r < world; ++r) total += slots[(uint64_t)r * block + j];
+  for (uint32_t q = 0; q < world; ++q) result.ptr[q][row] = total;
 }
 
 // Writes every lane's entries back to CSR positions (runs, then columns) and sorts the row.
@@ -362,6 +412,27 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   else if (m.flux_unroll == 3) TAPES_FLUX(3, 8);
   else TAPES_FLUX(2, 8);
 #undef TAPES_FLUX
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_flux_scatter(Model& m, const PeerPointers& staging, int world, int rank, uint64_t block, cudaStream_t st) {
+  if (m.flux_format != 1) throw std::runtime_error("the fused exchange needs the sliced flux structure");
+  if (world < 1 || world > PeerPointers::kMax || rank < 0 || rank >= world) throw std::runtime_error("bad world / rank");
+  if (block == 0 || block % 32 != 0 || block * (uint64_t)world < m.n_states)
+    throw std::runtime_error("ownership blocks must be multiples of 32 states and cover the table");
+  const FluxSlices& fs = m.slices;
+  const unsigned grid = grid_for(fs.n_slices * 32, kThreads);
+  const uint64_t rotate = (((uint64_t)rank + 1) % (uint64_t)world) * (block / 32) % fs.n_slices;
+  flux_slices_scatter_kernel<4><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, staging,
+                                                          (uint32_t)rank, block, rotate, fs.n_slices, m.n_states);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_sum_slots_broadcast(const double* d_slots, const PeerPointers& result, int world, int rank,
+                                uint64_t block, uint64_t n_rows, cudaStream_t st) {
+  if (world < 1 || world > PeerPointers::kMax || rank < 0 || rank >= world) throw std::runtime_error("bad world / rank");
+  sum_slots_broadcast_kernel<<<grid_for(block, kThreads), kThreads, 0, st>>>(d_slots, result, (uint32_t)world,
+                                                                            (uint32_t)rank, block, n_rows);
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 

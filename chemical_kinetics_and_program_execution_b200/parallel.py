@@ -146,6 +146,99 @@ class OverlappedAllReduceRhs:
     return out_full
 
 
+class _DeviceView:
+  """Lets torch wrap device memory owned by the C library (no copy)."""
+
+  def __init__(self, ptr, n):
+    self.__cuda_array_interface__ = dict(shape=(int(n),), typestr='<f8', data=(int(ptr), False), version=3)
+
+
+class PeerExchangeRhs:
+  """dy/dt of the full problem on every rank with the flux exchange done by this library's own
+  kernels over NVLink peer memory (ranks = GPUs of one node, one process each).
+
+  States are owned in contiguous blocks.  The product kernel stores this rank's partial dy/dt of a
+  state straight into the owner's staging buffer while it computes (tapes_flux_scatter_device);
+  after a barrier each owner adds its `world` slots in rank order and stores the sums into every
+  rank's result vector (tapes_sum_slots_broadcast).  No NCCL kernel competes with the
+  memory-bound product for SMs; the only collective left is a one-element all-reduce used as a
+  stream-ordered barrier.  Every rank ends up with bit-identical dy/dt.
+  """
+
+  def __init__(self, model, group=None):
+    import ctypes
+    from . import _lib, markov_tapes
+    self.lib = markov_tapes.u_lib
+    self.model = model
+    self.group = group
+    self.world = dist.get_world_size(group)
+    self.rank = dist.get_rank(group)
+    self.n = model.n_states
+    block = -(-self.n // self.world)
+    self.block = -(-block // 32) * 32
+    self.padded = self.block * self.world
+    h_staging = (ctypes.c_ubyte * 64)()
+    h_result = (ctypes.c_ubyte * 64)()
+    self.staging = self.lib.tapes_peer_alloc(self.padded, h_staging)
+    self.result = self.lib.tapes_peer_alloc(self.padded, h_result)
+    _lib.check(bool(self.staging) and bool(self.result), 'tapes_peer_alloc')
+    mine = (bytes(h_staging), bytes(h_result))
+    everyone = [None] * self.world
+    dist.all_gather_object(everyone, mine, group=group)
+    self._opened = []
+    staging, result = [], []
+    for r, (hs, hr) in enumerate(everyone):
+      if r == self.rank:
+        staging.append(self.staging)
+        result.append(self.result)
+        continue
+      ps = self.lib.tapes_peer_open(hs)  # bytes: ctypes passes the address of the 64-byte buffer
+      pr = self.lib.tapes_peer_open(hr)
+      _lib.check(bool(ps) and bool(pr), 'tapes_peer_open')
+      self._opened += [ps, pr]
+      staging.append(ps)
+      result.append(pr)
+    self._staging_table = (ctypes.c_void_p * self.world)(*staging)
+    self._result_table = (ctypes.c_void_p * self.world)(*result)
+    device = torch.device('cuda', torch.cuda.current_device())
+    self.out = torch.as_tensor(_DeviceView(self.result, self.padded), device=device)
+    self._token = torch.zeros(1, dtype=torch.float32, device=device)
+    self._barrier()
+    torch.cuda.synchronize()
+
+  def _barrier(self):
+    """Stream-ordered: later work on this stream starts after every rank's earlier work ended."""
+    dist.all_reduce(self._token, group=self.group)
+
+  def rhs_full(self, p_full):
+    """p_full: at least n_states doubles on this device.  Returns the summed dy/dt (a view of the
+    peer-visible result vector, valid until the next call)."""
+    from . import _lib, device as dev
+    stream = dev._current_stream_handle()
+    self.model.weights(p_full[:self.n])
+    rc = self.lib.tapes_flux_scatter_device(self.model.handle, self._staging_table, self.world, self.rank,
+                                            self.block, stream)
+    _lib.check(rc == 0, 'tapes_flux_scatter_device')
+    self._barrier()  # every rank's partial flux has landed in its owner's slots
+    rc = self.lib.tapes_sum_slots_broadcast(self.model.handle, self.staging, self._result_table, self.world,
+                                            self.rank, self.block, stream)
+    _lib.check(rc == 0, 'tapes_sum_slots_broadcast')
+    self._barrier()  # every owner's sums have landed everywhere; the slots may be overwritten
+    return self.out
+
+  def close(self):
+    torch.cuda.synchronize()
+    self._barrier()
+    torch.cuda.synchronize()
+    for p in self._opened:
+      self.lib.tapes_peer_close(p)
+    self._opened = []
+    self.out = None
+    self.lib.tapes_peer_free(self.staging)
+    self.lib.tapes_peer_free(self.result)
+    self.staging = self.result = None
+
+
 class OverlappedRhs:
   """dy/dt of the full problem with the exchange overlapped chunk by chunk.
 

@@ -73,6 +73,26 @@ int tapes_weights_device(void* model, const double* d_probs_in, void* cuda_strea
 int tapes_flux_rows_device(void* model, double* d_probs_out, int64_t row_lo, int64_t row_hi,
                            void* cuda_stream);
 
+/* ---- multi-GPU flux exchange over NVLink peer memory (one process per GPU, one node) -------
+ * States are owned in contiguous blocks of `block` states (a multiple of 32), state i by rank
+ * i / block.  tapes_flux_scatter_device is tapes_flux_rows_device for all states with the exchange
+ * fused in: this rank's partial dy/dt of a state is stored directly into the owner's staging
+ * buffer (slot `rank` of world slots of `block` doubles) by peer stores while the kernel computes.
+ * After a barrier, tapes_sum_slots_broadcast adds the owner's slots in rank order and stores the
+ * sums into every rank's full vector.  Buffers come from tapes_peer_alloc (cudaMalloc + a 64-byte
+ * CUDA IPC handle to send to the other ranks) and tapes_peer_open (maps a received handle). */
+void* tapes_peer_alloc(int64_t n_doubles, void* ipc_handle64);
+void* tapes_peer_open(const void* ipc_handle64);
+int tapes_peer_close(void* d_ptr);
+int tapes_peer_free(void* d_ptr);
+/* staging: HOST array of `world` device pointers, entry o = rank o's staging buffer. */
+int tapes_flux_scatter_device(void* model, void* const* staging, int world, int rank, int64_t block,
+                              void* cuda_stream);
+/* d_slots: this rank's own staging buffer; result: HOST array of `world` device pointers, entry q =
+ * rank q's full dy/dt vector (at least n_states doubles). */
+int tapes_sum_slots_broadcast(void* model, const double* d_slots, void* const* result, int world, int rank,
+                              int64_t block, void* cuda_stream);
+
 /* One right-hand side with CUDA events between its phases, recorded on the launching stream;
  * synchronises and writes the phase durations in ms: [0] marginal tables + leaf-world
  * probabilities, [1] forest levels, [2] S * w. */

@@ -39,6 +39,17 @@ for chunks in (1, 5):
     err = float((out - want).abs().max() / want.abs().max())
     print(f'rank {rank}/{world} all-reduce blocks={chunks} max rel dev vs unsplit = {err:.2e}', flush=True)
     assert err < 1e-13
+peer = parallel.PeerExchangeRhs(part)
+for _ in range(3):
+    got = peer.rhs_full(p)
+torch.cuda.synchronize()
+err = float((got[:n] - want).abs().max() / want.abs().max())
+everyone = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
+dist.all_gather(everyone, got[:n].contiguous())
+same = all(bool(torch.equal(everyone[0], e)) for e in everyone)
+print(f'rank {rank}/{world} peer exchange max rel dev vs unsplit = {err:.2e}, identical on all ranks: {same}', flush=True)
+assert err < 1e-13 and same
+peer.close()
 plain = parallel.ShardedRhs(lambda a, b: part.rhs(a, b), n, device=dev)
 pf = torch.zeros(plain.padded, dtype=torch.float64, device=dev); pf[:n] = p
 out = torch.zeros_like(pf)

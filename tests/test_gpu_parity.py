@@ -252,6 +252,34 @@ def test_explicit_parent_lists_are_bit_identical(mt, device, monkeypatch):
   assert numpy.array_equal(got[False][0], got[True][0])
 
 
+def test_peer_exchange_with_one_rank(mt, device):
+  """The fused product + exchange kernels on a world of one: staging slots, owner sums and the
+  result vector reproduce the plain product bit for bit (the N > 1 path is checked on the GPU box
+  by scripts/check_multi_gpu.py)."""
+  import socket
+  import torch
+  import torch.distributed as dist
+  from chemical_kinetics_and_program_execution_b200 import parallel
+  with socket.socket() as sock:
+    sock.bind(('127.0.0.1', 0))
+    port = sock.getsockname()[1]
+  dist.init_process_group('nccl', init_method=f'tcp://127.0.0.1:{port}', rank=0, world_size=1,
+                          device_id=torch.device('cuda', torch.cuda.current_device()))
+  try:
+    model = device.DeviceModel('ex5-msrtf-machine', 5)  # 3125 states: the last ownership block is ragged
+    p = torch.from_numpy(configs.markov_table(5, 5, 13)).cuda()
+    want = model.rhs(p).cpu().numpy()
+    peer = parallel.PeerExchangeRhs(model)
+    assert peer.block % 32 == 0 and peer.block >= model.n_states
+    for _ in range(2):
+      got = peer.rhs_full(p)
+    torch.cuda.synchronize()
+    assert numpy.array_equal(got[:model.n_states].cpu().numpy(), want)
+    peer.close()
+  finally:
+    dist.destroy_process_group()
+
+
 def test_csr_export_round_trip(mt, device, monkeypatch):
   """The sliced form expands back to the same canonical CSR the plain build keeps, for both
   encoders (full runs only; masked runs from a merge of the 32 rows)."""
