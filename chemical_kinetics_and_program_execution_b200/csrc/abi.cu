@@ -316,16 +316,8 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
     m.spmv_group = (int)value;
     return 0;
   }
-  if (std::strcmp(key, "flux_unroll") == 0 && value >= 2 && value <= 8) {
+  if (std::strcmp(key, "flux_unroll") == 0 && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) {
     m.flux_unroll = (int)value;
-    return 0;
-  }
-  if (std::strcmp(key, "level_own_unroll") == 0 && value >= 1 && value <= 8) {
-    m.level_own_unroll = (int)value;
-    return 0;
-  }
-  if (std::strcmp(key, "level_min_blocks") == 0 && value >= 1 && value <= 8) {
-    m.level_min_blocks = (int)value;
     return 0;
   }
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {

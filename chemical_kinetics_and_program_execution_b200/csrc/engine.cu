@@ -1014,8 +1014,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   // 24 rules): 1: 7.79, 2: 6.29, 4: 6.05, 5: 5.48, 8: 6.40 ms
   m.level_unroll = m.A <= 2 ? 2 : ((m.A + 4) / 5 * 5 - m.A <= (m.A + 3) / 4 * 4 - m.A ? 5 : 4);
   if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
-  if (const char* g = std::getenv("TAPES_LEVEL_OWN_UNROLL")) m.level_own_unroll = std::max(1, std::atoi(g));
-  if (const char* g = std::getenv("TAPES_LEVEL_MIN_BLOCKS")) m.level_min_blocks = std::max(1, std::atoi(g));
   if (const char* g = std::getenv("TAPES_FLUX_UNROLL")) m.flux_unroll = std::atoi(g);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
@@ -1082,19 +1080,17 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       const uint32_t q = 32u / c.A, r = 32u % c.A;
       const unsigned grid = left_blocks + group_blocks;
       const bool prog = lv.g_first != nullptr;
+      // U loads in flight per thread; a group that owns its parents evaluates UO of them at a time
+      // (each needs three loads).  Measured at n = 1e8, A = 10 (profiles/r01_g_sweep_fused_right_chain.log):
+      // (U, UO) = (5, 3) 5.42 ms, (5, 2) 5.47, (4, 2) 5.66, (2, 2) 5.83, (5, 5) 6.20 (spills), 64 registers
+      // at 4 blocks per SM 5.63-5.94.
 #define TAPES_LEVEL(U_, UO_, B_)                                                                             \
   (prog ? level_kernel<U_, UO_, true, B_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
         : level_kernel<U_, 1, false, 5><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
-      const int uo = m.level_own_unroll, mb = m.level_min_blocks;
       if (m.level_unroll >= 8) TAPES_LEVEL(8, 4, 4);
-      else if (m.level_unroll >= 5) {
-        if (mb <= 4) { if (uo >= 5) TAPES_LEVEL(5, 5, 4); else TAPES_LEVEL(5, 3, 4); }
-        else if (uo >= 5) TAPES_LEVEL(5, 5, 5);
-        else if (uo >= 3) TAPES_LEVEL(5, 3, 5);
-        else TAPES_LEVEL(5, 2, 5);
-      } else if (m.level_unroll >= 4) {
-        if (uo >= 4) TAPES_LEVEL(4, 4, 5); else TAPES_LEVEL(4, 2, 5);
-      } else if (m.level_unroll >= 2) TAPES_LEVEL(2, 2, 5);
+      else if (m.level_unroll >= 5) TAPES_LEVEL(5, 3, 5);
+      else if (m.level_unroll >= 4) TAPES_LEVEL(4, 2, 5);
+      else if (m.level_unroll >= 2) TAPES_LEVEL(2, 2, 5);
       else TAPES_LEVEL(1, 1, 5);
 #undef TAPES_LEVEL
     }

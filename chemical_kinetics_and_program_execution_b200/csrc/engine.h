@@ -125,8 +125,6 @@ struct Model {
   FluxSlices slices;
   int flux_format = 1;             // 1 = slices, 0 = plain CSR
   int level_unroll = 4;            // loads in flight per thread in level_kernel
-  int level_own_unroll = 3;        // parents evaluated at a time by a group that owns them
-  int level_min_blocks = 5;        // resident blocks per SM the level kernel is compiled for
   int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles

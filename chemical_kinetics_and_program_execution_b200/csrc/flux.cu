@@ -407,8 +407,7 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   // 3.55 ms, 6 at 48 registers 3.93 ms, 8 at 56 registers 4.22 ms
   if (m.flux_unroll >= 8) TAPES_FLUX(8, 4);
   else if (m.flux_unroll >= 6) TAPES_FLUX(6, 5);
-  else if (m.flux_unroll == 5) TAPES_FLUX(4, 8);  // 4 gathers, registers capped for 8 blocks per SM
-  else if (m.flux_unroll == 4) TAPES_FLUX(4, 6);
+  else if (m.flux_unroll >= 4) TAPES_FLUX(4, 6);
   else if (m.flux_unroll == 3) TAPES_FLUX(3, 8);
   else TAPES_FLUX(2, 8);
 #undef TAPES_FLUX

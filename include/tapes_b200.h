@@ -115,7 +115,7 @@ int tapes_model_info(void* model, int64_t* out, int capacity);
 
 /* Tuning knobs of a built model: "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row of the plain-CSR
  * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel), "flux_unroll"
- * (4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
+ * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
 /* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing, and

@@ -40,7 +40,7 @@ for fmt in formats:
 
   m = device.DeviceModel(tag, k)
   if fmt != 'csr':
-    for fu in (4,):
+    for fu in (2, 3, 4, 6, 8):
       m.set_option('flux_unroll', fu)
       print(f'format={fmt} flux_unroll={fu} flux_ms={phases(m)[2]:.3f}', flush=True)
     m.set_option('flux_unroll', 4)
@@ -57,12 +57,10 @@ for fmt in formats:
         f'dev_vs_first={dev:.1e} words_per_nnz={facts["slice_words"] / max(nnz, 1):.3f} {facts} timing={m.timing}',
         flush=True)
 
-for unroll, own, blocks in ((5, 3, 5), (5, 2, 5), (5, 5, 5), (5, 3, 4), (5, 5, 4), (4, 2, 5), (4, 4, 5), (8, 4, 4), (2, 2, 5)):
+for unroll in (1, 2, 4, 5, 8):
   m.set_option('level_unroll', unroll)
-  m.set_option('level_own_unroll', own)
-  m.set_option('level_min_blocks', blocks)
   ph = phases(m)
   o = out.cpu().numpy()
-  print(f'level_unroll={unroll} own={own} min_blocks={blocks} levels_ms={ph[1]:.3f} flux_ms={ph[2]:.3f} marg_ms={ph[0]:.3f} '
+  print(f'level_unroll={unroll} levels_ms={ph[1]:.3f} flux_ms={ph[2]:.3f} marg_ms={ph[0]:.3f} '
         f'dev={abs(o - ref).max() / abs(ref).max():.1e} owned_parents={m.info["owned_parents"]} '
         f'deferred_groups={m.info["deferred_groups"]}', flush=True)
