@@ -52,7 +52,8 @@ def parse_args():
   ap.add_argument('--cl-k', type=int, default=8)
   ap.add_argument('--rules-per-gpu', type=int, default=24)
   ap.add_argument('--seed', type=int, default=1)
-  ap.add_argument('--chunks', type=int, default=8, help='row blocks of the overlapped exchange (0 = no overlap)')
+  ap.add_argument('--chunks', type=int, default=4,
+                  help='rounds of the peer exchange / row blocks of the overlapped NCCL exchanges (0 or 1 = no overlap)')
   ap.add_argument('--exchange', default='peer', choices=['peer', 'rs_ag', 'allreduce'],
                   help='flux exchange for N > 1: fused into the product over NVLink peer memory, '
                        'NCCL reduce-scatter + all-gather, or NCCL all-reduce in row blocks')
@@ -337,7 +338,7 @@ def run_b200(args):
   sharded = None
   if world > 1:
     if args.exchange == 'peer':
-      sharded = parallel.PeerExchangeRhs(model)
+      sharded = parallel.PeerExchangeRhs(model, rounds=max(args.chunks, 1) if args.chunks <= 16 else 16)
       padded = n
     elif args.exchange == 'allreduce':
       sharded = parallel.OverlappedAllReduceRhs(model.weights, model.flux_rows, n, chunks=max(args.chunks, 1))
@@ -400,11 +401,8 @@ def run_b200(args):
     torch.cuda.synchronize()
     e0.record()
     for _ in range(5):
-      if args.exchange == 'peer':  # the exposed part: barrier, owner sums + broadcast, barrier
-        sharded._barrier()
-        mt.u_lib.tapes_sum_slots_broadcast(model.handle, sharded.staging, sharded._result_table, world, rank,
-                                           sharded.block, dev._current_stream_handle())
-        sharded._barrier()
+      if args.exchange == 'peer':  # no separate exchange step exists: it runs inside / beside the product
+        pass
       elif args.exchange == 'allreduce':
         dist.all_reduce(out_full, op=dist.ReduceOp.SUM)
       else:
@@ -415,7 +413,9 @@ def run_b200(args):
     torch.cuda.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / 5], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    comm_ms = float(t.item())
+    comm_ms = float(t.item()) if args.exchange != 'peer' else None
+    if args.exchange == 'peer':
+      sharded.check()
 
   # whole-job structural size
   sizes = torch.tensor([info['nnz'], info['n_nodes'], info['n_terms'], info['launches_per_rhs']],
@@ -498,15 +498,18 @@ def run_b200(args):
                             seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
                             parallelism=(f'rules dealt to {world} ranks; exchange per step: '
                                          + ('fused into the product kernel: partial flux stored into the owner\'s slots '
-                                            'over NVLink peer memory, owners sum and broadcast; 2 barriers'
+                                            f'over NVLink peer memory, owners sum and broadcast one round behind ({max(args.chunks, 1)} rounds)'
                                             if args.exchange == 'peer' else
                                             f'all-reduce of dy/dt in {max(args.chunks, 1)} row blocks overlapped with the product'
                                             if args.exchange == 'allreduce' else
                                             f'flux reduce-scatter + table all-gather, {args.chunks} overlapped row chunks'))
                             if world > 1 else 'single GPU',
                             l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
-                clocks=clocks.summary(), e2e=e2e, gpu_launches=int(launches_total / world) * args.steps,
+                clocks=clocks.summary(), e2e=e2e,
+                gpu_launches=(int(launches_total / world)
+                              + (4 * max(args.chunks, 1) + 1 if world > 1 and args.exchange == 'peer' else 0)) * args.steps,
                 roofline=roofline, roofline_levels=roofline_levels, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
+                exchange_exposed_ms=(ms_step - max(rank_ms)) if rank_ms else None,
                 states_expanded_per_s=(info['n_nodes'] + info['worlds_walked']) / max(expand_s, 1e-9),
                 build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],

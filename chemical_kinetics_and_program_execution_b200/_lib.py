@@ -17,8 +17,8 @@ SYMBOLS = (
     'tapes_last_error', 'tapes_clear_error', 'tapes_alphabet_size', 'tapes_register_rules',
     'tapes_model', 'tapes_release_model', 'tapes_rhs_device', 'tapes_weights_device', 'tapes_flux_rows_device', 'tapes_rhs_profile', 'tapes_sync', 'tapes_model_info',
     'tapes_model_set', 'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
-    'tapes_peer_alloc', 'tapes_peer_open', 'tapes_peer_close', 'tapes_peer_free', 'tapes_flux_scatter_device',
-    'tapes_sum_slots_broadcast',
+    'tapes_peer_alloc', 'tapes_peer_open', 'tapes_peer_close', 'tapes_peer_free', 'tapes_peer_group_create',
+    'tapes_peer_group_destroy', 'tapes_peer_rhs', 'tapes_peer_group_error', 'tapes_dop853_create_peer',
 )
 
 _lib = None
@@ -70,10 +70,16 @@ def load():
   lib.tapes_peer_close.argtypes = [vp]
   lib.tapes_peer_free.restype = i32
   lib.tapes_peer_free.argtypes = [vp]
-  lib.tapes_flux_scatter_device.restype = i32
-  lib.tapes_flux_scatter_device.argtypes = [vp, vp, i32, i32, i64, vp]
-  lib.tapes_sum_slots_broadcast.restype = i32
-  lib.tapes_sum_slots_broadcast.argtypes = [vp, vp, vp, i32, i32, i64, vp]
+  lib.tapes_peer_group_create.restype = vp
+  lib.tapes_peer_group_create.argtypes = [i32, i32, i64, i32, vp, vp, vp]
+  lib.tapes_peer_group_destroy.restype = None
+  lib.tapes_peer_group_destroy.argtypes = [vp]
+  lib.tapes_peer_rhs.restype = i32
+  lib.tapes_peer_rhs.argtypes = [vp, vp, vp, vp]
+  lib.tapes_peer_group_error.restype = i32
+  lib.tapes_peer_group_error.argtypes = [vp]
+  lib.tapes_dop853_create_peer.restype = vp
+  lib.tapes_dop853_create_peer.argtypes = [vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, dbl]
   lib.tapes_rhs_profile.restype = i32
   lib.tapes_rhs_profile.argtypes = [vp, vp, vp, vp, vp, i32]
   lib.tapes_sync.restype = i32

@@ -235,16 +235,25 @@ int tapes_peer_free(void* d_ptr) {
   return 0;
 }
 
-int tapes_flux_scatter_device(void* model, void* const* staging, int world, int rank, int64_t block,
-                              void* cuda_stream) {
-  if (!model || !staging) { fail("null model or staging table"); return 1; }
+void* tapes_peer_group_create(int world, int rank, int64_t block, int rounds, void* const* staging,
+                              void* const* result, void* const* flags) {
+  if (!ensure_cuda()) return nullptr;
+  if (!staging || !result || !flags) { fail("peer_group_create: null pointer table"); return nullptr; }
+  try {
+    return (void*)tapes::peer_group_create(world, rank, (uint64_t)block, rounds, staging, result, flags);
+  } catch (const std::exception& ex) {
+    fail(std::string("peer_group_create: ") + ex.what());
+    return nullptr;
+  }
+}
+
+void tapes_peer_group_destroy(void* group) { delete (tapes::PeerGroup*)group; }
+
+int tapes_peer_rhs(void* group, void* model, const double* d_probs_in, void* cuda_stream) {
+  if (!group || !model) { fail("null group or model"); return 1; }
   try {
     tapes::Model& m = *(tapes::Model*)model;
-    if (world < 1 || world > tapes::PeerPointers::kMax) throw std::runtime_error("world size out of range");
-    tapes::PeerPointers pp;
-    for (int i = 0; i < world; ++i) pp.ptr[i] = (double*)staging[i];
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m.stream;
-    tapes::launch_flux_scatter(m, pp, world, rank, (uint64_t)block, st);
+    tapes::peer_rhs(*(tapes::PeerGroup*)group, m, d_probs_in, cuda_stream ? (cudaStream_t)cuda_stream : m.stream);
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());
@@ -252,17 +261,10 @@ int tapes_flux_scatter_device(void* model, void* const* staging, int world, int 
   }
 }
 
-int tapes_sum_slots_broadcast(void* model, const double* d_slots, void* const* result, int world, int rank,
-                              int64_t block, void* cuda_stream) {
-  if (!model || !d_slots || !result) { fail("null argument"); return 1; }
+int tapes_peer_group_error(void* group) {
+  if (!group) { fail("null group"); return 1; }
   try {
-    tapes::Model& m = *(tapes::Model*)model;
-    if (world < 1 || world > tapes::PeerPointers::kMax) throw std::runtime_error("world size out of range");
-    tapes::PeerPointers pp;
-    for (int i = 0; i < world; ++i) pp.ptr[i] = (double*)result[i];
-    cudaStream_t st = cuda_stream ? (cudaStream_t)cuda_stream : m.stream;
-    tapes::launch_sum_slots_broadcast(d_slots, pp, world, rank, (uint64_t)block, m.n_states, st);
-    return 0;
+    return tapes::peer_group_error(*(tapes::PeerGroup*)group);
   } catch (const std::exception& ex) {
     fail(ex.what());
     return 1;
@@ -374,8 +376,16 @@ int tapes_export_node_weights(void* model, double* weights) {
   return 0;
 }
 
+void* tapes_dop853_create_peer(void* model, void* group, const double* tableau, const double* y0, double t0,
+                               double t_bound, double rtol, double atol, double max_step, double first_step);
+
 void* tapes_dop853_create(void* model, const double* tableau, const double* y0, double t0, double t_bound,
                           double rtol, double atol, double max_step, double first_step) {
+  return tapes_dop853_create_peer(model, nullptr, tableau, y0, t0, t_bound, rtol, atol, max_step, first_step);
+}
+
+void* tapes_dop853_create_peer(void* model, void* group, const double* tableau, const double* y0, double t0,
+                               double t_bound, double rtol, double atol, double max_step, double first_step) {
   if (!model) { fail("null model"); return nullptr; }
   try {
     tapes::Dop853Tableau tab;
@@ -386,7 +396,8 @@ void* tapes_dop853_create(void* model, const double* tableau, const double* y0, 
     std::memcpy(tab.E3, p, sizeof(tab.E3)); p += 13;
     std::memcpy(tab.E5, p, sizeof(tab.E5)); p += 13;
     std::memcpy(tab.D, p, sizeof(tab.D));
-    return (void*)tapes::dop853_create(*(tapes::Model*)model, tab, y0, t0, t_bound, rtol, atol, max_step, first_step);
+    return (void*)tapes::dop853_create(*(tapes::Model*)model, (tapes::PeerGroup*)group, tab, y0, t0, t_bound, rtol,
+                                       atol, max_step, first_step);
   } catch (const std::exception& ex) {
     fail(ex.what());
     return nullptr;

@@ -196,13 +196,40 @@ struct PeerPointers {
   static constexpr int kMax = 16;
   double* ptr[kMax] = {};
 };
-// This rank's partial dy/dt of every state, stored into the owner's staging slot `rank`
-// (staging.ptr[o]: world * block doubles in rank o's memory; state i belongs to rank i / block).
-void launch_flux_scatter(Model& m, const PeerPointers& staging, int world, int rank, uint64_t block, cudaStream_t st);
-// Owner side: sums the world slots of its block in rank order and stores the result into every
-// rank's full vector (result.ptr[q]: n_rows doubles in rank q's memory).
-void launch_sum_slots_broadcast(const double* d_slots, const PeerPointers& result, int world, int rank,
-                                uint64_t block, uint64_t n_rows, cudaStream_t st);
+struct PeerFlags {
+  unsigned long long* ptr[PeerPointers::kMax] = {};
+};
+
+// The ranks that evaluate one problem together (rule set dealt to the ranks, states owned in
+// contiguous blocks of `block` states).  One right-hand side:
+//   main stream: weights; then per round c: product of sub-block c of every owner, stored straight
+//                into the owner's staging slot `rank` (peer stores), signal "round c landed";
+//   side stream: per round c: wait until every rank signalled round c, add the world slots of the
+//                own sub-block in rank order, store the sums into every rank's result vector;
+//                finally signal / wait "sums landed", and the main stream joins.
+// The owner's half of round c runs while the main stream computes round c + 1.  Signals are
+// 64-bit epochs in peer-visible flag arrays (release / acquire at system scope); waits time out
+// and raise an error flag instead of hanging.
+struct PeerGroup {
+  static constexpr int kMaxRounds = 16;
+  int world = 1, rank = 0, rounds = 4;
+  uint64_t block = 0;          // states per owner; a multiple of 32 * rounds
+  PeerPointers staging;        // [o]: world * block doubles in rank o's memory
+  PeerPointers result;         // [q]: world * block doubles in rank q's memory (full dy/dt)
+  PeerFlags flags;             // [q]: 2 * world epochs in rank q's memory: landed[r], summed[r]
+  unsigned long long epoch = 0;
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  int* d_error = nullptr;      // set by a wait that timed out
+  ~PeerGroup();
+};
+PeerGroup* peer_group_create(int world, int rank, uint64_t block, int rounds, void* const* staging,
+                             void* const* result, void* const* flags);
+// dy/dt of the whole problem into result.ptr[rank] on every rank; asynchronous on `st` (the side
+// stream is joined before returning control of `st`).
+void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st);
+// Non-zero once a wait timed out (a rank died or fell more than the timeout behind).
+int peer_group_error(PeerGroup& g);
 
 // Rebuilds the canonical CSR entries (ascending inside each row) from the slices into a device
 // buffer of nnz words.

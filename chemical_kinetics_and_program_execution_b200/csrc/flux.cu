@@ -9,8 +9,11 @@
 // consecutive forest nodes, so 32 states are cut into runs "lane l holds first + rank(l)" that cost
 // 8 bytes per run instead of 4 bytes per entry, and the gathers of a run are one contiguous
 // segment of the weight vector.  What does not fall into runs is stored column-major (coalesced).
+#include <cuda/atomic>
+
 #include <algorithm>
 #include <chrono>
+#include <memory>
 
 #include "engine.h"
 #include "primitives.cuh"
@@ -271,42 +274,71 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
 // blocks of `block` states (a multiple of 32, so a slice has one owner), and this rank's partial
 // dy/dt of a state goes straight into the owner's staging memory, slot `rank`, with peer stores
 // over NVLink while the rest of the kernel computes.  staging.ptr[o] is owner o's buffer of
-// world * block doubles.
+// world * block doubles.  One launch handles sub-block `round` (sub_slices slices) of every owner.
+// Every rank starts with a different owner (rank r with owner r + 1, then r + 2, ...): started in
+// the same order, all ranks would store into one owner's memory at a time and queue up at its
+// NVLink ingress (measured at 8 GPUs: +1.5 ms on a 3.6 ms kernel).
 template <int U>
 __global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w,
-    const __grid_constant__ PeerPointers staging, uint32_t rank,
-    uint64_t block, uint64_t rotate, uint64_t n_slices, uint64_t n_rows) {
+    const __grid_constant__ PeerPointers staging, uint32_t world, uint32_t rank, uint64_t block,
+    uint64_t sub_slices, uint64_t round, uint64_t n_slices, uint64_t n_rows) {
   const unsigned lane = threadIdx.x & 31;
-  // Every rank starts with the slices of a different owner (rank r with owner r + 1, then r + 2,
-  // ...): started in the same order, all ranks would store into one owner's memory at a time and
-  // queue up at its NVLink ingress (measured at 8 GPUs: +1.5 ms on a 3.6 ms kernel).
-  uint64_t s = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-  if (s >= n_slices) return;
-  s += rotate;
-  if (s >= n_slices) s -= n_slices;
+  const uint64_t idx = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (idx >= sub_slices * world) return;
+  const uint64_t hop = idx / sub_slices, within = idx - hop * sub_slices;
+  uint64_t owner = rank + 1 + hop;
+  if (owner >= world) owner -= world;
+  const uint64_t s = owner * (block / 32) + round * sub_slices + within;
+  if (s >= n_slices) return;  // ragged end of the table
   const double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
-  const uint64_t first_row = s * 32;
-  const uint64_t owner = first_row / block;
-  const uint64_t row = first_row + lane;
+  const uint64_t row = s * 32 + lane;
   if (row < n_rows) staging.ptr[owner][(uint64_t)rank * block + (row - owner * block)] = acc;
 }
 
-// The owner's half of the exchange: adds the world slots of its block in rank order (so every
-// rank of a run, and every run, gets the same bits) and stores the sums into the full vector of
-// every rank (peer stores).  result.ptr[q] is rank q's full dy/dt vector.
+// The owner's half of the exchange: adds the world slots of rows [j_lo, j_hi) of its block in rank
+// order (so every rank of a run, and every run, gets the same bits) and stores the sums into the
+// full vector of every rank (peer stores).  result.ptr[q] is rank q's full dy/dt vector.
 __global__ void __launch_bounds__(kThreads) sum_slots_broadcast_kernel(const double* __restrict__ slots,
                                                                        const __grid_constant__ PeerPointers result,
-                                                                       uint32_t world,
-                                                                       uint32_t rank, uint64_t block,
-                                                                       uint64_t n_rows) {
-  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                                       uint32_t world, uint32_t rank, uint64_t block,
+                                                                       uint64_t j_lo, uint64_t j_hi, uint64_t n_rows) {
+  const uint64_t j = j_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t row = (uint64_t)rank * block + j;
-  if (j >= block || row >= n_rows) return;
+  if (j >= j_hi || row >= n_rows) return;
   double total = 0.0;
   for (uint32_t r = 0; r < world; ++r) total += slots[(uint64_t)r * block + j];
   for (uint32_t q = 0; q < world; ++q) result.ptr[q][row] = total;
+}
+
+// Cross-GPU signalling through peer-visible flag arrays.  flags.ptr[q] holds 2 * world epochs in
+// rank q's memory: [r] "rank r's partial flux of the current round has landed here", [world + r]
+// "rank r's sums of the current right-hand side have landed here".  A kernel boundary orders the
+// data stores of the preceding kernel before the signal.
+__global__ void peer_signal_kernel(const __grid_constant__ PeerFlags flags, uint32_t world, uint32_t rank,
+                                   uint32_t set, unsigned long long epoch) {
+  const uint32_t q = threadIdx.x;
+  if (q >= world) return;
+  __threadfence_system();
+  cuda::atomic_ref<unsigned long long, cuda::thread_scope_system> slot(flags.ptr[q][set * world + rank]);
+  slot.store(epoch, cuda::std::memory_order_release);
+}
+
+__global__ void peer_wait_kernel(unsigned long long* __restrict__ mine, uint32_t world, uint32_t set,
+                                 unsigned long long epoch, unsigned long long timeout_ns, int* __restrict__ error) {
+  const uint32_t r = threadIdx.x;
+  if (r >= world) return;
+  cuda::atomic_ref<unsigned long long, cuda::thread_scope_system> slot(mine[set * world + r]);
+  unsigned long long start;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
+  while (slot.load(cuda::std::memory_order_acquire) < epoch) {
+    unsigned long long now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+    if (now - start > timeout_ns) { atomicExch(error, 1); break; }
+    __nanosleep(200);
+  }
+  __threadfence_system();
 }
 
 // Writes every lane's entries back to CSR positions (runs, then columns) and sorts the row.
@@ -414,25 +446,75 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_flux_scatter(Model& m, const PeerPointers& staging, int world, int rank, uint64_t block, cudaStream_t st) {
-  if (m.flux_format != 1) throw std::runtime_error("the fused exchange needs the sliced flux structure");
+PeerGroup::~PeerGroup() {
+  if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
+  if (fork) cudaEventDestroy(fork);
+  if (join) cudaEventDestroy(join);
+  if (d_error) cudaFree(d_error);
+}
+
+PeerGroup* peer_group_create(int world, int rank, uint64_t block, int rounds, void* const* staging,
+                             void* const* result, void* const* flags) {
   if (world < 1 || world > PeerPointers::kMax || rank < 0 || rank >= world) throw std::runtime_error("bad world / rank");
-  if (block == 0 || block % 32 != 0 || block * (uint64_t)world < m.n_states)
-    throw std::runtime_error("ownership blocks must be multiples of 32 states and cover the table");
+  if (rounds < 1 || rounds > PeerGroup::kMaxRounds) throw std::runtime_error("rounds out of range");
+  if (block == 0 || block % (32ull * rounds) != 0)
+    throw std::runtime_error("ownership blocks must be multiples of 32 * rounds states");
+  std::unique_ptr<PeerGroup> g(new PeerGroup());
+  g->world = world; g->rank = rank; g->block = block; g->rounds = rounds;
+  for (int i = 0; i < world; ++i) {
+    if (!staging[i] || !result[i] || !flags[i]) throw std::runtime_error("null peer buffer");
+    g->staging.ptr[i] = (double*)staging[i];
+    g->result.ptr[i] = (double*)result[i];
+    g->flags.ptr[i] = (unsigned long long*)flags[i];
+  }
+  // highest priority: the owner's small kernels must get the block slots the product grid frees,
+  // not queue behind the rest of that grid
+  int least = 0, greatest = 0;
+  TAPES_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  TAPES_CUDA_CHECK(cudaStreamCreateWithPriority(&g->side, cudaStreamNonBlocking, greatest));
+  TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&g->fork, cudaEventDisableTiming));
+  TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&g->join, cudaEventDisableTiming));
+  TAPES_CUDA_CHECK(cudaMalloc((void**)&g->d_error, sizeof(int)));
+  TAPES_CUDA_CHECK(cudaMemset(g->d_error, 0, sizeof(int)));
+  return g.release();
+}
+
+void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
+  if (m.flux_format != 1) throw std::runtime_error("the fused exchange needs the sliced flux structure");
+  if (g.block * (uint64_t)g.world < m.n_states) throw std::runtime_error("ownership blocks do not cover the table");
   const FluxSlices& fs = m.slices;
-  const unsigned grid = grid_for(fs.n_slices * 32, kThreads);
-  const uint64_t rotate = (((uint64_t)rank + 1) % (uint64_t)world) * (block / 32) % fs.n_slices;
-  flux_slices_scatter_kernel<4><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, staging,
-                                                          (uint32_t)rank, block, rotate, fs.n_slices, m.n_states);
+  const uint32_t world = (uint32_t)g.world, rank = (uint32_t)g.rank;
+  const uint64_t sub = g.block / (uint64_t)g.rounds, sub_slices = sub / 32;
+  const unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+  unsigned long long* mine = g.flags.ptr[g.rank];
+  weights_device(m, d_p, st);
+  // the side stream must not run ahead of work already queued on the main stream
+  TAPES_CUDA_CHECK(cudaEventRecord(g.fork, st));
+  TAPES_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.fork, 0));
+  const unsigned scatter_grid = grid_for(sub_slices * world * 32, kThreads);
+  const unsigned long long base = g.epoch;
+  for (int c = 0; c < g.rounds; ++c) {
+    flux_slices_scatter_kernel<4><<<scatter_grid, kThreads, 0, st>>>(
+        fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, g.staging, world, rank, g.block, sub_slices, (uint64_t)c,
+        fs.n_slices, m.n_states);
+    peer_signal_kernel<<<1, 32, 0, st>>>(g.flags, world, rank, 0u, base + c + 1);
+    peer_wait_kernel<<<1, 32, 0, g.side>>>(mine, world, 0u, base + c + 1, timeout_ns, g.d_error);
+    sum_slots_broadcast_kernel<<<grid_for(sub, kThreads), kThreads, 0, g.side>>>(
+        g.staging.ptr[g.rank], g.result, world, rank, g.block, sub * c, sub * (c + 1), m.n_states);
+  }
+  g.epoch = base + g.rounds;
+  // every owner's sums have landed everywhere (and its slots may be overwritten) before st goes on
+  peer_signal_kernel<<<1, 32, 0, g.side>>>(g.flags, world, rank, 1u, g.epoch);
+  peer_wait_kernel<<<1, 32, 0, g.side>>>(mine, world, 1u, g.epoch, timeout_ns, g.d_error);
+  TAPES_CUDA_CHECK(cudaEventRecord(g.join, g.side));
+  TAPES_CUDA_CHECK(cudaStreamWaitEvent(st, g.join, 0));
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_sum_slots_broadcast(const double* d_slots, const PeerPointers& result, int world, int rank,
-                                uint64_t block, uint64_t n_rows, cudaStream_t st) {
-  if (world < 1 || world > PeerPointers::kMax || rank < 0 || rank >= world) throw std::runtime_error("bad world / rank");
-  sum_slots_broadcast_kernel<<<grid_for(block, kThreads), kThreads, 0, st>>>(d_slots, result, (uint32_t)world,
-                                                                            (uint32_t)rank, block, n_rows);
-  TAPES_CUDA_CHECK(cudaGetLastError());
+int peer_group_error(PeerGroup& g) {
+  int h = 0;
+  TAPES_CUDA_CHECK(cudaMemcpy(&h, g.d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  return h;
 }
 
 void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st) {

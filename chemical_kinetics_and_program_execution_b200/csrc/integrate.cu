@@ -147,6 +147,7 @@ __global__ void observe_kernel(const double* __restrict__ y, const int64_t* __re
 
 struct Dop853 {
   Model* m = nullptr;
+  PeerGroup* peer = nullptr;
   uint64_t n = 0;
   cudaStream_t st = nullptr;
   Dop853Tableau tab;
@@ -178,7 +179,13 @@ double* dvec(uint64_t n) {
 }
 
 void fun(Dop853* s, const double* y, double* out) {
-  rhs_device(*s->m, y, out, s->st);
+  if (s->peer) {  // all ranks together; the sum arrives in this rank's peer-visible result vector
+    peer_rhs(*s->peer, *s->m, y, s->st);
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(out, s->peer->result.ptr[s->peer->rank], s->n * sizeof(double),
+                                     cudaMemcpyDeviceToDevice, s->st));
+  } else {
+    rhs_device(*s->m, y, out, s->st);
+  }
   s->nfev++;
 }
 
@@ -273,11 +280,11 @@ double attempt(Dop853* s, double h) {
 
 }  // namespace
 
-Dop853* dop853_create(Model& m, const Dop853Tableau& tab, const double* h_y0, double t0, double t_bound,
-                      double rtol, double atol, double max_step, double first_step) {
+Dop853* dop853_create(Model& m, PeerGroup* peer, const Dop853Tableau& tab, const double* h_y0, double t0,
+                      double t_bound, double rtol, double atol, double max_step, double first_step) {
   Dop853* s = new Dop853();
   try {
-    s->m = &m; s->n = m.n_states; s->st = m.stream; s->tab = tab;
+    s->m = &m; s->peer = peer; s->n = m.n_states; s->st = m.stream; s->tab = tab;
     s->t = t0; s->t_old = t0; s->t_bound = t_bound;
     s->direction = t_bound != t0 ? (t_bound > t0 ? 1.0 : -1.0) : 1.0;
     // validate_tol: rtol below 100 eps is raised to it
@@ -285,6 +292,7 @@ Dop853* dop853_create(Model& m, const Dop853Tableau& tab, const double* h_y0, do
     s->rtol = std::max(rtol, 100 * eps); s->atol = atol;
     s->max_step = max_step > 0 ? max_step : std::numeric_limits<double>::infinity();
     if (const char* f = std::getenv("TAPES_RK_FUSED")) s->fused = std::atoi(f) != 0;
+    if (peer) s->fused = false;  // the stage update cannot ride on a product whose result is still partial
     for (int i = 0; i < 3; ++i) s->ybuf[i] = dvec(s->n);
     for (int i = 0; i < 16; ++i) s->K[i] = dvec(s->n);
     for (int i = 0; i < 7; ++i) s->F[i] = nullptr;

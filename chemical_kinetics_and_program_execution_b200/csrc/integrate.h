@@ -27,8 +27,11 @@ struct Dop853Tableau {
 struct Dop853;
 
 // y0: n_states doubles on the HOST.  first_step <= 0 selects the initial step like SciPy.
-Dop853* dop853_create(Model& m, const Dop853Tableau& tab, const double* h_y0, double t0, double t_bound,
-                      double rtol, double atol, double max_step, double first_step);
+// peer (may be null): the ranks that evaluate the problem together.  Every rank then runs this
+// stepper on the full table: the right-hand side is peer_rhs (identical bits on all ranks), so
+// error norms and step sizes agree without further communication.
+Dop853* dop853_create(Model& m, PeerGroup* peer, const Dop853Tableau& tab, const double* h_y0, double t0,
+                      double t_bound, double rtol, double atol, double max_step, double first_step);
 void dop853_destroy(Dop853* s);
 
 // One solver.step(): returns 0 = running, 1 = finished, -1 = failed (step size too small).

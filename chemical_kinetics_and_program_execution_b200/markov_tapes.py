@@ -235,7 +235,8 @@ def sequence_observable(size_a, cl_k, seq):
 
 
 def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max_step=numpy.inf,
-                         first_step=None, observables=None, return_states=True, want_stats=False):
+                         first_step=None, observables=None, return_states=True, want_stats=False,
+                         peer_group=None):
   """DOP853 integration with the table resident in HBM (no per-stage host round trips).
 
   Follows scipy.integrate.solve_ivp(method='DOP853', t_eval=ts) step for step, so the result
@@ -245,6 +246,11 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
   `observables` (a list of symbol sequences, each no longer than cl_k) is given, their
   probabilities at `ts` ([len(ts), len(observables)]), computed on the device.  With
   return_states=False only the observables cross the host boundary.
+
+  Several GPUs: `tag` names this rank's share of the rule set (parallel.split_rule_set) and
+  `peer_group` is the parallel.PeerExchangeRhs of its model; every rank calls this function with
+  the same arguments otherwise and gets the same result (right-hand sides are evaluated by all
+  ranks together, everything else is replicated).
   """
   p0 = _checked_p0(p0, size_a, cl_k)
   ts = numpy.asarray(ts, dtype=numpy.float64)
@@ -253,10 +259,13 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
   model = u_lib.tapes_model(tag.encode(), cl_k)
   _lib.check(bool(model), 'tapes_model')
   tab = _dop853_tableau()
-  solver = u_lib.tapes_dop853_create(model, tab.ctypes.data, numpy.ascontiguousarray(p0).ctypes.data,
-                                     float(ts[0]), float(ts[-1]), float(rtol), float(atol),
-                                     float(max_step) if numpy.isfinite(max_step) else -1.0,
-                                     float(first_step) if first_step else -1.0)
+  if peer_group is not None and peer_group.model.handle != model:
+    raise ValueError('peer_group belongs to a different model')
+  solver = u_lib.tapes_dop853_create_peer(model, peer_group.group if peer_group is not None else None,
+                                          tab.ctypes.data, numpy.ascontiguousarray(p0).ctypes.data,
+                                          float(ts[0]), float(ts[-1]), float(rtol), float(atol),
+                                          float(max_step) if numpy.isfinite(max_step) else -1.0,
+                                          float(first_step) if first_step else -1.0)
   _lib.check(bool(solver), 'tapes_dop853_create')
   n = size_a ** cl_k
   obs = None
@@ -297,6 +306,8 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
     u_lib.tapes_dop853_info(solver, info.ctypes.data)
   finally:
     u_lib.tapes_dop853_destroy(solver)
+  if peer_group is not None:
+    peer_group.check()
   out = tuple(x for x in (states, series) if x is not None)
   out = out[0] if len(out) == 1 else out
   if want_stats:

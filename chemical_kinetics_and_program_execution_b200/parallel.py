@@ -158,85 +158,77 @@ class PeerExchangeRhs:
   kernels over NVLink peer memory (ranks = GPUs of one node, one process each).
 
   States are owned in contiguous blocks.  The product kernel stores this rank's partial dy/dt of a
-  state straight into the owner's staging buffer while it computes (tapes_flux_scatter_device);
-  after a barrier each owner adds its `world` slots in rank order and stores the sums into every
-  rank's result vector (tapes_sum_slots_broadcast).  No NCCL kernel competes with the
-  memory-bound product for SMs; the only collective left is a one-element all-reduce used as a
-  stream-ordered barrier.  Every rank ends up with bit-identical dy/dt.
+  state straight into the owner's staging buffer while it computes; in `rounds` rounds the owners
+  add their `world` slots in rank order and store the sums into every rank's result vector, one
+  round behind the product (tapes_peer_rhs).  Cross-GPU ordering uses epoch flags in peer memory,
+  so no NCCL kernel competes with the memory-bound product for SMs; torch.distributed only
+  carries the 64-byte CUDA IPC handles at set-up.  Every rank ends up with bit-identical dy/dt.
   """
 
-  def __init__(self, model, group=None):
+  def __init__(self, model, group=None, rounds=4):
     import ctypes
     from . import _lib, markov_tapes
     self.lib = markov_tapes.u_lib
     self.model = model
-    self.group = group
     self.world = dist.get_world_size(group)
     self.rank = dist.get_rank(group)
     self.n = model.n_states
+    self.rounds = max(1, min(16, int(rounds)))
+    unit = 32 * self.rounds
     block = -(-self.n // self.world)
-    self.block = -(-block // 32) * 32
+    self.block = -(-block // unit) * unit
     self.padded = self.block * self.world
-    h_staging = (ctypes.c_ubyte * 64)()
-    h_result = (ctypes.c_ubyte * 64)()
-    self.staging = self.lib.tapes_peer_alloc(self.padded, h_staging)
-    self.result = self.lib.tapes_peer_alloc(self.padded, h_result)
-    _lib.check(bool(self.staging) and bool(self.result), 'tapes_peer_alloc')
-    mine = (bytes(h_staging), bytes(h_result))
+    sizes = (self.padded, self.padded, 2 * self.world)  # staging, result, flags
+    handles = [(ctypes.c_ubyte * 64)() for _ in sizes]
+    self._own = [self.lib.tapes_peer_alloc(n, h) for n, h in zip(sizes, handles)]
+    _lib.check(all(bool(p) for p in self._own), 'tapes_peer_alloc')
     everyone = [None] * self.world
-    dist.all_gather_object(everyone, mine, group=group)
+    dist.all_gather_object(everyone, tuple(bytes(h) for h in handles), group=group)
     self._opened = []
-    staging, result = [], []
-    for r, (hs, hr) in enumerate(everyone):
-      if r == self.rank:
-        staging.append(self.staging)
-        result.append(self.result)
-        continue
-      ps = self.lib.tapes_peer_open(hs)  # bytes: ctypes passes the address of the 64-byte buffer
-      pr = self.lib.tapes_peer_open(hr)
-      _lib.check(bool(ps) and bool(pr), 'tapes_peer_open')
-      self._opened += [ps, pr]
-      staging.append(ps)
-      result.append(pr)
-    self._staging_table = (ctypes.c_void_p * self.world)(*staging)
-    self._result_table = (ctypes.c_void_p * self.world)(*result)
+    tables = [[], [], []]
+    for r, theirs in enumerate(everyone):
+      for kind, handle in enumerate(theirs):
+        if r == self.rank:
+          tables[kind].append(self._own[kind])
+        else:
+          ptr = self.lib.tapes_peer_open(handle)  # bytes: ctypes passes the address of the 64-byte buffer
+          _lib.check(bool(ptr), 'tapes_peer_open')
+          self._opened.append(ptr)
+          tables[kind].append(ptr)
+    arrays = [(ctypes.c_void_p * self.world)(*t) for t in tables]
+    self.group = self.lib.tapes_peer_group_create(self.world, self.rank, self.block, self.rounds, *arrays)
+    _lib.check(bool(self.group), 'tapes_peer_group_create')
     device = torch.device('cuda', torch.cuda.current_device())
-    self.out = torch.as_tensor(_DeviceView(self.result, self.padded), device=device)
-    self._token = torch.zeros(1, dtype=torch.float32, device=device)
-    self._barrier()
-    torch.cuda.synchronize()
-
-  def _barrier(self):
-    """Stream-ordered: later work on this stream starts after every rank's earlier work ended."""
-    dist.all_reduce(self._token, group=self.group)
+    self.out = torch.as_tensor(_DeviceView(self._own[1], self.padded), device=device)
+    dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into them
 
   def rhs_full(self, p_full):
     """p_full: at least n_states doubles on this device.  Returns the summed dy/dt (a view of the
-    peer-visible result vector, valid until the next call)."""
+    peer-visible result vector, valid until the next call).  Collective: every rank calls it."""
     from . import _lib, device as dev
-    stream = dev._current_stream_handle()
-    self.model.weights(p_full[:self.n])
-    rc = self.lib.tapes_flux_scatter_device(self.model.handle, self._staging_table, self.world, self.rank,
-                                            self.block, stream)
-    _lib.check(rc == 0, 'tapes_flux_scatter_device')
-    self._barrier()  # every rank's partial flux has landed in its owner's slots
-    rc = self.lib.tapes_sum_slots_broadcast(self.model.handle, self.staging, self._result_table, self.world,
-                                            self.rank, self.block, stream)
-    _lib.check(rc == 0, 'tapes_sum_slots_broadcast')
-    self._barrier()  # every owner's sums have landed everywhere; the slots may be overwritten
+    rc = self.lib.tapes_peer_rhs(self.group, self.model.handle, p_full.data_ptr(), dev._current_stream_handle())
+    _lib.check(rc == 0, 'tapes_peer_rhs')
     return self.out
 
-  def close(self):
+  def check(self):
+    """Raises when a cross-GPU wait timed out (results after that point are not valid)."""
     torch.cuda.synchronize()
-    self._barrier()
+    if self.lib.tapes_peer_group_error(self.group):
+      raise RuntimeError('peer exchange: a rank did not signal within the timeout')
+
+  def close(self, group=None):
     torch.cuda.synchronize()
+    dist.barrier(group=group)  # nobody is still storing into a buffer that is about to go away
+    self.lib.tapes_peer_group_destroy(self.group)
+    self.group = None
     for p in self._opened:
       self.lib.tapes_peer_close(p)
     self._opened = []
     self.out = None
-    self.lib.tapes_peer_free(self.staging)
-    self.lib.tapes_peer_free(self.result)
-    self.staging = self.result = None
+    dist.barrier(group=group)
+    for p in self._own:
+      self.lib.tapes_peer_free(p)
+    self._own = []
 
 
 class OverlappedRhs:

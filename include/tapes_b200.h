@@ -74,24 +74,31 @@ int tapes_flux_rows_device(void* model, double* d_probs_out, int64_t row_lo, int
                            void* cuda_stream);
 
 /* ---- multi-GPU flux exchange over NVLink peer memory (one process per GPU, one node) -------
- * States are owned in contiguous blocks of `block` states (a multiple of 32), state i by rank
- * i / block.  tapes_flux_scatter_device is tapes_flux_rows_device for all states with the exchange
- * fused in: this rank's partial dy/dt of a state is stored directly into the owner's staging
- * buffer (slot `rank` of world slots of `block` doubles) by peer stores while the kernel computes.
- * After a barrier, tapes_sum_slots_broadcast adds the owner's slots in rank order and stores the
- * sums into every rank's full vector.  Buffers come from tapes_peer_alloc (cudaMalloc + a 64-byte
- * CUDA IPC handle to send to the other ranks) and tapes_peer_open (maps a received handle). */
+ * The rule set is dealt to the ranks; every rank evaluates its rules over the full table.  States
+ * are owned in contiguous blocks of `block` states (a multiple of 32 * rounds), state i by rank
+ * i / block.  tapes_peer_rhs evaluates dy/dt of the whole problem on all ranks together:
+ * the product kernel stores this rank's partial dy/dt of a state directly into the owner's staging
+ * buffer (slot `rank` of world slots of `block` doubles) by peer stores while it computes; in
+ * `rounds` rounds the owners add their slots in rank order and store the sums into every rank's
+ * result vector, one round behind the product.  Cross-GPU ordering uses epoch flags in peer
+ * memory; a wait that exceeds 20 s sets the group's error flag instead of hanging.
+ * Buffers come from tapes_peer_alloc (cudaMalloc, zero-filled, plus a 64-byte CUDA IPC handle to
+ * send to the other ranks) and tapes_peer_open (maps a received handle).  Per rank: staging
+ * (world * block doubles), result (world * block doubles), flags (2 * world 64-bit words). */
 void* tapes_peer_alloc(int64_t n_doubles, void* ipc_handle64);
 void* tapes_peer_open(const void* ipc_handle64);
 int tapes_peer_close(void* d_ptr);
 int tapes_peer_free(void* d_ptr);
-/* staging: HOST array of `world` device pointers, entry o = rank o's staging buffer. */
-int tapes_flux_scatter_device(void* model, void* const* staging, int world, int rank, int64_t block,
-                              void* cuda_stream);
-/* d_slots: this rank's own staging buffer; result: HOST array of `world` device pointers, entry q =
- * rank q's full dy/dt vector (at least n_states doubles). */
-int tapes_sum_slots_broadcast(void* model, const double* d_slots, void* const* result, int world, int rank,
-                              int64_t block, void* cuda_stream);
+/* staging / result / flags: HOST arrays of `world` device pointers, entry q = rank q's buffer as
+ * mapped in this process (the own buffers for q = rank).  NULL on failure. */
+void* tapes_peer_group_create(int world, int rank, int64_t block, int rounds, void* const* staging,
+                              void* const* result, void* const* flags);
+void tapes_peer_group_destroy(void* group);
+/* Collective over the group: every rank calls it with the same table.  Asynchronous on
+ * `cuda_stream`; the sum is in this rank's result buffer when the stream reaches this point. */
+int tapes_peer_rhs(void* group, void* model, const double* d_probs_in, void* cuda_stream);
+/* Non-zero once a wait timed out (synchronise first). */
+int tapes_peer_group_error(void* group);
 
 /* One right-hand side with CUDA events between its phases, recorded on the launching stream;
  * synchronises and writes the phase durations in ms: [0] marginal tables + leaf-world
@@ -140,6 +147,11 @@ int tapes_export_node_weights(void* model, double* weights);
 void* tapes_dop853_create(void* model, const double* tableau, const double* y0, double t0,
                           double t_bound, double rtol, double atol, double max_step,
                           double first_step);
+/* The same stepper for a group of ranks (tapes_peer_group_create): every rank holds the full table
+ * and calls every tapes_dop853_* function in lockstep; right-hand sides are tapes_peer_rhs. */
+void* tapes_dop853_create_peer(void* model, void* group, const double* tableau, const double* y0,
+                               double t0, double t_bound, double rtol, double atol, double max_step,
+                               double first_step);
 void tapes_dop853_destroy(void* solver);
 
 /* One solver.step(): 0 running, 1 finished, -1 step size too small, -2 error. */

@@ -39,17 +39,31 @@ for chunks in (1, 5):
     err = float((out - want).abs().max() / want.abs().max())
     print(f'rank {rank}/{world} all-reduce blocks={chunks} max rel dev vs unsplit = {err:.2e}', flush=True)
     assert err < 1e-13
-peer = parallel.PeerExchangeRhs(part)
-for _ in range(3):
-    got = peer.rhs_full(p)
-torch.cuda.synchronize()
-err = float((got[:n] - want).abs().max() / want.abs().max())
-everyone = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
-dist.all_gather(everyone, got[:n].contiguous())
-same = all(bool(torch.equal(everyone[0], e)) for e in everyone)
-print(f'rank {rank}/{world} peer exchange max rel dev vs unsplit = {err:.2e}, identical on all ranks: {same}', flush=True)
-assert err < 1e-13 and same
-peer.close()
+for rounds in (1, 4):
+    peer = parallel.PeerExchangeRhs(part, rounds=rounds)
+    for _ in range(3):
+        got = peer.rhs_full(p)
+    peer.check()
+    err = float((got[:n] - want).abs().max() / want.abs().max())
+    everyone = [torch.zeros(n, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(everyone, got[:n].contiguous())
+    same = all(bool(torch.equal(everyone[0], e)) for e in everyone)
+    print(f'rank {rank}/{world} peer exchange rounds={rounds} max rel dev vs unsplit = {err:.2e}, '
+          f'identical on all ranks: {same}', flush=True)
+    assert err < 1e-13 and same
+    if rounds == 4:
+        # the stepper of all ranks together against the stepper of one rank on the whole rule set
+        p0 = p.cpu().numpy()
+        ts = numpy.linspace(0.0, 2.0, 5)
+        seqs = [[1], [2, 3], [0, 0, 1]]
+        kw = dict(size_a=A, cl_k=k, p0=p0, ts=ts, rtol=1e-9, atol=1e-12, observables=seqs)
+        together, st_t = mt.ode_integrate_device(tag=f'mg-part{rank}', peer_group=peer, want_stats=True, **kw)
+        alone, st_a = mt.ode_integrate_device(tag='mg-full', want_stats=True, **kw)
+        dev_states = float(abs(together[0] - alone[0]).max() / abs(alone[0]).max())
+        print(f'rank {rank}/{world} peer stepper vs single-rank stepper: states {dev_states:.2e}, '
+              f'observables {float(abs(together[1] - alone[1]).max()):.2e}, steps {st_t} vs {st_a}', flush=True)
+        assert dev_states < 1e-11 and st_t['accepted'] == st_a['accepted']
+    peer.close()
 plain = parallel.ShardedRhs(lambda a, b: part.rhs(a, b), n, device=dev)
 pf = torch.zeros(plain.padded, dtype=torch.float64, device=dev); pf[:n] = p
 out = torch.zeros_like(pf)

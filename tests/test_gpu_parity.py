@@ -268,13 +268,18 @@ def test_peer_exchange_with_one_rank(mt, device):
     model = device.DeviceModel('ex5-msrtf-machine', 5)  # 3125 states: the last ownership block is ragged
     p = torch.from_numpy(configs.markov_table(5, 5, 13)).cuda()
     want = model.rhs(p).cpu().numpy()
-    peer = parallel.PeerExchangeRhs(model)
-    assert peer.block % 32 == 0 and peer.block >= model.n_states
-    for _ in range(2):
-      got = peer.rhs_full(p)
-    torch.cuda.synchronize()
-    assert numpy.array_equal(got[:model.n_states].cpu().numpy(), want)
-    peer.close()
+    for rounds in (1, 3):
+      peer = parallel.PeerExchangeRhs(model, rounds=rounds)
+      assert peer.block % (32 * rounds) == 0 and peer.block >= model.n_states
+      for _ in range(2):
+        got = peer.rhs_full(p)
+      peer.check()
+      assert numpy.array_equal(got[:model.n_states].cpu().numpy(), want)
+      if rounds == 3:  # the stepper on a group of one is the plain stepper (unfused stage updates)
+        kw = dict(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=configs.ex5_p0(5), ts=numpy.linspace(0, 3, 4),
+                  rtol=1e-10, atol=1e-12)
+        assert numpy.array_equal(mt.ode_integrate_device(peer_group=peer, **kw), mt.ode_integrate_device(**kw))
+      peer.close()
   finally:
     dist.destroy_process_group()
 
