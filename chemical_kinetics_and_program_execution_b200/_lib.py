@@ -19,6 +19,7 @@ SYMBOLS = (
     'tapes_model_set', 'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
     'tapes_peer_alloc', 'tapes_peer_open', 'tapes_peer_close', 'tapes_peer_free', 'tapes_peer_group_create',
     'tapes_peer_group_destroy', 'tapes_peer_rhs', 'tapes_peer_group_error', 'tapes_dop853_create_peer',
+    'tapes_check_table',
 )
 
 _lib = None
@@ -80,6 +81,8 @@ def load():
   lib.tapes_peer_group_error.argtypes = [vp]
   lib.tapes_dop853_create_peer.restype = vp
   lib.tapes_dop853_create_peer.argtypes = [vp, vp, vp, vp, dbl, dbl, dbl, dbl, dbl, dbl]
+  lib.tapes_check_table.restype = i32
+  lib.tapes_check_table.argtypes = [i64, i64, vp, i32, dbl, i64, dbl, vp]
   lib.tapes_rhs_profile.restype = i32
   lib.tapes_rhs_profile.argtypes = [vp, vp, vp, vp, vp, i32]
   lib.tapes_sync.restype = i32

@@ -15,6 +15,7 @@
 #include "engine.h"
 #include "integrate.h"
 #include "rules.h"
+#include "validate.h"
 
 namespace {
 
@@ -469,6 +470,36 @@ int tapes_observe(void* model, const double* d_y, const int64_t* offset, const i
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());
+    return 1;
+  }
+}
+
+int tapes_check_table(int64_t alphabet, int64_t cl_k, const double* probs, int on_device, double eps_mpp,
+                      int64_t max_iterations, double tolerance, double* out6) {
+  if (!probs || !out6) { fail("check_table: null argument"); return 1; }
+  if (!ensure_cuda()) return 1;
+  double* staged = nullptr;
+  try {
+    if (alphabet < 1 || cl_k < 2 || cl_k > 32) throw std::runtime_error("needs alphabet >= 1 and 2 <= cl_k <= 32");
+    double states = 1;
+    for (int64_t i = 0; i < cl_k; ++i) states *= (double)alphabet;
+    if (states >= 4294967296.0) throw std::runtime_error("A^cl_k must be below 2^32");
+    const double* d_p = probs;
+    if (!on_device) {
+      const size_t bytes = (size_t)states * sizeof(double);
+      if (cudaMalloc((void**)&staged, bytes) != cudaSuccess) throw std::runtime_error("out of device memory");
+      if (cudaMemcpy(staged, probs, bytes, cudaMemcpyHostToDevice) != cudaSuccess) throw std::runtime_error("copy failed");
+      d_p = staged;
+    }
+    const tapes::TableCheck c = tapes::check_table((int)alphabet, (int)cl_k, d_p, eps_mpp, (int)max_iterations,
+                                                   tolerance, nullptr);
+    out6[0] = c.total; out6[1] = c.marginal_distance; out6[2] = c.stationarity_residual;
+    out6[3] = c.power_distance; out6[4] = c.last_change; out6[5] = (double)c.iterations;
+    if (staged) cudaFree(staged);
+    return 0;
+  } catch (const std::exception& ex) {
+    if (staged) cudaFree(staged);
+    fail(std::string("check_table: ") + ex.what());
     return 1;
   }
 }

@@ -957,9 +957,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
           }
         }
       }
-      m.stats.hash_inserts += (int64_t)n_par;
-      m.stats.hash_unique += (int64_t)NG;
-      m.stats.sum_nodes += (int64_t)NG;
     }
     TAPES_CUDA_CHECK(cudaGetLastError());
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));

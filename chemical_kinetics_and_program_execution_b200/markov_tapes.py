@@ -315,6 +315,54 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
   return out
 
 
+def check_table(spd, *, size_a=None, cl_k=None, eps_mpp=None, max_iterations=0, tolerance=1e-14):
+  """Validates a subsequence-probability table on the GPU without a dense eigen-decomposition.
+
+  `get_ctm_eigenvalue1_eigenspace` (framework/markov_tapes.py:133-175) builds the
+  A^(k-1) x A^(k-1) context transfer matrix and calls numpy.linalg.eig on it, which stops being
+  possible around 10^4 contexts.  The matrix has A non-zeros per row, so the same questions are
+  answered by streaming kernels (csrc/validate.cu) for tables of any size that fits the device.
+
+  Args:
+    spd: array of shape [A]*k, or flat with `size_a` and `cl_k` given; numpy or a CUDA torch tensor.
+    eps_mpp: the clip of `mpp_from_spd` (default 1e-100, as there).
+    max_iterations: power-iteration steps v <- T v from the uniform vector (0 = skip).
+    tolerance: stop the iteration when two successive vectors differ by less (2-norm).
+
+  Returns a dict: `total` (sum of the table), `marginal_distance` (2-norm of last-axis minus
+  first-axis marginal: the quantity the reference compares with its `eps`),
+  `stationarity_residual` (|T pi - pi| for the context marginal pi), and when iterating
+  `power_distance` (|v - pi|: large when pi is not the only stationary vector the uniform start
+  converges to), `last_change`, `iterations`.
+  """
+  if eps_mpp is None:
+    eps_mpp = 1e-100
+  on_device = hasattr(spd, 'is_cuda') and spd.is_cuda
+  if size_a is None or cl_k is None:
+    size_a, cl_k = int(spd.shape[0]), int(spd.ndim if not hasattr(spd, 'dim') else spd.dim())
+  n = size_a ** cl_k
+  if on_device:
+    import torch
+    if spd.dtype != torch.float64 or not spd.is_contiguous() or spd.numel() != n:
+      raise ValueError(f'expected {n} contiguous float64 entries')
+    torch.cuda.current_stream().synchronize()
+    ptr, keep = spd.data_ptr(), spd
+  else:
+    keep = numpy.ascontiguousarray(numpy.asarray(spd, dtype=numpy.float64).ravel())
+    if keep.size != n:
+      raise ValueError(f'expected {n} entries, got {keep.size}')
+    ptr = keep.ctypes.data
+  out = numpy.zeros(6, dtype=numpy.float64)
+  rc = u_lib.tapes_check_table(size_a, cl_k, ptr, 1 if on_device else 0, float(eps_mpp), int(max_iterations),
+                               float(tolerance), out.ctypes.data)
+  _lib.check(rc == 0, 'tapes_check_table')
+  del keep
+  result = dict(total=float(out[0]), marginal_distance=float(out[1]), stationarity_residual=float(out[2]))
+  if max_iterations > 0:
+    result.update(power_distance=float(out[3]), last_change=float(out[4]), iterations=int(out[5]))
+  return result
+
+
 def _run_validation():
   fn_dy_dt = get_dy_dt(tag='__canary_problem_radioactive_decay', size_a=2, cl_k=3, debug=False)
   observed = fn_dy_dt(numpy.full([8], fill_value=0.125, dtype=numpy.float64), 0.0).tolist()

@@ -177,6 +177,16 @@ int tapes_dop853_info(void* solver, double* out6);
 int tapes_observe(void* model, const double* d_y, const int64_t* offset, const int64_t* stride,
                   const int64_t* count, int64_t n_obs, double* out);
 
+/* Validation of a table of A^cl_k doubles (HOST buffer, or DEVICE buffer when on_device != 0)
+ * without the dense eigen-decomposition of framework/markov_tapes.py:133-175: the context transfer
+ * matrix of markov_tapes.py:107-130 has A non-zeros per row and is applied by a streaming kernel.
+ * out6: sum of the table; |last-axis marginal - first-axis marginal|_2 (markov_tapes.py:160-164);
+ * |T pi - pi|_2 for the context marginal pi; |v - pi|_2 for the limit v of the power iteration
+ * v <- T v from the uniform vector (0 iterations: skipped); |v_n - v_{n-1}|_2 at the last
+ * convergence test; iterations done.  eps_mpp is the clip of mpp_from_spd (markov_tapes.py:101). */
+int tapes_check_table(int64_t alphabet, int64_t cl_k, const double* probs, int on_device, double eps_mpp,
+                      int64_t max_iterations, double tolerance, double* out6);
+
 /* Host-only (no GPU needed): the flux-rule table of (tag, cl_k).  Call with all pointers NULL to
  * get sizes: returns the number of rules and stores the total step count in *n_steps. Arrays:
  * rule_ptr[n_rules + 1]; per step kind, length, long_index, short_index, prob; per rule and tape

@@ -284,6 +284,58 @@ def test_peer_exchange_with_one_rank(mt, device):
     dist.destroy_process_group()
 
 
+def _table_check_reference(spd, eps_mpp=1e-100, iterations=0):
+  """The same quantities from the dense construction the reference uses
+  (framework/markov_tapes.py:81-130, 155-166), for small tables."""
+  import itertools
+  size_a, k = spd.shape[0], spd.ndim
+  clipped = numpy.clip(spd, eps_mpp, 1)
+  mpp = clipped / clipped.sum(axis=-1, keepdims=True)
+  m = size_a ** (k - 1)
+  ctm = numpy.zeros([size_a] * (2 * (k - 1)))
+  for idx in itertools.product(range(size_a), repeat=k):
+    ctm[idx[1:] + idx[:-1]] += mpp[idx]
+  ctm = ctm.reshape(m, m)
+  right, left = spd.sum(axis=-1).ravel(), spd.sum(axis=0).ravel()
+  out = dict(total=spd.sum(), marginal_distance=numpy.linalg.norm(right - left),
+             stationarity_residual=numpy.linalg.norm(ctm @ left - left))
+  if iterations:
+    v = numpy.full(m, 1.0 / m)
+    for _ in range(iterations):
+      v = ctm @ v
+    out['power_distance'] = numpy.linalg.norm(v - left)
+  return out
+
+
+def test_check_table_matches_dense_reference(mt, p0_fixtures):
+  """Sparse validation of a table (csrc/validate.cu) against the reference's dense transfer
+  matrix: shipped starting tables are stationary, a perturbed one is not, and the power iteration
+  finds the context marginal of an ergodic table."""
+  import torch
+  ex5 = configs.ex5_p0(5).reshape([5] * 5)
+  markov = configs.markov_table(3, 4, 7).reshape([3] * 4)
+  bent = markov.copy()
+  bent[0, 1, 2, 0] += 0.01
+  bent[2, 2, 1, 1] -= 0.004
+  for name, spd, iterations in (('ex5', ex5, 0), ('markov', markov, 64), ('bent', bent, 16)):
+    want = _table_check_reference(spd, iterations=iterations)
+    got = mt.check_table(spd, max_iterations=iterations, tolerance=0.0)
+    for key, value in want.items():
+      assert abs(got[key] - value) <= 1e-12 * max(1.0, abs(value)), (name, key, got[key], value)
+    on_device = mt.check_table(torch.from_numpy(spd.copy()).cuda().reshape(-1), size_a=spd.shape[0], cl_k=spd.ndim,
+                               max_iterations=iterations, tolerance=0.0)
+    assert on_device == got
+  assert mt.check_table(ex5)['marginal_distance'] <= 1e-15 and mt.check_table(ex5)['stationarity_residual'] <= 1e-15
+  ergodic = mt.check_table(markov, max_iterations=2000, tolerance=1e-15)
+  assert ergodic['power_distance'] <= 1e-12 and ergodic['iterations'] < 2000
+  assert mt.check_table(bent)['marginal_distance'] > 1e-3
+  # the reference's own verdicts on the same tables (dense eig) agree
+  delta, eigenspace = mt.get_ctm_eigenvalue1_eigenspace(markov)
+  assert eigenspace is not None and eigenspace.shape[1] == 1 and delta < 1e-12
+  delta, eigenspace = mt.get_ctm_eigenvalue1_eigenspace(bent)
+  assert eigenspace is None and abs(delta - mt.check_table(bent)['marginal_distance']) < 1e-12
+
+
 def test_csr_export_round_trip(mt, device, monkeypatch):
   """The sliced form expands back to the same canonical CSR the plain build keeps, for both
   encoders (full runs only; masked runs from a merge of the 32 rows)."""
