@@ -418,11 +418,15 @@ def run_b200(args):
       sharded.check()
 
   # whole-job structural size
-  sizes = torch.tensor([info['nnz'], info['n_nodes'], info['n_terms'], info['launches_per_rhs']],
-                       dtype=torch.float64, device=device)
+  sizes = torch.tensor([info['nnz'], info['n_nodes'], info['n_terms'], info['launches_per_rhs'],
+                        info['n_nodes'] + info['worlds_walked']], dtype=torch.float64, device=device)
+  expand_s = torch.tensor([(timing['device_expand_ms'] + timing['host_enumerate_ms']) * 1e-3],
+                          dtype=torch.float64, device=device)
   if world > 1:
     dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
-  nnz_total, nodes_total, terms_total, launches_total = [float(x) for x in sizes.tolist()]
+    dist.all_reduce(expand_s, op=dist.ReduceOp.MAX)  # the ranks expand their rules concurrently
+  nnz_total, nodes_total, terms_total, launches_total, expanded_total = [float(x) for x in sizes.tolist()]
+  expand_s = float(expand_s.item())
   job_bytes = 28.0 * nnz_total + world * (24.0 * n + 8.0 * n * (1.0 + 2.0 / max(args.size_a - 1, 1)))
   value = job_bytes / (ms_step * 1e-3) / 1e9
 
@@ -489,7 +493,6 @@ def run_b200(args):
                seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu)
 
   if rank == 0:
-    expand_s = (timing['device_expand_ms'] + timing['host_enumerate_ms']) * 1e-3
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
                 data='synthetic',
@@ -510,7 +513,7 @@ def run_b200(args):
                               + (4 * max(args.chunks, 1) + 1 if world > 1 and args.exchange == 'peer' else 0)) * args.steps,
                 roofline=roofline, roofline_levels=roofline_levels, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
                 exchange_exposed_ms=(ms_step - max(rank_ms)) if rank_ms else None,
-                states_expanded_per_s=(info['n_nodes'] + info['worlds_walked']) / max(expand_s, 1e-9),
+                states_expanded_per_s=expanded_total / max(expand_s, 1e-9),
                 build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],
                            flux_slices={k: info.get(k) for k in ('n_slices', 'slice_words', 'runs', 'run_entries',

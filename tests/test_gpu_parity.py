@@ -230,6 +230,27 @@ def test_fused_right_chain_is_bit_identical(mt, device, monkeypatch, tag, size_a
   assert numpy.array_equal(got['0'][0], got['1'][0])
 
 
+def test_long_rows(mt, device, oracle):
+  """States with more than 128 flux entries (many rules on a small alphabet): runs are only
+  tracked for the first 128 entries of a row, the rest goes to columns; term set and dy/dt must
+  still match the oracle."""
+  import torch
+  size_a, cl_k, tag = 2, 7, 'long-rows'
+  rules = configs.random_rule_set(size_a, 70, seed=21)
+  mt.register_rule_set(tag, size_a, rules)
+  oracle.register_rules(tag, size_a, rules)
+  p = configs.markov_table(size_a, cl_k, 17)
+  model = device.DeviceModel(tag, cl_k)
+  row_ptr, entries = model.csr()
+  assert numpy.diff(row_ptr).max() > 128
+  for lo, hi in zip(row_ptr[:-1], row_ptr[1:]):
+    assert (numpy.diff(entries[lo:hi].astype(numpy.int64)) > 0).all()  # canonical order survives the round trip
+  got = model.rhs(torch.from_numpy(p).cuda()).cpu().numpy()
+  want = oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED)
+  assert abs(got - want).max() <= 1e-13 * abs(want).max()
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+
+
 def test_explicit_parent_lists_are_bit_identical(mt, device, monkeypatch):
   """The general form of a level (explicit parent lists) and the usual one (arithmetic
   progressions of parent ids) evaluate the same sums in the same order."""
