@@ -1080,7 +1080,7 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       // U loads in flight per thread; a group that owns its parents evaluates UO of them at a time
       // (each needs three loads).  Measured at n = 1e8, A = 10 (profiles/r01_g_sweep_fused_right_chain.log):
       // (U, UO) = (5, 3) 5.42 ms, (5, 2) 5.47, (4, 2) 5.66, (2, 2) 5.83, (5, 5) 6.20 (spills), 64 registers
-      // at 4 blocks per SM 5.63-5.94.
+      // at 4 blocks per SM 5.63-5.94; 40 registers at 6 blocks per SM (120 B of spills) 5.37-5.55: no gain.
 #define TAPES_LEVEL(U_, UO_, B_)                                                                             \
   (prog ? level_kernel<U_, UO_, true, B_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
         : level_kernel<U_, 1, false, 5><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
