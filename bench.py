@@ -338,8 +338,15 @@ def run_b200(args):
   sharded = None
   if world > 1:
     if args.exchange == 'peer':
-      sharded = parallel.PeerExchangeRhs(model, rounds=max(args.chunks, 1) if args.chunks <= 16 else 16)
-      padded = n
+      try:
+        sharded = parallel.PeerExchangeRhs(model, rounds=max(args.chunks, 1) if args.chunks <= 16 else 16)
+        padded = n
+      except RuntimeError as ex:  # raised on all ranks together: no CUDA IPC between these processes
+        if rank == 0:
+          print(f'peer exchange unavailable ({ex}); using the NCCL all-reduce exchange', file=sys.stderr)
+        args.exchange = 'allreduce'
+    if args.exchange == 'peer':
+      pass
     elif args.exchange == 'allreduce':
       sharded = parallel.OverlappedAllReduceRhs(model.weights, model.flux_rows, n, chunks=max(args.chunks, 1))
       padded = n

@@ -95,6 +95,7 @@ void* setup_gambit(void) {
 void cleanup_gambit(void* handle) {
   (void)handle;
   g_models.clear();
+  if (g_runtime && g_runtime->cuda_ok) tapes::release_build_scratch();
   if (g_runtime) { delete g_runtime; g_runtime = nullptr; }
 }
 

@@ -46,7 +46,13 @@ struct AllocTimer {
 };
 
 template <typename T>
-T* dkeep(size_t n) {  // allocations that live as long as the model
+T* dkeep(Model& m, size_t n) {  // arrays that live as long as the model
+  AllocTimer timer;
+  return m.arena.array<T>(n);
+}
+
+template <typename T>
+T* dtemp(size_t n) {  // large temporaries handed back with cudaFree
   AllocTimer timer;
   void* p = nullptr;
   TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
@@ -262,16 +268,50 @@ __global__ void group_fill_vals_kernel(const uint32_t* __restrict__ group, const
   }
 }
 
+constexpr uint32_t kShortGroup = 64;  // groups up to this length are sorted by one thread
+
 __global__ void group_sort_kernel(const uint64_t* __restrict__ ptr, uint64_t n_groups,
-                                  uint32_t* __restrict__ vals) {
+                                  uint32_t* __restrict__ vals, uint32_t* __restrict__ long_groups,
+                                  unsigned long long* __restrict__ n_long) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_groups) return;
   const uint64_t lo = ptr[g], hi = ptr[g + 1];
-  for (uint64_t a = lo + 1; a < hi; ++a) {  // insertion sort; groups are short
+  if (hi - lo > kShortGroup) {  // left to group_sort_long_kernel (a state many rules flow through)
+    if (long_groups) long_groups[atomicAdd(n_long, 1ull)] = (uint32_t)g;
+    return;
+  }
+  for (uint64_t a = lo + 1; a < hi; ++a) {  // insertion sort
     const uint32_t v = vals[a];
     uint64_t b = a;
     while (b > lo && vals[b - 1] > v) { vals[b] = vals[b - 1]; --b; }
     vals[b] = v;
+  }
+}
+
+// One block per long group: bitonic network in its all-ascending form (the first step of every
+// merge compares mirrored positions), so positions past the end act as +infinity without ever
+// being touched.
+__global__ void __launch_bounds__(kThreads) group_sort_long_kernel(const uint64_t* __restrict__ ptr,
+                                                                   const uint32_t* __restrict__ long_groups,
+                                                                   uint32_t* __restrict__ vals) {
+  const uint32_t g = long_groups[blockIdx.x];
+  uint32_t* v = vals + ptr[g];
+  const uint64_t len = ptr[g + 1] - ptr[g];
+  uint64_t padded = 1;
+  while (padded < len) padded <<= 1;
+  auto exchange = [&](uint64_t i, uint64_t partner) {
+    if (partner > i && partner < len) {
+      const uint32_t a = v[i], b = v[partner];
+      if (a > b) { v[i] = b; v[partner] = a; }
+    }
+  };
+  for (uint64_t k = 2; k <= padded; k <<= 1) {
+    for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) exchange(i, i ^ (k - 1));
+    __syncthreads();
+    for (uint64_t j = k >> 2; j > 0; j >>= 1) {
+      for (uint64_t i = threadIdx.x; i < len; i += blockDim.x) exchange(i, i ^ j);
+      __syncthreads();
+    }
   }
 }
 
@@ -649,22 +689,74 @@ Consts make_consts(const Model& m) {
 
 }  // namespace
 
+void* DeviceArena::take(size_t n_bytes) {
+  n_bytes = (std::max<size_t>(n_bytes, 1) + 255) & ~(size_t)255;
+  bytes += n_bytes;
+  if (n_bytes <= left) {
+    void* p = cursor;
+    cursor += n_bytes; left -= n_bytes;
+    return p;
+  }
+  void* p = nullptr;
+  if (n_bytes >= next_chunk / 2) {  // large arrays get a chunk of their own; the open chunk stays open
+    TAPES_CUDA_CHECK(cudaMalloc(&p, n_bytes));
+    chunks.push_back(p);
+    return p;
+  }
+  TAPES_CUDA_CHECK(cudaMalloc(&p, next_chunk));
+  chunks.push_back(p);
+  cursor = (char*)p + n_bytes;
+  left = next_chunk - n_bytes;
+  next_chunk = std::min<size_t>(next_chunk * 2, (size_t)1 << 30);
+  return p;
+}
+
+void DeviceArena::release() {
+  for (void* p : chunks) cudaFree(p);
+  chunks.clear();
+  cursor = nullptr; left = 0; bytes = 0; next_chunk = 32u << 20;
+}
+
 Model::~Model() {
   cudaStream_t st = stream;
   if (st) cudaStreamSynchronize(st);
-  auto fr = [&](auto*& p) { if (p) { cudaFree((void*)p); p = nullptr; } };
-  fr(rule_ptr); fr(step_kind); fr(step_len); fr(step_long); fr(step_short); fr(step_prob); fr(rule_w);
-  for (Level& lv : levels) {
-    fr(lv.root_rule); fr(lv.lp_gid); fr(lv.lp_io); fr(lv.lp_len); fr(lv.g_prefix); fr(lv.g_ptr); fr(lv.g_parents);
-    fr(lv.g_first); fr(lv.g_stride); fr(lv.g_count); fr(lv.g_total);
-  }
-  fr(node_w); fr(row_ptr); fr(entries); fr(marg); fr(d_marg_off); fr(d_in); fr(d_out);
-  fr(slices.slice_ptr); fr(slices.slice_runs); fr(slices.words);
+  if (entries) cudaFree(entries);
+  entries = nullptr;
+  arena.release();
   if (copy_stream) {
     cudaStreamDestroy(copy_stream);
     for (cudaEvent_t e : copy_events) if (e) cudaEventDestroy(e);
   }
   if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+namespace {
+// Never destroyed (no cudaFree during static destruction); release_build_scratch() empties them.
+Slab* build_scratch() {
+  static Slab* slabs = new Slab[3];
+  return slabs;
+}
+
+// Ascending order inside every group of a CSR-like list: short groups by one thread each, long
+// ones (found on the way) by one block each.
+void sort_groups(const uint64_t* ptr, uint64_t n_groups, uint32_t* vals, cudaStream_t st) {
+  if (n_groups == 0) return;
+  uint32_t* long_groups = dalloc<uint32_t>(n_groups, st);
+  unsigned long long* n_long = dalloc<unsigned long long>(1, st);
+  TAPES_CUDA_CHECK(cudaMemsetAsync(n_long, 0, 8, st));
+  group_sort_kernel<<<grid_for(n_groups, kThreads), kThreads, 0, st>>>(ptr, n_groups, vals, long_groups, n_long);
+  unsigned long long h_long = 0;
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_long, n_long, 8, cudaMemcpyDeviceToHost, st));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  if (h_long) group_sort_long_kernel<<<(unsigned)h_long, kThreads, 0, st>>>(ptr, long_groups, vals);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+  dfree(long_groups, st); dfree(n_long, st);
+}
+}  // namespace
+
+void release_build_scratch() {
+  Slab* slabs = build_scratch();
+  for (int i = 0; i < 3; ++i) slabs[i].release();
 }
 
 std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) {
@@ -716,13 +808,13 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.n_rules = (uint32_t)table.rules.size();
     auto up = [&](auto*& dptr, const auto& h) {
       typedef typename std::remove_const<typename std::remove_reference<decltype(h[0])>::type>::type T;
-      dptr = dkeep<T>(h.size());
+      dptr = dkeep<T>(m, h.size());
       if (!h.empty())
         TAPES_CUDA_CHECK(cudaMemcpyAsync((void*)dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
     };
     up(m.rule_ptr, ptr); up(m.step_kind, kind); up(m.step_len, len);
     up(m.step_long, ilong); up(m.step_short, ishort); up(m.step_prob, prob);
-    m.rule_w = dkeep<double>(m.n_rules);
+    m.rule_w = dkeep<double>(m, m.n_rules);
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   }
 
@@ -772,8 +864,13 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   Level cur_level;
   cur_level.base = 0;
   cur_level.n_roots = (uint32_t)roots.size();
-  Slab cur_slab;    // owns the arrays of `cur`
-  Slab s1, s2;      // scratch sized before / after the counts of a level are known; s2 owns `next`
+  // kept between builds while small, so that the reference's small problems do not pay for
+  // driver allocations at all
+  Slab* slabs = build_scratch();
+  Slab& cur_slab = slabs[0];  // owns the arrays of `cur`
+  Slab& s1 = slabs[1];        // scratch sized before the counts of a level are known
+  Slab& s2 = slabs[2];        // ... and after; owns `next`
+  cur_slab.reset(); s1.reset(); s2.reset();
   auto plan_frontier = [](Slab& slab, uint64_t n, size_t idx[5]) {
     idx[0] = slab.want(n * 4); idx[1] = slab.want(n * 4); idx[2] = slab.want(n * 4);
     idx[3] = slab.want(n); idx[4] = slab.want(n);
@@ -789,7 +886,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       h_io[i] = roots[i].io; h_ia[i] = roots[i].ia; h_seed[i] = roots[i].seed; h_rule[i] = roots[i].rule;
       h_meta[i] = roots[i].meta; h_fl[i] = roots[i].flags;
     }
-    cur_level.root_rule = dkeep<uint32_t>(cur.n);
+    cur_level.root_rule = dkeep<uint32_t>(m, cur.n);
     size_t fi[5];
     plan_frontier(cur_slab, cur.n, fi);
     cur_slab.commit();
@@ -877,17 +974,17 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       rank_slots_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs);
     }
     if (NL) {
-      next_level.lp_gid = dkeep<uint32_t>(NL);
-      next_level.lp_io = dkeep<uint32_t>(NL);
-      next_level.lp_len = dkeep<uint8_t>(NL);
+      next_level.lp_gid = dkeep<uint32_t>(m, NL);
+      next_level.lp_io = dkeep<uint32_t>(m, NL);
+      next_level.lp_len = dkeep<uint8_t>(m, NL);
     }
     EdgeChunk ec{nullptr, nullptr, 2 * NT};
-    if (NT) { ec.row = dkeep<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT; }  // one allocation for both
+    if (NT) { ec.row = dtemp<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT; }  // one allocation for both
     emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, kflag, lrank, trank,
                                                           NL, hs, next, next_level.lp_gid, next_level.lp_io,
                                                           next_level.lp_len, ec.row, ec.val, keyrank);
     if (NG) {
-      next_level.g_prefix = dkeep<uint32_t>(NG);
+      next_level.g_prefix = dkeep<uint32_t>(m, NG);
       emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
                                                                      NL * (uint64_t)m.A, next_level.g_prefix);
       // parent lists of the prefix groups
@@ -899,10 +996,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       exclusive_scan_u32(cnt, NG, g_ptr, scan_tmp, st);
       TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
       group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base, g_ptr, cnt, g_parents);
-      group_sort_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(g_ptr, NG, g_parents);
-      next_level.g_first = dkeep<uint32_t>(NG);
-      next_level.g_stride = dkeep<uint32_t>(NG);
-      next_level.g_count = dkeep<uint32_t>(NG);
+      sort_groups(g_ptr, NG, g_parents, st);
+      next_level.g_first = dkeep<uint32_t>(m, NG);
+      next_level.g_stride = dkeep<uint32_t>(m, NG);
+      next_level.g_count = dkeep<uint32_t>(m, NG);
       group_progression_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
           g_ptr, g_parents, NG, next_level.g_first, next_level.g_stride, next_level.g_count, counters + 1);
       unsigned long long h_counts[2] = {0, 0};  // parents, irregular groups
@@ -913,10 +1010,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       next_level.n_group_parents = n_par;
       if (h_counts[1] != 0 || std::getenv("TAPES_KEEP_PARENT_LISTS")) {
         // some list is not a progression: this level keeps its explicit lists
-        auto drop = [](auto*& q) { AllocTimer timer; cudaFree((void*)q); q = nullptr; };
-        drop(next_level.g_first); drop(next_level.g_stride); drop(next_level.g_count);
-        next_level.g_ptr = dkeep<uint64_t>(NG + 1);
-        next_level.g_parents = dkeep<uint32_t>(n_par);
+        next_level.g_first = next_level.g_stride = next_level.g_count = nullptr;  // their memory stays in the arena
+        next_level.g_ptr = dkeep<uint64_t>(m, NG + 1);
+        next_level.g_parents = dkeep<uint32_t>(m, n_par);
         TAPES_CUDA_CHECK(cudaMemcpyAsync(next_level.g_ptr, g_ptr, (NG + 1) * 8, cudaMemcpyDeviceToDevice, st));
         TAPES_CUDA_CHECK(cudaMemcpyAsync(next_level.g_parents, g_parents, n_par * 4, cudaMemcpyDeviceToDevice, st));
         m.stats.irregular_levels++;
@@ -948,7 +1044,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
           TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_deferred, counters + 1, 8, cudaMemcpyDeviceToHost, st));
           TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
           if (h_deferred) {
-            cur_level.g_total = dkeep<double>(PG);
+            cur_level.g_total = dkeep<double>(m, PG);
             next_level.prev_right_base = right_base;
             next_level.prev_prefix = cur_level.g_prefix;
             next_level.prev_total = cur_level.g_total;
@@ -969,7 +1065,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     cur = next;
     cur_level = next_level;
   }
-  cur_slab.release(); s1.release(); s2.release();
+  if (cur_slab.capacity + s1.capacity + s2.capacity > ((size_t)1 << 30)) {
+    cur_slab.release(); s1.release(); s2.release();
+  }
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
   m.stats.nodes = (int64_t)m.n_nodes;
   m.stats.terms = (int64_t)total_terms;
@@ -986,10 +1084,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (const EdgeChunk& ec : edge_chunks)
       group_count_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.n, cnt);
-    m.row_ptr = dkeep<uint64_t>(n + 1);
+    m.row_ptr = dkeep<uint64_t>(m, n + 1);
     uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(n), st);
     exclusive_scan_u32(cnt, n, m.row_ptr, scan_tmp, st);
-    m.entries = dkeep<uint32_t>(m.nnz);
+    m.entries = dtemp<uint32_t>(m.nnz);
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (EdgeChunk& ec : edge_chunks) {
       group_fill_vals_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.val, ec.n, m.row_ptr, cnt, m.entries);
@@ -997,7 +1095,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       cudaFree(ec.row);  // row and val share one allocation
       ec.row = ec.val = nullptr;
     }
-    group_sort_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(m.row_ptr, n, m.entries);
+    sort_groups(m.row_ptr, n, m.entries, st);
     dfree(cnt, st); dfree(scan_tmp, st);
     TAPES_CUDA_CHECK(cudaGetLastError());
   }
@@ -1031,10 +1129,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   for (int L = 0; L < m.k; ++L) { m.marg_off[L] = m.marg_total; m.marg_total += m.pow_a[L]; }
   m.marg_off[m.k] = m.marg_total;
   for (int L = m.k + 1; L < 40; ++L) m.marg_off[L] = 0;
-  m.marg = dkeep<double>(m.marg_total);
-  m.d_marg_off = dkeep<uint64_t>(40);
+  m.marg = dkeep<double>(m, m.marg_total);
+  m.d_marg_off = dkeep<uint64_t>(m, 40);
   TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_marg_off, m.marg_off, 40 * 8, cudaMemcpyHostToDevice, st));
-  m.node_w = dkeep<double>(m.n_nodes);
+  m.node_w = dkeep<double>(m, m.n_nodes);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.launches_per_rhs = rhs_launch_count(m);
   return mp;
@@ -1182,8 +1280,8 @@ void rhs_host(Model& m, const double* h_p, double* h_out) {
   const uint64_t n = m.n_states;
   const size_t bytes = (size_t)n * 8;
   if (!m.d_in) {
-    m.d_in = dkeep<double>(n);
-    m.d_out = dkeep<double>(n);
+    m.d_in = dkeep<double>(m, n);
+    m.d_out = dkeep<double>(m, n);
     TAPES_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : m.copy_events) TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }

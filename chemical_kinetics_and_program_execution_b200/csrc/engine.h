@@ -80,6 +80,24 @@ struct FluxSlices {
   int min_run_lanes = 0;
 };
 
+// Device memory that lives as long as a model: a bump allocator over a few large cudaMalloc
+// chunks.  A model has a few hundred arrays; asking the driver for each of them cost 45-780 ms per
+// build (more the more memory the process already holds), most of the build time of the
+// reference's small problems.
+struct DeviceArena {
+  std::vector<void*> chunks;
+  char* cursor = nullptr;
+  size_t left = 0, next_chunk = 32u << 20, bytes = 0;
+  DeviceArena() {}
+  DeviceArena(const DeviceArena&) = delete;
+  DeviceArena& operator=(const DeviceArena&) = delete;
+  ~DeviceArena() { release(); }
+  void* take(size_t n_bytes);  // 256-byte aligned; throws std::runtime_error when out of memory
+  template <typename T>
+  T* array(size_t n) { return (T*)take((n ? n : 1) * sizeof(T)); }
+  void release();
+};
+
 struct BuildStats {
   int64_t worlds_walked = 0, leaf_worlds = 0, flux_rules = 0, seeds = 0;
   int64_t nodes = 0, sum_nodes = 0, terms = 0, levels = 0;  // sum_nodes = prefix groups
@@ -93,6 +111,7 @@ struct BuildStats {
 };
 
 struct Model {
+  DeviceArena arena;  // owns every array below except `entries`
   int A = 0, k = 0;
   uint64_t n_states = 0;  // A^k
   uint64_t pow_a[40];
@@ -145,6 +164,9 @@ struct Model {
 
   ~Model();
 };
+
+// Frees the scratch memory small builds leave behind for the next build.
+void release_build_scratch();
 
 // Builds the device structures for a rule table.  Throws std::runtime_error on failure.
 std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream);

@@ -33,12 +33,6 @@ T* dalloc(size_t n, cudaStream_t st) {
   TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st));
   return (T*)p;
 }
-template <typename T>
-T* dkeep(size_t n) {
-  void* p = nullptr;
-  TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
-  return (T*)p;
-}
 
 // One warp merges the (ascending) rows of its 32 states into one ascending stream and cuts it into
 // runs: a run continues while the next entry is the previous one + 1 and sits in a higher lane.
@@ -333,6 +327,7 @@ __global__ void peer_wait_kernel(unsigned long long* __restrict__ mine, uint32_t
   unsigned long long start;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(start));
   while (slot.load(cuda::std::memory_order_acquire) < epoch) {
+    if (*(volatile int*)error) break;  // an earlier wait already gave up: do not stack timeouts
     unsigned long long now;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
     if (now - start > timeout_ns) { atomicExch(error, 1); break; }
@@ -384,7 +379,7 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
   fs.min_run_lanes = std::max(1, std::min(32, min_run_lanes));
   const uint64_t S = fs.n_slices;
   const unsigned grid = grid_for(S * 32, kThreads);
-  fs.slice_runs = dkeep<uint32_t>(S);
+  fs.slice_runs = m.arena.array<uint32_t>(S);
   uint32_t* cols = dalloc<uint32_t>(S, st);
   uint32_t* sizes = dalloc<uint32_t>(S, st);
   const bool full_only = fs.min_run_lanes == 32;
@@ -395,12 +390,12 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
     encode_slices_kernel<false><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.min_run_lanes,
                                                           fs.slice_runs, cols, nullptr, nullptr);
   slice_sizes_kernel<<<grid_for(S, kThreads), kThreads, 0, st>>>(fs.slice_runs, cols, S, sizes);
-  fs.slice_ptr = dkeep<uint64_t>(S + 1);
+  fs.slice_ptr = m.arena.array<uint64_t>(S + 1);
   uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(S), st);
   exclusive_scan_u32(sizes, S, fs.slice_ptr, scan_tmp, st);
   TAPES_CUDA_CHECK(cudaMemcpyAsync(&fs.n_words, fs.slice_ptr + S, 8, cudaMemcpyDeviceToHost, st));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-  fs.words = dkeep<uint32_t>(fs.n_words);
+  fs.words = m.arena.array<uint32_t>(fs.n_words);
   TAPES_CUDA_CHECK(cudaMemsetAsync(fs.words, 0xff, fs.n_words * 4, st));  // columns default to "none"
   if (full_only)
     encode_full_runs_kernel<true><<<grid, kThreads, 0, st>>>(m.row_ptr, m.entries, n, S, fs.slice_runs, cols,

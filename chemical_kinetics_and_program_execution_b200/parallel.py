@@ -180,27 +180,62 @@ class PeerExchangeRhs:
     self.padded = self.block * self.world
     sizes = (self.padded, self.padded, 2 * self.world)  # staging, result, flags
     handles = [(ctypes.c_ubyte * 64)() for _ in sizes]
-    self._own = [self.lib.tapes_peer_alloc(n, h) for n, h in zip(sizes, handles)]
-    _lib.check(all(bool(p) for p in self._own), 'tapes_peer_alloc')
+    self._own, self._opened, self.group, self.out = [], [], None, None
+    # every step below ends in a collective that all ranks reach whether or not their own part
+    # worked, so a rank that cannot allocate or map peer memory makes all ranks raise together
+    # instead of leaving the others waiting
+    problem = None
+    try:
+      self._own = [self.lib.tapes_peer_alloc(n, h) for n, h in zip(sizes, handles)]
+      _lib.check(all(bool(p) for p in self._own), 'tapes_peer_alloc')
+    except Exception as ex:  # pylint: disable=broad-except
+      problem = repr(ex)
     everyone = [None] * self.world
-    dist.all_gather_object(everyone, tuple(bytes(h) for h in handles), group=group)
+    dist.all_gather_object(everyone, (problem, tuple(bytes(h) for h in handles)), group=group)
+    self._raise_together([e[0] for e in everyone], group, collective_done=True)
+    try:
+      tables = [[], [], []]
+      for r, (_, theirs) in enumerate(everyone):
+        for kind, handle in enumerate(theirs):
+          if r == self.rank:
+            tables[kind].append(self._own[kind])
+          else:
+            ptr = self.lib.tapes_peer_open(handle)  # bytes: ctypes passes the address of the 64-byte buffer
+            _lib.check(bool(ptr), 'tapes_peer_open')
+            self._opened.append(ptr)
+            tables[kind].append(ptr)
+      arrays = [(ctypes.c_void_p * self.world)(*t) for t in tables]
+      self.group = self.lib.tapes_peer_group_create(self.world, self.rank, self.block, self.rounds, *arrays)
+      _lib.check(bool(self.group), 'tapes_peer_group_create')
+      device = torch.device('cuda', torch.cuda.current_device())
+      self.out = torch.as_tensor(_DeviceView(self._own[1], self.padded), device=device)
+    except Exception as ex:  # pylint: disable=broad-except
+      problem = repr(ex)
+    # also the barrier "every rank has mapped every buffer" before anyone stores into them
+    self._raise_together([problem], group, collective_done=False)
+
+  def _raise_together(self, problems, group, collective_done):
+    if not collective_done:
+      gathered = [None] * self.world
+      dist.all_gather_object(gathered, problems[0], group=group)
+      problems = gathered
+    bad = [(r, p) for r, p in enumerate(problems) if p]
+    if bad:
+      self._release()
+      raise RuntimeError('peer exchange set-up failed on rank(s) ' + '; '.join(f'{r}: {p}' for r, p in bad))
+
+  def _release(self):
+    if self.group:
+      self.lib.tapes_peer_group_destroy(self.group)
+    self.group = None
+    for p in self._opened:
+      self.lib.tapes_peer_close(p)
     self._opened = []
-    tables = [[], [], []]
-    for r, theirs in enumerate(everyone):
-      for kind, handle in enumerate(theirs):
-        if r == self.rank:
-          tables[kind].append(self._own[kind])
-        else:
-          ptr = self.lib.tapes_peer_open(handle)  # bytes: ctypes passes the address of the 64-byte buffer
-          _lib.check(bool(ptr), 'tapes_peer_open')
-          self._opened.append(ptr)
-          tables[kind].append(ptr)
-    arrays = [(ctypes.c_void_p * self.world)(*t) for t in tables]
-    self.group = self.lib.tapes_peer_group_create(self.world, self.rank, self.block, self.rounds, *arrays)
-    _lib.check(bool(self.group), 'tapes_peer_group_create')
-    device = torch.device('cuda', torch.cuda.current_device())
-    self.out = torch.as_tensor(_DeviceView(self._own[1], self.padded), device=device)
-    dist.barrier(group=group)  # every rank has mapped every buffer before anyone stores into them
+    self.out = None
+    for p in self._own:
+      if p:
+        self.lib.tapes_peer_free(p)
+    self._own = []
 
   def rhs_full(self, p_full):
     """p_full: at least n_states doubles on this device.  Returns the summed dy/dt (a view of the
@@ -219,16 +254,8 @@ class PeerExchangeRhs:
   def close(self, group=None):
     torch.cuda.synchronize()
     dist.barrier(group=group)  # nobody is still storing into a buffer that is about to go away
-    self.lib.tapes_peer_group_destroy(self.group)
-    self.group = None
-    for p in self._opened:
-      self.lib.tapes_peer_close(p)
-    self._opened = []
-    self.out = None
+    self._release()
     dist.barrier(group=group)
-    for p in self._own:
-      self.lib.tapes_peer_free(p)
-    self._own = []
 
 
 class OverlappedRhs:
