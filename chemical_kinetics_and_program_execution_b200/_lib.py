@@ -19,7 +19,7 @@ SYMBOLS = (
     'tapes_model_set', 'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
     'tapes_peer_alloc', 'tapes_peer_open', 'tapes_peer_close', 'tapes_peer_free', 'tapes_peer_group_create',
     'tapes_peer_group_destroy', 'tapes_peer_rhs', 'tapes_peer_group_error', 'tapes_dop853_create_peer',
-    'tapes_check_table',
+    'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts',
 )
 
 _lib = None
@@ -55,6 +55,10 @@ def load():
   lib.tapes_register_rules.argtypes = [ctypes.c_char_p, i64, i64] + [vp] * 7
   lib.tapes_model.restype = vp
   lib.tapes_model.argtypes = [ctypes.c_char_p, i64]
+  lib.tapes_model_part.restype = vp
+  lib.tapes_model_part.argtypes = [ctypes.c_char_p, i64, i64, i64]
+  lib.tapes_rule_parts.restype = i64
+  lib.tapes_rule_parts.argtypes = [ctypes.c_char_p, i64, i64, vp, vp]
   lib.tapes_release_model.restype = i32
   lib.tapes_release_model.argtypes = [ctypes.c_char_p, i64]
   lib.tapes_rhs_device.restype = i32
@@ -136,7 +140,8 @@ MODEL_INFO_FIELDS = (
     'n_sum_nodes', 'worlds_walked', 'leaf_worlds', 'seeds', 'hash_inserts', 'hash_unique',
     'alphabet', 'cl_k', 'spmv_lanes_per_row', 'flux_format', 'n_slices', 'slice_words', 'runs',
     'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll',
-    'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups')
+    'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups',
+    'chain_levels', 'chain_kernels', 'chain_unroll')
 
 
 def model_info(model):
@@ -178,6 +183,19 @@ def rule_table(tag, cl_k):
   out['worlds_walked'] = int(stats[0])
   out['leaf_worlds'] = int(stats[1])
   return out
+
+
+def rule_parts(tag, cl_k, n_parts):
+  """Host-only: (owner[int32], cost[float64]) of every flux rule of (tag, cl_k) when the problem
+  is dealt to n_parts ranks (the dealing tapes_model_part uses)."""
+  lib = load()
+  n_rules = lib.tapes_rule_parts(tag.encode(), cl_k, n_parts, None, None)
+  check(n_rules >= 0, 'tapes_rule_parts')
+  owner = numpy.zeros(n_rules, dtype=numpy.int32)
+  cost = numpy.zeros(n_rules, dtype=numpy.float64)
+  check(lib.tapes_rule_parts(tag.encode(), cl_k, n_parts, owner.ctypes.data, cost.ctypes.data) == n_rules,
+        'tapes_rule_parts')
+  return owner, cost
 
 
 def register_rules(tag, size_a, rules):

@@ -10,6 +10,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 
 #include "../../include/tapes_b200.h"
 #include "engine.h"
@@ -26,7 +27,9 @@ struct Runtime {
 
 std::string g_error;
 Runtime* g_runtime = nullptr;
-std::map<std::pair<std::string, int>, std::unique_ptr<tapes::Model>> g_models;
+// (tag, cl_k, part, n_parts); the whole problem is part 0 of 1
+typedef std::tuple<std::string, int, int, int> ModelKey;
+std::map<ModelKey, std::unique_ptr<tapes::Model>> g_models;
 
 void fail(const std::string& msg) {
   g_error = msg;
@@ -60,9 +63,10 @@ bool ensure_cuda() {
   return true;
 }
 
-tapes::Model* get_model(const char* tag, int64_t cl_k) {
+tapes::Model* get_model(const char* tag, int64_t cl_k, int64_t part = 0, int64_t n_parts = 1) {
   tapes::register_builtin_problems();
-  auto key = std::make_pair(std::string(tag), (int)cl_k);
+  if (n_parts < 1 || part < 0 || part >= n_parts) { fail("part must be in 0..n_parts-1"); return nullptr; }
+  const ModelKey key(std::string(tag), (int)cl_k, (int)part, (int)n_parts);
   auto it = g_models.find(key);
   if (it != g_models.end()) return it->second.get();
   const tapes::Problem* prob = tapes::find_problem(tag);
@@ -71,6 +75,7 @@ tapes::Model* get_model(const char* tag, int64_t cl_k) {
   try {
     auto t0 = std::chrono::steady_clock::now();
     tapes::RuleTable table = tapes::enumerate_rules(*prob, (int)cl_k);
+    if (n_parts > 1) table = tapes::rule_table_part(table, (int)part, (int)n_parts);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     std::unique_ptr<tapes::Model> m = tapes::build_model(table, nullptr);
     m->stats.host_enumerate_ms = ms;
@@ -146,7 +151,7 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
     tapes::register_problem(tag, (int)alphabet, tapes::body_from_rewrite_rules(std::move(rules)));
     // a re-registered tag invalidates cached structures
     for (auto it = g_models.begin(); it != g_models.end();)
-      it = (it->first.first == tag) ? g_models.erase(it) : std::next(it);
+      it = (std::get<0>(it->first) == tag) ? g_models.erase(it) : std::next(it);
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());
@@ -156,8 +161,36 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
 
 void* tapes_model(const char* tag, int64_t cl_k) { return (void*)get_model(tag, cl_k); }
 
-int tapes_release_model(const char* tag, int64_t cl_k) {
-  return g_models.erase(std::make_pair(std::string(tag), (int)cl_k)) ? 0 : 1;
+void* tapes_model_part(const char* tag, int64_t cl_k, int64_t part, int64_t n_parts) {
+  return (void*)get_model(tag, cl_k, part, n_parts);
+}
+
+int tapes_release_model(const char* tag, int64_t cl_k) {  // the whole problem and every part of it
+  int released = 0;
+  for (auto it = g_models.begin(); it != g_models.end();) {
+    if (std::get<0>(it->first) == tag && std::get<1>(it->first) == (int)cl_k) { it = g_models.erase(it); ++released; }
+    else ++it;
+  }
+  return released ? 0 : 1;
+}
+
+int64_t tapes_rule_parts(const char* tag, int64_t cl_k, int64_t n_parts, int32_t* owner, double* cost) {
+  try {
+    tapes::register_builtin_problems();
+    const tapes::Problem* prob = tapes::find_problem(tag);
+    if (!prob) { fail(std::string("unknown problem tag: ") + tag); return -1; }
+    const tapes::RuleTable t = tapes::enumerate_rules(*prob, (int)cl_k);
+    const std::vector<double> costs = tapes::flux_rule_costs(t);
+    const std::vector<int> owners = tapes::deal_flux_rules(costs, (int)n_parts);
+    for (size_t r = 0; r < costs.size(); ++r) {
+      if (owner) owner[r] = owners[r];
+      if (cost) cost[r] = costs[r];
+    }
+    return (int64_t)costs.size();
+  } catch (const std::exception& ex) {
+    fail(ex.what());
+    return -1;
+  }
 }
 
 int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream) {
@@ -297,6 +330,8 @@ int tapes_sync(void* model) {
 int tapes_model_info(void* model, int64_t* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
   const tapes::Model& m = *(tapes::Model*)model;
+  int64_t chain_levels = 0;
+  for (const tapes::Level& lv : m.levels) chain_levels += lv.chain_uniform ? 1 : 0;
   const int64_t v[] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
                        (int64_t)m.levels.size(), m.launches_per_rhs, m.stats.terms, m.stats.sum_nodes,
                        m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
@@ -305,7 +340,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                        (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
                        (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
                        m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
-                       m.stats.owned_parents, m.stats.deferred_groups};
+                       m.stats.owned_parents, m.stats.deferred_groups, chain_levels, (int64_t)m.chain_kernels,
+                       (int64_t)m.chain_unroll};
   int n = (int)(sizeof(v) / sizeof(v[0]));
   if (n > capacity) n = capacity;
   for (int i = 0; i < n; ++i) out[i] = v[i];
@@ -326,6 +362,15 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {
     m.level_unroll = (int)value;
+    return 0;
+  }
+  if (std::strcmp(key, "chain_kernels") == 0 && (value == 0 || value == 1)) {
+    m.chain_kernels = (int)value;
+    m.launches_per_rhs = tapes::rhs_launch_count(m);
+    return 0;
+  }
+  if (std::strcmp(key, "chain_unroll") == 0 && value >= 1 && value <= 99) {
+    m.chain_unroll = (int)value;
     return 0;
   }
   fail(std::string("unknown option or value: ") + key);

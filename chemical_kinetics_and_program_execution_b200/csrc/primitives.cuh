@@ -82,28 +82,46 @@ __global__ void scan_tile_offsets_kernel(uint64_t* __restrict__ tile_sums, uint6
   if (threadIdx.x == 0) *grand_total = carry;
 }
 
-__global__ void scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
-                                  const uint64_t* __restrict__ tile_offsets,
-                                  uint64_t* __restrict__ out) {
+// Position of item i of a tile in the staging buffer: one pad word per 16 keeps both access
+// patterns below free of bank conflicts (striped: consecutive threads, consecutive words; blocked:
+// thread t touches word 16 * t + j, which lands 17 words after thread t - 1's).
+__device__ __forceinline__ int scan_slot(int i) { return i + (i >> 4); }
+
+__global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
+                                                                  const uint64_t* __restrict__ tile_offsets,
+                                                                  uint64_t* __restrict__ out) {
   __shared__ uint64_t wt[32];
   __shared__ uint64_t total;
+  __shared__ uint64_t stage[kScanTile + kScanTile / 16];
   const uint64_t tile0 = (uint64_t)blockIdx.x * kScanTile;
-  // thread owns kScanItems consecutive items so that the per-thread prefix is sequential
-  const uint64_t first = tile0 + (uint64_t)threadIdx.x * kScanItems;
+  // global memory is touched in striped order (coalesced both ways); the per-thread prefix needs
+  // kScanItems consecutive items per thread, so the tile is transposed through shared memory
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const int local = j * kScanThreads + (int)threadIdx.x;
+    const uint64_t i = tile0 + (uint64_t)local;
+    stage[scan_slot(local)] = i < n ? in[i] : 0u;
+  }
+  __syncthreads();
   uint32_t v[kScanItems];
   uint64_t s = 0;
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
-    uint64_t i = first + j;
-    v[j] = i < n ? in[i] : 0;
+    v[j] = (uint32_t)stage[scan_slot((int)threadIdx.x * kScanItems + j)];
     s += v[j];
   }
   uint64_t ex = block_exclusive_sum(s, wt, &total) + tile_offsets[blockIdx.x];
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
-    uint64_t i = first + j;
-    if (i < n) out[i] = ex;
+    stage[scan_slot((int)threadIdx.x * kScanItems + j)] = ex;
     ex += v[j];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < kScanItems; ++j) {
+    const int local = j * kScanThreads + (int)threadIdx.x;
+    const uint64_t i = tile0 + (uint64_t)local;
+    if (i < n) out[i] = stage[scan_slot(local)];
   }
 }
 

@@ -150,6 +150,65 @@ RuleTable enumerate_rules(const Problem& problem, int cl_k) {
   return table;
 }
 
+std::vector<double> flux_rule_costs(const RuleTable& table) {
+  const int A = table.alphabet, k = table.cl_k;
+  std::vector<double> costs;
+  for (const FluxRule& r : table.rules) {
+    double cost = 0.0;
+    for (int t = 0; t < 2; ++t) {
+      const Seed& sd = r.tape[t];
+      if (!sd.changed()) continue;
+      // changed[pos]: cell pos of the view (0 = left-most) differs between the two views
+      std::vector<char> changed((size_t)sd.length, 0);
+      int first = sd.length, last = -1;
+      uint64_t o = sd.orig, a = sd.adjusted;
+      for (int pos = sd.length - 1; pos >= 0; --pos) {
+        if (o % (uint64_t)A != a % (uint64_t)A) { changed[(size_t)pos] = 1; first = std::min(first, pos); last = std::max(last, pos); }
+        o /= (uint64_t)A; a /= (uint64_t)A;
+      }
+      for (int start = first - k + 1; start <= last; ++start) {
+        bool hit = false;
+        for (int pos = std::max(start, 0); pos < std::min(start + k, sd.length); ++pos) hit = hit || changed[(size_t)pos];
+        if (!hit) continue;
+        const int inside = std::max(0, std::min(start + k, sd.length) - std::max(start, 0));
+        cost += std::pow((double)A, k - inside);
+      }
+    }
+    costs.push_back(cost);
+  }
+  return costs;
+}
+
+std::vector<int> deal_flux_rules(const std::vector<double>& costs, int n_parts) {
+  if (n_parts < 1) throw std::runtime_error("need at least one part");
+  std::vector<size_t> order(costs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return costs[x] > costs[y]; });
+  std::vector<double> load((size_t)n_parts, 0.0);
+  std::vector<int> owner(costs.size(), 0);
+  for (size_t r : order) {
+    int best = 0;
+    for (int g = 1; g < n_parts; ++g)
+      if (load[(size_t)g] < load[(size_t)best]) best = g;
+    owner[r] = best;
+    load[(size_t)best] += costs[r];
+  }
+  return owner;
+}
+
+RuleTable rule_table_part(const RuleTable& table, int part, int n_parts) {
+  if (part < 0 || part >= n_parts) throw std::runtime_error("part outside 0..n_parts-1");
+  const std::vector<int> owner = deal_flux_rules(flux_rule_costs(table), n_parts);
+  RuleTable out;
+  out.alphabet = table.alphabet;
+  out.cl_k = table.cl_k;
+  out.worlds_walked = table.worlds_walked;
+  out.leaf_worlds = table.leaf_worlds;
+  for (size_t r = 0; r < table.rules.size(); ++r)
+    if (owner[r] == part) out.rules.push_back(table.rules[r]);
+  return out;
+}
+
 const Problem* find_problem(const std::string& tag) {
   auto it = registry().find(tag);
   return it == registry().end() ? nullptr : &it->second;

@@ -68,6 +68,16 @@ struct RuleTable {
 // Walks the full (unpruned) world tree of `problem` at correlation length cl_k.
 RuleTable enumerate_rules(const Problem& problem, int cl_k);
 
+// Several GPUs evaluate one problem by dealing its flux rules (the forests of different leaf
+// worlds are independent, and a rule's steps carry everything its probability depends on).
+// flux_rule_costs estimates the flux terms of every rule: one per length-k window overlapping a
+// changed cell and per assignment of the window cells outside the view.  deal_flux_rules is the
+// longest-processing-time assignment (descending cost to the least loaded part, ties to the lower
+// index), the same on every rank.  rule_table_part keeps the rules of one part, in table order.
+std::vector<double> flux_rule_costs(const RuleTable& table);
+std::vector<int> deal_flux_rules(const std::vector<double>& costs, int n_parts);
+RuleTable rule_table_part(const RuleTable& table, int part, int n_parts);
+
 // Problem registry (framework/tapes_py_interface.scm:24-36).
 const Problem* find_problem(const std::string& tag);
 void register_problem(const std::string& tag, int alphabet, Body body);

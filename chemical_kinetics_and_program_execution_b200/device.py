@@ -18,11 +18,18 @@ def _current_stream_handle():
 
 
 class DeviceModel:
-  """The structure of (tag, cl_k) on the current CUDA device."""
+  """The structure of (tag, cl_k) on the current CUDA device.
 
-  def __init__(self, tag, cl_k):
-    self.tag, self.cl_k = tag, cl_k
-    self.handle = markov_tapes.u_lib.tapes_model(tag.encode(), cl_k)
+  part=(rank, world) builds this rank's share only: the flux rules of the problem are dealt to
+  `world` ranks (tapes_model_part), for any registered problem; the sum of the parts' dy/dt is the
+  dy/dt of the whole problem (parallel.PeerExchangeRhs forms it over NVLink)."""
+
+  def __init__(self, tag, cl_k, part=None):
+    self.tag, self.cl_k, self.part = tag, cl_k, part
+    if part is None:
+      self.handle = markov_tapes.u_lib.tapes_model(tag.encode(), cl_k)
+    else:
+      self.handle = markov_tapes.u_lib.tapes_model_part(tag.encode(), cl_k, int(part[0]), int(part[1]))
     _lib.check(bool(self.handle), 'tapes_model')
     self.info = _lib.model_info(self.handle)
     self.timing = _lib.model_timing(self.handle)

@@ -247,20 +247,27 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
   probabilities at `ts` ([len(ts), len(observables)]), computed on the device.  With
   return_states=False only the observables cross the host boundary.
 
-  Several GPUs: `tag` names this rank's share of the rule set (parallel.split_rule_set) and
-  `peer_group` is the parallel.PeerExchangeRhs of its model; every rank calls this function with
-  the same arguments otherwise and gets the same result (right-hand sides are evaluated by all
-  ranks together, everything else is replicated).
+  Several GPUs: `peer_group` is the parallel.PeerExchangeRhs of this rank's share of the problem,
+  a device.DeviceModel(tag, cl_k, part=(rank, world)) - or `tag` names a share of a rule set made
+  with parallel.split_rule_set; every rank calls this function with the same arguments otherwise
+  and gets the same result (right-hand sides are evaluated by all ranks together, everything else
+  is replicated).
   """
   p0 = _checked_p0(p0, size_a, cl_k)
   ts = numpy.asarray(ts, dtype=numpy.float64)
   if ts.ndim != 1 or ts.size < 2 or not ((numpy.diff(ts) > 0).all() or (numpy.diff(ts) < 0).all()):
     raise ValueError('ts must be a strictly monotonic sequence of at least two times')
-  model = u_lib.tapes_model(tag.encode(), cl_k)
-  _lib.check(bool(model), 'tapes_model')
+  part = getattr(peer_group.model, 'part', None) if peer_group is not None else None
+  if part is not None:
+    if (peer_group.model.tag, peer_group.model.cl_k) != (tag, cl_k):
+      raise ValueError('peer_group belongs to a different model')
+    model = peer_group.model.handle
+  else:
+    model = u_lib.tapes_model(tag.encode(), cl_k)
+    _lib.check(bool(model), 'tapes_model')
+    if peer_group is not None and peer_group.model.handle != model:
+      raise ValueError('peer_group belongs to a different model')
   tab = _dop853_tableau()
-  if peer_group is not None and peer_group.model.handle != model:
-    raise ValueError('peer_group belongs to a different model')
   solver = u_lib.tapes_dop853_create_peer(model, peer_group.group if peer_group is not None else None,
                                           tab.ctypes.data, numpy.ascontiguousarray(p0).ctypes.data,
                                           float(ts[0]), float(ts[-1]), float(rtol), float(atol),

@@ -59,7 +59,20 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
 
 /* Builds (or fetches from the cache) the device structure for (tag, cl_k). NULL on failure. */
 void* tapes_model(const char* tag, int64_t cl_k);
+/* Frees the structure of (tag, cl_k) and of every part of it; 1 when there was none. */
 int tapes_release_model(const char* tag, int64_t cl_k);
+
+/* Part `part` of `n_parts` of (tag, cl_k), for ranks that evaluate one problem together: the flux
+ * rules (leaf worlds of the program that modify a tape, framework/tape_multiverse.scm:1416-1443)
+ * are dealt to the parts by estimated term count, and the part's right-hand side is the sum over
+ * its rules only.  The sum of all parts' dy/dt is the dy/dt of the whole problem, which is what
+ * tapes_peer_rhs forms.  Works for every registered problem.  NULL on failure. */
+void* tapes_model_part(const char* tag, int64_t cl_k, int64_t part, int64_t n_parts);
+
+/* Host-only (no GPU needed): the dealing tapes_model_part uses.  owner[r] = part of flux rule r
+ * (order of tapes_rule_table), cost[r] = its estimated number of flux terms; either may be NULL.
+ * Returns the number of flux rules, -1 on failure. */
+int64_t tapes_rule_parts(const char* tag, int64_t cl_k, int64_t n_parts, int32_t* owner, double* cost);
 
 /* dy/dt for DEVICE buffers; asynchronous on `cuda_stream` (a cudaStream_t, NULL = the model's
  * own stream). */
@@ -116,13 +129,16 @@ int tapes_sync(void* model);
  * entries held by columns, column slots incl. padding, minimum lanes of a run, loads in flight per
  * thread of the level kernel, forest levels whose parent lists are not arithmetic progressions,
  * left-parent records of all levels, gathers in flight per lane of the product kernel, right
- * children evaluated by the group they feed, groups whose children are evaluated by the next level.
- * Returns how many were written. */
+ * children evaluated by the group they feed, groups whose children are evaluated by the next level,
+ * pure right-chain levels (evaluated by the lean chain kernels), whether those kernels are in use,
+ * parents in flight per thread in them.  Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
 /* Tuning knobs of a built model: "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row of the plain-CSR
  * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel), "flux_unroll"
- * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
+ * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel), "chain_kernels" (1: pure
+ * right-chain levels use the lean kernels, 0: the general level kernel), "chain_unroll" (1..5 parents
+ * in flight per thread of the lean kernel).  Results are bit-identical for every setting. */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
 /* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing, and

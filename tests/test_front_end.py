@@ -72,6 +72,32 @@ def test_rule_set_problem_matches_oracle(oracle):
   assert sorted(w.tolist()) == sorted(prob[changed].tolist())
 
 
+@pytest.mark.parametrize('tag,size_a,cl_k', TAGS)
+def test_rule_parts_deal_every_rule_once_and_balanced(oracle, tag, size_a, cl_k):
+  """The dealing behind tapes_model_part: the estimated cost of a flux rule is its number of
+  distinct flux terms at full support (checked against the oracle's merged term list), every rule
+  has exactly one owner, and the longest-processing-time bound holds."""
+  p = configs.dirichlet_product_table(size_a, cl_k, 11)
+  n_terms = len(oracle.terms(tag, cl_k, p, mode=oracle.MERGED)[0])
+  n_rules = len(_lib.rule_table(tag, cl_k)['rule_ptr']) - 1
+  for n_parts in (1, 2, 3, 8):
+    owner, cost = _lib.rule_parts(tag, cl_k, n_parts)
+    assert len(owner) == n_rules and cost.sum() == n_terms and (cost > 0).all()
+    assert owner.min() >= 0 and owner.max() < n_parts
+    load = numpy.bincount(owner, weights=cost, minlength=n_parts)
+    assert load.max() <= cost.sum() / n_parts + cost.max()
+    again, _ = _lib.rule_parts(tag, cl_k, n_parts)
+    assert numpy.array_equal(owner, again)  # every rank computes the same dealing
+  assert (_lib.rule_parts(tag, cl_k, 1)[0] == 0).all()
+
+
+def test_rule_parts_errors():
+  with pytest.raises(RuntimeError):
+    _lib.rule_parts('nope', 3, 2)
+  with pytest.raises(RuntimeError):
+    _lib.rule_parts('ex2-ferromagnetic-chain', 3, 0)
+
+
 def test_unknown_tag():
   assert _lib.load().tapes_alphabet_size(b'nope') == -1
   with pytest.raises(RuntimeError):

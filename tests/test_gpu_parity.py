@@ -230,6 +230,38 @@ def test_fused_right_chain_is_bit_identical(mt, device, monkeypatch, tag, size_a
   assert numpy.array_equal(got['0'][0], got['1'][0])
 
 
+@pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex5-msrtf-machine', 5, 5),
+                                             ('ex3-copolymerization', 4, 7), ('ex2-ferromagnetic-chain', 2, 7),
+                                             ('synthetic', 10, 5), ('synthetic', 3, 7), ('synthetic', 17, 4)])
+def test_chain_kernels_are_bit_identical(mt, device, tag, size_a, cl_k):
+  """Pure right-chain levels evaluated by the lean kernels (one thread per prefix group, then one
+  per child) give the bits of the general level kernel, for every batching of the lean kernel."""
+  import torch
+  if tag == 'synthetic':
+    tag = f'chain-test-{size_a}'
+    mt.register_rule_set(tag, size_a, configs.random_rule_set(size_a, 9, seed=6))
+  p = torch.from_numpy(configs.markov_table(size_a, cl_k, 8)).cuda()
+  p[::7] = 0.0  # pruned branches take the same path in both forms
+  model = device.DeviceModel(tag, cl_k)
+  assert model.info['chain_kernels'] == 1
+  if tag.startswith('chain-test') and cl_k >= 5:
+    assert model.info['chain_levels'] >= 2
+  lean = model.rhs(p).cpu().numpy()
+  lean_w = model.node_weights()
+  launches = model.info['launches_per_rhs']
+  model.set_option('chain_kernels', 0)
+  assert model.info['launches_per_rhs'] <= launches
+  general = model.rhs(p).cpu().numpy()
+  assert numpy.array_equal(general, lean)
+  assert numpy.array_equal(model.node_weights(), lean_w)
+  model.set_option('chain_kernels', 1)
+  for unroll in (1, 2, 3, 4, 5, 81, 82, 52, 53, 54, 45):
+    model.set_option('chain_unroll', unroll)
+    assert numpy.array_equal(model.rhs(p).cpu().numpy(), lean), unroll
+    assert numpy.array_equal(model.node_weights(), lean_w), unroll
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+
+
 def test_long_rows(mt, device, oracle):
   """States with more than 128 flux entries (many rules on a small alphabet): runs are only
   tracked for the first 128 entries of a row, the rest goes to columns; term set and dy/dt must
@@ -270,6 +302,41 @@ def test_explicit_parent_lists_are_bit_identical(mt, device, monkeypatch):
   assert got[True][2]['owned_parents'] == 0
   assert numpy.array_equal(got[False][1], got[True][1])
   assert numpy.array_equal(got[False][0], got[True][0])
+
+
+@pytest.mark.parametrize('tag,size_a,cl_k,n_parts', [('ex4-chemical-turing', 9, 4, 3),
+                                                     ('ex5-msrtf-machine', 5, 5, 8),
+                                                     ('ex3-copolymerization', 4, 6, 5),
+                                                     ('ex1-radioactive-decay', 2, 4, 2)])
+def test_model_parts_sum_to_the_whole(mt, device, oracle, tag, size_a, cl_k, n_parts):
+  """The shares of a problem that ranks evaluate together (tapes_model_part; any registered problem,
+  flux rules dealt by cost): every flux term lands in exactly one part, with the bits it has in
+  the whole problem, and the parts' dy/dt add up to the whole (here all parts on one GPU)."""
+  import torch
+  p = configs.markov_table(size_a, cl_k, 23)
+  d_p = torch.from_numpy(p).cuda()
+  whole = device.DeviceModel(tag, cl_k)
+  want = whole.rhs(d_p).cpu().numpy()
+  torch.cuda.synchronize()
+  wsrc, wdst, ww = whole.terms()
+  total = numpy.zeros_like(want)
+  got_terms = []
+  n_rules = 0
+  for part in range(n_parts):
+    share = device.DeviceModel(tag, cl_k, part=(part, n_parts))
+    assert share.handle != whole.handle
+    total += share.rhs(d_p).cpu().numpy()
+    torch.cuda.synchronize()
+    got_terms.append(share.terms())
+    n_rules += share.info['n_flux_rules']
+  assert n_rules == whole.info['n_flux_rules']
+  if tag == 'ex1-radioactive-decay':
+    assert got_terms[1][0].size == 0  # more parts than rules: an empty share is a valid model
+  src, dst, w = (numpy.concatenate([t[i] for t in got_terms]) for i in range(3))
+  key = lambda s, d, x: sorted(zip(s.tolist(), d.tolist(), x.tolist()))
+  assert key(src, dst, w) == key(wsrc, wdst, ww)  # same terms, same weights, bit for bit
+  assert_rhs_close(total, want, gross_flux(oracle, tag, cl_k, p))
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
 
 
 def test_peer_exchange_with_one_rank(mt, device):
