@@ -330,8 +330,6 @@ int tapes_sync(void* model) {
 int tapes_model_info(void* model, int64_t* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
   const tapes::Model& m = *(tapes::Model*)model;
-  int64_t chain_levels = 0;
-  for (const tapes::Level& lv : m.levels) chain_levels += lv.chain_uniform ? 1 : 0;
   const int64_t v[] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
                        (int64_t)m.levels.size(), m.launches_per_rhs, m.stats.terms, m.stats.sum_nodes,
                        m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
@@ -340,8 +338,7 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                        (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
                        (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
                        m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
-                       m.stats.owned_parents, m.stats.deferred_groups, chain_levels, (int64_t)m.chain_kernels,
-                       (int64_t)m.chain_unroll};
+                       m.stats.owned_parents, m.stats.deferred_groups};
   int n = (int)(sizeof(v) / sizeof(v[0]));
   if (n > capacity) n = capacity;
   for (int i = 0; i < n; ++i) out[i] = v[i];
@@ -362,15 +359,6 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
   }
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {
     m.level_unroll = (int)value;
-    return 0;
-  }
-  if (std::strcmp(key, "chain_kernels") == 0 && (value == 0 || value == 1)) {
-    m.chain_kernels = (int)value;
-    m.launches_per_rhs = tapes::rhs_launch_count(m);
-    return 0;
-  }
-  if (std::strcmp(key, "chain_unroll") == 0 && value >= 1 && value <= 99) {
-    m.chain_unroll = (int)value;
     return 0;
   }
   fail(std::string("unknown option or value: ") + key);

@@ -623,86 +623,6 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
   }
 }
 
-// Lean form of a pure right-chain level (Level::chain_uniform): one thread per prefix group.  The
-// A parents of group g are the right children x_prev of the previous level's groups g_prev,
-// g_prev + g_step, ... (one per value j of the dropped digit), so parent j reads
-// p[j * A^(k-1) + prefix] and marg_{k-1}[j * A^(k-2) + prefix / A]; the thread evaluates them from
-// those groups' sums (tm.scm:1310-1318 for the previous shift), stores them at their nodes and
-// leaves their sum, added in ascending j, in g_total.  Same operations in the same order as
-// own_parents<., true>; the point is the register budget: the general kernel carries the left-parent
-// and the cooperative child-writing paths too and runs 5 blocks per SM, this one 8.
-template <int UO, int MIN_BLOCKS>
-__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) chain_parents_kernel(
-    const double* __restrict__ p, const double* __restrict__ short_table, const uint32_t* __restrict__ g_first,
-    const uint32_t* __restrict__ g_stride, const uint32_t* __restrict__ g_prefix,
-    const double* __restrict__ prev_total, double* __restrict__ g_total, double* __restrict__ ww,
-    uint32_t n_groups, uint32_t A, uint32_t M, uint32_t prev_right_base) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
-  const uint32_t first = g_first[g], stride = g_stride[g], mine = g_prefix[g];
-  const uint32_t rel = first - prev_right_base;
-  const uint32_t g_prev = rel / A, g_step = stride / A;
-  const uint32_t mine_short = mine / A, short_step = M / A;
-  double total = 0.0;
-  for (uint32_t e = 0; e < A; e += UO) {
-    double sum_prev[UO], p_long[UO], p_marg[UO];
-#pragma unroll
-    for (int u = 0; u < UO; ++u) {
-      const bool live = e + u < A;  // indices below stay under A^k < 2^32 and n_nodes < 2^31
-      sum_prev[u] = live ? prev_total[g_prev + (e + u) * g_step] : 0.0;
-      p_long[u] = live ? p[(e + u) * M + mine] : 0.0;
-      p_marg[u] = live ? short_table[(e + u) * short_step + mine_short] : 0.0;
-    }
-#pragma unroll
-    for (int u = 0; u < UO; ++u) {
-      const bool live = e + u < A;
-      const double v = live ? child_weight(sum_prev[u], p_long[u], p_marg[u]) : 0.0;
-      if (live) ww[first + (e + u) * stride] = v;
-      total += v;
-    }
-  }
-  g_total[g] = total;
-}
-
-// The right children of the groups of a pure right-chain level that no later level takes over
-// (tm.scm:1310-1322), one child per thread slot, kChildBatch slots per thread.
-constexpr int kChildBatch = 4;
-__global__ void __launch_bounds__(kThreads, 6) chain_children_kernel(
-    const double* __restrict__ p, const double* __restrict__ short_table, const uint32_t* __restrict__ g_prefix,
-    const uint32_t* __restrict__ g_count, const double* __restrict__ g_total, double* __restrict__ out,
-    uint64_t n_children, uint32_t A) {
-  const uint64_t i0 = (uint64_t)blockIdx.x * (kThreads * kChildBatch) + threadIdx.x;
-  double total[kChildBatch], p_long[kChildBatch], p_short[kChildBatch];
-  bool live[kChildBatch];
-#pragma unroll
-  for (int u = 0; u < kChildBatch; ++u) {
-    const uint64_t i = i0 + (uint64_t)u * kThreads;
-    const uint32_t g = (uint32_t)(i / A), x = (uint32_t)(i - (uint64_t)g * A);
-    live[u] = i < n_children && !(g_count[g] & Level::kChildrenDeferred);
-    const uint32_t prefix = live[u] ? g_prefix[g] : 0u;
-    total[u] = live[u] ? g_total[g] : 0.0;
-    p_long[u] = live[u] ? p[prefix * A + x] : 0.0;  // index below A^k < 2^32
-    p_short[u] = live[u] ? short_table[prefix] : 0.0;
-  }
-#pragma unroll
-  for (int u = 0; u < kChildBatch; ++u)
-    if (live[u]) out[i0 + (uint64_t)u * kThreads] = child_weight(total[u], p_long[u], p_short[u]);
-}
-
-// [0] groups with kOwnsParents and kAllDigits, [1] groups with kChildrenDeferred
-__global__ void count_group_flags_kernel(const uint32_t* __restrict__ g_count, uint64_t n_groups,
-                                         unsigned long long* __restrict__ out) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint32_t both = Level::kOwnsParents | Level::kAllDigits;
-  const uint32_t c = g < n_groups ? g_count[g] : 0u;
-  const unsigned direct = __ballot_sync(0xffffffffu, (c & both) == both);
-  const unsigned deferred = __ballot_sync(0xffffffffu, (c & Level::kChildrenDeferred) != 0);
-  if ((threadIdx.x & 31) == 0) {
-    if (direct) atomicAdd(&out[0], (unsigned long long)__popc(direct));
-    if (deferred) atomicAdd(&out[1], (unsigned long long)__popc(deferred));
-  }
-}
-
 // dy/dt[row] = sum over the row's entries of +-w[node].  G lanes share a row; every lane keeps
 // kSpmvUnroll independent entry loads and weight gathers in flight, then the lanes of a row are
 // combined by a shuffle reduction.  The summation order is fixed by (G, unroll), so results are
@@ -1148,23 +1068,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (cur_slab.capacity + s1.capacity + s2.capacity > ((size_t)1 << 30)) {
     cur_slab.release(); s1.release(); s2.release();
   }
-  // pure right-chain levels get the lean kernels (Level::chain_uniform)
-  {
-    unsigned long long* flag_counts = dalloc<unsigned long long>(2, st);
-    for (Level& lv : m.levels) {
-      if (!lv.g_count || lv.n_groups == 0) continue;
-      TAPES_CUDA_CHECK(cudaMemsetAsync(flag_counts, 0, 16, st));
-      count_group_flags_kernel<<<grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads), kThreads, 0, st>>>(
-          lv.g_count, lv.n_groups, flag_counts);
-      unsigned long long h[2] = {0, 0};
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(h, flag_counts, 16, cudaMemcpyDeviceToHost, st));
-      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      lv.n_deferred = (uint32_t)h[1];
-      lv.chain_uniform = lv.n_left == 0 && lv.n_roots == 0 && h[0] == lv.n_groups && lv.prev_total != nullptr;
-      if (lv.chain_uniform && !lv.g_total) lv.g_total = dkeep<double>(m, lv.n_groups);
-    }
-    dfree(flag_counts, st);
-  }
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
   m.stats.nodes = (int64_t)m.n_nodes;
   m.stats.terms = (int64_t)total_terms;
@@ -1207,8 +1110,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.level_unroll = m.A <= 2 ? 2 : ((m.A + 4) / 5 * 5 - m.A <= (m.A + 3) / 4 * 4 - m.A ? 5 : 4);
   if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
   if (const char* g = std::getenv("TAPES_FLUX_UNROLL")) m.flux_unroll = std::atoi(g);
-  if (const char* g = std::getenv("TAPES_CHAIN_KERNELS")) m.chain_kernels = std::atoi(g) != 0;
-  if (const char* g = std::getenv("TAPES_CHAIN_UNROLL")) m.chain_unroll = std::max(1, std::atoi(g));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
 
@@ -1268,34 +1169,6 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   for (const Level& lv : m.levels) {
     if (lv.n_roots) {
       root_kernel<<<grid_for(lv.n_roots, kThreads), kThreads, 0, st>>>(lv.root_rule, lv.n_roots, m.rule_w, m.node_w);
-    } else if (m.chain_kernels && lv.chain_uniform) {
-      const double* short_table = m.marg + m.marg_off[m.k - 1];
-      const unsigned grid = grid_for(lv.n_groups, kThreads);
-#define TAPES_CHAIN(UO_, B_)                                                                                  \
-  chain_parents_kernel<UO_, B_><<<grid, kThreads, 0, st>>>(d_p, short_table, lv.g_first, lv.g_stride, lv.g_prefix, \
-                                                           lv.prev_total, lv.g_total, m.node_w, lv.n_groups, c.A, \
-                                                           c.M, (uint32_t)lv.prev_right_base)
-      // chain_unroll = 10 * blocks per SM + parents in flight (plain 1..5: 6 blocks per SM)
-      switch (m.chain_unroll) {
-        case 81: TAPES_CHAIN(1, 8); break;
-        case 82: TAPES_CHAIN(2, 8); break;
-        case 61: case 1: TAPES_CHAIN(1, 6); break;
-        case 62: case 2: TAPES_CHAIN(2, 6); break;
-        case 63: case 3: TAPES_CHAIN(3, 6); break;
-        case 64: case 4: TAPES_CHAIN(4, 6); break;
-        case 52: TAPES_CHAIN(2, 5); break;
-        case 53: TAPES_CHAIN(3, 5); break;
-        case 54: TAPES_CHAIN(4, 5); break;
-        case 55: case 5: TAPES_CHAIN(5, 5); break;
-        case 45: TAPES_CHAIN(5, 4); break;
-        default: TAPES_CHAIN(2, 6); break;
-      }
-#undef TAPES_CHAIN
-      if (lv.n_deferred < lv.n_groups) {
-        const uint64_t n_children = (uint64_t)lv.n_groups * c.A;
-        chain_children_kernel<<<grid_for(n_children, kThreads * kChildBatch), kThreads, 0, st>>>(
-            d_p, short_table, lv.g_prefix, lv.g_count, lv.g_total, m.node_w + lv.base, n_children, c.A);
-      }
     } else if (lv.n_left + lv.n_groups) {
       const unsigned left_blocks = lv.n_left ? grid_for(lv.n_left, kThreads) : 0;
       const unsigned group_blocks = lv.n_groups ? grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads) : 0;
@@ -1306,6 +1179,9 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       // (each needs three loads).  Measured at n = 1e8, A = 10 (profiles/r01_g_sweep_fused_right_chain.log):
       // (U, UO) = (5, 3) 5.42 ms, (5, 2) 5.47, (4, 2) 5.66, (2, 2) 5.83, (5, 5) 6.20 (spills), 64 registers
       // at 4 blocks per SM 5.63-5.94; 40 registers at 6 blocks per SM (120 B of spills) 5.37-5.55: no gain.
+      // Separate lean kernels for the pure right-chain levels (one thread per group, 32-62 registers, 4-8
+      // blocks per SM, then one thread per child) measured 5.59-6.35 ms against 5.51 for this kernel
+      // (profiles/r01_m_sweep_lean_chain_kernels.log): the deep levels are not bound by registers.
 #define TAPES_LEVEL(U_, UO_, B_)                                                                             \
   (prog ? level_kernel<U_, UO_, true, B_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
         : level_kernel<U_, 1, false, 5><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
@@ -1366,10 +1242,8 @@ int64_t rhs_launch_count(const Model& m) {
   launches += (m.k - 1 - top);          // one kernel per long marginal table
   if (top >= 0) launches += 1;          // tail tables
   if (m.n_rules) launches += 1;         // leaf-world probabilities
-  for (const Level& lv : m.levels) {
+  for (const Level& lv : m.levels)
     if (lv.n_roots || lv.n_left + lv.n_groups) launches += 1;
-    if (!lv.n_roots && m.chain_kernels && lv.chain_uniform && lv.n_deferred < lv.n_groups) launches += 1;
-  }
   launches += 1;                        // S * w
   return launches;
 }

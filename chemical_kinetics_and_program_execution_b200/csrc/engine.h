@@ -61,13 +61,6 @@ struct Level {
   uint64_t prev_right_base = 0;         // node id of the previous level's first right child
   const uint32_t* prev_prefix = nullptr;  // previous level's g_prefix
   const double* prev_total = nullptr;     // previous level's g_total
-  // Pure right-chain level (found by the last pass of the build): no left parents, and every group
-  // owns its parents with kAllDigits.  Such levels - the deep half of a forest - are evaluated by
-  // two lean kernels instead of the general one (engine.cu chain_parents_kernel,
-  // chain_children_kernel): fewer registers, more warps in flight.  g_total then exists for every
-  // group of the level, deferred or not.
-  bool chain_uniform = false;
-  uint32_t n_deferred = 0;  // groups with kChildrenDeferred
 };
 
 // The flux structure cut into slices of 32 consecutive states, one warp lane per state.  Consecutive
@@ -152,8 +145,6 @@ struct Model {
   int flux_format = 1;             // 1 = slices, 0 = plain CSR
   int level_unroll = 4;            // loads in flight per thread in level_kernel
   int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
-  int chain_kernels = 1;           // 0: pure right-chain levels go through the general level kernel too
-  int chain_unroll = 2;            // parents in flight per thread in chain_parents_kernel
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;

@@ -129,16 +129,13 @@ int tapes_sync(void* model);
  * entries held by columns, column slots incl. padding, minimum lanes of a run, loads in flight per
  * thread of the level kernel, forest levels whose parent lists are not arithmetic progressions,
  * left-parent records of all levels, gathers in flight per lane of the product kernel, right
- * children evaluated by the group they feed, groups whose children are evaluated by the next level,
- * pure right-chain levels (evaluated by the lean chain kernels), whether those kernels are in use,
- * parents in flight per thread in them.  Returns how many were written. */
+ * children evaluated by the group they feed, groups whose children are evaluated by the next level.
+ * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
 /* Tuning knobs of a built model: "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row of the plain-CSR
  * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel), "flux_unroll"
- * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel), "chain_kernels" (1: pure
- * right-chain levels use the lean kernels, 0: the general level kernel), "chain_unroll" (1..5 parents
- * in flight per thread of the lean kernel).  Results are bit-identical for every setting. */
+ * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
 /* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing, and

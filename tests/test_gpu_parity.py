@@ -230,38 +230,6 @@ def test_fused_right_chain_is_bit_identical(mt, device, monkeypatch, tag, size_a
   assert numpy.array_equal(got['0'][0], got['1'][0])
 
 
-@pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex5-msrtf-machine', 5, 5),
-                                             ('ex3-copolymerization', 4, 7), ('ex2-ferromagnetic-chain', 2, 7),
-                                             ('synthetic', 10, 5), ('synthetic', 3, 7), ('synthetic', 17, 4)])
-def test_chain_kernels_are_bit_identical(mt, device, tag, size_a, cl_k):
-  """Pure right-chain levels evaluated by the lean kernels (one thread per prefix group, then one
-  per child) give the bits of the general level kernel, for every batching of the lean kernel."""
-  import torch
-  if tag == 'synthetic':
-    tag = f'chain-test-{size_a}'
-    mt.register_rule_set(tag, size_a, configs.random_rule_set(size_a, 9, seed=6))
-  p = torch.from_numpy(configs.markov_table(size_a, cl_k, 8)).cuda()
-  p[::7] = 0.0  # pruned branches take the same path in both forms
-  model = device.DeviceModel(tag, cl_k)
-  assert model.info['chain_kernels'] == 1
-  if tag.startswith('chain-test') and cl_k >= 5:
-    assert model.info['chain_levels'] >= 2
-  lean = model.rhs(p).cpu().numpy()
-  lean_w = model.node_weights()
-  launches = model.info['launches_per_rhs']
-  model.set_option('chain_kernels', 0)
-  assert model.info['launches_per_rhs'] <= launches
-  general = model.rhs(p).cpu().numpy()
-  assert numpy.array_equal(general, lean)
-  assert numpy.array_equal(model.node_weights(), lean_w)
-  model.set_option('chain_kernels', 1)
-  for unroll in (1, 2, 3, 4, 5, 81, 82, 52, 53, 54, 45):
-    model.set_option('chain_unroll', unroll)
-    assert numpy.array_equal(model.rhs(p).cpu().numpy(), lean), unroll
-    assert numpy.array_equal(model.node_weights(), lean_w), unroll
-  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
-
-
 def test_long_rows(mt, device, oracle):
   """States with more than 128 flux entries (many rules on a small alphabet): runs are only
   tracked for the first 128 entries of a row, the rest goes to columns; term set and dy/dt must
