@@ -427,13 +427,17 @@ def run_b200(args):
   # whole-job structural size
   sizes = torch.tensor([info['nnz'], info['n_nodes'], info['n_terms'], info['launches_per_rhs'],
                         info['n_nodes'] + info['worlds_walked']], dtype=torch.float64, device=device)
-  expand_s = torch.tensor([(timing['device_expand_ms'] + timing['host_enumerate_ms']) * 1e-3],
+  # expansion time with and without the part spent inside cudaMalloc / cudaFree: mapping ~50 GB of
+  # fresh device memory costs 0.04-1.4 s depending on the state the box's driver is in (same build,
+  # same binary: profiles/r01_n_build_cold_vs_warm.log), which says nothing about the expansion kernels
+  expand_s = torch.tensor([(timing['device_expand_ms'] + timing['host_enumerate_ms']) * 1e-3,
+                           (timing['device_expand_ms'] - timing['expand_alloc_ms'] + timing['host_enumerate_ms']) * 1e-3],
                           dtype=torch.float64, device=device)
   if world > 1:
     dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
     dist.all_reduce(expand_s, op=dist.ReduceOp.MAX)  # the ranks expand their rules concurrently
   nnz_total, nodes_total, terms_total, launches_total, expanded_total = [float(x) for x in sizes.tolist()]
-  expand_s = float(expand_s.item())
+  expand_s, expand_kernels_s = [float(x) for x in expand_s.tolist()]
   job_bytes = 28.0 * nnz_total + world * (24.0 * n + 8.0 * n * (1.0 + 2.0 / max(args.size_a - 1, 1)))
   value = job_bytes / (ms_step * 1e-3) / 1e9
 
@@ -520,7 +524,11 @@ def run_b200(args):
                               + (4 * max(args.chunks, 1) + 1 if world > 1 and args.exchange == 'peer' else 0)) * args.steps,
                 roofline=roofline, roofline_levels=roofline_levels, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
                 exchange_exposed_ms=(ms_step - max(rank_ms)) if rank_ms else None,
-                states_expanded_per_s=expanded_total / max(expand_s, 1e-9),
+                states_expanded_per_s=expanded_total / max(expand_kernels_s, 1e-9),
+                states_expanded_per_s_incl_driver_alloc=expanded_total / max(expand_s, 1e-9),
+                states_expanded_note=('forest nodes + program worlds of all ranks / (host enumeration + device expansion) of '
+                                      'the slowest rank; the first figure leaves out the time inside cudaMalloc / cudaFree '
+                                      '(build.expand_alloc_ms), the second includes it'),
                 build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],
                            flux_slices={k: info.get(k) for k in ('n_slices', 'slice_words', 'runs', 'run_entries',
