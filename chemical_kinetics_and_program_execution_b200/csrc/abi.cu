@@ -2,6 +2,8 @@
 // reference's ctypes layer binds (framework/markov_tapes.py:40-56).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -77,7 +79,19 @@ tapes::Model* get_model(const char* tag, int64_t cl_k, int64_t part = 0, int64_t
     tapes::RuleTable table = tapes::enumerate_rules(*prob, (int)cl_k);
     if (n_parts > 1) table = tapes::rule_table_part(table, (int)part, (int)n_parts);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    std::unique_ptr<tapes::Model> m = tapes::build_model(table, nullptr);
+    // node ids have 31 bits: a forest beyond about 10^9 flux terms is built as several structures
+    // over disjoint shares of the rules, evaluated one after the other (engine.h Model::more)
+    double limit = 1.0e9, total = 0.0;
+    if (const char* e = std::getenv("TAPES_MAX_PART_TERMS")) limit = std::max(1.0, std::atof(e));
+    for (double c : tapes::flux_rule_costs(table)) total += c;
+    const int pieces = (int)std::min<double>(std::ceil(total / limit), (double)std::max<size_t>(table.rules.size(), 1));
+    std::unique_ptr<tapes::Model> m;
+    if (pieces <= 1) {
+      m = tapes::build_model(table, nullptr);
+    } else {
+      m = tapes::build_model(tapes::rule_table_part(table, 0, pieces), nullptr);
+      for (int i = 1; i < pieces; ++i) m->more.push_back(tapes::build_model(tapes::rule_table_part(table, i, pieces), m->stream));
+    }
     m->stats.host_enumerate_ms = ms;
     tapes::Model* raw = m.get();
     g_models[key] = std::move(m);
@@ -329,36 +343,49 @@ int tapes_sync(void* model) {
 
 int tapes_model_info(void* model, int64_t* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
-  const tapes::Model& m = *(tapes::Model*)model;
-  const int64_t v[] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
-                       (int64_t)m.levels.size(), m.launches_per_rhs, m.stats.terms, m.stats.sum_nodes,
-                       m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
-                       m.stats.hash_unique, (int64_t)m.A, (int64_t)m.k, (int64_t)m.spmv_group,
-                       (int64_t)m.flux_format, (int64_t)m.slices.n_slices, (int64_t)m.slices.n_words,
-                       (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
-                       (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
-                       m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
-                       m.stats.owned_parents, m.stats.deferred_groups};
-  int n = (int)(sizeof(v) / sizeof(v[0]));
+  const tapes::Model& head = *(tapes::Model*)model;
+  const int kFields = 31;
+  // sizes add up over the parts of a composite model; facts shared by all parts come from the first
+  static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
+                                     true, false, false, false, false, false, true, true, true, true,
+                                     true, false, false, true, true, false, true, true, true};
+  int64_t total[kFields] = {};
+  for (size_t part = 0; part <= head.more.size(); ++part) {
+    const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
+    const int64_t v[kFields] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
+                                (int64_t)m.levels.size(), 0, m.stats.terms, m.stats.sum_nodes,
+                                m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
+                                m.stats.hash_unique, (int64_t)m.A, (int64_t)m.k, (int64_t)m.spmv_group,
+                                (int64_t)m.flux_format, (int64_t)m.slices.n_slices, (int64_t)m.slices.n_words,
+                                (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
+                                (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
+                                m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
+                                m.stats.owned_parents, m.stats.deferred_groups, 1};
+    for (int i = 0; i < kFields; ++i) {
+      if (part == 0) total[i] = v[i];
+      else if (adds[i]) total[i] += v[i];
+    }
+    if (v[4] > total[4]) total[4] = v[4];  // forest levels: the deepest part
+  }
+  total[5] = tapes::rhs_launch_count(head);  // kernel launches of one right-hand side, all parts
+  int n = kFields;
   if (n > capacity) n = capacity;
-  for (int i = 0; i < n; ++i) out[i] = v[i];
+  for (int i = 0; i < n; ++i) out[i] = total[i];
   return n;
 }
 
 int tapes_model_set(void* model, const char* key, int64_t value) {
   if (!model) { fail("null model"); return 1; }
-  tapes::Model& m = *(tapes::Model*)model;
-  if (std::strcmp(key, "spmv_lanes") == 0 &&
-      (value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
-    m.spmv_group = (int)value;
-    return 0;
-  }
-  if (std::strcmp(key, "flux_unroll") == 0 && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8)) {
-    m.flux_unroll = (int)value;
-    return 0;
-  }
-  if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) {
-    m.level_unroll = (int)value;
+  tapes::Model& head = *(tapes::Model*)model;
+  int tapes::Model::*field = nullptr;
+  if (std::strcmp(key, "spmv_lanes") == 0 && (value == 1 || value == 2 || value == 4 || value == 8 || value == 16))
+    field = &tapes::Model::spmv_group;
+  if (std::strcmp(key, "flux_unroll") == 0 && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8))
+    field = &tapes::Model::flux_unroll;
+  if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) field = &tapes::Model::level_unroll;
+  if (field) {
+    head.*field = (int)value;
+    for (auto& part : head.more) (*part).*field = (int)value;
     return 0;
   }
   fail(std::string("unknown option or value: ") + key);
@@ -367,9 +394,13 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
 
 int tapes_model_timing(void* model, double* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
-  const tapes::Model& m = *(tapes::Model*)model;
-  const double v[] = {m.stats.host_enumerate_ms, m.stats.device_expand_ms, m.stats.device_csr_ms,
-                      m.stats.device_slices_ms, m.stats.expand_alloc_ms};
+  const tapes::Model& head = *(tapes::Model*)model;
+  double v[5] = {0, 0, 0, 0, 0};
+  for (size_t part = 0; part <= head.more.size(); ++part) {  // the parts of a composite model are built in turn
+    const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
+    v[0] += m.stats.host_enumerate_ms; v[1] += m.stats.device_expand_ms; v[2] += m.stats.device_csr_ms;
+    v[3] += m.stats.device_slices_ms; v[4] += m.stats.expand_alloc_ms;
+  }
   int n = 5 > capacity ? capacity : 5;
   for (int i = 0; i < n; ++i) out[i] = v[i];
   return n;
@@ -378,6 +409,7 @@ int tapes_model_timing(void* model, double* out, int capacity) {
 int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
   if (!model) { fail("null model"); return 1; }
   tapes::Model& m = *(tapes::Model*)model;
+  if (!m.more.empty()) { fail("export_csr: composite model (forest above the 31-bit node ids); export shares made with tapes_model_part instead"); return 1; }
   cudaStreamSynchronize(m.stream);
   uint32_t* d_entries = m.entries;
   uint32_t* rebuilt = nullptr;
@@ -403,6 +435,7 @@ int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
 int tapes_export_node_weights(void* model, double* weights) {
   if (!model) { fail("null model"); return 1; }
   tapes::Model& m = *(tapes::Model*)model;
+  if (!m.more.empty()) { fail("export_node_weights: composite model; export shares made with tapes_model_part instead"); return 1; }
   cudaStreamSynchronize(m.stream);
   if (m.n_nodes && cudaMemcpy(weights, m.node_w, m.n_nodes * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
     fail("export_node_weights: copy failed");

@@ -633,7 +633,7 @@ template <int G, bool FUSED>
 __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ row_ptr,
                                                    const uint32_t* __restrict__ entries,
                                                    const double* __restrict__ w, double* __restrict__ out,
-                                                   uint64_t n_rows, StageUpdate up) {
+                                                   uint64_t n_rows, StageUpdate up, int accumulate) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t row = t / G;
   const int sub = (int)(t % G);
@@ -659,6 +659,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ 
     for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
   }
   if (sub == 0 && row < n_rows) {
+    if (accumulate) acc = out[row] + acc;  // a later part of a composite model
     out[row] = acc;
     if (FUSED) {  // Runge-Kutta stage update for this state (same term order as the unfused kernel)
       double a = 0.0;
@@ -718,6 +719,7 @@ void DeviceArena::release() {
 }
 
 Model::~Model() {
+  more.clear();  // the other parts of a composite model use this model's stream: they go first
   cudaStream_t st = stream;
   if (st) cudaStreamSynchronize(st);
   if (entries) cudaFree(entries);
@@ -1198,10 +1200,10 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
 
 template <bool FUSED>
 void launch_flux_impl(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
-                      const StageUpdate& up0) {
+                      const StageUpdate& up0, bool accumulate) {
   if (row_hi <= row_lo) return;
   if (m.flux_format == 1) {
-    launch_flux_slices(m, d_out, row_lo, row_hi, st, FUSED ? &up0 : nullptr);
+    launch_flux_slices(m, d_out, row_lo, row_hi, st, FUSED ? &up0 : nullptr, accumulate);
     return;
   }
   const uint64_t rows = row_hi - row_lo;
@@ -1215,24 +1217,33 @@ void launch_flux_impl(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi,
     up.stage += row_lo;
   }
   const unsigned grid = grid_for(threads, kThreads);
+  const int acc = accumulate ? 1 : 0;
   switch (m.spmv_group) {
-    case 1: spmv_kernel<1, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
-    case 2: spmv_kernel<2, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
-    case 4: spmv_kernel<4, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
-    case 8: spmv_kernel<8, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
-    default: spmv_kernel<16, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up); break;
+    case 1: spmv_kernel<1, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
+    case 2: spmv_kernel<2, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
+    case 4: spmv_kernel<4, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
+    case 8: spmv_kernel<8, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
+    default: spmv_kernel<16, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 
-void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st) {
-  launch_flux_impl<false>(m, d_out, row_lo, row_hi, st, StageUpdate());
+// The product of every part of a (possibly composite) model for a range of states: the first part
+// writes, the others add to it in order.  `up` (may be null) rides on the last part's kernel, which
+// is the one that sees the complete dy/dt.
+void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
+                 const StageUpdate* up = nullptr) {
+  const size_t parts = 1 + m.more.size();
+  for (size_t i = 0; i < parts; ++i) {
+    Model& part = i == 0 ? m : *m.more[i - 1];
+    if (up && i + 1 == parts) launch_flux_impl<true>(part, d_out, row_lo, row_hi, st, *up, i > 0);
+    else launch_flux_impl<false>(part, d_out, row_lo, row_hi, st, StageUpdate(), i > 0);
+  }
 }
 
-void rhs_launch(Model& m, const double* d_p, double* d_out, cudaStream_t st, cudaEvent_t* ev) {
-  launch_weights(m, d_p, st, ev);
-  if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
-  launch_flux(m, d_out, 0, m.n_states, st);
+void launch_all_weights(Model& m, const double* d_p, cudaStream_t st) {
+  launch_weights(m, d_p, st, nullptr);
+  for (auto& part : m.more) launch_weights(*part, d_p, st, nullptr);
 }
 }  // namespace
 
@@ -1245,21 +1256,24 @@ int64_t rhs_launch_count(const Model& m) {
   for (const Level& lv : m.levels)
     if (lv.n_roots || lv.n_left + lv.n_groups) launches += 1;
   launches += 1;                        // S * w
+  for (const auto& part : m.more) launches += rhs_launch_count(*part);
   return launches;
 }
 
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
-  rhs_launch(m, d_p, d_out, stream ? stream : m.stream, nullptr);
+  cudaStream_t st = stream ? stream : m.stream;
+  launch_all_weights(m, d_p, st);
+  launch_flux(m, d_out, 0, m.n_states, st);
 }
 
 void rhs_device_fused(Model& m, const double* d_p, double* d_out, const StageUpdate& up, cudaStream_t stream) {
   cudaStream_t st = stream ? stream : m.stream;
-  launch_weights(m, d_p, st, nullptr);
-  launch_flux_impl<true>(m, d_out, 0, m.n_states, st, up);
+  launch_all_weights(m, d_p, st);
+  launch_flux(m, d_out, 0, m.n_states, st, &up);
 }
 
 void weights_device(Model& m, const double* d_p, cudaStream_t stream) {
-  launch_weights(m, d_p, stream ? stream : m.stream, nullptr);
+  launch_all_weights(m, d_p, stream ? stream : m.stream);
 }
 
 void flux_rows_device(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t stream) {
@@ -1271,11 +1285,22 @@ void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_
   cudaStream_t st = stream ? stream : m.stream;
   cudaEvent_t ev[4];
   for (int i = 0; i < 4; ++i) TAPES_CUDA_CHECK(cudaEventCreate(&ev[i]));
-  TAPES_CUDA_CHECK(cudaEventRecord(ev[0], st));
-  rhs_launch(m, d_p, d_out, st, ev);
-  TAPES_CUDA_CHECK(cudaEventRecord(ev[3], st));
-  TAPES_CUDA_CHECK(cudaEventSynchronize(ev[3]));
-  for (int i = 0; i < 3; ++i) TAPES_CUDA_CHECK(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+  ms[0] = ms[1] = ms[2] = 0.0f;
+  const size_t parts = 1 + m.more.size();
+  for (size_t i = 0; i < parts; ++i) {  // part by part, so that the phases can be told apart
+    Model& part = i == 0 ? m : *m.more[i - 1];
+    TAPES_CUDA_CHECK(cudaEventRecord(ev[0], st));
+    launch_weights(part, d_p, st, ev);
+    TAPES_CUDA_CHECK(cudaEventRecord(ev[2], st));
+    launch_flux_impl<false>(part, d_out, 0, part.n_states, st, StageUpdate(), i > 0);
+    TAPES_CUDA_CHECK(cudaEventRecord(ev[3], st));
+    TAPES_CUDA_CHECK(cudaEventSynchronize(ev[3]));
+    for (int j = 0; j < 3; ++j) {
+      float t = 0.0f;
+      TAPES_CUDA_CHECK(cudaEventElapsedTime(&t, ev[j], ev[j + 1]));
+      ms[j] += t;
+    }
+  }
   for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
 }
 
@@ -1297,7 +1322,7 @@ void rhs_host(Model& m, const double* h_p, double* h_out) {
     TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
     return;
   }
-  launch_weights(m, m.d_in, m.stream, nullptr);
+  launch_all_weights(m, m.d_in, m.stream);
   const uint64_t per = ((n + blocks - 1) / blocks + 31) & ~31ull;
   for (int b = 0; b < blocks; ++b) {
     const uint64_t lo = std::min<uint64_t>(n, per * b), hi = std::min<uint64_t>(n, lo + per);

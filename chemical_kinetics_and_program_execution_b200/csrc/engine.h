@@ -162,6 +162,13 @@ struct Model {
   BuildStats stats;
   int64_t launches_per_rhs = 0;
 
+  // A problem whose forest would not fit the 31-bit node ids of one structure is built as several
+  // structures over disjoint shares of its flux rules (rule_table_part): this one plus `more`, all
+  // on this model's stream.  Every right-hand-side entry point below evaluates them one after the
+  // other, the later ones adding their flux to the result of the earlier ones (fixed order, so
+  // results stay reproducible).  Each part keeps its own marginal tables and node weights.
+  std::vector<std::unique_ptr<Model>> more;
+
   ~Model();
 };
 
@@ -210,8 +217,9 @@ int64_t rhs_launch_count(const Model& m);
 void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st);
 // dy/dt for the states row_lo <= i < row_hi from the node weights of the last weights pass; `up`
 // (may be null) fuses a Runge-Kutta stage update into the same pass.
+// accumulate: dy/dt[i] = d_out[i] + sum instead of the sum alone (later parts of a composite model).
 void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
-                        const StageUpdate* up);
+                        const StageUpdate* up, bool accumulate);
 // Multi-GPU exchange fused into the product (flux.cu).  Device pointers into the memory of the
 // ranks of one NVLink domain, opened through CUDA IPC by the caller.
 struct PeerPointers {
@@ -254,7 +262,7 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st);
 int peer_group_error(PeerGroup& g);
 
 // Rebuilds the canonical CSR entries (ascending inside each row) from the slices into a device
-// buffer of nnz words.
+// buffer of nnz words (single-structure models only).
 void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st);
 
 }  // namespace tapes

@@ -247,13 +247,14 @@ template <int U, bool FUSED, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
-    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up) {
+    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up, int accumulate) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t s = slice_lo + (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (s >= slice_hi) return;
-  const double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
+  double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
   const uint64_t row = s * 32 + lane;
   if (row >= row_lo && row < row_hi) {
+    if (accumulate) acc = out[row] + acc;  // a later part of a composite model (engine.h Model::more)
     out[row] = acc;
     if (FUSED) {  // Runge-Kutta stage update for this state (terms in tableau order)
       double a = 0.0;
@@ -420,16 +421,17 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
 }
 
 void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t st,
-                        const StageUpdate* up) {
+                        const StageUpdate* up, bool accumulate) {
   if (row_hi <= row_lo) return;
   const FluxSlices& fs = m.slices;
   const uint64_t slice_lo = row_lo / 32, slice_hi = (row_hi + 31) / 32;
   const unsigned grid = grid_for((slice_hi - slice_lo) * 32, kThreads);
+  const int acc_flag = accumulate ? 1 : 0;
 #define TAPES_FLUX(U_, B_)                                                                                     \
   (up ? flux_slices_kernel<U_, true, B_><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
-                                                                   d_out, slice_lo, slice_hi, row_lo, row_hi, *up) \
+                                                                   d_out, slice_lo, slice_hi, row_lo, row_hi, *up, acc_flag) \
       : flux_slices_kernel<U_, false, B_><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
-                                                                    d_out, slice_lo, slice_hi, row_lo, row_hi, StageUpdate()))
+                                                                    d_out, slice_lo, slice_hi, row_lo, row_hi, StageUpdate(), acc_flag))
   // measured on B200 (n = 1e8, 24 rules): occupancy beats depth: 4 gathers per lane at 40 registers
   // 3.55 ms, 6 at 48 registers 3.93 ms, 8 at 56 registers 4.22 ms
   if (m.flux_unroll >= 8) TAPES_FLUX(8, 4);
@@ -476,6 +478,8 @@ PeerGroup* peer_group_create(int world, int rank, uint64_t block, int rounds, vo
 
 void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   if (m.flux_format != 1) throw std::runtime_error("the fused exchange needs the sliced flux structure");
+  if (!m.more.empty())
+    throw std::runtime_error("this rank's share is a composite model (forest above 2^31 nodes): deal the problem to more ranks");
   if (g.block * (uint64_t)g.world < m.n_states) throw std::runtime_error("ownership blocks do not cover the table");
   const FluxSlices& fs = m.slices;
   const uint32_t world = (uint32_t)g.world, rank = (uint32_t)g.rank;
@@ -513,6 +517,7 @@ int peer_group_error(PeerGroup& g) {
 }
 
 void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st) {
+  if (!m.more.empty()) throw std::runtime_error("composite model: export its parts one by one");
   const FluxSlices& fs = m.slices;
   expand_slices_kernel<<<grid_for(fs.n_slices * 32, kThreads), kThreads, 0, st>>>(
       fs.slice_ptr, fs.slice_runs, fs.words, m.row_ptr, m.n_states, fs.n_slices, d_entries);

@@ -57,7 +57,9 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
                          const int32_t* replacement, const double* rate,
                          const double* select_weight);
 
-/* Builds (or fetches from the cache) the device structure for (tag, cl_k). NULL on failure. */
+/* Builds (or fetches from the cache) the device structure for (tag, cl_k). NULL on failure.
+ * Limits: A^cl_k < 2^32, cl_k <= 32; the forest itself may be of any size that fits the device
+ * memory (it is split into structures of at most ~10^9 flux terms each, see tapes_model_info). */
 void* tapes_model(const char* tag, int64_t cl_k);
 /* Frees the structure of (tag, cl_k) and of every part of it; 1 when there was none. */
 int tapes_release_model(const char* tag, int64_t cl_k);
@@ -129,7 +131,10 @@ int tapes_sync(void* model);
  * entries held by columns, column slots incl. padding, minimum lanes of a run, loads in flight per
  * thread of the level kernel, forest levels whose parent lists are not arithmetic progressions,
  * left-parent records of all levels, gathers in flight per lane of the product kernel, right
- * children evaluated by the group they feed, groups whose children are evaluated by the next level.
+ * children evaluated by the group they feed, groups whose children are evaluated by the next level,
+ * structures the model consists of (more than one when the forest exceeds the 31-bit node ids: the
+ * flux rules are then split over several structures evaluated one after the other; sizes above are
+ * sums over them; TAPES_MAX_PART_TERMS overrides the 10^9 flux terms a structure may hold).
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 

@@ -307,6 +307,57 @@ def test_model_parts_sum_to_the_whole(mt, device, oracle, tag, size_a, cl_k, n_p
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
 
 
+@pytest.mark.parametrize('tag,size_a,cl_k,limit', [('ex4-chemical-turing', 9, 4, 9000),
+                                                   ('ex5-msrtf-machine', 5, 5, 40000),
+                                                   ('ex3-copolymerization', 4, 6, 1)])
+def test_composite_model_matches_single_structure(mt, device, oracle, monkeypatch, tag, size_a, cl_k, limit):
+  """A forest too large for the 31-bit node ids of one structure is built as several structures
+  over disjoint rule shares and evaluated one after the other (here forced by a small term limit):
+  same sizes in total, dy/dt equal to the single structure within rounding, and every entry point
+  (device, host buffers, row ranges, fused and unfused stepper) consistent with the others bit for
+  bit."""
+  import torch
+  p = configs.markov_table(size_a, cl_k, 29)
+  d_p = torch.from_numpy(p).cuda()
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  single = device.DeviceModel(tag, cl_k)
+  assert single.info['structures'] == 1
+  want = single.rhs(d_p).cpu().numpy()
+  sizes = {key: single.info[key] for key in ('n_nodes', 'nnz', 'n_terms', 'n_flux_rules', 'n_states')}
+  kw = dict(tag=tag, size_a=size_a, cl_k=cl_k, p0=p, ts=numpy.linspace(0, 2.0, 5), rtol=1e-9, atol=1e-12,
+            want_stats=True)
+  want_run = mt.ode_integrate_device(**kw)
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  monkeypatch.setenv('TAPES_MAX_PART_TERMS', str(limit))
+  try:
+    model = device.DeviceModel(tag, cl_k)
+    assert model.info['structures'] > 1
+    if limit == 1:
+      assert model.info['structures'] == model.info['n_flux_rules']  # never more structures than rules
+    assert {key: model.info[key] for key in sizes} == sizes
+    got = model.rhs(d_p).cpu().numpy()
+    assert_rhs_close(got, want, gross_flux(oracle, tag, cl_k, p))
+    assert numpy.array_equal(mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)(p, 0.0), got)
+    out = torch.full((model.n_states,), float('nan'), dtype=torch.float64, device='cuda')
+    model.weights(d_p)
+    cuts = [0, 33, model.n_states // 2 + 1, model.n_states]
+    for lo, hi in zip(cuts[:-1], cuts[1:]):
+      model.flux_rows(out, lo, hi)
+    assert numpy.array_equal(out.cpu().numpy(), got)
+    assert model.rhs_profile(d_p, out).shape == (3,) and numpy.array_equal(out.cpu().numpy(), got)
+    with pytest.raises(RuntimeError):
+      model.csr()
+    runs = []
+    for flag in ('1', '0'):  # the stage update rides on the last structure's product
+      monkeypatch.setenv('TAPES_RK_FUSED', flag)
+      runs.append(mt.ode_integrate_device(**kw))
+    assert runs[0][1] == runs[1][1] == want_run[1]
+    assert numpy.array_equal(runs[0][0], runs[1][0])
+    assert abs(runs[0][0] - want_run[0]).max() <= 1e-12 * abs(want_run[0]).max()
+  finally:
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+
+
 def test_peer_exchange_with_one_rank(mt, device):
   """The fused product + exchange kernels on a world of one: staging slots, owner sums and the
   result vector reproduce the plain product bit for bit (the N > 1 path is checked on the GPU box

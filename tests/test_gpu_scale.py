@@ -38,6 +38,22 @@ def test_ex3_long_chain(mt, oracle):
   assert abs(got.sum()) <= 1e-13 * abs(got).sum()
 
 
+def test_ex3_long_chain_as_composite_model(mt, oracle, monkeypatch):
+  """The same configuration split into several structures (as a forest above 2^31 nodes would be):
+  exercises the host-buffer path that returns the result in row blocks while later blocks are
+  still being summed over the structures."""
+  p = configs.dirichlet_product_table(4, 12, 3)
+  mt.u_lib.tapes_release_model(b'ex3-copolymerization', 12)
+  monkeypatch.setenv('TAPES_MAX_PART_TERMS', '30000000')
+  try:
+    stats = mt.model_stats(tag='ex3-copolymerization', cl_k=12)
+    assert stats['structures'] >= 3
+    got = mt.get_dy_dt(tag='ex3-copolymerization', size_a=4, cl_k=12)(p, 0.0)
+    close(got, oracle.compute_dy_dt('ex3-copolymerization', 12, p, mode=oracle.MERGED))
+  finally:
+    mt.u_lib.tapes_release_model(b'ex3-copolymerization', 12)
+
+
 def test_autocatalysis_tape(mt, oracle):
   """BASELINE config 2: our tape restatement of the autocatalysis chemistry at ~10^6 states."""
   rules = configs.autocatalysis_rule_set()
