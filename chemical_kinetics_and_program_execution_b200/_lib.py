@@ -140,7 +140,8 @@ MODEL_INFO_FIELDS = (
     'n_sum_nodes', 'worlds_walked', 'leaf_worlds', 'seeds', 'hash_inserts', 'hash_unique',
     'alphabet', 'cl_k', 'spmv_lanes_per_row', 'flux_format', 'n_slices', 'slice_words', 'runs',
     'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll',
-    'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups', 'structures')
+    'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups', 'structures',
+    'interleaved_levels')
 
 
 def model_info(model):

@@ -79,18 +79,32 @@ tapes::Model* get_model(const char* tag, int64_t cl_k, int64_t part = 0, int64_t
     tapes::RuleTable table = tapes::enumerate_rules(*prob, (int)cl_k);
     if (n_parts > 1) table = tapes::rule_table_part(table, (int)part, (int)n_parts);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-    // node ids have 31 bits: a forest beyond about 10^9 flux terms is built as several structures
-    // over disjoint shares of the rules, evaluated one after the other (engine.h Model::more)
-    double limit = 1.0e9, total = 0.0;
+    // node ids have 31 bits: a larger forest is built as several structures over disjoint shares of
+    // the rules, evaluated one after the other (engine.h Model::more).  Nodes are estimated from the
+    // flux terms (interior nodes add about 1 / (A - 1)); if a structure still comes out too large
+    // the split is refined.
+    const double a = (double)std::max(table.alphabet, 2);
+    double limit = 1.9e9 * (a - 1.0) / a, total = 0.0;
     if (const char* e = std::getenv("TAPES_MAX_PART_TERMS")) limit = std::max(1.0, std::atof(e));
     for (double c : tapes::flux_rule_costs(table)) total += c;
-    const int pieces = (int)std::min<double>(std::ceil(total / limit), (double)std::max<size_t>(table.rules.size(), 1));
+    const int max_pieces = (int)std::max<size_t>(table.rules.size(), 1);
+    int pieces = (int)std::min<double>(std::max(1.0, std::ceil(total / limit)), (double)max_pieces);
     std::unique_ptr<tapes::Model> m;
-    if (pieces <= 1) {
-      m = tapes::build_model(table, nullptr);
-    } else {
-      m = tapes::build_model(tapes::rule_table_part(table, 0, pieces), nullptr);
-      for (int i = 1; i < pieces; ++i) m->more.push_back(tapes::build_model(tapes::rule_table_part(table, i, pieces), m->stream));
+    for (;;) {
+      try {
+        if (pieces <= 1) {
+          m = tapes::build_model(table, nullptr);
+        } else {
+          m = tapes::build_model(tapes::rule_table_part(table, 0, pieces), nullptr);
+          for (int i = 1; i < pieces; ++i)
+            m->more.push_back(tapes::build_model(tapes::rule_table_part(table, i, pieces), m->stream));
+        }
+        break;
+      } catch (const tapes::TooLarge&) {
+        m.reset();
+        if (pieces >= max_pieces) throw;
+        pieces = std::min(max_pieces, pieces + std::max(1, pieces / 2));
+      }
     }
     m->stats.host_enumerate_ms = ms;
     tapes::Model* raw = m.get();
@@ -344,14 +358,16 @@ int tapes_sync(void* model) {
 int tapes_model_info(void* model, int64_t* out, int capacity) {
   if (!model) { fail("null model"); return 0; }
   const tapes::Model& head = *(tapes::Model*)model;
-  const int kFields = 31;
+  const int kFields = 32;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
                                      true, false, false, false, false, false, true, true, true, true,
-                                     true, false, false, true, true, false, true, true, true};
+                                     true, false, false, true, true, false, true, true, true, true};
   int64_t total[kFields] = {};
   for (size_t part = 0; part <= head.more.size(); ++part) {
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
+    int64_t interleaved = 0;
+    for (const tapes::Level& lv : m.levels) interleaved += lv.block_order ? 1 : 0;
     const int64_t v[kFields] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
                                 (int64_t)m.levels.size(), 0, m.stats.terms, m.stats.sum_nodes,
                                 m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
@@ -360,7 +376,7 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                                 (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
                                 (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
                                 m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
-                                m.stats.owned_parents, m.stats.deferred_groups, 1};
+                                m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved};
     for (int i = 0; i < kFields; ++i) {
       if (part == 0) total[i] = v[i];
       else if (adds[i]) total[i] += v[i];
@@ -383,6 +399,7 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
   if (std::strcmp(key, "flux_unroll") == 0 && (value == 2 || value == 3 || value == 4 || value == 6 || value == 8))
     field = &tapes::Model::flux_unroll;
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) field = &tapes::Model::level_unroll;
+  if (std::strcmp(key, "interleave_seeds") == 0 && (value == 0 || value == 1)) field = &tapes::Model::interleave_seeds;
   if (field) {
     head.*field = (int)value;
     for (auto& part : head.more) (*part).*field = (int)value;

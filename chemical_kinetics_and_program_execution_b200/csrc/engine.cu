@@ -535,7 +535,8 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
     }
   } else {
     const unsigned lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x - left_blocks) * (kThreads / 32) + (threadIdx.x >> 5);
+    const uint32_t group_block = lv.block_order ? lv.block_order[blockIdx.x - left_blocks] : blockIdx.x - left_blocks;
+    const uint32_t warp = group_block * (kThreads / 32) + (threadIdx.x >> 5);
     const uint64_t g0 = (uint64_t)warp * 32;
     if (g0 >= lv.n_groups) return;
     const uint64_t g = g0 + lane;
@@ -859,7 +860,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   // 3.2 s first build (profiles/r01_e_*).
   auto t_expand = std::chrono::steady_clock::now();
   struct EdgeChunk { uint32_t* row; uint32_t* val; uint64_t n; };
-  std::vector<EdgeChunk> edge_chunks;
+  struct EdgeChunks : std::vector<EdgeChunk> {  // freed on every way out, a failed build included
+    ~EdgeChunks() { for (EdgeChunk& ec : *this) if (ec.row) cudaFree(ec.row); }
+  } edge_chunks;
 
   Frontier cur;
   cur.n = roots.size();
@@ -910,8 +913,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
                                ((seed_bits ? ((1ull << seed_bits) - 1) : 0ull) << 32);
 
   uint64_t total_terms = 0;
+  uint64_t node_limit = 0x7fffffffull;  // node id + sign bit in 32 bits; lowered by tests of the splitting
+  if (const char* e = std::getenv("TAPES_MAX_NODES")) node_limit = std::min<uint64_t>(node_limit, std::strtoull(e, nullptr, 10));
   while (cur.n > 0) {
-    if (cur_level.base + cur.n >= 0x7fffffffull) throw std::runtime_error("extension forest exceeds 2^31 nodes");
+    if (cur_level.base + cur.n >= node_limit) throw TooLarge("extension forest exceeds 2^31 nodes");
     m.stats.levels++;
     const uint64_t n = cur.n;
 
@@ -947,7 +952,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], counters, 8, cudaMemcpyDeviceToHost, st));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
     const uint64_t NL = h_tot[0], NT = h_tot[1], NG = h_tot[2];
-    if ((NL + NG) * (uint64_t)m.A >= 0xffffffffull) throw std::runtime_error("level too large");
+    if ((NL + NG) * (uint64_t)m.A >= 0xffffffffull) throw TooLarge("a level of the extension forest exceeds 2^32 nodes");
 
     // pass 2: children, parent records, flux edges
     Frontier next;
@@ -981,7 +986,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       next_level.lp_len = dkeep<uint8_t>(m, NL);
     }
     EdgeChunk ec{nullptr, nullptr, 2 * NT};
-    if (NT) { ec.row = dtemp<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT; }  // one allocation for both
+    if (NT) {  // one allocation for both arrays, owned by the list from here on
+      ec.row = dtemp<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT;
+      edge_chunks.push_back(ec);
+    }
     emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, kflag, lrank, trank,
                                                           NL, hs, next, next_level.lp_gid, next_level.lp_io,
                                                           next_level.lp_len, ec.row, ec.val, keyrank);
@@ -1058,7 +1066,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     }
     TAPES_CUDA_CHECK(cudaGetLastError());
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (NT) edge_chunks.push_back(ec);
     total_terms += NT;
     m.stats.left_parents += (int64_t)NL;
 
@@ -1069,6 +1076,30 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   }
   if (cur_slab.capacity + s1.capacity + s2.capacity > ((size_t)1 << 30)) {
     cur_slab.release(); s1.release(); s2.release();
+  }
+  // seeds walk through p together (Level::block_order): sort the blocks of 256 groups of every
+  // level by the prefix they start at; a level whose order comes out as the identity keeps none
+  {
+    std::vector<uint32_t> first_prefix, order;
+    for (Level& lv : m.levels) {
+      if (!lv.g_prefix || lv.n_groups <= (uint32_t)kThreads) continue;
+      const size_t n_blocks = ((size_t)lv.n_groups + kThreads - 1) / kThreads;
+      first_prefix.resize(n_blocks);
+      TAPES_CUDA_CHECK(cudaMemcpy2DAsync(first_prefix.data(), 4, lv.g_prefix, (size_t)kThreads * 4, 4, n_blocks,
+                                         cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      order.resize(n_blocks);
+      for (size_t b = 0; b < n_blocks; ++b) order[b] = (uint32_t)b;
+      std::stable_sort(order.begin(), order.end(),
+                       [&](uint32_t x, uint32_t y) { return first_prefix[x] < first_prefix[y]; });
+      bool identity = true;
+      for (size_t b = 0; b < n_blocks && identity; ++b) identity = order[b] == b;
+      if (identity) continue;
+      uint32_t* d_order = dkeep<uint32_t>(m, n_blocks);
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), n_blocks * 4, cudaMemcpyHostToDevice, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      lv.block_order = d_order;
+    }
   }
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
   m.stats.nodes = (int64_t)m.n_nodes;
@@ -1112,6 +1143,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.level_unroll = m.A <= 2 ? 2 : ((m.A + 4) / 5 * 5 - m.A <= (m.A + 3) / 4 * 4 - m.A ? 5 : 4);
   if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
   if (const char* g = std::getenv("TAPES_FLUX_UNROLL")) m.flux_unroll = std::atoi(g);
+  if (const char* g = std::getenv("TAPES_INTERLEAVE_SEEDS")) m.interleave_seeds = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
 
@@ -1168,7 +1200,9 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
     rule_weight_kernel<<<grid_for(m.n_rules, 128), 128, 0, st>>>(t, m.n_rules, m.rule_ptr, m.step_kind, m.step_len,
                                                                 m.step_long, m.step_short, m.step_prob, m.rule_w);
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
-  for (const Level& lv : m.levels) {
+  for (const Level& stored : m.levels) {
+    Level lv = stored;
+    if (!m.interleave_seeds) lv.block_order = nullptr;
     if (lv.n_roots) {
       root_kernel<<<grid_for(lv.n_roots, kThreads), kThreads, 0, st>>>(lv.root_rule, lv.n_roots, m.rule_w, m.node_w);
     } else if (lv.n_left + lv.n_groups) {

@@ -6,6 +6,7 @@
 
 #include <cstdint>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -61,6 +62,12 @@ struct Level {
   uint64_t prev_right_base = 0;         // node id of the previous level's first right child
   const uint32_t* prev_prefix = nullptr;  // previous level's g_prefix
   const double* prev_total = nullptr;     // previous level's g_total
+  // Groups are stored seed-major (canonical order), but the chains of different seeds read the same
+  // entries of p at the same prefix.  block_order[b] = which block of 256 groups thread block b of
+  // the group part evaluates: blocks sorted by the prefix they start at, so that the seeds walk
+  // through p together and the second reader of an entry finds it in L2.  Null when the level has
+  // one seed only (identity) or the option is off.
+  const uint32_t* block_order = nullptr;
 };
 
 // The flux structure cut into slices of 32 consecutive states, one warp lane per state.  Consecutive
@@ -145,6 +152,7 @@ struct Model {
   int flux_format = 1;             // 1 = slices, 0 = plain CSR
   int level_unroll = 4;            // loads in flight per thread in level_kernel
   int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
+  int interleave_seeds = 1;        // level kernel: use Level::block_order
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;
@@ -174,6 +182,11 @@ struct Model {
 
 // Frees the scratch memory small builds leave behind for the next build.
 void release_build_scratch();
+
+// Thrown by build_model when a forest does not fit the 32-bit indices of one structure.
+struct TooLarge : std::runtime_error {
+  explicit TooLarge(const std::string& what) : std::runtime_error(what) {}
+};
 
 // Builds the device structures for a rule table.  Throws std::runtime_error on failure.
 std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream);

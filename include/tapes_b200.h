@@ -59,7 +59,7 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
 
 /* Builds (or fetches from the cache) the device structure for (tag, cl_k). NULL on failure.
  * Limits: A^cl_k < 2^32, cl_k <= 32; the forest itself may be of any size that fits the device
- * memory (it is split into structures of at most ~10^9 flux terms each, see tapes_model_info). */
+ * memory (it is split into structures of at most 2^31 nodes each, see tapes_model_info). */
 void* tapes_model(const char* tag, int64_t cl_k);
 /* Frees the structure of (tag, cl_k) and of every part of it; 1 when there was none. */
 int tapes_release_model(const char* tag, int64_t cl_k);
@@ -134,13 +134,17 @@ int tapes_sync(void* model);
  * children evaluated by the group they feed, groups whose children are evaluated by the next level,
  * structures the model consists of (more than one when the forest exceeds the 31-bit node ids: the
  * flux rules are then split over several structures evaluated one after the other; sizes above are
- * sums over them; TAPES_MAX_PART_TERMS overrides the 10^9 flux terms a structure may hold).
+ * sums over them; TAPES_MAX_PART_TERMS overrides the ~1.7 * 10^9 flux terms a structure may hold), forest
+ * levels whose blocks of prefix groups are evaluated in prefix order across seeds.
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
 /* Tuning knobs of a built model: "spmv_lanes" (1, 2, 4, 8 or 16 lanes per row of the plain-CSR
  * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel), "flux_unroll"
- * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel). */
+ * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel), "interleave_seeds" (1: the
+ * level kernel evaluates the blocks of prefix groups of different seeds in prefix order so that they
+ * share their reads of the table through L2, 0: in storage order).  Results do not depend on any of
+ * them. */
 int tapes_model_set(void* model, const char* key, int64_t value);
 
 /* Build timings in ms: host rule enumeration, device expansion, device CSR assembly, slicing, and

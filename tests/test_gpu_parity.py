@@ -180,6 +180,7 @@ def test_flux_row_ranges_and_gather_depths(mt, device):
   p = torch.from_numpy(configs.markov_table(9, 5, 2)).cuda()
   model = device.DeviceModel('ex4-chemical-turing', 5)
   assert model.info['flux_format'] == 1 and model.info['runs'] > 0
+  assert model.info['interleaved_levels'] > 0  # 24 leaf worlds: their chains share the table reads
   want = model.rhs(p).cpu().numpy()
   n = model.n_states
   out = torch.full((n,), float('nan'), dtype=torch.float64, device='cuda')
@@ -192,7 +193,7 @@ def test_flux_row_ranges_and_gather_depths(mt, device):
   model.flux_rows(guard, 40, 50)  # nothing outside the range is written
   g = guard.cpu().numpy()
   assert (g[:40] == 7.0).all() and (g[50:] == 7.0).all() and numpy.array_equal(g[40:50], want[40:50])
-  for key, values in (('flux_unroll', (2, 3, 4, 6, 8)), ('level_unroll', (1, 2, 4, 5, 8))):
+  for key, values in (('flux_unroll', (2, 3, 4, 6, 8)), ('level_unroll', (1, 2, 4, 5, 8)), ('interleave_seeds', (0, 1))):
     keep = model.info.get(key, None)
     for v in values:
       model.set_option(key, v)
@@ -354,6 +355,29 @@ def test_composite_model_matches_single_structure(mt, device, oracle, monkeypatc
     assert runs[0][1] == runs[1][1] == want_run[1]
     assert numpy.array_equal(runs[0][0], runs[1][0])
     assert abs(runs[0][0] - want_run[0]).max() <= 1e-12 * abs(want_run[0]).max()
+  finally:
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+
+
+def test_oversized_structure_is_split_further(mt, device, oracle, monkeypatch):
+  """When the node estimate was too optimistic and a structure overflows its node ids, the build
+  starts over with more structures (here the node limit is lowered instead of the forest grown)."""
+  import torch
+  tag, size_a, cl_k = 'ex4-chemical-turing', 9, 4
+  p = configs.markov_table(size_a, cl_k, 41)
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  nodes = device.DeviceModel(tag, cl_k).info['n_nodes']
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  monkeypatch.setenv('TAPES_MAX_NODES', str(nodes // 3))
+  try:
+    model = device.DeviceModel(tag, cl_k)
+    assert model.info['structures'] >= 4 and model.info['n_nodes'] == nodes
+    got = model.rhs(torch.from_numpy(p).cuda()).cpu().numpy()
+    assert_rhs_close(got, oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED), gross_flux(oracle, tag, cl_k, p))
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+    monkeypatch.setenv('TAPES_MAX_NODES', '10')  # not even one rule fits: a clean error, nothing half built
+    with pytest.raises(RuntimeError, match='2\\^31'):
+      device.DeviceModel(tag, cl_k)
   finally:
     mt.u_lib.tapes_release_model(tag.encode(), cl_k)
 
