@@ -19,7 +19,7 @@ SYMBOLS = (
     'tapes_model_set', 'tapes_model_timing', 'tapes_export_csr', 'tapes_export_node_weights', 'tapes_rule_table',
     'tapes_peer_alloc', 'tapes_peer_open', 'tapes_peer_close', 'tapes_peer_free', 'tapes_peer_group_create',
     'tapes_peer_group_destroy', 'tapes_peer_rhs', 'tapes_peer_group_error', 'tapes_dop853_create_peer',
-    'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts',
+    'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts', 'tapes_register_program',
 )
 
 _lib = None
@@ -53,6 +53,8 @@ def load():
   lib.tapes_alphabet_size.argtypes = [ctypes.c_char_p]
   lib.tapes_register_rules.restype = i32
   lib.tapes_register_rules.argtypes = [ctypes.c_char_p, i64, i64] + [vp] * 7
+  lib.tapes_register_program.restype = i32
+  lib.tapes_register_program.argtypes = [ctypes.c_char_p, i64, i64] + [vp] * 6 + [i64, vp, i64, vp]
   lib.tapes_model.restype = vp
   lib.tapes_model.argtypes = [ctypes.c_char_p, i64]
   lib.tapes_model_part.restype = vp
@@ -196,6 +198,17 @@ def rule_parts(tag, cl_k, n_parts):
   check(lib.tapes_rule_parts(tag.encode(), cl_k, n_parts, owner.ctypes.data, cost.ctypes.data) == n_rules,
         'tapes_rule_parts')
   return owner, cost
+
+
+def register_program(tag, size_a, tree):
+  """Registers a program tree (dict of arrays as produced by programs.trace) under `tag`."""
+  i32 = lambda x: numpy.ascontiguousarray(numpy.asarray(x, dtype=numpy.int32))
+  cols = [i32(tree[key]) for key in ('kind', 'a', 'b', 'c', 'first_child', 'first_weight')]
+  child = i32(tree['child'])
+  weight = numpy.ascontiguousarray(numpy.asarray(tree['weight'], dtype=numpy.float64))
+  rc = load().tapes_register_program(tag.encode(), size_a, cols[0].size, *[col.ctypes.data for col in cols],
+                                     child.size, child.ctypes.data, weight.size, weight.ctypes.data)
+  check(rc == 0, 'tapes_register_program')
 
 
 def register_rules(tag, size_a, rules):

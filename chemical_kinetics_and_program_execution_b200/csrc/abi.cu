@@ -187,6 +187,30 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
   }
 }
 
+int tapes_register_program(const char* tag, int64_t alphabet, int64_t n_nodes, const int32_t* kind,
+                           const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* first_child,
+                           const int32_t* first_weight, int64_t n_children, const int32_t* child,
+                           int64_t n_weights, const double* weight) {
+  try {
+    tapes::register_builtin_problems();
+    if (alphabet < 1 || alphabet > 65535) throw std::runtime_error("alphabet size must be in 1..65535");
+    if (n_nodes < 1 || n_children < 0 || n_weights < 0) throw std::runtime_error("negative array length");
+    tapes::ProgramTree t;
+    t.kind.assign(kind, kind + n_nodes); t.a.assign(a, a + n_nodes); t.b.assign(b, b + n_nodes);
+    t.c.assign(c, c + n_nodes); t.first_child.assign(first_child, first_child + n_nodes);
+    t.first_weight.assign(first_weight, first_weight + n_nodes);
+    t.child.assign(child, child + n_children);
+    t.weight.assign(weight, weight + n_weights);
+    tapes::register_problem(tag, (int)alphabet, tapes::body_from_program(std::move(t), (int)alphabet));
+    for (auto it = g_models.begin(); it != g_models.end();)  // a re-registered tag invalidates cached structures
+      it = (std::get<0>(it->first) == tag) ? g_models.erase(it) : std::next(it);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("register_program: ") + ex.what());
+    return 1;
+  }
+}
+
 void* tapes_model(const char* tag, int64_t cl_k) { return (void*)get_model(tag, cl_k); }
 
 void* tapes_model_part(const char* tag, int64_t cl_k, int64_t part, int64_t n_parts) {

@@ -246,4 +246,53 @@ Body body_from_rewrite_rules(std::vector<RewriteRule> rules) {
   };
 }
 
+Body body_from_program(ProgramTree t, int alphabet) {
+  const size_t n = t.kind.size();
+  if (n == 0) throw std::runtime_error("program tree has no nodes");
+  if (t.a.size() != n || t.b.size() != n || t.c.size() != n || t.first_child.size() != n || t.first_weight.size() != n)
+    throw std::runtime_error("program tree arrays differ in length");
+  for (size_t i = 0; i < n; ++i) {
+    int fan = 0;
+    switch (t.kind[i]) {
+      case ProgramTree::END: break;
+      case ProgramTree::READ: fan = alphabet; break;
+      case ProgramTree::WRITE:
+        fan = 1;
+        if (t.c[i] < 0 || t.c[i] >= alphabet) throw std::runtime_error("program writes a symbol outside the alphabet");
+        break;
+      case ProgramTree::PICK:
+        fan = t.a[i];
+        if (fan < 1) throw std::runtime_error("choice without options");
+        if (t.first_weight[i] < 0 || (size_t)t.first_weight[i] + (size_t)fan > t.weight.size())
+          throw std::runtime_error("choice weights outside the weight array");
+        break;
+      default: throw std::runtime_error("unknown program node kind");
+    }
+    if (t.kind[i] == ProgramTree::READ || t.kind[i] == ProgramTree::WRITE) {
+      if (t.a[i] != 0 && t.a[i] != 1) throw std::runtime_error("tape must be 0 (program) or 1 (data)");
+      if (t.b[i] <= -kMaxSide || t.b[i] >= kMaxSide) throw std::runtime_error("cell index too far from the head");
+    }
+    if (fan) {
+      if (t.first_child[i] < 0 || (size_t)t.first_child[i] + (size_t)fan > t.child.size())
+        throw std::runtime_error("children outside the child array");
+      for (int j = 0; j < fan; ++j) {
+        const int32_t ch = t.child[(size_t)t.first_child[i] + (size_t)j];
+        if (ch <= (int32_t)i || (size_t)ch >= n) throw std::runtime_error("a child must come after its parent");
+      }
+    }
+  }
+  return [t](Machine& m) {
+    size_t i = 0;
+    for (;;) {
+      const size_t at = (size_t)t.first_child[i];
+      switch (t.kind[i]) {
+        case ProgramTree::END: return;
+        case ProgramTree::READ: i = (size_t)t.child[at + (size_t)m.read(t.a[i] ? DATA_TAPE : PROGRAM_TAPE, t.b[i])]; break;
+        case ProgramTree::WRITE: m.write(t.a[i] ? DATA_TAPE : PROGRAM_TAPE, t.b[i], t.c[i]); i = (size_t)t.child[at]; break;
+        default: i = (size_t)t.child[at + (size_t)m.pick(&t.weight[(size_t)t.first_weight[i]], t.a[i])]; break;
+      }
+    }
+  };
+}
+
 }  // namespace tapes

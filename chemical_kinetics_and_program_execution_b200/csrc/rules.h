@@ -96,4 +96,19 @@ struct RewriteRule {
 };
 Body body_from_rewrite_rules(std::vector<RewriteRule> rules);
 
+// Programs given as data: the decision tree of a problem body (what framework/problems.scm states
+// with tape-get / tape-set! / choose, framework/gambit_macros.scm:99-125), so that a new problem
+// needs no recompilation.  Node 0 is the entry; children have larger indices than their parent.
+struct ProgramTree {
+  enum Kind : int32_t { END = 0, READ = 1, WRITE = 2, PICK = 3 };
+  std::vector<int32_t> kind;         // per node
+  std::vector<int32_t> a, b, c;      // READ: tape, cell; WRITE: tape, cell, symbol; PICK: options
+  std::vector<int32_t> first_child;  // READ: A children by symbol read; WRITE: 1; PICK: one per option
+  std::vector<int32_t> first_weight; // PICK: offset of its (unnormalised) weights
+  std::vector<int32_t> child;
+  std::vector<double> weight;
+};
+// Throws std::runtime_error when the tree is malformed.
+Body body_from_program(ProgramTree tree, int alphabet);
+
 }  // namespace tapes

@@ -11,8 +11,8 @@ Differences, all documented in INTEGRATION.md:
     MARKOV_TAPES_DEBUG=1;
   * a failed library call raises RuntimeError (the reference drops into a Scheme REPL,
     framework/tapes_py_interface.scm:42-44);
-  * additions: `ode_integrate_device`, `sequence_observable`, `model_stats`,
-    `register_rule_set`; device-resident dy/dt lives in device.py.
+  * additions: `ode_integrate_device`, `sequence_observable`, `model_stats`, `check_table`,
+    `register_rule_set`, `register_program`; device-resident dy/dt lives in device.py.
 """
 
 import atexit
@@ -204,6 +204,15 @@ def ode_integrate_ivp(*, tag, size_a, cl_k, p0, ts, ivp_kwargs=types.MappingProx
 def register_rule_set(tag, size_a, rules):
   """Registers a rewrite-rule set under `tag` (see configs.random_rule_set)."""
   _lib.register_rules(tag, size_a, rules)
+
+
+def register_program(tag, size_a, body):
+  """Registers the problem stated by the Python function `body(tape)` under `tag`; `tape` offers
+  get(data_tape, index), set(data_tape, index, symbol), choose(weights) and choose_value(pairs),
+  the primitives of framework/gambit_macros.scm:99-125 (see programs.py).  Replaces editing
+  framework/problems.scm and rebuilding the shared object."""
+  from . import programs
+  _lib.register_program(tag, size_a, programs.trace(body, size_a))
 
 
 def model_stats(*, tag, cl_k):

@@ -57,6 +57,20 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
                          const int32_t* replacement, const double* rate,
                          const double* select_weight);
 
+/* Registers a problem given as the decision tree of its body - the data form of what
+ * framework/problems.scm states with tape-get / tape-set! / choose
+ * (framework/gambit_macros.scm:99-125); the reference needs an edit of problems.scm and a rebuild of
+ * the shared object for a new problem (MAKE.sh:43-47).  Per node: kind (0 end, 1 read, 2 write,
+ * 3 choose), a / b / c (read: tape 0 = program 1 = data, cell; write: tape, cell, symbol; choose:
+ * number of options), first_child (offset into child: `alphabet` children by symbol read, one after a
+ * write, one per option), first_weight (choose: offset into weight, unnormalised weights as in
+ * gambit_macros.scm:75-86).  Node 0 is the entry and children come after their parent.
+ * markov_tapes.register_program traces a Python function into this form. */
+int tapes_register_program(const char* tag, int64_t alphabet, int64_t n_nodes, const int32_t* kind,
+                           const int32_t* a, const int32_t* b, const int32_t* c, const int32_t* first_child,
+                           const int32_t* first_weight, int64_t n_children, const int32_t* child,
+                           int64_t n_weights, const double* weight);
+
 /* Builds (or fetches from the cache) the device structure for (tag, cl_k). NULL on failure.
  * Limits: A^cl_k < 2^32, cl_k <= 32; the forest itself may be of any size that fits the device
  * memory (it is split into structures of at most 2^31 nodes each, see tapes_model_info). */

@@ -54,6 +54,10 @@ def lib():
     _lib.oracle_register_rules.restype = ctypes.c_int
     _lib.oracle_register_rules.argtypes = [
         ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 7
+    _lib.oracle_register_program.restype = ctypes.c_int
+    _lib.oracle_register_program.argtypes = (
+        [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int64] + [ctypes.c_void_p] * 6
+        + [ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p])
     _lib.oracle_last_error.restype = ctypes.c_char_p
   return _lib
 
@@ -119,6 +123,19 @@ def register_rules(tag, size_a, rules):
   arrs = _rule_arrays(rules)
   rc = lib().oracle_register_rules(tag.encode(), size_a, arrs[0].shape[0],
                                    *[a.ctypes.data for a in arrs])
+  if rc != 0:
+    raise RuntimeError(last_error())
+
+
+def register_program(tag, size_a, tree):
+  """Registers a problem given as a decision tree (dict of arrays: kind, a, b, c, first_child,
+  first_weight per node, child, weight; see oracle_register_program in tape_oracle.cpp)."""
+  i32 = lambda x: numpy.ascontiguousarray(numpy.asarray(x, dtype=numpy.int32))
+  cols = [i32(tree[key]) for key in ('kind', 'a', 'b', 'c', 'first_child', 'first_weight')]
+  child = i32(tree['child'])
+  weight = numpy.ascontiguousarray(numpy.asarray(tree['weight'], dtype=numpy.float64))
+  rc = lib().oracle_register_program(tag.encode(), size_a, cols[0].size, *[col.ctypes.data for col in cols],
+                                     child.size, child.ctypes.data, weight.size, weight.ctypes.data)
   if rc != 0:
     raise RuntimeError(last_error())
 

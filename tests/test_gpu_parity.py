@@ -164,6 +164,34 @@ def test_rule_set_problem(mt, oracle):
     check_rhs(f, oracle, tag, cl_k, p, oracle.MERGED)
 
 
+def test_python_programs(mt, oracle):
+  """Problems stated as Python functions (markov_tapes.register_program): a restatement of a
+  reference body gives the bits of the compiled body, and a program that exists nowhere else
+  matches the oracle interpreting the same tree."""
+  import test_programs as tp
+  from chemical_kinetics_and_program_execution_b200 import programs
+  mt.register_program('py-gpu-ex2', 2, tp.ferromagnet)
+  mt.register_program('py-gpu-ex3', 4, tp.copolymerization)
+  for tag, ref, size_a, cl_k in (('py-gpu-ex2', 'ex2-ferromagnetic-chain', 2, 7),
+                                 ('py-gpu-ex3', 'ex3-copolymerization', 4, 6)):
+    p = configs.markov_table(size_a, cl_k, 12)
+    got = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)(p, 0.0)
+    assert numpy.array_equal(got, mt.get_dy_dt(tag=ref, size_a=size_a, cl_k=cl_k)(p, 0.0))
+  mt.register_program('py-gpu-relay', 3, tp.relay)
+  oracle.register_program('py-gpu-relay', 3, programs.trace(tp.relay, 3))
+  for cl_k in (1, 2, 5, 8):
+    for make in (configs.dirichlet_product_table, configs.markov_table):
+      p = make(3, cl_k, 14)
+      check_rhs(mt.get_dy_dt(tag='py-gpu-relay', size_a=3, cl_k=cl_k), oracle, 'py-gpu-relay', cl_k, p, oracle.MERGED)
+  p = configs.markov_table(3, 4, 15)
+  check_rhs(mt.get_dy_dt(tag='py-gpu-relay', size_a=3, cl_k=4), oracle, 'py-gpu-relay', 4, p, oracle.LITERAL)
+  # re-registering a tag replaces the program and drops the structures built for the old one
+  before = mt.get_dy_dt(tag='py-gpu-relay', size_a=3, cl_k=4)(p, 0.0)
+  mt.register_program('py-gpu-relay', 3, lambda tape: tape.set(True, 0, 0) if tape.get(True, 0) else None)
+  after = mt.get_dy_dt(tag='py-gpu-relay', size_a=3, cl_k=4)(p, 0.0)
+  assert not numpy.array_equal(before, after)
+
+
 def test_device_rhs_equals_host_rhs(mt, device):
   import torch
   p = configs.markov_table(5, 5, 1)
