@@ -42,6 +42,17 @@ METRIC = 'master-eq SpMV GB/s (whole dy/dt step incl. rate re-evaluation, algori
 UNIT = 'GB/s'
 
 
+# stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent
+# to stderr by pointing file descriptor 1 at it; the line itself goes to the original descriptor
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+  sys.stdout.flush()
+  os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+
+
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
@@ -299,7 +310,7 @@ def run_reference(args):
               cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample_desc),
               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
               gpu_launches=0)
-  print(json.dumps(line), flush=True)
+  emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -533,7 +544,7 @@ def run_b200(args):
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],
                            flux_slices={k: info.get(k) for k in ('n_slices', 'slice_words', 'runs', 'run_entries',
                                                                   'column_entries', 'column_slots')}))
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
