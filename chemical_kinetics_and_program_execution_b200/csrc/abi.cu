@@ -424,7 +424,15 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
     field = &tapes::Model::flux_unroll;
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) field = &tapes::Model::level_unroll;
   if (std::strcmp(key, "interleave_seeds") == 0 && (value == 0 || value == 1)) field = &tapes::Model::interleave_seeds;
+  if (std::strcmp(key, "graphs") == 0 && (value == 0 || value == 1)) {
+    cudaStreamSynchronize(head.stream);
+    head.drop_weight_graphs();
+    head.use_graphs = (int)value;
+    return 0;
+  }
   if (field) {
+    cudaStreamSynchronize(head.stream);
+    head.drop_weight_graphs();  // captured launches carry the old setting
     head.*field = (int)value;
     for (auto& part : head.more) (*part).*field = (int)value;
     return 0;

@@ -719,12 +719,22 @@ void DeviceArena::release() {
   cursor = nullptr; left = 0; bytes = 0; next_chunk = 32u << 20;
 }
 
+void Model::drop_weight_graphs() {
+  for (WeightsGraph& g : weight_graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  weight_graphs.clear();
+}
+
 Model::~Model() {
+  if (stream) cudaStreamSynchronize(stream);
+  drop_weight_graphs();
   more.clear();  // the other parts of a composite model use this model's stream: they go first
   cudaStream_t st = stream;
   if (st) cudaStreamSynchronize(st);
   if (entries) cudaFree(entries);
   entries = nullptr;
+  if (h_pinned) cudaFreeHost(h_pinned);
+  if (d_obs_spec) cudaFree(d_obs_spec);
+  if (d_obs_out) cudaFree(d_obs_out);
   arena.release();
   if (copy_stream) {
     cudaStreamDestroy(copy_stream);
@@ -1144,6 +1154,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (const char* g = std::getenv("TAPES_LEVEL_UNROLL")) m.level_unroll = std::max(1, std::atoi(g));
   if (const char* g = std::getenv("TAPES_FLUX_UNROLL")) m.flux_unroll = std::atoi(g);
   if (const char* g = std::getenv("TAPES_INTERLEAVE_SEEDS")) m.interleave_seeds = std::atoi(g) != 0;
+  if (const char* g = std::getenv("TAPES_GRAPHS")) m.use_graphs = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.stats.device_csr_ms = ms_since(t_csr);
 
@@ -1275,9 +1286,70 @@ void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cuda
   }
 }
 
-void launch_all_weights(Model& m, const double* d_p, cudaStream_t st) {
+void launch_all_weights_plain(Model& m, const double* d_p, cudaStream_t st) {
   launch_weights(m, d_p, st, nullptr);
   for (auto& part : m.more) launch_weights(*part, d_p, st, nullptr);
+}
+
+// Replays (after capturing it on first use) the graph of launch_all_weights_plain for this input
+// pointer; false when graphs do not apply and the caller has to launch directly.
+bool launch_weights_graph(Model& m, const double* d_p, cudaStream_t st) {
+  if (!m.use_graphs || m.n_states > Model::kGraphMaxStates) return false;
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return false;  // cannot be captured
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &status) != cudaSuccess || status != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;  // the caller is capturing this stream itself
+  }
+  ++m.graph_clock;
+  for (Model::WeightsGraph& g : m.weight_graphs) {
+    if (g.d_p == d_p) {
+      g.last_use = m.graph_clock;
+      TAPES_CUDA_CHECK(cudaGraphLaunch(g.exec, st));
+      return true;
+    }
+  }
+  if (cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  bool ok = true;
+  try {
+    launch_all_weights_plain(m, d_p, st);
+  } catch (const std::exception&) {
+    ok = false;
+  }
+  if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) ok = false;
+  if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+  if (graph) cudaGraphDestroy(graph);
+  if (!ok) {
+    cudaGetLastError();
+    if (exec) cudaGraphExecDestroy(exec);
+    m.use_graphs = 0;  // do not try again on every call
+    return false;
+  }
+  Model::WeightsGraph entry;
+  entry.d_p = d_p; entry.exec = exec; entry.last_use = m.graph_clock;
+  if (m.weight_graphs.size() < Model::kMaxWeightGraphs) {
+    m.weight_graphs.push_back(entry);
+  } else {
+    size_t oldest = 0;
+    for (size_t i = 1; i < m.weight_graphs.size(); ++i)
+      if (m.weight_graphs[i].last_use < m.weight_graphs[oldest].last_use) oldest = i;
+    // the replaced graph may still be running on some stream: launches are ordered on the streams
+    // they went to, and destroying an executable graph waits for nothing, so wait here
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaGraphExecDestroy(m.weight_graphs[oldest].exec);
+    m.weight_graphs[oldest] = entry;
+  }
+  TAPES_CUDA_CHECK(cudaGraphLaunch(exec, st));
+  return true;
+}
+
+void launch_all_weights(Model& m, const double* d_p, cudaStream_t st) {
+  if (!launch_weights_graph(m, d_p, st)) launch_all_weights_plain(m, d_p, st);
 }
 }  // namespace
 
@@ -1347,11 +1419,24 @@ void rhs_host(Model& m, const double* h_p, double* h_out) {
     TAPES_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : m.copy_events) TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
+  const bool pinned = n <= Model::kPinnedStagingStates;
+  if (pinned) {
+    if (!m.h_pinned) TAPES_CUDA_CHECK(cudaHostAlloc((void**)&m.h_pinned, 2 * bytes, cudaHostAllocDefault));
+    std::memcpy(m.h_pinned, h_p, bytes);
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, m.h_pinned, bytes, cudaMemcpyHostToDevice, m.stream));
+  } else {
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
+  }
   // large tables: the result goes back in row blocks while the product of the next block runs
   const int blocks = n >= (1ull << 22) ? Model::kCopyBlocks : 1;
   if (blocks == 1) {
     rhs_device(m, m.d_in, m.d_out, m.stream);
+    if (pinned) {
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(m.h_pinned + n, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+      std::memcpy(h_out, m.h_pinned + n, bytes);
+      return;
+    }
     TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
     return;

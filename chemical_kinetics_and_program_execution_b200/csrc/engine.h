@@ -166,6 +166,17 @@ struct Model {
   double* d_out = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t copy_events[kCopyBlocks] = {};
+  // small tables: the caller's (pageable) buffers are copied through pinned memory of the model, so
+  // that both transfers are plain DMA instead of the driver's staged path
+  static constexpr uint64_t kPinnedStagingStates = 1ull << 20;
+  double* h_pinned = nullptr;  // [2 * n_states]
+
+  // device copy of the last set of strided sums asked for (sequence observables are evaluated at
+  // thousands of output times with the same set)
+  std::vector<int64_t> obs_spec;
+  int64_t* d_obs_spec = nullptr;
+  double* d_obs_out = nullptr;
+  size_t obs_capacity = 0;
 
   BuildStats stats;
   int64_t launches_per_rhs = 0;
@@ -176,6 +187,22 @@ struct Model {
   // other, the later ones adding their flux to the result of the earlier ones (fixed order, so
   // results stay reproducible).  Each part keeps its own marginal tables and node weights.
   std::vector<std::unique_ptr<Model>> more;
+
+  // Small problems are launch-bound (about 20 kernels of a few microseconds per right-hand side):
+  // everything that depends on p only through the input pointer - marginal tables, leaf-world
+  // probabilities, all forest levels, of all parts - is captured once per input pointer into a
+  // CUDA graph and replayed.  The product stays a plain launch (its arguments change per call).
+  struct WeightsGraph {
+    const double* d_p = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t last_use = 0;
+  };
+  std::vector<WeightsGraph> weight_graphs;  // at most kMaxWeightGraphs, least recently used replaced
+  static constexpr size_t kMaxWeightGraphs = 16;
+  static constexpr uint64_t kGraphMaxStates = 1ull << 22;  // larger tables are bandwidth-bound
+  uint64_t graph_clock = 0;
+  int use_graphs = 1;
+  void drop_weight_graphs();  // after a change of launch options
 
   ~Model();
 };

@@ -172,9 +172,12 @@ struct Dop853 {
 
 namespace {
 
-double* dvec(uint64_t n) {
+// Solver vectors come from the stream-ordered pool, which keeps freed memory (the release threshold
+// is raised in build_model): creating a solver per integration then costs no driver allocation,
+// which takes anything from microseconds to milliseconds per call depending on the box.
+double* dvec(uint64_t n, cudaStream_t st) {
   void* p = nullptr;
-  TAPES_CUDA_CHECK(cudaMalloc(&p, std::max<uint64_t>(n, 1) * sizeof(double)));
+  TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<uint64_t>(n, 1) * sizeof(double), st));
   return (double*)p;
 }
 
@@ -293,12 +296,13 @@ Dop853* dop853_create(Model& m, PeerGroup* peer, const Dop853Tableau& tab, const
     s->max_step = max_step > 0 ? max_step : std::numeric_limits<double>::infinity();
     if (const char* f = std::getenv("TAPES_RK_FUSED")) s->fused = std::atoi(f) != 0;
     if (peer) s->fused = false;  // the stage update cannot ride on a product whose result is still partial
-    for (int i = 0; i < 3; ++i) s->ybuf[i] = dvec(s->n);
-    for (int i = 0; i < 16; ++i) s->K[i] = dvec(s->n);
+    for (int i = 0; i < 16; ++i) s->K[i] = nullptr;
     for (int i = 0; i < 7; ++i) s->F[i] = nullptr;
-    s->stage = dvec(s->n);
-    s->partial = dvec(2 * kReduceBlocks);
-    s->d_sums = dvec(4);
+    for (int i = 0; i < 3; ++i) s->ybuf[i] = dvec(s->n, s->st);
+    for (int i = 0; i < 16; ++i) s->K[i] = dvec(s->n, s->st);
+    s->stage = dvec(s->n, s->st);
+    s->partial = dvec(2 * kReduceBlocks, s->st);
+    s->d_sums = dvec(4, s->st);
     TAPES_CUDA_CHECK(cudaMemcpyAsync(s->y(), h_y0, s->n * sizeof(double), cudaMemcpyHostToDevice, s->st));
     fun(s, s->y(), s->K[0]);  // self.f = self.fun(self.t, self.y)
     s->h_abs = first_step > 0 ? first_step : select_initial_step(s);
@@ -312,13 +316,13 @@ Dop853* dop853_create(Model& m, PeerGroup* peer, const Dop853Tableau& tab, const
 
 void dop853_destroy(Dop853* s) {
   if (!s) return;
+  for (double* p : s->ybuf) if (p) cudaFreeAsync(p, s->st);
+  for (double* p : s->K) if (p) cudaFreeAsync(p, s->st);
+  for (double* p : s->F) if (p) cudaFreeAsync(p, s->st);
+  if (s->stage) cudaFreeAsync(s->stage, s->st);
+  if (s->partial) cudaFreeAsync(s->partial, s->st);
+  if (s->d_sums) cudaFreeAsync(s->d_sums, s->st);
   if (s->st) cudaStreamSynchronize(s->st);
-  for (double* p : s->ybuf) if (p) cudaFree(p);
-  for (double* p : s->K) if (p) cudaFree(p);
-  for (double* p : s->F) if (p) cudaFree(p);
-  if (s->stage) cudaFree(s->stage);
-  if (s->partial) cudaFree(s->partial);
-  if (s->d_sums) cudaFree(s->d_sums);
   delete s;
 }
 
@@ -378,7 +382,7 @@ void dop853_dense_eval(Dop853* s, double t, double* d_out) {  // DOP853._dense_o
   const unsigned grid = grid_for(s->n, kThreads);
   if (!s->dense_ready) {
     if (!s->have_F_mem) {
-      for (int i = 0; i < 7; ++i) s->F[i] = dvec(s->n);
+      for (int i = 0; i < 7; ++i) s->F[i] = dvec(s->n, s->st);
       s->have_F_mem = true;
     }
     const double h = s->h_previous;
@@ -414,26 +418,35 @@ void dop853_info(const Dop853* s, double out[6]) {
 void observe_strided(Model& m, const double* d_y, const int64_t* offset, const int64_t* stride,
                      const int64_t* count, int64_t n_obs, double* h_out) {
   if (n_obs <= 0) return;
-  int64_t* d_meta = nullptr;
-  double* d_out = nullptr;
-  TAPES_CUDA_CHECK(cudaMalloc((void**)&d_meta, 3 * n_obs * sizeof(int64_t)));
-  TAPES_CUDA_CHECK(cudaMalloc((void**)&d_out, n_obs * sizeof(double)));
-  try {
-    for (int64_t o = 0; o < n_obs; ++o)
-      if (offset[o] < 0 || stride[o] < 1 || count[o] < 0 ||
-          (count[o] > 0 && (uint64_t)(offset[o] + (count[o] - 1) * stride[o]) >= m.n_states))
-        throw std::runtime_error("observable outside the state table");
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(d_meta, offset, n_obs * 8, cudaMemcpyHostToDevice, m.stream));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(d_meta + n_obs, stride, n_obs * 8, cudaMemcpyHostToDevice, m.stream));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(d_meta + 2 * n_obs, count, n_obs * 8, cudaMemcpyHostToDevice, m.stream));
-    observe_kernel<<<(unsigned)n_obs, 1024, 0, m.stream>>>(d_y, d_meta, d_meta + n_obs, d_meta + 2 * n_obs, d_out);
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, n_obs * 8, cudaMemcpyDeviceToHost, m.stream));
-    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
-  } catch (...) {
-    cudaFree(d_meta); cudaFree(d_out);
-    throw;
+  for (int64_t o = 0; o < n_obs; ++o)
+    if (offset[o] < 0 || stride[o] < 1 || count[o] < 0 ||
+        (count[o] > 0 && (uint64_t)(offset[o] + (count[o] - 1) * stride[o]) >= m.n_states))
+      throw std::runtime_error("observable outside the state table");
+  // the set of sums is uploaded when it changes, not per call
+  std::vector<int64_t> spec((size_t)(3 * n_obs));
+  for (int64_t o = 0; o < n_obs; ++o) {
+    spec[(size_t)o] = offset[o]; spec[(size_t)(n_obs + o)] = stride[o]; spec[(size_t)(2 * n_obs + o)] = count[o];
   }
-  cudaFree(d_meta); cudaFree(d_out);
+  if (spec != m.obs_spec) {
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+    if ((size_t)n_obs > m.obs_capacity) {
+      if (m.d_obs_spec) cudaFree(m.d_obs_spec);
+      if (m.d_obs_out) cudaFree(m.d_obs_out);
+      m.d_obs_spec = nullptr; m.d_obs_out = nullptr; m.obs_capacity = 0; m.obs_spec.clear();
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_obs_spec, 3 * (size_t)n_obs * sizeof(int64_t)));
+      TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_obs_out, (size_t)n_obs * sizeof(double)));
+      m.obs_capacity = (size_t)n_obs;
+    }
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_obs_spec, spec.data(), spec.size() * sizeof(int64_t), cudaMemcpyHostToDevice,
+                                     m.stream));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));  // `spec` is pageable and about to change hands
+    m.obs_spec.swap(spec);
+  }
+  observe_kernel<<<(unsigned)n_obs, 1024, 0, m.stream>>>(d_y, m.d_obs_spec, m.d_obs_spec + n_obs,
+                                                        m.d_obs_spec + 2 * n_obs, m.d_obs_out);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+  TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_obs_out, (size_t)n_obs * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
 }
 
 }  // namespace tapes

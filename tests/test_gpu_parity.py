@@ -192,6 +192,35 @@ def test_python_programs(mt, oracle):
   assert not numpy.array_equal(before, after)
 
 
+def test_graph_replay_is_bit_identical(mt, device, p0_fixtures):
+  """Small problems replay the weight kernels from a CUDA graph captured per input pointer (host
+  entry point, stepper, any non-default stream); launching them one by one gives the same bits."""
+  import torch
+  tag, size_a, cl_k = 'ex4-chemical-turing', 9, 5
+  f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
+  model = device.DeviceModel(tag, cl_k)
+  tables = [configs.markov_table(size_a, cl_k, s) for s in (1, 2, 3)]
+  p0 = dense(p0_fixtures['ex4_a_idx'], p0_fixtures['ex4_a_val'], 9 ** 5)
+  kw = dict(tag=tag, size_a=size_a, cl_k=cl_k, p0=p0, ts=numpy.linspace(0, 30.0, 7), rtol=1e-10, atol=1e-12,
+            want_stats=True)
+  # more distinct input pointers than graphs are kept, each used twice (capture, then replay)
+  bufs = [torch.from_numpy(tables[i % 3]).cuda().clone() for i in range(24)]
+  side = torch.cuda.Stream()
+  torch.cuda.synchronize()
+  results = []
+  for flag in (1, 0):
+    model.set_option('graphs', flag)
+    host = [f(p, 0.0) for p in tables for _ in range(2)]
+    with torch.cuda.stream(side):
+      outs = [model.rhs(b).cpu().numpy() for _ in range(2) for b in bufs]
+    results.append((host + outs, mt.ode_integrate_device(**kw)))
+  model.set_option('graphs', 1)
+  for x, y in zip(results[0][0], results[1][0]):
+    assert numpy.array_equal(x, y)
+  assert results[0][1][1] == results[1][1][1] and numpy.array_equal(results[0][1][0], results[1][1][0])
+  assert numpy.array_equal(results[0][0][0], results[0][0][6])  # host path and device path agree as well
+
+
 def test_device_rhs_equals_host_rhs(mt, device):
   import torch
   p = configs.markov_table(5, 5, 1)
