@@ -20,6 +20,8 @@ SYMBOLS = (
     'tapes_peer_alloc', 'tapes_peer_open', 'tapes_peer_close', 'tapes_peer_free', 'tapes_peer_group_create',
     'tapes_peer_group_destroy', 'tapes_peer_rhs', 'tapes_peer_group_error', 'tapes_dop853_create_peer',
     'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts', 'tapes_register_program',
+    'tapes_mc_create', 'tapes_mc_destroy', 'tapes_mc_run', 'tapes_mc_window_counts', 'tapes_mc_fetch',
+    'tapes_mc_sample_ring', 'tapes_program_tree',
 )
 
 _lib = None
@@ -55,6 +57,20 @@ def load():
   lib.tapes_register_rules.argtypes = [ctypes.c_char_p, i64, i64] + [vp] * 7
   lib.tapes_register_program.restype = i32
   lib.tapes_register_program.argtypes = [ctypes.c_char_p, i64, i64] + [vp] * 6 + [i64, vp, i64, vp]
+  lib.tapes_mc_create.restype = vp
+  lib.tapes_mc_create.argtypes = [ctypes.c_char_p, i64, vp, i64, ctypes.c_uint64]
+  lib.tapes_mc_destroy.restype = None
+  lib.tapes_mc_destroy.argtypes = [vp]
+  lib.tapes_mc_run.restype = i32
+  lib.tapes_mc_run.argtypes = [vp, i64]
+  lib.tapes_mc_window_counts.restype = i32
+  lib.tapes_mc_window_counts.argtypes = [vp, i64, vp]
+  lib.tapes_mc_fetch.restype = i32
+  lib.tapes_mc_fetch.argtypes = [vp, vp]
+  lib.tapes_mc_sample_ring.restype = i32
+  lib.tapes_mc_sample_ring.argtypes = [i64, i64, vp, i64, ctypes.c_uint64, vp]
+  lib.tapes_program_tree.restype = i64
+  lib.tapes_program_tree.argtypes = [ctypes.c_char_p] + [vp] * 9
   lib.tapes_model.restype = vp
   lib.tapes_model.argtypes = [ctypes.c_char_p, i64]
   lib.tapes_model_part.restype = vp
@@ -198,6 +214,33 @@ def rule_parts(tag, cl_k, n_parts):
   check(lib.tapes_rule_parts(tag.encode(), cl_k, n_parts, owner.ctypes.data, cost.ctypes.data) == n_rules,
         'tapes_rule_parts')
   return owner, cost
+
+
+def program_tree(tag):
+  """Host-only: the decision tree of the body registered under `tag` (dict of arrays, the form
+  register_program takes)."""
+  lib = load()
+  sizes = numpy.zeros(3, dtype=numpy.int64)
+  n = lib.tapes_program_tree(tag.encode(), sizes.ctypes.data, *([None] * 8))
+  check(n >= 0, 'tapes_program_tree')
+  tree = {key: numpy.zeros(sizes[0], dtype=numpy.int32) for key in ('kind', 'a', 'b', 'c', 'first_child', 'first_weight')}
+  tree['child'] = numpy.zeros(sizes[1], dtype=numpy.int32)
+  tree['weight'] = numpy.zeros(sizes[2], dtype=numpy.float64)
+  n2 = lib.tapes_program_tree(tag.encode(), sizes.ctypes.data, *[tree[key].ctypes.data for key in (
+      'kind', 'a', 'b', 'c', 'first_child', 'first_weight', 'child', 'weight')])
+  check(n2 == n, 'tapes_program_tree')
+  return tree
+
+
+def sample_ring(size_a, cl_k, table, n_sites, seed):
+  """Host-only: a ring of n_sites symbols whose length-cl_k window statistics follow `table`."""
+  table = numpy.ascontiguousarray(numpy.asarray(table, dtype=numpy.float64).ravel())
+  if table.size != size_a ** cl_k:
+    raise ValueError(f'expected {size_a ** cl_k} table entries, got {table.size}')
+  tape = numpy.zeros(n_sites, dtype=numpy.uint8)
+  rc = load().tapes_mc_sample_ring(size_a, cl_k, table.ctypes.data, n_sites, seed, tape.ctypes.data)
+  check(rc == 0, 'tapes_mc_sample_ring')
+  return tape
 
 
 def register_program(tag, size_a, tree):

@@ -17,6 +17,7 @@
 #include "../../include/tapes_b200.h"
 #include "engine.h"
 #include "integrate.h"
+#include "montecarlo.h"
 #include "rules.h"
 #include "validate.h"
 
@@ -617,6 +618,92 @@ int tapes_check_table(int64_t alphabet, int64_t cl_k, const double* probs, int o
     if (staged) cudaFree(staged);
     fail(std::string("check_table: ") + ex.what());
     return 1;
+  }
+}
+
+void* tapes_mc_create(const char* tag, int64_t n_sites, const uint8_t* tape0, int64_t events_per_substep,
+                      uint64_t seed) {
+  try {
+    tapes::register_builtin_problems();
+    const tapes::Problem* prob = tapes::find_problem(tag);
+    if (!prob) throw std::runtime_error(std::string("unknown problem tag: ") + tag);
+    if (!tape0 || n_sites < 1 || events_per_substep < 1) throw std::runtime_error("bad ring or event count");
+    if (!ensure_cuda()) return nullptr;
+    const tapes::ProgramTree tree = tapes::trace_body(prob->body, prob->alphabet);
+    return (void*)tapes::mc_create(tree, prob->alphabet, (uint64_t)n_sites, tape0, (uint32_t)std::min<int64_t>(events_per_substep, 1 << 20),
+                                   seed);
+  } catch (const std::exception& ex) {
+    fail(std::string("mc_create: ") + ex.what());
+    return nullptr;
+  }
+}
+
+void tapes_mc_destroy(void* mc) { tapes::mc_destroy((tapes::MonteCarlo*)mc); }
+
+int tapes_mc_run(void* mc, int64_t n_substeps) {
+  if (!mc || n_substeps < 0) { fail("mc_run: bad argument"); return 1; }
+  try {
+    tapes::mc_run((tapes::MonteCarlo*)mc, (uint64_t)n_substeps);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("mc_run: ") + ex.what());
+    return 1;
+  }
+}
+
+int tapes_mc_window_counts(void* mc, int64_t cl_k, int64_t* counts) {
+  if (!mc || !counts) { fail("mc_window_counts: null argument"); return 1; }
+  try {
+    tapes::mc_window_counts((tapes::MonteCarlo*)mc, (int)cl_k, counts);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("mc_window_counts: ") + ex.what());
+    return 1;
+  }
+}
+
+int tapes_mc_fetch(void* mc, uint8_t* tape) {
+  if (!mc || !tape) { fail("mc_fetch: null argument"); return 1; }
+  try {
+    tapes::mc_fetch((tapes::MonteCarlo*)mc, tape);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("mc_fetch: ") + ex.what());
+    return 1;
+  }
+}
+
+int tapes_mc_sample_ring(int64_t alphabet, int64_t cl_k, const double* table, int64_t n_sites, uint64_t seed,
+                         uint8_t* tape) {
+  if (!table || !tape || n_sites < 1) { fail("mc_sample_ring: bad argument"); return 1; }
+  try {
+    tapes::mc_sample_ring((int)alphabet, (int)cl_k, table, (uint64_t)n_sites, seed, tape);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("mc_sample_ring: ") + ex.what());
+    return 1;
+  }
+}
+
+int64_t tapes_program_tree(const char* tag, int64_t* sizes3, int32_t* kind, int32_t* a, int32_t* b, int32_t* c,
+                           int32_t* first_child, int32_t* first_weight, int32_t* child, double* weight) {
+  try {
+    tapes::register_builtin_problems();
+    const tapes::Problem* prob = tapes::find_problem(tag);
+    if (!prob) throw std::runtime_error(std::string("unknown problem tag: ") + tag);
+    const tapes::ProgramTree t = tapes::trace_body(prob->body, prob->alphabet);
+    if (sizes3) { sizes3[0] = (int64_t)t.kind.size(); sizes3[1] = (int64_t)t.child.size(); sizes3[2] = (int64_t)t.weight.size(); }
+    if (kind) {
+      std::copy(t.kind.begin(), t.kind.end(), kind); std::copy(t.a.begin(), t.a.end(), a);
+      std::copy(t.b.begin(), t.b.end(), b); std::copy(t.c.begin(), t.c.end(), c);
+      std::copy(t.first_child.begin(), t.first_child.end(), first_child);
+      std::copy(t.first_weight.begin(), t.first_weight.end(), first_weight);
+      std::copy(t.child.begin(), t.child.end(), child); std::copy(t.weight.begin(), t.weight.end(), weight);
+    }
+    return (int64_t)t.kind.size();
+  } catch (const std::exception& ex) {
+    fail(std::string("program_tree: ") + ex.what());
+    return -1;
   }
 }
 

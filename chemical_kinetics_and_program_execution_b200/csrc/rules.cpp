@@ -295,4 +295,121 @@ Body body_from_program(ProgramTree t, int alphabet) {
   };
 }
 
+namespace {
+
+struct TraceFork { int ways; };
+
+struct TraceOp {
+  int32_t kind, a, b, c;
+  std::vector<double> weights;
+  bool operator==(const TraceOp& o) const {
+    return kind == o.kind && a == o.a && b == o.b && c == o.c && weights == o.weights;
+  }
+};
+
+// Records what a body does at the level of its own calls (not of the cell-by-cell unfolding).
+class Tracer : public Machine {
+ public:
+  Tracer(int A, const std::vector<int>& decisions) : A_(A), decisions_(decisions) {}
+  int read(Tape t, int cell) override {
+    auto it = known_[t].find(cell);
+    if (it != known_[t].end()) return it->second;
+    ops.push_back(TraceOp{ProgramTree::READ, (int32_t)t, cell, 0, {}});
+    const int s = decide(A_);
+    known_[t][cell] = s;
+    return s;
+  }
+  void write(Tape t, int cell, int symbol) override {
+    ops.push_back(TraceOp{ProgramTree::WRITE, (int32_t)t, cell, symbol, {}});
+    known_[t][cell] = symbol;
+  }
+  int pick(const double* weights, int n) override {
+    ops.push_back(TraceOp{ProgramTree::PICK, n, 0, 0, std::vector<double>(weights, weights + n)});
+    return decide(n);
+  }
+  std::vector<TraceOp> ops;
+
+ private:
+  int decide(int ways) {
+    if (pos_ >= decisions_.size()) throw TraceFork{ways};
+    return decisions_[pos_++];
+  }
+  int A_;
+  const std::vector<int>& decisions_;
+  size_t pos_ = 0;
+  std::map<int, int> known_[2];
+};
+
+struct TrieNode {
+  bool has_op = false;
+  TraceOp op;
+  std::vector<int> children;  // indices into the trie
+};
+
+}  // namespace
+
+ProgramTree trace_body(const Body& body, int alphabet, size_t max_nodes) {
+  std::vector<TrieNode> trie(1);
+  std::vector<std::vector<int>> todo;
+  todo.push_back({});
+  while (!todo.empty()) {
+    std::vector<int> decisions = std::move(todo.back());
+    todo.pop_back();
+    Tracer m(alphabet, decisions);
+    try {
+      body(m);
+    } catch (const TraceFork& f) {
+      for (int c = f.ways - 1; c >= 0; --c) {
+        std::vector<int> d = decisions;
+        d.push_back(c);
+        todo.push_back(std::move(d));
+      }
+      continue;
+    }
+    size_t node = 0, used = 0;
+    for (const TraceOp& op : m.ops) {
+      if (!trie[node].has_op) {
+        const int fan = op.kind == ProgramTree::READ ? alphabet : (op.kind == ProgramTree::WRITE ? 1 : op.a);
+        trie[node].has_op = true;
+        trie[node].op = op;
+        for (int j = 0; j < fan; ++j) {
+          trie[node].children.push_back((int)trie.size());
+          trie.emplace_back();
+        }
+        if (trie.size() > max_nodes) throw std::runtime_error("program tree too large");
+      } else if (!(trie[node].op == op)) {
+        throw std::runtime_error("the body is not deterministic");
+      }
+      node = (size_t)trie[node].children[op.kind == ProgramTree::WRITE ? 0 : (size_t)decisions[used++]];
+    }
+    if (trie[node].has_op) throw std::runtime_error("the body is not deterministic");
+  }
+  // flatten in preorder; every run ends in the shared END node, which comes last
+  std::vector<int> id(trie.size(), -1), order, stack(1, 0);
+  while (!stack.empty()) {
+    const int n = stack.back();
+    stack.pop_back();
+    if (!trie[(size_t)n].has_op) continue;
+    id[(size_t)n] = (int)order.size();
+    order.push_back(n);
+    for (size_t j = trie[(size_t)n].children.size(); j-- > 0;) stack.push_back(trie[(size_t)n].children[j]);
+  }
+  const int end_id = (int)order.size();
+  ProgramTree t;
+  const size_t n = order.size() + 1;
+  t.kind.assign(n, ProgramTree::END); t.a.assign(n, 0); t.b.assign(n, 0); t.c.assign(n, 0);
+  t.first_child.assign(n, 0); t.first_weight.assign(n, 0);
+  for (size_t i = 0; i < order.size(); ++i) {
+    const TrieNode& nd = trie[(size_t)order[i]];
+    t.kind[i] = nd.op.kind; t.a[i] = nd.op.a; t.b[i] = nd.op.b; t.c[i] = nd.op.c;
+    t.first_child[i] = (int32_t)t.child.size();
+    for (int ch : nd.children) t.child.push_back(trie[(size_t)ch].has_op ? id[(size_t)ch] : end_id);
+    if (nd.op.kind == ProgramTree::PICK) {
+      t.first_weight[i] = (int32_t)t.weight.size();
+      t.weight.insert(t.weight.end(), nd.op.weights.begin(), nd.op.weights.end());
+    }
+  }
+  return t;
+}
+
 }  // namespace tapes

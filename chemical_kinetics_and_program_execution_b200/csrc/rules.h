@@ -111,4 +111,10 @@ struct ProgramTree {
 // Throws std::runtime_error when the tree is malformed.
 Body body_from_program(ProgramTree tree, int alphabet);
 
+// The decision tree of any body (compiled, rewrite rules, or itself a tree): the body is run
+// against every combination of outcomes of its reads and choices.  Cells a body has read or written
+// are remembered, so a node exists only where an outcome is open.  Used by the Monte-Carlo
+// simulator, which interprets the tree on the device.
+ProgramTree trace_body(const Body& body, int alphabet, size_t max_nodes = (size_t)1 << 22);
+
 }  // namespace tapes

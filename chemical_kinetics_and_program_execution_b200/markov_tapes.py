@@ -12,7 +12,7 @@ Differences, all documented in INTEGRATION.md:
   * a failed library call raises RuntimeError (the reference drops into a Scheme REPL,
     framework/tapes_py_interface.scm:42-44);
   * additions: `ode_integrate_device`, `sequence_observable`, `model_stats`, `check_table`,
-    `register_rule_set`, `register_program`; device-resident dy/dt lives in device.py.
+    `register_rule_set`, `register_program`, `monte_carlo`; device-resident dy/dt lives in device.py.
 """
 
 import atexit
@@ -377,6 +377,52 @@ def check_table(spd, *, size_a=None, cl_k=None, eps_mpp=None, max_iterations=0, 
   if max_iterations > 0:
     result.update(power_distance=float(out[3]), last_change=float(out[4]), iterations=int(out[5]))
   return result
+
+
+def monte_carlo(*, tag, size_a, cl_k, ts, p0=None, tape0=None, n_sites=1 << 20, events_per_substep=None, seed=0,
+                return_tape=False):
+  """Monte-Carlo estimate of the subsequence table over time: the problem's program is run at
+  random positions of one long ring tape, every site being visited at rate 1, and the length-cl_k
+  window frequencies are read off at the times `ts` (csrc/montecarlo.cu).  An independent check of
+  the closure behind `ode_integrate*`: where the closure is exact (e.g. ex1) the two agree within
+  the statistical error ~ n_sites**-0.5, elsewhere the difference is what the closure neglects.
+  The reference has such a simulation for the ferromagnet only
+  (examples/ex2_ferromagnet_mc.py:46-122).
+
+  The ring starts as `tape0` (symbols, one per site) or is sampled from the table `p0`.  Events
+  happen `events_per_substep` at a time (default n_sites / 1000, i.e. dt = 0.001).  Returns
+  [len(ts), size_a**cl_k] frequencies shaped like `ode_integrate`'s output (and the final ring with
+  return_tape=True)."""
+  ts = numpy.asarray(ts, dtype=numpy.float64)
+  if ts.ndim != 1 or ts.size < 1 or (numpy.diff(ts) < 0).any() or ts[0] < 0:
+    raise ValueError('ts must be a non-decreasing sequence of non-negative times')
+  if tape0 is None:
+    if p0 is None:
+      raise ValueError('give the initial ring (tape0) or a table to sample it from (p0)')
+    tape0 = _lib.sample_ring(size_a, cl_k, _checked_p0(p0, size_a, cl_k), int(n_sites), int(seed))
+  tape0 = numpy.ascontiguousarray(numpy.asarray(tape0, dtype=numpy.uint8).ravel())
+  n_sites = tape0.size
+  if events_per_substep is None:
+    events_per_substep = max(1, n_sites // 1000)
+  mc = u_lib.tapes_mc_create(tag.encode(), n_sites, tape0.ctypes.data, int(events_per_substep), int(seed))
+  _lib.check(bool(mc), 'tapes_mc_create')
+  out = numpy.zeros((ts.size, size_a ** cl_k), dtype=numpy.float64)
+  counts = numpy.zeros(size_a ** cl_k, dtype=numpy.int64)
+  done = 0
+  try:
+    for i, t in enumerate(ts):
+      target = int(round(t * n_sites / events_per_substep))
+      _lib.check(u_lib.tapes_mc_run(mc, target - done) == 0, 'tapes_mc_run')
+      done = target
+      _lib.check(u_lib.tapes_mc_window_counts(mc, cl_k, counts.ctypes.data) == 0, 'tapes_mc_window_counts')
+      out[i] = counts / float(n_sites)
+    if return_tape:
+      tape = numpy.zeros(n_sites, dtype=numpy.uint8)
+      _lib.check(u_lib.tapes_mc_fetch(mc, tape.ctypes.data) == 0, 'tapes_mc_fetch')
+      return out, tape
+  finally:
+    u_lib.tapes_mc_destroy(mc)
+  return out
 
 
 def _run_validation():

@@ -224,6 +224,32 @@ int tapes_observe(void* model, const double* d_y, const int64_t* offset, const i
 int tapes_check_table(int64_t alphabet, int64_t cl_k, const double* probs, int on_device, double eps_mpp,
                       int64_t max_iterations, double tolerance, double* out6);
 
+/* ---- Monte-Carlo simulation of a registered problem on one long ring tape: an independent check
+ * of the closure behind the master equation (the reference has one for the ferromagnet only,
+ * examples/ex2_ferromagnet_mc.py:46-122).  An event puts the program head and the data head on two
+ * random sites and runs the program there; events_per_substep events happen at once and a sub-step
+ * advances time by events_per_substep / n_sites (every site is visited at rate 1, the normalisation
+ * of compute-dy/dt).  Deterministic given the seed; rules in csrc/montecarlo.cu. ---------------- */
+
+/* tape0: HOST array of n_sites symbols (one byte each, alphabet <= 256).  NULL on failure. */
+void* tapes_mc_create(const char* tag, int64_t n_sites, const uint8_t* tape0, int64_t events_per_substep,
+                      uint64_t seed);
+void tapes_mc_destroy(void* mc);
+int tapes_mc_run(void* mc, int64_t n_substeps);
+/* counts: HOST array of A^cl_k entries: occurrences of every length-cl_k window on the ring. */
+int tapes_mc_window_counts(void* mc, int64_t cl_k, int64_t* counts);
+/* Copies the ring to a HOST array of n_sites bytes. */
+int tapes_mc_fetch(void* mc, uint8_t* tape);
+/* Host-only: a ring whose length-cl_k window statistics follow `table` (A^cl_k doubles). */
+int tapes_mc_sample_ring(int64_t alphabet, int64_t cl_k, const double* table, int64_t n_sites, uint64_t seed,
+                         uint8_t* tape);
+
+/* Host-only: the decision tree of the body registered under `tag` in the array form of
+ * tapes_register_program (any problem: compiled, rewrite rules, or registered as a tree).  Call with
+ * kind == NULL to get the lengths in sizes3 = {nodes, children, weights}.  Returns the node count. */
+int64_t tapes_program_tree(const char* tag, int64_t* sizes3, int32_t* kind, int32_t* a, int32_t* b, int32_t* c,
+                           int32_t* first_child, int32_t* first_weight, int32_t* child, double* weight);
+
 /* Host-only (no GPU needed): the flux-rule table of (tag, cl_k).  Call with all pointers NULL to
  * get sizes: returns the number of rules and stores the total step count in *n_steps. Arrays:
  * rule_ptr[n_rules + 1]; per step kind, length, long_index, short_index, prob; per rule and tape
