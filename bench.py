@@ -6,13 +6,14 @@ multiverse (BASELINE.json: last config).
 
 One "step" is one full right-hand side over the whole state table: marginal tables, leaf-world
 probabilities, every level of the window-extension forest (the p-dependent re-evaluation of the
-rate structure) and the CSR product S*w.  With N > 1 the rule set is dealt to the ranks
-(parallel.py) and a step also contains the flux reduce-scatter and the table all-gather.
+rate structure) and the CSR product S*w.  With N > 1 every rank gets its own 24 rules (weak
+scaling) and a step also contains the flux exchange, by default fused into the product kernel over
+NVLink peer memory (parallel.PeerExchangeRhs).
 
 `value` is algorithmic GB/s of the whole step (bytes defined in DESIGN.md, "Algorithmic bytes"):
   step_bytes = 28 * nnz + 24 * n + 8 * n * (1 + 2 / (A - 1))
-`roofline` describes the dominant kernel, the product S*w (flux_slices_kernel, 4.3 ms per launch;
-the 13 level_kernel launches of a step are at most 1 ms each and are summarised in
+`roofline` describes the dominant kernel, the product S*w (flux_slices_kernel, 3.7 ms per launch;
+the 13 level_kernel launches of a step are at most 0.9 ms each and are summarised in
 `roofline_levels`), against the measured HBM peak, with the survey's CSR byte count
   spmv_bytes = 12 * nnz + 16 * n
 The kernel streams a compressed form of the CSR (runs of 32 states), so its DRAM traffic

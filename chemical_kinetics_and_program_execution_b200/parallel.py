@@ -1,13 +1,20 @@
-"""Multi-GPU sharding of the master-equation step (one process per GPU, torch.distributed).
+"""Multi-GPU evaluation of the master-equation step (one process per GPU, torch.distributed for
+set-up and barriers).
 
-The window-extension forests of different flux rules are independent, so the rule set is dealt
-round-robin to the ranks: rank g builds and evaluates only its rules over the full state space
-and produces a partial dy/dt.  States are owned block-cyclically: the table is cut into row
-chunks and every chunk into one block per rank.  As soon as the product for a chunk has been
-launched, a reduce-scatter sums that chunk's partial flux into the owners' blocks (the flux
-exchange) and an all-gather returns the owners' results, both asynchronously, so the exchange of
-chunk c runs under the product of chunks c+1...  Nothing here touches the GPU directly, so the
-plumbing is testable with the gloo backend on CPU.
+The window-extension forests of different flux rules are independent, so the rules are dealt to
+the ranks: rank g builds and evaluates only its share over the full state space and produces a
+partial dy/dt; the partial results are summed by one of the exchanges below.  The library deals any
+registered problem itself (device.DeviceModel(tag, k, part=(rank, world)), tapes_model_part); the
+helpers here do the same for rewrite-rule dicts, which the weak-scaling benchmark uses to give every
+rank a rotated copy of the same rules.
+
+  PeerExchangeRhs          the default: the exchange runs inside the product kernel over NVLink peer
+                           memory (tapes_peer_rhs), no NCCL kernel on the data path
+  OverlappedAllReduceRhs   NCCL all-reduce of dy/dt in row blocks, overlapped with the product
+  OverlappedRhs, ShardedRhs   NCCL reduce-scatter + all-gather, with and without overlap
+
+The NCCL variants touch the GPU only through torch, so their plumbing is testable with the gloo
+backend on CPU (tests/test_parallel.py).
 """
 
 import numpy
