@@ -44,14 +44,22 @@ UNIT = 'GB/s'
 
 
 # stdout carries exactly one JSON line: libraries that print there (NCCL's version banner) are sent
-# to stderr by pointing file descriptor 1 at it; the line itself goes to the original descriptor
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
+# to stderr by pointing file descriptor 1 at it; the line itself goes to the original descriptor.
+# Done by main() only, so that scripts importing this module keep their stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+  global _REAL_STDOUT
+  if _REAL_STDOUT is None:
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
 
 
 def emit(line):
   sys.stdout.flush()
-  os.write(_REAL_STDOUT, (json.dumps(line) + '\n').encode())
+  os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + '\n').encode())
 
 
 def parse_args():
@@ -552,6 +560,7 @@ def run_b200(args):
 
 def main():
   args = parse_args()
+  claim_stdout()
   if args.impl == 'reference':
     run_reference(args)
   else:

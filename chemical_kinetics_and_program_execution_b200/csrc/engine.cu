@@ -122,7 +122,7 @@ struct Frontier {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c, HashSet hs,
                                                             uint32_t* __restrict__ lflag, uint32_t* __restrict__ tflag,
-                                                            uint8_t* __restrict__ kflag, uint64_t* __restrict__ unique,
+                                                            uint32_t* __restrict__ keyslot, uint64_t* __restrict__ unique,
                                                             unsigned long long* __restrict__ n_unique) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < f.n;
@@ -146,11 +146,12 @@ __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c
     }
     lflag[i] = left;
     tflag[i] = (fl & FL_TERM) ? 1u : 0u;
-    kflag[i] = haskey ? 1 : 0;
   }
   // keys seen for the first time are compacted into the new frontier's group list as they are
   // inserted (block scan, one atomic per block); the list is put in canonical order afterwards
-  const bool fresh = hash_insert_warp(hs, haskey, key, pa);
+  uint32_t slot = 0;
+  const bool fresh = hash_insert_warp(hs, haskey, key, pa, &slot);
+  if (valid) keyslot[i] = haskey ? slot : kNoRank;  // emit_kernel finds the key's group without probing
   block_append_u64(fresh, key, unique, n_unique);
 }
 
@@ -167,12 +168,13 @@ __global__ void rank_slots_kernel(const uint64_t* __restrict__ sorted_keys, uint
 // (x * n_left_parents + parent rank): consecutive nodes then have consecutive table indices.
 // ---------------------------------------------------------------------------------------------
 __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ lflag,
-                            const uint32_t* __restrict__ tflag, const uint8_t* __restrict__ kflag,
+                            const uint32_t* __restrict__ tflag, const uint32_t* __restrict__ keyslot,
                             const uint64_t* __restrict__ lrank, const uint64_t* __restrict__ trank,
                             uint64_t n_left_parents, HashSet hs, Frontier next, uint32_t* __restrict__ lp_gid,
                             uint32_t* __restrict__ lp_io, uint8_t* __restrict__ lp_len,
                             uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
-                            uint32_t* __restrict__ keyrank) {
+                            uint32_t* __restrict__ keyrank, uint32_t* __restrict__ gmin, uint32_t* __restrict__ gmax,
+                            uint32_t* __restrict__ gcnt) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.n) return;
   const uint8_t meta = f.meta[i];
@@ -211,12 +213,60 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
     edge_row[e] = io;     edge_val[e] = gid | kOutflowBit;   // -w at the original window
     edge_row[e + 1] = ia; edge_val[e + 1] = gid;             // +w at the adjusted window
   }
-  if (kflag[i]) {
-    const uint64_t key = ((uint64_t)seed << 32) | (io % c.M);
-    keyrank[i] = hs.ranks[hash_slot(hs, key)];
+  const uint32_t slot = keyslot[i];
+  if (slot != kNoRank) {
+    // the node is a parent of prefix group g: parent lists are almost always arithmetic progressions
+    // of node ids, which smallest id, largest id and count describe completely
+    const uint32_t g = hs.ranks[slot];
+    keyrank[i] = g;
+    atomicMin(&gmin[g], gid);
+    atomicMax(&gmax[g], gid);
+    atomicAdd(&gcnt[g], 1u);
   } else {
     keyrank[i] = kNoRank;
   }
+}
+
+// (first, stride, count) of every group from the extremes of its parent ids; a group whose extremes
+// cannot belong to a progression of `count` ids is counted as irregular.  facts: [1] irregular
+// groups, [2] parents of all groups.
+__global__ void derive_progressions_kernel(const uint32_t* __restrict__ gmin, const uint32_t* __restrict__ gmax,
+                                           const uint32_t* __restrict__ gcnt, uint64_t n_groups,
+                                           uint32_t* __restrict__ first, uint32_t* __restrict__ stride,
+                                           uint32_t* __restrict__ count, unsigned long long* __restrict__ facts) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t n = 0;
+  bool bad = false;
+  if (g < n_groups) {
+    n = gcnt[g];
+    const uint32_t lo = n ? gmin[g] : 0u, span = n ? gmax[g] - lo : 0u;
+    const uint32_t d = n > 1 ? span / (n - 1) : 0u;
+    bad = n > 1 && (d == 0 || span % (n - 1) != 0);
+    first[g] = lo; stride[g] = d; count[g] = n;
+  }
+  unsigned long long parents = n;
+  for (int o = 16; o > 0; o >>= 1) parents += __shfl_down_sync(0xffffffffu, parents, o);
+  const unsigned bad_lanes = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (parents) atomicAdd(&facts[2], parents);
+    if (bad_lanes) atomicAdd(&facts[1], (unsigned long long)__popc(bad_lanes));
+  }
+}
+
+// Every parent must sit on its group's progression; together with distinct ids, matching extremes
+// and the count this makes the parent set exactly {first + j * stride : j < count}.
+__global__ void verify_progressions_kernel(const uint32_t* __restrict__ keyrank, uint64_t n, uint64_t id_base,
+                                           const uint32_t* __restrict__ first, const uint32_t* __restrict__ stride,
+                                           unsigned long long* __restrict__ facts) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (i < n && keyrank[i] != kNoRank) {
+    const uint32_t g = keyrank[i], id = (uint32_t)(id_base + i);
+    const uint32_t d = stride[g], off = id - first[g];
+    bad = d ? (off % d != 0) : (off != 0);
+  }
+  const unsigned bad_lanes = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad_lanes) atomicAdd(&facts[1], (unsigned long long)__popc(bad_lanes));
 }
 
 // The A right children of every prefix group (tm.scm:1310-1322), group-major so that consecutive
@@ -313,25 +363,6 @@ __global__ void __launch_bounds__(kThreads) group_sort_long_kernel(const uint64_
       __syncthreads();
     }
   }
-}
-
-// Parent lists are almost always arithmetic progressions of node ids (the parents of a prefix group
-// differ in the dropped, most significant digit only): store (first, stride, count) and count the
-// groups that are not.
-__global__ void group_progression_kernel(const uint64_t* __restrict__ ptr, const uint32_t* __restrict__ parents,
-                                         uint64_t n_groups, uint32_t* __restrict__ first,
-                                         uint32_t* __restrict__ stride, uint32_t* __restrict__ count,
-                                         unsigned long long* __restrict__ irregular) {
-  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_groups) return;
-  const uint64_t lo = ptr[g], hi = ptr[g + 1];
-  const uint32_t n = (uint32_t)(hi - lo);
-  const uint32_t f = n ? parents[lo] : 0u;
-  const uint32_t d = n > 1 ? parents[lo + 1] - f : 0u;
-  bool ok = true;
-  for (uint64_t e = lo + 2; e < hi; ++e) ok = ok && (parents[e] - parents[e - 1] == d);
-  first[g] = f; stride[g] = d; count[g] = n;
-  if (!ok) atomicAdd(irregular, 1ull);
 }
 
 // Fused right chain, build side.  A group may own its parents when they are right children of the
@@ -935,25 +966,25 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     while (cap < 2 * n) cap <<= 1;
     s1.reset();
     const size_t i_keys = s1.want(cap * 8), i_vals = s1.want(cap * 4), i_ranks = s1.want(cap * 4);
-    const size_t i_lflag = s1.want(n * 4), i_tflag = s1.want(n * 4), i_kflag = s1.want(n);
+    const size_t i_lflag = s1.want(n * 4), i_tflag = s1.want(n * 4), i_kflag = s1.want(n * 4);
     const size_t i_lrank = s1.want((n + 1) * 8), i_trank = s1.want((n + 1) * 8);
     const size_t i_scan = s1.want(scan_tmp_elems(std::max<uint64_t>(n, 256ull * 1184)) * 8);
-    const size_t i_unique = s1.want(n * 8), i_counters = s1.want(16);
+    const size_t i_unique = s1.want(n * 8), i_counters = s1.want(32);
     s1.commit();
     HashSet hs;
     hs.keys = s1.at<uint64_t>(i_keys); hs.vals = s1.at<uint32_t>(i_vals); hs.ranks = s1.at<uint32_t>(i_ranks);
     hs.mask = cap - 1;
     uint32_t* lflag = s1.at<uint32_t>(i_lflag);
     uint32_t* tflag = s1.at<uint32_t>(i_tflag);
-    uint8_t* kflag = s1.at<uint8_t>(i_kflag);
+    uint32_t* keyslot = s1.at<uint32_t>(i_kflag);
     uint64_t* lrank = s1.at<uint64_t>(i_lrank);
     uint64_t* trank = s1.at<uint64_t>(i_trank);
     uint64_t* scan_tmp = s1.at<uint64_t>(i_scan);
     uint64_t* keys_a = s1.at<uint64_t>(i_unique);
-    unsigned long long* counters = s1.at<unsigned long long>(i_counters);  // [0] unique keys, [1] irregular groups
+    unsigned long long* counters = s1.at<unsigned long long>(i_counters);  // [0] unique keys, [1] irregular groups, [2] parents
     TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
-    TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16, st));
-    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, tflag, kflag, keys_a, counters);
+    TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 32, st));
+    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, tflag, keyslot, keys_a, counters);
     exclusive_scan_u32(lflag, n, lrank, scan_tmp, st);
     exclusive_scan_u32(tflag, n, trank, scan_tmp, st);
     uint64_t h_tot[3];
@@ -977,6 +1008,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     plan_frontier(s2, next.n, fi);
     const size_t i_keys_b = s2.want(NG * 8), i_rh = s2.want(256ull * plan.blocks * 4);
     const size_t i_ro = s2.want((256ull * plan.blocks + 1) * 8), i_keyrank = s2.want(n * 4), i_cnt = s2.want(NG * 4);
+    const size_t i_gmin = s2.want(NG * 4), i_gmax = s2.want(NG * 4);
     const size_t i_consumed = s2.want((size_t)cur_level.n_groups * 4);
     const size_t i_gptr = s2.want((NG + 1) * 8), i_gparents = s2.want(n * 4);  // parent lists (at most n parents)
     s2.commit();
@@ -995,41 +1027,49 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       next_level.lp_io = dkeep<uint32_t>(m, NL);
       next_level.lp_len = dkeep<uint8_t>(m, NL);
     }
+    uint32_t* gmin = s2.at<uint32_t>(i_gmin);
+    uint32_t* gmax = s2.at<uint32_t>(i_gmax);
+    uint32_t* gcnt = s2.at<uint32_t>(i_cnt);
+    if (NG) {
+      TAPES_CUDA_CHECK(cudaMemsetAsync(gmin, 0xff, NG * 4, st));
+      TAPES_CUDA_CHECK(cudaMemsetAsync(gmax, 0, NG * 4, st));
+      TAPES_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, NG * 4, st));
+    }
     EdgeChunk ec{nullptr, nullptr, 2 * NT};
     if (NT) {  // one allocation for both arrays, owned by the list from here on
       ec.row = dtemp<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT;
       edge_chunks.push_back(ec);
     }
-    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, kflag, lrank, trank,
+    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, keyslot, lrank, trank,
                                                           NL, hs, next, next_level.lp_gid, next_level.lp_io,
-                                                          next_level.lp_len, ec.row, ec.val, keyrank);
+                                                          next_level.lp_len, ec.row, ec.val, keyrank, gmin, gmax, gcnt);
     if (NG) {
       next_level.g_prefix = dkeep<uint32_t>(m, NG);
       emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
                                                                      NL * (uint64_t)m.A, next_level.g_prefix);
-      // parent lists of the prefix groups
-      uint32_t* cnt = s2.at<uint32_t>(i_cnt);
-      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
-      group_count_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cnt);
-      uint64_t* g_ptr = s2.at<uint64_t>(i_gptr);
-      uint32_t* g_parents = s2.at<uint32_t>(i_gparents);
-      exclusive_scan_u32(cnt, NG, g_ptr, scan_tmp, st);
-      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
-      group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base, g_ptr, cnt, g_parents);
-      sort_groups(g_ptr, NG, g_parents, st);
+      // parent lists of the prefix groups: as progressions (first, stride, count) when every list is
+      // one - found from the extremes and counts emit_kernel collected, then checked parent by parent
       next_level.g_first = dkeep<uint32_t>(m, NG);
       next_level.g_stride = dkeep<uint32_t>(m, NG);
       next_level.g_count = dkeep<uint32_t>(m, NG);
-      group_progression_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
-          g_ptr, g_parents, NG, next_level.g_first, next_level.g_stride, next_level.g_count, counters + 1);
-      unsigned long long h_counts[2] = {0, 0};  // parents, irregular groups
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_counts[0], g_ptr + NG, 8, cudaMemcpyDeviceToHost, st));
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_counts[1], counters + 1, 8, cudaMemcpyDeviceToHost, st));
+      derive_progressions_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
+          gmin, gmax, gcnt, NG, next_level.g_first, next_level.g_stride, next_level.g_count, counters);
+      verify_progressions_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(
+          keyrank, n, cur_level.base, next_level.g_first, next_level.g_stride, counters);
+      unsigned long long h_counts[2] = {0, 0};  // irregular groups or parents off their progression, parents
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(h_counts, counters + 1, 16, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      const uint64_t n_par = h_counts[0];
+      const uint64_t n_par = h_counts[1];
       next_level.n_group_parents = n_par;
-      if (h_counts[1] != 0 || std::getenv("TAPES_KEEP_PARENT_LISTS")) {
-        // some list is not a progression: this level keeps its explicit lists
+      if (h_counts[0] != 0 || std::getenv("TAPES_KEEP_PARENT_LISTS")) {
+        // some list is not a progression: this level keeps explicit lists, ascending inside each group
+        uint32_t* cnt = gcnt;
+        uint64_t* g_ptr = s2.at<uint64_t>(i_gptr);
+        uint32_t* g_parents = s2.at<uint32_t>(i_gparents);
+        exclusive_scan_u32(cnt, NG, g_ptr, scan_tmp, st);
+        TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
+        group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base, g_ptr, cnt, g_parents);
+        sort_groups(g_ptr, NG, g_parents, st);
         next_level.g_first = next_level.g_stride = next_level.g_count = nullptr;  // their memory stays in the arena
         next_level.g_ptr = dkeep<uint64_t>(m, NG + 1);
         next_level.g_parents = dkeep<uint32_t>(m, n_par);

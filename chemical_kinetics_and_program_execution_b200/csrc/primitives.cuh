@@ -163,15 +163,18 @@ __device__ __forceinline__ uint64_t hash_mix(uint64_t x) {
 }
 
 // All 32 lanes must call this; `active` says whether the lane has a key.  Returns true in the
-// lane that claimed an empty slot for a key not seen before.
+// lane that claimed an empty slot for a key not seen before; *slot receives the slot of the lane's
+// key (every active lane, so that later passes need not probe again).
 __device__ __forceinline__ bool hash_insert_warp(const HashSet& hs, bool active, uint64_t key,
-                                                 uint32_t val) {
+                                                 uint32_t val, uint32_t* slot) {
   const unsigned lane = threadIdx.x & 31;
   const unsigned peers = __match_any_sync(0xffffffffu, active ? key : (kEmptyKey - lane));
-  const bool leader = active && ((__ffs(peers) - 1) == (int)lane);
+  const int leader_lane = __ffs(peers) - 1;
+  const bool leader = active && (leader_lane == (int)lane);
   bool fresh = false;
+  uint64_t h = 0;
   if (leader) {
-    uint64_t h = hash_mix(key) & hs.mask;
+    h = hash_mix(key) & hs.mask;
     for (;;) {
       unsigned long long prev =
           atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey,
@@ -181,6 +184,7 @@ __device__ __forceinline__ bool hash_insert_warp(const HashSet& hs, bool active,
       h = (h + 1) & hs.mask;
     }
   }
+  *slot = __shfl_sync(0xffffffffu, (uint32_t)h, leader_lane);  // capacity is at most 2^31
   return fresh;
 }
 
