@@ -487,6 +487,17 @@ def run_b200(args):
                          dram_frac=(lv_traffic / (phase[1] * 1e-3) / 1e9 / peak) if lv_traffic else None,
                          algorithmic_bytes_per_step=level_bytes(info), kernel_ms=float(phase[1]))
 
+  # the expansion, once per structure: SURVEY.md section 8(d) counts about 85 algorithmic bytes per
+  # expanded state (48 B record written, 32 B of hash-slot traffic, the record read again shared by
+  # its children); time = this rank's device expansion without the driver's allocation time
+  expand_rank_s = max((timing['device_expand_ms'] - timing['expand_alloc_ms']) * 1e-3, 1e-9)
+  expand_gbs = 85.0 * info['n_nodes'] / expand_rank_s / 1e9
+  roofline_expand = dict(bound='hbm', kernel='classify_kernel + emit_kernel + emit_groups_kernel + scans + key sort '
+                         '(frontier expansion, once per structure; hash inserts and compaction are latency- and '
+                         'atomics-bound rather than streaming)', achieved=expand_gbs, peak=peak, unit='GB/s',
+                         frac=expand_gbs / peak, traffic=None, algorithmic_bytes_per_state=85.0,
+                         states=info['n_nodes'], seconds=expand_rank_s)
+
   # end to end through the reference-facing C ABI call with pinned HOST buffers
   e2e = None
   if rank == 0 and world == 1:
@@ -542,7 +553,7 @@ def run_b200(args):
                 clocks=clocks.summary(), e2e=e2e,
                 gpu_launches=(int(launches_total / world)
                               + (4 * max(args.chunks, 1) + 1 if world > 1 and args.exchange == 'peer' else 0)) * args.steps,
-                roofline=roofline, roofline_levels=roofline_levels, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
+                roofline=roofline, roofline_levels=roofline_levels, roofline_expand=roofline_expand, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
                 exchange_exposed_ms=(ms_step - max(rank_ms)) if rank_ms else None,
                 states_expanded_per_s=expanded_total / max(expand_kernels_s, 1e-9),
                 states_expanded_per_s_incl_driver_alloc=expanded_total / max(expand_s, 1e-9),
