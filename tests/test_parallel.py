@@ -132,3 +132,35 @@ def test_two_rank_rhs_equals_unsplit(tmp_path, oracle):
   p = configs.markov_table(SIZE_A, CL_K, 3)
   want = oracle.compute_dy_dt('par-test-full', CL_K, p, mode=oracle.MERGED)
   assert abs(got - want).max() <= 1e-14 * abs(want).max()
+
+
+def _parts_worker(rank, world, port, result_path):
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  from chemical_kinetics_and_program_execution_b200 import _lib
+  report = {}
+  for tag, cl_k in (('ex4-chemical-turing', 5), ('ex5-msrtf-machine', 5), ('ex3-copolymerization', 12)):
+    owner, cost = _lib.rule_parts(tag, cl_k, world)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (owner.tolist(), cost.tolist()))
+    assert all(e == everyone[0] for e in everyone)  # every rank deals the same way without talking
+    mine = numpy.nonzero(owner == rank)[0]
+    counts = [None] * world
+    dist.all_gather_object(counts, (len(mine), float(cost[mine].sum())))
+    assert sum(c[0] for c in counts) == len(owner)
+    loads = [c[1] for c in counts]
+    assert max(loads) <= sum(loads) / world + cost.max()
+    report[tag] = loads
+  if rank == 0:
+    numpy.save(result_path, numpy.array([report[t] for t in sorted(report)]))
+  dist.destroy_process_group()
+
+
+def test_library_deals_registered_problems_consistently_on_two_ranks(tmp_path):
+  """tapes_model_part's dealing (host-only part, no GPU): two processes compute it independently
+  and must agree on every flux rule's owner, with balanced loads."""
+  path = str(tmp_path / 'loads.npy')
+  mp.spawn(_parts_worker, args=(2, _free_port(), path), nprocs=2, join=True)
+  loads = numpy.load(path)
+  assert loads.shape == (3, 2) and (loads > 0).all()
+  assert (abs(loads[:, 0] - loads[:, 1]) <= 0.1 * loads.sum(axis=1)).all()
