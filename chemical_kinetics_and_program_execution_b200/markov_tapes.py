@@ -403,7 +403,7 @@ def monte_carlo(*, tag, size_a, cl_k, ts, p0=None, tape0=None, n_sites=1 << 20, 
   tape0 = numpy.ascontiguousarray(numpy.asarray(tape0, dtype=numpy.uint8).ravel())
   n_sites = tape0.size
   if events_per_substep is None:
-    events_per_substep = max(1, n_sites // 1000)
+    events_per_substep = max(1, min(n_sites // 1000, (1 << 20) - 1))  # the library takes fewer than 2^20
   mc = u_lib.tapes_mc_create(tag.encode(), n_sites, tape0.ctypes.data, int(events_per_substep), int(seed))
   _lib.check(bool(mc), 'tapes_mc_create')
   out = numpy.zeros((ts.size, size_a ** cl_k), dtype=numpy.float64)
