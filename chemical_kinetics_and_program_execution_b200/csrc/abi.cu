@@ -425,6 +425,7 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
     field = &tapes::Model::flux_unroll;
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) field = &tapes::Model::level_unroll;
   if (std::strcmp(key, "interleave_seeds") == 0 && (value == 0 || value == 1)) field = &tapes::Model::interleave_seeds;
+  if (std::strcmp(key, "ratio_table") == 0 && (value == 0 || value == 1)) field = &tapes::Model::ratio_table;
   if (std::strcmp(key, "graphs") == 0 && (value == 0 || value == 1)) {
     cudaStreamSynchronize(head.stream);
     head.drop_weight_graphs();
@@ -436,6 +437,7 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
     head.drop_weight_graphs();  // captured launches carry the old setting
     head.*field = (int)value;
     for (auto& part : head.more) (*part).*field = (int)value;
+    head.launches_per_rhs = tapes::rhs_launch_count(head);
     return 0;
   }
   fail(std::string("unknown option or value: ") + key);

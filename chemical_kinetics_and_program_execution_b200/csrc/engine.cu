@@ -491,11 +491,37 @@ __device__ __forceinline__ double child_weight(double w_parent, double p_long, d
   return r > 0.0 ? w_parent * r : 0.0;
 }
 
+// The ratio of a right extension depends on the window alone: p[i] against marg_{k-1}[i / A] (the
+// window without its last cell).  It is evaluated once per step for the whole table; the chains of all
+// seeds and levels then read one number and multiply instead of reading two and dividing.
+__device__ __forceinline__ double extension_ratio(double p_long, double p_short) {
+  return p_long == 0.0 ? 0.0 : p_long / fmax(p_long, p_short);
+}
+__device__ __forceinline__ double weight_from_ratio(double w_parent, double r) { return r > 0.0 ? w_parent * r : 0.0; }
+
+constexpr int kRatioBatch = 4;  // entries per thread: loads and divisions of a batch overlap
+__global__ void __launch_bounds__(kThreads) ratio_right_kernel(const double* __restrict__ p, const double* __restrict__ short_table,
+                                                               double* __restrict__ ratio, uint64_t n, uint32_t A) {
+  const uint64_t base = (uint64_t)blockIdx.x * (kThreads * kRatioBatch) + threadIdx.x;
+  double p_long[kRatioBatch], p_short[kRatioBatch];
+#pragma unroll
+  for (int u = 0; u < kRatioBatch; ++u) {
+    const uint64_t i = base + (uint64_t)u * kThreads;
+    p_long[u] = i < n ? p[i] : 0.0;
+    p_short[u] = i < n ? short_table[i / A] : 0.0;
+  }
+#pragma unroll
+  for (int u = 0; u < kRatioBatch; ++u) {
+    const uint64_t i = base + (uint64_t)u * kThreads;
+    if (i < n) ratio[i] = extension_ratio(p_long[u], p_short[u]);
+  }
+}
+
 // A group that owns its parents (fused right chain, engine.h Level): evaluates parent j = child
 // x_prev of previous-level group g_prev + j * g_step from that group's sum, stores it at its node
 // and returns the sum over j in ascending order.  DIRECT: the parents are the A values of the
 // dropped digit in order, so their table indices follow from the group's own prefix.
-template <int UO, bool DIRECT>
+template <int UO, bool DIRECT, bool RATIO>
 __device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, const double* __restrict__ p,
                                               const double* __restrict__ short_table, double* __restrict__ ww,
                                               uint64_t g, uint32_t first, uint32_t stride, uint32_t n,
@@ -521,12 +547,13 @@ __device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, 
     }
 #pragma unroll
     for (int u = 0; u < UO; ++u) {
-      p_long[u] = e + u < n ? p[i_long[u]] : 0.0;
-      p_marg[u] = e + u < n ? short_table[i_short[u]] : 0.0;
+      p_long[u] = e + u < n ? p[i_long[u]] : 0.0;  // RATIO: p is the ratio table, i_short = i_long / A is built in
+      p_marg[u] = !RATIO && e + u < n ? short_table[i_short[u]] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < UO; ++u) {
-      const double v = e + u < n ? child_weight(sum_prev[u], p_long[u], p_marg[u]) : 0.0;
+      const double v = e + u >= n ? 0.0 : (RATIO ? weight_from_ratio(sum_prev[u], p_long[u])
+                                                 : child_weight(sum_prev[u], p_long[u], p_marg[u]));
       if (e + u < n) ww[first + (e + u) * stride] = v;
       total += v;
     }
@@ -542,10 +569,11 @@ __device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, 
 // Loads are issued U at a time before the divisions and stores that depend on them: the kernel is
 // bound by HBM latency x bandwidth, and one load in flight per thread reaches ~60 % of peak only
 // (profiles/r01_c_*).  wr and ww are the same vector: reads touch earlier levels only.
-template <int U, int UO, bool PROGRESSIONS, int MIN_BLOCKS>
+template <int U, int UO, bool PROGRESSIONS, int MIN_BLOCKS, bool RATIO>
 __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
                                                          uint32_t warp_step_q, uint32_t warp_step_r,
-                                                         const double* __restrict__ wr, double* __restrict__ ww) {
+                                                         const double* __restrict__ wr, double* __restrict__ ww,
+                                                         const double* __restrict__ ratio) {
   if (blockIdx.x < left_blocks) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= lv.n_left) return;
@@ -574,7 +602,8 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
     double total = 0.0, p_short = 0.0;
     uint32_t prefix = 0;
     bool deferred = true;  // lanes without a group have no children to write
-    const double* __restrict__ p = t.p;
+    // right extensions: the table itself, or (RATIO) the per-window ratios ratio_right_kernel left behind
+    const double* __restrict__ p = RATIO ? ratio : t.p;
     if (g < lv.n_groups) {
       if (PROGRESSIONS) {  // parents first, first + stride, ...
         const uint32_t first = lv.g_first[g], stride = lv.g_stride[g], packed = lv.g_count[g];
@@ -587,9 +616,9 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
           const uint32_t g_prev = rel / c.A, x_prev = rel - g_prev * c.A, g_step = stride / c.A;
           const double* __restrict__ short_table = table(t, c.k - 1);
           if (packed & Level::kAllDigits)
-            total = own_parents<UO, true>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
+            total = own_parents<UO, true, RATIO>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
           else
-            total = own_parents<UO, false>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
+            total = own_parents<UO, false, RATIO>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
         } else {
           for (uint32_t e = 0; e < n; e += U) {
             double v[U];
@@ -616,7 +645,7 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
       }
       if (!deferred) {
         prefix = lv.g_prefix[g];
-        p_short = table(t, c.k - 1)[prefix];
+        if (!RATIO) p_short = table(t, c.k - 1)[prefix];
       }
     }
     const uint32_t skip = __ballot_sync(0xffffffffu, deferred);  // bit gl: children of group gl are not ours
@@ -648,8 +677,12 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const double wp = __shfl_sync(0xffffffffu, total, gu[u]);
-        const double ps = __shfl_sync(0xffffffffu, p_short, gu[u]);
-        if (live[u]) out[j + 32 * u] = child_weight(wp, p_long[u], ps);
+        if (RATIO) {
+          if (live[u]) out[j + 32 * u] = weight_from_ratio(wp, p_long[u]);
+        } else {
+          const double ps = __shfl_sync(0xffffffffu, p_short, gu[u]);
+          if (live[u]) out[j + 32 * u] = child_weight(wp, p_long[u], ps);
+        }
       }
     }
   }
@@ -1218,6 +1251,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.d_marg_off = dkeep<uint64_t>(m, 40);
   TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_marg_off, m.marg_off, 40 * 8, cudaMemcpyHostToDevice, st));
   m.node_w = dkeep<double>(m, m.n_nodes);
+  if (const char* g = std::getenv("TAPES_RATIO_TABLE")) m.ratio_table = std::atoi(g) != 0;
+  bool any_groups = false;
+  for (const Level& lv : m.levels) any_groups = any_groups || lv.n_groups > 0;
+  if (any_groups && m.k >= 2) m.ratio_right = dkeep<double>(m, m.n_states);  // right-extension ratios, per step
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.launches_per_rhs = rhs_launch_count(m);
   return mp;
@@ -1241,6 +1278,7 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
 
   // marginal tables, longest first
   const int top = marginal_tail_top(m);
+  const bool use_ratio = m.ratio_table && m.ratio_right && m.k >= 2;
   for (int L = m.k - 1; L > top; --L) {
     const double* src = (L + 1 == m.k) ? d_p : m.marg + m.marg_off[L + 1];
     marginal_kernel<<<grid_for(m.pow_a[L], kThreads), kThreads, 0, st>>>(src, m.marg + m.marg_off[L], m.pow_a[L], c.A);
@@ -1250,6 +1288,9 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   if (m.n_rules)
     rule_weight_kernel<<<grid_for(m.n_rules, 128), 128, 0, st>>>(t, m.n_rules, m.rule_ptr, m.step_kind, m.step_len,
                                                                 m.step_long, m.step_short, m.step_prob, m.rule_w);
+  if (use_ratio)  // writing the ratios from the marginal kernel (which has the operands at hand) measured slower: strided stores
+    ratio_right_kernel<<<grid_for(m.n_states, kThreads * kRatioBatch), kThreads, 0, st>>>(d_p, m.marg + m.marg_off[m.k - 1], m.ratio_right,
+                                                                          m.n_states, c.A);
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
   for (const Level& stored : m.levels) {
     Level lv = stored;
@@ -1269,15 +1310,19 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       // Separate lean kernels for the pure right-chain levels (one thread per group, 32-62 registers, 4-8
       // blocks per SM, then one thread per child) measured 5.59-6.35 ms against 5.51 for this kernel
       // (profiles/r01_m_sweep_lean_chain_kernels.log): the deep levels are not bound by registers.
-#define TAPES_LEVEL(U_, UO_, B_)                                                                             \
-  (prog ? level_kernel<U_, UO_, true, B_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w) \
-        : level_kernel<U_, 1, false, 5><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w))
+#define TAPES_LEVEL_R(U_, UO_, B_, R_)                                                                       \
+  (prog ? level_kernel<U_, UO_, true, B_, R_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w, \
+                                                                          m.ratio_right)                           \
+        : level_kernel<U_, 1, false, 5, R_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w, \
+                                                                        m.ratio_right))
+#define TAPES_LEVEL(U_, UO_, B_) (use_ratio ? TAPES_LEVEL_R(U_, UO_, B_, true) : TAPES_LEVEL_R(U_, UO_, B_, false))
       if (m.level_unroll >= 8) TAPES_LEVEL(8, 4, 4);
       else if (m.level_unroll >= 5) TAPES_LEVEL(5, 3, 5);
       else if (m.level_unroll >= 4) TAPES_LEVEL(4, 2, 5);
       else if (m.level_unroll >= 2) TAPES_LEVEL(2, 2, 5);
       else TAPES_LEVEL(1, 1, 5);
 #undef TAPES_LEVEL
+#undef TAPES_LEVEL_R
     }
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
@@ -1399,6 +1444,7 @@ int64_t rhs_launch_count(const Model& m) {
   launches += (m.k - 1 - top);          // one kernel per long marginal table
   if (top >= 0) launches += 1;          // tail tables
   if (m.n_rules) launches += 1;         // leaf-world probabilities
+  if (m.ratio_table && m.ratio_right && m.k >= 2) launches += 1;  // right-extension ratios
   for (const Level& lv : m.levels)
     if (lv.n_roots || lv.n_left + lv.n_groups) launches += 1;
   launches += 1;                        // S * w

@@ -153,6 +153,8 @@ struct Model {
   int level_unroll = 4;            // loads in flight per thread in level_kernel
   int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
   int interleave_seeds = 1;        // level kernel: use Level::block_order
+  int ratio_table = 1;             // right-extension ratios evaluated once per step into ratio_right
+  double* ratio_right = nullptr;   // [n_states] p[i] / max(p[i], marg_{k-1}[i / A]), 0 where p[i] == 0
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;
