@@ -157,7 +157,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity);
  * kernel), "level_unroll" (1..8 loads in flight per thread of the level kernel), "flux_unroll"
  * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel), "interleave_seeds" (1: the
  * level kernel evaluates the blocks of prefix groups of different seeds in prefix order so that they
- * share their reads of the table through L2, 0: in storage order), "graphs" (1: for tables of up to
+ * share their reads of the table through L2, 0: in storage order), "ratio_table" (1: the ratios of right extensions are evaluated once per
+ * step into a table the level kernel reads, 0: per node), "graphs" (1: for tables of up to
  * 2^22 states the kernels that evaluate the weights are replayed from a CUDA graph captured per input
  * pointer, 0: launched one by one).  Results do not depend on any of them. */
 int tapes_model_set(void* model, const char* key, int64_t value);
