@@ -102,3 +102,29 @@ def test_gpu_matches_oracle_on_random_programs(oracle, size_a, seed, depth):
       # entry, so the bound is 1e-13 instead of the 1e-14 used for the shipped problems
       assert (abs(got - want) <= 1e-13 * gross_flux(oracle, tag, cl_k, p) + 1e-300).all()
     mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+
+
+@pytest.mark.parametrize('size_a,seed,depth', CASES)
+def test_retraced_tree_is_the_same_program(oracle, size_a, seed, depth):
+  """The C++ tracer (which feeds the Monte-Carlo simulator) run on a random tree's body gives a
+  tree without the reads of already known cells; both must be the same program to the oracle, bit for
+  bit, and tracing the traced tree again must reproduce it."""
+  tree = random_tree(size_a, seed, depth)
+  tag = f'rnd-retrace-{seed}'
+  _lib.register_program(tag, size_a, tree)
+  traced = _lib.program_tree(tag)
+  assert traced['kind'].size <= tree['kind'].size + 1
+  oracle.register_program(tag, size_a, tree)
+  oracle.register_program(tag + '-t', size_a, traced)
+  _lib.register_program(tag + '-t', size_a, traced)
+  again = _lib.program_tree(tag + '-t')
+  for key in traced:
+    assert numpy.array_equal(traced[key], again[key]), key
+  for cl_k in (1, 3, 4):
+    for p in tables(size_a, cl_k, seed):
+      for mode in (oracle.LITERAL, oracle.MERGED):
+        assert numpy.array_equal(oracle.compute_dy_dt(tag, cl_k, p, mode=mode),
+                                 oracle.compute_dy_dt(tag + '-t', cl_k, p, mode=mode))
+    a, b = _lib.rule_table(tag, cl_k), _lib.rule_table(tag + '-t', cl_k)
+    for key in ('rule_ptr', 'step_kind', 'step_len', 'step_long', 'step_short', 'step_prob', 'seed_len', 'seed_orig', 'seed_adj'):
+      assert numpy.array_equal(a[key], b[key]), key
