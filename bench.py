@@ -270,6 +270,39 @@ def cpu_port_step(args, rules_subset, nnz_per_rule_state, reps=1):
   return min(times), cores, counters
 
 
+def literal_vs_merged(args, rules, n_rules=4):
+  """beside the states this library expands (every distinct node once), the
+  number the reference's literal recursion visits for the same rules (right-shifted windows are
+  revisited once per left context, about A^(2k-3) per one-cell rule).  Counted exactly by the CPU port
+  in both modes at the window lengths where the literal recursion finishes in a second, then
+  extrapolated to the bench's cl_k with the last measured growth factor per unit of k."""
+  from oracle import oracle
+  from chemical_kinetics_and_program_execution_b200 import configs
+  sample = {k: numpy.asarray(v)[:n_rules] for k, v in rules.items()}
+  oracle.register_rules('bench-literal-count', args.size_a, sample)
+  rows = []
+  for k in range(2, args.cl_k + 1):
+    if float(args.size_a) ** (2 * k - 3) * n_rules > 6e7:
+      break
+    p = configs.dirichlet_product_table(args.size_a, k, 3)
+    lit = oracle.compute_dy_dt('bench-literal-count', k, p, mode=oracle.LITERAL, want_counters=True)[1]
+    mer = oracle.compute_dy_dt('bench-literal-count', k, p, mode=oracle.MERGED, want_counters=True)[1]
+    rows.append(dict(cl_k=k, literal_nodes=lit['ext_nodes'] + lit['worlds'], literal_accumulate_calls=lit['acc_calls'],
+                     merged_nodes=mer['ext_nodes'] + mer['worlds'], merged_terms=mer['acc_calls']))
+  out = dict(rules=n_rules, counted=rows)
+  if len(rows) >= 2 and rows[-1]['cl_k'] < args.cl_k:
+    steps = args.cl_k - rows[-1]['cl_k']
+    g_lit = rows[-1]['literal_nodes'] / max(rows[-2]['literal_nodes'], 1)
+    g_mer = rows[-1]['merged_nodes'] / max(rows[-2]['merged_nodes'], 1)
+    out['extrapolated'] = dict(cl_k=args.cl_k, literal_nodes=rows[-1]['literal_nodes'] * g_lit ** steps,
+                               merged_nodes=rows[-1]['merged_nodes'] * g_mer ** steps,
+                               growth_per_k=dict(literal=g_lit, merged=g_mer),
+                               note='the reference visits literal_nodes for what is merged_nodes distinct nodes here; '
+                                    'the literal growth factor is still rising towards A^2 at the last counted '
+                                    'cl_k, so the extrapolation understates the reference\'s work')
+  return out
+
+
 def run_reference(args):
   """--impl reference: the CPU port of the reference's compute-dy/dt (oracle, merged mode; the
   Gambit-C original cannot be built in this image) with one worker process per rule on all usable
@@ -532,7 +565,8 @@ def run_b200(args):
                sample=(f'first {n_sample} of {args.rules_per_gpu} rules on the full {n}-state table '
                        f'(nnz={nnz_s}), merged-mode CPU port of compute-dy/dt, {cores} worker processes, '
                        f'{t_cpu:.1f} s'),
-               seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu)
+               seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu,
+               reference_equivalent_work=literal_vs_merged(args, rules))
 
   if rank == 0:
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
