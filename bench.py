@@ -270,6 +270,14 @@ def cpu_port_step(args, rules_subset, nnz_per_rule_state, reps=1):
   return min(times), cores, counters
 
 
+def _guarded(fn, *fn_args):
+  """An auxiliary figure must not cost the bench line."""
+  try:
+    return fn(*fn_args)
+  except Exception as ex:  # pylint: disable=broad-except
+    return dict(error=repr(ex))
+
+
 def literal_vs_merged(args, rules, n_rules=4):
   """beside the states this library expands (every distinct node once), the
   number the reference's literal recursion visits for the same rules (right-shifted windows are
@@ -566,7 +574,7 @@ def run_b200(args):
                        f'(nnz={nnz_s}), merged-mode CPU port of compute-dy/dt, {cores} worker processes, '
                        f'{t_cpu:.1f} s'),
                seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu,
-               reference_equivalent_work=literal_vs_merged(args, rules))
+               reference_equivalent_work=_guarded(literal_vs_merged, args, rules))
 
   if rank == 0:
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
