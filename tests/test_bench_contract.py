@@ -1,0 +1,51 @@
+"""CPU checks of bench.py's contract: the reference arm prints exactly one JSON line with the keys
+the driver reads, and the helper figures are what DESIGN.md says they are."""
+
+import json
+import os
+import subprocess
+import sys
+import types
+
+import numpy
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_json_line():
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '2',
+                        '--warmup', '1', '--size-a', '3', '--cl-k', '5', '--rules-per-gpu', '3'],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT)
+  assert out.returncode == 0, out.stderr
+  lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+  assert len(lines) == 1
+  line = json.loads(lines[0])
+  assert line['impl'] == 'reference' and line['steps'] == 2 and line['warmup'] == 1 and line['n_gpus'] == 1
+  assert line['higher_is_better'] is True and line['unit'] == 'GB/s' and line['value'] > 0
+  assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['cores'] >= 1
+  assert line['cpu_baseline']['value'] == line['value']
+  assert line['e2e'] == dict(value=line['value'], unit='GB/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+  assert line['config']['workload'] == 'synthetic-random-rewrite-rules'
+
+
+def test_other_ranks_of_the_reference_arm_stay_silent():
+  env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+  out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2',
+                        '--steps', '1', '--warmup', '0', '--size-a', '3', '--cl-k', '4', '--rules-per-gpu', '2'],
+                       capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+  assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_byte_counts_and_reference_equivalent_work():
+  sys.path.insert(0, ROOT)
+  import bench
+  from chemical_kinetics_and_program_execution_b200 import configs
+  assert bench.spmv_bytes(10, 3) == 12 * 10 + 16 * 3
+  assert bench.step_bytes(10, 3, 5) == 28 * 10 + 24 * 3 + 8 * 3 * 1.5
+  work = bench.literal_vs_merged(types.SimpleNamespace(size_a=4, cl_k=7), configs.random_rule_set(4, 6, seed=2))
+  rows = work['counted']
+  assert rows[0]['cl_k'] == 2 and all(r['literal_nodes'] >= r['merged_nodes'] for r in rows)
+  assert rows[-1]['literal_accumulate_calls'] > rows[-1]['merged_terms']  # windows revisited per left context
+  if 'extrapolated' in work:
+    assert work['extrapolated']['literal_nodes'] > work['extrapolated']['merged_nodes']
+  assert 'error' in bench._guarded(bench.literal_vs_merged, types.SimpleNamespace(size_a=4, cl_k=7), {'bad': 1})
