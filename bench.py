@@ -10,16 +10,19 @@ rate structure) and the CSR product S*w.  With N > 1 every rank gets its own 24 
 scaling) and a step also contains the flux exchange, by default fused into the product kernel over
 NVLink peer memory (parallel.PeerExchangeRhs).
 
-`value` is algorithmic GB/s of the whole step (bytes defined in DESIGN.md, "Algorithmic bytes"):
-  step_bytes = 28 * nnz + 24 * n + 8 * n * (1 + 2 / (A - 1))
-`roofline` describes the dominant kernel, the product S*w (flux_slices_kernel, 3.7 ms per launch;
-the 13 level_kernel launches of a step are at most 0.9 ms each and are summarised in
-`roofline_levels`), against the measured HBM peak, with the survey's CSR byte count
-  spmv_bytes = 12 * nnz + 16 * n
-The kernel streams a compressed form of the CSR (runs of 32 states), so its DRAM traffic
-(`traffic`, from the ncu capture recorded in profiles/ncu_traffic.json) is below that figure and
-`frac` can exceed 1; `dram_frac` = traffic / time / peak is the fraction of the HBM roofline the
-kernel actually occupies.
+`value` is the survey's metric: CSR-EQUIVALENT algorithmic GB/s of the
+whole step, i.e. the bytes a plain CSR SpMV with per-step rate re-evaluation would move,
+  step_bytes = 28 * nnz + 24 * n + 8 * n * (1 + 2 / (A - 1)),
+divided by the step time.  It is a work rate, not a bandwidth: the kernels stream a compressed
+structure (implicit children, runs of 32 states), so it can exceed the HBM peak.  The bandwidth
+figures are `value_dram_gbs` / `dram_frac` (whole step: DRAM bytes of every kernel of a step from
+the committed ncu capture of this very structure, profiles/ncu_traffic.json, over the step time)
+and the `roofline*` objects, whose `achieved` counts the bytes the shipped format must move at the
+least (every array a kernel streams read once, every result written once: DESIGN.md section 4),
+which is below the real traffic, so `frac` <= `dram_frac` <= 1.  `roofline` is the product kernel
+(flux_slices_kernel, the longest single launch), `roofline_levels` the level_kernel launches summed.
+`parity_check`: the dy/dt of the TIMED workload is checked inside this run (sum over states = 0, and
+against the CPU port evaluated on the same rules and table in the cpu_baseline leg).
 Prints exactly one JSON line on rank 0.
 """
 
@@ -39,7 +42,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
-METRIC = 'master-eq SpMV GB/s (whole dy/dt step incl. rate re-evaluation, algorithmic bytes)'
+METRIC = 'master-eq SpMV GB/s (whole dy/dt step incl. rate re-evaluation; CSR-equivalent algorithmic bytes)'
 UNIT = 'GB/s'
 
 
@@ -81,6 +84,12 @@ def parse_args():
   ap.add_argument('--cpu-rules', type=int, default=0,
                   help='rules in the CPU-baseline sample (0 = one per usable host core, at most all)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                  help='N > 1: weak = rules-per-gpu rules on every rank (work grows with N), strong = the '
+                       'N = 1 problem (rules-per-gpu rules in all) dealt to the N ranks')
+  ap.add_argument('--ref-budget-s', type=float, default=600.0,
+                  help='--impl reference: seconds of CPU work the timed steps may take in all (fewer steps '
+                       'are timed, and reported, when `steps` full-table evaluations do not fit)')
   return ap.parse_args()
 
 
@@ -93,28 +102,71 @@ def spmv_bytes(nnz, n):
 
 
 def level_bytes(info):
-  """Algorithmic bytes of all level_kernel launches of one step: 16 B per
-  child node (table read + weight write), 25 B per left-parent record, per prefix group 24 B
-  (prefix, short marginal, parent progression), 8 B per parent weight that is gathered (parents a
-  group evaluates itself are not read back) and 16 B per group sum handed to the next level."""
+  """Algorithmic bytes of all level_kernel launches of one step, every access
+  counted as if it came from DRAM: 16 B per child node (table or ratio read + weight write), 25 B
+  per left-parent record (ids, length, parent weight, short marginal), per prefix group 16 B
+  (prefix + parent progression, or what the run descriptors leave of it), 8 B per parent weight that is
+  gathered (parents a group evaluates itself are not read back) and 16 B per group sum handed to
+  the next level."""
   children = info['n_nodes']
   gathered = info['hash_inserts'] - info.get('owned_parents', 0)
-  return (16.0 * children + 25.0 * info.get('left_parents', 0) + 24.0 * info['hash_unique'] + 8.0 * gathered
+  per_group = info.get('group_record_bytes', 16 * info['hash_unique'])
+  return (16.0 * children + 25.0 * info.get('left_parents', 0) + float(per_group) + 8.0 * gathered
           + 16.0 * info.get('deferred_groups', 0))
 
 
+def flux_format_bytes(info, n):
+  """Bytes the product kernel must move at the least in the shipped format (sliced flux structure,
+  csrc/flux.cu): slice pointers and run counts, every structure word once, every term's weight once
+  (a term is read by its source and its destination row; the second read is credited to L2), the
+  result once.  Below the real traffic by what L2 misses of the second reads and by the padding of
+  the columns, so `frac` computed from it is a lower bound of the share of the HBM roofline."""
+  slices = info.get('n_slices', (n + 31) // 32)
+  return 8.0 * (slices + 1) + 4.0 * slices + 4.0 * info.get('slice_words', 0) + 8.0 * info['n_terms'] + 8.0 * n
+
+
+def prepass_bytes(info, n, size_a):
+  """Marginal tables (read the table, write the k - 1 shorter ones) and the per-step ratio tables
+  (read the table, write one ratio per state and table)."""
+  return 8.0 * n * (1.0 + 2.0 / max(size_a - 1, 1)) + 16.0 * n * info.get('ratio_tables', 1)
+
+
+_TRAFFIC = None
+
+
 def recorded_traffic(kernel, info, args):
-  """DRAM bytes per launch (or per step for level_kernel) of `kernel` from the committed ncu
-  capture, when that capture was taken on this very structure; else None."""
+  """DRAM bytes per step of `kernel` (all its launches of one right-hand side summed) from the
+  committed ncu capture, when that capture was taken on this very structure; else None.
+  kernel = None: the whole step (every kernel of the capture)."""
+  global _TRAFFIC
   try:
-    with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
-      rec = json.load(f)
+    if _TRAFFIC is None:
+      with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+        _TRAFFIC = json.load(f)
+    rec = _TRAFFIC
     same = all(rec['config'].get(k) == v for k, v in
                dict(size_a=args.size_a, cl_k=args.cl_k, rules=args.rules_per_gpu, seed=args.seed,
                     nnz=info['nnz'], n_nodes=info['n_nodes']).items())
-    return float(rec['kernels'][kernel]['dram_bytes']) if same else None
+    if not same:
+      return None
+    if kernel is None:
+      return float(sum(k['dram_bytes'] for k in rec['kernels'].values()))
+    return float(rec['kernels'][kernel]['dram_bytes'])
   except Exception:
     return None
+
+
+def workload_config(args, world):
+  """`config` of the JSON line: names the workload only, so that this repo's arm and the reference
+  arm print the same object for the same command line."""
+  strong = getattr(args, 'scaling', 'weak') == 'strong'
+  total_rules = args.rules_per_gpu if strong else args.rules_per_gpu * world
+  return dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a, cl_k=args.cl_k,
+              n_states=args.size_a ** args.cl_k, rules_per_gpu=args.rules_per_gpu, total_rules=total_rules,
+              seed=args.seed, table='full-support product table (Dirichlet symbol frequencies, seed + 2)',
+              parallelism=('single GPU' if world == 1 else
+                           f'{total_rules} rules dealt to {world} ranks, one flux exchange per step'),
+              l2='inputs larger than L2 (table, weights and flux structure each exceed 126 MB)')
 
 
 def usable_cpu_workers(n_states, wanted):
@@ -216,8 +268,14 @@ def make_workload(args, world, rank):
   structure sizes), and rank g evaluates copy g."""
   from chemical_kinetics_and_program_execution_b200 import configs, parallel
   base = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)
-  rules = configs.concat_rule_sets([configs.rotated_rule_set(base, g, args.size_a) for g in range(world)])
   r = args.rules_per_gpu
+  if getattr(args, 'scaling', 'weak') == 'strong':
+    # strong scaling: the N = 1 problem itself, its rules dealt to the ranks by their term counts
+    rules = base
+    local = parallel.split_rule_set(rules, world, rank, args.size_a, args.cl_k) if world > 1 else rules
+    tag = configs.synthetic_tag(args.size_a, r, args.seed) + (f'-part{rank}of{world}' if world > 1 else '')
+    return rules, local, tag
+  rules = configs.concat_rule_sets([configs.rotated_rule_set(base, g, args.size_a) for g in range(world)])
   local = parallel.take_rules(rules, numpy.arange(rank * r, (rank + 1) * r)) if world > 1 else rules
   tag = configs.synthetic_tag(args.size_a, r * world, args.seed) + (f'-rank{rank}of{world}' if world > 1 else '')
   return rules, local, tag
@@ -237,8 +295,11 @@ def device_product_table(size_a, cl_k, seed, device):
 # --------------------------------------------------------------------------------------------
 # CPU port (oracle) legs: the only places bench.py executes anything under oracle/.
 # --------------------------------------------------------------------------------------------
+_SHARED_ROWS = None  # anonymous shared mapping the forked workers write their dy/dt into
+
+
 def _cpu_worker(job):
-  tag, size_a, cl_k, rules, seed = job
+  tag, size_a, cl_k, rules, seed, row = job
   from chemical_kinetics_and_program_execution_b200 import configs
   from oracle import oracle
   oracle.register_rules(tag, size_a, rules)
@@ -246,28 +307,52 @@ def _cpu_worker(job):
   p = configs.product_table(f, cl_k)
   t0 = time.perf_counter()
   out, counters = oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED, want_counters=True)
-  return time.perf_counter() - t0, counters, float(abs(out).sum())
+  seconds = time.perf_counter() - t0
+  if _SHARED_ROWS is not None and row is not None:  # not timed: hands the result to the parent
+    n = out.size
+    numpy.frombuffer(_SHARED_ROWS, dtype=numpy.float64, count=n, offset=8 * n * row)[:] = out
+  return seconds, counters
 
 
-def cpu_port_step(args, rules_subset, nnz_per_rule_state, reps=1):
-  """Times the merged-mode CPU port on `rules_subset`, one worker process per rule (the forests
-  of different rules are independent, which is the only parallelism the path offers on a CPU)."""
+def cpu_port_step(args, rules_subset, reps=1, want_result=False):
+  """Times the merged-mode CPU port on `rules_subset` (as a problem of its own: the selection
+  weights of the subset), one worker process per share of the rules (the forests of different
+  rules are independent, which is the only parallelism the path offers on a CPU).  Returns
+  (seconds, workers, counters, dy/dt or None); with want_result the workers leave their partial
+  dy/dt in shared memory and the parent adds them up in worker order."""
+  global _SHARED_ROWS
+  import mmap
   import multiprocessing as mp
   from chemical_kinetics_and_program_execution_b200 import parallel
   n_rules = len(rules_subset['rate'])
   cl_k = getattr(args, 'cpu_cl_k', None) or args.cl_k
-  cores = usable_cpu_workers(args.size_a ** cl_k, n_rules)
-  jobs = [(f'cpu-sample-{i}', args.size_a, cl_k, parallel.split_rule_set(rules_subset, cores, i), args.seed + 2)
-          for i in range(cores)]
+  n = args.size_a ** cl_k
+  cores = usable_cpu_workers(n, n_rules)
+  jobs = [(f'cpu-sample-{i}', args.size_a, cl_k, parallel.split_rule_set(rules_subset, cores, i), args.seed + 2,
+           i if want_result else None) for i in range(cores)]
+  _SHARED_ROWS = mmap.mmap(-1, 8 * n * cores) if want_result else None  # inherited by the forked workers
   ctx = mp.get_context('fork')
-  times = []
-  counters = None
-  for _ in range(reps):
-    with ctx.Pool(cores) as pool:
-      res = pool.map(_cpu_worker, jobs)
-    times.append(max(r[0] for r in res))  # workers run concurrently; table set-up is not timed
-    counters = {k: sum(r[1][k] for r in res) for k in res[0][1]}
-  return min(times), cores, counters
+  times, counters, total = [], None, None
+  try:
+    for _ in range(reps):
+      with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, jobs)
+      times.append(max(r[0] for r in res))  # workers run concurrently; table set-up is not timed
+      counters = {k: sum(r[1][k] for r in res) for k in res[0][1]}
+    if want_result:
+      rows = numpy.frombuffer(_SHARED_ROWS, dtype=numpy.float64, count=n * cores).reshape(cores, n)
+      total = rows[0].copy()
+      for i in range(1, cores):
+        total += rows[i]
+      del rows
+  finally:
+    if _SHARED_ROWS is not None:
+      try:
+        _SHARED_ROWS.close()
+      except BufferError:
+        pass
+      _SHARED_ROWS = None
+  return min(times), cores, counters, total
 
 
 def _guarded(fn, *fn_args):
@@ -313,52 +398,48 @@ def literal_vs_merged(args, rules, n_rules=4):
 
 def run_reference(args):
   """--impl reference: the CPU port of the reference's compute-dy/dt (oracle, merged mode; the
-  Gambit-C original cannot be built in this image) with one worker process per rule on all usable
-  host cores.  Each step is a bounded sample of the bench workload: as many of rank 0's rules as
-  there are workers, on the full table when (warmup + steps) of those fit in about three minutes,
-  else on the same rule set with a shorter window (smaller cl_k; same per-term work)."""
+  Gambit-C original cannot be built in this image) on the bench's own configuration: the same
+  table (size_a ** cl_k states) and rank 0's rules_per_gpu rules, one worker process per share of
+  the rules on all usable host cores.  At N > 1 (weak scaling) that is a bounded sample of the job -
+  one rank's rules of the N * rules_per_gpu - at the same per-rule work, so the GB/s figure is the
+  one the whole job would show.  warmup + steps full-table evaluations are run when they fit
+  --ref-budget-s seconds of CPU work; when they do not, the warm-up goes first (the CPU path has
+  nothing to warm up: no cached structures, no clocks to ramp - every evaluation rebuilds the tree
+  like the reference, tm.scm:1476), then timed steps; `warmup` and `steps` of the line say what was
+  actually run."""
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
   from chemical_kinetics_and_program_execution_b200 import configs
   from oracle import oracle
   oracle.build()
-  total_rules = args.rules_per_gpu * args.gpus
+  world = max(1, args.gpus)
+  config = workload_config(args, world)
   rules = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)  # rank 0's rules
-  n_sample = args.cpu_rules or usable_cpu_workers(args.size_a ** args.cl_k, args.rules_per_gpu)
-  sample = {k: numpy.asarray(v)[:n_sample] for k, v in rules.items()}
-  # calibrate on a short window, then pick the longest window whose run fits the time budget
-  budget_s = 170.0 / max(1, args.warmup + args.steps)
-  args.cpu_cl_k = min(args.cl_k, 5)
-  t_cal, _, _ = cpu_port_step(args, sample, None)
-  k_use, est = args.cpu_cl_k, t_cal
-  while k_use < args.cl_k:
-    nxt = est * args.size_a * (k_use + 1) / k_use  # terms per rule grow like k * A^(k-1)
-    if nxt > budget_s:
-      break
-    k_use, est = k_use + 1, nxt
-  args.cpu_cl_k = k_use
-  n = args.size_a ** k_use
-  times, cores, counters = [], 1, None
-  for _ in range(args.warmup + args.steps):
-    t, cores, counters = cpu_port_step(args, sample, None)
-    times.append(t)
-  timed = times[args.warmup:]
+  n = args.size_a ** args.cl_k
+  t1, cores, counters, _ = cpu_port_step(args, rules)
+  steps, warmup = max(1, args.steps), max(0, args.warmup)
+  if (warmup + steps) * t1 > args.ref_budget_s:
+    warmup = 0
+    steps = max(1, min(steps, int(args.ref_budget_s // max(t1, 1e-9))))
+  every = [t1]
+  while len(every) < warmup + steps:
+    every.append(cpu_port_step(args, rules)[0])
+  times = every[warmup:]
   nnz = 2 * counters['acc_calls']
   bytes_step = step_bytes(nnz, n, args.size_a)
-  ms = 1e3 * sum(timed) / len(timed)
+  ms = 1e3 * sum(times) / len(times)
   value = bytes_step / (ms * 1e-3) / 1e9
-  sample_desc = (f'first {n_sample} of {total_rules} rules of the same rule set on the '
-                 f'{n}-state table (cl_k={k_use}; bench workload cl_k={args.cl_k}), nnz={nnz}, '
-                 f'merged-mode CPU port of compute-dy/dt, {cores} worker processes')
+  sample_desc = (f'{args.rules_per_gpu} of {config["total_rules"]} rules (rank 0\'s share) on the full {n}-state table '
+                 f'(cl_k={args.cl_k}, the bench configuration), nnz={nnz}, merged-mode CPU port of compute-dy/dt, '
+                 f'{cores} worker processes, {warmup} warm-up + {len(times)} timed steps (requested {args.warmup} + {args.steps})')
   line = dict(impl='reference', metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus,
-              steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True,
-              scaling='weak', vs_baseline=None, dtype='f64', data='synthetic',
-              config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a,
-                          cl_k=args.cl_k, n_states=args.size_a ** args.cl_k, rules_per_gpu=args.rules_per_gpu,
-                          total_rules=total_rules, seed=args.seed, sample=sample_desc),
+              steps=len(times), warmup=warmup, ms_per_step=ms, higher_is_better=True,
+              scaling=args.scaling, vs_baseline=None, dtype='f64', data='synthetic',
+              config=config, same_config=True, steps_requested=args.steps, warmup_requested=args.warmup,
               cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='port', sample=sample_desc),
               e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+              states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / (ms * 1e-3),
               gpu_launches=0)
   emit(line)
 
@@ -499,8 +580,19 @@ def run_b200(args):
     dist.all_reduce(expand_s, op=dist.ReduceOp.MAX)  # the ranks expand their rules concurrently
   nnz_total, nodes_total, terms_total, launches_total, expanded_total = [float(x) for x in sizes.tolist()]
   expand_s, expand_kernels_s = [float(x) for x in expand_s.tolist()]
-  job_bytes = 28.0 * nnz_total + world * (24.0 * n + 8.0 * n * (1.0 + 2.0 / max(args.size_a - 1, 1)))
+  strong = args.scaling == 'strong'
+  # weak: every rank evaluates its own rules on its own copy of the table; strong: one problem, one table
+  table_passes = 1 if strong else world
+  job_bytes = 28.0 * nnz_total + table_passes * (24.0 * n + 8.0 * n * (1.0 + 2.0 / max(args.size_a - 1, 1)))
   value = job_bytes / (ms_step * 1e-3) / 1e9
+
+  # parity of the timed workload, part 1: every flux term adds +w and -w (tm.scm:1288-1291), so the
+  # dy/dt the timed loop left behind must sum to zero up to rounding
+  result = out if sharded is None else (sharded.out if args.exchange == 'peer' else out_full)[:n]
+  torch.cuda.synchronize()
+  flux_sum, flux_abs = float(result.sum().item()), float(result.abs().sum().item())
+  parity = dict(sum_dy_dt=flux_sum, sum_abs_dy_dt=flux_abs, sum_rel=abs(flux_sum) / max(flux_abs, 1e-300),
+                sum_tolerance=1e-12, sum_ok=bool(abs(flux_sum) <= 1e-12 * flux_abs and flux_abs > 0))
 
   # per-phase device times of this rank's kernels (CUDA events on the launching stream)
   phase = numpy.zeros(3)
@@ -509,24 +601,39 @@ def run_b200(args):
     phase += model.rhs_profile(p, out)
   phase /= reps
   peak, peak_src = measured_peak()
-  spmv_gbs = spmv_bytes(info['nnz'], n) / (phase[2] * 1e-3) / 1e9
-  flux_kernel = 'flux_slices_kernel' if info.get('flux_format', 0) == 1 else 'spmv_kernel'
+  sliced = info.get('flux_format', 0) == 1
+  flux_kernel = 'flux_slices_kernel' if sliced else 'spmv_kernel'
+  flux_bytes = flux_format_bytes(info, n) if sliced else spmv_bytes(info['nnz'], n)
+  flux_gbs = flux_bytes / (phase[2] * 1e-3) / 1e9
   traffic = recorded_traffic(flux_kernel, info, args)
-  roofline = dict(bound='hbm', kernel=flux_kernel + ' (S*w, one launch per step)', achieved=spmv_gbs, peak=peak,
-                  unit='GB/s', frac=spmv_gbs / peak, traffic=traffic,
+  roofline = dict(bound='hbm', kernel=flux_kernel + ' (S*w, one launch per step)', achieved=flux_gbs, peak=peak,
+                  unit='GB/s', frac=flux_gbs / peak, traffic=traffic,
                   dram_frac=(traffic / (phase[2] * 1e-3) / 1e9 / peak) if traffic else None,
                   peak_source=peak_src,
-                  algorithmic_bytes_per_launch=spmv_bytes(info['nnz'], n),
+                  algorithmic_bytes_per_launch=flux_bytes,
+                  algorithmic_bytes_are=('the sliced format\'s own minimum: slice pointers + structure words + one 8-byte '
+                                         'weight per flux term + the result (DESIGN.md section 4)' if sliced else
+                                         'plain CSR: 12 * nnz + 16 * n'),
+                  csr_equivalent_gbs=spmv_bytes(info['nnz'], n) / (phase[2] * 1e-3) / 1e9,
                   kernel_ms=float(phase[2]),
                   phases_ms=dict(marginals_and_world_probs=float(phase[0]), forest_levels=float(phase[1]),
-                                 spmv=float(phase[2])),
-                  step_frac_of_peak=(step_bytes(info['nnz'], n, args.size_a) / (phase.sum() * 1e-3) / 1e9) / peak)
+                                 spmv=float(phase[2])))
   lv_gbs = level_bytes(info) / (phase[1] * 1e-3) / 1e9
   lv_traffic = recorded_traffic('level_kernel', info, args)
   roofline_levels = dict(bound='hbm', kernel=f'level_kernel ({info["n_levels"] - 1} launches per step, summed)',
                          achieved=lv_gbs, peak=peak, unit='GB/s', frac=lv_gbs / peak, traffic=lv_traffic,
                          dram_frac=(lv_traffic / (phase[1] * 1e-3) / 1e9 / peak) if lv_traffic else None,
                          algorithmic_bytes_per_step=level_bytes(info), kernel_ms=float(phase[1]))
+  pre_bytes = prepass_bytes(info, n, args.size_a)
+  step_traffic = recorded_traffic(None, info, args)  # every kernel of one right-hand side
+  pre_traffic = (step_traffic - lv_traffic - traffic) if (step_traffic and lv_traffic and traffic) else None
+  roofline_prepass = dict(bound='hbm', kernel='marginal tables + per-step ratio tables + leaf-world probabilities',
+                          achieved=pre_bytes / (phase[0] * 1e-3) / 1e9, peak=peak, unit='GB/s',
+                          frac=pre_bytes / (phase[0] * 1e-3) / 1e9 / peak, traffic=pre_traffic,
+                          dram_frac=(pre_traffic / (phase[0] * 1e-3) / 1e9 / peak) if pre_traffic else None,
+                          algorithmic_bytes_per_step=pre_bytes, kernel_ms=float(phase[0]))
+  # the whole step as a bandwidth: DRAM bytes of all its kernels (ncu) over the timed step
+  value_dram = (step_traffic / (ms_step * 1e-3) / 1e9) if (step_traffic and world == 1) else None
 
   # the expansion, once per structure: SURVEY.md section 8(d) counts about 85 algorithmic bytes per
   # expanded state (48 B record written, 32 B of hash-slot traffic, the record read again shared by
@@ -556,6 +663,20 @@ def run_b200(args):
     e2e = dict(value=step_bytes(info['nnz'], n, args.size_a) / (e2e_ms * 1e-3) / 1e9, unit=UNIT,
                h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n, ms_per_step=e2e_ms,
                api='c_compute_dy_dt (host buffers, pinned)')
+    # the same call the way a user of the reference module makes it: get_dy_dt(...)(numpy array, t)
+    # with a PAGEABLE input array, a fresh result array per call (framework/markov_tapes.py:275-288)
+    def drop_in():
+      y = h_in.numpy().copy()  # pageable
+      f(y, 0.0)
+      t1 = time.perf_counter()
+      for _ in range(args.e2e_steps):
+        res = f(y, 0.0)
+      ms = 1e3 * (time.perf_counter() - t1) / args.e2e_steps
+      ok = bool(numpy.array_equal(res, h_out.numpy()))
+      return dict(value=step_bytes(info['nnz'], n, args.size_a) / (ms * 1e-3) / 1e9, unit=UNIT, ms_per_step=ms,
+                  api='markov_tapes.get_dy_dt(...)(pageable numpy array, t) -> new numpy array',
+                  same_bits_as_pinned_call=ok)
+    e2e['drop_in'] = _guarded(drop_in)
     del f
   elif world > 1:
     # N > 1: every rank brings the table in from pinned host memory over its own PCIe link, the ranks
@@ -600,37 +721,60 @@ def run_b200(args):
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import oracle
     oracle.build()
-    n_sample = args.cpu_rules or usable_cpu_workers(n, args.rules_per_gpu)
+    # the sample is the whole timed workload unless --cpu-rules asks for fewer rules: all rules on
+    # the full table, so that its dy/dt can be held against the GPU's (parity of the timed workload,
+    # part 2); fewer rules are compared with a GPU structure built for exactly those rules
+    n_sample = min(args.cpu_rules or args.rules_per_gpu, args.rules_per_gpu)
     sample = {k: numpy.asarray(v)[:n_sample] for k, v in rules.items()}
-    t_cpu, cores, counters = cpu_port_step(args, sample, None)
+    t_cpu, cores, counters, cpu_out = cpu_port_step(args, sample, want_result=True)
     nnz_s = 2 * counters['acc_calls']
     cpu = dict(value=step_bytes(nnz_s, n, args.size_a) / t_cpu / 1e9, unit=UNIT, cores=cores, kind='port',
-               sample=(f'first {n_sample} of {args.rules_per_gpu} rules on the full {n}-state table '
+               sample=(f'{"all" if n_sample == args.rules_per_gpu else "first"} {n_sample} of {args.rules_per_gpu} rules '
+                       f'on the full {n}-state table '
                        f'(nnz={nnz_s}), merged-mode CPU port of compute-dy/dt, {cores} worker processes, '
                        f'{t_cpu:.1f} s'),
                seconds=t_cpu, states_expanded_per_s=(counters['ext_nodes'] + counters['worlds']) / t_cpu,
                reference_equivalent_work=_guarded(literal_vs_merged, args, rules))
 
+    def against_cpu():
+      if n_sample == args.rules_per_gpu:
+        gpu_out = out.cpu().numpy()
+      else:
+        sample_tag = tag + f'-first{n_sample}'
+        mt.register_rule_set(sample_tag, args.size_a, sample)
+        sample_model = dev.DeviceModel(sample_tag, args.cl_k)
+        gpu_out = sample_model.rhs(p).cpu().numpy()
+        mt.u_lib.tapes_release_model(sample_tag.encode(), args.cl_k)
+      scale = float(abs(cpu_out).max())
+      err = float(abs(gpu_out - cpu_out).max())
+      return dict(rules_compared=n_sample, states_compared=int(n), max_abs_err=err, max_abs_dy_dt=scale,
+                  max_rel_err=err / max(scale, 1e-300), tolerance=1e-12, ok=bool(err <= 1e-12 * scale and scale > 0),
+                  note='GPU dy/dt of the timed workload against the CPU port on the same rules and table, '
+                       'error relative to the largest |dy/dt|')
+    parity['vs_cpu_port'] = _guarded(against_cpu)
+    del cpu_out
+
   if rank == 0:
+    parity['ok'] = bool(parity['sum_ok'] and parity.get('vs_cpu_port', {}).get('ok', True))
+    exchange = None
+    if world > 1:
+      exchange = ('fused into the product kernel: partial flux stored into the owner\'s slots over NVLink peer memory, '
+                  f'owners sum and broadcast one round behind ({max(args.chunks, 1)} rounds)' if args.exchange == 'peer' else
+                  f'all-reduce of dy/dt in {max(args.chunks, 1)} row blocks overlapped with the product'
+                  if args.exchange == 'allreduce' else
+                  f'flux reduce-scatter + table all-gather, {args.chunks} overlapped row chunks')
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
-                ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f64',
-                data='synthetic',
-                config=dict(workload='synthetic-random-rewrite-rules', size_a=args.size_a, cl_k=args.cl_k,
-                            n_states=n, rules_per_gpu=args.rules_per_gpu, total_rules=args.rules_per_gpu * world,
-                            seed=args.seed, nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total,
-                            parallelism=(f'rules dealt to {world} ranks; exchange per step: '
-                                         + ('fused into the product kernel: partial flux stored into the owner\'s slots '
-                                            f'over NVLink peer memory, owners sum and broadcast one round behind ({max(args.chunks, 1)} rounds)'
-                                            if args.exchange == 'peer' else
-                                            f'all-reduce of dy/dt in {max(args.chunks, 1)} row blocks overlapped with the product'
-                                            if args.exchange == 'allreduce' else
-                                            f'flux reduce-scatter + table all-gather, {args.chunks} overlapped row chunks'))
-                            if world > 1 else 'single GPU',
-                            l2='inputs larger than L2 (table, weights and CSR each exceed 126 MB)'),
+                ms_per_step=ms_step, higher_is_better=True, scaling=args.scaling, vs_baseline=None, dtype='f64',
+                data='synthetic', config=workload_config(args, world),
+                value_is='CSR-equivalent algorithmic bytes per second (a work rate; may exceed the HBM peak)',
+                value_dram_gbs=value_dram, dram_frac=(value_dram / peak) if value_dram else None,
+                structure=dict(nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total, exchange=exchange),
+                parity_check=parity,
                 clocks=clocks.summary(), e2e=e2e,
                 gpu_launches=(int(launches_total / world)
                               + (4 * max(args.chunks, 1) + 1 if world > 1 and args.exchange == 'peer' else 0)) * args.steps,
-                roofline=roofline, roofline_levels=roofline_levels, roofline_expand=roofline_expand, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
+                roofline=roofline, roofline_levels=roofline_levels, roofline_prepass=roofline_prepass,
+                roofline_expand=roofline_expand, cpu_baseline=cpu, rank_compute_ms=rank_ms, exchange_ms=comm_ms,
                 exchange_exposed_ms=(ms_step - max(rank_ms)) if rank_ms else None,
                 states_expanded_per_s=expanded_total / max(expand_kernels_s, 1e-9),
                 states_expanded_per_s_incl_driver_alloc=expanded_total / max(expand_s, 1e-9),

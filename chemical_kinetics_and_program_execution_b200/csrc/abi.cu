@@ -30,9 +30,22 @@ struct Runtime {
 
 std::string g_error;
 Runtime* g_runtime = nullptr;
+
+// What the C ABI hands out as "model": a small record that outlives the structure it names.  The
+// structure itself is shared between the cache and whoever still works on it (a live stepper), so
+// re-registering a tag or releasing a model invalidates the handle instead of leaving a dangling
+// pointer: later calls through it fail with a message, and a stepper created before keeps its
+// structure until it is destroyed.  Handles are never freed (a few bytes per build).
+struct ModelHandle {
+  static constexpr uint64_t kMagic = 0x7461706573423230ull;  // "tapesB20"
+  uint64_t magic = kMagic;
+  std::shared_ptr<tapes::Model> model;
+  std::string what;  // tag and cl_k, for messages
+};
+
 // (tag, cl_k, part, n_parts); the whole problem is part 0 of 1
 typedef std::tuple<std::string, int, int, int> ModelKey;
-std::map<ModelKey, std::unique_ptr<tapes::Model>> g_models;
+std::map<ModelKey, ModelHandle*> g_models;
 
 void fail(const std::string& msg) {
   g_error = msg;
@@ -66,12 +79,31 @@ bool ensure_cuda() {
   return true;
 }
 
-tapes::Model* get_model(const char* tag, int64_t cl_k, int64_t part = 0, int64_t n_parts = 1) {
+void invalidate(ModelHandle* h) {
+  if (h->model && h->model->stream) cudaStreamSynchronize(h->model->stream);
+  h->model.reset();  // the structure goes once the last stepper working on it is destroyed
+}
+
+// The structure behind a handle, or null (with the error set) when the handle is not one of ours
+// or its structure was released / its tag registered again.
+std::shared_ptr<tapes::Model> resolve(void* handle) {
+  ModelHandle* h = (ModelHandle*)handle;
+  if (!h) { fail("null model"); return nullptr; }
+  if (h->magic != ModelHandle::kMagic) { fail("not a model handle"); return nullptr; }
+  if (!h->model) {
+    fail("model " + h->what + " was invalidated (its tag was registered again, or it was released); fetch it again with tapes_model");
+    return nullptr;
+  }
+  return h->model;
+}
+
+ModelHandle* get_model(const char* tag, int64_t cl_k, int64_t part = 0, int64_t n_parts = 1) {
   tapes::register_builtin_problems();
+  if (!tag) { fail("null tag"); return nullptr; }
   if (n_parts < 1 || part < 0 || part >= n_parts) { fail("part must be in 0..n_parts-1"); return nullptr; }
   const ModelKey key(std::string(tag), (int)cl_k, (int)part, (int)n_parts);
   auto it = g_models.find(key);
-  if (it != g_models.end()) return it->second.get();
+  if (it != g_models.end()) return it->second;
   const tapes::Problem* prob = tapes::find_problem(tag);
   if (!prob) { fail(std::string("unknown problem tag: ") + tag); return nullptr; }
   if (!ensure_cuda()) return nullptr;
@@ -108,13 +140,30 @@ tapes::Model* get_model(const char* tag, int64_t cl_k, int64_t part = 0, int64_t
       }
     }
     m->stats.host_enumerate_ms = ms;
-    tapes::Model* raw = m.get();
-    g_models[key] = std::move(m);
-    return raw;
+    ModelHandle* h = new ModelHandle();
+    h->model = std::shared_ptr<tapes::Model>(m.release());
+    h->what = std::string(tag) + " (cl_k = " + std::to_string(cl_k) + ")";
+    g_models[key] = h;
+    return h;
   } catch (const std::exception& ex) {
     fail(std::string("building ") + tag + " k=" + std::to_string(cl_k) + " failed: " + ex.what());
     return nullptr;
   }
+}
+
+// Invalidates the handles of every cached structure of `tag` (cl_k < 0: all window lengths).
+int drop_models_of(const std::string& tag, int cl_k) {
+  int dropped = 0;
+  for (auto it = g_models.begin(); it != g_models.end();) {
+    if (std::get<0>(it->first) == tag && (cl_k < 0 || std::get<1>(it->first) == cl_k)) {
+      invalidate(it->second);
+      it = g_models.erase(it);
+      ++dropped;
+    } else {
+      ++it;
+    }
+  }
+  return dropped;
 }
 
 }  // namespace
@@ -128,6 +177,7 @@ void* setup_gambit(void) {
 
 void cleanup_gambit(void* handle) {
   (void)handle;
+  for (auto& kv : g_models) invalidate(kv.second);
   g_models.clear();
   if (g_runtime && g_runtime->cuda_ok) tapes::release_build_scratch();
   if (g_runtime) { delete g_runtime; g_runtime = nullptr; }
@@ -144,15 +194,41 @@ int64_t c_register_problems(int64_t n) {
   return n + 1;
 }
 
+// The reference has no error channel here: a failing compute-dy/dt never returns (the Scheme error
+// handler drops into a REPL, framework/tapes_py_interface.scm:42-44, 81).  The binding of the
+// unmodified framework/markov_tapes.py:279-288 hands in a zero-filled result buffer and checks
+// nothing, so returning with the buffer untouched would let odeint / solve_ivp integrate dy/dt = 0
+// and report a plausible trajectory.  A failed call therefore poisons the result: every entry NaN
+// when the table size is known, the first entry when it is not (the buffer has at least one), and
+// with TAPES_ABORT_ON_ERROR=1 the process stops like the reference does.
+static void poison_result(const char* tag, int64_t cl_k, double* probs_out) {
+  if (const char* e = std::getenv("TAPES_ABORT_ON_ERROR"))
+    if (std::atoi(e) != 0) std::abort();
+  if (!probs_out) return;
+  const double nan = std::nan("");
+  uint64_t n = 1;
+  const tapes::Problem* prob = tag ? tapes::find_problem(tag) : nullptr;
+  if (prob && prob->alphabet >= 1 && cl_k >= 1 && cl_k <= 32) {
+    for (int64_t i = 0; i < cl_k && n < (1ull << 32); ++i) n *= (uint64_t)prob->alphabet;
+    if (n >= (1ull << 32)) n = 1;  // no such table can have been allocated for this library
+  }
+  for (uint64_t i = 0; i < n; ++i) probs_out[i] = nan;
+}
+
 void c_compute_dy_dt(const char* tag, int64_t cl_k, int64_t debug, const double* probs_in,
                      double* probs_out) {
   (void)debug;
-  tapes::Model* m = get_model(tag, cl_k);
-  if (!m) return;
+  g_error.clear();  // the message describes this call, not an earlier unchecked one
+  ModelHandle* h = get_model(tag, cl_k);
+  std::shared_ptr<tapes::Model> m = h ? resolve(h) : nullptr;
+  if (!m) { poison_result(tag, cl_k, probs_out); return; }
+  if (!probs_in || !probs_out) { fail("c_compute_dy_dt: null buffer"); poison_result(tag, cl_k, probs_out); return; }
   try {
     tapes::rhs_host(*m, probs_in, probs_out);
   } catch (const std::exception& ex) {
     fail(ex.what());
+    cudaGetLastError();
+    poison_result(tag, cl_k, probs_out);
   }
 }
 
@@ -178,9 +254,7 @@ int tapes_register_rules(const char* tag, int64_t alphabet, int64_t n_rules, con
       r.rate = rate[i]; r.select_weight = select_weight[i];
     }
     tapes::register_problem(tag, (int)alphabet, tapes::body_from_rewrite_rules(std::move(rules)));
-    // a re-registered tag invalidates cached structures
-    for (auto it = g_models.begin(); it != g_models.end();)
-      it = (std::get<0>(it->first) == tag) ? g_models.erase(it) : std::next(it);
+    drop_models_of(tag, -1);  // a re-registered tag invalidates cached structures
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());
@@ -203,8 +277,7 @@ int tapes_register_program(const char* tag, int64_t alphabet, int64_t n_nodes, c
     t.child.assign(child, child + n_children);
     t.weight.assign(weight, weight + n_weights);
     tapes::register_problem(tag, (int)alphabet, tapes::body_from_program(std::move(t), (int)alphabet));
-    for (auto it = g_models.begin(); it != g_models.end();)  // a re-registered tag invalidates cached structures
-      it = (std::get<0>(it->first) == tag) ? g_models.erase(it) : std::next(it);
+    drop_models_of(tag, -1);  // a re-registered tag invalidates cached structures
     return 0;
   } catch (const std::exception& ex) {
     fail(std::string("register_program: ") + ex.what());
@@ -219,12 +292,8 @@ void* tapes_model_part(const char* tag, int64_t cl_k, int64_t part, int64_t n_pa
 }
 
 int tapes_release_model(const char* tag, int64_t cl_k) {  // the whole problem and every part of it
-  int released = 0;
-  for (auto it = g_models.begin(); it != g_models.end();) {
-    if (std::get<0>(it->first) == tag && std::get<1>(it->first) == (int)cl_k) { it = g_models.erase(it); ++released; }
-    else ++it;
-  }
-  return released ? 0 : 1;
+  if (!tag) return 1;
+  return drop_models_of(tag, (int)cl_k) ? 0 : 1;
 }
 
 int64_t tapes_rule_parts(const char* tag, int64_t cl_k, int64_t n_parts, int32_t* owner, double* cost) {
@@ -247,9 +316,10 @@ int64_t tapes_rule_parts(const char* tag, int64_t cl_k, int64_t n_parts, int32_t
 }
 
 int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream) {
-  if (!model) { fail("null model"); return 1; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
   try {
-    tapes::rhs_device(*(tapes::Model*)model, d_probs_in, d_probs_out, (cudaStream_t)cuda_stream);
+    tapes::rhs_device(*mp, d_probs_in, d_probs_out, (cudaStream_t)cuda_stream);
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());
@@ -258,9 +328,10 @@ int tapes_rhs_device(void* model, const double* d_probs_in, double* d_probs_out,
 }
 
 int tapes_weights_device(void* model, const double* d_probs_in, void* cuda_stream) {
-  if (!model) { fail("null model"); return 1; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
   try {
-    tapes::weights_device(*(tapes::Model*)model, d_probs_in, (cudaStream_t)cuda_stream);
+    tapes::weights_device(*mp, d_probs_in, (cudaStream_t)cuda_stream);
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());
@@ -269,9 +340,10 @@ int tapes_weights_device(void* model, const double* d_probs_in, void* cuda_strea
 }
 
 int tapes_flux_rows_device(void* model, double* d_probs_out, int64_t row_lo, int64_t row_hi, void* cuda_stream) {
-  if (!model) { fail("null model"); return 1; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
   try {
-    tapes::flux_rows_device(*(tapes::Model*)model, d_probs_out, (uint64_t)row_lo, (uint64_t)row_hi,
+    tapes::flux_rows_device(*mp, d_probs_out, (uint64_t)row_lo, (uint64_t)row_hi,
                             (cudaStream_t)cuda_stream);
     return 0;
   } catch (const std::exception& ex) {
@@ -338,9 +410,11 @@ void* tapes_peer_group_create(int world, int rank, int64_t block, int rounds, vo
 void tapes_peer_group_destroy(void* group) { delete (tapes::PeerGroup*)group; }
 
 int tapes_peer_rhs(void* group, void* model, const double* d_probs_in, void* cuda_stream) {
-  if (!group || !model) { fail("null group or model"); return 1; }
+  if (!group) { fail("null group"); return 1; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
   try {
-    tapes::Model& m = *(tapes::Model*)model;
+    tapes::Model& m = *mp;
     tapes::peer_rhs(*(tapes::PeerGroup*)group, m, d_probs_in, cuda_stream ? (cudaStream_t)cuda_stream : m.stream);
     return 0;
   } catch (const std::exception& ex) {
@@ -361,10 +435,11 @@ int tapes_peer_group_error(void* group) {
 
 int tapes_rhs_profile(void* model, const double* d_probs_in, double* d_probs_out, void* cuda_stream,
                       double* phase_ms, int capacity) {
-  if (!model) { fail("null model"); return 1; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
   try {
     float ms[3] = {0, 0, 0};
-    tapes::rhs_device_profiled(*(tapes::Model*)model, d_probs_in, d_probs_out, (cudaStream_t)cuda_stream, ms);
+    tapes::rhs_device_profiled(*mp, d_probs_in, d_probs_out, (cudaStream_t)cuda_stream, ms);
     for (int i = 0; i < 3 && i < capacity; ++i) phase_ms[i] = ms[i];
     return 0;
   } catch (const std::exception& ex) {
@@ -374,15 +449,17 @@ int tapes_rhs_profile(void* model, const double* d_probs_in, double* d_probs_out
 }
 
 int tapes_sync(void* model) {
-  if (!model) { fail("null model"); return 1; }
-  cudaError_t err = cudaStreamSynchronize(((tapes::Model*)model)->stream);
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
+  cudaError_t err = cudaStreamSynchronize(mp->stream);
   if (err != cudaSuccess) { fail(cudaGetErrorString(err)); return 1; }
   return 0;
 }
 
 int tapes_model_info(void* model, int64_t* out, int capacity) {
-  if (!model) { fail("null model"); return 0; }
-  const tapes::Model& head = *(tapes::Model*)model;
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 0;
+  const tapes::Model& head = *mp;
   const int kFields = 32;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
@@ -416,8 +493,9 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
 }
 
 int tapes_model_set(void* model, const char* key, int64_t value) {
-  if (!model) { fail("null model"); return 1; }
-  tapes::Model& head = *(tapes::Model*)model;
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
+  tapes::Model& head = *mp;
   int tapes::Model::*field = nullptr;
   if (std::strcmp(key, "spmv_lanes") == 0 && (value == 1 || value == 2 || value == 4 || value == 8 || value == 16))
     field = &tapes::Model::spmv_group;
@@ -445,8 +523,9 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
 }
 
 int tapes_model_timing(void* model, double* out, int capacity) {
-  if (!model) { fail("null model"); return 0; }
-  const tapes::Model& head = *(tapes::Model*)model;
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 0;
+  const tapes::Model& head = *mp;
   double v[5] = {0, 0, 0, 0, 0};
   for (size_t part = 0; part <= head.more.size(); ++part) {  // the parts of a composite model are built in turn
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
@@ -459,8 +538,9 @@ int tapes_model_timing(void* model, double* out, int capacity) {
 }
 
 int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
-  if (!model) { fail("null model"); return 1; }
-  tapes::Model& m = *(tapes::Model*)model;
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
+  tapes::Model& m = *mp;
   if (!m.more.empty()) { fail("export_csr: composite model (forest above the 31-bit node ids); export shares made with tapes_model_part instead"); return 1; }
   cudaStreamSynchronize(m.stream);
   uint32_t* d_entries = m.entries;
@@ -485,8 +565,9 @@ int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
 }
 
 int tapes_export_node_weights(void* model, double* weights) {
-  if (!model) { fail("null model"); return 1; }
-  tapes::Model& m = *(tapes::Model*)model;
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
+  tapes::Model& m = *mp;
   if (!m.more.empty()) { fail("export_node_weights: composite model; export shares made with tapes_model_part instead"); return 1; }
   cudaStreamSynchronize(m.stream);
   if (m.n_nodes && cudaMemcpy(weights, m.node_w, m.n_nodes * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
@@ -506,7 +587,8 @@ void* tapes_dop853_create(void* model, const double* tableau, const double* y0, 
 
 void* tapes_dop853_create_peer(void* model, void* group, const double* tableau, const double* y0, double t0,
                                double t_bound, double rtol, double atol, double max_step, double first_step) {
-  if (!model) { fail("null model"); return nullptr; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return nullptr;
   try {
     tapes::Dop853Tableau tab;
     const double* p = tableau;
@@ -516,7 +598,7 @@ void* tapes_dop853_create_peer(void* model, void* group, const double* tableau, 
     std::memcpy(tab.E3, p, sizeof(tab.E3)); p += 13;
     std::memcpy(tab.E5, p, sizeof(tab.E5)); p += 13;
     std::memcpy(tab.D, p, sizeof(tab.D));
-    return (void*)tapes::dop853_create(*(tapes::Model*)model, (tapes::PeerGroup*)group, tab, y0, t0, t_bound, rtol,
+    return (void*)tapes::dop853_create(mp, (tapes::PeerGroup*)group, tab, y0, t0, t_bound, rtol,
                                        atol, max_step, first_step);
   } catch (const std::exception& ex) {
     fail(ex.what());
@@ -583,9 +665,10 @@ int tapes_dop853_info(void* solver, double* out6) {
 
 int tapes_observe(void* model, const double* d_y, const int64_t* offset, const int64_t* stride,
                   const int64_t* count, int64_t n_obs, double* out) {
-  if (!model) { fail("null model"); return 1; }
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
   try {
-    tapes::observe_strided(*(tapes::Model*)model, d_y, offset, stride, count, n_obs, out);
+    tapes::observe_strided(*mp, d_y, offset, stride, count, n_obs, out);
     return 0;
   } catch (const std::exception& ex) {
     fail(ex.what());

@@ -30,9 +30,7 @@ constexpr int kThreads = 256;
 
 template <typename T>
 T* dalloc(size_t n, cudaStream_t st) {
-  void* p = nullptr;
-  TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st));
-  return (T*)p;
+  return (T*)pool_alloc(std::max<size_t>(n, 1) * sizeof(T), st);
 }
 template <typename T>
 void dfree(T*& p, cudaStream_t st) {
@@ -755,6 +753,53 @@ Consts make_consts(const Model& m) {
 
 }  // namespace
 
+cudaMemPool_t library_pool() {
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  TAPES_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) throw std::runtime_error("device index out of range");
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    TAPES_CUDA_CHECK(cudaMemPoolCreate(&pools[dev], &props));
+    uint64_t keep = 2048ull << 20;
+    if (const char* e = std::getenv("TAPES_POOL_KEEP_MB")) keep = std::strtoull(e, nullptr, 10) << 20;
+    TAPES_CUDA_CHECK(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+  }
+  return pools[dev];
+}
+
+void* pool_alloc(size_t bytes, cudaStream_t st) {
+  void* p = nullptr;
+  TAPES_CUDA_CHECK(cudaMallocFromPoolAsync(&p, std::max<size_t>(bytes, 1), library_pool(), st));
+  return p;
+}
+
+namespace {
+bool capturing(cudaStream_t st) {
+  if (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) return false;
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &status) != cudaSuccess) { cudaGetLastError(); return false; }
+  return status != cudaStreamCaptureStatusNone;
+}
+}  // namespace
+
+void begin_use(Model& m, cudaStream_t st) {
+  if (!m.in_use || m.last_stream == st || capturing(st)) return;  // a capturing caller orders its graph itself
+  TAPES_CUDA_CHECK(cudaStreamWaitEvent(st, m.busy, 0));
+}
+
+void end_use(Model& m, cudaStream_t st) {
+  if (capturing(st)) return;
+  if (!m.busy) TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&m.busy, cudaEventDisableTiming));
+  TAPES_CUDA_CHECK(cudaEventRecord(m.busy, st));
+  m.last_stream = st;
+  m.in_use = true;
+}
+
 void* DeviceArena::take(size_t n_bytes) {
   n_bytes = (std::max<size_t>(n_bytes, 1) + 255) & ~(size_t)255;
   bytes += n_bytes;
@@ -799,6 +844,7 @@ Model::~Model() {
   if (h_pinned) cudaFreeHost(h_pinned);
   if (d_obs_spec) cudaFree(d_obs_spec);
   if (d_obs_out) cudaFree(d_obs_out);
+  if (busy) cudaEventDestroy(busy);
   arena.release();
   if (copy_stream) {
     cudaStreamDestroy(copy_stream);
@@ -834,6 +880,7 @@ void sort_groups(const uint64_t* ptr, uint64_t n_groups, uint32_t* vals, cudaStr
 void release_build_scratch() {
   Slab* slabs = build_scratch();
   for (int i = 0; i < 3; ++i) slabs[i].release();
+  if (cudaMemPoolTrimTo(library_pool(), 0) != cudaSuccess) cudaGetLastError();
 }
 
 std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) {
@@ -854,14 +901,6 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.own_stream = true;
   }
   cudaStream_t st = m.stream;
-  {
-    int dev = 0;
-    TAPES_CUDA_CHECK(cudaGetDevice(&dev));
-    cudaMemPool_t pool;
-    TAPES_CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, dev));
-    uint64_t keep = ~0ull;
-    TAPES_CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-  }
 
   const Consts c = make_consts(m);
   const uint64_t W = m.n_states, M = m.pow_a[m.k - 1];
@@ -1454,27 +1493,38 @@ int64_t rhs_launch_count(const Model& m) {
 
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
   cudaStream_t st = stream ? stream : m.stream;
+  begin_use(m, st);
   launch_all_weights(m, d_p, st);
   launch_flux(m, d_out, 0, m.n_states, st);
+  end_use(m, st);
 }
 
 void rhs_device_fused(Model& m, const double* d_p, double* d_out, const StageUpdate& up, cudaStream_t stream) {
   cudaStream_t st = stream ? stream : m.stream;
+  begin_use(m, st);
   launch_all_weights(m, d_p, st);
   launch_flux(m, d_out, 0, m.n_states, st, &up);
+  end_use(m, st);
 }
 
 void weights_device(Model& m, const double* d_p, cudaStream_t stream) {
-  launch_all_weights(m, d_p, stream ? stream : m.stream);
+  cudaStream_t st = stream ? stream : m.stream;
+  begin_use(m, st);
+  launch_all_weights(m, d_p, st);
+  end_use(m, st);
 }
 
 void flux_rows_device(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cudaStream_t stream) {
   if (row_hi > m.n_states || row_lo > row_hi) throw std::runtime_error("row range outside the state table");
-  launch_flux(m, d_out, row_lo, row_hi, stream ? stream : m.stream);
+  cudaStream_t st = stream ? stream : m.stream;
+  begin_use(m, st);
+  launch_flux(m, d_out, row_lo, row_hi, st);
+  end_use(m, st);
 }
 
 void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_t stream, float ms[3]) {
   cudaStream_t st = stream ? stream : m.stream;
+  begin_use(m, st);
   cudaEvent_t ev[4];
   for (int i = 0; i < 4; ++i) TAPES_CUDA_CHECK(cudaEventCreate(&ev[i]));
   ms[0] = ms[1] = ms[2] = 0.0f;
@@ -1494,9 +1544,19 @@ void rhs_device_profiled(Model& m, const double* d_p, double* d_out, cudaStream_
     }
   }
   for (int i = 0; i < 4; ++i) cudaEventDestroy(ev[i]);
+  end_use(m, st);
 }
 
+namespace {
+void rhs_host_impl(Model& m, const double* h_p, double* h_out);
+}
 void rhs_host(Model& m, const double* h_p, double* h_out) {
+  begin_use(m, m.stream);
+  rhs_host_impl(m, h_p, h_out);
+  m.in_use = false;  // both streams were synchronised: nothing of this model is in flight
+}
+namespace {
+void rhs_host_impl(Model& m, const double* h_p, double* h_out) {
   const uint64_t n = m.n_states;
   const size_t bytes = (size_t)n * 8;
   if (!m.d_in) {
@@ -1540,5 +1600,6 @@ void rhs_host(Model& m, const double* h_p, double* h_out) {
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.copy_stream));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
 }
+}  // namespace
 
 }  // namespace tapes

@@ -183,6 +183,14 @@ struct Model {
   BuildStats stats;
   int64_t launches_per_rhs = 0;
 
+  // Every right-hand side writes scratch of the model (rule_w, node_w, marg, the ratio tables,
+  // g_total) and the caller picks the stream.  `busy` is recorded on the stream of the most recent
+  // call; a call that arrives on another stream waits for it first (begin_use / end_use below), so
+  // work of two streams never overlaps on the scratch.
+  cudaEvent_t busy = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool in_use = false;
+
   // A problem whose forest would not fit the 31-bit node ids of one structure is built as several
   // structures over disjoint shares of its flux rules (rule_table_part): this one plus `more`, all
   // on this model's stream.  Every right-hand-side entry point below evaluates them one after the
@@ -209,8 +217,21 @@ struct Model {
   ~Model();
 };
 
-// Frees the scratch memory small builds leave behind for the next build.
+// Frees the scratch memory small builds leave behind for the next build and returns the unused
+// part of the library's memory pool to the driver.
 void release_build_scratch();
+
+// Stream-ordered allocations (build temporaries, solver vectors) come from a pool of the library's
+// own, one per device, so that the process-wide default pool keeps its settings and what this
+// library hoards stays bounded: freed memory above the release threshold (2 GiB, TAPES_POOL_KEEP_MB)
+// goes back to the driver at the next synchronisation.
+cudaMemPool_t library_pool();
+void* pool_alloc(size_t bytes, cudaStream_t st);  // throws std::runtime_error
+
+// Ordering between streams that use one model (see Model::busy).  Every entry point that touches
+// the model's scratch calls begin_use before its first launch and end_use after its last.
+void begin_use(Model& m, cudaStream_t st);
+void end_use(Model& m, cudaStream_t st);
 
 // Thrown by build_model when a forest does not fit the 32-bit indices of one structure.
 struct TooLarge : std::runtime_error {

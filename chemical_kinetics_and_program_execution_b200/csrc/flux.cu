@@ -29,9 +29,7 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 
 template <typename T>
 T* dalloc(size_t n, cudaStream_t st) {
-  void* p = nullptr;
-  TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st));
-  return (T*)p;
+  return (T*)pool_alloc(std::max<size_t>(n, 1) * sizeof(T), st);
 }
 
 // One warp merges the (ascending) rows of its 32 states into one ascending stream and cuts it into
@@ -508,6 +506,7 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   TAPES_CUDA_CHECK(cudaEventRecord(g.join, g.side));
   TAPES_CUDA_CHECK(cudaStreamWaitEvent(st, g.join, 0));
   TAPES_CUDA_CHECK(cudaGetLastError());
+  end_use(m, st);  // the product kernels read the model's weights after weights_device's own record
 }
 
 int peer_group_error(PeerGroup& g) {

@@ -146,6 +146,7 @@ __global__ void observe_kernel(const double* __restrict__ y, const int64_t* __re
 }  // namespace
 
 struct Dop853 {
+  std::shared_ptr<Model> keep;  // the structure stays alive as long as the solver
   Model* m = nullptr;
   PeerGroup* peer = nullptr;
   uint64_t n = 0;
@@ -172,13 +173,12 @@ struct Dop853 {
 
 namespace {
 
-// Solver vectors come from the stream-ordered pool, which keeps freed memory (the release threshold
-// is raised in build_model): creating a solver per integration then costs no driver allocation,
-// which takes anything from microseconds to milliseconds per call depending on the box.
+// Solver vectors come from the library's stream-ordered pool (engine.h library_pool), which keeps
+// up to its release threshold of freed memory: creating a solver per integration of a small problem
+// then costs no driver allocation, which takes anything from microseconds to milliseconds per call
+// depending on the box.
 double* dvec(uint64_t n, cudaStream_t st) {
-  void* p = nullptr;
-  TAPES_CUDA_CHECK(cudaMallocAsync(&p, std::max<uint64_t>(n, 1) * sizeof(double), st));
-  return (double*)p;
+  return (double*)pool_alloc(std::max<uint64_t>(n, 1) * sizeof(double), st);
 }
 
 void fun(Dop853* s, const double* y, double* out) {
@@ -283,10 +283,13 @@ double attempt(Dop853* s, double h) {
 
 }  // namespace
 
-Dop853* dop853_create(Model& m, PeerGroup* peer, const Dop853Tableau& tab, const double* h_y0, double t0,
-                      double t_bound, double rtol, double atol, double max_step, double first_step) {
+Dop853* dop853_create(std::shared_ptr<Model> model, PeerGroup* peer, const Dop853Tableau& tab, const double* h_y0,
+                      double t0, double t_bound, double rtol, double atol, double max_step, double first_step) {
+  if (!model) throw std::runtime_error("null model");
+  Model& m = *model;
   Dop853* s = new Dop853();
   try {
+    s->keep = model;
     s->m = &m; s->peer = peer; s->n = m.n_states; s->st = m.stream; s->tab = tab;
     s->t = t0; s->t_old = t0; s->t_bound = t_bound;
     s->direction = t_bound != t0 ? (t_bound > t0 ? 1.0 : -1.0) : 1.0;

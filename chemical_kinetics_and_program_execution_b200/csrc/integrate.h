@@ -10,6 +10,7 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
 
 #include "engine.h"
 
@@ -30,8 +31,10 @@ struct Dop853;
 // peer (may be null): the ranks that evaluate the problem together.  Every rank then runs this
 // stepper on the full table: the right-hand side is peer_rhs (identical bits on all ranks), so
 // error norms and step sizes agree without further communication.
-Dop853* dop853_create(Model& m, PeerGroup* peer, const Dop853Tableau& tab, const double* h_y0, double t0,
-                      double t_bound, double rtol, double atol, double max_step, double first_step);
+// The solver shares ownership of the structure: releasing the model or registering its tag again
+// while the solver lives leaves the solver working on the structure it was created with.
+Dop853* dop853_create(std::shared_ptr<Model> model, PeerGroup* peer, const Dop853Tableau& tab, const double* h_y0,
+                      double t0, double t_bound, double rtol, double atol, double max_step, double first_step);
 void dop853_destroy(Dop853* s);
 
 // One solver.step(): returns 0 = running, 1 = finished, -1 = failed (step size too small).

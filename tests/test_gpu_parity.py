@@ -667,3 +667,75 @@ def test_fused_stage_update_is_bit_identical(mt, p0_fixtures, monkeypatch):
                                         rtol=1e-10, atol=1e-12, want_stats=True))
   assert runs[0][1] == runs[1][1]
   assert numpy.array_equal(runs[0][0], runs[1][0])
+
+
+def test_reregistering_a_tag_invalidates_handles_instead_of_freeing_under_them(mt, device):
+  """registering a tag again (or releasing the model) used to free the structure under
+  live DeviceModel handles and steppers.  Now the old handle is refused with a message, a stepper
+  created before keeps working on the structure it was created with, and a fresh handle works."""
+  import torch
+  rules = configs.random_rule_set(3, 4, seed=11)
+  tag = 'reregistered-rule-set'
+  mt.register_rule_set(tag, 3, rules)
+  old = device.DeviceModel(tag, 4)
+  p = torch.from_numpy(configs.dirichlet_product_table(3, 4, 5)).cuda()
+  want = old.rhs(p).cpu().numpy()
+  solver_states = mt.ode_integrate_device(tag=tag, size_a=3, cl_k=4, p0=p.cpu().numpy(), ts=[0.0, 0.5],
+                                          rtol=1e-10, atol=1e-12)
+  mt.register_rule_set(tag, 3, rules)  # same rules: same answers from a new structure
+  with pytest.raises(RuntimeError, match='invalidated'):
+    old.rhs(p)
+  with pytest.raises(RuntimeError, match='invalidated'):
+    old.node_weights()
+  fresh = device.DeviceModel(tag, 4)
+  assert numpy.array_equal(fresh.rhs(p).cpu().numpy(), want)
+  again = mt.ode_integrate_device(tag=tag, size_a=3, cl_k=4, p0=p.cpu().numpy(), ts=[0.0, 0.5], rtol=1e-10, atol=1e-12)
+  assert numpy.array_equal(again, solver_states)
+  assert mt.u_lib.tapes_release_model(tag.encode(), 4) == 0
+  with pytest.raises(RuntimeError, match='invalidated'):
+    fresh.rhs(p)
+
+
+def test_two_streams_on_one_model_do_not_overlap_on_its_scratch(mt, device):
+  """the weights of a right-hand side live in per-model scratch and the caller picks the
+  stream.  Calls on different streams are ordered by the library (engine.h Model::busy): results of
+  interleaved asynchronous calls equal those of synchronised ones."""
+  import torch
+  tag, size_a, cl_k = 'ex4-chemical-turing', 9, 5
+  model = device.DeviceModel(tag, cl_k)
+  tables = [torch.from_numpy(configs.markov_table(size_a, cl_k, s)).cuda() for s in range(4)]
+  want = []
+  for t in tables:
+    want.append(model.rhs(t).clone())
+    torch.cuda.synchronize()
+  f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
+  host = [t.cpu().numpy() for t in tables]
+  streams = [torch.cuda.Stream() for _ in range(3)]
+  torch.cuda.synchronize()
+  for rep in range(20):
+    outs = []
+    for i, t in enumerate(tables):
+      with torch.cuda.stream(streams[(rep + i) % 3]):
+        outs.append(model.rhs(t))        # asynchronous, caller's stream
+      if i == 1:
+        got_host = f(host[2], 0.0)        # the model's own stream, right behind an asynchronous call
+        assert numpy.array_equal(got_host, want[2].cpu().numpy())
+    torch.cuda.synchronize()
+    for o, w in zip(outs, want):
+      assert torch.equal(o, w)
+
+
+def test_failure_through_the_reference_binding_is_loud(mt):
+  """A failing c_compute_dy_dt on a box WITH a device: the result buffer of the reference's binding
+  (zero-filled, framework/markov_tapes.py:279) comes back NaN, not zero."""
+  from test_abi import reference_binding, reference_dy_dt
+  u_lib = reference_binding()
+  out = reference_dy_dt(u_lib, 'no-such-problem', 3, numpy.full(8, 0.125))
+  assert numpy.isnan(out[0])
+  # cl_k = 0 is refused by the engine after the tag was found: the table size (A^0 = 1) is known
+  out = reference_dy_dt(u_lib, 'ex1-radioactive-decay', 0, numpy.full(1, 1.0))
+  assert numpy.isnan(out).all()
+  mt.u_lib.tapes_clear_error()
+  # and the next good call is not disturbed by the message the failures left behind
+  good = mt.get_dy_dt(tag='__canary_problem_radioactive_decay', size_a=2, cl_k=3)(numpy.full(8, 0.125), 0.0)
+  assert good.tolist() == [0.375, 0.125, 0.125, -0.125, 0.125, -0.125, -0.125, -0.375]
