@@ -10,6 +10,8 @@ if ROOT not in sys.path:
   sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+if GOLDEN not in sys.path:
+  sys.path.insert(0, GOLDEN)  # the generating scripts hold the lists of observables the tests read
 
 
 def pytest_configure(config):

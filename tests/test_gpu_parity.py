@@ -599,6 +599,31 @@ def test_ex2_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
     assert abs(ys[-1] - want).max() <= 1e-10 * abs(want).max()
 
 
+def test_ex2_island_probabilities_follow_the_analytic_approximation(mt, p0_fixtures):
+  """BASELINE config 1's own check (examples/ex2_ferromagnet_tape.py:112-135, plots only in the
+  reference): island probabilities p(0 1^L 0), L = 1..5, of the cl_k = 7 run against the reference's
+  analytic approximation (examples/ex2_ferromagnet_analytic.py:39-61, golden produced by importing
+  that module: tests/golden/make_golden_round2.py).  The approximation neglects island merging and
+  correlations beyond nearest neighbours: the two agree to a few per cent (L <= 4: 5 %; L = 5, whose
+  probabilities are ~1e-5 and which the cl_k = 7 closure resolves least: 15 %), at t = 15, 30, 60."""
+  import os
+  from conftest import GOLDEN
+  gold = numpy.load(os.path.join(GOLDEN, 'ex2_analytic.npz'))
+  k = 7
+  p0 = dense(p0_fixtures[f'ex2_k{k}_idx'], p0_fixtures[f'ex2_k{k}_val'], 2 ** k)
+  ts = numpy.linspace(0, 60, 1001)
+  assert numpy.array_equal(ts, gold['ts'])
+  ys = mt.ode_integrate(tag='ex2-ferromagnetic-chain', size_a=2, cl_k=k, p0=p0, ts=ts,
+                        odeint_kwargs=dict(rtol=1e-9, atol=1e-9))
+  table = ys.reshape((len(ys),) + (2,) * k)
+  for length in (1, 2, 3, 4, 5):
+    probs = mt.seq_prob(table, (0, *((1,) * length), 0), num_prefix_indices=1)[0]
+    for i in (250, 500, 1000):
+      want = gold['islands'][i, length - 1]
+      tol = 0.05 if length <= 4 else 0.15
+      assert abs(probs[i] - want) <= tol * want, (length, ts[i], probs[i], want)
+
+
 def test_ex5_trajectory_matches_oracle(mt, trajectories, p0_fixtures):
   p0 = dense(p0_fixtures['ex5_idx'], p0_fixtures['ex5_val'], 5 ** 5)
   ys = mt.ode_integrate_ivp(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=p0,

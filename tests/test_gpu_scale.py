@@ -101,3 +101,38 @@ def test_full_size_synthetic_properties(mt, device, oracle):
   torch.cuda.synchronize()
   assert float((total - want).abs().max()) <= 1e-13 * float(want.abs().max())
   mt.u_lib.tapes_release_model(b'scale-full', cl_k)
+
+
+def test_ex3_long_chain_trajectory(mt):
+  """BASELINE config 3 end to end: examples/ex3_copolymerization.py:38-64
+  with cl_k = 12 (1.68e7 states) integrated to a fixed horizon, t in [0, 10], DOP853 at
+  rtol = atol = 1e-10, table resident in HBM, the observables of ex3_copolymerization.py:112-118 read
+  on the device.  Golden: the CPU oracle through SciPy's DOP853 with the same settings
+  (tests/golden/make_golden_round2.py).  Same steps on both sides (equal number of right-hand
+  sides), so the trajectories differ through dy/dt rounding only: 1e-12 relative."""
+  import os
+  import time
+  from conftest import GOLDEN
+  from make_golden_round2 import EX3_SEQS
+  gold = numpy.load(os.path.join(GOLDEN, 'ex3_k12_trajectory.npz'))
+  p0 = configs.ex3_p0(12)
+  mt.model_stats(tag='ex3-copolymerization', cl_k=12)  # build outside the timed part
+  t0 = time.perf_counter()
+  series, stats = mt.ode_integrate_device(tag='ex3-copolymerization', size_a=4, cl_k=12, p0=p0, ts=gold['ts'],
+                                          rtol=1e-10, atol=1e-10, observables=EX3_SEQS, return_states=False,
+                                          want_stats=True)
+  seconds = time.perf_counter() - t0
+  print(f'ex3 cl_k=12 to t=10: {seconds:.3f} s, {stats["nfev"]} right-hand sides, {stats["accepted"]} steps')
+  # solve_ivp counts the right-hand sides of the steps only; the dense output adds 3 per step that has
+  # an output time in it on both sides
+  assert stats['nfev'] == int(gold['nfev'][0]), (stats, gold['nfev'])
+  want = gold['observables']
+  assert series.shape == want.shape
+  assert (abs(series - want) <= 1e-12 * abs(want) + 1e-300).all(), abs(series / numpy.where(want == 0, 1, want) - 1).max()
+  states = mt.ode_integrate_device(tag='ex3-copolymerization', size_a=4, cl_k=12, p0=p0, ts=[0.0, 10.0],
+                                   rtol=1e-10, atol=1e-10)
+  end = numpy.zeros(4 ** 12)
+  end[gold['end_idx']] = gold['end_val']
+  close(states[-1], end)
+  assert (abs(states[-1] - end) <= 1e-12 * abs(end) + 1e-18).all()
+  assert abs(states[-1].sum() - 1) < 1e-12

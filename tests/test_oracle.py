@@ -1,5 +1,7 @@
 """CPU tests of the oracle against the reference's known answers and its own invariants."""
 
+import os
+
 import numpy
 import pytest
 import scipy.integrate
@@ -101,3 +103,24 @@ def test_autocatalysis_rule_set(oracle):
   assert abs(lit).max() > 0
   assert abs(lit - mer).max() <= 1e-13 * abs(lit).max()
   assert abs(lit.sum()) <= 1e-13 * abs(lit).sum()
+
+
+def test_ex3_long_chain_golden_is_what_the_oracle_gives(oracle):
+  """tests/golden/ex3_k12_trajectory.npz (BASELINE config 3, used by the GPU suite) is the merged-mode
+  oracle through SciPy's DOP853; regenerating its first output times reproduces it bit for bit."""
+  import scipy.integrate
+  from conftest import GOLDEN
+  from make_golden_round2 import EX3_SEQS, seq_sum
+  from chemical_kinetics_and_program_execution_b200 import configs
+  gold = numpy.load(os.path.join(GOLDEN, 'ex3_k12_trajectory.npz'))
+  f = oracle.get_dy_dt(tag='ex3-copolymerization', size_a=4, cl_k=12, mode=oracle.MERGED)
+  # t_eval does not influence the steps, and the steps up to t = 2 do not depend on what follows:
+  # a terminal event ends the run once t = 2 has been passed
+  def passed(t, y):
+    return t - 2.5
+  passed.terminal = True
+  sol = scipy.integrate.solve_ivp(lambda t, y: f(y, t), (0.0, 10.0), configs.ex3_p0(12), t_eval=[0.0, 1.0, 2.0],
+                                  method='DOP853', rtol=1e-10, atol=1e-10, events=passed)
+  for i in range(3):
+    got = [seq_sum(sol.y[:, i], 4, 12, s) for s in EX3_SEQS]
+    assert got == gold['observables'][i].tolist()
