@@ -21,7 +21,8 @@ SYMBOLS = (
     'tapes_peer_group_destroy', 'tapes_peer_rhs', 'tapes_peer_group_error', 'tapes_dop853_create_peer',
     'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts', 'tapes_register_program',
     'tapes_mc_create', 'tapes_mc_destroy', 'tapes_mc_run', 'tapes_mc_window_counts', 'tapes_mc_fetch',
-    'tapes_mc_sample_ring', 'tapes_program_tree',
+    'tapes_mc_sample_ring', 'tapes_program_tree', 'tapes_observe_sequences', 'tapes_dop853_observe_sequences',
+    'tapes_markov_entropy', 'tapes_dop853_entropy',
 )
 
 _lib = None
@@ -137,6 +138,14 @@ def load():
   lib.tapes_dop853_info.argtypes = [vp, vp]
   lib.tapes_observe.restype = i32
   lib.tapes_observe.argtypes = [vp, vp, vp, vp, vp, i64, vp]
+  lib.tapes_observe_sequences.restype = i32
+  lib.tapes_observe_sequences.argtypes = [vp, vp, i64, vp, vp, dbl, vp]
+  lib.tapes_dop853_observe_sequences.restype = i32
+  lib.tapes_dop853_observe_sequences.argtypes = [vp, i32, i64, vp, vp, dbl, vp]
+  lib.tapes_markov_entropy.restype = i32
+  lib.tapes_markov_entropy.argtypes = [vp, vp, vp]
+  lib.tapes_dop853_entropy.restype = i32
+  lib.tapes_dop853_entropy.argtypes = [vp, i32, vp]
   _lib = lib
   return lib
 
@@ -173,6 +182,14 @@ def model_timing(model):
   load().tapes_model_timing(model, buf.ctypes.data, 5)
   return dict(host_enumerate_ms=float(buf[0]), device_expand_ms=float(buf[1]),
               device_csr_ms=float(buf[2]), device_slices_ms=float(buf[3]), expand_alloc_ms=float(buf[4]))
+
+
+def pack_sequences(seqs):
+  """(seq_ptr[int64], symbols[int32]) of a list of symbol sequences, the form tapes_observe_sequences takes."""
+  seq_ptr = numpy.zeros(len(seqs) + 1, dtype=numpy.int64)
+  seq_ptr[1:] = numpy.cumsum([len(s) for s in seqs])
+  symbols = numpy.ascontiguousarray(numpy.array([int(x) for s in seqs for x in s] or [0], dtype=numpy.int32))
+  return seq_ptr, symbols
 
 
 def rule_table(tag, cl_k):

@@ -676,6 +676,60 @@ int tapes_observe(void* model, const double* d_y, const int64_t* offset, const i
   }
 }
 
+int tapes_observe_sequences(void* model, const double* d_y, int64_t n_seq, const int64_t* seq_ptr,
+                            const int32_t* symbols, double eps, double* out) {
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
+  if (!d_y || !seq_ptr || !symbols || !out) { fail("observe_sequences: null argument"); return 1; }
+  try {
+    tapes::observe_sequences(*mp, d_y, n_seq, seq_ptr, symbols, eps, out);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("observe_sequences: ") + ex.what());
+    return 1;
+  }
+}
+
+int tapes_dop853_observe_sequences(void* solver, int which, int64_t n_seq, const int64_t* seq_ptr,
+                                   const int32_t* symbols, double eps, double* out) {
+  if (!solver) { fail("null solver"); return 1; }
+  if (!seq_ptr || !symbols || !out) { fail("observe_sequences: null argument"); return 1; }
+  try {
+    tapes::Dop853* s = (tapes::Dop853*)solver;
+    const double* src = which == 0 ? tapes::dop853_state(s) : tapes::dop853_dense_buffer(s);
+    tapes::observe_sequences(tapes::dop853_model(s), src, n_seq, seq_ptr, symbols, eps, out);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("observe_sequences: ") + ex.what());
+    return 1;
+  }
+}
+
+int tapes_markov_entropy(void* model, const double* d_y, double* out) {
+  std::shared_ptr<tapes::Model> mp = resolve(model);
+  if (!mp) return 1;
+  if (!d_y || !out) { fail("markov_entropy: null argument"); return 1; }
+  try {
+    *out = tapes::markov_entropy(*mp, d_y);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("markov_entropy: ") + ex.what());
+    return 1;
+  }
+}
+
+int tapes_dop853_entropy(void* solver, int which, double* out) {
+  if (!solver || !out) { fail("null solver"); return 1; }
+  try {
+    tapes::Dop853* s = (tapes::Dop853*)solver;
+    *out = tapes::markov_entropy(tapes::dop853_model(s), which == 0 ? tapes::dop853_state(s) : tapes::dop853_dense_buffer(s));
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("markov_entropy: ") + ex.what());
+    return 1;
+  }
+}
+
 int tapes_check_table(int64_t alphabet, int64_t cl_k, const double* probs, int on_device, double eps_mpp,
                       int64_t max_iterations, double tolerance, double* out6) {
   if (!probs || !out6) { fail("check_table: null argument"); return 1; }

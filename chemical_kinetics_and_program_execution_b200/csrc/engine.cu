@@ -844,6 +844,7 @@ Model::~Model() {
   if (h_pinned) cudaFreeHost(h_pinned);
   if (d_obs_spec) cudaFree(d_obs_spec);
   if (d_obs_out) cudaFree(d_obs_out);
+  if (d_obs_partial) cudaFree(d_obs_partial);
   if (busy) cudaEventDestroy(busy);
   arena.release();
   if (copy_stream) {

@@ -179,6 +179,8 @@ struct Model {
   int64_t* d_obs_spec = nullptr;
   double* d_obs_out = nullptr;
   size_t obs_capacity = 0;
+  double* d_obs_partial = nullptr;  // per-block partial sums of the observables
+  size_t obs_partial_capacity = 0;
 
   BuildStats stats;
   int64_t launches_per_rhs = 0;

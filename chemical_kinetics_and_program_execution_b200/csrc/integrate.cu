@@ -131,16 +131,88 @@ __global__ void dense_eval_kernel(double* __restrict__ out, SevenVecs fv, const 
   out[i] = y + y_old[i];
 }
 
-__global__ void observe_kernel(const double* __restrict__ y, const int64_t* __restrict__ offset,
-                               const int64_t* __restrict__ stride, const int64_t* __restrict__ count,
-                               double* __restrict__ out) {
+// Strided sums over the whole grid: block (b, o) adds the elements  b * chunk <= j < (b + 1) * chunk  of
+// observable o (chunk = ceil(count / gridDim.x)), then one block per observable adds the partial sums in
+// block order.  Fixed launch shape per (count, n_obs), so the sums are reproducible.  A one-symbol
+// observable at 10^8 states touches every sector of the table: one block per observable (the first
+// version) read it through one SM.
+__global__ void __launch_bounds__(kThreads) observe_partials_kernel(const double* __restrict__ y,
+                                                                    const int64_t* __restrict__ offset,
+                                                                    const int64_t* __restrict__ stride,
+                                                                    const int64_t* __restrict__ count,
+                                                                    double* __restrict__ partial) {
+  __shared__ double smem[32];
+  const int o = blockIdx.y;
+  const int64_t off = offset[o], st = stride[o], cnt = count[o];
+  const int64_t chunk = (cnt + gridDim.x - 1) / gridDim.x;
+  const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < cnt ? lo + chunk : cnt;
+  double s = 0.0;
+  for (int64_t j = lo + threadIdx.x; j < hi; j += blockDim.x) s += y[off + j * st];
+  const double r = block_sum(s, smem);
+  if (threadIdx.x == 0) partial[(int64_t)o * gridDim.x + blockIdx.x] = r;
+}
+
+__global__ void observe_final_kernel(const double* __restrict__ partial, int blocks, double* __restrict__ out) {
   __shared__ double smem[32];
   const int o = blockIdx.x;
-  const int64_t off = offset[o], st = stride[o], cnt = count[o];
   double s = 0.0;
-  for (int64_t j = threadIdx.x; j < cnt; j += blockDim.x) s += y[off + j * st];
+  for (int i = threadIdx.x; i < blocks; i += blockDim.x) s += partial[(int64_t)o * blocks + i];
   const double r = block_sum(s, smem);
   if (threadIdx.x == 0) out[o] = r;
+}
+
+// Probability of a sequence longer than the window (framework/markov_tapes.py:223-233): the table entry
+// of the first k symbols times, for every later window, the Markov process parameter
+// clip(p[window], eps, 1) / sum_s clip(p[prefix of the window, s], eps, 1)  (markov_tapes.py:81-104),
+// multiplied in sequence order.  One block per sequence, one thread per window.
+__global__ void observe_long_kernel(const double* __restrict__ y, const int64_t* __restrict__ seq_ptr,
+                                    const int32_t* __restrict__ symbols, const int32_t* __restrict__ which,
+                                    int k, uint32_t A, double eps, double* __restrict__ out) {
+  extern __shared__ double factor[];
+  const int o = blockIdx.x;
+  const int32_t* seq = symbols + seq_ptr[o];
+  const int len = (int)(seq_ptr[o + 1] - seq_ptr[o]);
+  const int windows = len - k + 1;
+  for (int j = threadIdx.x; j < windows; j += blockDim.x) {
+    uint64_t idx = 0;
+    for (int c = 0; c < k; ++c) idx = idx * A + (uint32_t)seq[j + c];
+    if (j == 0) {
+      factor[0] = y[idx];
+    } else {
+      const uint64_t base = idx - idx % A;
+      double total = 0.0;
+      for (uint32_t sym = 0; sym < A; ++sym) total += fmin(fmax(y[base + sym], eps), 1.0);
+      factor[j] = fmin(fmax(y[idx], eps), 1.0) / total;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double current = factor[0];
+    for (int j = 1; j < windows; ++j) current = factor[j] * current;
+    out[which[o]] = current;
+  }
+}
+
+// Entropy rate of the Markov chain the table describes (framework/markov_tapes.py:178-187): with
+// c = clip(p, 1e-280, 1) and the context sums  m[x] = sum_s c[x, s]:  sum_x m[x] * sum_s -(c/m) log(c/m).
+// One thread per context; partial[b] = the block's share, added up in block order afterwards.
+__global__ void __launch_bounds__(kThreads) entropy_partials_kernel(const double* __restrict__ y, uint64_t n_contexts,
+                                                                    uint32_t A, double* __restrict__ partial) {
+  __shared__ double smem[32];
+  double s = 0.0;
+  for (uint64_t x = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; x < n_contexts; x += (uint64_t)gridDim.x * blockDim.x) {
+    const double* row = y + x * A;
+    double m = 0.0;
+    for (uint32_t sym = 0; sym < A; ++sym) m += fmin(fmax(row[sym], 1e-280), 1.0);
+    double h = 0.0;
+    for (uint32_t sym = 0; sym < A; ++sym) {
+      const double cond = fmin(fmax(row[sym], 1e-280), 1.0) / m;
+      h += -cond * log(cond);
+    }
+    s += h * m;
+  }
+  const double r = block_sum(s, smem);
+  if (threadIdx.x == 0) partial[blockIdx.x] = r;
 }
 
 }  // namespace
@@ -445,11 +517,103 @@ void observe_strided(Model& m, const double* d_y, const int64_t* offset, const i
     TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));  // `spec` is pageable and about to change hands
     m.obs_spec.swap(spec);
   }
-  observe_kernel<<<(unsigned)n_obs, 1024, 0, m.stream>>>(d_y, m.d_obs_spec, m.d_obs_spec + n_obs,
-                                                        m.d_obs_spec + 2 * n_obs, m.d_obs_out);
+  int64_t longest = 0;
+  for (int64_t o = 0; o < n_obs; ++o) longest = std::max(longest, count[o]);
+  // about 2048 elements per block, at most 8 blocks per SM's worth over all observables
+  int64_t blocks = std::max<int64_t>(1, std::min<int64_t>((longest + 2047) / 2048, std::max<int64_t>(1, kReduceBlocks / n_obs)));
+  if ((size_t)(n_obs * blocks) > m.obs_partial_capacity) {
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+    if (m.d_obs_partial) cudaFree(m.d_obs_partial);
+    m.d_obs_partial = nullptr; m.obs_partial_capacity = 0;
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&m.d_obs_partial, (size_t)(n_obs * blocks) * sizeof(double)));
+    m.obs_partial_capacity = (size_t)(n_obs * blocks);
+  }
+  observe_partials_kernel<<<dim3((unsigned)blocks, (unsigned)n_obs), kThreads, 0, m.stream>>>(
+      d_y, m.d_obs_spec, m.d_obs_spec + n_obs, m.d_obs_spec + 2 * n_obs, m.d_obs_partial);
+  observe_final_kernel<<<(unsigned)n_obs, 256, 0, m.stream>>>(m.d_obs_partial, (int)blocks, m.d_obs_out);
   TAPES_CUDA_CHECK(cudaGetLastError());
   TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_obs_out, (size_t)n_obs * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+}
+
+void observe_sequences(Model& m, const double* d_y, int64_t n_seq, const int64_t* seq_ptr, const int32_t* symbols,
+                       double eps, double* h_out) {
+  if (n_seq <= 0) return;
+  const int k = m.k;
+  const uint64_t A = (uint64_t)m.A;
+  std::vector<int64_t> offset, stride, count, where_short;
+  std::vector<int64_t> long_ptr(1, 0);
+  std::vector<int32_t> long_symbols, where_long;
+  for (int64_t o = 0; o < n_seq; ++o) {
+    const int64_t len = seq_ptr[o + 1] - seq_ptr[o];
+    if (len < 0) throw std::runtime_error("sequence offsets must ascend");
+    for (int64_t c = 0; c < len; ++c)
+      if (symbols[seq_ptr[o] + c] < 0 || (uint64_t)symbols[seq_ptr[o] + c] >= A)
+        throw std::runtime_error("sequence symbol outside the alphabet");
+    if (len <= k) {  // framework/markov_tapes.py:215-222: the last len axes fixed, the leading ones summed
+      uint64_t off = 0;
+      for (int64_t c = 0; c < len; ++c) off = off * A + (uint64_t)symbols[seq_ptr[o] + c];
+      offset.push_back((int64_t)off); stride.push_back((int64_t)m.pow_a[len]); count.push_back((int64_t)m.pow_a[k - len]);
+      where_short.push_back(o);
+    } else {
+      if (len - k + 1 > 4096) throw std::runtime_error("sequence too long");
+      long_symbols.insert(long_symbols.end(), symbols + seq_ptr[o], symbols + seq_ptr[o + 1]);
+      long_ptr.push_back((int64_t)long_symbols.size());
+      where_long.push_back((int32_t)where_long.size());
+    }
+  }
+  if (!where_short.empty()) {
+    std::vector<double> sums(where_short.size());
+    observe_strided(m, d_y, offset.data(), stride.data(), count.data(), (int64_t)where_short.size(), sums.data());
+    for (size_t i = 0; i < where_short.size(); ++i) h_out[where_short[i]] = sums[i];
+  }
+  if (!where_long.empty()) {
+    const size_t n_long = where_long.size();
+    int64_t* d_ptr = (int64_t*)pool_alloc((n_long + 1) * sizeof(int64_t), m.stream);
+    int32_t* d_sym = (int32_t*)pool_alloc(long_symbols.size() * sizeof(int32_t), m.stream);
+    int32_t* d_where = (int32_t*)pool_alloc(n_long * sizeof(int32_t), m.stream);
+    double* d_out = (double*)pool_alloc(n_long * sizeof(double), m.stream);
+    std::vector<double> got(n_long);
+    size_t windows = 1;
+    for (size_t i = 0; i < n_long; ++i) windows = std::max<size_t>(windows, (size_t)(long_ptr[i + 1] - long_ptr[i]) - k + 1);
+    try {
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(d_ptr, long_ptr.data(), (n_long + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, m.stream));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(d_sym, long_symbols.data(), long_symbols.size() * sizeof(int32_t), cudaMemcpyHostToDevice, m.stream));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(d_where, where_long.data(), n_long * sizeof(int32_t), cudaMemcpyHostToDevice, m.stream));
+      observe_long_kernel<<<(unsigned)n_long, 128, windows * sizeof(double), m.stream>>>(d_y, d_ptr, d_sym, d_where, k, (uint32_t)A, eps, d_out);
+      TAPES_CUDA_CHECK(cudaGetLastError());
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(got.data(), d_out, n_long * sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+    } catch (...) {
+      cudaFreeAsync(d_ptr, m.stream); cudaFreeAsync(d_sym, m.stream); cudaFreeAsync(d_where, m.stream); cudaFreeAsync(d_out, m.stream);
+      throw;
+    }
+    cudaFreeAsync(d_ptr, m.stream); cudaFreeAsync(d_sym, m.stream); cudaFreeAsync(d_where, m.stream); cudaFreeAsync(d_out, m.stream);
+    size_t i = 0;
+    for (int64_t o = 0; o < n_seq; ++o)
+      if (seq_ptr[o + 1] - seq_ptr[o] > k) h_out[o] = got[i++];
+  }
+}
+
+double markov_entropy(Model& m, const double* d_y) {
+  if (m.k < 1) throw std::runtime_error("entropy needs cl_k >= 1");
+  const uint64_t contexts = m.pow_a[m.k - 1];
+  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((contexts + kThreads - 1) / kThreads, (uint64_t)kReduceBlocks));
+  double* d_partial = (double*)pool_alloc((size_t)blocks * sizeof(double), m.stream);
+  double* d_sum = (double*)pool_alloc(sizeof(double), m.stream);
+  double h = 0.0;
+  try {
+    entropy_partials_kernel<<<blocks, kThreads, 0, m.stream>>>(d_y, contexts, (uint32_t)m.A, d_partial);
+    final_sum_kernel<<<1, 1024, 0, m.stream>>>(d_partial, blocks, 1, d_sum);
+    TAPES_CUDA_CHECK(cudaGetLastError());
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h, d_sum, sizeof(double), cudaMemcpyDeviceToHost, m.stream));
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+  } catch (...) {
+    cudaFreeAsync(d_partial, m.stream); cudaFreeAsync(d_sum, m.stream);
+    throw;
+  }
+  cudaFreeAsync(d_partial, m.stream); cudaFreeAsync(d_sum, m.stream);
+  return h;
 }
 
 }  // namespace tapes

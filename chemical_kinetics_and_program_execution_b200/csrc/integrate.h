@@ -52,8 +52,17 @@ Model& dop853_model(Dop853* s);
 void dop853_info(const Dop853* s, double out[6]);
 
 // Observables on device: sums[o] = sum_{j < count[o]} y[offset[o] + j * stride[o]], each summed in a
-// fixed order by one block.  offset/stride/count are HOST arrays; result to a HOST array.
+// fixed order by a grid of blocks.  offset/stride/count are HOST arrays; result to a HOST array.
 void observe_strided(Model& m, const double* d_y, const int64_t* offset, const int64_t* stride,
                      const int64_t* count, int64_t n_obs, double* h_out);
+
+// seq_prob of framework/markov_tapes.py:190-233 for symbol sequences of any length (HOST arrays:
+// sequence o is symbols[seq_ptr[o] .. seq_ptr[o + 1])): up to cl_k symbols a strided sum over the
+// leading axes, longer ones extended with the Markov process parameters clipped at eps.
+void observe_sequences(Model& m, const double* d_y, int64_t n_seq, const int64_t* seq_ptr, const int32_t* symbols,
+                       double eps, double* h_out);
+
+// markov_entropy of framework/markov_tapes.py:178-187 of a DEVICE table.
+double markov_entropy(Model& m, const double* d_y);
 
 }  // namespace tapes

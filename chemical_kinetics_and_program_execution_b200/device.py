@@ -71,16 +71,28 @@ class DeviceModel:
     _lib.check(rc == 0, 'tapes_rhs_profile')
     return ms
 
-  def observe(self, y, seqs):
-    """Sequence probabilities (len(seq) <= k) of a CUDA table, summed on the device."""
+  def observe(self, y, seqs, eps=None):
+    """Sequence probabilities of a CUDA table evaluated on the device: `seq_prob` of
+    framework/markov_tapes.py:190-233 for sequences of any length."""
+    assert y.is_cuda and y.dtype == torch.float64 and y.is_contiguous() and y.numel() == self.n_states
     torch.cuda.current_stream().synchronize()  # the sums run on the model's stream
-    triples = [markov_tapes.sequence_observable(self.info['alphabet'], self.cl_k, s) for s in seqs]
-    cols = [numpy.ascontiguousarray(numpy.array(c, dtype=numpy.int64)) for c in zip(*triples)]
     out = numpy.zeros(len(seqs), dtype=numpy.float64)
-    rc = markov_tapes.u_lib.tapes_observe(self.handle, y.data_ptr(), cols[0].ctypes.data, cols[1].ctypes.data,
-                                          cols[2].ctypes.data, len(seqs), out.ctypes.data)
-    _lib.check(rc == 0, 'tapes_observe')
+    if len(seqs):
+      seq_ptr, symbols = _lib.pack_sequences(seqs)
+      rc = markov_tapes.u_lib.tapes_observe_sequences(self.handle, y.data_ptr(), len(seqs), seq_ptr.ctypes.data,
+                                                      symbols.ctypes.data, 1e-100 if eps is None else float(eps),
+                                                      out.ctypes.data)
+      _lib.check(rc == 0, 'tapes_observe_sequences')
     return out
+
+  def entropy(self, y):
+    """`markov_entropy` (framework/markov_tapes.py:178-187) of a CUDA table, evaluated on the device."""
+    assert y.is_cuda and y.dtype == torch.float64 and y.is_contiguous() and y.numel() == self.n_states
+    torch.cuda.current_stream().synchronize()
+    out = numpy.zeros(1, dtype=numpy.float64)
+    _lib.check(markov_tapes.u_lib.tapes_markov_entropy(self.handle, y.data_ptr(), out.ctypes.data) == 0,
+               'tapes_markov_entropy')
+    return float(out[0])
 
   def csr(self):
     """(row_ptr[int64], entries[uint32]) copied to host."""

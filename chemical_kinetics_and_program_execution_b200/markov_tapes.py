@@ -245,16 +245,19 @@ def sequence_observable(size_a, cl_k, seq):
 
 def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max_step=numpy.inf,
                          first_step=None, observables=None, return_states=True, want_stats=False,
-                         peer_group=None):
+                         peer_group=None, entropy=False, eps=None):
   """DOP853 integration with the table resident in HBM (no per-stage host round trips).
 
   Follows scipy.integrate.solve_ivp(method='DOP853', t_eval=ts) step for step, so the result
   matches `ode_integrate_ivp(..., ivp_kwargs=dict(method='DOP853', rtol=..., atol=...))`.
 
   Returns the states at `ts` shaped like odeint's output ([len(ts), size_a**cl_k]) and/or, when
-  `observables` (a list of symbol sequences, each no longer than cl_k) is given, their
-  probabilities at `ts` ([len(ts), len(observables)]), computed on the device.  With
-  return_states=False only the observables cross the host boundary.
+  `observables` (a list of symbol sequences of any length) is given, their probabilities at `ts`
+  ([len(ts), len(observables)]) as `seq_prob` defines them (framework/markov_tapes.py:190-233;
+  sequences longer than cl_k are extended with the Markov process parameters clipped at `eps`,
+  default 1e-100), computed on the device; with entropy=True also `markov_entropy`
+  (framework/markov_tapes.py:178-187) at `ts` ([len(ts)]).  With return_states=False only these
+  numbers cross the host boundary.
 
   Several GPUs: `peer_group` is the parallel.PeerExchangeRhs of this rank's share of the problem,
   a device.DeviceModel(tag, cl_k, part=(rank, world)) - or `tag` names a share of a rule set made
@@ -286,10 +289,11 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
   n = size_a ** cl_k
   obs = None
   if observables is not None:
-    triples = [sequence_observable(size_a, cl_k, seq) for seq in observables]
-    obs = [numpy.ascontiguousarray(numpy.array(col, dtype=numpy.int64)) for col in zip(*triples)]
+    obs = _lib.pack_sequences(observables)
   states = numpy.empty((ts.size, n), dtype=numpy.float64) if return_states else None
   series = numpy.empty((ts.size, len(observables)), dtype=numpy.float64) if obs is not None else None
+  entropies = numpy.empty(ts.size, dtype=numpy.float64) if entropy else None
+  one = numpy.zeros(1, dtype=numpy.float64)
   forward = ts[-1] > ts[0]
   info = numpy.zeros(6, dtype=numpy.float64)
   try:
@@ -314,17 +318,20 @@ def ode_integrate_device(*, tag, size_a, cl_k, p0, ts, rtol=1e-3, atol=1e-6, max
         _lib.check(rc == 0, 'tapes_dop853_dense')
         if states is not None:
           _lib.check(u_lib.tapes_dop853_fetch(solver, 1, states[i].ctypes.data) == 0, 'tapes_dop853_fetch')
-        if series is not None:
-          rc = u_lib.tapes_dop853_observe(solver, 1, obs[0].ctypes.data, obs[1].ctypes.data,
-                                          obs[2].ctypes.data, len(observables), series[i].ctypes.data)
-          _lib.check(rc == 0, 'tapes_dop853_observe')
+        if series is not None and len(observables):
+          rc = u_lib.tapes_dop853_observe_sequences(solver, 1, len(observables), obs[0].ctypes.data, obs[1].ctypes.data,
+                                                    1e-100 if eps is None else float(eps), series[i].ctypes.data)
+          _lib.check(rc == 0, 'tapes_dop853_observe_sequences')
+        if entropies is not None:
+          _lib.check(u_lib.tapes_dop853_entropy(solver, 1, one.ctypes.data) == 0, 'tapes_dop853_entropy')
+          entropies[i] = one[0]
       done = max(done, upto)
     u_lib.tapes_dop853_info(solver, info.ctypes.data)
   finally:
     u_lib.tapes_dop853_destroy(solver)
   if peer_group is not None:
     peer_group.check()
-  out = tuple(x for x in (states, series) if x is not None)
+  out = tuple(x for x in (states, series, entropies) if x is not None)
   out = out[0] if len(out) == 1 else out
   if want_stats:
     return out, dict(nfev=int(info[3]), accepted=int(info[4]), rejected=int(info[5]), t=float(info[0]))

@@ -215,6 +215,22 @@ int tapes_dop853_info(void* solver, double* out6);
 int tapes_observe(void* model, const double* d_y, const int64_t* offset, const int64_t* stride,
                   const int64_t* count, int64_t n_obs, double* out);
 
+/* seq_prob of framework/markov_tapes.py:190-233 evaluated on the device for a DEVICE table of n_states
+ * doubles: sequence o is symbols[seq_ptr[o] .. seq_ptr[o + 1]) (HOST arrays).  Sequences of up to cl_k
+ * symbols are read off the table (last axes fixed, leading axes summed, markov_tapes.py:215-222); longer
+ * ones are extended with the Markov process parameters of markov_tapes.py:81-104 clipped at eps
+ * (markov_tapes.py:223-233; the reference's default eps is 1e-100).  out: n_seq doubles (HOST). */
+int tapes_observe_sequences(void* model, const double* d_y, int64_t n_seq, const int64_t* seq_ptr,
+                            const int32_t* symbols, double eps, double* out);
+/* The same for the current state (which = 0) or the dense-output buffer (which = 1) of a solver. */
+int tapes_dop853_observe_sequences(void* solver, int which, int64_t n_seq, const int64_t* seq_ptr,
+                                   const int32_t* symbols, double eps, double* out);
+
+/* markov_entropy of framework/markov_tapes.py:178-187 (entropy rate of the chain the table describes)
+ * of a DEVICE table, evaluated on the device; *out receives the value. */
+int tapes_markov_entropy(void* model, const double* d_y, double* out);
+int tapes_dop853_entropy(void* solver, int which, double* out);
+
 /* Validation of a table of A^cl_k doubles (HOST buffer, or DEVICE buffer when on_device != 0)
  * without the dense eigen-decomposition of framework/markov_tapes.py:133-175: the context transfer
  * matrix of markov_tapes.py:107-130 has A non-zeros per row and is applied by a streaming kernel.

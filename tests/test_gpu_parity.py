@@ -680,6 +680,72 @@ def test_device_observables(mt, device):
     assert abs(g - want) <= 1e-14 * abs(want)
 
 
+def test_device_observables_beyond_the_window_and_entropy(mt, device, p0_fixtures):
+  """SURVEY.md section 8(f) rank 1, the rest of it: `seq_prob` for sequences longer than cl_k
+  (framework/markov_tapes.py:223-233, Markov extension with the clipped process parameters) and
+  `markov_entropy` (markov_tapes.py:178-187) evaluated on the device, against the host functions."""
+  import torch
+  model = device.DeviceModel('ex3-copolymerization', 6)
+  tables = [configs.markov_table(4, 6, 5), configs.dirichlet_product_table(4, 6, 9),
+            dense(p0_fixtures['ex3_k6_idx'], p0_fixtures['ex3_k6_val'], 4 ** 6)]  # the last has zeros: clips matter
+  seqs = [[0, 1, 2, 3, 0, 1, 2], [1, 3, 1, 2, 0, 0, 1, 2, 3, 3, 0], [2], [0, 0, 0, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0]]
+  for p in tables:
+    d_p = torch.from_numpy(p).cuda()
+    got = model.observe(d_p, seqs)
+    spd = p.reshape([4] * 6)
+    for g, seq in zip(got, seqs):
+      want = float(mt.seq_prob(spd, seq)[0])
+      assert abs(g - want) <= 1e-13 * abs(want) + 1e-300, (seq, g, want)
+    want_h = float(mt.markov_entropy(spd))
+    assert abs(model.entropy(d_p) - want_h) <= 1e-13 * abs(want_h), (model.entropy(d_p), want_h)
+  # eps is honoured (framework/markov_tapes.py:101)
+  p = tables[2]
+  got = model.observe(torch.from_numpy(p).cuda(), [[0, 0, 0, 0, 0, 0, 1, 3]], eps=1e-30)[0]
+  want = float(mt.seq_prob(p.reshape([4] * 6), [0, 0, 0, 0, 0, 0, 1, 3], eps=1e-30)[0])
+  assert abs(got - want) <= 1e-13 * abs(want)
+  with pytest.raises(RuntimeError, match='alphabet'):
+    model.observe(torch.from_numpy(p).cuda(), [[0, 7]])
+
+
+def test_observable_sums_use_the_whole_grid(mt, device):
+  """A short sequence at a large table is a strided sum over every sector of the table; it is now
+  evaluated by a grid of blocks with a fixed order of additions (was one block per observable)."""
+  import time
+  import torch
+  rules = configs.random_rule_set(10, 2, seed=3)
+  mt.register_rule_set('observe-at-scale', 10, rules)
+  model = device.DeviceModel('observe-at-scale', 7)  # 10^7 states
+  p = configs.dirichlet_product_table(10, 7, 4)
+  d_p = torch.from_numpy(p).cuda()
+  seqs = [[3], [9, 0], [1, 2, 3, 4, 5, 6, 7], [4, 4, 4]]
+  got = model.observe(d_p, seqs)
+  spd = p.reshape([10] * 7)
+  for g, seq in zip(got, seqs):
+    want = float(mt.seq_prob(spd, seq)[0])
+    assert abs(g - want) <= 1e-13 * abs(want)
+  assert numpy.array_equal(got, model.observe(d_p, seqs))  # reproducible
+  t0 = time.perf_counter()
+  for _ in range(20):
+    model.observe(d_p, seqs)
+  print(f'4 observables at 10^7 states: {(time.perf_counter() - t0) / 20 * 1e6:.0f} us per call')
+  mt.u_lib.tapes_release_model(b'observe-at-scale', 7)
+
+
+def test_stepper_returns_long_sequences_and_entropy(mt, p0_fixtures):
+  p0 = dense(p0_fixtures['ex5_idx'], p0_fixtures['ex5_val'], 5 ** 5)
+  ts = numpy.linspace(0, 5.0, 6)
+  seqs = [[0, 1], [0, 1, 2, 0, 1, 2, 0], [4, 4, 4, 4, 4, 4]]
+  states, series, entropy = mt.ode_integrate_device(tag='ex5-msrtf-machine', size_a=5, cl_k=5, p0=p0, ts=ts, rtol=1e-10,
+                                                    atol=1e-12, observables=seqs, entropy=True)
+  for i in range(ts.size):
+    spd = states[i].reshape([5] * 5)
+    for j, seq in enumerate(seqs):
+      want = float(mt.seq_prob(spd, seq)[0])
+      assert abs(series[i, j] - want) <= 1e-13 * abs(want) + 1e-300
+    want_h = float(mt.markov_entropy(spd))
+    assert abs(entropy[i] - want_h) <= 1e-13 * abs(want_h)
+
+
 def test_fused_stage_update_is_bit_identical(mt, p0_fixtures, monkeypatch):
   """The Runge-Kutta stage update fused into the product kernel keeps the term order of the
   separate kernel, so both integrators produce the same bits."""
