@@ -502,13 +502,13 @@ def run_b200(args):
     p_full[:n] = p
     out_full = torch.zeros_like(p_full)
 
-  def one_step():
+  def one_step(table=None):
     if sharded is None:
-      model.rhs(p, out)
+      model.rhs(p if table is None else table, out)
     elif args.exchange == 'peer':
-      sharded.rhs_full(p_full)
+      sharded.rhs_full(p_full if table is None else table)
     else:
-      sharded.rhs_full(p_full, out_full)
+      sharded.rhs_full(p_full if table is None else table, out_full)
 
   for _ in range(args.warmup):
     one_step()
@@ -679,24 +679,31 @@ def run_b200(args):
     e2e['drop_in'] = _guarded(drop_in)
     del f
   elif world > 1:
-    # N > 1: every rank brings the table in from pinned host memory over its own PCIe link, the ranks
-    # evaluate the step together, and every rank takes the summed dy/dt back out.  No collective
-    # inside the guarded part other than the step itself (whose waits time out), so a rank that fails
-    # cannot leave the others hanging; the figures meet in one all-reduce afterwards.
+    # N > 1: the table comes in once over the N PCIe links together - rank r copies its 1 / N slice from
+    # pinned host memory and the ranks all-gather the slices over NVLink - the ranks evaluate the step
+    # together, and rank 0 takes the summed dy/dt back out to pinned host memory (every rank holds it).
+    # Nothing inside the guarded part but the step's own collectives (whose waits time out or belong to
+    # NCCL's watchdog), and the figures meet in one all-reduce afterwards.
     mine_ms, failed = 0.0, 0.0
+    share = -(-n // world)
     try:
-      h_in = torch.empty(n, dtype=torch.float64).pin_memory()
-      h_out = torch.empty(n, dtype=torch.float64).pin_memory()
-      h_in.copy_(p)
+      h_in = torch.empty(share * world, dtype=torch.float64).pin_memory()
+      h_in[:n].copy_(p)
+      h_out = torch.empty(n, dtype=torch.float64).pin_memory() if rank == 0 else None
+      table = torch.zeros(max(share * world, p_full.numel()), dtype=torch.float64, device=device)
+      mine = torch.empty(share, dtype=torch.float64, device=device)
 
       def e2e_step():
-        p_full[:n].copy_(h_in, non_blocking=True)
-        one_step()
-        result = sharded.out if args.exchange == 'peer' else out_full
-        h_out.copy_(result[:n], non_blocking=True)
+        mine.copy_(h_in[rank * share:(rank + 1) * share], non_blocking=True)
+        dist.all_gather_into_tensor(table[:share * world], mine)
+        one_step(table)
+        if rank == 0:
+          result = sharded.out if args.exchange == 'peer' else out_full
+          h_out.copy_(result[:n], non_blocking=True)
         torch.cuda.synchronize()
 
       e2e_step()
+      dist.barrier()
       t0 = time.perf_counter()
       for _ in range(args.e2e_steps):
         e2e_step()
@@ -709,13 +716,13 @@ def run_b200(args):
     e2e_ms, any_failed = float(both[0].item()), float(both[1].item()) > 0
     if rank == 0:
       if any_failed or not e2e_ms > 0:
-        e2e = dict(value=None, unit=UNIT, h2d_bytes_per_step=8 * n * world, d2h_bytes_per_step=8 * n * world,
+        e2e = dict(value=None, unit=UNIT, h2d_bytes_per_step=8 * n, d2h_bytes_per_step=8 * n,
                    note='end-to-end measurement failed on some rank (see stderr)')
       else:
-        e2e = dict(value=job_bytes / (e2e_ms * 1e-3) / 1e9, unit=UNIT, h2d_bytes_per_step=8 * n * world,
-                   d2h_bytes_per_step=8 * n * world, ms_per_step=e2e_ms,
-                   api='pinned host table -> every rank (H2D), step of all ranks together, summed dy/dt -> pinned '
-                       'host on every rank (D2H); max over ranks')
+        e2e = dict(value=job_bytes / (e2e_ms * 1e-3) / 1e9, unit=UNIT, h2d_bytes_per_step=8 * share * world,
+                   d2h_bytes_per_step=8 * n, ms_per_step=e2e_ms,
+                   api='pinned host table -> 1 / N slice per rank (H2D) + all-gather over NVLink, step of all ranks '
+                       'together, summed dy/dt -> pinned host on rank 0 (D2H); max over ranks')
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -22,7 +22,7 @@ SYMBOLS = (
     'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts', 'tapes_register_program',
     'tapes_mc_create', 'tapes_mc_destroy', 'tapes_mc_run', 'tapes_mc_window_counts', 'tapes_mc_fetch',
     'tapes_mc_sample_ring', 'tapes_program_tree', 'tapes_observe_sequences', 'tapes_dop853_observe_sequences',
-    'tapes_markov_entropy', 'tapes_dop853_entropy',
+    'tapes_markov_entropy', 'tapes_dop853_entropy', 'tapes_host_alloc', 'tapes_host_free',
 )
 
 _lib = None
@@ -146,6 +146,10 @@ def load():
   lib.tapes_markov_entropy.argtypes = [vp, vp, vp]
   lib.tapes_dop853_entropy.restype = i32
   lib.tapes_dop853_entropy.argtypes = [vp, i32, vp]
+  lib.tapes_host_alloc.restype = vp
+  lib.tapes_host_alloc.argtypes = [i64]
+  lib.tapes_host_free.restype = i32
+  lib.tapes_host_free.argtypes = [vp]
   _lib = lib
   return lib
 
@@ -182,6 +186,41 @@ def model_timing(model):
   load().tapes_model_timing(model, buf.ctypes.data, 5)
   return dict(host_enumerate_ms=float(buf[0]), device_expand_ms=float(buf[1]),
               device_csr_ms=float(buf[2]), device_slices_ms=float(buf[3]), expand_alloc_ms=float(buf[4]))
+
+
+class PinnedResults:
+  """Result arrays of get_dy_dt for large tables: NumPy arrays over page-locked memory, so that the
+  device-to-host copy is plain DMA and no fresh 8 * n bytes are zero-filled per call.  A buffer goes
+  back to the pool when the array that wraps it is garbage-collected (the SciPy steppers copy the
+  returned values into their own stage arrays and drop the array at once); at most `limit` buffers
+  exist, and when all of them are still referenced the caller gets an ordinary NumPy array."""
+
+  def __init__(self, n_doubles, limit=4):
+    self.n, self.limit = int(n_doubles), int(limit)
+    self.free, self.alive = [], 0
+
+  def take(self):
+    import weakref
+    if self.free:
+      ptr = self.free.pop()
+    elif self.alive < self.limit:
+      ptr = load().tapes_host_alloc(8 * self.n)
+      if not ptr:
+        load().tapes_clear_error()
+        return None
+      self.alive += 1
+    else:
+      return None
+    buf = (ctypes.c_double * self.n).from_address(ptr)
+    arr = numpy.frombuffer(buf, dtype=numpy.float64, count=self.n)
+    weakref.finalize(buf, self.free.append, ptr)  # `arr` (and every view of it) keeps `buf` alive
+    return arr
+
+  def release(self):
+    """Frees the idle buffers (buffers still wrapped by live arrays stay valid)."""
+    while self.free:
+      load().tapes_host_free(self.free.pop())
+      self.alive -= 1
 
 
 def pack_sequences(seqs):

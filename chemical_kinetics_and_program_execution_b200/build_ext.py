@@ -12,8 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'tapes_py_interface.so')
-SOURCES = ['abi.cu', 'engine.cu', 'flux.cu', 'integrate.cu', 'validate.cu', 'montecarlo.cu', 'rules.cpp', 'problems.cpp']
-HEADERS = ['engine.h', 'rules.h', 'primitives.cuh', 'integrate.h', 'validate.h', 'montecarlo.h', 'cuda_check.h',
+SOURCES = ['abi.cu', 'engine.cu', 'flux.cu', 'integrate.cu', 'validate.cu', 'montecarlo.cu', 'hostcopy.cu', 'rules.cpp',
+           'problems.cpp']
+HEADERS = ['engine.h', 'rules.h', 'primitives.cuh', 'integrate.h', 'validate.h', 'montecarlo.h', 'cuda_check.h', 'hostcopy.h',
            os.path.join('..', '..', 'include', 'tapes_b200.h')]
 
 NVCC_FLAGS = [

@@ -16,6 +16,7 @@
 
 #include "../../include/tapes_b200.h"
 #include "engine.h"
+#include "hostcopy.h"
 #include "integrate.h"
 #include "montecarlo.h"
 #include "rules.h"
@@ -179,6 +180,7 @@ void cleanup_gambit(void* handle) {
   (void)handle;
   for (auto& kv : g_models) invalidate(kv.second);
   g_models.clear();
+  tapes::staged_copy_shutdown();
   if (g_runtime && g_runtime->cuda_ok) tapes::release_build_scratch();
   if (g_runtime) { delete g_runtime; g_runtime = nullptr; }
 }
@@ -230,6 +232,22 @@ void c_compute_dy_dt(const char* tag, int64_t cl_k, int64_t debug, const double*
     cudaGetLastError();
     poison_result(tag, cl_k, probs_out);
   }
+}
+
+void* tapes_host_alloc(int64_t bytes) {
+  if (!ensure_cuda()) return nullptr;
+  void* p = nullptr;
+  if (bytes < 0 || cudaHostAlloc(&p, (size_t)std::max<int64_t>(bytes, 1), cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    fail("host_alloc: cudaHostAlloc failed");
+    return nullptr;
+  }
+  return p;
+}
+
+int tapes_host_free(void* p) {
+  if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); fail("host_free failed"); return 1; }
+  return 0;
 }
 
 const char* tapes_last_error(void) { return g_error.c_str(); }

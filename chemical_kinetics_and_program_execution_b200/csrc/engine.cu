@@ -15,6 +15,7 @@
 #include <cstring>
 #include <type_traits>
 
+#include "hostcopy.h"
 #include "primitives.cuh"
 
 namespace tapes {
@@ -1566,37 +1567,49 @@ void rhs_host_impl(Model& m, const double* h_p, double* h_out) {
     TAPES_CUDA_CHECK(cudaStreamCreateWithFlags(&m.copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t& e : m.copy_events) TAPES_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  const bool pinned = n <= Model::kPinnedStagingStates;
-  if (pinned) {
+  const bool small = n <= Model::kPinnedStagingStates;
+  if (small) {
+    // small tables: through pinned memory of the model, so that both transfers are plain DMA
     if (!m.h_pinned) TAPES_CUDA_CHECK(cudaHostAlloc((void**)&m.h_pinned, 2 * bytes, cudaHostAllocDefault));
     std::memcpy(m.h_pinned, h_p, bytes);
     TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, m.h_pinned, bytes, cudaMemcpyHostToDevice, m.stream));
-  } else {
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
-  }
-  // large tables: the result goes back in row blocks while the product of the next block runs
-  const int blocks = n >= (1ull << 22) ? Model::kCopyBlocks : 1;
-  if (blocks == 1) {
     rhs_device(m, m.d_in, m.d_out, m.stream);
-    if (pinned) {
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(m.h_pinned + n, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
-      TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
-      std::memcpy(h_out, m.h_pinned + n, bytes);
-      return;
-    }
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(m.h_pinned + n, m.d_out, bytes, cudaMemcpyDeviceToHost, m.stream));
     TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+    std::memcpy(h_out, m.h_pinned + n, bytes);
     return;
   }
+  // large tables.  Pinned caller buffers go by DMA on the model's streams; pageable ones (what the
+  // reference's binding hands over, framework/markov_tapes.py:278-279) through the threaded staging
+  // of hostcopy.h.  The result goes back in row blocks while the product of the next block runs.
+  if (is_pinned_host(h_p)) {
+    TAPES_CUDA_CHECK(cudaMemcpyAsync(m.d_in, h_p, bytes, cudaMemcpyHostToDevice, m.stream));
+  } else {
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));  // d_in is idle: the copy runs on the stagers' streams
+    staged_h2d(m.d_in, h_p, bytes);
+  }
+  const bool out_pinned = is_pinned_host(h_out);
+  const int blocks = n >= (1ull << 22) ? Model::kCopyBlocks : 1;
   launch_all_weights(m, m.d_in, m.stream);
   const uint64_t per = ((n + blocks - 1) / blocks + 31) & ~31ull;
+  int launched = 0;
   for (int b = 0; b < blocks; ++b) {
     const uint64_t lo = std::min<uint64_t>(n, per * b), hi = std::min<uint64_t>(n, lo + per);
     if (hi <= lo) break;
     launch_flux(m, m.d_out, lo, hi, m.stream);
     TAPES_CUDA_CHECK(cudaEventRecord(m.copy_events[b], m.stream));
-    TAPES_CUDA_CHECK(cudaStreamWaitEvent(m.copy_stream, m.copy_events[b], 0));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out + lo, m.d_out + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, m.copy_stream));
+    ++launched;
+    if (out_pinned) {
+      TAPES_CUDA_CHECK(cudaStreamWaitEvent(m.copy_stream, m.copy_events[b], 0));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(h_out + lo, m.d_out + lo, (hi - lo) * 8, cudaMemcpyDeviceToHost, m.copy_stream));
+    }
+  }
+  if (!out_pinned) {
+    for (int b = 0; b < launched; ++b) {  // block b leaves while the products of the later blocks run
+      const uint64_t lo = std::min<uint64_t>(n, per * b), hi = std::min<uint64_t>(n, lo + per);
+      TAPES_CUDA_CHECK(cudaEventSynchronize(m.copy_events[b]));
+      staged_d2h(h_out + lo, m.d_out + lo, (hi - lo) * 8);
+    }
   }
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.copy_stream));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));

@@ -144,6 +144,9 @@ def tprint(size_a, cl_k, adata, epsilon=1e-10, nmax=float('inf'), file=None):
 
 ### Right-hand side and integrators
 
+_PINNED_RESULT_STATES = 1 << 22
+
+
 def _tag_buffer(tag):
   return numpy.frombuffer(tag.encode() + b'\x00', dtype=numpy.uint8)
 
@@ -156,15 +159,20 @@ def get_dy_dt(*, tag, size_a, cl_k, debug=False):
   a_tag = _tag_buffer(tag)
   do_debug = 1 if debug else 0
   expected_size = size_a ** cl_k
+  # large tables: results in page-locked arrays (plain DMA, no zero-filling of 8 * n fresh bytes per
+  # call); the library overwrites every entry, or fills the array with NaN when it fails
+  pinned = _lib.PinnedResults(expected_size) if expected_size >= _PINNED_RESULT_STATES else None
 
   def dy_dt(a_probs_in, t):
     if IS_DEBUG:
       print(f'DDD {t=:.10g}')
     c_probs_in = numpy.ascontiguousarray(numpy.asarray(a_probs_in, dtype=numpy.float64).ravel())
-    c_probs_out = numpy.zeros_like(c_probs_in)
     if c_probs_in.size != expected_size:
       raise ValueError(f'probability-array should have size {expected_size}, '
                        f'observed: {c_probs_in.size}')
+    c_probs_out = pinned.take() if pinned is not None else None
+    if c_probs_out is None:
+      c_probs_out = numpy.zeros_like(c_probs_in)
     u_lib.c_compute_dy_dt(a_tag.ctypes.data, cl_k, do_debug, c_probs_in.ctypes.data,
                           c_probs_out.ctypes.data)
     if u_lib.tapes_last_error():

@@ -47,6 +47,13 @@ void c_compute_dy_dt(const char* tag, int64_t cl_k, int64_t debug, const double*
 const char* tapes_last_error(void);
 void tapes_clear_error(void);
 
+/* Page-locked host memory for tables and results: c_compute_dy_dt moves pinned buffers by plain DMA
+ * (about 55 GB/s over PCIe 5 x16) and pageable ones - what NumPy hands the reference's binding -
+ * through bounce buffers filled by several host threads (csrc/hostcopy.h).  markov_tapes.get_dy_dt
+ * takes its result arrays for large tables from a small pool of such buffers.  NULL on failure. */
+void* tapes_host_alloc(int64_t bytes);
+int tapes_host_free(void* p);
+
 /* Alphabet size registered for `tag`, or -1. */
 int64_t tapes_alphabet_size(const char* tag);
 

@@ -136,3 +136,25 @@ def test_ex3_long_chain_trajectory(mt):
   close(states[-1], end)
   assert (abs(states[-1] - end) <= 1e-12 * abs(end) + 1e-18).all()
   assert abs(states[-1].sum() - 1) < 1e-12
+
+
+def test_pinned_result_pool_and_pageable_buffers(mt):
+  """Large tables through the host-buffer entry point: the mirror's get_dy_dt returns arrays over
+  page-locked memory from a small pool (reused once the caller drops them, ordinary arrays when
+  all are still held); the reference's own binding hands over pageable NumPy buffers, which go
+  through the threaded staging (csrc/hostcopy.h).  Same bits every way."""
+  from test_abi import reference_binding, reference_dy_dt
+  f = mt.get_dy_dt(tag='ex3-copolymerization', size_a=4, cl_k=12)
+  p = configs.dirichlet_product_table(4, 12, 3)
+  first = f(p, 0.0)
+  address = first.ctypes.data
+  keep = first.copy()
+  del first
+  again = f(p, 0.0)
+  assert again.ctypes.data == address and numpy.array_equal(again, keep)  # the buffer came back
+  held = [again] + [f(p, 0.0) for _ in range(6)]  # more than the pool holds
+  assert all(numpy.array_equal(x, keep) for x in held)
+  assert len({x.ctypes.data for x in held}) == len(held)
+  out = reference_dy_dt(reference_binding(), 'ex3-copolymerization', 12, p)  # pageable in, pageable out
+  assert numpy.array_equal(out, keep)
+  assert abs(keep.sum()) <= 1e-13 * abs(keep).sum()
