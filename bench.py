@@ -110,7 +110,8 @@ def level_bytes(info):
   the next level."""
   children = info['n_nodes']
   gathered = info['hash_inserts'] - info.get('owned_parents', 0)
-  per_group = info.get('group_record_bytes', 16 * info['hash_unique'])
+  plane = info.get('plane_groups', 0)  # 32 bytes per block of 256 such groups instead of 16 per group
+  per_group = 16.0 * (info['hash_unique'] - plane) + 32.0 * plane / 256
   return (16.0 * children + 25.0 * info.get('left_parents', 0) + float(per_group) + 8.0 * gathered
           + 16.0 * info.get('deferred_groups', 0))
 

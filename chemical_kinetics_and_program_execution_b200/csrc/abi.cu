@@ -478,11 +478,12 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   std::shared_ptr<tapes::Model> mp = resolve(model);
   if (!mp) return 0;
   const tapes::Model& head = *mp;
-  const int kFields = 32;
+  const int kFields = 34;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
                                      true, false, false, false, false, false, true, true, true, true,
-                                     true, false, false, true, true, false, true, true, true, true};
+                                     true, false, false, true, true, false, true, true, true, true,
+                                     true, false};
   int64_t total[kFields] = {};
   for (size_t part = 0; part <= head.more.size(); ++part) {
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
@@ -496,7 +497,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                                 (int64_t)m.slices.runs, (int64_t)m.slices.run_entries, (int64_t)m.slices.column_entries,
                                 (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
                                 m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
-                                m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved};
+                                m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved,
+                                m.stats.plane_groups, (int64_t)((m.ratio_right ? 1 : 0) + (m.ratio_left ? 1 : 0))};
     for (int i = 0; i < kFields; ++i) {
       if (part == 0) total[i] = v[i];
       else if (adds[i]) total[i] += v[i];
@@ -522,6 +524,7 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
   if (std::strcmp(key, "level_unroll") == 0 && value >= 1 && value <= 8) field = &tapes::Model::level_unroll;
   if (std::strcmp(key, "interleave_seeds") == 0 && (value == 0 || value == 1)) field = &tapes::Model::interleave_seeds;
   if (std::strcmp(key, "ratio_table") == 0 && (value == 0 || value == 1)) field = &tapes::Model::ratio_table;
+  if (std::strcmp(key, "plane_kernel") == 0 && (value == 0 || value == 1)) field = &tapes::Model::plane_kernel;
   if (std::strcmp(key, "graphs") == 0 && (value == 0 || value == 1)) {
     cudaStreamSynchronize(head.stream);
     head.drop_weight_graphs();

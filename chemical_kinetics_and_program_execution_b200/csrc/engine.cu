@@ -499,20 +499,29 @@ __device__ __forceinline__ double extension_ratio(double p_long, double p_short)
 __device__ __forceinline__ double weight_from_ratio(double w_parent, double r) { return r > 0.0 ? w_parent * r : 0.0; }
 
 constexpr int kRatioBatch = 4;  // entries per thread: loads and divisions of a batch overlap
-__global__ void __launch_bounds__(kThreads) ratio_right_kernel(const double* __restrict__ p, const double* __restrict__ short_table,
-                                                               double* __restrict__ ratio, uint64_t n, uint32_t A) {
+// Both per-step ratio tables from one read of the table: right extensions divide by the marginal of
+// the window without its last cell, left extensions / left shifts to a full window by the marginal
+// of the window without its first cell (both last-axis marginals marg_{k-1}, tm.scm:1263-1269 with
+// the short indices of 1305-1311 and 1341-1366).  ratio_left may be null.
+__global__ void __launch_bounds__(kThreads) ratio_tables_kernel(const double* __restrict__ p, const double* __restrict__ short_table,
+                                                                double* __restrict__ ratio_right, double* __restrict__ ratio_left,
+                                                                uint64_t n, uint32_t A, uint32_t M) {
   const uint64_t base = (uint64_t)blockIdx.x * (kThreads * kRatioBatch) + threadIdx.x;
-  double p_long[kRatioBatch], p_short[kRatioBatch];
+  double p_long[kRatioBatch], right_short[kRatioBatch], left_short[kRatioBatch];
 #pragma unroll
   for (int u = 0; u < kRatioBatch; ++u) {
     const uint64_t i = base + (uint64_t)u * kThreads;
     p_long[u] = i < n ? p[i] : 0.0;
-    p_short[u] = i < n ? short_table[i / A] : 0.0;
+    right_short[u] = i < n ? short_table[i / A] : 0.0;
+    left_short[u] = (ratio_left && i < n) ? short_table[i % M] : 0.0;
   }
 #pragma unroll
   for (int u = 0; u < kRatioBatch; ++u) {
     const uint64_t i = base + (uint64_t)u * kThreads;
-    if (i < n) ratio[i] = extension_ratio(p_long[u], p_short[u]);
+    if (i < n) {
+      ratio_right[i] = extension_ratio(p_long[u], right_short[u]);
+      if (ratio_left) ratio_left[i] = extension_ratio(p_long[u], left_short[u]);
+    }
   }
 }
 
@@ -572,17 +581,30 @@ template <int U, int UO, bool PROGRESSIONS, int MIN_BLOCKS, bool RATIO>
 __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
                                                          uint32_t warp_step_q, uint32_t warp_step_r,
                                                          const double* __restrict__ wr, double* __restrict__ ww,
-                                                         const double* __restrict__ ratio) {
+                                                         const double* __restrict__ ratio, const double* __restrict__ ratio_left) {
   if (blockIdx.x < left_blocks) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= lv.n_left) return;
     const int len = lv.lp_len[r];
     const uint32_t bo = lv.lp_io[r];
     const double wp = wr[lv.lp_gid[r]];
-    const double* __restrict__ tl = table(t, len);
-    const double p_short = table(t, len - 1)[bo];
     const uint32_t step = c.pw[len - 1];
     double* out = ww + lv.base + r;
+    if (RATIO && ratio_left && len == c.k) {
+      // children with a full window: child x has table index bo + x * A^(k-1) and divides by
+      // marg_{k-1}[bo] - exactly the pair of operands ratio_left holds the quotient of
+      for (uint32_t x0 = 0; x0 < c.A; x0 += U) {
+        double rl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) rl[u] = x0 + u < c.A ? ratio_left[bo + (x0 + u) * step] : 0.0;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (x0 + u < c.A) out[(uint64_t)(x0 + u) * lv.n_left] = weight_from_ratio(wp, rl[u]);
+      }
+      return;
+    }
+    const double* __restrict__ tl = table(t, len);
+    const double p_short = table(t, len - 1)[bo];
     for (uint32_t x0 = 0; x0 < c.A; x0 += U) {
       double p_long[U];
 #pragma unroll
@@ -684,6 +706,122 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
         }
       }
     }
+  }
+}
+
+// One regular block of 256 prefix groups (engine.h Level::PlaneBlock): thread t evaluates group t of
+// the block.  Same operands, same operations and the same order of additions as level_kernel's
+// own_parents path (tm.scm:1310-1322), so weights keep their bits; what is gone are the four
+// per-group records, the bounds tests, and the dependence of the parent loads on one another:
+// with the alphabet size known at compile time (A_ > 0) all 2 * A loads of a thread are in flight
+// at once.  A_ = 0: any alphabet, loads in batches of four.
+template <int A_>
+__global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_kernel(Consts c, Level lv, const double* __restrict__ ratio,
+                                                                       double* __restrict__ ww) {
+  const uint4* rec4 = (const uint4*)(lv.plane_blocks + blockIdx.x);
+  const uint4 r0 = rec4[0], r1 = rec4[1];
+  const uint32_t A = A_ ? (uint32_t)A_ : c.A;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t g = r0.x * (uint32_t)kThreads + tid, prefix = r0.y + tid, first = r0.z + tid, i_long = r0.w + tid;
+  const uint32_t stride = r1.x, n_par = r1.y & 0xffffu;
+  const bool deferred = (r1.y & Level::kPlaneDeferred) != 0;
+  const uint32_t rel = first - (uint32_t)lv.prev_right_base;
+  const uint32_t gp = rel / A;
+  const double* __restrict__ prev_total = lv.prev_total;
+  double total = 0.0;
+  if (n_par == 1) {
+    total = weight_from_ratio(prev_total[gp], ratio[i_long]);
+    ww[first] = total;
+  } else {
+    const uint32_t g_step = stride / A;
+    if (A_ > 0) {
+      double r[A_ > 0 ? A_ : 1], t[A_ > 0 ? A_ : 1];
+#pragma unroll
+      for (int j = 0; j < A_; ++j) {
+        r[j] = ratio[i_long + (uint32_t)j * c.M];
+        t[j] = prev_total[gp + (uint32_t)j * g_step];
+      }
+#pragma unroll
+      for (int j = 0; j < A_; ++j) {
+        const double v = weight_from_ratio(t[j], r[j]);
+        ww[first + (uint32_t)j * stride] = v;
+        total += v;
+      }
+    } else {
+      for (uint32_t j0 = 0; j0 < A; j0 += 4) {
+        double r[4], t[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          r[u] = j0 + u < A ? ratio[i_long + (j0 + u) * c.M] : 0.0;
+          t[u] = j0 + u < A ? prev_total[gp + (j0 + u) * g_step] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (j0 + u < A) {
+            const double v = weight_from_ratio(t[u], r[u]);
+            ww[first + (j0 + u) * stride] = v;
+            total += v;
+          }
+        }
+      }
+    }
+  }
+  if (deferred) {
+    lv.g_total[g] = total;
+    return;
+  }
+  // the 32 * A children of the warp's 32 groups, contiguous in the table and in the weight vector
+  const uint32_t lane = tid & 31, warp_first = tid - lane;
+  const uint64_t child0 = (uint64_t)(r0.x * (uint32_t)kThreads + warp_first) * A;
+  const uint64_t table0 = (uint64_t)(r0.y + warp_first) * A;
+  double* out = ww + lv.base + (uint64_t)A * lv.n_left + child0;
+#pragma unroll 5
+  for (uint32_t j = lane; j < 32 * A; j += 32) {
+    const double wp = __shfl_sync(0xffffffffu, total, j / A);
+    out[j] = weight_from_ratio(wp, ratio[table0 + j]);
+  }
+  (void)prefix;
+}
+
+// Build side of the plane blocks: is the block of 256 groups starting at 256 * b regular (engine.h
+// Level::PlaneBlock)?  rec[b] is written for every block (prefix0 also orders the other blocks).
+__global__ void __launch_bounds__(kThreads) classify_plane_blocks_kernel(Level lv, Consts c, uint32_t n_blocks,
+                                                                         Level::PlaneBlock* __restrict__ rec,
+                                                                         uint32_t* __restrict__ is_plane) {
+  __shared__ uint32_t base[5];  // first, stride, packed, prefix, long of the block's first group
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  const uint64_t g = (uint64_t)b * kThreads + tid;
+  const bool full = (uint64_t)(b + 1) * kThreads <= lv.n_groups;
+  uint32_t first = 0, stride = 0, packed = 0, prefix = 0, i_long = 0;
+  bool ok = full && lv.g_first != nullptr;
+  if (g < lv.n_groups) prefix = lv.g_prefix[g];
+  if (ok) {
+    first = lv.g_first[g]; stride = lv.g_stride[g]; packed = lv.g_count[g];
+    const uint32_t n = packed & Level::kCountMask;
+    ok = (packed & Level::kOwnsParents) != 0 && lv.prev_total != nullptr;
+    if (ok && n == c.A && (packed & Level::kAllDigits) && c.A > 1) {
+      i_long = prefix;  // parent j reads j * A^(k-1) + prefix
+      ok = stride % c.A == 0;
+    } else if (ok && n == 1) {
+      const uint32_t rel = first - (uint32_t)lv.prev_right_base;
+      const uint64_t at = (uint64_t)lv.prev_prefix[rel / c.A] * c.A + rel % c.A;
+      i_long = (uint32_t)at;
+    } else {
+      ok = false;
+    }
+  }
+  if (tid == 0) { base[0] = first; base[1] = stride; base[2] = packed; base[3] = prefix; base[4] = i_long; }
+  __syncthreads();
+  ok = ok && first == base[0] + tid && stride == base[1] && packed == base[2] && prefix == base[3] + tid &&
+       i_long == base[4] + tid;
+  const int bad = __syncthreads_or(ok ? 0 : 1);
+  if (tid == 0) {
+    Level::PlaneBlock out;
+    out.group_block = b; out.prefix0 = base[3]; out.first0 = base[0]; out.long0 = base[4]; out.stride = base[1];
+    out.meta = (base[2] & Level::kCountMask) | ((base[2] & Level::kChildrenDeferred) ? Level::kPlaneDeferred : 0u);
+    out.pad[0] = out.pad[1] = 0;
+    rec[b] = out;
+    is_plane[b] = bad ? 0u : 1u;
   }
 }
 
@@ -1202,27 +1340,50 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     cur_slab.release(); s1.release(); s2.release();
   }
   // seeds walk through p together (Level::block_order): sort the blocks of 256 groups of every
-  // level by the prefix they start at; a level whose order comes out as the identity keeps none
+  // level by the prefix they start at; a level whose order comes out as the identity keeps none.
+  // The same pass finds the regular blocks (Level::plane_blocks) and lists the others.
   {
-    std::vector<uint32_t> first_prefix, order;
+    std::vector<Level::PlaneBlock> recs;
+    std::vector<uint32_t> flags, order, general;
+    std::vector<Level::PlaneBlock> planes;
     for (Level& lv : m.levels) {
       if (!lv.g_prefix || lv.n_groups <= (uint32_t)kThreads) continue;
       const size_t n_blocks = ((size_t)lv.n_groups + kThreads - 1) / kThreads;
-      first_prefix.resize(n_blocks);
-      TAPES_CUDA_CHECK(cudaMemcpy2DAsync(first_prefix.data(), 4, lv.g_prefix, (size_t)kThreads * 4, 4, n_blocks,
-                                         cudaMemcpyDeviceToHost, st));
+      Level::PlaneBlock* d_rec = dalloc<Level::PlaneBlock>(n_blocks, st);
+      uint32_t* d_flag = dalloc<uint32_t>(n_blocks, st);
+      classify_plane_blocks_kernel<<<(unsigned)n_blocks, kThreads, 0, st>>>(lv, c, (uint32_t)n_blocks, d_rec, d_flag);
+      recs.resize(n_blocks); flags.resize(n_blocks);
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(recs.data(), d_rec, n_blocks * sizeof(Level::PlaneBlock), cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(flags.data(), d_flag, n_blocks * 4, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      dfree(d_rec, st); dfree(d_flag, st);
       order.resize(n_blocks);
       for (size_t b = 0; b < n_blocks; ++b) order[b] = (uint32_t)b;
       std::stable_sort(order.begin(), order.end(),
-                       [&](uint32_t x, uint32_t y) { return first_prefix[x] < first_prefix[y]; });
+                       [&](uint32_t x, uint32_t y) { return recs[x].prefix0 < recs[y].prefix0; });
       bool identity = true;
       for (size_t b = 0; b < n_blocks && identity; ++b) identity = order[b] == b;
-      if (identity) continue;
-      uint32_t* d_order = dkeep<uint32_t>(m, n_blocks);
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), n_blocks * 4, cudaMemcpyHostToDevice, st));
-      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      lv.block_order = d_order;
+      if (!identity) {
+        uint32_t* d_order = dkeep<uint32_t>(m, n_blocks);
+        TAPES_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), n_blocks * 4, cudaMemcpyHostToDevice, st));
+        lv.block_order = d_order;
+      }
+      general.clear(); planes.clear();
+      for (uint32_t b : order) {
+        if (flags[b]) planes.push_back(recs[b]);
+        else general.push_back(b);
+      }
+      if (!planes.empty()) {
+        Level::PlaneBlock* d_planes = dkeep<Level::PlaneBlock>(m, planes.size());
+        uint32_t* d_general = dkeep<uint32_t>(m, general.size());
+        TAPES_CUDA_CHECK(cudaMemcpyAsync(d_planes, planes.data(), planes.size() * sizeof(Level::PlaneBlock), cudaMemcpyHostToDevice, st));
+        if (!general.empty())
+          TAPES_CUDA_CHECK(cudaMemcpyAsync(d_general, general.data(), general.size() * 4, cudaMemcpyHostToDevice, st));
+        lv.plane_blocks = d_planes; lv.n_plane_blocks = (uint32_t)planes.size();
+        lv.general_blocks = d_general; lv.n_general_blocks = (uint32_t)general.size();
+        m.stats.plane_groups += (int64_t)planes.size() * kThreads;
+      }
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));  // the host vectors are reused by the next level
     }
   }
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
@@ -1296,6 +1457,11 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   bool any_groups = false;
   for (const Level& lv : m.levels) any_groups = any_groups || lv.n_groups > 0;
   if (any_groups && m.k >= 2) m.ratio_right = dkeep<double>(m, m.n_states);  // right-extension ratios, per step
+  bool any_full_left = false;  // left parents whose children have a full window
+  for (const Level& lv : m.levels) any_full_left = any_full_left || lv.n_left > 0;
+  if (m.ratio_right && any_full_left && !(std::getenv("TAPES_RATIO_LEFT") && std::atoi(std::getenv("TAPES_RATIO_LEFT")) == 0))
+    m.ratio_left = dkeep<double>(m, m.n_states);
+  if (const char* g = std::getenv("TAPES_PLANE_KERNEL")) m.plane_kernel = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   m.launches_per_rhs = rhs_launch_count(m);
   return mp;
@@ -1330,8 +1496,8 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
     rule_weight_kernel<<<grid_for(m.n_rules, 128), 128, 0, st>>>(t, m.n_rules, m.rule_ptr, m.step_kind, m.step_len,
                                                                 m.step_long, m.step_short, m.step_prob, m.rule_w);
   if (use_ratio)  // writing the ratios from the marginal kernel (which has the operands at hand) measured slower: strided stores
-    ratio_right_kernel<<<grid_for(m.n_states, kThreads * kRatioBatch), kThreads, 0, st>>>(d_p, m.marg + m.marg_off[m.k - 1], m.ratio_right,
-                                                                          m.n_states, c.A);
+    ratio_tables_kernel<<<grid_for(m.n_states, kThreads * kRatioBatch), kThreads, 0, st>>>(
+        d_p, m.marg + m.marg_off[m.k - 1], m.ratio_right, m.ratio_left, m.n_states, c.A, c.M);
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
   for (const Level& stored : m.levels) {
     Level lv = stored;
@@ -1340,9 +1506,22 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       root_kernel<<<grid_for(lv.n_roots, kThreads), kThreads, 0, st>>>(lv.root_rule, lv.n_roots, m.rule_w, m.node_w);
     } else if (lv.n_left + lv.n_groups) {
       const unsigned left_blocks = lv.n_left ? grid_for(lv.n_left, kThreads) : 0;
-      const unsigned group_blocks = lv.n_groups ? grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads) : 0;
+      unsigned group_blocks = lv.n_groups ? grid_for(((uint64_t)lv.n_groups + 31) / 32 * 32, kThreads) : 0;
+      const bool planes = use_ratio && m.plane_kernel && lv.n_plane_blocks > 0;
+      if (planes) {
+        // the regular blocks of this level go to plane_kernel, level_kernel keeps the others
+        lv.block_order = lv.general_blocks;
+        group_blocks = lv.n_general_blocks;
+        switch (c.A) {
+          case 10: plane_kernel<10><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
+          case 4: plane_kernel<4><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
+          case 2: plane_kernel<2><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
+          default: plane_kernel<0><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
+        }
+      }
       const uint32_t q = 32u / c.A, r = 32u % c.A;
       const unsigned grid = left_blocks + group_blocks;
+      if (grid == 0) continue;
       const bool prog = lv.g_first != nullptr;
       // U loads in flight per thread; a group that owns its parents evaluates UO of them at a time
       // (each needs three loads).  Measured at n = 1e8, A = 10 (profiles/r01_g_sweep_fused_right_chain.log):
@@ -1353,9 +1532,9 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
       // (profiles/r01_m_sweep_lean_chain_kernels.log): the deep levels are not bound by registers.
 #define TAPES_LEVEL_R(U_, UO_, B_, R_)                                                                       \
   (prog ? level_kernel<U_, UO_, true, B_, R_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w, \
-                                                                          m.ratio_right)                           \
+                                                                          m.ratio_right, m.ratio_left)             \
         : level_kernel<U_, 1, false, 5, R_><<<grid, kThreads, 0, st>>>(t, c, lv, left_blocks, q, r, m.node_w, m.node_w, \
-                                                                        m.ratio_right))
+                                                                        m.ratio_right, m.ratio_left))
 #define TAPES_LEVEL(U_, UO_, B_) (use_ratio ? TAPES_LEVEL_R(U_, UO_, B_, true) : TAPES_LEVEL_R(U_, UO_, B_, false))
       if (m.level_unroll >= 8) TAPES_LEVEL(8, 4, 4);
       else if (m.level_unroll >= 5) TAPES_LEVEL(5, 3, 5);
@@ -1486,8 +1665,13 @@ int64_t rhs_launch_count(const Model& m) {
   if (top >= 0) launches += 1;          // tail tables
   if (m.n_rules) launches += 1;         // leaf-world probabilities
   if (m.ratio_table && m.ratio_right && m.k >= 2) launches += 1;  // right-extension ratios
-  for (const Level& lv : m.levels)
-    if (lv.n_roots || lv.n_left + lv.n_groups) launches += 1;
+  const bool use_ratio = m.ratio_table && m.ratio_right && m.k >= 2;
+  for (const Level& lv : m.levels) {
+    if (lv.n_roots) { launches += 1; continue; }
+    const bool planes = use_ratio && m.plane_kernel && lv.n_plane_blocks > 0;
+    if (planes) launches += 1;
+    if (lv.n_left + (planes ? lv.n_general_blocks : lv.n_groups)) launches += 1;
+  }
   launches += 1;                        // S * w
   for (const auto& part : m.more) launches += rhs_launch_count(*part);
   return launches;

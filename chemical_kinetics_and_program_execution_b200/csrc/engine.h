@@ -68,6 +68,28 @@ struct Level {
   // through p together and the second reader of an entry finds it in L2.  Null when the level has
   // one seed only (identity) or the option is off.
   const uint32_t* block_order = nullptr;
+  // Plane blocks.  Most prefix groups of a large problem come in long regular stretches: one seed's
+  // groups at one level with consecutive prefixes, consecutive first parents, one stride, one
+  // parent count (A parents that are the A values of the dropped digit, or the single parent of a
+  // group whose dropped digit is a fixed cell of the view), all owning their parents.  A block of
+  // 256 consecutive groups that is regular in this sense needs no per-group records at all: one
+  // 32-byte record describes it (PlaneBlock), and plane_kernel evaluates it with every load of a
+  // thread independent of the others.  plane_blocks lists those blocks, general_blocks the others
+  // (evaluated by level_kernel as before), both in prefix order like block_order.
+  struct PlaneBlock {
+    uint32_t group_block;  // groups 256 * group_block ... + 255
+    uint32_t prefix0;      // prefix of the first group; group t has prefix0 + t
+    uint32_t first0;       // first parent of the first group; group t has first0 + t
+    uint32_t long0;        // table index of parent 0 of the first group; parent j of group t: long0 + t + j * A^(k-1)
+    uint32_t stride;       // node-id distance between the parents of a group
+    uint32_t meta;         // parents per group (1 or A) | kPlaneDeferred
+    uint32_t pad[2];
+  };
+  static constexpr uint32_t kPlaneDeferred = 0x80000000u;
+  const PlaneBlock* plane_blocks = nullptr;
+  uint32_t n_plane_blocks = 0;
+  const uint32_t* general_blocks = nullptr;
+  uint32_t n_general_blocks = 0;
 };
 
 // The flux structure cut into slices of 32 consecutive states, one warp lane per state.  Consecutive
@@ -113,6 +135,7 @@ struct BuildStats {
   int64_t left_parents = 0;      // parent records of left extensions / left shifts, all levels
   int64_t owned_parents = 0;     // right children computed by the group they feed (fused right chain)
   int64_t deferred_groups = 0;   // groups whose children are computed by the next level
+  int64_t plane_groups = 0;      // groups evaluated by plane_kernel (in blocks of 256)
   double host_enumerate_ms = 0, device_expand_ms = 0, device_csr_ms = 0, device_slices_ms = 0;
   double expand_alloc_ms = 0;  // part of device_expand_ms spent inside cudaMalloc / cudaFree
 };
@@ -153,8 +176,10 @@ struct Model {
   int level_unroll = 4;            // loads in flight per thread in level_kernel
   int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
   int interleave_seeds = 1;        // level kernel: use Level::block_order
-  int ratio_table = 1;             // right-extension ratios evaluated once per step into ratio_right
+  int ratio_table = 1;             // extension ratios of full windows evaluated once per step into tables
   double* ratio_right = nullptr;   // [n_states] p[i] / max(p[i], marg_{k-1}[i / A]), 0 where p[i] == 0
+  double* ratio_left = nullptr;    // [n_states] p[i] / max(p[i], marg_{k-1}[i % A^(k-1)]): left extensions / shifts to a full window
+  int plane_kernel = 1;            // regular blocks of prefix groups go to plane_kernel (Level::plane_blocks)
 
   // marginal tables marg_L, L < k, concatenated; marg_off[L] = offset in doubles
   double* marg = nullptr;

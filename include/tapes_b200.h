@@ -156,7 +156,9 @@ int tapes_sync(void* model);
  * structures the model consists of (more than one when the forest exceeds the 31-bit node ids: the
  * flux rules are then split over several structures evaluated one after the other; sizes above are
  * sums over them; TAPES_MAX_PART_TERMS overrides the ~1.7 * 10^9 flux terms a structure may hold), forest
- * levels whose blocks of prefix groups are evaluated in prefix order across seeds.
+ * levels whose blocks of prefix groups are evaluated in prefix order across seeds, prefix groups that
+ * sit in regular blocks of 256 and are evaluated by the plane kernel (csrc/engine.h Level::PlaneBlock),
+ * per-step ratio tables (0, 1: right extensions, 2: also left extensions to a full window).
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
@@ -165,7 +167,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity);
  * (2, 3, 4, 6 or 8 gathers in flight per lane of the sliced product kernel), "interleave_seeds" (1: the
  * level kernel evaluates the blocks of prefix groups of different seeds in prefix order so that they
  * share their reads of the table through L2, 0: in storage order), "ratio_table" (1: the ratios of right extensions are evaluated once per
- * step into a table the level kernel reads, 0: per node), "graphs" (1: for tables of up to
+ * step into a table the level kernel reads, 0: per node), "plane_kernel" (1: regular blocks of 256
+ * prefix groups are evaluated by the record-free plane kernel, 0: by the general level kernel), "graphs" (1: for tables of up to
  * 2^22 states the kernels that evaluate the weights are replayed from a CUDA graph captured per input
  * pointer, 0: launched one by one).  Results do not depend on any of them. */
 int tapes_model_set(void* model, const char* key, int64_t value);

@@ -250,7 +250,8 @@ def test_flux_row_ranges_and_gather_depths(mt, device):
   model.flux_rows(guard, 40, 50)  # nothing outside the range is written
   g = guard.cpu().numpy()
   assert (g[:40] == 7.0).all() and (g[50:] == 7.0).all() and numpy.array_equal(g[40:50], want[40:50])
-  for key, values in (('flux_unroll', (2, 3, 4, 6, 8)), ('level_unroll', (1, 2, 4, 5, 8)), ('interleave_seeds', (0, 1)), ('ratio_table', (0, 1))):
+  for key, values in (('flux_unroll', (2, 3, 4, 6, 8)), ('level_unroll', (1, 2, 4, 5, 8)), ('interleave_seeds', (0, 1)), ('ratio_table', (0, 1)),
+                      ('plane_kernel', (0, 1))):
     keep = model.info.get(key, None)
     for v in values:
       model.set_option(key, v)
@@ -258,6 +259,40 @@ def test_flux_row_ranges_and_gather_depths(mt, device):
     if keep:
       model.set_option(key, keep)
   mt.u_lib.tapes_release_model(b'ex4-chemical-turing', 5)  # later tests get a model with default options
+
+
+@pytest.mark.parametrize('size_a,cl_k,n_rules', [(10, 5, 6), (4, 8, 6), (2, 13, 4), (3, 9, 5), (10, 6, 8)])
+def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle, monkeypatch, size_a, cl_k, n_rules):
+  """Regular blocks of 256 prefix groups are evaluated by plane_kernel (one 32-byte record per block,
+  all loads of a thread independent) and left children with a full window read the left ratio table:
+  same operands, same operations, same order of additions as the general level kernel, so node
+  weights and dy/dt keep their bits; and they match the oracle."""
+  import torch
+  rules = configs.random_rule_set(size_a, n_rules, seed=size_a + cl_k)
+  tag = f'plane-{size_a}-{cl_k}'
+  mt.register_rule_set(tag, size_a, rules)
+  oracle.register_rules(tag, size_a, rules)
+  p_host = configs.markov_table(size_a, cl_k, 3)
+  p = torch.from_numpy(p_host).cuda()
+  model = device.DeviceModel(tag, cl_k)
+  assert model.info['plane_groups'] > 0 and model.info['ratio_tables'] == 2, model.info
+  with_planes, weights = model.rhs(p).cpu().numpy(), model.node_weights()
+  assert_rhs_close(with_planes, oracle.compute_dy_dt(tag, cl_k, p_host, mode=oracle.MERGED), gross_flux(oracle, tag, cl_k, p_host))
+  launches = model.info['launches_per_rhs']
+  model.set_option('plane_kernel', 0)
+  assert model.info['launches_per_rhs'] < launches
+  assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
+  assert numpy.array_equal(model.node_weights(), weights)
+  model.set_option('ratio_table', 0)  # neither table: every node divides
+  assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
+  assert numpy.array_equal(model.node_weights(), weights)
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  monkeypatch.setenv('TAPES_RATIO_LEFT', '0')  # right table only, as in round 1
+  model = device.DeviceModel(tag, cl_k)
+  assert model.info['ratio_tables'] == 1
+  assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
+  assert numpy.array_equal(model.node_weights(), weights)
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
 
 
 @pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex5-msrtf-machine', 5, 5),
