@@ -717,50 +717,57 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
 // at once.  A_ = 0: any alphabet, loads in batches of four.
 template <int A_>
 __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_kernel(Consts c, Level lv, const double* __restrict__ ratio,
-                                                                       double* __restrict__ ww) {
+                                                                       const double* __restrict__ wr, double* __restrict__ ww) {
   const uint4* rec4 = (const uint4*)(lv.plane_blocks + blockIdx.x);
-  const uint4 r0 = rec4[0], r1 = rec4[1];
+  const uint4 r0 = rec4[0], r1 = rec4[1], r2 = rec4[2];
   const uint32_t A = A_ ? (uint32_t)A_ : c.A;
   const uint32_t tid = threadIdx.x;
-  const uint32_t g = r0.x * (uint32_t)kThreads + tid, prefix = r0.y + tid, first = r0.z + tid, i_long = r0.w + tid;
+  const uint32_t g = r0.x * (uint32_t)kThreads + tid, first = r0.z + tid;
+  uint32_t prefix = r0.y + tid;
+  if (tid > r1.z) prefix += r2.y * (1u + (tid - r1.z - 1u) / r2.x);  // r1.z = jump_at, r2.x = period, r2.y = jump
+  const uint32_t i_long = prefix + r0.w;
   const uint32_t stride = r1.x, n_par = r1.y & 0xffffu;
   const bool deferred = (r1.y & Level::kPlaneDeferred) != 0;
-  const uint32_t rel = first - (uint32_t)lv.prev_right_base;
-  const uint32_t gp = rel / A;
-  const double* __restrict__ prev_total = lv.prev_total;
   double total = 0.0;
-  if (n_par == 1) {
-    total = weight_from_ratio(prev_total[gp], ratio[i_long]);
-    ww[first] = total;
+  if (r1.y & Level::kPlaneGather) {
+    total = wr[first];  // the parent is a stored node of the previous level
   } else {
-    const uint32_t g_step = stride / A;
-    if (A_ > 0) {
-      double r[A_ > 0 ? A_ : 1], t[A_ > 0 ? A_ : 1];
-#pragma unroll
-      for (int j = 0; j < A_; ++j) {
-        r[j] = ratio[i_long + (uint32_t)j * c.M];
-        t[j] = prev_total[gp + (uint32_t)j * g_step];
-      }
-#pragma unroll
-      for (int j = 0; j < A_; ++j) {
-        const double v = weight_from_ratio(t[j], r[j]);
-        ww[first + (uint32_t)j * stride] = v;
-        total += v;
-      }
+    const uint32_t rel = first - (uint32_t)lv.prev_right_base;
+    const uint32_t gp = rel / A;
+    const double* __restrict__ prev_total = lv.prev_total;
+    if (n_par == 1) {
+      total = weight_from_ratio(prev_total[gp], ratio[i_long]);
+      ww[first] = total;
     } else {
-      for (uint32_t j0 = 0; j0 < A; j0 += 4) {
-        double r[4], t[4];
+      const uint32_t g_step = stride / A;
+      if (A_ > 0) {
+        double r[A_ > 0 ? A_ : 1], t[A_ > 0 ? A_ : 1];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          r[u] = j0 + u < A ? ratio[i_long + (j0 + u) * c.M] : 0.0;
-          t[u] = j0 + u < A ? prev_total[gp + (j0 + u) * g_step] : 0.0;
+        for (int j = 0; j < A_; ++j) {
+          r[j] = ratio[i_long + (uint32_t)j * c.M];
+          t[j] = prev_total[gp + (uint32_t)j * g_step];
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          if (j0 + u < A) {
-            const double v = weight_from_ratio(t[u], r[u]);
-            ww[first + (j0 + u) * stride] = v;
-            total += v;
+        for (int j = 0; j < A_; ++j) {
+          const double v = weight_from_ratio(t[j], r[j]);
+          ww[first + (uint32_t)j * stride] = v;
+          total += v;
+        }
+      } else {
+        for (uint32_t j0 = 0; j0 < A; j0 += 4) {
+          double r[4], t[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            r[u] = j0 + u < A ? ratio[i_long + (j0 + u) * c.M] : 0.0;
+            t[u] = j0 + u < A ? prev_total[gp + (j0 + u) * g_step] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (j0 + u < A) {
+              const double v = weight_from_ratio(t[u], r[u]);
+              ww[first + (j0 + u) * stride] = v;
+              total += v;
+            }
           }
         }
       }
@@ -770,17 +777,17 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
     lv.g_total[g] = total;
     return;
   }
-  // the 32 * A children of the warp's 32 groups, contiguous in the table and in the weight vector
+  // the 32 * A children of the warp's 32 groups: contiguous in the weight vector, and in the table
+  // wherever the prefixes are
   const uint32_t lane = tid & 31, warp_first = tid - lane;
-  const uint64_t child0 = (uint64_t)(r0.x * (uint32_t)kThreads + warp_first) * A;
-  const uint64_t table0 = (uint64_t)(r0.y + warp_first) * A;
-  double* out = ww + lv.base + (uint64_t)A * lv.n_left + child0;
+  double* out = ww + lv.base + (uint64_t)A * lv.n_left + (uint64_t)(r0.x * (uint32_t)kThreads + warp_first) * A;
 #pragma unroll 5
   for (uint32_t j = lane; j < 32 * A; j += 32) {
-    const double wp = __shfl_sync(0xffffffffu, total, j / A);
-    out[j] = weight_from_ratio(wp, ratio[table0 + j]);
+    const uint32_t gl = j / A, x = j - gl * A;
+    const double wp = __shfl_sync(0xffffffffu, total, gl);
+    const uint32_t pre = __shfl_sync(0xffffffffu, prefix, gl);
+    out[j] = weight_from_ratio(wp, ratio[(uint64_t)pre * A + x]);
   }
-  (void)prefix;
 }
 
 // Build side of the plane blocks: is the block of 256 groups starting at 256 * b regular (engine.h
@@ -788,38 +795,58 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
 __global__ void __launch_bounds__(kThreads) classify_plane_blocks_kernel(Level lv, Consts c, uint32_t n_blocks,
                                                                          Level::PlaneBlock* __restrict__ rec,
                                                                          uint32_t* __restrict__ is_plane) {
-  __shared__ uint32_t base[5];  // first, stride, packed, prefix, long of the block's first group
+  __shared__ uint32_t base[5];  // first, stride, packed, prefix, long - prefix of the block's first group
+  __shared__ uint32_t pre[kThreads];
+  __shared__ uint32_t jump_at, jump_next;
   const uint32_t b = blockIdx.x, tid = threadIdx.x;
   const uint64_t g = (uint64_t)b * kThreads + tid;
   const bool full = (uint64_t)(b + 1) * kThreads <= lv.n_groups;
-  uint32_t first = 0, stride = 0, packed = 0, prefix = 0, i_long = 0;
+  uint32_t first = 0, stride = 0, packed = 0, prefix = 0, long_off = 0;
   bool ok = full && lv.g_first != nullptr;
   if (g < lv.n_groups) prefix = lv.g_prefix[g];
+  pre[tid] = prefix;
+  if (tid == 0) { jump_at = 0xffffffffu; jump_next = 0xffffffffu; }
   if (ok) {
     first = lv.g_first[g]; stride = lv.g_stride[g]; packed = lv.g_count[g];
     const uint32_t n = packed & Level::kCountMask;
-    ok = (packed & Level::kOwnsParents) != 0 && lv.prev_total != nullptr;
-    if (ok && n == c.A && (packed & Level::kAllDigits) && c.A > 1) {
-      i_long = prefix;  // parent j reads j * A^(k-1) + prefix
-      ok = stride % c.A == 0;
-    } else if (ok && n == 1) {
-      const uint32_t rel = first - (uint32_t)lv.prev_right_base;
-      const uint64_t at = (uint64_t)lv.prev_prefix[rel / c.A] * c.A + rel % c.A;
-      i_long = (uint32_t)at;
+    if (packed & Level::kOwnsParents) {
+      ok = lv.prev_total != nullptr;
+      if (ok && n == c.A && (packed & Level::kAllDigits) && c.A > 1) {
+        long_off = 0;  // parent j reads j * A^(k-1) + prefix
+        ok = stride % c.A == 0;
+      } else if (ok && n == 1) {
+        const uint32_t rel = first - (uint32_t)lv.prev_right_base;
+        const uint64_t at = (uint64_t)lv.prev_prefix[rel / c.A] * c.A + rel % c.A;
+        long_off = (uint32_t)at - prefix;
+      } else {
+        ok = false;
+      }
     } else {
-      ok = false;
+      ok = n == 1;  // one stored parent: its weight is gathered
     }
   }
-  if (tid == 0) { base[0] = first; base[1] = stride; base[2] = packed; base[3] = prefix; base[4] = i_long; }
+  if (tid == 0) { base[0] = first; base[1] = stride; base[2] = packed; base[3] = prefix; base[4] = long_off; }
   __syncthreads();
-  ok = ok && first == base[0] + tid && stride == base[1] && packed == base[2] && prefix == base[3] + tid &&
-       i_long == base[4] + tid;
+  // where the prefix does not simply count up: first such place, then the next one
+  const bool jumps_here = tid + 1 < (uint32_t)kThreads && pre[tid + 1] != pre[tid] + 1u;
+  if (jumps_here) atomicMin(&jump_at, tid);
+  __syncthreads();
+  const uint32_t a = jump_at;
+  if (jumps_here && tid > a) atomicMin(&jump_next, tid);
+  __syncthreads();
+  const uint32_t period = jump_next != 0xffffffffu ? jump_next - a : 0x40000000u;
+  const uint32_t jump = a != 0xffffffffu ? pre[a + 1] - pre[a] - 1u : 0u;
+  uint32_t expect = base[3] + tid;
+  if (tid > a) expect += jump * (1u + (tid - a - 1u) / period);
+  ok = ok && first == base[0] + tid && stride == base[1] && packed == base[2] && prefix == expect && long_off == base[4];
   const int bad = __syncthreads_or(ok ? 0 : 1);
   if (tid == 0) {
     Level::PlaneBlock out;
-    out.group_block = b; out.prefix0 = base[3]; out.first0 = base[0]; out.long0 = base[4]; out.stride = base[1];
-    out.meta = (base[2] & Level::kCountMask) | ((base[2] & Level::kChildrenDeferred) ? Level::kPlaneDeferred : 0u);
-    out.pad[0] = out.pad[1] = 0;
+    out.group_block = b; out.prefix0 = base[3]; out.first0 = base[0]; out.long_off = base[4]; out.stride = base[1];
+    out.meta = (base[2] & Level::kCountMask) | ((base[2] & Level::kChildrenDeferred) ? Level::kPlaneDeferred : 0u) |
+               ((base[2] & Level::kOwnsParents) ? 0u : Level::kPlaneGather);
+    out.jump_at = a; out.period = period; out.jump = jump;
+    out.pad[0] = out.pad[1] = out.pad[2] = 0;
     rec[b] = out;
     is_plane[b] = bad ? 0u : 1u;
   }
@@ -1459,7 +1486,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (any_groups && m.k >= 2) m.ratio_right = dkeep<double>(m, m.n_states);  // right-extension ratios, per step
   bool any_full_left = false;  // left parents whose children have a full window
   for (const Level& lv : m.levels) any_full_left = any_full_left || lv.n_left > 0;
-  if (m.ratio_right && any_full_left && !(std::getenv("TAPES_RATIO_LEFT") && std::atoi(std::getenv("TAPES_RATIO_LEFT")) == 0))
+  // Off unless asked for: at the bench size the second table costs 0.21 ms per step (0.8 GB written) and
+  // the division-free left part of the level kernel gains 0.11 ms (profiles/r02_c_sweep*.log): the
+  // level kernel is not bound by its divisions.
+  if (m.ratio_right && any_full_left && std::getenv("TAPES_RATIO_LEFT") && std::atoi(std::getenv("TAPES_RATIO_LEFT")) != 0)
     m.ratio_left = dkeep<double>(m, m.n_states);
   if (const char* g = std::getenv("TAPES_PLANE_KERNEL")) m.plane_kernel = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1513,10 +1543,10 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
         lv.block_order = lv.general_blocks;
         group_blocks = lv.n_general_blocks;
         switch (c.A) {
-          case 10: plane_kernel<10><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
-          case 4: plane_kernel<4><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
-          case 2: plane_kernel<2><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
-          default: plane_kernel<0><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w); break;
+          case 10: plane_kernel<10><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
+          case 4: plane_kernel<4><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
+          case 2: plane_kernel<2><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
+          default: plane_kernel<0><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
         }
       }
       const uint32_t q = 32u / c.A, r = 32u % c.A;

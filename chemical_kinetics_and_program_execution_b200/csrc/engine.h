@@ -69,23 +69,29 @@ struct Level {
   // one seed only (identity) or the option is off.
   const uint32_t* block_order = nullptr;
   // Plane blocks.  Most prefix groups of a large problem come in long regular stretches: one seed's
-  // groups at one level with consecutive prefixes, consecutive first parents, one stride, one
+  // groups at one level.  Their first parents are consecutive node ids, they share one stride, one
   // parent count (A parents that are the A values of the dropped digit, or the single parent of a
-  // group whose dropped digit is a fixed cell of the view), all owning their parents.  A block of
-  // 256 consecutive groups that is regular in this sense needs no per-group records at all: one
-  // 32-byte record describes it (PlaneBlock), and plane_kernel evaluates it with every load of a
-  // thread independent of the others.  plane_blocks lists those blocks, general_blocks the others
-  // (evaluated by level_kernel as before), both in prefix order like block_order.
+  // group whose dropped digit is a fixed cell of the view) and one set of flags, and their prefixes
+  // are consecutive except where the fixed cells of the seed's view sit inside the prefix: there the
+  // prefix jumps by a constant every `period` groups.  A block of 256 consecutive groups that is
+  // regular in this sense needs no per-group records at all: one 48-byte record describes it
+  // (PlaneBlock), and plane_kernel evaluates it with every load of a thread independent of the
+  // others.  plane_blocks lists those blocks, general_blocks the others (evaluated by level_kernel
+  // as before), both in prefix order like block_order.
   struct PlaneBlock {
     uint32_t group_block;  // groups 256 * group_block ... + 255
-    uint32_t prefix0;      // prefix of the first group; group t has prefix0 + t
+    uint32_t prefix0;      // prefix of the first group; group t: prefix0 + t + jump * (jumps before t)
     uint32_t first0;       // first parent of the first group; group t has first0 + t
-    uint32_t long0;        // table index of parent 0 of the first group; parent j of group t: long0 + t + j * A^(k-1)
+    uint32_t long_off;     // table index of parent j of a group = its prefix + long_off + j * A^(k-1)
     uint32_t stride;       // node-id distance between the parents of a group
-    uint32_t meta;         // parents per group (1 or A) | kPlaneDeferred
-    uint32_t pad[2];
+    uint32_t meta;         // parents per group (1 or A) | kPlaneDeferred | kPlaneGather
+    uint32_t jump_at;      // last group before the first jump of the prefix (0xffffffff: no jump in the block)
+    uint32_t period;       // groups between jumps
+    uint32_t jump;         // what a jump adds on top of the usual + 1
+    uint32_t pad[3];
   };
   static constexpr uint32_t kPlaneDeferred = 0x80000000u;
+  static constexpr uint32_t kPlaneGather = 0x40000000u;  // the single parent is a stored node (not owned): its weight is read
   const PlaneBlock* plane_blocks = nullptr;
   uint32_t n_plane_blocks = 0;
   const uint32_t* general_blocks = nullptr;

@@ -274,6 +274,7 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
   oracle.register_rules(tag, size_a, rules)
   p_host = configs.markov_table(size_a, cl_k, 3)
   p = torch.from_numpy(p_host).cuda()
+  monkeypatch.setenv('TAPES_RATIO_LEFT', '1')  # the left table is an option (it does not pay at the bench size)
   model = device.DeviceModel(tag, cl_k)
   assert model.info['plane_groups'] > 0 and model.info['ratio_tables'] == 2, model.info
   with_planes, weights = model.rhs(p).cpu().numpy(), model.node_weights()
@@ -287,7 +288,7 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
   assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
   assert numpy.array_equal(model.node_weights(), weights)
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
-  monkeypatch.setenv('TAPES_RATIO_LEFT', '0')  # right table only, as in round 1
+  monkeypatch.delenv('TAPES_RATIO_LEFT')  # the default: right table only
   model = device.DeviceModel(tag, cl_k)
   assert model.info['ratio_tables'] == 1
   assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
