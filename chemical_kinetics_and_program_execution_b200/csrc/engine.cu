@@ -724,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
   const uint32_t tid = threadIdx.x;
   const uint32_t g = r0.x * (uint32_t)kThreads + tid, first = r0.z + tid;
   uint32_t prefix = r0.y + tid;
-  if (tid > r1.z) prefix += r2.y * (1u + (tid - r1.z - 1u) / r2.x);  // r1.z = jump_at, r2.x = period, r2.y = jump
+  if (tid > r1.z) prefix += r2.x * (1u + (tid - r1.z - 1u) / r1.w);  // r1.z = jump_at, r1.w = period, r2.x = jump
   const uint32_t i_long = prefix + r0.w;
   const uint32_t stride = r1.x, n_par = r1.y & 0xffffu;
   const bool deferred = (r1.y & Level::kPlaneDeferred) != 0;

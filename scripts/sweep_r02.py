@@ -9,7 +9,7 @@ import numpy, torch
 import bench
 from chemical_kinetics_and_program_execution_b200 import configs, device, markov_tapes as mt
 
-A, k, R = (int(x) for x in sys.argv[1:4]) if len(sys.argv) > 3 else (10, 8, 24)
+A, k, R = (int(x) for x in sys.argv[1:4]) if len(sys.argv) > 3 and sys.argv[1].isdigit() else (10, 8, 24)
 rules = configs.random_rule_set(A, R, seed=1)
 tag = configs.synthetic_tag(A, R, 1)
 mt.register_rule_set(tag, A, rules)
@@ -43,6 +43,8 @@ os.environ['TAPES_RATIO_LEFT'] = '0'
 mt.u_lib.tapes_release_model(tag.encode(), k)
 model = device.DeviceModel(tag, k)
 
+if '--no-host' in sys.argv:
+  sys.exit(0)
 # host-buffer entry point
 n = A ** k
 h_in = torch.empty(n, dtype=torch.float64).pin_memory()
