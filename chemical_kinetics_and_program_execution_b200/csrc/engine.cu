@@ -15,6 +15,7 @@
 #include <cstring>
 #include <type_traits>
 
+#include "flux_device.cuh"
 #include "hostcopy.h"
 #include "primitives.cuh"
 
@@ -455,12 +456,9 @@ __device__ __forceinline__ const double* table(const Tables& t, int L) {
 
 // Leaf-world probabilities: product of unfold ratios (tm.scm:556-565) and choice
 // probabilities (tm.scm:617-618) in program order.
-__global__ void rule_weight_kernel(Tables t, uint32_t n_rules, const uint32_t* __restrict__ rule_ptr,
-                                   const uint8_t* __restrict__ kind, const uint8_t* __restrict__ len,
-                                   const uint32_t* __restrict__ ilong, const uint32_t* __restrict__ ishort,
-                                   const double* __restrict__ prob, double* __restrict__ rule_w) {
-  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= n_rules) return;
+__device__ __forceinline__ double rule_weight(const Tables& t, uint32_t r, const uint32_t* rule_ptr, const uint8_t* kind,
+                                              const uint8_t* len, const uint32_t* ilong, const uint32_t* ishort,
+                                              const double* prob) {
   double w = 1.0;
   for (uint32_t s = rule_ptr[r]; s < rule_ptr[r + 1]; ++s) {
     if (kind[s] == Step::UNFOLD) {
@@ -474,7 +472,15 @@ __global__ void rule_weight_kernel(Tables t, uint32_t n_rules, const uint32_t* _
       w = fmax(0.0, prob[s]) * w;
     }
   }
-  rule_w[r] = w;
+  return w;
+}
+
+__global__ void rule_weight_kernel(Tables t, uint32_t n_rules, const uint32_t* __restrict__ rule_ptr,
+                                   const uint8_t* __restrict__ kind, const uint8_t* __restrict__ len,
+                                   const uint32_t* __restrict__ ilong, const uint32_t* __restrict__ ishort,
+                                   const double* __restrict__ prob, double* __restrict__ rule_w) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < n_rules) rule_w[r] = rule_weight(t, r, rule_ptr, kind, len, ilong, ishort, prob);
 }
 
 __global__ void root_kernel(const uint32_t* __restrict__ root_rule, uint32_t n_roots,
@@ -530,8 +536,8 @@ __global__ void __launch_bounds__(kThreads) ratio_tables_kernel(const double* __
 // and returns the sum over j in ascending order.  DIRECT: the parents are the A values of the
 // dropped digit in order, so their table indices follow from the group's own prefix.
 template <int UO, bool DIRECT, bool RATIO>
-__device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, const double* __restrict__ p,
-                                              const double* __restrict__ short_table, double* __restrict__ ww,
+__device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, const double* p,
+                                              const double* short_table, double* ww,
                                               uint64_t g, uint32_t first, uint32_t stride, uint32_t n,
                                               uint32_t g_prev, uint32_t g_step, uint32_t x_prev) {
   double total = 0.0;
@@ -577,13 +583,15 @@ __device__ __forceinline__ double own_parents(const Level& lv, const Consts& c, 
 // Loads are issued U at a time before the divisions and stores that depend on them: the kernel is
 // bound by HBM latency x bandwidth, and one load in flight per thread reaches ~60 % of peak only
 // (profiles/r01_c_*).  wr and ww are the same vector: reads touch earlier levels only.
-template <int U, int UO, bool PROGRESSIONS, int MIN_BLOCKS, bool RATIO>
-__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
-                                                         uint32_t warp_step_q, uint32_t warp_step_r,
-                                                         const double* __restrict__ wr, double* __restrict__ ww,
-                                                         const double* __restrict__ ratio, const double* __restrict__ ratio_left) {
-  if (blockIdx.x < left_blocks) {
-    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+// The body takes the block index and the thread index inside the block (256 threads) as arguments so
+// that the single-launch kernel of small problems (fused_rhs_kernel) can run the same code over
+// virtual blocks.  Its pointers carry no __restrict__: the kernels that inline it say what may alias.
+template <int U, int UO, bool PROGRESSIONS, bool RATIO>
+__device__ __forceinline__ void level_body(const Tables& t, const Consts& c, const Level& lv, uint32_t left_blocks,
+                                           uint32_t warp_step_q, uint32_t warp_step_r, const double* wr, double* ww,
+                                           const double* ratio, const double* ratio_left, uint32_t block, uint32_t tid) {
+  if (block < left_blocks) {
+    const uint32_t r = block * (uint32_t)kThreads + tid;
     if (r >= lv.n_left) return;
     const int len = lv.lp_len[r];
     const uint32_t bo = lv.lp_io[r];
@@ -603,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
       }
       return;
     }
-    const double* __restrict__ tl = table(t, len);
+    const double* tl = table(t, len);
     const double p_short = table(t, len - 1)[bo];
     for (uint32_t x0 = 0; x0 < c.A; x0 += U) {
       double p_long[U];
@@ -614,9 +622,9 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
         if (x0 + u < c.A) out[(uint64_t)(x0 + u) * lv.n_left] = child_weight(wp, p_long[u], p_short);
     }
   } else {
-    const unsigned lane = threadIdx.x & 31;
-    const uint32_t group_block = lv.block_order ? lv.block_order[blockIdx.x - left_blocks] : blockIdx.x - left_blocks;
-    const uint32_t warp = group_block * (kThreads / 32) + (threadIdx.x >> 5);
+    const unsigned lane = tid & 31;
+    const uint32_t group_block = lv.block_order ? lv.block_order[block - left_blocks] : block - left_blocks;
+    const uint32_t warp = group_block * (kThreads / 32) + (tid >> 5);
     const uint64_t g0 = (uint64_t)warp * 32;
     if (g0 >= lv.n_groups) return;
     const uint64_t g = g0 + lane;
@@ -624,7 +632,7 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
     uint32_t prefix = 0;
     bool deferred = true;  // lanes without a group have no children to write
     // right extensions: the table itself, or (RATIO) the per-window ratios ratio_right_kernel left behind
-    const double* __restrict__ p = RATIO ? ratio : t.p;
+    const double* p = RATIO ? ratio : t.p;
     if (g < lv.n_groups) {
       if (PROGRESSIONS) {  // parents first, first + stride, ...
         const uint32_t first = lv.g_first[g], stride = lv.g_stride[g], packed = lv.g_count[g];
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
           // evaluate and store them here (tm.scm:1310-1318 for the previous shift), then add them up
           const uint32_t rel = first - (uint32_t)lv.prev_right_base;
           const uint32_t g_prev = rel / c.A, x_prev = rel - g_prev * c.A, g_step = stride / c.A;
-          const double* __restrict__ short_table = table(t, c.k - 1);
+          const double* short_table = table(t, c.k - 1);
           if (packed & Level::kAllDigits)
             total = own_parents<UO, true, RATIO>(lv, c, p, short_table, ww, g, first, stride, n, g_prev, g_step, x_prev);
           else
@@ -707,6 +715,15 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
       }
     }
   }
+}
+
+template <int U, int UO, bool PROGRESSIONS, int MIN_BLOCKS, bool RATIO>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, Consts c, Level lv, uint32_t left_blocks,
+                                                         uint32_t warp_step_q, uint32_t warp_step_r,
+                                                         const double* __restrict__ wr, double* __restrict__ ww,
+                                                         const double* __restrict__ ratio, const double* __restrict__ ratio_left) {
+  level_body<U, UO, PROGRESSIONS, RATIO>(t, c, lv, left_blocks, warp_step_q, warp_step_r, wr, ww, ratio, ratio_left, blockIdx.x,
+                                         threadIdx.x);
 }
 
 // One regular block of 256 prefix groups (engine.h Level::PlaneBlock): thread t evaluates group t of
@@ -849,6 +866,124 @@ __global__ void __launch_bounds__(kThreads) classify_plane_blocks_kernel(Level l
     out.pad[0] = out.pad[1] = out.pad[2] = 0;
     rec[b] = out;
     is_plane[b] = bad ? 0u : 1u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small problems: the whole right-hand side in ONE launch.
+//
+// The reference's shipped problems have 8 ... 10^5 states; about 20 dependent kernels of a few
+// microseconds each were launch latency and nothing else (ex2 at cl_k = 7: 57.6 us on the GPU
+// against 40 us for the CPU port, profiles/r01_l_*).  Here one thread block, or one cluster of up to
+// 16 thread blocks (distributed over as many SMs, synchronised by the hardware cluster barrier), walks
+// through the phases - marginal tables, leaf-world probabilities and ratio table, every forest
+// level, the product - with a barrier between them.  The phases run the very code of the separate
+// kernels (level_body, slice_sum, rule_weight), over virtual blocks, so every result keeps its bits.
+// ---------------------------------------------------------------------------------------------
+struct FusedLevel {
+  Level lv;
+  uint32_t left_blocks, group_blocks, warp_step_q, warp_step_r;
+};
+
+struct FusedArgs {
+  const FusedLevel* levels;
+  int n_levels;
+  uint32_t n_rules;
+  const uint32_t* rule_ptr;
+  const uint8_t* step_kind;
+  const uint8_t* step_len;
+  const uint32_t* step_long;
+  const uint32_t* step_short;
+  const double* step_prob;
+  double* rule_w;
+  double* marg;
+  double* ratio_right;
+  double* node_w;
+  const uint64_t* slice_ptr;
+  const uint32_t* slice_runs;
+  const uint32_t* words;
+  uint64_t n_states, n_slices;
+  double* out;
+  int fused_update;
+};
+
+constexpr int kFusedThreads = 1024;
+
+template <bool CLUSTER>
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, Consts c, FusedArgs a, StageUpdate up) {
+  uint32_t cta = 0, n_cta = 1;
+  if (CLUSTER) {
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta));
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(n_cta));
+  }
+  auto phase_barrier = [&]() {
+    if (CLUSTER) {
+      // release / acquire at cluster scope: the global writes of the phase are visible to all blocks
+      asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+      asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+      __syncthreads();
+    }
+  };
+  const uint32_t gtid = cta * kFusedThreads + threadIdx.x, gthreads = n_cta * kFusedThreads;
+  const double* p = t.p;
+  // marginal tables, longest first (tm.scm:378-384: j ascending from an exact 0)
+  uint64_t n_out = c.M;
+  for (int L = c.k - 1; L >= 0; --L) {
+    const double* src = (L + 1 == c.k) ? p : a.marg + t.off[L + 1];
+    double* dst = a.marg + t.off[L];
+    for (uint64_t i = gtid; i < n_out; i += gthreads) {
+      const double* s = src + i * c.A;
+      double total = 0.0;
+      for (uint32_t j = 0; j < c.A; ++j) total = total + s[j];
+      dst[i] = total;
+    }
+    n_out /= c.A;
+    phase_barrier();
+  }
+  // leaf-world probabilities and the right-extension ratios
+  for (uint32_t r = gtid; r < a.n_rules; r += gthreads)
+    a.rule_w[r] = rule_weight(t, r, a.rule_ptr, a.step_kind, a.step_len, a.step_long, a.step_short, a.step_prob);
+  if (a.ratio_right) {
+    const double* short_table = a.marg + t.off[c.k - 1];
+    for (uint64_t i = gtid; i < a.n_states; i += gthreads) a.ratio_right[i] = extension_ratio(p[i], short_table[i / c.A]);
+  }
+  phase_barrier();
+  // forest levels over virtual blocks of 256 threads
+  const uint32_t sub = threadIdx.x / kThreads, tid = threadIdx.x % kThreads;
+  constexpr uint32_t kSubs = kFusedThreads / kThreads;
+  for (int l = 0; l < a.n_levels; ++l) {
+    const FusedLevel& fl = a.levels[l];
+    if (fl.lv.n_roots) {
+      for (uint32_t i = gtid; i < fl.lv.n_roots; i += gthreads) a.node_w[i] = a.rule_w[fl.lv.root_rule[i]];
+    } else {
+      const uint32_t blocks = fl.left_blocks + fl.group_blocks;
+      if (fl.lv.g_first != nullptr || fl.lv.n_groups == 0) {
+        for (uint32_t vb = cta * kSubs + sub; vb < blocks; vb += n_cta * kSubs)
+          level_body<4, 2, true, true>(t, c, fl.lv, fl.left_blocks, fl.warp_step_q, fl.warp_step_r, a.node_w, a.node_w,
+                                       a.ratio_right, nullptr, vb, tid);
+      } else {
+        for (uint32_t vb = cta * kSubs + sub; vb < blocks; vb += n_cta * kSubs)
+          level_body<4, 1, false, true>(t, c, fl.lv, fl.left_blocks, fl.warp_step_q, fl.warp_step_r, a.node_w, a.node_w,
+                                        a.ratio_right, nullptr, vb, tid);
+      }
+    }
+    phase_barrier();
+  }
+  // the product, one slice of 32 states per warp
+  const unsigned lane = threadIdx.x & 31;
+  for (uint64_t s = gtid >> 5; s < a.n_slices; s += gthreads >> 5) {
+    const double acc = slice_sum<4>(a.slice_ptr, a.slice_runs, a.words, a.node_w, s, lane);
+    const uint64_t row = s * 32 + lane;
+    if (row < a.n_states) {
+      a.out[row] = acc;
+      if (a.fused_update) {  // Runge-Kutta stage update, terms in tableau order (as in flux_slices_kernel)
+        double sum = 0.0;
+        for (int j = 0; j < up.n; ++j) sum += up.vec[j][row] * up.coef[j];
+        sum += acc * up.coef_self;
+        up.stage[row] = up.y[row] + sum * up.h;
+      }
+    }
   }
 }
 
@@ -1493,6 +1628,19 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.ratio_left = dkeep<double>(m, m.n_states);
   if (const char* g = std::getenv("TAPES_PLANE_KERNEL")) m.plane_kernel = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  // small problems: one launch per right-hand side.  Work = what the phases touch; one block up to
+  // 2^15, a cluster of 8 (the portable size) up to 2^19, of 16 up to 2^22 (measured crossover with the
+  // multi-launch path: profiles/r02_*small*).
+  {
+    const uint64_t work = m.n_nodes + m.nnz + m.n_states;
+    m.fused_cluster = work <= (1ull << 15) ? 1 : (work <= (1ull << 19) ? 8 : (work <= (1ull << 22) ? 16 : 0));
+    if (m.flux_format != 1 || m.n_rules == 0 || m.k < 1) m.fused_cluster = 0;
+    if (const char* e = std::getenv("TAPES_FUSED_CLUSTER")) {
+      const int v = std::atoi(e);
+      if (v == 0 || v == 1 || v == 2 || v == 4 || v == 8 || v == 16) m.fused_cluster = m.flux_format == 1 && m.n_rules ? v : 0;
+    }
+    if (const char* e = std::getenv("TAPES_FUSED_SMALL")) m.fused_small = std::atoi(e) != 0;
+  }
   m.launches_per_rhs = rhs_launch_count(m);
   return mp;
 }
@@ -1621,6 +1769,59 @@ void launch_flux(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi, cuda
   }
 }
 
+// The whole right-hand side of a small single-structure model in one launch; false when the model is
+// not eligible (the caller then takes the multi-launch path).
+bool launch_fused(Model& m, const double* d_p, double* d_out, cudaStream_t st, const StageUpdate* up) {
+  if (!m.fused_small || m.fused_cluster <= 0 || !m.more.empty() || m.flux_format != 1) return false;
+  if (m.ratio_right == nullptr) {  // the fused kernel reads right-extension ratios from the table
+    for (const Level& lv : m.levels)
+      if (lv.n_groups) return false;
+  }
+  const Consts c = make_consts(m);
+  if (!m.d_fused_levels) {
+    std::vector<FusedLevel> host(m.levels.size());
+    for (size_t i = 0; i < m.levels.size(); ++i) {
+      FusedLevel& fl = host[i];
+      fl.lv = m.levels[i];
+      if (!m.interleave_seeds) fl.lv.block_order = nullptr;
+      fl.left_blocks = fl.lv.n_left ? grid_for(fl.lv.n_left, kThreads) : 0;
+      fl.group_blocks = fl.lv.n_groups ? grid_for(((uint64_t)fl.lv.n_groups + 31) / 32 * 32, kThreads) : 0;
+      fl.warp_step_q = 32u / c.A; fl.warp_step_r = 32u % c.A;
+    }
+    FusedLevel* d = dkeep<FusedLevel>(m, host.size());
+    TAPES_CUDA_CHECK(cudaMemcpy(d, host.data(), host.size() * sizeof(FusedLevel), cudaMemcpyHostToDevice));
+    m.d_fused_levels = d;
+    static bool allowed = false;
+    if (!allowed) {
+      TAPES_CUDA_CHECK(cudaFuncSetAttribute(fused_rhs_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      allowed = true;
+    }
+  }
+  Tables t;
+  t.p = d_p; t.marg = m.marg; t.k = m.k;
+  for (int i = 0; i < 34; ++i) t.off[i] = i <= m.k ? m.marg_off[i] : 0;
+  FusedArgs a;
+  a.levels = (const FusedLevel*)m.d_fused_levels; a.n_levels = (int)m.levels.size();
+  a.n_rules = m.n_rules; a.rule_ptr = m.rule_ptr; a.step_kind = m.step_kind; a.step_len = m.step_len;
+  a.step_long = m.step_long; a.step_short = m.step_short; a.step_prob = m.step_prob; a.rule_w = m.rule_w;
+  a.marg = m.marg; a.ratio_right = m.k >= 2 ? m.ratio_right : nullptr; a.node_w = m.node_w;
+  a.slice_ptr = m.slices.slice_ptr; a.slice_runs = m.slices.slice_runs; a.words = m.slices.words;
+  a.n_states = m.n_states; a.n_slices = m.slices.n_slices; a.out = d_out; a.fused_update = up ? 1 : 0;
+  StageUpdate upd = up ? *up : StageUpdate();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)m.fused_cluster); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (m.fused_cluster > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)m.fused_cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    TAPES_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_rhs_kernel<true>, t, c, a, upd));
+  } else {
+    TAPES_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fused_rhs_kernel<false>, t, c, a, upd));
+  }
+  return true;
+}
+
 void launch_all_weights_plain(Model& m, const double* d_p, cudaStream_t st) {
   launch_weights(m, d_p, st, nullptr);
   for (auto& part : m.more) launch_weights(*part, d_p, st, nullptr);
@@ -1689,6 +1890,11 @@ void launch_all_weights(Model& m, const double* d_p, cudaStream_t st) {
 }  // namespace
 
 int64_t rhs_launch_count(const Model& m) {
+  if (m.fused_small && m.fused_cluster > 0 && m.more.empty() && m.flux_format == 1) {
+    bool table_ok = m.ratio_right != nullptr;
+    for (const Level& lv : m.levels) table_ok = table_ok || lv.n_groups == 0;
+    if (table_ok || m.levels.empty()) return 1;  // fused_rhs_kernel
+  }
   int64_t launches = 0;
   const int top = marginal_tail_top(m);
   launches += (m.k - 1 - top);          // one kernel per long marginal table
@@ -1710,16 +1916,20 @@ int64_t rhs_launch_count(const Model& m) {
 void rhs_device(Model& m, const double* d_p, double* d_out, cudaStream_t stream) {
   cudaStream_t st = stream ? stream : m.stream;
   begin_use(m, st);
-  launch_all_weights(m, d_p, st);
-  launch_flux(m, d_out, 0, m.n_states, st);
+  if (!launch_fused(m, d_p, d_out, st, nullptr)) {
+    launch_all_weights(m, d_p, st);
+    launch_flux(m, d_out, 0, m.n_states, st);
+  }
   end_use(m, st);
 }
 
 void rhs_device_fused(Model& m, const double* d_p, double* d_out, const StageUpdate& up, cudaStream_t stream) {
   cudaStream_t st = stream ? stream : m.stream;
   begin_use(m, st);
-  launch_all_weights(m, d_p, st);
-  launch_flux(m, d_out, 0, m.n_states, st, &up);
+  if (!launch_fused(m, d_p, d_out, st, &up)) {
+    launch_all_weights(m, d_p, st);
+    launch_flux(m, d_out, 0, m.n_states, st, &up);
+  }
   end_use(m, st);
 }
 

@@ -16,14 +16,13 @@
 #include <memory>
 
 #include "engine.h"
+#include "flux_device.cuh"
 #include "primitives.cuh"
 
 namespace tapes {
 
 namespace {
 
-constexpr uint32_t kNone = 0xffffffffu;  // node ids stay below 2^31 - 1, so this is never an entry
-constexpr uint32_t kSignBit = 0x80000000u;
 constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 
@@ -181,64 +180,6 @@ __global__ void run_facts_kernel(const uint64_t* __restrict__ slice_ptr, const u
     pairs += __shfl_down_sync(0xffffffffu, pairs, d);
   }
   if ((threadIdx.x & 31) == 0) { atomicAdd(&facts[0], runs); atomicAdd(&facts[1], held); atomicAdd(&facts[2], pairs); }
-}
-
-// dy/dt for one slice per warp.  Every lane sums its state's terms in the order runs, then
-// columns.  The kernel is bound by memory latency x bandwidth (ncu, profiles/r01_f_*: 67 % of the
-// HBM peak with 4 gathers per lane and one dependent load phase per batch), so U gathers are in
-// flight per lane and the column words of the next batch are loaded while the current one is
-// gathered.
-template <int U>
-__device__ __forceinline__ double slice_sum(const uint64_t* __restrict__ slice_ptr,
-                                            const uint32_t* __restrict__ slice_runs,
-                                            const uint32_t* __restrict__ words, const double* __restrict__ w,
-                                            uint64_t s, unsigned lane) {
-  const uint64_t at = slice_ptr[s], stop = slice_ptr[s + 1];
-  const uint32_t n_runs = slice_runs[s];
-  const uint32_t n_pairs = (n_runs + 1u) & ~1u;
-  const uint2* __restrict__ runs = (const uint2*)(words + at);
-  const uint32_t* __restrict__ cols = words + at + 2ull * n_pairs + lane;
-  const uint32_t n_cols = (uint32_t)((stop - at - 2ull * n_pairs) >> 5);
-  const uint32_t below = (1u << lane) - 1u;
-  double acc = 0.0;
-
-  uint2 mine = lane < n_runs ? runs[lane] : make_uint2(0u, 0u);
-  uint32_t v[U];  // column words of the batch about to be gathered
-#pragma unroll
-  for (int u = 0; u < U; ++u) v[u] = (uint32_t)u < n_cols ? cols[32u * u] : kNone;
-
-  for (uint32_t j0 = 0; j0 < n_runs; j0 += 32) {
-    const uint32_t here = min(32u, n_runs - j0);
-    for (uint32_t jj = 0; jj < here; jj += U) {  // lanes past `here` hold the empty run
-      uint32_t first[U], mask[U];
-      double x[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        first[u] = __shfl_sync(0xffffffffu, mine.x, (jj + u) & 31);
-        mask[u] = __shfl_sync(0xffffffffu, mine.y, (jj + u) & 31);
-        if (32 % U != 0 && jj + u >= 32) mask[u] = 0;
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        x[u] = ((mask[u] >> lane) & 1u) ? w[(first[u] & ~kSignBit) + __popc(mask[u] & below)] : 0.0;
-#pragma unroll
-      for (int u = 0; u < U; ++u) acc += (first[u] & kSignBit) ? -x[u] : x[u];
-    }
-    if (j0 + 32 < n_runs) mine = j0 + 32 + lane < n_runs ? runs[j0 + 32 + lane] : make_uint2(0u, 0u);
-  }
-  for (uint32_t c0 = 0; c0 < n_cols; c0 += U) {
-    uint32_t ahead[U];
-    double x[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) ahead[u] = c0 + U + u < n_cols ? cols[32u * (c0 + U + u)] : kNone;
-#pragma unroll
-    for (int u = 0; u < U; ++u) x[u] = v[u] != kNone ? w[v[u] & ~kSignBit] : 0.0;
-#pragma unroll
-    for (int u = 0; u < U; ++u) acc += (v[u] & kSignBit) ? -x[u] : x[u];
-#pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = ahead[u];
-  }
-  return acc;
 }
 
 template <int U, bool FUSED, int MIN_BLOCKS>

@@ -208,6 +208,7 @@ def test_graph_replay_is_bit_identical(mt, device, p0_fixtures):
   side = torch.cuda.Stream()
   torch.cuda.synchronize()
   results = []
+  model.set_option('fused_small', 0)  # the single-launch kernel would bypass the graphs this test is about
   for flag in (1, 0):
     model.set_option('graphs', flag)
     host = [f(p, 0.0) for p in tables for _ in range(2)]
@@ -215,10 +216,48 @@ def test_graph_replay_is_bit_identical(mt, device, p0_fixtures):
       outs = [model.rhs(b).cpu().numpy() for _ in range(2) for b in bufs]
     results.append((host + outs, mt.ode_integrate_device(**kw)))
   model.set_option('graphs', 1)
+  model.set_option('fused_small', 1)
   for x, y in zip(results[0][0], results[1][0]):
     assert numpy.array_equal(x, y)
   assert results[0][1][1] == results[1][1][1] and numpy.array_equal(results[0][1][0], results[1][1][0])
   assert numpy.array_equal(results[0][0][0], results[0][0][6])  # host path and device path agree as well
+
+
+@pytest.mark.parametrize('tag,size_a,cl_k', [('ex2-ferromagnetic-chain', 2, 3), ('ex2-ferromagnetic-chain', 2, 7),
+                                             ('ex1-radioactive-decay', 2, 1), ('ex3-copolymerization', 4, 6),
+                                             ('ex5-msrtf-machine', 5, 5), ('ex4-chemical-turing', 9, 5),
+                                             ('ex4var2-chemical-turing', 10, 4)])
+def test_single_launch_right_hand_side_is_bit_identical(mt, device, oracle, tag, size_a, cl_k):
+  """Small problems evaluate the whole right-hand side in one launch (one thread block or one
+  cluster of thread blocks running the phases of the separate kernels over virtual blocks,
+  engine.cu fused_rhs_kernel).  Every cluster size gives the bits of the multi-launch path - for
+  dy/dt, for the node weights, through the host entry point and through the stepper, whose stage
+  update rides on the product phase - and dy/dt matches the oracle."""
+  import torch
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  model = device.DeviceModel(tag, cl_k)
+  assert model.info['launches_per_rhs'] == 1, model.info
+  tables = [configs.markov_table(size_a, cl_k, 7), configs.dirichlet_product_table(size_a, cl_k, 8)]
+  f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
+  p0 = tables[0]
+  kw = dict(tag=tag, size_a=size_a, cl_k=cl_k, p0=p0, ts=numpy.linspace(0, 2.0, 5), rtol=1e-9, atol=1e-11, want_stats=True)
+  model.set_option('fused_small', 0)
+  assert model.info['launches_per_rhs'] > 1
+  want = [model.rhs(torch.from_numpy(p).cuda()).cpu().numpy() for p in tables]
+  want_w = model.node_weights()
+  want_run = mt.ode_integrate_device(**kw)
+  for p, w in zip(tables, want):
+    assert_rhs_close(w, oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED), gross_flux(oracle, tag, cl_k, p))
+  model.set_option('fused_small', 1)
+  for cluster in (1, 2, 8, 16):
+    model.set_option('fused_cluster', cluster)
+    for p, w in zip(tables, want):
+      assert numpy.array_equal(model.rhs(torch.from_numpy(p).cuda()).cpu().numpy(), w), cluster
+      assert numpy.array_equal(f(p, 0.0), w), cluster
+    assert numpy.array_equal(model.node_weights(), want_w), cluster
+    run = mt.ode_integrate_device(**kw)
+    assert run[1] == want_run[1] and numpy.array_equal(run[0], want_run[0]), cluster
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
 
 
 def test_device_rhs_equals_host_rhs(mt, device):
@@ -277,6 +316,7 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
   monkeypatch.setenv('TAPES_RATIO_LEFT', '1')  # the left table is an option (it does not pay at the bench size)
   model = device.DeviceModel(tag, cl_k)
   assert model.info['plane_groups'] > 0 and model.info['ratio_tables'] == 2, model.info
+  model.set_option('fused_small', 0)  # the smaller cases here would otherwise take the single-launch kernel
   with_planes, weights = model.rhs(p).cpu().numpy(), model.node_weights()
   assert_rhs_close(with_planes, oracle.compute_dy_dt(tag, cl_k, p_host, mode=oracle.MERGED), gross_flux(oracle, tag, cl_k, p_host))
   launches = model.info['launches_per_rhs']
@@ -290,6 +330,7 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
   monkeypatch.delenv('TAPES_RATIO_LEFT')  # the default: right table only
   model = device.DeviceModel(tag, cl_k)
+  model.set_option('fused_small', 0)
   assert model.info['ratio_tables'] == 1
   assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
   assert numpy.array_equal(model.node_weights(), weights)
