@@ -22,7 +22,7 @@ SYMBOLS = (
     'tapes_check_table', 'tapes_model_part', 'tapes_rule_parts', 'tapes_register_program',
     'tapes_mc_create', 'tapes_mc_destroy', 'tapes_mc_run', 'tapes_mc_window_counts', 'tapes_mc_fetch',
     'tapes_mc_sample_ring', 'tapes_program_tree', 'tapes_observe_sequences', 'tapes_dop853_observe_sequences',
-    'tapes_markov_entropy', 'tapes_dop853_entropy', 'tapes_host_alloc', 'tapes_host_free',
+    'tapes_markov_entropy', 'tapes_dop853_entropy', 'tapes_host_alloc', 'tapes_host_free', 'tapes_mc_ferromagnet_chains',
 )
 
 _lib = None
@@ -146,6 +146,8 @@ def load():
   lib.tapes_markov_entropy.argtypes = [vp, vp, vp]
   lib.tapes_dop853_entropy.restype = i32
   lib.tapes_dop853_entropy.argtypes = [vp, i32, vp]
+  lib.tapes_mc_ferromagnet_chains.restype = i32
+  lib.tapes_mc_ferromagnet_chains.argtypes = [i64, i64, i64, i64, vp, vp, vp, vp, vp]
   lib.tapes_host_alloc.restype = vp
   lib.tapes_host_alloc.argtypes = [i64]
   lib.tapes_host_free.restype = i32

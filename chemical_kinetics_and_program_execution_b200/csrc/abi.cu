@@ -850,6 +850,20 @@ int tapes_mc_sample_ring(int64_t alphabet, int64_t cl_k, const double* table, in
   }
 }
 
+int tapes_mc_ferromagnet_chains(int64_t n_trials, int64_t chain_length, int64_t n_steps, int64_t trials_per_step,
+                                const uint8_t* chain0, const int32_t* sites, const double* uniforms, const double* accept,
+                                double* counts) {
+  if (!chain0 || !accept || !counts || (n_steps > 1 && (!sites || !uniforms))) { fail("mc_ferromagnet_chains: null argument"); return 1; }
+  if (!ensure_cuda()) return 1;
+  try {
+    tapes::mc_ferromagnet_chains(n_trials, chain_length, n_steps, trials_per_step, chain0, sites, uniforms, accept, counts);
+    return 0;
+  } catch (const std::exception& ex) {
+    fail(std::string("mc_ferromagnet_chains: ") + ex.what());
+    return 1;
+  }
+}
+
 int64_t tapes_program_tree(const char* tag, int64_t* sizes3, int32_t* kind, int32_t* a, int32_t* b, int32_t* c,
                            int32_t* first_child, int32_t* first_weight, int32_t* child, double* weight) {
   try {

@@ -1628,12 +1628,16 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.ratio_left = dkeep<double>(m, m.n_states);
   if (const char* g = std::getenv("TAPES_PLANE_KERNEL")) m.plane_kernel = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-  // small problems: one launch per right-hand side.  Work = what the phases touch; one block up to
-  // 2^15, a cluster of 8 (the portable size) up to 2^19, of 16 up to 2^22 (measured crossover with the
-  // multi-launch path: profiles/r02_*small*).
+  // Tiny problems: one launch per right-hand side by ONE thread block.  Work = what the phases touch.
+  // Measured on B200 (profiles/r02_e_time_small.log, device-resident, us per right-hand side, multi-launch
+  // graph replay -> single launch): ex2 k=3 (work 136) 16.4 -> 11.2, ex2 k=7 (3.7e3) 34.8 -> 22.5; ex3 k=6
+  // (4.1e4) 38.3 -> 36.1 with a cluster of 4; ex5 (1.1e6) 79.4 -> 112 and ex4 (3.0e6) 71.7 -> 100 with a
+  // cluster of 16: beyond a few thousand nodes 16 SMs lose against the whole GPU even with ~4 us of launch
+  // latency per kernel, so only the tiny ones take the single launch by default (clusters stay
+  // available through "fused_cluster" / TAPES_FUSED_CLUSTER).
   {
     const uint64_t work = m.n_nodes + m.nnz + m.n_states;
-    m.fused_cluster = work <= (1ull << 15) ? 1 : (work <= (1ull << 19) ? 8 : (work <= (1ull << 22) ? 16 : 0));
+    m.fused_cluster = work <= (1ull << 13) ? 1 : 0;
     if (m.flux_format != 1 || m.n_rules == 0 || m.k < 1) m.fused_cluster = 0;
     if (const char* e = std::getenv("TAPES_FUSED_CLUSTER")) {
       const int v = std::atoi(e);

@@ -15,6 +15,7 @@
 // 2 + i = the i-th choice of the event.
 #include "montecarlo.h"
 
+#include <algorithm>
 #include <stdexcept>
 #include <vector>
 
@@ -253,6 +254,102 @@ void mc_sample_ring(int alphabet, int cl_k, const double* table, uint64_t n_site
     h_tape[pos] = (uint8_t)sym;
     context = (context * (uint64_t)alphabet + (uint64_t)sym) % m;
   }
+}
+
+namespace {
+
+constexpr int kChainThreads = 512;
+
+// One trial per block.  Shared memory: previous and current chain (bytes, padded to words) and six
+// counters.  Per time step: the trials of the step read `prev` and xor into `cur`; islands of `cur`
+// are counted from their first site; `cur` becomes `prev`.
+__global__ void __launch_bounds__(kChainThreads) ferromagnet_chain_kernel(int64_t chain_length, int64_t n_steps,
+                                                                          int64_t trials_per_step,
+                                                                          const uint8_t* __restrict__ chain0,
+                                                                          const int32_t* __restrict__ sites,
+                                                                          const double* __restrict__ uniforms,
+                                                                          const double* __restrict__ accept,
+                                                                          double* __restrict__ counts) {
+  extern __shared__ unsigned int smem[];
+  const int64_t words = (chain_length + 3) / 4;
+  unsigned int* prev_w = smem;
+  unsigned int* cur_w = smem + words;
+  unsigned int* tally = smem + 2 * words;  // [6]
+  uint8_t* prev = (uint8_t*)prev_w;
+  uint8_t* cur = (uint8_t*)cur_w;
+  const int64_t trial = blockIdx.x;
+  const int64_t n = chain_length;
+  double acc[6];
+  for (int i = 0; i < 6; ++i) acc[i] = accept[i];
+  for (int64_t w = threadIdx.x; w < words; w += blockDim.x) { prev_w[w] = 0; cur_w[w] = 0; }
+  __syncthreads();
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { prev[i] = chain0[trial * n + i]; cur[i] = prev[i]; }
+  __syncthreads();
+  for (int64_t step = 0; step < n_steps; ++step) {
+    if (step > 0) {
+      const int32_t* my_sites = sites + (trial * (n_steps - 1) + (step - 1)) * trials_per_step;
+      const double* my_u = uniforms + (trial * (n_steps - 1) + (step - 1)) * trials_per_step;
+      for (int64_t t = threadIdx.x; t < trials_per_step; t += blockDim.x) {
+        const int64_t i = my_sites[t];
+        const int64_t left = i == 0 ? n - 1 : i - 1, right = i + 1 == n ? 0 : i + 1;
+        const int mid = prev[i];
+        const int equal = (prev[left] == mid) + (prev[right] == mid);
+        if (my_u[t] < acc[2 * equal + mid]) atomicXor(&cur_w[i >> 2], 1u << (8 * (i & 3)));
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x < 6) tally[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      if (cur[i] && !cur[i == 0 ? n - 1 : i - 1]) {  // first site of an island
+        int len = 1;
+        int64_t at = i + 1 == n ? 0 : i + 1;
+        while (len < 6 && cur[at]) { ++len; at = at + 1 == n ? 0 : at + 1; }
+        if (len < 6) atomicAdd(&tally[len], 1u);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) counts[(trial * n_steps + step) * 6 + threadIdx.x] = threadIdx.x ? (double)tally[threadIdx.x] : 0.0;
+    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) prev_w[w] = cur_w[w];
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+void mc_ferromagnet_chains(int64_t n_trials, int64_t chain_length, int64_t n_steps, int64_t trials_per_step,
+                           const uint8_t* chain0, const int32_t* sites, const double* uniforms, const double* accept,
+                           double* counts) {
+  if (n_trials < 1 || chain_length < 3 || n_steps < 1 || trials_per_step < 1) throw std::runtime_error("bad sizes");
+  const size_t smem = (size_t)(2 * ((chain_length + 3) / 4) + 8) * sizeof(unsigned int);
+  if (smem > 200 * 1024) throw std::runtime_error("the chain must fit shared memory twice (at most ~100 000 sites)");
+  for (int64_t i = 0; i < n_trials * (n_steps - 1) * trials_per_step; ++i)
+    if (sites[i] < 0 || sites[i] >= chain_length) throw std::runtime_error("site outside the chain");
+  TAPES_CUDA_CHECK(cudaFuncSetAttribute(ferromagnet_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t n_draws = (size_t)(n_trials * (n_steps - 1) * trials_per_step);
+  uint8_t* d_chain = nullptr; int32_t* d_sites = nullptr; double* d_u = nullptr; double* d_acc = nullptr; double* d_counts = nullptr;
+  auto release = [&]() { cudaFree(d_chain); cudaFree(d_sites); cudaFree(d_u); cudaFree(d_acc); cudaFree(d_counts); };
+  try {
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&d_chain, (size_t)(n_trials * chain_length)));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&d_sites, std::max<size_t>(n_draws, 1) * 4));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&d_u, std::max<size_t>(n_draws, 1) * 8));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&d_acc, 6 * 8));
+    TAPES_CUDA_CHECK(cudaMalloc((void**)&d_counts, (size_t)(n_trials * n_steps * 6) * 8));
+    TAPES_CUDA_CHECK(cudaMemcpy(d_chain, chain0, (size_t)(n_trials * chain_length), cudaMemcpyHostToDevice));
+    if (n_draws) {
+      TAPES_CUDA_CHECK(cudaMemcpy(d_sites, sites, n_draws * 4, cudaMemcpyHostToDevice));
+      TAPES_CUDA_CHECK(cudaMemcpy(d_u, uniforms, n_draws * 8, cudaMemcpyHostToDevice));
+    }
+    TAPES_CUDA_CHECK(cudaMemcpy(d_acc, accept, 6 * 8, cudaMemcpyHostToDevice));
+    ferromagnet_chain_kernel<<<(unsigned)n_trials, kChainThreads, smem>>>(chain_length, n_steps, trials_per_step, d_chain, d_sites,
+                                                                         d_u, d_acc, d_counts);
+    TAPES_CUDA_CHECK(cudaGetLastError());
+    TAPES_CUDA_CHECK(cudaMemcpy(counts, d_counts, (size_t)(n_trials * n_steps * 6) * 8, cudaMemcpyDeviceToHost));
+  } catch (...) {
+    release();
+    throw;
+  }
+  release();
 }
 
 }  // namespace tapes

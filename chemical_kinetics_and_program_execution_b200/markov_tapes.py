@@ -12,7 +12,8 @@ Differences, all documented in INTEGRATION.md:
   * a failed library call raises RuntimeError (the reference drops into a Scheme REPL,
     framework/tapes_py_interface.scm:42-44);
   * additions: `ode_integrate_device`, `sequence_observable`, `model_stats`, `check_table`,
-    `register_rule_set`, `register_program`, `monte_carlo`; device-resident dy/dt lives in device.py.
+    `register_rule_set`, `register_program`, `monte_carlo`, `ferromagnet_monte_carlo`; device-resident
+    dy/dt lives in device.py.
 """
 
 import atexit
@@ -438,6 +439,60 @@ def monte_carlo(*, tag, size_a, cl_k, ts, p0=None, tape0=None, n_sites=1 << 20, 
   finally:
     u_lib.tapes_mc_destroy(mc)
   return out
+
+
+def ferromagnet_mc_inputs(*, n_trials, chain_length, n_steps, sites_per_pair, trials_per_step, beta=1.0, J=1.0, h=-0.25,
+                          seed_offset=1000, first_trial=0):
+  """Everything random or parameter-dependent of the reference's ferromagnet Monte Carlo
+  (examples/ex2_ferromagnet_mc.py), drawn exactly as the script draws it: per trial
+  numpy.random.RandomState(seed = trial + seed_offset) (172), the initial chain from one uniform
+  vector (175-176), then per time step `randint` for the sites and `uniform` for the acceptance
+  tests (93-94).  Returns (chain0 [T, N] uint8, sites [T, S-1, M] int32, uniforms [T, S-1, M] float64,
+  accept [3, 2]): accept[c, s] is the flip probability of a spin s with c equal neighbours (101-113)."""
+  chain0 = numpy.zeros((n_trials, chain_length), dtype=numpy.uint8)
+  sites = numpy.zeros((n_trials, max(n_steps - 1, 0), trials_per_step), dtype=numpy.int32)
+  uniforms = numpy.zeros((n_trials, max(n_steps - 1, 0), trials_per_step), dtype=numpy.float64)
+  for t in range(n_trials):
+    rng = numpy.random.RandomState(seed=first_trial + t + seed_offset)
+    pair_positions = rng.uniform(0, 1, size=chain_length) < 1 / sites_per_pair
+    chain0[t] = (pair_positions | numpy.roll(pair_positions, 1)).astype(numpy.uint8)
+    for nt in range(n_steps - 1):
+      sites[t, nt] = rng.randint(0, chain_length, size=trials_per_step)
+      uniforms[t, nt] = rng.uniform(0, 1, size=trials_per_step)
+  beta_j, beta_h = beta * J, beta * h
+  accept = numpy.zeros((3, 2), dtype=numpy.float64)
+  for equal in range(3):
+    energy_change = 2 * (equal - (2 - equal))  # neighbour energy after minus before, in units of J
+    for spin in (0, 1):
+      e_j = numpy.exp(-beta_j * (energy_change + 4))
+      e_h = numpy.exp(-2 * beta_h * spin) if h > 0 else numpy.exp(+2 * beta_h * (1 - spin))
+      accept[equal, spin] = e_j * e_h
+  return chain0, sites, uniforms, accept
+
+
+def ferromagnet_monte_carlo(*, n_trials=100, chain_length=50000, n_steps=4000, sites_per_pair=250, trials_per_step=None,
+                            beta=1.0, J=1.0, h=-0.25, seed_offset=1000, batch=10):
+  """The reference's Monte-Carlo experiment on the ferromagnetic chain
+  (examples/ex2_ferromagnet_mc.py:33-45, 167-191) on the GPU, with the script's defaults: returns
+  `chain_counts` [n_trials, n_steps, 6], the number of up-spin islands of length 1..5 at every time
+  step of every trial - the array the script stores as `chain_counts` in
+  ferromagnet_mc_chain_counts.npz.  The random numbers are the script's own (ferromagnet_mc_inputs),
+  so the counts are the script's counts, number for number.  One thread block per trial, chain in
+  shared memory (csrc/montecarlo.cu); trials go to the device `batch` at a time."""
+  if trials_per_step is None:
+    trials_per_step = chain_length // 100
+  counts = numpy.zeros((n_trials, n_steps, 6), dtype=numpy.float64)
+  for first in range(0, n_trials, batch):
+    n = min(batch, n_trials - first)
+    chain0, sites, uniforms, accept = ferromagnet_mc_inputs(
+        n_trials=n, chain_length=chain_length, n_steps=n_steps, sites_per_pair=sites_per_pair,
+        trials_per_step=trials_per_step, beta=beta, J=J, h=h, seed_offset=seed_offset, first_trial=first)
+    part = numpy.zeros((n, n_steps, 6), dtype=numpy.float64)
+    rc = u_lib.tapes_mc_ferromagnet_chains(n, chain_length, n_steps, trials_per_step, chain0.ctypes.data, sites.ctypes.data,
+                                           uniforms.ctypes.data, accept.ctypes.data, part.ctypes.data)
+    _lib.check(rc == 0, 'tapes_mc_ferromagnet_chains')
+    counts[first:first + n] = part
+  return counts
 
 
 def _run_validation():

@@ -271,6 +271,20 @@ int tapes_mc_fetch(void* mc, uint8_t* tape);
 int tapes_mc_sample_ring(int64_t alphabet, int64_t cl_k, const double* table, int64_t n_sites, uint64_t seed,
                          uint8_t* tape);
 
+/* The reference's own Monte Carlo of the ferromagnetic chain (examples/ex2_ferromagnet_mc.py:46-122
+ * `simulate`, 134-163 `island_length_stats`, driver loop 169-191), all trials at once, one thread block
+ * per trial with the chain in shared memory.  At every time step trials_per_step sites are looked at in
+ * the state of the previous step and flipped in the new one when their uniform number is below
+ * accept[equal neighbours][own spin]; two flips of a site within a step cancel, as in the reference.
+ * HOST arrays: chain0 [n_trials][chain_length] of 0 / 1; sites (int32) and uniforms (double)
+ * [n_trials][n_steps - 1][trials_per_step] - the numbers the reference draws from
+ * numpy.random.RandomState(seed) at ex2_ferromagnet_mc.py:93-94; accept [3][2]; counts
+ * [n_trials][n_steps][6] receives the numbers of up-spin islands of length 1..5 (entry 0 stays 0), step 0
+ * being the initial chain - the layout of the reference's ferromagnet_mc_chain_counts.npz. */
+int tapes_mc_ferromagnet_chains(int64_t n_trials, int64_t chain_length, int64_t n_steps, int64_t trials_per_step,
+                                const uint8_t* chain0, const int32_t* sites, const double* uniforms, const double* accept,
+                                double* counts);
+
 /* Host-only: the decision tree of the body registered under `tag` in the array form of
  * tapes_register_program (any problem: compiled, rewrite rules, or registered as a tree).  Call with
  * kind == NULL to get the lengths in sizes3 = {nodes, children, weights}.  Returns the node count. */

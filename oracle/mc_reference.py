@@ -99,3 +99,34 @@ def sample_ring(p, size_a, k, N, rng):
     row = cond[tuple(tape[n - k + 1:n])]
     tape[n] = min(numpy.searchsorted(numpy.cumsum(row), u[n]), size_a - 1)
   return tape
+
+
+def ferromagnet_chain_counts(chain0, sites, uniforms, accept):
+  """NumPy restatement of the reference's ferromagnet Monte Carlo for given random numbers
+  (examples/ex2_ferromagnet_mc.py:46-122 `simulate`, 134-163 `island_length_stats`, 182-189): the
+  checker of tapes_mc_ferromagnet_chains.  chain0 [T, N], sites / uniforms [T, S-1, M], accept [3, 2];
+  returns counts [T, S, 6].  The trials of a time step all read the state of the previous step and
+  xor into the new one (ex2_ferromagnet_mc.py:95-121: `result[nt-1, stride3]`, `result[nt, ...] ^= 1`)."""
+  chain0 = numpy.asarray(chain0).astype(numpy.int64)
+  n_trials, n = chain0.shape
+  n_steps = sites.shape[1] + 1
+  counts = numpy.zeros((n_trials, n_steps, 6))
+  for t in range(n_trials):
+    cur = chain0[t].copy()
+    for step in range(n_steps):
+      if step > 0:
+        prev = cur.copy()
+        i = numpy.asarray(sites[t, step - 1], dtype=numpy.int64)
+        mid = prev[i]
+        equal = (prev[(i - 1) % n] == mid).astype(numpy.int64) + (prev[(i + 1) % n] == mid)
+        flips = uniforms[t, step - 1] < accept[equal, mid]
+        numpy.bitwise_xor.at(cur, i[flips], 1)
+      starts = numpy.nonzero((cur == 1) & (numpy.roll(cur, 1) == 0))[0]
+      length = numpy.ones(starts.size, dtype=numpy.int64)
+      alive = numpy.ones(starts.size, dtype=bool)
+      for d in range(1, 6):
+        alive &= cur[(starts + d) % n] == 1
+        length += alive
+      for c_len in range(1, 6):
+        counts[t, step, c_len] = numpy.count_nonzero(length == c_len)
+  return counts

@@ -12,7 +12,10 @@ box uses the committed files.
    observables of examples/ex3_copolymerization.py:112-118 at 11 output times, the number of
    right-hand sides, and the end state (sparse).
 
-Usage: python tests/golden/make_golden_round2.py
+3. ex2_mc_chain_counts.npz: the island counts of the reference's ferromagnet Monte Carlo
+   (examples/ex2_ferromagnet_mc.py) on a small chain, produced by the script's own functions.
+
+Usage: python tests/golden/make_golden_round2.py [--mc-only]
 """
 
 import importlib.util
@@ -65,7 +68,43 @@ def make_ex3_long_chain():
   print(f'wrote ex3_k12_trajectory.npz: nfev={sol.nfev} {time.time() - t0:.1f}s non-zeros at t=10: {idx.size}')
 
 
+
+
+# ---- ferromagnet Monte Carlo ----------------------------------------
+MC_SMALL = dict(n_trials=3, chain_length=2000, n_steps=300, sites_per_pair=40, trials_per_step=20, seed_offset=1000,
+                beta=1.0, J=1.0, h=-0.25)
+
+
+def make_ferromagnet_mc():
+  """ex2_mc_chain_counts.npz: examples/ex2_ferromagnet_mc.py's own `simulate` (46-122) and
+  `island_length_stats` (134-163), extracted from the script (which cannot be imported: it runs the
+  full experiment and plots at import time) and run with its driver loop (169-191) on a small chain."""
+  import ast
+  path = os.path.join(REF, 'examples', 'ex2_ferromagnet_mc.py')
+  tree = ast.parse(open(path).read())
+  ns = dict(numpy=numpy)
+  for node in tree.body:
+    if isinstance(node, ast.FunctionDef) and node.name in ('simulate', 'island_length_stats'):
+      exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), ns)
+  c = MC_SMALL
+  counts = numpy.zeros([c['n_trials'], c['n_steps'], 6])
+  for n_trial in range(c['n_trials']):
+    rng = numpy.random.RandomState(seed=n_trial + c['seed_offset'])
+    pair_positions = rng.uniform(0, 1, size=c['chain_length']) < 1 / c['sites_per_pair']
+    chain0 = (pair_positions | numpy.roll(pair_positions, 1)).astype(numpy.int8)
+    history = ns['simulate'](chain0, c['n_steps'], num_trials_per_time_step=c['trials_per_step'], J=c['J'], h=c['h'],
+                             beta=c['beta'], rng=rng)
+    for n_time, chain in enumerate(history):
+      stats = ns['island_length_stats'](chain)
+      for c_len in range(1, 6):
+        counts[n_trial, n_time, c_len] = stats.get(c_len, 0)
+  numpy.savez_compressed(os.path.join(HERE, 'ex2_mc_chain_counts.npz'), chain_counts=counts)
+  print('wrote ex2_mc_chain_counts.npz', counts.shape, counts.sum(axis=(0, 1)))
+
+
 if __name__ == '__main__':
-  oracle.build()
-  make_ex2_analytic()
-  make_ex3_long_chain()
+  if '--mc-only' not in sys.argv:
+    oracle.build()
+    make_ex2_analytic()
+    make_ex3_long_chain()
+  make_ferromagnet_mc()

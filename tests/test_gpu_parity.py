@@ -236,7 +236,7 @@ def test_single_launch_right_hand_side_is_bit_identical(mt, device, oracle, tag,
   import torch
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
   model = device.DeviceModel(tag, cl_k)
-  assert model.info['launches_per_rhs'] == 1, model.info
+  assert (model.info['launches_per_rhs'] == 1) == (model.info['n_nodes'] + model.info['nnz'] + size_a ** cl_k <= 8192)
   tables = [configs.markov_table(size_a, cl_k, 7), configs.dirichlet_product_table(size_a, cl_k, 8)]
   f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
   p0 = tables[0]

@@ -102,3 +102,60 @@ def test_cuda_simulator_follows_the_master_equation():
     assert abs(sim[0] - p0).max() < 5 / numpy.sqrt(n)
     assert abs(sim - ode).max() < tol / numpy.sqrt(n), (tag, abs(sim - ode).max())
     assert abs(ode[-1] - ode[0]).max() > moved / numpy.sqrt(n)  # the comparison is not vacuous
+
+
+def test_ferromagnet_chain_restatement_reproduces_the_reference_script():
+  """the reference's own ferromagnet Monte Carlo
+  (examples/ex2_ferromagnet_mc.py).  Golden: island counts produced by the script's `simulate` and
+  `island_length_stats` on a small chain (tests/golden/make_golden_round2.py).  The inputs drawn
+  like the script draws them plus the NumPy restatement of its update rule give the same counts,
+  number for number - which pins the checker of the CUDA kernel."""
+  import os
+  from conftest import GOLDEN
+  from make_golden_round2 import MC_SMALL as c
+  from chemical_kinetics_and_program_execution_b200 import configs  # noqa: F401  (package import without the library)
+  import importlib.util
+  import sys
+  # markov_tapes needs a GPU to import; the input generator is plain NumPy, so load the function alone
+  inputs = _load_function('ferromagnet_mc_inputs')
+  gold = numpy.load(os.path.join(GOLDEN, 'ex2_mc_chain_counts.npz'))['chain_counts']
+  chain0, sites, uniforms, accept = inputs(n_trials=c['n_trials'], chain_length=c['chain_length'], n_steps=c['n_steps'],
+                                           sites_per_pair=c['sites_per_pair'], trials_per_step=c['trials_per_step'],
+                                           beta=c['beta'], J=c['J'], h=c['h'], seed_offset=c['seed_offset'])
+  got = mc_reference.ferromagnet_chain_counts(chain0, sites, uniforms, accept)
+  assert got.shape == gold.shape and numpy.array_equal(got, gold)
+  assert gold[:, :, 1:].sum() > 1000  # the golden run is not trivial
+
+
+def _load_function(name):
+  """A top-level function of markov_tapes.py without importing the module (which initialises CUDA)."""
+  import ast
+  import os
+  from conftest import ROOT
+  path = os.path.join(ROOT, 'chemical_kinetics_and_program_execution_b200', 'markov_tapes.py')
+  tree = ast.parse(open(path).read())
+  ns = dict(numpy=numpy)
+  for node in tree.body:
+    if isinstance(node, ast.FunctionDef) and node.name == name:
+      exec(compile(ast.Module(body=[node], type_ignores=[]), path, 'exec'), ns)
+  return ns[name]
+
+
+@pytest.mark.gpu
+def test_cuda_ferromagnet_chains_reproduce_the_reference_script():
+  """The CUDA kernel against the reference script's own counts (golden) and, on a chain of the
+  script's size, against the NumPy restatement."""
+  import os
+  from conftest import GOLDEN
+  from make_golden_round2 import MC_SMALL as c
+  from chemical_kinetics_and_program_execution_b200 import markov_tapes as mt
+  gold = numpy.load(os.path.join(GOLDEN, 'ex2_mc_chain_counts.npz'))['chain_counts']
+  got = mt.ferromagnet_monte_carlo(n_trials=c['n_trials'], chain_length=c['chain_length'], n_steps=c['n_steps'],
+                                   sites_per_pair=c['sites_per_pair'], trials_per_step=c['trials_per_step'], beta=c['beta'],
+                                   J=c['J'], h=c['h'], seed_offset=c['seed_offset'], batch=2)
+  assert numpy.array_equal(got, gold)
+  # the script's chain length and trials per step (50 000 sites, 500 trials per step), fewer steps and trials
+  kw = dict(n_trials=2, chain_length=50000, n_steps=40, sites_per_pair=250, trials_per_step=500)
+  got = mt.ferromagnet_monte_carlo(**kw)
+  want = mc_reference.ferromagnet_chain_counts(*mt.ferromagnet_mc_inputs(**kw))
+  assert numpy.array_equal(got, want) and got[:, 0, 2].min() > 100  # pairs of up-spins to start with
