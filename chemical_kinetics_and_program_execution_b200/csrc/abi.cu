@@ -525,6 +525,7 @@ int tapes_model_set(void* model, const char* key, int64_t value) {
   if (std::strcmp(key, "interleave_seeds") == 0 && (value == 0 || value == 1)) field = &tapes::Model::interleave_seeds;
   if (std::strcmp(key, "ratio_table") == 0 && (value == 0 || value == 1)) field = &tapes::Model::ratio_table;
   if (std::strcmp(key, "plane_kernel") == 0 && (value == 0 || value == 1)) field = &tapes::Model::plane_kernel;
+  if (std::strcmp(key, "fuse_marginal_ratio") == 0 && (value == 0 || value == 1)) field = &tapes::Model::fuse_marginal_ratio;
   if (std::strcmp(key, "fused_small") == 0 && (value == 0 || value == 1)) field = &tapes::Model::fused_small;
   if (std::strcmp(key, "fused_cluster") == 0 && (value == 0 || value == 1 || value == 2 || value == 4 || value == 8 || value == 16)) {
     if (head.flux_format != 1 || head.n_rules == 0) { fail("fused_cluster: this model has no single-launch form"); return 1; }

@@ -531,6 +531,42 @@ __global__ void __launch_bounds__(kThreads) ratio_tables_kernel(const double* __
   }
 }
 
+// marg_{k-1} and the right-extension ratios in one pass over the table: a block stages 256 rows of A
+// entries in shared memory (coalesced), thread r adds up row r in the reference's order (j ascending
+// from an exact 0, tm.scm:378-384), then every entry is divided by its row's sum - the operands
+// ratio_tables_kernel reads from global memory - and stored coalesced.  Saves the second read of the
+// table (0.8 GB of 2.5 GB at 10^8 states).  Rows are padded to an odd number of doubles so that the
+// row sums run without bank conflicts.
+constexpr int kRowsPerBlock = kThreads;
+__global__ void __launch_bounds__(kThreads) marginal_ratio_kernel(const double* __restrict__ p, double* __restrict__ marg,
+                                                                  double* __restrict__ ratio, uint64_t n_rows, uint32_t A) {
+  extern __shared__ double tile[];  // [kRowsPerBlock * (A | 1)] entries, then [kRowsPerBlock] row sums
+  const uint32_t pitch = A | 1u;
+  double* sums = tile + (size_t)kRowsPerBlock * pitch;
+  const uint64_t row0 = (uint64_t)blockIdx.x * kRowsPerBlock;
+  const uint32_t rows = (uint32_t)min((uint64_t)kRowsPerBlock, n_rows - row0);
+  const uint32_t entries = rows * A;
+  const double* src = p + row0 * A;
+  for (uint32_t e = threadIdx.x; e < entries; e += kThreads) {
+    const uint32_t r = e / A;
+    tile[r * pitch + (e - r * A)] = src[e];
+  }
+  __syncthreads();
+  if (threadIdx.x < rows) {
+    const double* mine = tile + threadIdx.x * pitch;
+    double total = 0.0;
+    for (uint32_t j = 0; j < A; ++j) total = total + mine[j];
+    sums[threadIdx.x] = total;
+    marg[row0 + threadIdx.x] = total;
+  }
+  __syncthreads();
+  double* dst = ratio + row0 * A;
+  for (uint32_t e = threadIdx.x; e < entries; e += kThreads) {
+    const uint32_t r = e / A;
+    dst[e] = extension_ratio(tile[r * pitch + (e - r * A)], sums[r]);
+  }
+}
+
 // A group that owns its parents (fused right chain, engine.h Level): evaluates parent j = child
 // x_prev of previous-level group g_prev + j * g_step from that group's sum, stores it at its node
 // and returns the sum over j in ascending order.  DIRECT: the parents are the A values of the
@@ -1627,6 +1663,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (m.ratio_right && any_full_left && std::getenv("TAPES_RATIO_LEFT") && std::atoi(std::getenv("TAPES_RATIO_LEFT")) != 0)
     m.ratio_left = dkeep<double>(m, m.n_states);
   if (const char* g = std::getenv("TAPES_PLANE_KERNEL")) m.plane_kernel = std::atoi(g) != 0;
+  if (const char* g = std::getenv("TAPES_FUSE_MARGINAL_RATIO")) m.fuse_marginal_ratio = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   // Tiny problems: one launch per right-hand side by ONE thread block.  Work = what the phases touch.
   // Measured on B200 (profiles/r02_e_time_small.log, device-resident, us per right-hand side, multi-launch
@@ -1668,16 +1705,24 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   // marginal tables, longest first
   const int top = marginal_tail_top(m);
   const bool use_ratio = m.ratio_table && m.ratio_right && m.k >= 2;
+  // the longest marginal table and the right-extension ratios come from one pass over p when both
+  // are wanted and a tile of 256 rows fits shared memory
+  const size_t tile_bytes = ((size_t)kRowsPerBlock * (c.A | 1u) + kRowsPerBlock) * sizeof(double);
+  const bool one_pass = use_ratio && !m.ratio_left && m.fuse_marginal_ratio && m.k - 1 > top && tile_bytes <= 48 * 1024;
   for (int L = m.k - 1; L > top; --L) {
     const double* src = (L + 1 == m.k) ? d_p : m.marg + m.marg_off[L + 1];
-    marginal_kernel<<<grid_for(m.pow_a[L], kThreads), kThreads, 0, st>>>(src, m.marg + m.marg_off[L], m.pow_a[L], c.A);
+    if (one_pass && L == m.k - 1)
+      marginal_ratio_kernel<<<grid_for(m.pow_a[L], kRowsPerBlock), kThreads, tile_bytes, st>>>(
+          d_p, m.marg + m.marg_off[L], m.ratio_right, m.pow_a[L], c.A);
+    else
+      marginal_kernel<<<grid_for(m.pow_a[L], kThreads), kThreads, 0, st>>>(src, m.marg + m.marg_off[L], m.pow_a[L], c.A);
   }
   if (top >= 0)
     marginal_tail_kernel<<<1, 1024, 0, st>>>(d_p, m.marg, m.d_marg_off, m.k, top, c.A);
   if (m.n_rules)
     rule_weight_kernel<<<grid_for(m.n_rules, 128), 128, 0, st>>>(t, m.n_rules, m.rule_ptr, m.step_kind, m.step_len,
                                                                 m.step_long, m.step_short, m.step_prob, m.rule_w);
-  if (use_ratio)  // writing the ratios from the marginal kernel (which has the operands at hand) measured slower: strided stores
+  if (use_ratio && !one_pass)
     ratio_tables_kernel<<<grid_for(m.n_states, kThreads * kRatioBatch), kThreads, 0, st>>>(
         d_p, m.marg + m.marg_off[m.k - 1], m.ratio_right, m.ratio_left, m.n_states, c.A, c.M);
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
@@ -1904,7 +1949,12 @@ int64_t rhs_launch_count(const Model& m) {
   launches += (m.k - 1 - top);          // one kernel per long marginal table
   if (top >= 0) launches += 1;          // tail tables
   if (m.n_rules) launches += 1;         // leaf-world probabilities
-  if (m.ratio_table && m.ratio_right && m.k >= 2) launches += 1;  // right-extension ratios
+  {
+    const size_t tile_bytes = ((size_t)kRowsPerBlock * ((size_t)m.A | 1u) + kRowsPerBlock) * sizeof(double);
+    const bool one_pass = m.ratio_table && m.ratio_right && m.k >= 2 && !m.ratio_left && m.fuse_marginal_ratio &&
+                          m.k - 1 > top && tile_bytes <= 48 * 1024;
+    if (m.ratio_table && m.ratio_right && m.k >= 2 && !one_pass) launches += 1;  // extension ratios in a pass of their own
+  }
   const bool use_ratio = m.ratio_table && m.ratio_right && m.k >= 2;
   for (const Level& lv : m.levels) {
     if (lv.n_roots) { launches += 1; continue; }

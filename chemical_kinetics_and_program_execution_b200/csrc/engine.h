@@ -186,6 +186,7 @@ struct Model {
   double* ratio_right = nullptr;   // [n_states] p[i] / max(p[i], marg_{k-1}[i / A]), 0 where p[i] == 0
   double* ratio_left = nullptr;    // [n_states] p[i] / max(p[i], marg_{k-1}[i % A^(k-1)]): left extensions / shifts to a full window
   int plane_kernel = 1;            // regular blocks of prefix groups go to plane_kernel (Level::plane_blocks)
+  int fuse_marginal_ratio = 1;     // marg_{k-1} and ratio_right from one pass over the table (marginal_ratio_kernel)
   // Small problems: the whole right-hand side in one launch by one thread block or one cluster of
   // thread blocks (engine.cu fused_rhs_kernel).  fused_cluster: 0 = not eligible, else blocks used.
   int fused_small = 1;

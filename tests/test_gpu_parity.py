@@ -290,7 +290,7 @@ def test_flux_row_ranges_and_gather_depths(mt, device):
   g = guard.cpu().numpy()
   assert (g[:40] == 7.0).all() and (g[50:] == 7.0).all() and numpy.array_equal(g[40:50], want[40:50])
   for key, values in (('flux_unroll', (2, 3, 4, 6, 8)), ('level_unroll', (1, 2, 4, 5, 8)), ('interleave_seeds', (0, 1)), ('ratio_table', (0, 1)),
-                      ('plane_kernel', (0, 1))):
+                      ('plane_kernel', (0, 1)), ('fuse_marginal_ratio', (0, 1))):
     keep = model.info.get(key, None)
     for v in values:
       model.set_option(key, v)
