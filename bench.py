@@ -726,6 +726,54 @@ def run_b200(args):
                    api='pinned host table -> 1 / N slice per rank (H2D) + all-gather over NVLink, step of all ranks '
                        'together, summed dy/dt -> pinned host on rank 0 (D2H); max over ranks')
 
+  # N > 1, weak run: the strong-scaling figure beside it.  The N = 1 problem (rank 0's 24 rules, which
+  # is also what every rank evaluates alone in the weak run, so its one-GPU time is rank_compute_ms) is
+  # dealt to the N ranks by term counts and evaluated with the same fused exchange.
+  strong_leg = None
+  if world > 1 and args.scaling == 'weak' and args.exchange == 'peer':
+    def measure_strong():
+      base = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)
+      part_tag = configs.synthetic_tag(args.size_a, args.rules_per_gpu, args.seed) + f'-part{rank}of{world}'
+      built = 1.0
+      try:
+        mt.register_rule_set(part_tag, args.size_a, parallel.split_rule_set(base, world, rank, args.size_a, args.cl_k))
+        part_model = dev.DeviceModel(part_tag, args.cl_k)
+      except Exception as ex:  # pylint: disable=broad-except
+        built = 0.0
+        print(f'rank {rank}: strong-scaling structure failed: {ex!r}', file=sys.stderr)
+      flag = torch.tensor([built], dtype=torch.float64, device=device)
+      dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # every rank reaches this, so nobody waits for a rank that failed
+      if float(flag.item()) == 0:
+        return dict(error='building a share of the rules failed on some rank (see stderr)')
+      ex_strong = parallel.PeerExchangeRhs(part_model, rounds=max(args.chunks, 1) if args.chunks <= 16 else 16)
+      for _ in range(3):
+        ex_strong.rhs_full(p_full)
+      torch.cuda.synchronize()
+      dist.barrier()
+      s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      s0.record()
+      for _ in range(10):
+        ex_strong.rhs_full(p_full)
+      s1.record()
+      torch.cuda.synchronize()
+      t = torch.tensor([s0.elapsed_time(s1) / 10], dtype=torch.float64, device=device)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      bad = torch.tensor([float(ex_strong.lib.tapes_peer_group_error(ex_strong.group))], dtype=torch.float64, device=device)
+      dist.all_reduce(bad, op=dist.ReduceOp.MAX)  # all ranks take the same way out
+      got = ex_strong.out[:n]
+      total, gross = float(got.sum().item()), float(got.abs().sum().item())
+      ex_strong.close()
+      mt.u_lib.tapes_release_model(part_tag.encode(), args.cl_k)
+      if float(bad.item()) != 0:
+        return dict(error='a cross-GPU wait timed out')
+      one_gpu = max(rank_ms)
+      return dict(ms_per_step=float(t.item()), one_gpu_ms=one_gpu, speedup=one_gpu / float(t.item()), n_gpus=world,
+                  rules=args.rules_per_gpu, sum_rel=abs(total) / max(gross, 1e-300),
+                  note='the N = 1 problem dealt to the N ranks (bench.py --scaling strong times the same thing as its own '
+                       'line); one_gpu_ms = this run\'s time of the same rules on one GPU')
+    from chemical_kinetics_and_program_execution_b200 import configs
+    strong_leg = _guarded(measure_strong)
+
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
     from oracle import oracle
@@ -778,7 +826,7 @@ def run_b200(args):
                 value_is='CSR-equivalent algorithmic bytes per second (a work rate; may exceed the HBM peak)',
                 value_dram_gbs=value_dram, dram_frac=(value_dram / peak) if value_dram else None,
                 structure=dict(nnz=nnz_total, forest_nodes=nodes_total, flux_terms=terms_total, exchange=exchange),
-                parity_check=parity,
+                parity_check=parity, strong_scaling=strong_leg,
                 clocks=clocks.summary(), e2e=e2e,
                 gpu_launches=(int(launches_total / world)
                               + (4 * max(args.chunks, 1) + 1 if world > 1 and args.exchange == 'peer' else 0)) * args.steps,

@@ -338,6 +338,50 @@ __global__ void group_sort_kernel(const uint64_t* __restrict__ ptr, uint64_t n_g
   }
 }
 
+// The same sort with the rows of a block staged in shared memory: 256 consecutive groups own one
+// contiguous stretch of `vals`, which is loaded and stored coalesced, and every thread sorts its row
+// in shared memory.  (One thread sorting a 100-byte row straight in global memory touches a different
+// sector on every step: group_sort_kernel took 19 % of the build's kernel time, profiles/r01_n_*.)
+// A block whose stretch does not fit the tile falls back to the global-memory sort of its rows.
+constexpr uint32_t kSortTileWords = 11264;  // 44 KB
+__global__ void __launch_bounds__(kThreads) group_sort_tile_kernel(const uint64_t* __restrict__ ptr, uint64_t n_groups,
+                                                                   uint32_t* __restrict__ vals, uint32_t* __restrict__ long_groups,
+                                                                   unsigned long long* __restrict__ n_long) {
+  __shared__ uint32_t tile[kSortTileWords];
+  const uint64_t g0 = (uint64_t)blockIdx.x * kThreads;
+  const uint64_t g = g0 + threadIdx.x;
+  const uint64_t g_end = min(g0 + (uint64_t)kThreads, n_groups);
+  const uint64_t base = ptr[g0], stop = ptr[g_end];
+  const bool staged = stop - base <= kSortTileWords;
+  uint64_t lo = 0, hi = 0;
+  if (g < n_groups) { lo = ptr[g]; hi = ptr[g + 1]; }
+  const bool is_long = hi - lo > kShortGroup;
+  if (is_long && long_groups) long_groups[atomicAdd(n_long, 1ull)] = (uint32_t)g;  // left to group_sort_long_kernel
+  if (staged) {
+    for (uint64_t i = base + threadIdx.x; i < stop; i += kThreads) tile[i - base] = vals[i];
+    __syncthreads();
+    if (!is_long) {
+      uint32_t* v = tile + (lo - base);
+      const uint32_t len = (uint32_t)(hi - lo);
+      for (uint32_t a = 1; a < len; ++a) {  // insertion sort
+        const uint32_t x = v[a];
+        uint32_t b = a;
+        while (b > 0 && v[b - 1] > x) { v[b] = v[b - 1]; --b; }
+        v[b] = x;
+      }
+    }
+    __syncthreads();
+    for (uint64_t i = base + threadIdx.x; i < stop; i += kThreads) vals[i] = tile[i - base];
+  } else if (g < n_groups && !is_long) {
+    for (uint64_t a = lo + 1; a < hi; ++a) {
+      const uint32_t x = vals[a];
+      uint64_t b = a;
+      while (b > lo && vals[b - 1] > x) { vals[b] = vals[b - 1]; --b; }
+      vals[b] = x;
+    }
+  }
+}
+
 // One block per long group: bitonic network in its all-ascending form (the first step of every
 // merge compares mirrored positions), so positions past the end act as +infinity without ever
 // being touched.
@@ -1205,7 +1249,10 @@ void sort_groups(const uint64_t* ptr, uint64_t n_groups, uint32_t* vals, cudaStr
   uint32_t* long_groups = dalloc<uint32_t>(n_groups, st);
   unsigned long long* n_long = dalloc<unsigned long long>(1, st);
   TAPES_CUDA_CHECK(cudaMemsetAsync(n_long, 0, 8, st));
-  group_sort_kernel<<<grid_for(n_groups, kThreads), kThreads, 0, st>>>(ptr, n_groups, vals, long_groups, n_long);
+  if (std::getenv("TAPES_SORT_IN_GLOBAL"))
+    group_sort_kernel<<<grid_for(n_groups, kThreads), kThreads, 0, st>>>(ptr, n_groups, vals, long_groups, n_long);
+  else
+    group_sort_tile_kernel<<<grid_for(n_groups, kThreads), kThreads, 0, st>>>(ptr, n_groups, vals, long_groups, n_long);
   unsigned long long h_long = 0;
   TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_long, n_long, 8, cudaMemcpyDeviceToHost, st));
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
