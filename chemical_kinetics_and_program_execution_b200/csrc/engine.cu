@@ -576,26 +576,56 @@ __global__ void __launch_bounds__(kThreads) ratio_tables_kernel(const double* __
 }
 
 // marg_{k-1} and the right-extension ratios in one pass over the table: a block stages 256 rows of A
-// entries in shared memory (coalesced), thread r adds up row r in the reference's order (j ascending
-// from an exact 0, tm.scm:378-384), then every entry is divided by its row's sum - the operands
+// entries in shared memory, thread r adds up row r in the reference's order (j ascending from an
+// exact 0, tm.scm:378-384), then every entry is divided by its row's sum - the operands
 // ratio_tables_kernel reads from global memory - and stored coalesced.  Saves the second read of the
-// table (0.8 GB of 2.5 GB at 10^8 states).  Rows are padded to an odd number of doubles so that the
-// row sums run without bank conflicts.
+// table (0.8 GB of 2.5 GB at 10^8 states).
+// BULK: the block's stretch of the table is one contiguous piece of global memory, which one thread
+// hands to the bulk-copy engine (cp.async.bulk, completion on an mbarrier) instead of 2560 per-thread
+// loads; it needs 16-byte alignment and a multiple of 16 bytes, which the host checks.  Otherwise the
+// threads load it, into rows padded to an odd pitch so that the row sums run without bank conflicts.
 constexpr int kRowsPerBlock = kThreads;
+template <bool BULK>
 __global__ void __launch_bounds__(kThreads) marginal_ratio_kernel(const double* __restrict__ p, double* __restrict__ marg,
                                                                   double* __restrict__ ratio, uint64_t n_rows, uint32_t A) {
-  extern __shared__ double tile[];  // [kRowsPerBlock * (A | 1)] entries, then [kRowsPerBlock] row sums
-  const uint32_t pitch = A | 1u;
-  double* sums = tile + (size_t)kRowsPerBlock * pitch;
+  extern __shared__ __align__(16) double tile[];  // [kRowsPerBlock * pitch] entries, then [kRowsPerBlock] row sums
+  __shared__ __align__(8) unsigned long long arrived;
+  const uint32_t pitch = BULK ? A : (A | 1u);
+  double* sums = tile + (size_t)kRowsPerBlock * (A | 1u);
   const uint64_t row0 = (uint64_t)blockIdx.x * kRowsPerBlock;
   const uint32_t rows = (uint32_t)min((uint64_t)kRowsPerBlock, n_rows - row0);
   const uint32_t entries = rows * A;
   const double* src = p + row0 * A;
-  for (uint32_t e = threadIdx.x; e < entries; e += kThreads) {
-    const uint32_t r = e / A;
-    tile[r * pitch + (e - r * A)] = src[e];
+  if (BULK) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&arrived);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(tile);
+    const uint32_t bytes = entries * (uint32_t)sizeof(double);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(src), "r"(bytes), "r"(bar)
+                   : "memory");
+    }
+    uint32_t done = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred ok;\n\tmbarrier.try_wait.parity.shared::cta.b64 ok, [%1], 0;\n\tselp.u32 %0, 1, 0, ok;\n\t}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+    }
+  } else {
+    for (uint32_t e = threadIdx.x; e < entries; e += kThreads) {
+      const uint32_t r = e / A;
+      tile[r * pitch + (e - r * A)] = src[e];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   if (threadIdx.x < rows) {
     const double* mine = tile + threadIdx.x * pitch;
     double total = 0.0;
@@ -1758,10 +1788,18 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   const bool one_pass = use_ratio && !m.ratio_left && m.fuse_marginal_ratio && m.k - 1 > top && tile_bytes <= 48 * 1024;
   for (int L = m.k - 1; L > top; --L) {
     const double* src = (L + 1 == m.k) ? d_p : m.marg + m.marg_off[L + 1];
-    if (one_pass && L == m.k - 1)
-      marginal_ratio_kernel<<<grid_for(m.pow_a[L], kRowsPerBlock), kThreads, tile_bytes, st>>>(
-          d_p, m.marg + m.marg_off[L], m.ratio_right, m.pow_a[L], c.A);
-    else
+    if (one_pass && L == m.k - 1) {
+      // bulk copies need 16-byte aligned pieces of a multiple of 16 bytes: every block's stretch starts
+      // at a multiple of 256 * A entries; the last block's length is rows * A entries
+      const uint64_t last_rows = m.pow_a[L] % kRowsPerBlock;
+      const bool bulk = ((uintptr_t)d_p % 16 == 0) && ((last_rows * c.A) % 2 == 0) && !std::getenv("TAPES_NO_BULK_COPY");
+      if (bulk)
+        marginal_ratio_kernel<true><<<grid_for(m.pow_a[L], kRowsPerBlock), kThreads, tile_bytes, st>>>(
+            d_p, m.marg + m.marg_off[L], m.ratio_right, m.pow_a[L], c.A);
+      else
+        marginal_ratio_kernel<false><<<grid_for(m.pow_a[L], kRowsPerBlock), kThreads, tile_bytes, st>>>(
+            d_p, m.marg + m.marg_off[L], m.ratio_right, m.pow_a[L], c.A);
+    } else
       marginal_kernel<<<grid_for(m.pow_a[L], kThreads), kThreads, 0, st>>>(src, m.marg + m.marg_off[L], m.pow_a[L], c.A);
   }
   if (top >= 0)
