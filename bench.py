@@ -768,7 +768,7 @@ def run_b200(args):
         return dict(error='a cross-GPU wait timed out')
       one_gpu = max(rank_ms)
       return dict(ms_per_step=float(t.item()), one_gpu_ms=one_gpu, speedup=one_gpu / float(t.item()), n_gpus=world,
-                  rules=args.rules_per_gpu, sum_rel=abs(total) / max(gross, 1e-300),
+                  rules=args.rules_per_gpu, sum_dy_dt=total, sum_abs_dy_dt=gross, sum_rel=abs(total) / max(gross, 1e-300),
                   note='the N = 1 problem dealt to the N ranks (bench.py --scaling strong times the same thing as its own '
                        'line); one_gpu_ms = this run\'s time of the same rules on one GPU')
     from chemical_kinetics_and_program_execution_b200 import configs
