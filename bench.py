@@ -112,8 +112,11 @@ def level_bytes(info):
   gathered = info['hash_inserts'] - info.get('owned_parents', 0)
   plane = info.get('plane_groups', 0)  # 32 bytes per block of 256 such groups instead of 16 per group
   per_group = 16.0 * (info['hash_unique'] - plane) + 32.0 * plane / 256
-  return (16.0 * children + 25.0 * info.get('left_parents', 0) + float(per_group) + 8.0 * gathered
-          + 16.0 * info.get('deferred_groups', 0))
+  groups, prefixes = info['hash_unique'], info['n_states'] // max(info['alphabet'], 1)
+  # every group leaves its sum (8 B); the next level reads the sums of the groups whose children it evaluates
+  # (8 B each); prefix_sums_kernel reads every group's number and sum and writes one sum per prefix
+  sums = 8.0 * groups + 8.0 * info.get('deferred_groups', 0) + 12.0 * groups + 16.0 * prefixes
+  return 16.0 * children + 25.0 * info.get('left_parents', 0) + float(per_group) + 8.0 * gathered + sums
 
 
 def flux_format_bytes(info, n):
@@ -123,7 +126,9 @@ def flux_format_bytes(info, n):
   result once.  Below the real traffic by what L2 misses of the second reads and by the padding of
   the columns, so `frac` computed from it is a lower bound of the share of the HBM roofline."""
   slices = info.get('n_slices', (n + 31) // 32)
-  return 8.0 * (slices + 1) + 4.0 * slices + 4.0 * info.get('slice_words', 0) + 8.0 * info['n_terms'] + 8.0 * n
+  # the outflow of right children: the row's ratio (8 B per state) and one sum per prefix
+  outflow = 8.0 * n + 8.0 * (n // max(info.get('alphabet', 1), 1)) if info.get('nnz_stored', info['nnz']) < info['nnz'] else 0.0
+  return 8.0 * (slices + 1) + 4.0 * slices + 4.0 * info.get('slice_words', 0) + 8.0 * info['n_terms'] + 8.0 * n + outflow
 
 
 def prepass_bytes(info, n, size_a):

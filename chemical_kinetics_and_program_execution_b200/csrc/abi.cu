@@ -478,12 +478,12 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   std::shared_ptr<tapes::Model> mp = resolve(model);
   if (!mp) return 0;
   const tapes::Model& head = *mp;
-  const int kFields = 34;
+  const int kFields = 35;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
                                      true, false, false, false, false, false, true, true, true, true,
                                      true, false, false, true, true, false, true, true, true, true,
-                                     true, false};
+                                     true, false, true};
   int64_t total[kFields] = {};
   for (size_t part = 0; part <= head.more.size(); ++part) {
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
@@ -498,7 +498,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                                 (int64_t)m.slices.column_slots, (int64_t)m.slices.min_run_lanes, (int64_t)m.level_unroll,
                                 m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
                                 m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved,
-                                m.stats.plane_groups, (int64_t)((m.ratio_right ? 1 : 0) + (m.ratio_left ? 1 : 0))};
+                                m.stats.plane_groups, (int64_t)((m.ratio_right ? 1 : 0) + (m.ratio_left ? 1 : 0)),
+                                (int64_t)m.nnz_stored};
     for (int i = 0; i < kFields; ++i) {
       if (part == 0) total[i] = v[i];
       else if (adds[i]) total[i] += v[i];
@@ -569,25 +570,13 @@ int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries) {
   if (!mp) return 1;
   tapes::Model& m = *mp;
   if (!m.more.empty()) { fail("export_csr: composite model (forest above the 31-bit node ids); export shares made with tapes_model_part instead"); return 1; }
-  cudaStreamSynchronize(m.stream);
-  uint32_t* d_entries = m.entries;
-  uint32_t* rebuilt = nullptr;
   try {
-    if (!d_entries && m.nnz) {  // only the sliced form is resident: expand it back
-      if (cudaMalloc((void**)&rebuilt, m.nnz * 4) != cudaSuccess) throw std::runtime_error("out of device memory");
-      tapes::expand_flux_slices(m, rebuilt, m.stream);
-      if (cudaStreamSynchronize(m.stream) != cudaSuccess) throw std::runtime_error("expansion failed");
-      d_entries = rebuilt;
-    }
-    if (cudaMemcpy(row_ptr, m.row_ptr, (m.n_states + 1) * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
-        (m.nnz && cudaMemcpy(entries, d_entries, m.nnz * 4, cudaMemcpyDeviceToHost) != cudaSuccess))
-      throw std::runtime_error("copy failed");
+    tapes::export_full_csr(m, row_ptr, entries);
   } catch (const std::exception& ex) {
-    if (rebuilt) cudaFree(rebuilt);
+    cudaGetLastError();
     fail(std::string("export_csr: ") + ex.what());
     return 1;
   }
-  if (rebuilt) cudaFree(rebuilt);
   return 0;
 }
 

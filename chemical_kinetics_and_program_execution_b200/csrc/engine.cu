@@ -27,6 +27,7 @@ constexpr uint8_t FL_TERM = 1;   // contributes a flux term (window is full)
 constexpr uint8_t FL_LEFT = 2;   // expands leftwards
 constexpr uint8_t FL_RIGHT = 4;  // hands its weight to the right chain
 constexpr uint32_t kNoRank = 0xffffffffu;
+const double* const kLinkLater = reinterpret_cast<const double*>(uintptr_t(8));  // Level::prev_total until the sums exist
 constexpr uint32_t kOutflowBit = 0x80000000u;
 constexpr int kThreads = 256;
 
@@ -145,7 +146,9 @@ __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c
       key = ((uint64_t)f.seed[i] << 32) | po;
     }
     lflag[i] = left;
-    tflag[i] = (fl & FL_TERM) ? 1u : 0u;
+    // flux edges stored for the node: a term has an outflow and an inflow edge, but the outflow of a right
+    // child is not stored per term - it leaves its row through the per-prefix sums (Model::out_ptr)
+    tflag[i] = (fl & FL_TERM) ? ((meta >> 6) == NODE_RIGHT ? 1u : 2u) : 0u;
   }
   // keys seen for the first time are compacted into the new frontier's group list as they are
   // inserted (block scan, one atomic per block); the list is put in canonical order afterwards
@@ -208,10 +211,10 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
       next.flags[ci] = nfl;
     }
   }
-  if (tflag[i]) {
-    const uint64_t e = 2 * trank[i];
-    edge_row[e] = io;     edge_val[e] = gid | kOutflowBit;   // -w at the original window
-    edge_row[e + 1] = ia; edge_val[e + 1] = gid;             // +w at the adjusted window
+  if (const uint32_t n_edges = tflag[i]) {
+    uint64_t e = trank[i];
+    if (n_edges == 2) { edge_row[e] = io; edge_val[e] = gid | kOutflowBit; ++e; }  // -w at the original window
+    edge_row[e] = ia; edge_val[e] = gid;                                           // +w at the adjusted window
   }
   const uint32_t slot = keyslot[i];
   if (slot != kNoRank) {
@@ -546,7 +549,6 @@ __device__ __forceinline__ double child_weight(double w_parent, double p_long, d
 __device__ __forceinline__ double extension_ratio(double p_long, double p_short) {
   return p_long == 0.0 ? 0.0 : p_long / fmax(p_long, p_short);
 }
-__device__ __forceinline__ double weight_from_ratio(double w_parent, double r) { return r > 0.0 ? w_parent * r : 0.0; }
 
 constexpr int kRatioBatch = 4;  // entries per thread: loads and divisions of a batch overlap
 // Both per-step ratio tables from one read of the table: right extensions divide by the marginal of
@@ -767,7 +769,6 @@ __device__ __forceinline__ void level_body(const Tables& t, const Consts& c, con
             for (int u = 0; u < U; ++u) total += v[u];  // ascending id order; + 0.0 leaves the sum as it is
           }
         }
-        if (deferred) lv.g_total[g] = total;
       } else {
         deferred = false;
         const uint64_t lo = lv.g_ptr[g], hi = lv.g_ptr[g + 1];
@@ -782,6 +783,7 @@ __device__ __forceinline__ void level_body(const Tables& t, const Consts& c, con
           for (int u = 0; u < U; ++u) total += v[u];
         }
       }
+      lv.g_total[g] = total;  // read by the next level when it owns this group's children, and by prefix_sums_kernel
       if (!deferred) {
         prefix = lv.g_prefix[g];
         if (!RATIO) p_short = table(t, c.k - 1)[prefix];
@@ -834,6 +836,26 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) level_kernel(Tables t, C
                                                          const double* __restrict__ ratio, const double* __restrict__ ratio_left) {
   level_body<U, UO, PROGRESSIONS, RATIO>(t, c, lv, left_blocks, warp_step_q, warp_step_r, wr, ww, ratio, ratio_left, blockIdx.x,
                                          threadIdx.x);
+}
+
+// out_sum[q] = sum of the sums of all prefix groups with prefix q, in ascending group number (fixed
+// order): the common factor of the outflow of every right child that leaves a row q * A + x
+// (tm.scm:1310-1318: child weight = sum * ratio; accumulate-dp/dt 1288: -w at the original window).
+__global__ void __launch_bounds__(kThreads) prefix_sums_kernel(const uint64_t* __restrict__ out_ptr, const uint32_t* __restrict__ out_ids,
+                                                               const double* __restrict__ totals, double* __restrict__ out_sum,
+                                                               uint64_t n_prefixes) {
+  const uint64_t q = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_prefixes) return;
+  const uint64_t lo = out_ptr[q], hi = out_ptr[q + 1];
+  double total = 0.0;
+  for (uint64_t e = lo; e < hi; e += 4) {
+    double v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = e + u < hi ? totals[out_ids[e + u]] : 0.0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) total += v[u];
+  }
+  out_sum[q] = total;
 }
 
 // One regular block of 256 prefix groups (engine.h Level::PlaneBlock): thread t evaluates group t of
@@ -900,10 +922,8 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
       }
     }
   }
-  if (deferred) {
-    lv.g_total[g] = total;
-    return;
-  }
+  lv.g_total[g] = total;  // read by the next level when it owns this group's children, and by prefix_sums_kernel
+  if (deferred) return;
   // the 32 * A children of the warp's 32 groups: contiguous in the weight vector, and in the table
   // wherever the prefixes are
   const uint32_t lane = tid & 31, warp_first = tid - lane;
@@ -1015,6 +1035,11 @@ struct FusedArgs {
   uint64_t n_states, n_slices;
   double* out;
   int fused_update;
+  const uint64_t* out_ptr;   // right-chain outflow (engine.h Model::out_ptr); out_sum null: none
+  const uint32_t* out_ids;
+  const double* g_total_all;
+  double* out_sum;
+  uint64_t n_prefixes;
 };
 
 constexpr int kFusedThreads = 1024;
@@ -1080,12 +1105,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
     }
     phase_barrier();
   }
+  // what leaves the rows through right children: one sum per prefix (prefix_sums_kernel)
+  if (a.out_sum) {
+    for (uint64_t q = gtid; q < a.n_prefixes; q += gthreads) {
+      double total = 0.0;
+      for (uint64_t e = a.out_ptr[q]; e < a.out_ptr[q + 1]; ++e) total += a.g_total_all[a.out_ids[e]];
+      a.out_sum[q] = total;
+    }
+    phase_barrier();
+  }
   // the product, one slice of 32 states per warp
   const unsigned lane = threadIdx.x & 31;
+  RightOutflow outflow;
+  outflow.out_sum = a.out_sum; outflow.ratio = a.ratio_right; outflow.A = c.A;
   for (uint64_t s = gtid >> 5; s < a.n_slices; s += gthreads >> 5) {
-    const double acc = slice_sum<4>(a.slice_ptr, a.slice_runs, a.words, a.node_w, s, lane);
+    double acc = slice_sum<4>(a.slice_ptr, a.slice_runs, a.words, a.node_w, s, lane);
     const uint64_t row = s * 32 + lane;
     if (row < a.n_states) {
+      acc = acc - right_outflow(outflow, row);
       a.out[row] = acc;
       if (a.fused_update) {  // Runge-Kutta stage update, terms in tableau order (as in flux_slices_kernel)
         double sum = 0.0;
@@ -1107,7 +1144,8 @@ template <int G, bool FUSED>
 __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ row_ptr,
                                                    const uint32_t* __restrict__ entries,
                                                    const double* __restrict__ w, double* __restrict__ out,
-                                                   uint64_t n_rows, StageUpdate up, int accumulate) {
+                                                   uint64_t n_rows, StageUpdate up, int accumulate, RightOutflow outflow,
+                                                   uint64_t first_row) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t row = t / G;
   const int sub = (int)(t % G);
@@ -1133,6 +1171,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ 
     for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
   }
   if (sub == 0 && row < n_rows) {
+    acc = acc - right_outflow(outflow, first_row + row);
     if (accumulate) acc = out[row] + acc;  // a later part of a composite model
     out[row] = acc;
     if (FUSED) {  // Runge-Kutta stage update for this state (same term order as the unfused kernel)
@@ -1440,7 +1479,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   const uint64_t significant = ((prefix_bits ? ((1ull << prefix_bits) - 1) : 0ull)) |
                                ((seed_bits ? ((1ull << seed_bits) - 1) : 0ull) << 32);
 
-  uint64_t total_terms = 0;
+  uint64_t total_terms = 0, total_edges = 0;
   uint64_t node_limit = 0x7fffffffull;  // node id + sign bit in 32 bits; lowered by tests of the splitting
   if (const char* e = std::getenv("TAPES_MAX_NODES")) node_limit = std::min<uint64_t>(node_limit, std::strtoull(e, nullptr, 10));
   while (cur.n > 0) {
@@ -1522,9 +1561,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       TAPES_CUDA_CHECK(cudaMemsetAsync(gmax, 0, NG * 4, st));
       TAPES_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, NG * 4, st));
     }
-    EdgeChunk ec{nullptr, nullptr, 2 * NT};
+    EdgeChunk ec{nullptr, nullptr, NT};  // NT = flux edges of this level (two per term, one per right child)
     if (NT) {  // one allocation for both arrays, owned by the list from here on
-      ec.row = dtemp<uint32_t>(4 * NT); ec.val = ec.row + 2 * NT;
+      ec.row = dtemp<uint32_t>(2 * NT); ec.val = ec.row + NT;
       edge_chunks.push_back(ec);
     }
     emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, keyslot, lrank, trank,
@@ -1591,10 +1630,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
           TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_deferred, counters + 1, 8, cudaMemcpyDeviceToHost, st));
           TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
           if (h_deferred) {
-            cur_level.g_total = dkeep<double>(m, PG);
             next_level.prev_right_base = right_base;
             next_level.prev_prefix = cur_level.g_prefix;
-            next_level.prev_total = cur_level.g_total;
+            next_level.prev_total = kLinkLater;  // the previous level's sums: all levels' sums share one array, made below
             m.stats.deferred_groups += (int64_t)h_deferred;
             m.stats.owned_parents += (int64_t)h_deferred * m.A;
           }
@@ -1603,7 +1641,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     }
     TAPES_CUDA_CHECK(cudaGetLastError());
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-    total_terms += NT;
+    total_edges += NT;
+    total_terms += (NT + (uint64_t)cur_level.n_groups * (uint64_t)m.A) / 2;  // every right child is a term with one stored edge
     m.stats.left_parents += (int64_t)NL;
 
     m.levels.push_back(cur_level);
@@ -1614,6 +1653,51 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (cur_slab.capacity + s1.capacity + s2.capacity > ((size_t)1 << 30)) {
     cur_slab.release(); s1.release(); s2.release();
   }
+  // ---- the sums of all prefix groups in one array; per-prefix lists of the groups (right-chain outflow) ----
+  // A right child of group g with prefix q leaves row q * A + x with weight sum(g) * ratio[q * A + x]: all
+  // right children of all groups with prefix q share the factor ratio[row], so the rows' outflow
+  // through right children is ratio[row] * (sum over those groups' sums) - one number per prefix,
+  // out_sum[q], added up per step by prefix_sums_kernel in a fixed order.  These 40 % of all flux
+  // edges are therefore not stored in the flux structure at all.
+  {
+    uint64_t n_all = 0;
+    for (const Level& lv : m.levels) n_all += lv.n_groups;
+    m.n_groups_all = n_all;
+    if (n_all >= 0xffffffffull) throw TooLarge("more than 2^32 prefix groups");
+    if (n_all) {
+      m.g_total_all = dkeep<double>(m, n_all);
+      uint64_t at = 0;
+      for (size_t l = 0; l < m.levels.size(); ++l) {
+        Level& lv = m.levels[l];
+        if (lv.n_groups) lv.g_total = m.g_total_all + at;
+        if (lv.prev_total == kLinkLater) lv.prev_total = m.levels[l - 1].g_total;
+        at += lv.n_groups;
+      }
+      const uint64_t B = M;  // prefixes
+      uint32_t* cnt = dalloc<uint32_t>(B, st);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, B * 4, st));
+      for (const Level& lv : m.levels)
+        if (lv.n_groups) group_count_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_prefix, lv.n_groups, cnt);
+      m.out_ptr = dkeep<uint64_t>(m, B + 1);
+      uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(B), st);
+      exclusive_scan_u32(cnt, B, m.out_ptr, scan_tmp, st);
+      m.out_ids = dkeep<uint32_t>(m, n_all);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, B * 4, st));
+      at = 0;
+      for (const Level& lv : m.levels) {
+        if (lv.n_groups)
+          group_fill_ids_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_prefix, lv.n_groups, at, m.out_ptr, cnt,
+                                                                                    m.out_ids);
+        at += lv.n_groups;
+      }
+      sort_groups(m.out_ptr, B, m.out_ids, st);  // ascending group number: the order of the additions
+      m.out_sum = dkeep<double>(m, B);
+      dfree(cnt, st); dfree(scan_tmp, st);
+      TAPES_CUDA_CHECK(cudaGetLastError());
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+  }
+
   // seeds walk through p together (Level::block_order): sort the blocks of 256 groups of every
   // level by the prefix they start at; a level whose order comes out as the identity keeps none.
   // The same pass finds the regular blocks (Level::plane_blocks) and lists the others.
@@ -1672,6 +1756,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   auto t_csr = std::chrono::steady_clock::now();
   const uint64_t n = m.n_states;
   m.nnz = 2 * total_terms;
+  m.nnz_stored = total_edges;
   {
     uint32_t* cnt = dalloc<uint32_t>(n, st);
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
@@ -1680,7 +1765,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.row_ptr = dkeep<uint64_t>(m, n + 1);
     uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(n), st);
     exclusive_scan_u32(cnt, n, m.row_ptr, scan_tmp, st);
-    m.entries = dtemp<uint32_t>(m.nnz);
+    m.entries = dtemp<uint32_t>(m.nnz_stored);
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (EdgeChunk& ec : edge_chunks) {
       group_fill_vals_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.val, ec.n, m.row_ptr, cnt, m.entries);
@@ -1692,7 +1777,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     dfree(cnt, st); dfree(scan_tmp, st);
     TAPES_CUDA_CHECK(cudaGetLastError());
   }
-  const double per_row = n ? (double)m.nnz / (double)n : 0.0;
+  const double per_row = n ? (double)m.nnz_stored / (double)n : 0.0;
   m.spmv_group = per_row > 128 ? 4 : (per_row > 64 ? 2 : 1);
   if (const char* g = std::getenv("TAPES_SPMV_LANES")) {
     const int v = std::atoi(g);
@@ -1781,11 +1866,12 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
 
   // marginal tables, longest first
   const int top = marginal_tail_top(m);
-  const bool use_ratio = m.ratio_table && m.ratio_right && m.k >= 2;
+  const bool need_ratio = m.ratio_right && m.k >= 2;     // the product reads the ratios (right-chain outflow)
+  const bool use_ratio = m.ratio_table && need_ratio;    // ... and the levels, unless switched off
   // the longest marginal table and the right-extension ratios come from one pass over p when both
   // are wanted and a tile of 256 rows fits shared memory
   const size_t tile_bytes = ((size_t)kRowsPerBlock * (c.A | 1u) + kRowsPerBlock) * sizeof(double);
-  const bool one_pass = use_ratio && !m.ratio_left && m.fuse_marginal_ratio && m.k - 1 > top && tile_bytes <= 48 * 1024;
+  const bool one_pass = need_ratio && !m.ratio_left && m.fuse_marginal_ratio && m.k - 1 > top && tile_bytes <= 48 * 1024;
   for (int L = m.k - 1; L > top; --L) {
     const double* src = (L + 1 == m.k) ? d_p : m.marg + m.marg_off[L + 1];
     if (one_pass && L == m.k - 1) {
@@ -1807,7 +1893,7 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   if (m.n_rules)
     rule_weight_kernel<<<grid_for(m.n_rules, 128), 128, 0, st>>>(t, m.n_rules, m.rule_ptr, m.step_kind, m.step_len,
                                                                 m.step_long, m.step_short, m.step_prob, m.rule_w);
-  if (use_ratio && !one_pass)
+  if (need_ratio && !one_pass)
     ratio_tables_kernel<<<grid_for(m.n_states, kThreads * kRatioBatch), kThreads, 0, st>>>(
         d_p, m.marg + m.marg_off[m.k - 1], m.ratio_right, m.ratio_left, m.n_states, c.A, c.M);
   if (ev) TAPES_CUDA_CHECK(cudaEventRecord(ev[1], st));
@@ -1857,7 +1943,16 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
 #undef TAPES_LEVEL_R
     }
   }
+  if (m.out_sum)  // what leaves the rows through right children: one sum per prefix
+    prefix_sums_kernel<<<grid_for(m.pow_a[m.k - 1], kThreads), kThreads, 0, st>>>(m.out_ptr, m.out_ids, m.g_total_all, m.out_sum,
+                                                                                 m.pow_a[m.k - 1]);
   TAPES_CUDA_CHECK(cudaGetLastError());
+}
+
+RightOutflow right_outflow_of(const Model& m) {
+  RightOutflow of;
+  of.out_sum = m.out_sum; of.ratio = m.ratio_right; of.A = (uint32_t)m.A;
+  return of;
 }
 
 template <bool FUSED>
@@ -1880,12 +1975,13 @@ void launch_flux_impl(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi,
   }
   const unsigned grid = grid_for(threads, kThreads);
   const int acc = accumulate ? 1 : 0;
+  const RightOutflow of = right_outflow_of(m);
   switch (m.spmv_group) {
-    case 1: spmv_kernel<1, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
-    case 2: spmv_kernel<2, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
-    case 4: spmv_kernel<4, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
-    case 8: spmv_kernel<8, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
-    default: spmv_kernel<16, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc); break;
+    case 1: spmv_kernel<1, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
+    case 2: spmv_kernel<2, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
+    case 4: spmv_kernel<4, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
+    case 8: spmv_kernel<8, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
+    default: spmv_kernel<16, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
   }
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
@@ -1941,6 +2037,8 @@ bool launch_fused(Model& m, const double* d_p, double* d_out, cudaStream_t st, c
   a.marg = m.marg; a.ratio_right = m.k >= 2 ? m.ratio_right : nullptr; a.node_w = m.node_w;
   a.slice_ptr = m.slices.slice_ptr; a.slice_runs = m.slices.slice_runs; a.words = m.slices.words;
   a.n_states = m.n_states; a.n_slices = m.slices.n_slices; a.out = d_out; a.fused_update = up ? 1 : 0;
+  a.out_ptr = m.out_ptr; a.out_ids = m.out_ids; a.g_total_all = m.g_total_all; a.out_sum = m.out_sum;
+  a.n_prefixes = m.pow_a[m.k - 1];
   StageUpdate upd = up ? *up : StageUpdate();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)m.fused_cluster); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -2036,9 +2134,9 @@ int64_t rhs_launch_count(const Model& m) {
   if (m.n_rules) launches += 1;         // leaf-world probabilities
   {
     const size_t tile_bytes = ((size_t)kRowsPerBlock * ((size_t)m.A | 1u) + kRowsPerBlock) * sizeof(double);
-    const bool one_pass = m.ratio_table && m.ratio_right && m.k >= 2 && !m.ratio_left && m.fuse_marginal_ratio &&
+    const bool one_pass = m.ratio_right && m.k >= 2 && !m.ratio_left && m.fuse_marginal_ratio &&
                           m.k - 1 > top && tile_bytes <= 48 * 1024;
-    if (m.ratio_table && m.ratio_right && m.k >= 2 && !one_pass) launches += 1;  // extension ratios in a pass of their own
+    if (m.ratio_right && m.k >= 2 && !one_pass) launches += 1;  // extension ratios in a pass of their own
   }
   const bool use_ratio = m.ratio_table && m.ratio_right && m.k >= 2;
   for (const Level& lv : m.levels) {
@@ -2047,6 +2145,7 @@ int64_t rhs_launch_count(const Model& m) {
     if (planes) launches += 1;
     if (lv.n_left + (planes ? lv.n_general_blocks : lv.n_groups)) launches += 1;
   }
+  if (m.out_sum) launches += 1;         // per-prefix sums of the group sums (right-chain outflow)
   launches += 1;                        // S * w
   for (const auto& part : m.more) launches += rhs_launch_count(*part);
   return launches;
@@ -2178,5 +2277,60 @@ void rhs_host_impl(Model& m, const double* h_p, double* h_out) {
   TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
 }
 }  // namespace
+
+void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries) {
+  if (!m.more.empty()) throw std::runtime_error("composite model: export its parts one by one");
+  const uint64_t n = m.n_states, A = (uint64_t)m.A;
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+  std::vector<uint64_t> rp(n + 1);
+  TAPES_CUDA_CHECK(cudaMemcpy(rp.data(), m.row_ptr, (n + 1) * 8, cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> stored(m.nnz_stored);
+  if (m.nnz_stored) {
+    uint32_t* d_entries = m.entries;
+    uint32_t* rebuilt = nullptr;
+    if (!d_entries) {  // only the sliced form is resident: expand it back
+      if (cudaMalloc((void**)&rebuilt, m.nnz_stored * 4) != cudaSuccess) throw std::runtime_error("out of device memory");
+      try {
+        expand_flux_slices(m, rebuilt, m.stream);
+        TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+      } catch (...) {
+        cudaFree(rebuilt);
+        throw;
+      }
+      d_entries = rebuilt;
+    }
+    const cudaError_t err = cudaMemcpy(stored.data(), d_entries, m.nnz_stored * 4, cudaMemcpyDeviceToHost);
+    if (rebuilt) cudaFree(rebuilt);
+    TAPES_CUDA_CHECK(err);
+  }
+  // the outflow entries of the right children, which the device structure keeps as per-prefix sums
+  std::vector<std::vector<uint32_t>> prefixes(m.levels.size());
+  std::vector<int64_t> count(n + 1, 0);
+  for (uint64_t r = 0; r < n; ++r) count[r] = (int64_t)(rp[r + 1] - rp[r]);
+  for (size_t l = 0; l < m.levels.size(); ++l) {
+    const Level& lv = m.levels[l];
+    if (!lv.n_groups) continue;
+    prefixes[l].resize(lv.n_groups);
+    TAPES_CUDA_CHECK(cudaMemcpy(prefixes[l].data(), lv.g_prefix, (size_t)lv.n_groups * 4, cudaMemcpyDeviceToHost));
+    for (uint32_t g = 0; g < lv.n_groups; ++g)
+      for (uint64_t x = 0; x < A; ++x) count[(uint64_t)prefixes[l][g] * A + x] += 1;
+  }
+  h_row_ptr[0] = 0;
+  for (uint64_t r = 0; r < n; ++r) h_row_ptr[r + 1] = h_row_ptr[r] + count[r];
+  if ((uint64_t)h_row_ptr[n] != m.nnz) throw std::runtime_error("export: entry count does not match the flux terms");
+  std::vector<int64_t> cursor(h_row_ptr, h_row_ptr + n);
+  for (uint64_t r = 0; r < n; ++r)
+    for (uint64_t e = rp[r]; e < rp[r + 1]; ++e) h_entries[cursor[r]++] = stored[e];
+  for (size_t l = 0; l < m.levels.size(); ++l) {
+    const Level& lv = m.levels[l];
+    const uint64_t right_base = lv.base + A * lv.n_left;
+    for (uint32_t g = 0; g < lv.n_groups; ++g)
+      for (uint64_t x = 0; x < A; ++x) {
+        const uint64_t row = (uint64_t)prefixes[l][g] * A + x;
+        h_entries[cursor[row]++] = (uint32_t)(right_base + (uint64_t)g * A + x) | kOutflowBit;
+      }
+  }
+  for (uint64_t r = 0; r < n; ++r) std::sort(h_entries + h_row_ptr[r], h_entries + h_row_ptr[r + 1]);
+}
 
 }  // namespace tapes

@@ -170,7 +170,8 @@ struct Model {
   double* node_w = nullptr;        // [n_nodes] evaluated per right-hand side
 
   // flux structure S (n_states x n_nodes, entries +-1) in CSR by state
-  uint64_t nnz = 0;
+  uint64_t nnz = 0;                // 2 per flux term
+  uint64_t nnz_stored = 0;         // entries held by row_ptr / entries / slices: the outflow of right children is not (out_ptr)
   uint64_t* row_ptr = nullptr;     // [n_states + 1]
   uint32_t* entries = nullptr;     // [nnz] node id | sign << 31 (1 = outflow); freed once the sliced
                                    // form below exists (tapes_export_csr rebuilds it on demand)
@@ -184,6 +185,14 @@ struct Model {
   int interleave_seeds = 1;        // level kernel: use Level::block_order
   int ratio_table = 1;             // extension ratios of full windows evaluated once per step into tables
   double* ratio_right = nullptr;   // [n_states] p[i] / max(p[i], marg_{k-1}[i / A]), 0 where p[i] == 0
+  // Right-chain outflow (engine.cu build_model): per (k-1)-digit prefix q the prefix groups of all
+  // levels and seeds whose prefix is q, as numbers into g_total_all (ascending); out_sum[q] = the sum
+  // of their sums, evaluated per step; the product subtracts  out_sum[row / A] * ratio_right[row].
+  uint64_t n_groups_all = 0;
+  double* g_total_all = nullptr;   // [n_groups_all] the levels' g_total, one after the other
+  uint64_t* out_ptr = nullptr;     // [A^(k-1) + 1]
+  uint32_t* out_ids = nullptr;     // [n_groups_all]
+  double* out_sum = nullptr;       // [A^(k-1)], rewritten each step
   double* ratio_left = nullptr;    // [n_states] p[i] / max(p[i], marg_{k-1}[i % A^(k-1)]): left extensions / shifts to a full window
   int plane_kernel = 1;            // regular blocks of prefix groups go to plane_kernel (Level::plane_blocks)
   int fuse_marginal_ratio = 1;     // marg_{k-1} and ratio_right from one pass over the table (marginal_ratio_kernel)
@@ -363,8 +372,13 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st);
 // Non-zero once a wait timed out (a rank died or fell more than the timeout behind).
 int peer_group_error(PeerGroup& g);
 
-// Rebuilds the canonical CSR entries (ascending inside each row) from the slices into a device
-// buffer of nnz words (single-structure models only).
+// Rebuilds the stored CSR entries (ascending inside each row) from the slices into a device
+// buffer of nnz_stored words (single-structure models only).
 void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st);
+
+// The complete flux structure on the HOST in canonical form: row_ptr [n_states + 1], entries [nnz]
+// (node id | outflow << 31, ascending inside each row) - the stored entries plus the outflow entries
+// of the right children, which the device keeps as per-prefix sums (Model::out_ptr).
+void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries);
 
 }  // namespace tapes

@@ -186,13 +186,15 @@ template <int U, bool FUSED, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
-    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up, int accumulate) {
+    uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up, int accumulate,
+    RightOutflow outflow) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t s = slice_lo + (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (s >= slice_hi) return;
   double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
   const uint64_t row = s * 32 + lane;
   if (row >= row_lo && row < row_hi) {
+    acc = acc - right_outflow(outflow, row);  // what leaves the row through right children (engine.h Model::out_ptr)
     if (accumulate) acc = out[row] + acc;  // a later part of a composite model (engine.h Model::more)
     out[row] = acc;
     if (FUSED) {  // Runge-Kutta stage update for this state (terms in tableau order)
@@ -217,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w,
     const __grid_constant__ PeerPointers staging, uint32_t world, uint32_t rank, uint64_t block,
-    uint64_t sub_slices, uint64_t round, uint64_t n_slices, uint64_t n_rows) {
+    uint64_t sub_slices, uint64_t round, uint64_t n_slices, uint64_t n_rows, RightOutflow outflow) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t idx = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (idx >= sub_slices * world) return;
@@ -228,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
   if (s >= n_slices) return;  // ragged end of the table
   const double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
   const uint64_t row = s * 32 + lane;
-  if (row < n_rows) staging.ptr[owner][(uint64_t)rank * block + (row - owner * block)] = acc;
+  if (row < n_rows) staging.ptr[owner][(uint64_t)rank * block + (row - owner * block)] = acc - right_outflow(outflow, row);
 }
 
 // The owner's half of the exchange: adds the world slots of rows [j_lo, j_hi) of its block in rank
@@ -352,7 +354,7 @@ void build_flux_slices(Model& m, int min_run_lanes, cudaStream_t st) {
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   fs.runs = h_facts[0];
   fs.run_entries = h_facts[1];
-  fs.column_entries = m.nnz - fs.run_entries;
+  fs.column_entries = m.nnz_stored - fs.run_entries;
   fs.column_slots = fs.n_words - 2 * h_facts[2];
   cudaFreeAsync(cols, st); cudaFreeAsync(sizes, st); cudaFreeAsync(scan_tmp, st); cudaFreeAsync(facts, st);
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -366,11 +368,13 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   const uint64_t slice_lo = row_lo / 32, slice_hi = (row_hi + 31) / 32;
   const unsigned grid = grid_for((slice_hi - slice_lo) * 32, kThreads);
   const int acc_flag = accumulate ? 1 : 0;
+  RightOutflow of;
+  of.out_sum = m.out_sum; of.ratio = m.ratio_right; of.A = (uint32_t)m.A;
 #define TAPES_FLUX(U_, B_)                                                                                     \
   (up ? flux_slices_kernel<U_, true, B_><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
-                                                                   d_out, slice_lo, slice_hi, row_lo, row_hi, *up, acc_flag) \
+                                                                   d_out, slice_lo, slice_hi, row_lo, row_hi, *up, acc_flag, of) \
       : flux_slices_kernel<U_, false, B_><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
-                                                                    d_out, slice_lo, slice_hi, row_lo, row_hi, StageUpdate(), acc_flag))
+                                                                    d_out, slice_lo, slice_hi, row_lo, row_hi, StageUpdate(), acc_flag, of))
   // measured on B200 (n = 1e8, 24 rules): occupancy beats depth: 4 gathers per lane at 40 registers
   // 3.55 ms, 6 at 48 registers 3.93 ms, 8 at 56 registers 4.22 ms
   if (m.flux_unroll >= 8) TAPES_FLUX(8, 4);
@@ -430,11 +434,13 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   TAPES_CUDA_CHECK(cudaEventRecord(g.fork, st));
   TAPES_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.fork, 0));
   const unsigned scatter_grid = grid_for(sub_slices * world * 32, kThreads);
+  RightOutflow of;
+  of.out_sum = m.out_sum; of.ratio = m.ratio_right; of.A = (uint32_t)m.A;
   const unsigned long long base = g.epoch;
   for (int c = 0; c < g.rounds; ++c) {
     flux_slices_scatter_kernel<4><<<scatter_grid, kThreads, 0, st>>>(
         fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, g.staging, world, rank, g.block, sub_slices, (uint64_t)c,
-        fs.n_slices, m.n_states);
+        fs.n_slices, m.n_states, of);
     peer_signal_kernel<<<1, 32, 0, st>>>(g.flags, world, rank, 0u, base + c + 1);
     peer_wait_kernel<<<1, 32, 0, g.side>>>(mine, world, 0u, base + c + 1, timeout_ns, g.d_error);
     sum_slots_broadcast_kernel<<<grid_for(sub, kThreads), kThreads, 0, g.side>>>(

@@ -10,6 +10,21 @@ namespace {
 constexpr uint32_t kNone = 0xffffffffu;  // node ids stay below 2^31 - 1, so this is never an entry
 constexpr uint32_t kSignBit = 0x80000000u;
 
+// w_child = w_parent * ratio, pruned when the ratio is not > 0 (tm.scm:1316, 1350, 1373).
+__device__ __forceinline__ double weight_from_ratio(double w_parent, double r) { return r > 0.0 ? w_parent * r : 0.0; }
+
+// What leaves a row through right children (engine.h Model::out_ptr): the sum over the prefix groups
+// with the row's prefix times the row's right-extension ratio.  out_sum null: the model has no
+// prefix groups.
+struct RightOutflow {
+  const double* out_sum = nullptr;
+  const double* ratio = nullptr;
+  uint32_t A = 1;
+};
+__device__ __forceinline__ double right_outflow(const RightOutflow& o, uint64_t row) {
+  return o.out_sum ? weight_from_ratio(o.out_sum[row / o.A], o.ratio[row]) : 0.0;
+}
+
 // The pointers carry no __restrict__ here: the kernels that call this say what may alias (the
 // product kernels declare their arguments const __restrict__ and get the read-only path; the
 // single-launch kernel reads weights written earlier in the same launch and must not).

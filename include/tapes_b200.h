@@ -158,7 +158,9 @@ int tapes_sync(void* model);
  * sums over them; TAPES_MAX_PART_TERMS overrides the ~1.7 * 10^9 flux terms a structure may hold), forest
  * levels whose blocks of prefix groups are evaluated in prefix order across seeds, prefix groups that
  * sit in regular blocks of 256 and are evaluated by the plane kernel (csrc/engine.h Level::PlaneBlock),
- * per-step ratio tables (0, 1: right extensions, 2: also left extensions to a full window).
+ * per-step ratio tables (0, 1: right extensions, 2: also left extensions to a full window), entries
+ * the flux structure stores (nnz minus the outflow entries of right children, which leave their rows
+ * through per-prefix sums instead).
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
@@ -177,9 +179,10 @@ int tapes_model_set(void* model, const char* key, int64_t value);
  * the part of the expansion spent inside cudaMalloc / cudaFree. */
 int tapes_model_timing(void* model, double* out, int capacity);
 
-/* Copies the CSR flux structure to host: row_ptr has n_states + 1 entries, entries has nnz
- * (node id | outflow << 31), ascending inside each row (rebuilt from the sliced form when that is
- * the only resident one). */
+/* Copies the complete flux structure to host in canonical CSR form: row_ptr has n_states + 1
+ * entries, entries has nnz (node id | outflow << 31), ascending inside each row.  It is rebuilt from
+ * what the device holds: the sliced form of the stored entries plus the outflow entries of the right
+ * children, which the device keeps as per-prefix sums. */
 int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries);
 
 /* Copies the node weights of the most recent right-hand side to host (n_nodes doubles). */

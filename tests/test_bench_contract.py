@@ -80,7 +80,7 @@ def test_byte_counts_and_reference_equivalent_work():
   from chemical_kinetics_and_program_execution_b200 import configs
   assert bench.spmv_bytes(10, 3) == 12 * 10 + 16 * 3
   assert bench.step_bytes(10, 3, 5) == 28 * 10 + 24 * 3 + 8 * 3 * 1.5
-  info = dict(n_slices=2, slice_words=100, n_terms=30)
+  info = dict(n_slices=2, slice_words=100, n_terms=30, nnz=60)
   assert bench.flux_format_bytes(info, 40) == 8 * 3 + 4 * 2 + 4 * 100 + 8 * 30 + 8 * 40
   work = bench.literal_vs_merged(types.SimpleNamespace(size_a=4, cl_k=7), configs.random_rule_set(4, 6, seed=2))
   rows = work['counted']
