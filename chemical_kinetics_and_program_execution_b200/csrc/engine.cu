@@ -1653,6 +1653,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (cur_slab.capacity + s1.capacity + s2.capacity > ((size_t)1 << 30)) {
     cur_slab.release(); s1.release(); s2.release();
   }
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+  m.stats.device_expand_ms = ms_since(t_expand);
+  m.stats.expand_alloc_ms = g_alloc_ms;
+  auto t_lists = std::chrono::steady_clock::now();
   // ---- the sums of all prefix groups in one array; per-prefix lists of the groups (right-chain outflow) ----
   // A right child of group g with prefix q leaves row q * A + x with weight sum(g) * ratio[q * A + x]: all
   // right children of all groups with prefix q share the factor ratio[row], so the rows' outflow
@@ -1749,8 +1753,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.stats.nodes = (int64_t)m.n_nodes;
   m.stats.terms = (int64_t)total_terms;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-  m.stats.device_expand_ms = ms_since(t_expand);
-  m.stats.expand_alloc_ms = g_alloc_ms;
+  const double lists_and_blocks_ms = ms_since(t_lists);  // per-prefix lists, block order, plane blocks
 
   // ---- CSR assembly: count per state, scan, fill, sort inside each row ----
   auto t_csr = std::chrono::steady_clock::now();
@@ -1791,7 +1794,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   if (const char* g = std::getenv("TAPES_INTERLEAVE_SEEDS")) m.interleave_seeds = std::atoi(g) != 0;
   if (const char* g = std::getenv("TAPES_GRAPHS")) m.use_graphs = std::atoi(g) != 0;
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-  m.stats.device_csr_ms = ms_since(t_csr);
+  m.stats.device_csr_ms = ms_since(t_csr) + lists_and_blocks_ms;
 
   // ---- the form the product kernel streams: slices of 32 states (flux.cu) ----
   m.flux_format = 1;
