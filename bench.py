@@ -102,33 +102,40 @@ def spmv_bytes(nnz, n):
 
 
 def level_bytes(info):
-  """Algorithmic bytes of all level_kernel launches of one step, every access
-  counted as if it came from DRAM: 16 B per child node (table or ratio read + weight write), 25 B
-  per left-parent record (ids, length, parent weight, short marginal), per prefix group 16 B
-  (prefix + parent progression, or what the run descriptors leave of it), 8 B per parent weight that is
-  gathered (parents a group evaluates itself are not read back) and 16 B per group sum handed to
-  the next level."""
-  children = info['n_nodes']
+  """Algorithmic bytes of the level evaluation of one step (plane_kernel + level_kernel launches and
+  prefix_sums_kernel), every access counted as if it came from DRAM: per node one
+  8-byte read of the table or ratio; one 8-byte weight write per node that is written (the right children
+  of groups in regular blocks are not, unless a later level reads them); 25 B per left-parent record
+  (ids, length, parent weight, short marginal); per prefix group 16 B of records outside regular blocks
+  (48 B per 256 groups inside), its sum written (8 B), read by the level that evaluates its children (8 B)
+  and by prefix_sums_kernel with its number (12 B); 8 B per parent weight that is gathered; 16 B per
+  prefix for the per-prefix sums."""
+  nodes, size_a = info['n_nodes'], max(info['alphabet'], 1)
   gathered = info['hash_inserts'] - info.get('owned_parents', 0)
-  plane = info.get('plane_groups', 0)  # 32 bytes per block of 256 such groups instead of 16 per group
-  per_group = 16.0 * (info['hash_unique'] - plane) + 32.0 * plane / 256
-  groups, prefixes = info['hash_unique'], info['n_states'] // max(info['alphabet'], 1)
-  # every group leaves its sum (8 B); the next level reads the sums of the groups whose children it evaluates
-  # (8 B each); prefix_sums_kernel reads every group's number and sum and writes one sum per prefix
+  plane = info.get('plane_groups', 0)  # 48 bytes per block of 256 such groups instead of 16 per group
+  groups, prefixes = info['hash_unique'], info['n_states'] // size_a
+  unwritten = 0 if info.get('materialize_right', 1) else plane * size_a
+  per_group = 16.0 * (groups - plane) + 48.0 * plane / 256
   sums = 8.0 * groups + 8.0 * info.get('deferred_groups', 0) + 12.0 * groups + 16.0 * prefixes
-  return 16.0 * children + 25.0 * info.get('left_parents', 0) + float(per_group) + 8.0 * gathered + sums
+  return 8.0 * nodes + 8.0 * (nodes - unwritten) + 25.0 * info.get('left_parents', 0) + per_group + 8.0 * gathered + sums
 
 
 def flux_format_bytes(info, n):
-  """Bytes the product kernel must move at the least in the shipped format (sliced flux structure,
-  csrc/flux.cu): slice pointers and run counts, every structure word once, every term's weight once
-  (a term is read by its source and its destination row; the second read is credited to L2), the
-  result once.  Below the real traffic by what L2 misses of the second reads and by the padding of
-  the columns, so `frac` computed from it is a lower bound of the share of the HBM roofline."""
-  slices = info.get('n_slices', (n + 31) // 32)
-  # the outflow of right children: the row's ratio (8 B per state) and one sum per prefix
-  outflow = 8.0 * n + 8.0 * (n // max(info.get('alphabet', 1), 1)) if info.get('nnz_stored', info['nnz']) < info['nnz'] else 0.0
-  return 8.0 * (slices + 1) + 4.0 * slices + 4.0 * info.get('slice_words', 0) + 8.0 * info['n_terms'] + 8.0 * n + outflow
+  """Bytes the product kernel must move at the least in the shipped format (sliced flux structure of
+  the stored entries + per-group flux of the right children, csrc/flux.cu, csrc/flux_device.cuh): slice
+  pointers and run counts, every structure word once, the weight of every stored term once (a term is
+  read by its source and its destination row; the second read is credited to L2); per prefix group its
+  inflow list entry (8 B), its sum (8 B) and one ratio per child (8 A B); per state its own ratio (8 B)
+  for the outflow and the result (8 B); one outflow sum per prefix.  Below the real traffic by what L2
+  misses of the second reads and by the padding of the columns, so `frac` computed from it is a lower
+  bound of the share of the HBM roofline."""
+  slices, size_a = info.get('n_slices', (n + 31) // 32), max(info.get('alphabet', 1), 1)
+  grouped = info.get('nnz_stored', info['nnz']) < info['nnz']
+  groups = info.get('hash_unique', 0) if grouped else 0
+  right_children = groups * size_a
+  lists = (16.0 + 8.0 * size_a) * groups + (8.0 * n + 8.0 * (n // size_a) if grouped else 0.0)
+  return (8.0 * (slices + 1) + 4.0 * slices + 4.0 * info.get('slice_words', 0) + 8.0 * (info['n_terms'] - right_children)
+          + lists + 8.0 * n)
 
 
 def prepass_bytes(info, n, size_a):

@@ -478,12 +478,12 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   std::shared_ptr<tapes::Model> mp = resolve(model);
   if (!mp) return 0;
   const tapes::Model& head = *mp;
-  const int kFields = 35;
+  const int kFields = 36;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
                                      true, false, false, false, false, false, true, true, true, true,
                                      true, false, false, true, true, false, true, true, true, true,
-                                     true, false, true};
+                                     true, false, true, false};
   int64_t total[kFields] = {};
   for (size_t part = 0; part <= head.more.size(); ++part) {
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
@@ -499,7 +499,7 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                                 m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
                                 m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved,
                                 m.stats.plane_groups, (int64_t)((m.ratio_right ? 1 : 0) + (m.ratio_left ? 1 : 0)),
-                                (int64_t)m.nnz_stored};
+                                (int64_t)m.nnz_stored, (int64_t)m.materialize_right};
     for (int i = 0; i < kFields; ++i) {
       if (part == 0) total[i] = v[i];
       else if (adds[i]) total[i] += v[i];
@@ -585,7 +585,12 @@ int tapes_export_node_weights(void* model, double* weights) {
   if (!mp) return 1;
   tapes::Model& m = *mp;
   if (!m.more.empty()) { fail("export_node_weights: composite model; export shares made with tapes_model_part instead"); return 1; }
-  cudaStreamSynchronize(m.stream);
+  try {
+    tapes::materialize_node_weights(m);  // right children are not written per step
+  } catch (const std::exception& ex) {
+    fail(std::string("export_node_weights: ") + ex.what());
+    return 1;
+  }
   if (m.n_nodes && cudaMemcpy(weights, m.node_w, m.n_nodes * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
     fail("export_node_weights: copy failed");
     return 1;

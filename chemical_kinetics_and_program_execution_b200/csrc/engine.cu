@@ -146,9 +146,9 @@ __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c
       key = ((uint64_t)f.seed[i] << 32) | po;
     }
     lflag[i] = left;
-    // flux edges stored for the node: a term has an outflow and an inflow edge, but the outflow of a right
-    // child is not stored per term - it leaves its row through the per-prefix sums (Model::out_ptr)
-    tflag[i] = (fl & FL_TERM) ? ((meta >> 6) == NODE_RIGHT ? 1u : 2u) : 0u;
+    // flux edges stored for the node: a term has an outflow and an inflow edge; the terms of right children
+    // are not stored per node at all - their flux is evaluated per prefix group (Model::out_ptr, in_ptr)
+    tflag[i] = ((fl & FL_TERM) && (meta >> 6) != NODE_RIGHT) ? 2u : 0u;
   }
   // keys seen for the first time are compacted into the new frontier's group list as they are
   // inserted (block scan, one atomic per block); the list is put in canonical order afterwards
@@ -211,10 +211,10 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
       next.flags[ci] = nfl;
     }
   }
-  if (const uint32_t n_edges = tflag[i]) {
-    uint64_t e = trank[i];
-    if (n_edges == 2) { edge_row[e] = io; edge_val[e] = gid | kOutflowBit; ++e; }  // -w at the original window
-    edge_row[e] = ia; edge_val[e] = gid;                                           // +w at the adjusted window
+  if (tflag[i]) {
+    const uint64_t e = trank[i];
+    edge_row[e] = io;     edge_val[e] = gid | kOutflowBit;   // -w at the original window
+    edge_row[e + 1] = ia; edge_val[e + 1] = gid;             // +w at the adjusted window
   }
   const uint32_t slot = keyslot[i];
   if (slot != kNoRank) {
@@ -275,12 +275,14 @@ __global__ void verify_progressions_kernel(const uint32_t* __restrict__ keyrank,
 // The A right children of every prefix group (tm.scm:1310-1322), group-major so that consecutive
 // nodes read consecutive entries of p.
 __global__ void emit_groups_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs,
-                                   Consts c, Frontier next, uint64_t first, uint32_t* __restrict__ g_prefix) {
+                                   Consts c, Frontier next, uint64_t first, uint32_t* __restrict__ g_prefix,
+                                   uint32_t* __restrict__ g_adjusted) {
   const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= n_keys) return;
   const uint64_t key = sorted_keys[g];
   const uint32_t po = (uint32_t)key, pa = hs.vals[hash_slot(hs, key)], seed = (uint32_t)(key >> 32);
   g_prefix[g] = po;
+  g_adjusted[g] = pa;
   const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
   for (uint32_t x = 0; x < c.A; ++x) {
     const uint64_t ci = first + (uint64_t)g * c.A + x;
@@ -319,6 +321,27 @@ __global__ void group_fill_vals_kernel(const uint32_t* __restrict__ group, const
     const uint32_t g = group[i];
     out[ptr[g] + atomicAdd(&cursor[g], 1u)] = val[i];
   }
+}
+
+__global__ void gather_u32_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ index,
+                                  uint32_t* __restrict__ out, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = table[index[i]];
+}
+
+// Groups that do not own their parents gather stored weights; counts those with a parent among the
+// right children of the previous level (node ids from prev_right_base on).
+__global__ void count_right_readers_kernel(const uint32_t* __restrict__ first, const uint32_t* __restrict__ stride,
+                                           const uint32_t* __restrict__ count, uint64_t n_groups, uint64_t prev_right_base,
+                                           unsigned long long* __restrict__ readers) {
+  const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool reads = false;
+  if (g < n_groups && !(count[g] & Level::kOwnsParents)) {
+    const uint32_t n = count[g] & Level::kCountMask;
+    reads = n > 0 && (uint64_t)first[g] + (uint64_t)(n - 1) * stride[g] >= prev_right_base;
+  }
+  const unsigned lanes = __ballot_sync(0xffffffffu, reads);
+  if ((threadIdx.x & 31) == 0 && lanes) atomicAdd(readers, (unsigned long long)__popc(lanes));
 }
 
 constexpr uint32_t kShortGroup = 64;  // groups up to this length are sorted by one thread
@@ -864,7 +887,10 @@ __global__ void __launch_bounds__(kThreads) prefix_sums_kernel(const uint64_t* _
 // per-group records, the bounds tests, and the dependence of the parent loads on one another:
 // with the alphabet size known at compile time (A_ > 0) all 2 * A loads of a thread are in flight
 // at once.  A_ = 0: any alphabet, loads in batches of four.
-template <int A_>
+// STORE: the weights of the right children (the groups' parents, the children of groups nobody
+// takes over) are written; they are needed only when a later level reads stored weights
+// (Model::materialize_right) - the flux of right children is evaluated from the group sums.
+template <int A_, bool STORE>
 __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_kernel(Consts c, Level lv, const double* __restrict__ ratio,
                                                                        const double* __restrict__ wr, double* __restrict__ ww) {
   const uint4* rec4 = (const uint4*)(lv.plane_blocks + blockIdx.x);
@@ -886,7 +912,7 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
     const double* __restrict__ prev_total = lv.prev_total;
     if (n_par == 1) {
       total = weight_from_ratio(prev_total[gp], ratio[i_long]);
-      ww[first] = total;
+      if (STORE) ww[first] = total;
     } else {
       const uint32_t g_step = stride / A;
       if (A_ > 0) {
@@ -899,7 +925,7 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
 #pragma unroll
         for (int j = 0; j < A_; ++j) {
           const double v = weight_from_ratio(t[j], r[j]);
-          ww[first + (uint32_t)j * stride] = v;
+          if (STORE) ww[first + (uint32_t)j * stride] = v;
           total += v;
         }
       } else {
@@ -914,7 +940,7 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
           for (int u = 0; u < 4; ++u) {
             if (j0 + u < A) {
               const double v = weight_from_ratio(t[u], r[u]);
-              ww[first + (j0 + u) * stride] = v;
+              if (STORE) ww[first + (j0 + u) * stride] = v;
               total += v;
             }
           }
@@ -922,8 +948,8 @@ __global__ void __launch_bounds__(kThreads, A_ > 8 || A_ == 0 ? 3 : 4) plane_ker
       }
     }
   }
-  lv.g_total[g] = total;  // read by the next level when it owns this group's children, and by prefix_sums_kernel
-  if (deferred) return;
+  lv.g_total[g] = total;  // read by the next level when it owns this group's children, and by the product
+  if (deferred || !STORE) return;
   // the 32 * A children of the warp's 32 groups: contiguous in the weight vector, and in the table
   // wherever the prefixes are
   const uint32_t lane = tid & 31, warp_first = tid - lane;
@@ -1035,11 +1061,14 @@ struct FusedArgs {
   uint64_t n_states, n_slices;
   double* out;
   int fused_update;
-  const uint64_t* out_ptr;   // right-chain outflow (engine.h Model::out_ptr); out_sum null: none
+  const uint64_t* out_ptr;   // flux of the right children (engine.h Model::out_ptr, in_ptr); out_sum null: none
   const uint32_t* out_ids;
   const double* g_total_all;
   double* out_sum;
   uint64_t n_prefixes;
+  const uint64_t* in_ptr;
+  const uint32_t* in_ids;
+  const uint32_t* in_src;
 };
 
 constexpr int kFusedThreads = 1024;
@@ -1116,13 +1145,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
   }
   // the product, one slice of 32 states per warp
   const unsigned lane = threadIdx.x & 31;
-  RightOutflow outflow;
-  outflow.out_sum = a.out_sum; outflow.ratio = a.ratio_right; outflow.A = c.A;
+  RightFlux right;
+  right.out_sum = a.out_sum; right.ratio = a.ratio_right; right.totals = a.g_total_all;
+  right.in_ptr = a.in_ptr; right.in_ids = a.in_ids; right.in_src = a.in_src; right.A = c.A;
   for (uint64_t s = gtid >> 5; s < a.n_slices; s += gthreads >> 5) {
     double acc = slice_sum<4>(a.slice_ptr, a.slice_runs, a.words, a.node_w, s, lane);
     const uint64_t row = s * 32 + lane;
     if (row < a.n_states) {
-      acc = acc - right_outflow(outflow, row);
+      acc = acc + right_flux<4>(right, row);
       a.out[row] = acc;
       if (a.fused_update) {  // Runge-Kutta stage update, terms in tableau order (as in flux_slices_kernel)
         double sum = 0.0;
@@ -1132,6 +1162,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
       }
     }
   }
+}
+
+// The weights of the right children of one level from the group sums of the last evaluation - what
+// the level kernels write when Model::materialize_right is set (same operands, same product).
+__global__ void materialize_right_kernel(Level lv, Consts c, const double* __restrict__ ratio, double* __restrict__ w) {
+  const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= (uint64_t)lv.n_groups * c.A) return;
+  const uint64_t g = j / c.A, x = j - g * c.A;
+  w[lv.base + (uint64_t)c.A * lv.n_left + j] = weight_from_ratio(lv.g_total[g], ratio[(uint64_t)lv.g_prefix[g] * c.A + x]);
 }
 
 // dy/dt[row] = sum over the row's entries of +-w[node].  G lanes share a row; every lane keeps
@@ -1144,7 +1183,7 @@ template <int G, bool FUSED>
 __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ row_ptr,
                                                    const uint32_t* __restrict__ entries,
                                                    const double* __restrict__ w, double* __restrict__ out,
-                                                   uint64_t n_rows, StageUpdate up, int accumulate, RightOutflow outflow,
+                                                   uint64_t n_rows, StageUpdate up, int accumulate, RightFlux right,
                                                    uint64_t first_row) {
   const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const uint64_t row = t / G;
@@ -1171,7 +1210,7 @@ __global__ void __launch_bounds__(256) spmv_kernel(const uint64_t* __restrict__ 
     for (int d = G / 2; d > 0; d >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, d, G);
   }
   if (sub == 0 && row < n_rows) {
-    acc = acc - right_outflow(outflow, first_row + row);
+    acc = acc + right_flux<kSpmvUnroll>(right, first_row + row);
     if (accumulate) acc = out[row] + acc;  // a later part of a composite model
     out[row] = acc;
     if (FUSED) {  // Runge-Kutta stage update for this state (same term order as the unfused kernel)
@@ -1561,7 +1600,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       TAPES_CUDA_CHECK(cudaMemsetAsync(gmax, 0, NG * 4, st));
       TAPES_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, NG * 4, st));
     }
-    EdgeChunk ec{nullptr, nullptr, NT};  // NT = flux edges of this level (two per term, one per right child)
+    EdgeChunk ec{nullptr, nullptr, NT};  // NT = stored flux edges of this level (two per term that is not a right child)
     if (NT) {  // one allocation for both arrays, owned by the list from here on
       ec.row = dtemp<uint32_t>(2 * NT); ec.val = ec.row + NT;
       edge_chunks.push_back(ec);
@@ -1571,8 +1610,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
                                                           next_level.lp_len, ec.row, ec.val, keyrank, gmin, gmax, gcnt);
     if (NG) {
       next_level.g_prefix = dkeep<uint32_t>(m, NG);
+      next_level.g_adjusted = dkeep<uint32_t>(m, NG);
       emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
-                                                                     NL * (uint64_t)m.A, next_level.g_prefix);
+                                                                     NL * (uint64_t)m.A, next_level.g_prefix,
+                                                                     next_level.g_adjusted);
       // parent lists of the prefix groups: as progressions (first, stride, count) when every list is
       // one - found from the extremes and counts emit_kernel collected, then checked parent by parent
       next_level.g_first = dkeep<uint32_t>(m, NG);
@@ -1642,7 +1683,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     TAPES_CUDA_CHECK(cudaGetLastError());
     TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
     total_edges += NT;
-    total_terms += (NT + (uint64_t)cur_level.n_groups * (uint64_t)m.A) / 2;  // every right child is a term with one stored edge
+    total_terms += NT / 2 + (uint64_t)cur_level.n_groups * (uint64_t)m.A;  // every right child is a term
     m.stats.left_parents += (int64_t)NL;
 
     m.levels.push_back(cur_level);
@@ -1696,6 +1737,45 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       }
       sort_groups(m.out_ptr, B, m.out_ids, st);  // ascending group number: the order of the additions
       m.out_sum = dkeep<double>(m, B);
+      // inflow: the same groups listed by their ADJUSTED prefix, each with its own prefix
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, B * 4, st));
+      for (const Level& lv : m.levels)
+        if (lv.n_groups) group_count_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_adjusted, lv.n_groups, cnt);
+      m.in_ptr = dkeep<uint64_t>(m, B + 1);
+      exclusive_scan_u32(cnt, B, m.in_ptr, scan_tmp, st);
+      m.in_ids = dkeep<uint32_t>(m, n_all);
+      m.in_src = dkeep<uint32_t>(m, n_all);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, B * 4, st));
+      uint32_t* prefix_all = dalloc<uint32_t>(n_all, st);  // the levels' g_prefix, one after the other
+      at = 0;
+      for (const Level& lv : m.levels) {
+        if (lv.n_groups) {
+          group_fill_ids_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_adjusted, lv.n_groups, at, m.in_ptr, cnt,
+                                                                                    m.in_ids);
+          TAPES_CUDA_CHECK(cudaMemcpyAsync(prefix_all + at, lv.g_prefix, (size_t)lv.n_groups * 4, cudaMemcpyDeviceToDevice, st));
+        }
+        at += lv.n_groups;
+      }
+      sort_groups(m.in_ptr, B, m.in_ids, st);
+      gather_u32_kernel<<<grid_for(n_all, kThreads), kThreads, 0, st>>>(prefix_all, m.in_ids, m.in_src, n_all);
+      // does any level read stored weights of right children (parents of a group that does not own them)?
+      unsigned long long* readers = dalloc<unsigned long long>(1, st);
+      TAPES_CUDA_CHECK(cudaMemsetAsync(readers, 0, 8, st));
+      bool explicit_lists = false;
+      for (size_t l = 1; l < m.levels.size(); ++l) {
+        const Level& lv = m.levels[l];
+        if (!lv.n_groups) continue;
+        if (!lv.g_first) { explicit_lists = true; continue; }
+        const uint64_t prev_right_base = m.levels[l - 1].base + (uint64_t)m.A * m.levels[l - 1].n_left;
+        count_right_readers_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_first, lv.g_stride, lv.g_count, lv.n_groups,
+                                                                                       prev_right_base, readers);
+      }
+      unsigned long long h_readers = 0;
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_readers, readers, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      m.materialize_right = (h_readers != 0 || explicit_lists) ? 1 : 0;
+      if (const char* e = std::getenv("TAPES_MATERIALIZE_RIGHT")) m.materialize_right = std::atoi(e) != 0 || m.materialize_right;
+      dfree(prefix_all, st); dfree(readers, st);
       dfree(cnt, st); dfree(scan_tmp, st);
       TAPES_CUDA_CHECK(cudaGetLastError());
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1913,12 +1993,16 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
         // the regular blocks of this level go to plane_kernel, level_kernel keeps the others
         lv.block_order = lv.general_blocks;
         group_blocks = lv.n_general_blocks;
+#define TAPES_PLANE(A_)                                                                                               \
+  (m.materialize_right ? plane_kernel<A_, true><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w) \
+                       : plane_kernel<A_, false><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w))
         switch (c.A) {
-          case 10: plane_kernel<10><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
-          case 4: plane_kernel<4><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
-          case 2: plane_kernel<2><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
-          default: plane_kernel<0><<<lv.n_plane_blocks, kThreads, 0, st>>>(c, lv, m.ratio_right, m.node_w, m.node_w); break;
+          case 10: TAPES_PLANE(10); break;
+          case 4: TAPES_PLANE(4); break;
+          case 2: TAPES_PLANE(2); break;
+          default: TAPES_PLANE(0); break;
         }
+#undef TAPES_PLANE
       }
       const uint32_t q = 32u / c.A, r = 32u % c.A;
       const unsigned grid = left_blocks + group_blocks;
@@ -1952,10 +2036,11 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 
-RightOutflow right_outflow_of(const Model& m) {
-  RightOutflow of;
-  of.out_sum = m.out_sum; of.ratio = m.ratio_right; of.A = (uint32_t)m.A;
-  return of;
+RightFlux right_flux_of(const Model& m) {
+  RightFlux f;
+  f.out_sum = m.out_sum; f.ratio = m.ratio_right; f.totals = m.g_total_all;
+  f.in_ptr = m.in_ptr; f.in_ids = m.in_ids; f.in_src = m.in_src; f.A = (uint32_t)m.A;
+  return f;
 }
 
 template <bool FUSED>
@@ -1978,7 +2063,7 @@ void launch_flux_impl(Model& m, double* d_out, uint64_t row_lo, uint64_t row_hi,
   }
   const unsigned grid = grid_for(threads, kThreads);
   const int acc = accumulate ? 1 : 0;
-  const RightOutflow of = right_outflow_of(m);
+  const RightFlux of = right_flux_of(m);
   switch (m.spmv_group) {
     case 1: spmv_kernel<1, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
     case 2: spmv_kernel<2, FUSED><<<grid, kThreads, 0, st>>>(rp, m.entries, m.node_w, out, rows, up, acc, of, row_lo); break;
@@ -2042,6 +2127,7 @@ bool launch_fused(Model& m, const double* d_p, double* d_out, cudaStream_t st, c
   a.n_states = m.n_states; a.n_slices = m.slices.n_slices; a.out = d_out; a.fused_update = up ? 1 : 0;
   a.out_ptr = m.out_ptr; a.out_ids = m.out_ids; a.g_total_all = m.g_total_all; a.out_sum = m.out_sum;
   a.n_prefixes = m.pow_a[m.k - 1];
+  a.in_ptr = m.in_ptr; a.in_ids = m.in_ids; a.in_src = m.in_src;
   StageUpdate upd = up ? *up : StageUpdate();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)m.fused_cluster); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
@@ -2281,6 +2367,16 @@ void rhs_host_impl(Model& m, const double* h_p, double* h_out) {
 }
 }  // namespace
 
+void materialize_node_weights(Model& m) {
+  if (!m.ratio_right) return;
+  const Consts c = make_consts(m);
+  for (const Level& lv : m.levels)
+    if (lv.n_groups)
+      materialize_right_kernel<<<grid_for((uint64_t)lv.n_groups * c.A, kThreads), kThreads, 0, m.stream>>>(lv, c, m.ratio_right, m.node_w);
+  TAPES_CUDA_CHECK(cudaGetLastError());
+  TAPES_CUDA_CHECK(cudaStreamSynchronize(m.stream));
+}
+
 void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries) {
   if (!m.more.empty()) throw std::runtime_error("composite model: export its parts one by one");
   const uint64_t n = m.n_states, A = (uint64_t)m.A;
@@ -2306,8 +2402,8 @@ void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries) {
     if (rebuilt) cudaFree(rebuilt);
     TAPES_CUDA_CHECK(err);
   }
-  // the outflow entries of the right children, which the device structure keeps as per-prefix sums
-  std::vector<std::vector<uint32_t>> prefixes(m.levels.size());
+  // the entries of the right children, whose flux the device evaluates per prefix group
+  std::vector<std::vector<uint32_t>> prefixes(m.levels.size()), adjusted(m.levels.size());
   std::vector<int64_t> count(n + 1, 0);
   for (uint64_t r = 0; r < n; ++r) count[r] = (int64_t)(rp[r + 1] - rp[r]);
   for (size_t l = 0; l < m.levels.size(); ++l) {
@@ -2315,8 +2411,13 @@ void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries) {
     if (!lv.n_groups) continue;
     prefixes[l].resize(lv.n_groups);
     TAPES_CUDA_CHECK(cudaMemcpy(prefixes[l].data(), lv.g_prefix, (size_t)lv.n_groups * 4, cudaMemcpyDeviceToHost));
+    adjusted[l].resize(lv.n_groups);
+    TAPES_CUDA_CHECK(cudaMemcpy(adjusted[l].data(), lv.g_adjusted, (size_t)lv.n_groups * 4, cudaMemcpyDeviceToHost));
     for (uint32_t g = 0; g < lv.n_groups; ++g)
-      for (uint64_t x = 0; x < A; ++x) count[(uint64_t)prefixes[l][g] * A + x] += 1;
+      for (uint64_t x = 0; x < A; ++x) {
+        count[(uint64_t)prefixes[l][g] * A + x] += 1;
+        count[(uint64_t)adjusted[l][g] * A + x] += 1;
+      }
   }
   h_row_ptr[0] = 0;
   for (uint64_t r = 0; r < n; ++r) h_row_ptr[r + 1] = h_row_ptr[r] + count[r];
@@ -2329,8 +2430,9 @@ void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries) {
     const uint64_t right_base = lv.base + A * lv.n_left;
     for (uint32_t g = 0; g < lv.n_groups; ++g)
       for (uint64_t x = 0; x < A; ++x) {
-        const uint64_t row = (uint64_t)prefixes[l][g] * A + x;
-        h_entries[cursor[row]++] = (uint32_t)(right_base + (uint64_t)g * A + x) | kOutflowBit;
+        const uint32_t node = (uint32_t)(right_base + (uint64_t)g * A + x);
+        h_entries[cursor[(uint64_t)prefixes[l][g] * A + x]++] = node | kOutflowBit;
+        h_entries[cursor[(uint64_t)adjusted[l][g] * A + x]++] = node;
       }
   }
   for (uint64_t r = 0; r < n; ++r) std::sort(h_entries + h_row_ptr[r], h_entries + h_row_ptr[r + 1]);

@@ -39,6 +39,7 @@ struct Level {
   uint32_t* lp_io = nullptr;      // [n_left] table index shared by the children (before adding x)
   uint8_t* lp_len = nullptr;      // [n_left] window length of the children
   uint32_t* g_prefix = nullptr;   // [n_groups] (k-1)-digit window prefix
+  uint32_t* g_adjusted = nullptr; // [n_groups] the same prefix in the adjusted window: the children's inflow goes to rows g_adjusted * A + x
   uint64_t* g_ptr = nullptr;      // [n_groups + 1] offsets into g_parents
   uint32_t* g_parents = nullptr;  // parent node ids, ascending inside each group
   uint64_t n_group_parents = 0;
@@ -185,14 +186,28 @@ struct Model {
   int interleave_seeds = 1;        // level kernel: use Level::block_order
   int ratio_table = 1;             // extension ratios of full windows evaluated once per step into tables
   double* ratio_right = nullptr;   // [n_states] p[i] / max(p[i], marg_{k-1}[i / A]), 0 where p[i] == 0
-  // Right-chain outflow (engine.cu build_model): per (k-1)-digit prefix q the prefix groups of all
-  // levels and seeds whose prefix is q, as numbers into g_total_all (ascending); out_sum[q] = the sum
-  // of their sums, evaluated per step; the product subtracts  out_sum[row / A] * ratio_right[row].
+  // Flux of the right children, evaluated per prefix group instead of per stored term (engine.cu
+  // build_model).  A right child x of group g (prefix q, adjusted prefix q') has weight
+  // sum(g) * ratio_right[q * A + x]; it leaves row q * A + x and enters row q' * A + x.
+  //   outflow: all right children that leave a row share the factor ratio_right[row], so per prefix q
+  //            the groups of all levels and seeds with prefix q are listed (out_ptr / out_ids, numbers
+  //            into g_total_all, ascending) and out_sum[q] = the sum of their sums is formed per step;
+  //            the product subtracts out_sum[row / A] * ratio_right[row];
+  //   inflow:  per adjusted prefix q' the groups with that adjusted prefix are listed with their own
+  //            prefix (in_ptr / in_ids / in_src); the product adds, for row q' * A + x,
+  //            sum(g) * ratio_right[in_src * A + x] over the list.
+  // Neither kind of term is stored in row_ptr / entries / slices, and the weights of right children are
+  // not written at all in regular blocks (Level::plane_blocks) unless a later level reads them
+  // (materialize_right) - tapes_export_node_weights fills them in on demand.
   uint64_t n_groups_all = 0;
   double* g_total_all = nullptr;   // [n_groups_all] the levels' g_total, one after the other
   uint64_t* out_ptr = nullptr;     // [A^(k-1) + 1]
   uint32_t* out_ids = nullptr;     // [n_groups_all]
   double* out_sum = nullptr;       // [A^(k-1)], rewritten each step
+  uint64_t* in_ptr = nullptr;      // [A^(k-1) + 1]
+  uint32_t* in_ids = nullptr;      // [n_groups_all] group numbers, ascending inside each list
+  uint32_t* in_src = nullptr;      // [n_groups_all] the listed group's own prefix
+  int materialize_right = 0;       // 1: some level reads stored weights of right children, so all are written
   double* ratio_left = nullptr;    // [n_states] p[i] / max(p[i], marg_{k-1}[i % A^(k-1)]): left extensions / shifts to a full window
   int plane_kernel = 1;            // regular blocks of prefix groups go to plane_kernel (Level::plane_blocks)
   int fuse_marginal_ratio = 1;     // marg_{k-1} and ratio_right from one pass over the table (marginal_ratio_kernel)
@@ -376,9 +391,13 @@ int peer_group_error(PeerGroup& g);
 // buffer of nnz_stored words (single-structure models only).
 void expand_flux_slices(Model& m, uint32_t* d_entries, cudaStream_t st);
 
+// Fills in the weights of the right children from the group sums of the last evaluation (they are
+// not written per step unless Model::materialize_right); synchronises.
+void materialize_node_weights(Model& m);
+
 // The complete flux structure on the HOST in canonical form: row_ptr [n_states + 1], entries [nnz]
-// (node id | outflow << 31, ascending inside each row) - the stored entries plus the outflow entries
-// of the right children, which the device keeps as per-prefix sums (Model::out_ptr).
+// (node id | outflow << 31, ascending inside each row) - the stored entries plus the entries of the
+// right children, whose flux the device evaluates per prefix group (Model::out_ptr, in_ptr).
 void export_full_csr(Model& m, int64_t* h_row_ptr, uint32_t* h_entries);
 
 }  // namespace tapes

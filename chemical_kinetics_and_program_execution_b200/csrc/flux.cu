@@ -23,6 +23,13 @@ namespace tapes {
 
 namespace {
 
+RightFlux right_flux_of(const Model& m) {
+  RightFlux f;
+  f.out_sum = m.out_sum; f.ratio = m.ratio_right; f.totals = m.g_total_all;
+  f.in_ptr = m.in_ptr; f.in_ids = m.in_ids; f.in_src = m.in_src; f.A = (uint32_t)m.A;
+  return f;
+}
+
 constexpr int kThreads = 256;
 constexpr int kWarpsPerBlock = kThreads / 32;
 
@@ -187,14 +194,14 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w, double* __restrict__ out,
     uint64_t slice_lo, uint64_t slice_hi, uint64_t row_lo, uint64_t row_hi, StageUpdate up, int accumulate,
-    RightOutflow outflow) {
+    RightFlux right) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t s = slice_lo + (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (s >= slice_hi) return;
   double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
   const uint64_t row = s * 32 + lane;
   if (row >= row_lo && row < row_hi) {
-    acc = acc - right_outflow(outflow, row);  // what leaves the row through right children (engine.h Model::out_ptr)
+    acc = acc + right_flux<U>(right, row);  // the terms of right children, per prefix group (engine.h Model::out_ptr)
     if (accumulate) acc = out[row] + acc;  // a later part of a composite model (engine.h Model::more)
     out[row] = acc;
     if (FUSED) {  // Runge-Kutta stage update for this state (terms in tableau order)
@@ -219,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w,
     const __grid_constant__ PeerPointers staging, uint32_t world, uint32_t rank, uint64_t block,
-    uint64_t sub_slices, uint64_t round, uint64_t n_slices, uint64_t n_rows, RightOutflow outflow) {
+    uint64_t sub_slices, uint64_t round, uint64_t n_slices, uint64_t n_rows, RightFlux right) {
   const unsigned lane = threadIdx.x & 31;
   const uint64_t idx = (uint64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (idx >= sub_slices * world) return;
@@ -230,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
   if (s >= n_slices) return;  // ragged end of the table
   const double acc = slice_sum<U>(slice_ptr, slice_runs, words, w, s, lane);
   const uint64_t row = s * 32 + lane;
-  if (row < n_rows) staging.ptr[owner][(uint64_t)rank * block + (row - owner * block)] = acc - right_outflow(outflow, row);
+  if (row < n_rows) staging.ptr[owner][(uint64_t)rank * block + (row - owner * block)] = acc + right_flux<U>(right, row);
 }
 
 // The owner's half of the exchange: adds the world slots of rows [j_lo, j_hi) of its block in rank
@@ -368,8 +375,7 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   const uint64_t slice_lo = row_lo / 32, slice_hi = (row_hi + 31) / 32;
   const unsigned grid = grid_for((slice_hi - slice_lo) * 32, kThreads);
   const int acc_flag = accumulate ? 1 : 0;
-  RightOutflow of;
-  of.out_sum = m.out_sum; of.ratio = m.ratio_right; of.A = (uint32_t)m.A;
+  const RightFlux of = right_flux_of(m);
 #define TAPES_FLUX(U_, B_)                                                                                     \
   (up ? flux_slices_kernel<U_, true, B_><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
                                                                    d_out, slice_lo, slice_hi, row_lo, row_hi, *up, acc_flag, of) \
@@ -434,8 +440,7 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   TAPES_CUDA_CHECK(cudaEventRecord(g.fork, st));
   TAPES_CUDA_CHECK(cudaStreamWaitEvent(g.side, g.fork, 0));
   const unsigned scatter_grid = grid_for(sub_slices * world * 32, kThreads);
-  RightOutflow of;
-  of.out_sum = m.out_sum; of.ratio = m.ratio_right; of.A = (uint32_t)m.A;
+  const RightFlux of = right_flux_of(m);
   const unsigned long long base = g.epoch;
   for (int c = 0; c < g.rounds; ++c) {
     flux_slices_scatter_kernel<4><<<scatter_grid, kThreads, 0, st>>>(

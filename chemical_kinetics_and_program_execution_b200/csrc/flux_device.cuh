@@ -13,16 +13,41 @@ constexpr uint32_t kSignBit = 0x80000000u;
 // w_child = w_parent * ratio, pruned when the ratio is not > 0 (tm.scm:1316, 1350, 1373).
 __device__ __forceinline__ double weight_from_ratio(double w_parent, double r) { return r > 0.0 ? w_parent * r : 0.0; }
 
-// What leaves a row through right children (engine.h Model::out_ptr): the sum over the prefix groups
-// with the row's prefix times the row's right-extension ratio.  out_sum null: the model has no
-// prefix groups.
-struct RightOutflow {
-  const double* out_sum = nullptr;
-  const double* ratio = nullptr;
+// The flux of the right children, evaluated per prefix group (engine.h Model::out_ptr, in_ptr).
+// out_sum null: the model has no prefix groups.
+struct RightFlux {
+  const double* out_sum = nullptr;   // per prefix: sum of the sums of the groups with that prefix
+  const double* ratio = nullptr;     // right-extension ratio of every window
+  const double* totals = nullptr;    // sums of all prefix groups
+  const uint64_t* in_ptr = nullptr;  // per adjusted prefix: the groups that flow in there ...
+  const uint32_t* in_ids = nullptr;
+  const uint32_t* in_src = nullptr;  // ... and their own prefixes
   uint32_t A = 1;
 };
-__device__ __forceinline__ double right_outflow(const RightOutflow& o, uint64_t row) {
-  return o.out_sum ? weight_from_ratio(o.out_sum[row / o.A], o.ratio[row]) : 0.0;
+
+// dy/dt of `row` through right children: + the groups whose adjusted prefix is the row's (each child
+// weight = group sum * ratio of the child's ORIGINAL window, tm.scm:1310-1318, added at the adjusted
+// window, 1290), in list order, then - the row's own outflow (1288).  U list entries are in flight.
+template <int U>
+__device__ __forceinline__ double right_flux(const RightFlux& f, uint64_t row) {
+  if (!f.out_sum) return 0.0;
+  const uint64_t q = row / f.A;
+  const uint32_t x = (uint32_t)(row - q * f.A);
+  double in = 0.0;
+  const uint64_t lo = f.in_ptr[q], hi = f.in_ptr[q + 1];
+  for (uint64_t e = lo; e < hi; e += U) {
+    double t[U], r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool live = e + u < hi;
+      const uint32_t id = live ? f.in_ids[e + u] : 0u, src = live ? f.in_src[e + u] : 0u;
+      t[u] = live ? f.totals[id] : 0.0;
+      r[u] = live ? f.ratio[(uint64_t)src * f.A + x] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) in += weight_from_ratio(t[u], r[u]);
+  }
+  return in - weight_from_ratio(f.out_sum[q], f.ratio[row]);
 }
 
 // The pointers carry no __restrict__ here: the kernels that call this say what may alias (the

@@ -159,8 +159,9 @@ int tapes_sync(void* model);
  * levels whose blocks of prefix groups are evaluated in prefix order across seeds, prefix groups that
  * sit in regular blocks of 256 and are evaluated by the plane kernel (csrc/engine.h Level::PlaneBlock),
  * per-step ratio tables (0, 1: right extensions, 2: also left extensions to a full window), entries
- * the flux structure stores (nnz minus the outflow entries of right children, which leave their rows
- * through per-prefix sums instead).
+ * the flux structure stores (nnz minus the entries of right children, whose flux is evaluated per
+ * prefix group from the group sums), 1 when the weights of right children are written per step because
+ * a later level reads them (else they exist only after tapes_export_node_weights).
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
@@ -181,11 +182,12 @@ int tapes_model_timing(void* model, double* out, int capacity);
 
 /* Copies the complete flux structure to host in canonical CSR form: row_ptr has n_states + 1
  * entries, entries has nnz (node id | outflow << 31), ascending inside each row.  It is rebuilt from
- * what the device holds: the sliced form of the stored entries plus the outflow entries of the right
- * children, which the device keeps as per-prefix sums. */
+ * what the device holds: the sliced form of the stored entries plus the entries of the right
+ * children, whose flux the device evaluates per prefix group. */
 int tapes_export_csr(void* model, int64_t* row_ptr, uint32_t* entries);
 
-/* Copies the node weights of the most recent right-hand side to host (n_nodes doubles). */
+/* Copies the node weights of the most recent right-hand side to host (n_nodes doubles); the weights
+ * of right children, which a step does not write, are filled in from the group sums first. */
 int tapes_export_node_weights(void* model, double* weights);
 
 /* ---- device-resident time stepping (replaces the SciPy stepper call sites

@@ -82,6 +82,8 @@ def test_byte_counts_and_reference_equivalent_work():
   assert bench.step_bytes(10, 3, 5) == 28 * 10 + 24 * 3 + 8 * 3 * 1.5
   info = dict(n_slices=2, slice_words=100, n_terms=30, nnz=60)
   assert bench.flux_format_bytes(info, 40) == 8 * 3 + 4 * 2 + 4 * 100 + 8 * 30 + 8 * 40
+  grouped = dict(info, nnz_stored=20, hash_unique=2, alphabet=10)
+  assert bench.flux_format_bytes(grouped, 40) == 8 * 3 + 4 * 2 + 4 * 100 + 8 * 10 + (16 + 80) * 2 + 8 * 40 + 8 * 4 + 8 * 40
   work = bench.literal_vs_merged(types.SimpleNamespace(size_a=4, cl_k=7), configs.random_rule_set(4, 6, seed=2))
   rows = work['counted']
   assert rows[0]['cl_k'] == 2 and all(r['literal_nodes'] >= r['merged_nodes'] for r in rows)

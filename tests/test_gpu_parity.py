@@ -329,9 +329,10 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
   assert numpy.array_equal(model.node_weights(), weights)
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
   monkeypatch.delenv('TAPES_RATIO_LEFT')  # the default: right table only
+  monkeypatch.setenv('TAPES_MATERIALIZE_RIGHT', '1')  # and the weights of right children written per step
   model = device.DeviceModel(tag, cl_k)
   model.set_option('fused_small', 0)
-  assert model.info['ratio_tables'] == 1
+  assert model.info['ratio_tables'] == 1 and model.info['materialize_right'] == 1
   assert numpy.array_equal(model.rhs(p).cpu().numpy(), with_planes)
   assert numpy.array_equal(model.node_weights(), weights)
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
