@@ -323,10 +323,11 @@ __global__ void group_fill_vals_kernel(const uint32_t* __restrict__ group, const
   }
 }
 
-__global__ void gather_u32_kernel(const uint32_t* __restrict__ table, const uint32_t* __restrict__ index,
-                                  uint32_t* __restrict__ out, uint64_t n) {
+// (group number, the group's own prefix) for every entry of the inflow lists
+__global__ void pair_with_prefix_kernel(const uint32_t* __restrict__ prefix_all, const uint32_t* __restrict__ ids,
+                                        uint2* __restrict__ out, uint64_t n) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = table[index[i]];
+  if (i < n) out[i] = make_uint2(ids[i], prefix_all[ids[i]]);
 }
 
 // Groups that do not own their parents gather stored weights; counts those with a parent among the
@@ -1067,8 +1068,7 @@ struct FusedArgs {
   double* out_sum;
   uint64_t n_prefixes;
   const uint64_t* in_ptr;
-  const uint32_t* in_ids;
-  const uint32_t* in_src;
+  const uint2* in_pairs;
 };
 
 constexpr int kFusedThreads = 1024;
@@ -1147,7 +1147,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
   const unsigned lane = threadIdx.x & 31;
   RightFlux right;
   right.out_sum = a.out_sum; right.ratio = a.ratio_right; right.totals = a.g_total_all;
-  right.in_ptr = a.in_ptr; right.in_ids = a.in_ids; right.in_src = a.in_src; right.A = c.A;
+  right.in_ptr = a.in_ptr; right.in_pairs = a.in_pairs; right.A = c.A;
   for (uint64_t s = gtid >> 5; s < a.n_slices; s += gthreads >> 5) {
     double acc = slice_sum<4>(a.slice_ptr, a.slice_runs, a.words, a.node_w, s, lane);
     const uint64_t row = s * 32 + lane;
@@ -1743,21 +1743,21 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
         if (lv.n_groups) group_count_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_adjusted, lv.n_groups, cnt);
       m.in_ptr = dkeep<uint64_t>(m, B + 1);
       exclusive_scan_u32(cnt, B, m.in_ptr, scan_tmp, st);
-      m.in_ids = dkeep<uint32_t>(m, n_all);
-      m.in_src = dkeep<uint32_t>(m, n_all);
+      uint32_t* in_ids = dalloc<uint32_t>(n_all, st);
+      m.in_pairs = dkeep<uint2>(m, n_all);
       TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, B * 4, st));
       uint32_t* prefix_all = dalloc<uint32_t>(n_all, st);  // the levels' g_prefix, one after the other
       at = 0;
       for (const Level& lv : m.levels) {
         if (lv.n_groups) {
           group_fill_ids_kernel<<<grid_for(lv.n_groups, kThreads), kThreads, 0, st>>>(lv.g_adjusted, lv.n_groups, at, m.in_ptr, cnt,
-                                                                                    m.in_ids);
+                                                                                    in_ids);
           TAPES_CUDA_CHECK(cudaMemcpyAsync(prefix_all + at, lv.g_prefix, (size_t)lv.n_groups * 4, cudaMemcpyDeviceToDevice, st));
         }
         at += lv.n_groups;
       }
-      sort_groups(m.in_ptr, B, m.in_ids, st);
-      gather_u32_kernel<<<grid_for(n_all, kThreads), kThreads, 0, st>>>(prefix_all, m.in_ids, m.in_src, n_all);
+      sort_groups(m.in_ptr, B, in_ids, st);
+      pair_with_prefix_kernel<<<grid_for(n_all, kThreads), kThreads, 0, st>>>(prefix_all, in_ids, m.in_pairs, n_all);
       // does any level read stored weights of right children (parents of a group that does not own them)?
       unsigned long long* readers = dalloc<unsigned long long>(1, st);
       TAPES_CUDA_CHECK(cudaMemsetAsync(readers, 0, 8, st));
@@ -1775,7 +1775,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
       m.materialize_right = (h_readers != 0 || explicit_lists) ? 1 : 0;
       if (const char* e = std::getenv("TAPES_MATERIALIZE_RIGHT")) m.materialize_right = std::atoi(e) != 0 || m.materialize_right;
-      dfree(prefix_all, st); dfree(readers, st);
+      dfree(prefix_all, st); dfree(readers, st); dfree(in_ids, st);
       dfree(cnt, st); dfree(scan_tmp, st);
       TAPES_CUDA_CHECK(cudaGetLastError());
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -2039,7 +2039,7 @@ void launch_weights(Model& m, const double* d_p, cudaStream_t st, cudaEvent_t* e
 RightFlux right_flux_of(const Model& m) {
   RightFlux f;
   f.out_sum = m.out_sum; f.ratio = m.ratio_right; f.totals = m.g_total_all;
-  f.in_ptr = m.in_ptr; f.in_ids = m.in_ids; f.in_src = m.in_src; f.A = (uint32_t)m.A;
+  f.in_ptr = m.in_ptr; f.in_pairs = m.in_pairs; f.A = (uint32_t)m.A;
   return f;
 }
 
@@ -2127,7 +2127,7 @@ bool launch_fused(Model& m, const double* d_p, double* d_out, cudaStream_t st, c
   a.n_states = m.n_states; a.n_slices = m.slices.n_slices; a.out = d_out; a.fused_update = up ? 1 : 0;
   a.out_ptr = m.out_ptr; a.out_ids = m.out_ids; a.g_total_all = m.g_total_all; a.out_sum = m.out_sum;
   a.n_prefixes = m.pow_a[m.k - 1];
-  a.in_ptr = m.in_ptr; a.in_ids = m.in_ids; a.in_src = m.in_src;
+  a.in_ptr = m.in_ptr; a.in_pairs = m.in_pairs;
   StageUpdate upd = up ? *up : StageUpdate();
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)m.fused_cluster); cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = 0; cfg.stream = st;

@@ -194,8 +194,8 @@ struct Model {
   //            into g_total_all, ascending) and out_sum[q] = the sum of their sums is formed per step;
   //            the product subtracts out_sum[row / A] * ratio_right[row];
   //   inflow:  per adjusted prefix q' the groups with that adjusted prefix are listed with their own
-  //            prefix (in_ptr / in_ids / in_src); the product adds, for row q' * A + x,
-  //            sum(g) * ratio_right[in_src * A + x] over the list.
+  //            prefix (in_ptr / in_pairs); the product adds, for row q' * A + x,
+  //            sum(g) * ratio_right[own prefix * A + x] over the list.
   // Neither kind of term is stored in row_ptr / entries / slices, and the weights of right children are
   // not written at all in regular blocks (Level::plane_blocks) unless a later level reads them
   // (materialize_right) - tapes_export_node_weights fills them in on demand.
@@ -205,8 +205,7 @@ struct Model {
   uint32_t* out_ids = nullptr;     // [n_groups_all]
   double* out_sum = nullptr;       // [A^(k-1)], rewritten each step
   uint64_t* in_ptr = nullptr;      // [A^(k-1) + 1]
-  uint32_t* in_ids = nullptr;      // [n_groups_all] group numbers, ascending inside each list
-  uint32_t* in_src = nullptr;      // [n_groups_all] the listed group's own prefix
+  uint2* in_pairs = nullptr;       // [n_groups_all] (group number, the group's own prefix), group numbers ascending inside each list
   int materialize_right = 0;       // 1: some level reads stored weights of right children, so all are written
   double* ratio_left = nullptr;    // [n_states] p[i] / max(p[i], marg_{k-1}[i % A^(k-1)]): left extensions / shifts to a full window
   int plane_kernel = 1;            // regular blocks of prefix groups go to plane_kernel (Level::plane_blocks)

@@ -26,7 +26,7 @@ namespace {
 RightFlux right_flux_of(const Model& m) {
   RightFlux f;
   f.out_sum = m.out_sum; f.ratio = m.ratio_right; f.totals = m.g_total_all;
-  f.in_ptr = m.in_ptr; f.in_ids = m.in_ids; f.in_src = m.in_src; f.A = (uint32_t)m.A;
+  f.in_ptr = m.in_ptr; f.in_pairs = m.in_pairs; f.A = (uint32_t)m.A;
   return f;
 }
 

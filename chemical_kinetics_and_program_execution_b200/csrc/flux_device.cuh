@@ -20,34 +20,37 @@ struct RightFlux {
   const double* ratio = nullptr;     // right-extension ratio of every window
   const double* totals = nullptr;    // sums of all prefix groups
   const uint64_t* in_ptr = nullptr;  // per adjusted prefix: the groups that flow in there ...
-  const uint32_t* in_ids = nullptr;
-  const uint32_t* in_src = nullptr;  // ... and their own prefixes
+  const uint2* in_pairs = nullptr;   // ... as (group number, the group's own prefix)
   uint32_t A = 1;
 };
 
 // dy/dt of `row` through right children: + the groups whose adjusted prefix is the row's (each child
 // weight = group sum * ratio of the child's ORIGINAL window, tm.scm:1310-1318, added at the adjusted
 // window, 1290), in list order, then - the row's own outflow (1288).  U list entries are in flight.
+// Table indices stay below A^k < 2^32, so the index arithmetic is 32-bit.
 template <int U>
 __device__ __forceinline__ double right_flux(const RightFlux& f, uint64_t row) {
   if (!f.out_sum) return 0.0;
-  const uint64_t q = row / f.A;
-  const uint32_t x = (uint32_t)(row - q * f.A);
+  const uint32_t row32 = (uint32_t)row;
+  const uint32_t q = row32 / f.A, x = row32 - q * f.A;
   double in = 0.0;
-  const uint64_t lo = f.in_ptr[q], hi = f.in_ptr[q + 1];
-  for (uint64_t e = lo; e < hi; e += U) {
+  const uint64_t lo = f.in_ptr[q];
+  const uint32_t n = (uint32_t)(f.in_ptr[q + 1] - lo);
+  const uint2* list = f.in_pairs + lo;
+  for (uint32_t e = 0; e < n; e += U) {
+    uint2 pair[U];
     double t[U], r[U];
 #pragma unroll
+    for (int u = 0; u < U; ++u) pair[u] = e + u < n ? list[e + u] : make_uint2(0u, 0u);
+#pragma unroll
     for (int u = 0; u < U; ++u) {
-      const bool live = e + u < hi;
-      const uint32_t id = live ? f.in_ids[e + u] : 0u, src = live ? f.in_src[e + u] : 0u;
-      t[u] = live ? f.totals[id] : 0.0;
-      r[u] = live ? f.ratio[(uint64_t)src * f.A + x] : 0.0;
+      t[u] = e + u < n ? f.totals[pair[u].x] : 0.0;
+      r[u] = e + u < n ? f.ratio[pair[u].y * f.A + x] : 0.0;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) in += weight_from_ratio(t[u], r[u]);
   }
-  return in - weight_from_ratio(f.out_sum[q], f.ratio[row]);
+  return in - weight_from_ratio(f.out_sum[q], f.ratio[row32]);
 }
 
 // The pointers carry no __restrict__ here: the kernels that call this say what may alias (the

@@ -18,7 +18,7 @@ for lanes in [int(x) for x in sys.argv[1:]] or [32, 16, 10, 8]:
   os.environ['TAPES_RUN_MIN_LANES'] = str(lanes)
   mt.u_lib.tapes_release_model(tag.encode(), k)
   model = device.DeviceModel(tag, k)
-  for unroll in (4, 6):
+  for unroll in (2, 3, 4, 6):
     model.set_option('flux_unroll', unroll)
     for _ in range(3):
       model.rhs(p, out)
