@@ -182,7 +182,7 @@ struct Model {
   FluxSlices slices;
   int flux_format = 1;             // 1 = slices, 0 = plain CSR
   int level_unroll = 4;            // loads in flight per thread in level_kernel
-  int flux_unroll = 4;             // gathers in flight per lane in flux_slices_kernel
+  int flux_unroll = 3;             // gathers in flight per lane in flux_slices_kernel (3: 32 registers, 8 blocks per SM)
   int interleave_seeds = 1;        // level kernel: use Level::block_order
   int ratio_table = 1;             // extension ratios of full windows evaluated once per step into tables
   double* ratio_right = nullptr;   // [n_states] p[i] / max(p[i], marg_{k-1}[i / A]), 0 where p[i] == 0

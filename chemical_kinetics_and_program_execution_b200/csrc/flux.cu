@@ -381,8 +381,10 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
                                                                    d_out, slice_lo, slice_hi, row_lo, row_hi, *up, acc_flag, of) \
       : flux_slices_kernel<U_, false, B_><<<grid, kThreads, 0, st>>>(fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, \
                                                                     d_out, slice_lo, slice_hi, row_lo, row_hi, StageUpdate(), acc_flag, of))
-  // measured on B200 (n = 1e8, 24 rules): occupancy beats depth: 4 gathers per lane at 40 registers
-  // 3.55 ms, 6 at 48 registers 3.93 ms, 8 at 56 registers 4.22 ms
+  // measured on B200 (n = 1e8, 24 rules): occupancy beats depth.  Round 1 (all terms stored): 4 gathers per
+  // lane at 40 registers 3.55 ms, 6 at 48 registers 3.93 ms, 8 at 56 registers 4.22 ms.  Round 2 (right
+  // children per prefix group, the kernel walks lists and is bound by latency): 3 at 32 registers and 8
+  // blocks per SM 2.73 ms, 4 at 40 registers 2.96 ms, 2: 3.07 ms, 6: 3.24 ms (profiles/r02_m_*)
   if (m.flux_unroll >= 8) TAPES_FLUX(8, 4);
   else if (m.flux_unroll >= 6) TAPES_FLUX(6, 5);
   else if (m.flux_unroll >= 4) TAPES_FLUX(4, 6);
