@@ -384,7 +384,9 @@ void launch_flux_slices(Model& m, double* d_out, uint64_t row_lo, uint64_t row_h
   // measured on B200 (n = 1e8, 24 rules): occupancy beats depth.  Round 1 (all terms stored): 4 gathers per
   // lane at 40 registers 3.55 ms, 6 at 48 registers 3.93 ms, 8 at 56 registers 4.22 ms.  Round 2 (right
   // children per prefix group, the kernel walks lists and is bound by latency): 3 at 32 registers and 8
-  // blocks per SM 2.73 ms, 4 at 40 registers 2.96 ms, 2: 3.07 ms, 6: 3.24 ms (profiles/r02_m_*)
+  // blocks per SM 2.73 ms, 4 at 40 registers 2.96 ms, 2: 3.07 ms, 6: 3.24 ms (profiles/r02_m_*).  Issuing the
+  // first loads of the per-group lists before the slice is walked (two chains of dependent loads side by
+  // side) needs registers the kernel does not have: 96 B of spills, 3.32 ms; dropped again.
   if (m.flux_unroll >= 8) TAPES_FLUX(8, 4);
   else if (m.flux_unroll >= 6) TAPES_FLUX(6, 5);
   else if (m.flux_unroll >= 4) TAPES_FLUX(4, 6);
