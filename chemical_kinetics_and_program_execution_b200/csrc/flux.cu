@@ -221,8 +221,8 @@ __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_kernel(
 // Every rank starts with a different owner (rank r with owner r + 1, then r + 2, ...): started in
 // the same order, all ranks would store into one owner's memory at a time and queue up at its
 // NVLink ingress (measured at 8 GPUs: +1.5 ms on a 3.6 ms kernel).
-template <int U>
-__global__ void __launch_bounds__(kThreads, 6) flux_slices_scatter_kernel(
+template <int U, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) flux_slices_scatter_kernel(
     const uint64_t* __restrict__ slice_ptr, const uint32_t* __restrict__ slice_runs,
     const uint32_t* __restrict__ words, const double* __restrict__ w,
     const __grid_constant__ PeerPointers staging, uint32_t world, uint32_t rank, uint64_t block,
@@ -447,9 +447,14 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   const RightFlux of = right_flux_of(m);
   const unsigned long long base = g.epoch;
   for (int c = 0; c < g.rounds; ++c) {
-    flux_slices_scatter_kernel<4><<<scatter_grid, kThreads, 0, st>>>(
-        fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, g.staging, world, rank, g.block, sub_slices, (uint64_t)c,
-        fs.n_slices, m.n_states, of);
+    if (m.flux_unroll >= 4)
+      flux_slices_scatter_kernel<4, 6><<<scatter_grid, kThreads, 0, st>>>(
+          fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, g.staging, world, rank, g.block, sub_slices, (uint64_t)c,
+          fs.n_slices, m.n_states, of);
+    else  // like the product of one rank: 3 gathers in flight at 8 blocks per SM
+      flux_slices_scatter_kernel<3, 8><<<scatter_grid, kThreads, 0, st>>>(
+          fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, g.staging, world, rank, g.block, sub_slices, (uint64_t)c,
+          fs.n_slices, m.n_states, of);
     peer_signal_kernel<<<1, 32, 0, st>>>(g.flags, world, rank, 0u, base + c + 1);
     peer_wait_kernel<<<1, 32, 0, g.side>>>(mine, world, 0u, base + c + 1, timeout_ns, g.d_error);
     sum_slots_broadcast_kernel<<<grid_for(sub, kThreads), kThreads, 0, g.side>>>(
