@@ -632,8 +632,9 @@ def run_b200(args):
                   phases_ms=dict(marginals_and_world_probs=float(phase[0]), forest_levels=float(phase[1]),
                                  spmv=float(phase[2])))
   lv_gbs = level_bytes(info) / (phase[1] * 1e-3) / 1e9
-  lv_traffic = recorded_traffic('level_kernel', info, args)
-  roofline_levels = dict(bound='hbm', kernel=f'level_kernel ({info["n_levels"] - 1} launches per step, summed)',
+  lv_parts = [recorded_traffic(k, info, args) for k in ('level_kernel', 'plane_kernel', 'prefix_sums_kernel')]
+  lv_traffic = sum(x for x in lv_parts if x) if lv_parts[0] else None
+  roofline_levels = dict(bound='hbm', kernel='plane_kernel + level_kernel per forest level and prefix_sums_kernel, summed',
                          achieved=lv_gbs, peak=peak, unit='GB/s', frac=lv_gbs / peak, traffic=lv_traffic,
                          dram_frac=(lv_traffic / (phase[1] * 1e-3) / 1e9 / peak) if lv_traffic else None,
                          algorithmic_bytes_per_step=level_bytes(info), kernel_ms=float(phase[1]))
