@@ -139,9 +139,14 @@ def flux_format_bytes(info, n):
 
 
 def prepass_bytes(info, n, size_a):
-  """Marginal tables (read the table, write the k - 1 shorter ones) and the per-step ratio tables
-  (read the table, write one ratio per state and table)."""
-  return 8.0 * n * (1.0 + 2.0 / max(size_a - 1, 1)) + 16.0 * n * info.get('ratio_tables', 1)
+  """Marginal tables and per-step ratio tables.  With the right table only (the default) the longest
+  marginal table and the ratios come from one pass over the table (marginal_ratio_kernel): the table
+  read once, one ratio per state written, the shorter marginal tables written and read once each.
+  With the left table as well: the table read once more and a second ratio per state written."""
+  shorter = 16.0 * n / max(size_a - 1, 1)
+  if info.get('ratio_tables', 1) <= 1:
+    return 16.0 * n + shorter
+  return 8.0 * n + shorter + 8.0 * n + 16.0 * n
 
 
 _TRAFFIC = None
