@@ -174,7 +174,8 @@ MODEL_INFO_FIELDS = (
     'alphabet', 'cl_k', 'spmv_lanes_per_row', 'flux_format', 'n_slices', 'slice_words', 'runs',
     'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll',
     'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups', 'structures',
-    'interleaved_levels', 'plane_groups', 'ratio_tables', 'nnz_stored', 'materialize_right')
+    'interleaved_levels', 'plane_groups', 'ratio_tables', 'nnz_stored', 'materialize_right',
+    'hash_retries')
 
 
 def model_info(model):

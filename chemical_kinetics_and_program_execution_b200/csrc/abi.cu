@@ -478,12 +478,12 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   std::shared_ptr<tapes::Model> mp = resolve(model);
   if (!mp) return 0;
   const tapes::Model& head = *mp;
-  const int kFields = 36;
+  const int kFields = 37;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
                                      true, false, false, false, false, false, true, true, true, true,
                                      true, false, false, true, true, false, true, true, true, true,
-                                     true, false, true, false};
+                                     true, false, true, false, true};
   int64_t total[kFields] = {};
   for (size_t part = 0; part <= head.more.size(); ++part) {
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
@@ -499,7 +499,7 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                                 m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
                                 m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved,
                                 m.stats.plane_groups, (int64_t)((m.ratio_right ? 1 : 0) + (m.ratio_left ? 1 : 0)),
-                                (int64_t)m.nnz_stored, (int64_t)m.materialize_right};
+                                (int64_t)m.nnz_stored, (int64_t)m.materialize_right, m.stats.hash_retries};
     for (int i = 0; i < kFields; ++i) {
       if (part == 0) total[i] = v[i];
       else if (adds[i]) total[i] += v[i];

@@ -121,8 +121,9 @@ struct Frontier {
 // ---------------------------------------------------------------------------------------------
 // Expansion pass 1: classify every frontier node and hash-insert right-chain prefixes.
 // ---------------------------------------------------------------------------------------------
+template <bool VOTE>
 __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c, HashSet hs,
-                                                            uint32_t* __restrict__ lflag, uint32_t* __restrict__ tflag,
+                                                            uint32_t* __restrict__ ltflag,
                                                             uint32_t* __restrict__ keyslot, uint64_t* __restrict__ unique,
                                                             unsigned long long* __restrict__ n_unique) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,23 +146,17 @@ __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c
       haskey = po != pa;                              // tm.scm:1308-1309
       key = ((uint64_t)f.seed[i] << 32) | po;
     }
-    lflag[i] = left;
-    // flux edges stored for the node: a term has an outflow and an inflow edge; the terms of right children
-    // are not stored per node at all - their flux is evaluated per prefix group (Model::out_ptr, in_ptr)
-    tflag[i] = ((fl & FL_TERM) && (meta >> 6) != NODE_RIGHT) ? 2u : 0u;
+    // bit 0: the node has left children; bit 1: its flux term is stored as a pair of edges (outflow,
+    // inflow).  The terms of right children are not stored per node at all - their flux is evaluated
+    // per prefix group (Model::out_ptr, in_ptr).  One scan ranks both (exclusive_scan_u32<true>).
+    ltflag[i] = left | (((fl & FL_TERM) && (meta >> 6) != NODE_RIGHT) ? 2u : 0u);
   }
   // keys seen for the first time are compacted into the new frontier's group list as they are
   // inserted (block scan, one atomic per block); the list is put in canonical order afterwards
   uint32_t slot = 0;
-  const bool fresh = hash_insert_warp(hs, haskey, key, pa, &slot);
+  const bool fresh = VOTE ? hash_insert_warp(hs, haskey, key, pa, &slot) : hash_insert_lane(hs, haskey, key, pa, &slot);
   if (valid) keyslot[i] = haskey ? slot : kNoRank;  // emit_kernel finds the key's group without probing
   block_append_u64(fresh, key, unique, n_unique);
-}
-
-// ranks[slot of sorted_keys[g]] = g
-__global__ void rank_slots_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < n_keys) hs.ranks[hash_slot(hs, sorted_keys[g])] = g;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -170,22 +165,22 @@ __global__ void rank_slots_kernel(const uint64_t* __restrict__ sorted_keys, uint
 // extension adds the MOST significant digit, so left children are stored digit-major
 // (x * n_left_parents + parent rank): consecutive nodes then have consecutive table indices.
 // ---------------------------------------------------------------------------------------------
-__global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ lflag,
-                            const uint32_t* __restrict__ tflag, const uint32_t* __restrict__ keyslot,
-                            const uint64_t* __restrict__ lrank, const uint64_t* __restrict__ trank,
+__global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint32_t* __restrict__ ltflag,
+                            const uint32_t* __restrict__ keyslot, const uint64_t* __restrict__ ltrank,
                             uint64_t n_left_parents, HashSet hs, Frontier next, uint32_t* __restrict__ lp_gid,
                             uint32_t* __restrict__ lp_io, uint8_t* __restrict__ lp_len,
                             uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
-                            uint32_t* __restrict__ keyrank, uint32_t* __restrict__ gmin, uint32_t* __restrict__ gmax,
-                            uint32_t* __restrict__ gcnt) {
+                            uint32_t* __restrict__ keyrank, uint4* __restrict__ gstat) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.n) return;
   const uint8_t meta = f.meta[i];
   const int len = meta & 63;
   const uint32_t io = f.io[i], ia = f.ia[i], seed = f.seed[i];
   const uint32_t gid = (uint32_t)(cur_base + i);
-  if (lflag[i]) {
-    const uint64_t r = lrank[i];
+  const uint32_t lt = ltflag[i];
+  const uint64_t ranks = lt ? ltrank[i] : 0ull;  // low half: rank among the left parents, high half: among the stored terms
+  if (lt & 1u) {
+    const uint64_t r = (uint32_t)ranks;
     uint32_t bo, ba, step;
     int nl;
     uint8_t nfl;
@@ -211,8 +206,8 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
       next.flags[ci] = nfl;
     }
   }
-  if (tflag[i]) {
-    const uint64_t e = trank[i];
+  if (lt & 2u) {
+    const uint64_t e = 2 * (ranks >> 32);
     edge_row[e] = io;     edge_val[e] = gid | kOutflowBit;   // -w at the original window
     edge_row[e + 1] = ia; edge_val[e + 1] = gid;             // +w at the adjusted window
   }
@@ -222,9 +217,11 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
     // of node ids, which smallest id, largest id and count describe completely
     const uint32_t g = hs.ranks[slot];
     keyrank[i] = g;
-    atomicMin(&gmin[g], gid);
-    atomicMax(&gmax[g], gid);
-    atomicAdd(&gcnt[g], 1u);
+    // one 16-byte record per group, cleared to all ones: smallest id, complement of the largest id,
+    // complement of the count - the three updates of a parent land in one sector
+    atomicMin(&gstat[g].x, gid);
+    atomicMin(&gstat[g].y, ~gid);
+    atomicSub(&gstat[g].z, 1u);
   } else {
     keyrank[i] = kNoRank;
   }
@@ -233,16 +230,16 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
 // (first, stride, count) of every group from the extremes of its parent ids; a group whose extremes
 // cannot belong to a progression of `count` ids is counted as irregular.  facts: [1] irregular
 // groups, [2] parents of all groups.
-__global__ void derive_progressions_kernel(const uint32_t* __restrict__ gmin, const uint32_t* __restrict__ gmax,
-                                           const uint32_t* __restrict__ gcnt, uint64_t n_groups,
+__global__ void derive_progressions_kernel(const uint4* __restrict__ gstat, uint64_t n_groups,
                                            uint32_t* __restrict__ first, uint32_t* __restrict__ stride,
                                            uint32_t* __restrict__ count, unsigned long long* __restrict__ facts) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t n = 0;
   bool bad = false;
   if (g < n_groups) {
-    n = gcnt[g];
-    const uint32_t lo = n ? gmin[g] : 0u, span = n ? gmax[g] - lo : 0u;
+    const uint4 st = gstat[g];
+    n = ~st.z;
+    const uint32_t lo = n ? st.x : 0u, span = n ? ~st.y - lo : 0u;
     const uint32_t d = n > 1 ? span / (n - 1) : 0u;
     bad = n > 1 && (d == 0 || span % (n - 1) != 0);
     first[g] = lo; stride[g] = d; count[g] = n;
@@ -273,22 +270,35 @@ __global__ void verify_progressions_kernel(const uint32_t* __restrict__ keyrank,
 }
 
 // The A right children of every prefix group (tm.scm:1310-1322), group-major so that consecutive
-// nodes read consecutive entries of p.
-__global__ void emit_groups_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys, HashSet hs,
-                                   Consts c, Frontier next, uint64_t first, uint32_t* __restrict__ g_prefix,
-                                   uint32_t* __restrict__ g_adjusted) {
-  const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= n_keys) return;
-  const uint64_t key = sorted_keys[g];
-  const uint32_t po = (uint32_t)key, pa = hs.vals[hash_slot(hs, key)], seed = (uint32_t)(key >> 32);
-  g_prefix[g] = po;
-  g_adjusted[g] = pa;
+// nodes read consecutive entries of p.  A block takes kThreads groups: every thread finds the slot
+// of one group's key (the only probe of the table after the insertions: the slot's rank is recorded
+// here for emit_kernel, and the adjusted prefix comes out of it), then the block writes the
+// kThreads * A children with consecutive threads on consecutive children.
+__global__ void __launch_bounds__(kThreads) emit_groups_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys,
+                                                               HashSet hs, Consts c, Frontier next, uint64_t first,
+                                                               uint32_t* __restrict__ g_prefix,
+                                                               uint32_t* __restrict__ g_adjusted) {
+  __shared__ uint32_t s_po[kThreads], s_pa[kThreads], s_seed[kThreads];
+  const uint32_t g0 = blockIdx.x * kThreads, g = g0 + threadIdx.x;
+  if (g < n_keys) {
+    const uint64_t key = sorted_keys[g];
+    const uint64_t slot = hash_slot(hs, key);
+    const uint32_t po = (uint32_t)key, pa = hs.vals[slot];
+    hs.ranks[slot] = g;
+    g_prefix[g] = po;
+    g_adjusted[g] = pa;
+    s_po[threadIdx.x] = po; s_pa[threadIdx.x] = pa; s_seed[threadIdx.x] = (uint32_t)(key >> 32);
+  }
+  __syncthreads();
+  const uint32_t groups = min((uint32_t)kThreads, n_keys - g0), children = groups * c.A;
   const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
-  for (uint32_t x = 0; x < c.A; ++x) {
-    const uint64_t ci = first + (uint64_t)g * c.A + x;
-    next.io[ci] = po * c.A + x;
-    next.ia[ci] = pa * c.A + x;
-    next.seed[ci] = seed;
+  const uint64_t base = first + (uint64_t)g0 * c.A;
+  for (uint32_t j = threadIdx.x; j < children; j += kThreads) {
+    const uint32_t q = j / c.A, x = j - q * c.A;
+    const uint64_t ci = base + j;
+    next.io[ci] = s_po[q] * c.A + x;
+    next.ia[ci] = s_pa[q] * c.A + x;
+    next.seed[ci] = s_seed[q];
     next.meta[ci] = nmeta;
     next.flags[ci] = FL_TERM | FL_RIGHT;
   }
@@ -1520,44 +1530,73 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
 
   uint64_t total_terms = 0, total_edges = 0;
   uint64_t node_limit = 0x7fffffffull;  // node id + sign bit in 32 bits; lowered by tests of the splitting
+  int hash_vote = -1;  // -1: by table shape
+  int hash_guess = 1;  // 0: always 2 n slots; 1: sized on a guess; 2: start every level with the smallest table (tests of the retry)
+  if (const char* e = std::getenv("TAPES_HASH_GUESS")) hash_guess = std::atoi(e);
+  uint64_t prev_n = 0, prev_groups = 0;
+  if (const char* e = std::getenv("TAPES_HASH_VOTE")) hash_vote = std::atoi(e);
   if (const char* e = std::getenv("TAPES_MAX_NODES")) node_limit = std::min<uint64_t>(node_limit, std::strtoull(e, nullptr, 10));
   while (cur.n > 0) {
     if (cur_level.base + cur.n >= node_limit) throw TooLarge("extension forest exceeds 2^31 nodes");
     m.stats.levels++;
     const uint64_t n = cur.n;
 
-    // pass 1: classify + hash-dedup of the right-chain prefixes
-    uint64_t cap = 1024;
-    while (cap < 2 * n) cap <<= 1;
-    s1.reset();
-    const size_t i_keys = s1.want(cap * 8), i_vals = s1.want(cap * 4), i_ranks = s1.want(cap * 4);
-    const size_t i_lflag = s1.want(n * 4), i_tflag = s1.want(n * 4), i_kflag = s1.want(n * 4);
-    const size_t i_lrank = s1.want((n + 1) * 8), i_trank = s1.want((n + 1) * 8);
-    const size_t i_scan = s1.want(scan_tmp_elems(std::max<uint64_t>(n, 256ull * 1184)) * 8);
-    const size_t i_unique = s1.want(n * 8), i_counters = s1.want(32);
-    s1.commit();
+    // pass 1: classify + hash-dedup of the right-chain prefixes.  The table is sized on a guess of the
+    // number of distinct prefixes - the previous level's, scaled by the growth of the level: most
+    // prefixes are reached from A parents, and a table of 2 n slots would be several times larger than
+    // needed, which costs in cleared and randomly touched memory - and the pass starts over with the
+    // safe size when the guess turns out too small.
+    uint64_t cap_safe = 1024;
+    while (cap_safe < 2 * n) cap_safe <<= 1;
+    uint64_t cap = cap_safe;
+    if (hash_guess == 2) cap = 1024;
+    else if (hash_guess && prev_n) {
+      const double guess = 1.25 * (double)prev_groups * ((double)n / (double)prev_n) + 4096.0;
+      cap = 1024;
+      while (cap < cap_safe && (double)cap < 2.0 * guess) cap <<= 1;
+    }
     HashSet hs;
-    hs.keys = s1.at<uint64_t>(i_keys); hs.vals = s1.at<uint32_t>(i_vals); hs.ranks = s1.at<uint32_t>(i_ranks);
-    hs.mask = cap - 1;
-    uint32_t* lflag = s1.at<uint32_t>(i_lflag);
-    uint32_t* tflag = s1.at<uint32_t>(i_tflag);
-    uint32_t* keyslot = s1.at<uint32_t>(i_kflag);
-    uint64_t* lrank = s1.at<uint64_t>(i_lrank);
-    uint64_t* trank = s1.at<uint64_t>(i_trank);
-    uint64_t* scan_tmp = s1.at<uint64_t>(i_scan);
-    uint64_t* keys_a = s1.at<uint64_t>(i_unique);
-    unsigned long long* counters = s1.at<unsigned long long>(i_counters);  // [0] unique keys, [1] irregular groups, [2] parents
-    TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
-    TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 32, st));
-    classify_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, lflag, tflag, keyslot, keys_a, counters);
-    exclusive_scan_u32(lflag, n, lrank, scan_tmp, st);
-    exclusive_scan_u32(tflag, n, trank, scan_tmp, st);
-    uint64_t h_tot[3];
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], lrank + n, 8, cudaMemcpyDeviceToHost, st));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], trank + n, 8, cudaMemcpyDeviceToHost, st));
-    TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], counters, 8, cudaMemcpyDeviceToHost, st));
-    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-    const uint64_t NL = h_tot[0], NT = h_tot[1], NG = h_tot[2];
+    uint32_t *ltflag = nullptr, *keyslot = nullptr;
+    uint64_t *ltrank = nullptr, *scan_tmp = nullptr, *keys_a = nullptr;
+    unsigned long long* counters = nullptr;  // [0] unique keys, [1] irregular groups, [2] parents, [3] table too small
+    uint64_t NL = 0, NT = 0, NG = 0;
+    for (;;) {
+      s1.reset();
+      const size_t i_keys = s1.want(cap * 8), i_vals = s1.want(cap * 4), i_ranks = s1.want(cap * 4);
+      const size_t i_ltflag = s1.want(n * 4), i_kflag = s1.want(n * 4);
+      const size_t i_ltrank = s1.want((n + 1) * 8);
+      const size_t i_scan = s1.want(scan_tmp_elems(std::max<uint64_t>(n, 256ull * 1184)) * 8);
+      const size_t i_unique = s1.want(n * 8), i_counters = s1.want(32);
+      s1.commit();
+      hs.keys = s1.at<uint64_t>(i_keys); hs.vals = s1.at<uint32_t>(i_vals); hs.ranks = s1.at<uint32_t>(i_ranks);
+      hs.mask = cap - 1;
+      ltflag = s1.at<uint32_t>(i_ltflag);
+      keyslot = s1.at<uint32_t>(i_kflag);
+      ltrank = s1.at<uint64_t>(i_ltrank);
+      scan_tmp = s1.at<uint64_t>(i_scan);
+      keys_a = s1.at<uint64_t>(i_unique);
+      counters = s1.at<unsigned long long>(i_counters);
+      hs.full = counters + 3;
+      TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
+      TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 32, st));
+      // lanes of a warp hold different prefixes unless the level is tiny or the table short (M < 32):
+      // the warp vote that merges equal keys before the insertion only pays there
+      if (hash_vote < 0 ? c.M < 32 : hash_vote)
+        classify_kernel<true><<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
+      else
+        classify_kernel<false><<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
+      exclusive_scan_u32<true>(ltflag, n, ltrank, scan_tmp, st);
+      uint64_t h_tot[3];
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], ltrank + n, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], counters + 3, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], counters, 8, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      NL = (uint32_t)h_tot[0]; NT = 2 * (h_tot[0] >> 32); NG = h_tot[2];  // NT counts edges, two per stored term
+      if (cap == cap_safe || (h_tot[1] == 0 && NG * 10 <= cap * 7)) break;
+      cap = cap_safe;  // the guess was too small: the slots handed out are not to be trusted
+      m.stats.hash_retries++;
+    }
+    prev_n = n; prev_groups = NG;
     if ((NL + NG) * (uint64_t)m.A >= 0xffffffffull) throw TooLarge("a level of the extension forest exceeds 2^32 nodes");
 
     // pass 2: children, parent records, flux edges
@@ -1572,8 +1611,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     size_t fi[5];
     plan_frontier(s2, next.n, fi);
     const size_t i_keys_b = s2.want(NG * 8), i_rh = s2.want(256ull * plan.blocks * 4);
-    const size_t i_ro = s2.want((256ull * plan.blocks + 1) * 8), i_keyrank = s2.want(n * 4), i_cnt = s2.want(NG * 4);
-    const size_t i_gmin = s2.want(NG * 4), i_gmax = s2.want(NG * 4);
+    const size_t i_ro = s2.want((256ull * plan.blocks + 1) * 8), i_keyrank = s2.want(n * 4), i_gstat = s2.want(NG * 16);
     const size_t i_consumed = s2.want((size_t)cur_level.n_groups * 4);
     const size_t i_gptr = s2.want((NG + 1) * 8), i_gparents = s2.want(n * 4);  // parent lists (at most n parents)
     s2.commit();
@@ -1585,42 +1623,36 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     if (NG) {
       sorted = radix_sort_u64(keys_a, s2.at<uint64_t>(i_keys_b), NG, significant, s2.at<uint32_t>(i_rh),
                               s2.at<uint64_t>(i_ro), scan_tmp, st);
-      rank_slots_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs);
+      // the children of the groups; records every group's rank in the table for emit_kernel
+      next_level.g_prefix = dkeep<uint32_t>(m, NG);
+      next_level.g_adjusted = dkeep<uint32_t>(m, NG);
+      emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
+                                                                     NL * (uint64_t)m.A, next_level.g_prefix,
+                                                                     next_level.g_adjusted);
     }
     if (NL) {
       next_level.lp_gid = dkeep<uint32_t>(m, NL);
       next_level.lp_io = dkeep<uint32_t>(m, NL);
       next_level.lp_len = dkeep<uint8_t>(m, NL);
     }
-    uint32_t* gmin = s2.at<uint32_t>(i_gmin);
-    uint32_t* gmax = s2.at<uint32_t>(i_gmax);
-    uint32_t* gcnt = s2.at<uint32_t>(i_cnt);
-    if (NG) {
-      TAPES_CUDA_CHECK(cudaMemsetAsync(gmin, 0xff, NG * 4, st));
-      TAPES_CUDA_CHECK(cudaMemsetAsync(gmax, 0, NG * 4, st));
-      TAPES_CUDA_CHECK(cudaMemsetAsync(gcnt, 0, NG * 4, st));
-    }
+    uint4* gstat = s2.at<uint4>(i_gstat);  // per group: smallest parent id, ~largest, ~count (emit_kernel)
+    if (NG) TAPES_CUDA_CHECK(cudaMemsetAsync(gstat, 0xff, NG * 16, st));
     EdgeChunk ec{nullptr, nullptr, NT};  // NT = stored flux edges of this level (two per term that is not a right child)
     if (NT) {  // one allocation for both arrays, owned by the list from here on
       ec.row = dtemp<uint32_t>(2 * NT); ec.val = ec.row + NT;
       edge_chunks.push_back(ec);
     }
-    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, lflag, tflag, keyslot, lrank, trank,
+    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, ltflag, keyslot, ltrank,
                                                           NL, hs, next, next_level.lp_gid, next_level.lp_io,
-                                                          next_level.lp_len, ec.row, ec.val, keyrank, gmin, gmax, gcnt);
+                                                          next_level.lp_len, ec.row, ec.val, keyrank, gstat);
     if (NG) {
-      next_level.g_prefix = dkeep<uint32_t>(m, NG);
-      next_level.g_adjusted = dkeep<uint32_t>(m, NG);
-      emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
-                                                                     NL * (uint64_t)m.A, next_level.g_prefix,
-                                                                     next_level.g_adjusted);
       // parent lists of the prefix groups: as progressions (first, stride, count) when every list is
       // one - found from the extremes and counts emit_kernel collected, then checked parent by parent
       next_level.g_first = dkeep<uint32_t>(m, NG);
       next_level.g_stride = dkeep<uint32_t>(m, NG);
       next_level.g_count = dkeep<uint32_t>(m, NG);
       derive_progressions_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(
-          gmin, gmax, gcnt, NG, next_level.g_first, next_level.g_stride, next_level.g_count, counters);
+          gstat, NG, next_level.g_first, next_level.g_stride, next_level.g_count, counters);
       verify_progressions_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(
           keyrank, n, cur_level.base, next_level.g_first, next_level.g_stride, counters);
       unsigned long long h_counts[2] = {0, 0};  // irregular groups or parents off their progression, parents
@@ -1630,10 +1662,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       next_level.n_group_parents = n_par;
       if (h_counts[0] != 0 || std::getenv("TAPES_KEEP_PARENT_LISTS")) {
         // some list is not a progression: this level keeps explicit lists, ascending inside each group
-        uint32_t* cnt = gcnt;
+        uint32_t* cnt = (uint32_t*)gstat;  // the records have been read: their memory serves as the fill cursors
         uint64_t* g_ptr = s2.at<uint64_t>(i_gptr);
         uint32_t* g_parents = s2.at<uint32_t>(i_gparents);
-        exclusive_scan_u32(cnt, NG, g_ptr, scan_tmp, st);
+        exclusive_scan_u32(next_level.g_count, NG, g_ptr, scan_tmp, st);
         TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, NG * 4, st));
         group_fill_ids_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(keyrank, n, cur_level.base, g_ptr, cnt, g_parents);
         sort_groups(g_ptr, NG, g_parents, st);

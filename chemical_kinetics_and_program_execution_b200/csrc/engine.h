@@ -138,6 +138,7 @@ struct BuildStats {
   int64_t worlds_walked = 0, leaf_worlds = 0, flux_rules = 0, seeds = 0;
   int64_t nodes = 0, sum_nodes = 0, terms = 0, levels = 0;  // sum_nodes = prefix groups
   int64_t hash_inserts = 0, hash_unique = 0;
+  int64_t hash_retries = 0;  // levels whose table of prefixes was sized too small at first (engine.cu, pass 1)
   int64_t irregular_levels = 0;  // levels whose parent lists are kept explicitly
   int64_t left_parents = 0;      // parent records of left extensions / left shifts, all levels
   int64_t owned_parents = 0;     // right children computed by the group they feed (fused right chain)

@@ -51,6 +51,14 @@ __device__ __forceinline__ uint64_t block_exclusive_sum(uint64_t v, uint64_t* wa
   return res;
 }
 
+// PAIR: the input words carry two flags (bit 0, bit 1) that are counted side by side, bit 0 in the
+// low and bit 1 in the high half of the 64-bit sums (each count below 2^32): one scan for two ranks.
+template <bool PAIR>
+__device__ __forceinline__ uint64_t scan_value(uint32_t v) {
+  return PAIR ? ((uint64_t)(v & 1u) | ((uint64_t)((v >> 1) & 1u) << 32)) : (uint64_t)v;
+}
+
+template <bool PAIR>
 __global__ void scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t n,
                                       uint64_t* __restrict__ tile_sums) {
   __shared__ uint64_t wt[32];
@@ -60,7 +68,7 @@ __global__ void scan_tile_sums_kernel(const uint32_t* __restrict__ in, uint64_t 
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     uint64_t i = tile0 + (uint64_t)j * kScanThreads + threadIdx.x;
-    if (i < n) s += in[i];
+    if (i < n) s += scan_value<PAIR>(in[i]);
   }
   (void)block_exclusive_sum(s, wt, &total);
   if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
@@ -87,6 +95,7 @@ __global__ void scan_tile_offsets_kernel(uint64_t* __restrict__ tile_sums, uint6
 // thread t touches word 16 * t + j, which lands 17 words after thread t - 1's).
 __device__ __forceinline__ int scan_slot(int i) { return i + (i >> 4); }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t* __restrict__ in, uint64_t n,
                                                                   const uint64_t* __restrict__ tile_offsets,
                                                                   uint64_t* __restrict__ out) {
@@ -108,13 +117,13 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     v[j] = (uint32_t)stage[scan_slot((int)threadIdx.x * kScanItems + j)];
-    s += v[j];
+    s += scan_value<PAIR>(v[j]);
   }
   uint64_t ex = block_exclusive_sum(s, wt, &total) + tile_offsets[blockIdx.x];
 #pragma unroll
   for (int j = 0; j < kScanItems; ++j) {
     stage[scan_slot((int)threadIdx.x * kScanItems + j)] = ex;
-    ex += v[j];
+    ex += scan_value<PAIR>(v[j]);
   }
   __syncthreads();
 #pragma unroll
@@ -128,6 +137,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(const uint32_t
 // `tmp` must hold ceil(n / kScanTile) + 1 u64; out must hold n + 1 u64 (out[n] = total).
 inline size_t scan_tmp_elems(uint64_t n) { return (size_t)((n + kScanTile - 1) / kScanTile + 1); }
 
+template <bool PAIR = false>
 inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint64_t* out, uint64_t* tmp,
                                cudaStream_t st) {
   if (n == 0) {
@@ -135,9 +145,9 @@ inline void exclusive_scan_u32(const uint32_t* in, uint64_t n, uint64_t* out, ui
     return;
   }
   const uint64_t ntiles = (n + kScanTile - 1) / kScanTile;
-  scan_tile_sums_kernel<<<(unsigned)ntiles, kScanThreads, 0, st>>>(in, n, tmp);
+  scan_tile_sums_kernel<PAIR><<<(unsigned)ntiles, kScanThreads, 0, st>>>(in, n, tmp);
   scan_tile_offsets_kernel<<<1, 1024, 0, st>>>(tmp, ntiles, out + n);
-  scan_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, st>>>(in, n, tmp, out);
+  scan_apply_kernel<PAIR><<<(unsigned)ntiles, kScanThreads, 0, st>>>(in, n, tmp, out);
   TAPES_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -153,7 +163,22 @@ struct HashSet {
   uint32_t* vals = nullptr;
   uint32_t* ranks = nullptr;
   uint64_t mask = 0;  // capacity - 1 (capacity is a power of two)
+  // set by an insertion that gave up (the table was sized on a guess of the number of distinct keys
+  // and the guess was too small): the caller starts over with a larger table
+  unsigned long long* full = nullptr;
 };
+
+constexpr uint32_t kMaxProbes = 1u << 12;
+
+// Advances a probe; false when the insertion has to be abandoned.
+__device__ __forceinline__ bool hash_next_probe(const HashSet& hs, uint64_t& h, uint32_t& probes) {
+  h = (h + 1) & hs.mask;
+  if ((++probes & 63u) == 0 && (probes >= kMaxProbes || *(volatile unsigned long long*)hs.full)) {
+    *(volatile unsigned long long*)hs.full = 1ull;
+    return false;
+  }
+  return true;
+}
 
 __device__ __forceinline__ uint64_t hash_mix(uint64_t x) {
   x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
@@ -175,16 +200,36 @@ __device__ __forceinline__ bool hash_insert_warp(const HashSet& hs, bool active,
   uint64_t h = 0;
   if (leader) {
     h = hash_mix(key) & hs.mask;
+    uint32_t probes = 0;
     for (;;) {
       unsigned long long prev =
           atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey,
                     (unsigned long long)key);
       if (prev == kEmptyKey) { hs.vals[h] = val; fresh = true; break; }
       if (prev == key) break;
-      h = (h + 1) & hs.mask;
+      if (!hash_next_probe(hs, h, probes)) break;
     }
   }
   *slot = __shfl_sync(0xffffffffu, (uint32_t)h, leader_lane);  // capacity is at most 2^31
+  return fresh;
+}
+
+// The same without the warp vote, for key streams in which the lanes of a warp hold different keys
+// anyway (consecutive nodes of a level: their prefixes differ): every lane with a key inserts it.
+__device__ __forceinline__ bool hash_insert_lane(const HashSet& hs, bool active, uint64_t key, uint32_t val,
+                                                 uint32_t* slot) {
+  if (!active) { *slot = 0; return false; }
+  uint64_t h = hash_mix(key) & hs.mask;
+  bool fresh = false;
+  uint32_t probes = 0;
+  for (;;) {
+    unsigned long long prev =
+        atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+    if (prev == kEmptyKey) { hs.vals[h] = val; fresh = true; break; }
+    if (prev == key) break;
+    if (!hash_next_probe(hs, h, probes)) break;
+  }
+  *slot = (uint32_t)h;
   return fresh;
 }
 

@@ -338,6 +338,37 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
 
 
+@pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex3-copolymerization', 4, 7),
+                                             ('synthetic', 10, 5), ('synthetic', 2, 12)])
+def test_prefix_table_sizing_does_not_change_the_structure(mt, device, monkeypatch, tag, size_a, cl_k):
+  """The table that removes duplicate right-chain prefixes during the build is sized on a guess
+  (the previous level's count scaled by the level's growth); when the guess is too small the pass
+  starts over with the safe size.  The structure - and so dy/dt and the node weights, bit for bit -
+  must not depend on which happened: built with the safe size throughout, with the guess, and
+  with a table that is too small at every level (every level retried)."""
+  import torch
+  if tag == 'synthetic':
+    tag = f'hash-{size_a}-{cl_k}'
+    mt.register_rule_set(tag, size_a, configs.random_rule_set(size_a, 6, seed=cl_k))
+  p = torch.from_numpy(configs.markov_table(size_a, cl_k, 11)).cuda()
+  results = {}
+  for mode in ('0', '1', '2'):
+    monkeypatch.setenv('TAPES_HASH_GUESS', mode)
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+    model = device.DeviceModel(tag, cl_k)
+    info = model.info
+    results[mode] = (model.rhs(p).cpu().numpy(), model.node_weights(), info['n_nodes'], info['nnz'], info['hash_unique'])
+    if mode == '0':
+      assert info['hash_retries'] == 0
+    if mode == '2' and info['hash_unique'] > 1024 * info['n_levels']:  # some level has more prefixes than 1024 slots
+      assert info['hash_retries'] > 0, info
+  mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+  for mode in ('1', '2'):
+    assert results[mode][2:] == results['0'][2:], mode
+    assert numpy.array_equal(results[mode][0], results['0'][0]), mode
+    assert numpy.array_equal(results[mode][1], results['0'][1]), mode
+
+
 @pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex5-msrtf-machine', 5, 5),
                                              ('ex3-copolymerization', 4, 7), ('ex2-ferromagnetic-chain', 2, 7),
                                              ('synthetic', 10, 5), ('synthetic', 3, 6)])
