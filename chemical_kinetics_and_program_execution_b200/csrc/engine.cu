@@ -170,7 +170,8 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
                             uint64_t n_left_parents, HashSet hs, Frontier next, uint32_t* __restrict__ lp_gid,
                             uint32_t* __restrict__ lp_io, uint8_t* __restrict__ lp_len,
                             uint32_t* __restrict__ edge_row, uint32_t* __restrict__ edge_val,
-                            uint32_t* __restrict__ keyrank, uint4* __restrict__ gstat) {
+                            uint32_t* __restrict__ keyrank, uint4* __restrict__ gstat,
+                            unsigned long long* __restrict__ chain_starts) {
   const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= f.n) return;
   const uint8_t meta = f.meta[i];
@@ -178,6 +179,13 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
   const uint32_t io = f.io[i], ia = f.ia[i], seed = f.seed[i];
   const uint32_t gid = (uint32_t)(cur_base + i);
   const uint32_t lt = ltflag[i];
+  {  // left children of window length k - 1 start right chains: their number bounds the prefixes they add
+    // to the next level, which sizes that level's table (build, pass 1)
+    const unsigned active = __activemask();
+    const unsigned starters = __ballot_sync(active, (lt & 1u) && len == c.k - 2);
+    if (starters && (threadIdx.x & 31) == (unsigned)(__ffs(active) - 1))
+      atomicAdd(chain_starts, (unsigned long long)__popc(starters) * c.A);
+  }
   const uint64_t ranks = lt ? ltrank[i] : 0ull;  // low half: rank among the left parents, high half: among the stored terms
   if (lt & 1u) {
     const uint64_t r = (uint32_t)ranks;
@@ -1533,7 +1541,10 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   int hash_vote = -1;  // -1: by table shape
   int hash_guess = 1;  // 0: always 2 n slots; 1: sized on a guess; 2: start every level with the smallest table (tests of the retry)
   if (const char* e = std::getenv("TAPES_HASH_GUESS")) hash_guess = std::atoi(e);
-  uint64_t prev_n = 0, prev_groups = 0;
+  uint64_t prev_groups = 0;
+  unsigned long long chain_starts = 0;
+  bool chain_starts_known = false;
+  const bool build_trace = std::getenv("TAPES_BUILD_TRACE") != nullptr;
   if (const char* e = std::getenv("TAPES_HASH_VOTE")) hash_vote = std::atoi(e);
   if (const char* e = std::getenv("TAPES_MAX_NODES")) node_limit = std::min<uint64_t>(node_limit, std::strtoull(e, nullptr, 10));
   while (cur.n > 0) {
@@ -1541,24 +1552,26 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.stats.levels++;
     const uint64_t n = cur.n;
 
-    // pass 1: classify + hash-dedup of the right-chain prefixes.  The table is sized on a guess of the
-    // number of distinct prefixes - the previous level's, scaled by the growth of the level: most
-    // prefixes are reached from A parents, and a table of 2 n slots would be several times larger than
-    // needed, which costs in cleared and randomly touched memory - and the pass starts over with the
-    // safe size when the guess turns out too small.
+    // pass 1: classify + hash-dedup of the right-chain prefixes.  A table of 2 n slots is always enough
+    // but several times larger than needed (most prefixes are reached from A parents), which costs in
+    // cleared and randomly touched memory: the table is sized on an estimate of the number of distinct
+    // prefixes instead, and the pass starts over with the safe size when the estimate was too small.
     uint64_t cap_safe = 1024;
     while (cap_safe < 2 * n) cap_safe <<= 1;
     uint64_t cap = cap_safe;
     if (hash_guess == 2) cap = 1024;
-    else if (hash_guess && prev_n) {
-      const double guess = 1.25 * (double)prev_groups * ((double)n / (double)prev_n) + 4096.0;
+    else if (hash_guess && chain_starts_known) {
+      // nodes that start right chains bring one prefix each at most; the right children of the G groups of
+      // the level before bring A G prefixes that usually merge A to one (same prefix but for the first symbol)
+      const double guess = (double)chain_starts + 1.5 * (double)prev_groups + 4096.0;
       cap = 1024;
       while (cap < cap_safe && (double)cap < 2.0 * guess) cap <<= 1;
     }
     HashSet hs;
     uint32_t *ltflag = nullptr, *keyslot = nullptr;
     uint64_t *ltrank = nullptr, *scan_tmp = nullptr, *keys_a = nullptr;
-    unsigned long long* counters = nullptr;  // [0] unique keys, [1] irregular groups, [2] parents, [3] table too small
+    // [0] unique keys, [1] irregular groups, [2] parents, [3] table too small, [4] nodes of the next level that start right chains
+    unsigned long long* counters = nullptr;
     uint64_t NL = 0, NT = 0, NG = 0;
     for (;;) {
       s1.reset();
@@ -1566,7 +1579,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       const size_t i_ltflag = s1.want(n * 4), i_kflag = s1.want(n * 4);
       const size_t i_ltrank = s1.want((n + 1) * 8);
       const size_t i_scan = s1.want(scan_tmp_elems(std::max<uint64_t>(n, 256ull * 1184)) * 8);
-      const size_t i_unique = s1.want(n * 8), i_counters = s1.want(32);
+      const size_t i_unique = s1.want(n * 8), i_counters = s1.want(64);
       s1.commit();
       hs.keys = s1.at<uint64_t>(i_keys); hs.vals = s1.at<uint32_t>(i_vals); hs.ranks = s1.at<uint32_t>(i_ranks);
       hs.mask = cap - 1;
@@ -1578,7 +1591,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       counters = s1.at<unsigned long long>(i_counters);
       hs.full = counters + 3;
       TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
-      TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 32, st));
+      TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64, st));
       // lanes of a warp hold different prefixes unless the level is tiny or the table short (M < 32):
       // the warp vote that merges equal keys before the insertion only pays there
       if (hash_vote < 0 ? c.M < 32 : hash_vote)
@@ -1592,11 +1605,16 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], counters, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
       NL = (uint32_t)h_tot[0]; NT = 2 * (h_tot[0] >> 32); NG = h_tot[2];  // NT counts edges, two per stored term
+      if (build_trace)
+        std::fprintf(stderr, "[tapes] level %d: %llu nodes, %llu left parents, %llu prefixes, table %llu slots%s\n",
+                     (int)m.stats.levels, (unsigned long long)n, (unsigned long long)NL, (unsigned long long)NG,
+                     (unsigned long long)cap, (cap != cap_safe && (h_tot[1] != 0 || NG * 10 > cap * 7)) ? " (too small)" : "");
       if (cap == cap_safe || (h_tot[1] == 0 && NG * 10 <= cap * 7)) break;
       cap = cap_safe;  // the guess was too small: the slots handed out are not to be trusted
       m.stats.hash_retries++;
     }
-    prev_n = n; prev_groups = NG;
+    prev_groups = NG;
+    chain_starts_known = false;  // read below when this level has prefix groups; otherwise the next table gets the safe size
     if ((NL + NG) * (uint64_t)m.A >= 0xffffffffull) throw TooLarge("a level of the extension forest exceeds 2^32 nodes");
 
     // pass 2: children, parent records, flux edges
@@ -1644,7 +1662,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     }
     emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, ltflag, keyslot, ltrank,
                                                           NL, hs, next, next_level.lp_gid, next_level.lp_io,
-                                                          next_level.lp_len, ec.row, ec.val, keyrank, gstat);
+                                                          next_level.lp_len, ec.row, ec.val, keyrank, gstat, counters + 4);
     if (NG) {
       // parent lists of the prefix groups: as progressions (first, stride, count) when every list is
       // one - found from the extremes and counts emit_kernel collected, then checked parent by parent
@@ -1657,7 +1675,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
           keyrank, n, cur_level.base, next_level.g_first, next_level.g_stride, counters);
       unsigned long long h_counts[2] = {0, 0};  // irregular groups or parents off their progression, parents
       TAPES_CUDA_CHECK(cudaMemcpyAsync(h_counts, counters + 1, 16, cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(&chain_starts, counters + 4, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      chain_starts_known = true;
       const uint64_t n_par = h_counts[1];
       next_level.n_group_parents = n_par;
       if (h_counts[0] != 0 || std::getenv("TAPES_KEEP_PARENT_LISTS")) {

@@ -223,10 +223,14 @@ __device__ __forceinline__ bool hash_insert_lane(const HashSet& hs, bool active,
   bool fresh = false;
   uint32_t probes = 0;
   for (;;) {
-    unsigned long long prev =
-        atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
-    if (prev == kEmptyKey) { hs.vals[h] = val; fresh = true; break; }
-    if (prev == key) break;
+    // most keys are in the table already (a prefix is reached from several parents): look before
+    // the atomic.  A slot is written once, so a key read here is final; "empty" is settled by the CAS.
+    unsigned long long seen = __ldcg((const unsigned long long*)&hs.keys[h]);
+    if (seen == kEmptyKey) {
+      seen = atomicCAS((unsigned long long*)&hs.keys[h], (unsigned long long)kEmptyKey, (unsigned long long)key);
+      if (seen == kEmptyKey) { hs.vals[h] = val; fresh = true; break; }
+    }
+    if (seen == key) break;
     if (!hash_next_probe(hs, h, probes)) break;
   }
   *slot = (uint32_t)h;

@@ -341,9 +341,9 @@ def test_plane_kernel_and_left_ratio_table_are_bit_identical(mt, device, oracle,
 @pytest.mark.parametrize('tag,size_a,cl_k', [('ex4-chemical-turing', 9, 5), ('ex3-copolymerization', 4, 7),
                                              ('synthetic', 10, 5), ('synthetic', 2, 12)])
 def test_prefix_table_sizing_does_not_change_the_structure(mt, device, monkeypatch, tag, size_a, cl_k):
-  """The table that removes duplicate right-chain prefixes during the build is sized on a guess
-  (the previous level's count scaled by the level's growth); when the guess is too small the pass
-  starts over with the safe size.  The structure - and so dy/dt and the node weights, bit for bit -
+  """The table that removes duplicate right-chain prefixes during the build is sized on an estimate
+  (the nodes that start right chains plus 1.5 times the previous level's prefixes); when the estimate
+  is too small the pass starts over with the safe size.  The structure - and so dy/dt and the node weights, bit for bit -
   must not depend on which happened: built with the safe size throughout, with the guess, and
   with a table that is too small at every level (every level retried)."""
   import torch
