@@ -1539,6 +1539,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   uint64_t total_terms = 0, total_edges = 0;
   uint64_t node_limit = 0x7fffffffull;  // node id + sign bit in 32 bits; lowered by tests of the splitting
   int hash_vote = -1;  // -1: by table shape
+  int hash_run_bits = 2;
+  if (const char* e = std::getenv("TAPES_HASH_RUN_BITS")) hash_run_bits = std::max(0, std::min(8, std::atoi(e)));
   int hash_guess = 1;  // 0: always 2 n slots; 1: sized on a guess; 2: start every level with the smallest table (tests of the retry)
   if (const char* e = std::getenv("TAPES_HASH_GUESS")) hash_guess = std::atoi(e);
   uint64_t prev_groups = 0;
@@ -1590,6 +1592,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       keys_a = s1.at<uint64_t>(i_unique);
       counters = s1.at<unsigned long long>(i_counters);
       hs.full = counters + 3;
+      hs.run_bits = hash_run_bits;
       TAPES_CUDA_CHECK(cudaMemsetAsync(hs.keys, 0xff, cap * 8, st));
       TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64, st));
       // lanes of a warp hold different prefixes unless the level is tiny or the table short (M < 32):

@@ -166,6 +166,7 @@ struct HashSet {
   // set by an insertion that gave up (the table was sized on a guess of the number of distinct keys
   // and the guess was too small): the caller starts over with a larger table
   unsigned long long* full = nullptr;
+  int run_bits = 2;  // keys that differ in this many low bits only are neighbours in the table (hash_home)
 };
 
 constexpr uint32_t kMaxProbes = 1u << 12;
@@ -187,6 +188,13 @@ __device__ __forceinline__ uint64_t hash_mix(uint64_t x) {
   return x;
 }
 
+// Home slot of a key.  Keys that differ in their lowest bits only - the prefixes of consecutive nodes
+// of a level - get neighbouring slots, so that the probes of a warp share DRAM sectors (a sector holds
+// 4 keys) instead of touching 32 of them; the rest of the key is mixed.
+__device__ __forceinline__ uint64_t hash_home(const HashSet& hs, uint64_t key) {
+  return ((hash_mix(key >> hs.run_bits) << hs.run_bits) | (key & ((1ull << hs.run_bits) - 1))) & hs.mask;
+}
+
 // All 32 lanes must call this; `active` says whether the lane has a key.  Returns true in the
 // lane that claimed an empty slot for a key not seen before; *slot receives the slot of the lane's
 // key (every active lane, so that later passes need not probe again).
@@ -199,7 +207,7 @@ __device__ __forceinline__ bool hash_insert_warp(const HashSet& hs, bool active,
   bool fresh = false;
   uint64_t h = 0;
   if (leader) {
-    h = hash_mix(key) & hs.mask;
+    h = hash_home(hs, key);
     uint32_t probes = 0;
     for (;;) {
       unsigned long long prev =
@@ -219,7 +227,7 @@ __device__ __forceinline__ bool hash_insert_warp(const HashSet& hs, bool active,
 __device__ __forceinline__ bool hash_insert_lane(const HashSet& hs, bool active, uint64_t key, uint32_t val,
                                                  uint32_t* slot) {
   if (!active) { *slot = 0; return false; }
-  uint64_t h = hash_mix(key) & hs.mask;
+  uint64_t h = hash_home(hs, key);
   bool fresh = false;
   uint32_t probes = 0;
   for (;;) {
@@ -239,7 +247,7 @@ __device__ __forceinline__ bool hash_insert_lane(const HashSet& hs, bool active,
 
 // Slot of a key that is known to be present.
 __device__ __forceinline__ uint64_t hash_slot(const HashSet& hs, uint64_t key) {
-  uint64_t h = hash_mix(key) & hs.mask;
+  uint64_t h = hash_home(hs, key);
   while (hs.keys[h] != key) h = (h + 1) & hs.mask;
   return h;
 }
