@@ -252,13 +252,8 @@ __global__ void derive_progressions_kernel(const uint4* __restrict__ gstat, uint
     bad = n > 1 && (d == 0 || span % (n - 1) != 0);
     first[g] = lo; stride[g] = d; count[g] = n;
   }
-  unsigned long long parents = n;
-  for (int o = 16; o > 0; o >>= 1) parents += __shfl_down_sync(0xffffffffu, parents, o);
-  const unsigned bad_lanes = __ballot_sync(0xffffffffu, bad);
-  if ((threadIdx.x & 31) == 0) {
-    if (parents) atomicAdd(&facts[2], parents);
-    if (bad_lanes) atomicAdd(&facts[1], (unsigned long long)__popc(bad_lanes));
-  }
+  block_add(n, &facts[2]);
+  block_add(bad ? 1ull : 0ull, &facts[1]);
 }
 
 // Every parent must sit on its group's progression; together with distinct ids, matching extremes
@@ -480,7 +475,7 @@ __global__ void mark_owned_parents_kernel(const uint32_t* __restrict__ first, co
 __global__ void check_consumed_kernel(const uint32_t* __restrict__ consumed, uint64_t n_prev_groups, uint32_t A,
                                       unsigned long long* __restrict__ partial) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < n_prev_groups && consumed[g] != 0 && consumed[g] != A) atomicAdd(partial, 1ull);
+  block_add((g < n_prev_groups && consumed[g] != 0 && consumed[g] != A) ? 1ull : 0ull, partial);
 }
 
 __global__ void clear_owned_parents_kernel(uint32_t* __restrict__ count, uint64_t n_groups) {
@@ -491,10 +486,9 @@ __global__ void clear_owned_parents_kernel(uint32_t* __restrict__ count, uint64_
 __global__ void mark_deferred_kernel(uint32_t* __restrict__ prev_count, const uint32_t* __restrict__ consumed,
                                      uint64_t n_prev_groups, uint32_t A, unsigned long long* __restrict__ n_deferred) {
   const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g < n_prev_groups && consumed[g] == A) {
-    prev_count[g] |= Level::kChildrenDeferred;
-    atomicAdd(n_deferred, 1ull);
-  }
+  const bool deferred = g < n_prev_groups && consumed[g] == A;
+  if (deferred) prev_count[g] |= Level::kChildrenDeferred;
+  block_add(deferred ? 1ull : 0ull, n_deferred);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -252,6 +252,18 @@ __device__ __forceinline__ uint64_t hash_slot(const HashSet& hs, uint64_t key) {
   return h;
 }
 
+// Adds the block's sum of v to *counter with one global atomic per block (a counter that every warp
+// of a large grid adds to is a serial bottleneck in L2).  All threads of the block must call this.
+__device__ __forceinline__ void block_add(unsigned long long v, unsigned long long* __restrict__ counter) {
+  __shared__ unsigned long long block_sum;
+  if (threadIdx.x == 0) block_sum = 0;
+  __syncthreads();
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(&block_sum, v);
+  __syncthreads();
+  if (threadIdx.x == 0 && block_sum) atomicAdd(counter, block_sum);
+}
+
 // Block-wide compaction: every thread with `take` appends `item` to `list`; one atomic per block
 // on the shared counter.  All threads of the block must call this.
 __device__ __forceinline__ void block_append_u64(bool take, uint64_t item, uint64_t* __restrict__ list,
