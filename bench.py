@@ -102,14 +102,17 @@ def spmv_bytes(nnz, n):
 
 
 def level_bytes(info):
-  """Algorithmic bytes of the level evaluation of one step (plane_kernel + level_kernel launches and
-  prefix_sums_kernel), every access counted as if it came from DRAM: per node one
-  8-byte read of the table or ratio; one 8-byte weight write per node that is written (the right children
-  of groups in regular blocks are not, unless a later level reads them); 25 B per left-parent record
-  (ids, length, parent weight, short marginal); per prefix group 16 B of records outside regular blocks
-  (48 B per 256 groups inside), its sum written (8 B), read by the level that evaluates its children (8 B)
-  and by prefix_sums_kernel with its number (12 B); 8 B per parent weight that is gathered; 16 B per
-  prefix for the per-prefix sums."""
+  """Compulsory bytes of the level evaluation of one step (plane_kernel + level_kernel launches and
+  prefix_sums_kernel): what one launch must move if every byte it touches came
+  from DRAM exactly once.  Per level the table / ratio entries its nodes read, each entry once however
+  many nodes (of different seeds) read it: min(nodes of the level, states) * 8 B, summed over the levels
+  (model info `distinct_table_reads`); one 8-byte weight write per node that is written (the right
+  children of groups in regular blocks are not, unless a later level reads them); 25 B per left-parent
+  record (ids, length, parent weight, short marginal); per prefix group 16 B of records outside regular
+  blocks (48 B per 256 groups inside), its sum written (8 B), read by the level that evaluates its
+  children (8 B) and by prefix_sums_kernel with its number (12 B); 8 B per parent weight that is
+  gathered (a node is the parent of one group); 16 B per prefix for the per-prefix sums.  The real
+  traffic is above this by the L2 misses of repeated reads."""
   nodes, size_a = info['n_nodes'], max(info['alphabet'], 1)
   gathered = info['hash_inserts'] - info.get('owned_parents', 0)
   plane = info.get('plane_groups', 0)  # 48 bytes per block of 256 such groups instead of 16 per group
@@ -117,23 +120,25 @@ def level_bytes(info):
   unwritten = 0 if info.get('materialize_right', 1) else plane * size_a
   per_group = 16.0 * (groups - plane) + 48.0 * plane / 256
   sums = 8.0 * groups + 8.0 * info.get('deferred_groups', 0) + 12.0 * groups + 16.0 * prefixes
-  return 8.0 * nodes + 8.0 * (nodes - unwritten) + 25.0 * info.get('left_parents', 0) + per_group + 8.0 * gathered + sums
+  table_reads = 8.0 * info.get('distinct_table_reads', nodes)
+  return table_reads + 8.0 * (nodes - unwritten) + 25.0 * info.get('left_parents', 0) + per_group + 8.0 * gathered + sums
 
 
 def flux_format_bytes(info, n):
-  """Bytes the product kernel must move at the least in the shipped format (sliced flux structure of
-  the stored entries + per-group flux of the right children, csrc/flux.cu, csrc/flux_device.cuh): slice
-  pointers and run counts, every structure word once, the weight of every stored term once (a term is
-  read by its source and its destination row; the second read is credited to L2); per prefix group its
-  inflow list entry (8 B), its sum (8 B) and one ratio per child (8 A B); per state its own ratio (8 B)
-  for the outflow and the result (8 B); one outflow sum per prefix.  Below the real traffic by what L2
-  misses of the second reads and by the padding of the columns, so `frac` computed from it is a lower
-  bound of the share of the HBM roofline."""
+  """Compulsory bytes of the product kernel in the shipped format (sliced flux structure of the stored
+  entries + per-group flux of the right children, csrc/flux.cu, csrc/flux_device.cuh), every byte
+  counted once: slice pointers and run counts, every structure word (column padding included: the
+  kernel has to read it), the weight of every stored term once (a term is read by its source and its
+  destination row; the second read is credited to L2); per prefix group its inflow list entry (8 B)
+  and its sum (8 B); the ratio table once (8 B per state: the outflow reads a state's own ratio, the
+  inflows read ratios of other prefixes - repeats credited to L2); per prefix the list offset and the
+  outflow sum (16 B); the result (8 B per state).  The real traffic is above this by the L2 misses
+  of the repeated reads."""
   slices, size_a = info.get('n_slices', (n + 31) // 32), max(info.get('alphabet', 1), 1)
   grouped = info.get('nnz_stored', info['nnz']) < info['nnz']
   groups = info.get('hash_unique', 0) if grouped else 0
   right_children = groups * size_a
-  lists = (16.0 + 8.0 * size_a) * groups + (8.0 * n + 8.0 * (n // size_a) if grouped else 0.0)
+  lists = 16.0 * groups + (8.0 * n + 16.0 * (n // size_a) if grouped else 0.0)
   return (8.0 * (slices + 1) + 4.0 * slices + 4.0 * info.get('slice_words', 0) + 8.0 * (info['n_terms'] - right_children)
           + lists + 8.0 * n)
 
@@ -629,8 +634,10 @@ def run_b200(args):
                   dram_frac=(traffic / (phase[2] * 1e-3) / 1e9 / peak) if traffic else None,
                   peak_source=peak_src,
                   algorithmic_bytes_per_launch=flux_bytes,
-                  algorithmic_bytes_are=('the sliced format\'s own minimum: slice pointers + structure words + one 8-byte '
-                                         'weight per flux term + the result (DESIGN.md section 4)' if sliced else
+                  algorithmic_bytes_are=('compulsory bytes of the shipped format, each byte once: slice pointers + structure '
+                                         'words + one 8-byte weight per stored term + per prefix group its list entry and sum '
+                                         '+ ratio table + result (bench.py flux_format_bytes, DESIGN.md section 4); `traffic` '
+                                         'above it = L2 misses of repeated reads' if sliced else
                                          'plain CSR: 12 * nnz + 16 * n'),
                   csr_equivalent_gbs=spmv_bytes(info['nnz'], n) / (phase[2] * 1e-3) / 1e9,
                   kernel_ms=float(phase[2]),

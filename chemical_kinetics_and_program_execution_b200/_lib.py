@@ -175,7 +175,7 @@ MODEL_INFO_FIELDS = (
     'run_entries', 'column_entries', 'column_slots', 'min_run_lanes', 'level_unroll',
     'irregular_levels', 'left_parents', 'flux_unroll', 'owned_parents', 'deferred_groups', 'structures',
     'interleaved_levels', 'plane_groups', 'ratio_tables', 'nnz_stored', 'materialize_right',
-    'hash_retries')
+    'hash_retries', 'distinct_table_reads')
 
 
 def model_info(model):

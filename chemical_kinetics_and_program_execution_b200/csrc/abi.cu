@@ -478,17 +478,22 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
   std::shared_ptr<tapes::Model> mp = resolve(model);
   if (!mp) return 0;
   const tapes::Model& head = *mp;
-  const int kFields = 37;
+  const int kFields = 38;
   // sizes add up over the parts of a composite model; facts shared by all parts come from the first
   static const bool adds[kFields] = {false, true, true, true, false, false, true, true, false, false, true, true,
                                      true, false, false, false, false, false, true, true, true, true,
                                      true, false, false, true, true, false, true, true, true, true,
-                                     true, false, true, false, true};
+                                     true, false, true, false, true, true};
   int64_t total[kFields] = {};
   for (size_t part = 0; part <= head.more.size(); ++part) {
     const tapes::Model& m = part == 0 ? head : *head.more[part - 1];
     int64_t interleaved = 0;
-    for (const tapes::Level& lv : m.levels) interleaved += lv.block_order ? 1 : 0;
+    int64_t distinct_reads = 0;  // table / ratio entries a level can read at most once each: min(nodes of the level, states)
+    for (const tapes::Level& lv : m.levels) {
+      interleaved += lv.block_order ? 1 : 0;
+      const uint64_t level_nodes = (uint64_t)lv.n_roots + ((uint64_t)lv.n_left + lv.n_groups) * (uint64_t)m.A;
+      distinct_reads += (int64_t)std::min<uint64_t>(level_nodes, m.n_states);
+    }
     const int64_t v[kFields] = {(int64_t)m.n_states, (int64_t)m.n_nodes, (int64_t)m.nnz, (int64_t)m.n_rules,
                                 (int64_t)m.levels.size(), 0, m.stats.terms, m.stats.sum_nodes,
                                 m.stats.worlds_walked, m.stats.leaf_worlds, m.stats.seeds, m.stats.hash_inserts,
@@ -499,7 +504,8 @@ int tapes_model_info(void* model, int64_t* out, int capacity) {
                                 m.stats.irregular_levels, m.stats.left_parents, (int64_t)m.flux_unroll,
                                 m.stats.owned_parents, m.stats.deferred_groups, 1, interleaved,
                                 m.stats.plane_groups, (int64_t)((m.ratio_right ? 1 : 0) + (m.ratio_left ? 1 : 0)),
-                                (int64_t)m.nnz_stored, (int64_t)m.materialize_right, m.stats.hash_retries};
+                                (int64_t)m.nnz_stored, (int64_t)m.materialize_right, m.stats.hash_retries,
+                                distinct_reads};
     for (int i = 0; i < kFields; ++i) {
       if (part == 0) total[i] = v[i];
       else if (adds[i]) total[i] += v[i];

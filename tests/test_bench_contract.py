@@ -83,7 +83,12 @@ def test_byte_counts_and_reference_equivalent_work():
   info = dict(n_slices=2, slice_words=100, n_terms=30, nnz=60)
   assert bench.flux_format_bytes(info, 40) == 8 * 3 + 4 * 2 + 4 * 100 + 8 * 30 + 8 * 40
   grouped = dict(info, nnz_stored=20, hash_unique=2, alphabet=10)
-  assert bench.flux_format_bytes(grouped, 40) == 8 * 3 + 4 * 2 + 4 * 100 + 8 * 10 + (16 + 80) * 2 + 8 * 40 + 8 * 4 + 8 * 40
+  # grouped right children: list entry + sum per group, the ratio table once, offset + outflow sum per prefix
+  assert bench.flux_format_bytes(grouped, 40) == 8 * 3 + 4 * 2 + 4 * 100 + 8 * 10 + 16 * 2 + 8 * 40 + 16 * 4 + 8 * 40
+  levels = dict(n_nodes=1000, alphabet=10, hash_inserts=300, owned_parents=100, plane_groups=0, hash_unique=50, n_states=100,
+                materialize_right=1, left_parents=20, deferred_groups=5, distinct_table_reads=400)
+  assert bench.level_bytes(levels) == 8 * 400 + 8 * 1000 + 25 * 20 + 16 * 50 + 8 * 200 + (8 * 50 + 8 * 5 + 12 * 50 + 16 * 10)
+  assert bench.level_bytes(dict(levels, distinct_table_reads=1000)) - bench.level_bytes(levels) == 8 * 600
   work = bench.literal_vs_merged(types.SimpleNamespace(size_a=4, cl_k=7), configs.random_rule_set(4, 6, seed=2))
   rows = work['counted']
   assert rows[0]['cl_k'] == 2 and all(r['literal_nodes'] >= r['merged_nodes'] for r in rows)
