@@ -1104,17 +1104,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
   const uint32_t gtid = cta * kFusedThreads + threadIdx.x, gthreads = n_cta * kFusedThreads;
   const double* p = t.p;
   // marginal tables, longest first (tm.scm:378-384: j ascending from an exact 0)
-  uint64_t n_out = c.M;
+  // (32-bit index arithmetic throughout: a 64-bit division per phase and thread is a third of a phase
+  // of a tiny problem, profiles/r02_aj_small_kernel_phase_cycles.txt)
   for (int L = c.k - 1; L >= 0; --L) {
     const double* src = (L + 1 == c.k) ? p : a.marg + t.off[L + 1];
     double* dst = a.marg + t.off[L];
-    for (uint64_t i = gtid; i < n_out; i += gthreads) {
+    const uint32_t n_out = c.pw[L];  // A^L
+    for (uint32_t i = gtid; i < n_out; i += gthreads) {
       const double* s = src + i * c.A;
       double total = 0.0;
       for (uint32_t j = 0; j < c.A; ++j) total = total + s[j];
       dst[i] = total;
     }
-    n_out /= c.A;
     phase_barrier();
   }
   // leaf-world probabilities and the right-extension ratios
@@ -1122,7 +1123,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
     a.rule_w[r] = rule_weight(t, r, a.rule_ptr, a.step_kind, a.step_len, a.step_long, a.step_short, a.step_prob);
   if (a.ratio_right) {
     const double* short_table = a.marg + t.off[c.k - 1];
-    for (uint64_t i = gtid; i < a.n_states; i += gthreads) a.ratio_right[i] = extension_ratio(p[i], short_table[i / c.A]);
+    const uint32_t n32 = (uint32_t)a.n_states;
+    for (uint32_t i = gtid; i < n32; i += gthreads) a.ratio_right[i] = extension_ratio(p[i], short_table[i / c.A]);
   }
   phase_barrier();
   // forest levels over virtual blocks of 256 threads
@@ -1148,7 +1150,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rhs_kernel(Tables t, C
   }
   // what leaves the rows through right children: one sum per prefix (prefix_sums_kernel)
   if (a.out_sum) {
-    for (uint64_t q = gtid; q < a.n_prefixes; q += gthreads) {
+    const uint32_t n_prefixes = (uint32_t)a.n_prefixes;
+    for (uint32_t q = gtid; q < n_prefixes; q += gthreads) {
       double total = 0.0;
       for (uint64_t e = a.out_ptr[q]; e < a.out_ptr[q + 1]; ++e) total += a.g_total_all[a.out_ids[e]];
       a.out_sum[q] = total;
