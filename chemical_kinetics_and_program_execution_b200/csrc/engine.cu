@@ -1609,6 +1609,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
         std::fprintf(stderr, "[tapes] level %d: %llu nodes, %llu left parents, %llu prefixes, table %llu slots%s\n",
                      (int)m.stats.levels, (unsigned long long)n, (unsigned long long)NL, (unsigned long long)NG,
                      (unsigned long long)cap, (cap != cap_safe && (h_tot[1] != 0 || NG * 10 > cap * 7)) ? " (too small)" : "");
+      if (cap == cap_safe && h_tot[1] != 0)  // cannot happen with 2 n slots for at most n keys unless probing degenerates
+        throw std::runtime_error("the prefix table of the expansion overflowed at its safe size");
       if (cap == cap_safe || (h_tot[1] == 0 && NG * 10 <= cap * 7)) break;
       cap = cap_safe;  // the guess was too small: the slots handed out are not to be trusted
       m.stats.hash_retries++;
