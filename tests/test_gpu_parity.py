@@ -223,6 +223,75 @@ def test_python_programs(mt, oracle):
   assert not numpy.array_equal(before, after)
 
 
+def random_program(seed, size_a):
+  """A random tape program as a Python body: a decision tree over reads (cells -2..2 of either tape),
+  writes and weighted choices, at most four reads deep, that depends on nothing but what it reads and
+  chooses (the tree is drawn once, here; the body only walks it)."""
+  rng = numpy.random.default_rng(seed)
+
+  def grow(depth, reads):
+    kind = rng.choice(['read', 'pick', 'write', 'end'], p=[0.45, 0.15, 0.3, 0.1] if depth < 6 else [0, 0, 0.5, 0.5])
+    if kind == 'read' and reads >= 4:
+      kind = 'write'
+    if kind == 'read':
+      return ('read', bool(rng.integers(2)), int(rng.integers(-2, 3)), [grow(depth + 1, reads + 1) for _ in range(size_a)])
+    if kind == 'pick':
+      ways = int(rng.integers(2, 4))
+      return ('pick', [float(w) for w in rng.uniform(0.1, 1.0, ways)], [grow(depth + 1, reads) for _ in range(ways)])
+    if kind == 'write':
+      return ('write', bool(rng.integers(2)), int(rng.integers(-2, 3)), int(rng.integers(size_a)), grow(depth + 1, reads))
+    return ('end',)
+
+  tree = grow(0, 0)
+
+  def body(tape):
+    node = tree
+    while node[0] != 'end':
+      if node[0] == 'read':
+        node = node[3][tape.get(node[1], node[2])]
+      elif node[0] == 'pick':
+        node = node[2][tape.choose(node[1])]
+      else:
+        tape.set(node[1], node[2], node[3])
+        node = node[4]
+  return body
+
+
+@pytest.mark.parametrize('seed', range(32))
+def test_random_programs_match_the_oracle(mt, oracle, seed):
+  """Random decision trees over the reference's three primitives (tape-get, tape-set!, choose,
+  gambit_macros.scm:99-125) - reads after writes, writes to cells never read, several writes to one
+  cell, choices before and after reads - through register_program, for windows shorter and longer than
+  the cells a program touches: dy/dt against the oracle interpreting the same tree, both modes."""
+  from chemical_kinetics_and_program_execution_b200 import programs
+  rng = numpy.random.default_rng(5000 + seed)
+  size_a = int(rng.integers(2, 4))
+  body = random_program(seed, size_a)
+  tag = f'fuzz-program-{seed}'
+  mt.register_program(tag, size_a, body)
+  oracle.register_program(tag, size_a, programs.trace(body, size_a))
+  for cl_k in sorted(set(min(int(k), 6 if size_a == 3 else 7) for k in rng.integers(1, 8, size=3))):
+    f = mt.get_dy_dt(tag=tag, size_a=size_a, cl_k=cl_k)
+    full = configs.markov_table(size_a, cl_k, seed)
+    sparse = full * (rng.random(full.shape) > 0.35)
+    sparse = sparse / sparse.sum() if sparse.sum() > 0 else full
+    for p in (full, sparse):
+      got = f(p, 0.0)
+      src, dst, w = oracle.terms(tag, cl_k, p, mode=oracle.MERGED)
+      gross = numpy.zeros(p.size)
+      numpy.add.at(gross, src, abs(w))
+      numpy.add.at(gross, dst, abs(w))
+      # deep trees put up to 3 * 10^4 terms on one state (seed 7, k = 6): the rounding of a sum in another
+      # order grows like the square root of their number (the oracle's own two modes differ by 4.6e-14 of
+      # the gross flux there), so the tolerance does beyond 100 terms per state
+      scale = max(1.0, (len(w) / p.size / 100.0) ** 0.5)
+      assert_rhs_close(got, oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.MERGED), gross, tolerance=1e-14 * scale)
+      if len(w) <= 3_000_000:  # the literal recursion takes half a minute beyond
+        assert_rhs_close(got, oracle.compute_dy_dt(tag, cl_k, p, mode=oracle.LITERAL), gross, tolerance=3e-14 * scale)
+      assert abs(got.sum()) <= 1e-14 * scale * gross.sum() + 1e-300
+    mt.u_lib.tapes_release_model(tag.encode(), cl_k)
+
+
 def test_graph_replay_is_bit_identical(mt, device, p0_fixtures):
   """Small problems replay the weight kernels from a CUDA graph captured per input pointer (host
   entry point, stepper, any non-default stream); launching them one by one gives the same bits."""
