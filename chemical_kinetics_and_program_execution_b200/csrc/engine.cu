@@ -116,12 +116,19 @@ struct Frontier {
   uint32_t* seed = nullptr;  // which (leaf world, tape) the node descends from
   uint8_t* meta = nullptr;   // kind << 6 | window length
   uint8_t* flags = nullptr;  // FL_*
+  // A level that consists of the right children of prefix groups only (every level after the last left
+  // extension: right children extend to the right only) is not materialised: node i is child i % A of group
+  // i / A, with the window indices prefix * A + x and adjusted prefix * A + x, full length, FL_TERM | FL_RIGHT.
+  bool right_only = false;
+  const uint32_t* g_prefix = nullptr;    // [n / A] of this level's groups
+  const uint32_t* g_adjusted = nullptr;
+  const uint32_t* g_seed = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------
 // Expansion pass 1: classify every frontier node and hash-insert right-chain prefixes.
 // ---------------------------------------------------------------------------------------------
-template <bool VOTE>
+template <bool VOTE, bool RIGHT_ONLY>
 __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c, HashSet hs,
                                                             uint32_t* __restrict__ ltflag,
                                                             uint32_t* __restrict__ keyslot, uint64_t* __restrict__ unique,
@@ -131,7 +138,13 @@ __global__ void __launch_bounds__(kThreads) classify_kernel(Frontier f, Consts c
   bool haskey = false;
   uint64_t key = 0;
   uint32_t pa = 0;
-  if (valid) {
+  if (valid && RIGHT_ONLY) {  // no left children, no stored terms: nothing to rank (ltflag is not written)
+    const uint32_t g = (uint32_t)i / c.A, x = (uint32_t)i - g * c.A;
+    const uint32_t po = (f.g_prefix[g] * c.A + x) % c.M;
+    pa = (f.g_adjusted[g] * c.A + x) % c.M;
+    haskey = po != pa;
+    key = ((uint64_t)f.g_seed[g] << 32) | po;
+  } else if (valid) {
     const uint8_t meta = f.meta[i], fl = f.flags[i];
     const int len = meta & 63;
     const uint32_t io = f.io[i], ia = f.ia[i];
@@ -235,6 +248,23 @@ __global__ void emit_kernel(Frontier f, Consts c, uint64_t cur_base, const uint3
   }
 }
 
+// emit_kernel for a level of right children only: nothing but the group each node is a parent of.
+__global__ void emit_right_only_kernel(uint64_t n, uint64_t cur_base, const uint32_t* __restrict__ keyslot, HashSet hs,
+                                       uint32_t* __restrict__ keyrank, uint4* __restrict__ gstat) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t slot = keyslot[i];
+  if (slot != kNoRank) {
+    const uint32_t g = hs.ranks[slot], gid = (uint32_t)(cur_base + i);
+    keyrank[i] = g;
+    atomicMin(&gstat[g].x, gid);
+    atomicMin(&gstat[g].y, ~gid);
+    atomicSub(&gstat[g].z, 1u);
+  } else {
+    keyrank[i] = kNoRank;
+  }
+}
+
 // (first, stride, count) of every group from the extremes of its parent ids; a group whose extremes
 // cannot belong to a progression of `count` ids is counted as irregular.  facts: [1] irregular
 // groups, [2] parents of all groups.
@@ -280,7 +310,8 @@ __global__ void verify_progressions_kernel(const uint32_t* __restrict__ keyrank,
 __global__ void __launch_bounds__(kThreads) emit_groups_kernel(const uint64_t* __restrict__ sorted_keys, uint32_t n_keys,
                                                                HashSet hs, Consts c, Frontier next, uint64_t first,
                                                                uint32_t* __restrict__ g_prefix,
-                                                               uint32_t* __restrict__ g_adjusted) {
+                                                               uint32_t* __restrict__ g_adjusted,
+                                                               uint32_t* __restrict__ g_seed) {
   __shared__ uint32_t s_po[kThreads], s_pa[kThreads], s_seed[kThreads];
   const uint32_t g0 = blockIdx.x * kThreads, g = g0 + threadIdx.x;
   if (g < n_keys) {
@@ -290,8 +321,10 @@ __global__ void __launch_bounds__(kThreads) emit_groups_kernel(const uint64_t* _
     hs.ranks[slot] = g;
     g_prefix[g] = po;
     g_adjusted[g] = pa;
+    if (g_seed) g_seed[g] = (uint32_t)(key >> 32);
     s_po[threadIdx.x] = po; s_pa[threadIdx.x] = pa; s_seed[threadIdx.x] = (uint32_t)(key >> 32);
   }
+  if (g_seed) return;  // the next level is not materialised (Frontier::right_only)
   __syncthreads();
   const uint32_t groups = min((uint32_t)kThreads, n_keys - g0), children = groups * c.A;
   const uint8_t nmeta = (uint8_t)((NODE_RIGHT << 6) | c.k);
@@ -1536,6 +1569,8 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   uint64_t total_terms = 0, total_edges = 0;
   uint64_t node_limit = 0x7fffffffull;  // node id + sign bit in 32 bits; lowered by tests of the splitting
   int hash_vote = -1;  // -1: by table shape
+  bool virtual_right_levels = true;  // TAPES_VIRTUAL_RIGHT_LEVELS=0: write every level out (A/B and tests)
+  if (const char* e = std::getenv("TAPES_VIRTUAL_RIGHT_LEVELS")) virtual_right_levels = std::atoi(e) != 0;
   int hash_run_bits = 2;
   if (const char* e = std::getenv("TAPES_HASH_RUN_BITS")) hash_run_bits = std::max(0, std::min(8, std::atoi(e)));
   int hash_guess = 1;  // 0: always 2 n slots; 1: sized on a guess; 2: start every level with the smallest table (tests of the retry)
@@ -1575,8 +1610,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     for (;;) {
       s1.reset();
       const size_t i_keys = s1.want(cap * 8), i_vals = s1.want(cap * 4), i_ranks = s1.want(cap * 4);
-      const size_t i_ltflag = s1.want(n * 4), i_kflag = s1.want(n * 4);
-      const size_t i_ltrank = s1.want((n + 1) * 8);
+      const uint64_t n_ranked = cur.right_only ? 0 : n;  // right-only levels rank nothing
+      const size_t i_ltflag = s1.want(n_ranked * 4), i_kflag = s1.want(n * 4);
+      const size_t i_ltrank = s1.want((n_ranked + 1) * 8);
       const size_t i_scan = s1.want(scan_tmp_elems(std::max<uint64_t>(n, 256ull * 1184)) * 8);
       const size_t i_unique = s1.want(n * 8), i_counters = s1.want(64);
       s1.commit();
@@ -1594,13 +1630,18 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       TAPES_CUDA_CHECK(cudaMemsetAsync(counters, 0, 64, st));
       // lanes of a warp hold different prefixes unless the level is tiny or the table short (M < 32):
       // the warp vote that merges equal keys before the insertion only pays there
-      if (hash_vote < 0 ? c.M < 32 : hash_vote)
-        classify_kernel<true><<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
-      else
-        classify_kernel<false><<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
-      exclusive_scan_u32<true>(ltflag, n, ltrank, scan_tmp, st);
-      uint64_t h_tot[3];
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], ltrank + n, 8, cudaMemcpyDeviceToHost, st));
+      const bool vote = hash_vote < 0 ? c.M < 32 : hash_vote != 0;
+      const unsigned grid = grid_for(n, kThreads);
+      if (cur.right_only) {  // nothing to rank: no node has left children or a stored term
+        if (vote) classify_kernel<true, true><<<grid, kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
+        else classify_kernel<false, true><<<grid, kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
+      } else {
+        if (vote) classify_kernel<true, false><<<grid, kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
+        else classify_kernel<false, false><<<grid, kThreads, 0, st>>>(cur, c, hs, ltflag, keyslot, keys_a, counters);
+        exclusive_scan_u32<true>(ltflag, n, ltrank, scan_tmp, st);
+      }
+      uint64_t h_tot[3] = {0, 0, 0};
+      if (!cur.right_only) TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[0], ltrank + n, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[1], counters + 3, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaMemcpyAsync(&h_tot[2], counters, 8, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1628,8 +1669,12 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     next_level.n_groups = (uint32_t)NG;
     const RadixPlan plan = radix_plan(std::max<uint64_t>(NG, 1));
     s2.reset();  // owns `next` until the end of the next level; the memory of the level before is reused
+    // a level without left parents is followed by right children only: that level is not written out
+    // (Frontier::right_only), only the seed of every group is kept beside the model's group arrays
+    next.right_only = NL == 0 && virtual_right_levels;
     size_t fi[5];
-    plan_frontier(s2, next.n, fi);
+    plan_frontier(s2, next.right_only ? 0 : next.n, fi);
+    const size_t i_gseed = s2.want(next.right_only ? NG * 4 : 0);
     const size_t i_keys_b = s2.want(NG * 8), i_rh = s2.want(256ull * plan.blocks * 4);
     const size_t i_ro = s2.want((256ull * plan.blocks + 1) * 8), i_keyrank = s2.want(n * 4), i_gstat = s2.want(NG * 16);
     const size_t i_consumed = s2.want((size_t)cur_level.n_groups * 4);
@@ -1646,9 +1691,11 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       // the children of the groups; records every group's rank in the table for emit_kernel
       next_level.g_prefix = dkeep<uint32_t>(m, NG);
       next_level.g_adjusted = dkeep<uint32_t>(m, NG);
+      uint32_t* g_seed = next.right_only ? s2.at<uint32_t>(i_gseed) : nullptr;
       emit_groups_kernel<<<grid_for(NG, kThreads), kThreads, 0, st>>>(sorted, (uint32_t)NG, hs, c, next,
                                                                      NL * (uint64_t)m.A, next_level.g_prefix,
-                                                                     next_level.g_adjusted);
+                                                                     next_level.g_adjusted, g_seed);
+      next.g_prefix = next_level.g_prefix; next.g_adjusted = next_level.g_adjusted; next.g_seed = g_seed;
     }
     if (NL) {
       next_level.lp_gid = dkeep<uint32_t>(m, NL);
@@ -1662,9 +1709,12 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       ec.row = dtemp<uint32_t>(2 * NT); ec.val = ec.row + NT;
       edge_chunks.push_back(ec);
     }
-    emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, ltflag, keyslot, ltrank,
-                                                          NL, hs, next, next_level.lp_gid, next_level.lp_io,
-                                                          next_level.lp_len, ec.row, ec.val, keyrank, gstat, counters + 4);
+    if (cur.right_only)
+      emit_right_only_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(n, cur_level.base, keyslot, hs, keyrank, gstat);
+    else
+      emit_kernel<<<grid_for(n, kThreads), kThreads, 0, st>>>(cur, c, cur_level.base, ltflag, keyslot, ltrank,
+                                                            NL, hs, next, next_level.lp_gid, next_level.lp_io,
+                                                            next_level.lp_len, ec.row, ec.val, keyrank, gstat, counters + 4);
     if (NG) {
       // parent lists of the prefix groups: as progressions (first, stride, count) when every list is
       // one - found from the extremes and counts emit_kernel collected, then checked parent by parent

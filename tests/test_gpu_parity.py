@@ -452,8 +452,11 @@ def test_prefix_table_sizing_does_not_change_the_structure(mt, device, monkeypat
     mt.register_rule_set(tag, size_a, configs.random_rule_set(size_a, 6, seed=cl_k))
   p = torch.from_numpy(configs.markov_table(size_a, cl_k, 11)).cuda()
   results = {}
-  for mode in ('0', '1', '2'):
-    monkeypatch.setenv('TAPES_HASH_GUESS', mode)
+  for mode in ('0', '1', '2', 'written-out'):
+    # 'written-out': levels of right children only are materialised like the others instead of being
+    # read off their groups (Frontier::right_only) - again the same structure
+    monkeypatch.setenv('TAPES_HASH_GUESS', '1' if mode == 'written-out' else mode)
+    monkeypatch.setenv('TAPES_VIRTUAL_RIGHT_LEVELS', '0' if mode == 'written-out' else '1')
     mt.u_lib.tapes_release_model(tag.encode(), cl_k)
     model = device.DeviceModel(tag, cl_k)
     info = model.info
@@ -463,7 +466,7 @@ def test_prefix_table_sizing_does_not_change_the_structure(mt, device, monkeypat
     if mode == '2' and info['hash_unique'] > 1024 * info['n_levels']:  # some level has more prefixes than 1024 slots
       assert info['hash_retries'] > 0, info
   mt.u_lib.tapes_release_model(tag.encode(), cl_k)
-  for mode in ('1', '2'):
+  for mode in ('1', '2', 'written-out'):
     assert results[mode][2:] == results['0'][2:], mode
     assert numpy.array_equal(results[mode][0], results['0'][0]), mode
     assert numpy.array_equal(results[mode][1], results['0'][1]), mode
