@@ -666,7 +666,7 @@ def run_b200(args):
   # its children); time = this rank's device expansion without the driver's allocation time
   expand_rank_s = max((timing['device_expand_ms'] - timing['expand_alloc_ms']) * 1e-3, 1e-9)
   expand_gbs = 85.0 * info['n_nodes'] / expand_rank_s / 1e9
-  roofline_expand = dict(bound='hbm', kernel='classify_kernel + emit_kernel + emit_groups_kernel + scans + key sort '
+  roofline_expand = dict(bound='hbm', kernel='classify_kernel + emit_kernel / emit_right_only_kernel + emit_groups_kernel + scan + key sort '
                          '(frontier expansion, once per structure; hash inserts and compaction are latency- and '
                          'atomics-bound rather than streaming)', achieved=expand_gbs, peak=peak, unit='GB/s',
                          frac=expand_gbs / peak, traffic=None, algorithmic_bytes_per_state=85.0,
