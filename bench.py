@@ -84,6 +84,7 @@ def parse_args():
   ap.add_argument('--cpu-rules', type=int, default=0,
                   help='rules in the CPU-baseline sample (0 = one per usable host core, at most all)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-strong-leg', action='store_true', help='N > 1, weak scaling: skip the strong-scaling measurement the line carries')
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='N > 1: weak = rules-per-gpu rules on every rank (work grows with N), strong = the '
                        'N = 1 problem (rules-per-gpu rules in all) dealt to the N ranks')
@@ -755,7 +756,7 @@ def run_b200(args):
   # is also what every rank evaluates alone in the weak run, so its one-GPU time is rank_compute_ms) is
   # dealt to the N ranks by term counts and evaluated with the same fused exchange.
   strong_leg = None
-  if world > 1 and args.scaling == 'weak' and args.exchange == 'peer':
+  if world > 1 and args.scaling == 'weak' and args.exchange == 'peer' and not args.no_strong_leg:
     def measure_strong():
       base = configs.random_rule_set(args.size_a, args.rules_per_gpu, seed=args.seed)
       part_tag = configs.synthetic_tag(args.size_a, args.rules_per_gpu, args.seed) + f'-part{rank}of{world}'

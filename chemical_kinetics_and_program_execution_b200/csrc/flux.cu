@@ -13,7 +13,11 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
+#include <utility>
+#include <vector>
 
 #include "engine.h"
 #include "flux_device.cuh"
@@ -247,12 +251,16 @@ __global__ void __launch_bounds__(kThreads) sum_slots_broadcast_kernel(const dou
                                                                        const __grid_constant__ PeerPointers result,
                                                                        uint32_t world, uint32_t rank, uint64_t block,
                                                                        uint64_t j_lo, uint64_t j_hi, uint64_t n_rows) {
-  const uint64_t j = j_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const uint64_t row = (uint64_t)rank * block + j;
-  if (j >= j_hi || row >= n_rows) return;
-  double total = 0.0;
-  for (uint32_t r = 0; r < world; ++r) total += slots[(uint64_t)r * block + j];
-  for (uint32_t q = 0; q < world; ++q) result.ptr[q][row] = total;
+  // grid-stride: the launch may use fewer blocks than rows / 256 (peer_rhs: a round's sums are pushed at a
+  // moderate rate while the product of the next round runs, so that the product's own peer stores do not
+  // queue behind a burst on the same NVLink egress)
+  for (uint64_t j = j_lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j_hi; j += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = (uint64_t)rank * block + j;
+    if (row >= n_rows) return;
+    double total = 0.0;
+    for (uint32_t r = 0; r < world; ++r) total += slots[(uint64_t)r * block + j];
+    for (uint32_t q = 0; q < world; ++q) result.ptr[q][row] = total;
+  }
 }
 
 // Cross-GPU signalling through peer-visible flag arrays.  flags.ptr[q] holds 2 * world epochs in
@@ -439,6 +447,18 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   const uint64_t sub = g.block / (uint64_t)g.rounds, sub_slices = sub / 32;
   const unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
   unsigned long long* mine = g.flags.ptr[g.rank];
+  // TAPES_PEER_TRACE=1: time stamps (CUDA events on both streams) of every kernel of the exchange, printed
+  // by rank 0 two calls later - a diagnostic
+  static const bool trace = std::getenv("TAPES_PEER_TRACE") != nullptr;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  auto mark = [&](const char* what, cudaStream_t on) {
+    if (!trace) return;
+    cudaEvent_t e;
+    TAPES_CUDA_CHECK(cudaEventCreate(&e));
+    TAPES_CUDA_CHECK(cudaEventRecord(e, on));
+    marks.push_back({what, e});
+  };
+  mark("start", st);
   weights_device(m, d_p, st);
   // the side stream must not run ahead of work already queued on the main stream
   TAPES_CUDA_CHECK(cudaEventRecord(g.fork, st));
@@ -446,6 +466,11 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
   const unsigned scatter_grid = grid_for(sub_slices * world * 32, kThreads);
   const RightFlux of = right_flux_of(m);
   const unsigned long long base = g.epoch;
+  // blocks of the owner's sum + broadcast kernel in the rounds that run beside a product (0 = one thread per
+  // row): measured at 2 GPUs, 4 rounds: uncapped 6.33 ms per step, 296 blocks 6.09, 148 blocks 6.08, 64 blocks
+  // 6.76 (too slow to keep up), profiles/r02_aq_sum_blocks_n2.log
+  static const int sum_blocks = std::getenv("TAPES_PEER_SUM_BLOCKS") ? std::atoi(std::getenv("TAPES_PEER_SUM_BLOCKS")) : 296;
+  mark("weights done", st);
   for (int c = 0; c < g.rounds; ++c) {
     if (m.flux_unroll >= 4)
       flux_slices_scatter_kernel<4, 6><<<scatter_grid, kThreads, 0, st>>>(
@@ -455,18 +480,48 @@ void peer_rhs(PeerGroup& g, Model& m, const double* d_p, cudaStream_t st) {
       flux_slices_scatter_kernel<3, 8><<<scatter_grid, kThreads, 0, st>>>(
           fs.slice_ptr, fs.slice_runs, fs.words, m.node_w, g.staging, world, rank, g.block, sub_slices, (uint64_t)c,
           fs.n_slices, m.n_states, of);
+    mark("scatter done", st);
     peer_signal_kernel<<<1, 32, 0, st>>>(g.flags, world, rank, 0u, base + c + 1);
     peer_wait_kernel<<<1, 32, 0, g.side>>>(mine, world, 0u, base + c + 1, timeout_ns, g.d_error);
-    sum_slots_broadcast_kernel<<<grid_for(sub, kThreads), kThreads, 0, g.side>>>(
+    mark("all partials here", g.side);
+    // every round but the last runs beside the next round's product
+    const unsigned sum_grid = (c + 1 < g.rounds && sum_blocks > 0) ? std::min<unsigned>(grid_for(sub, kThreads), (unsigned)sum_blocks)
+                                                                    : grid_for(sub, kThreads);
+    sum_slots_broadcast_kernel<<<sum_grid, kThreads, 0, g.side>>>(
         g.staging.ptr[g.rank], g.result, world, rank, g.block, sub * c, sub * (c + 1), m.n_states);
+    mark("sums sent", g.side);
   }
   g.epoch = base + g.rounds;
   // every owner's sums have landed everywhere (and its slots may be overwritten) before st goes on
   peer_signal_kernel<<<1, 32, 0, g.side>>>(g.flags, world, rank, 1u, g.epoch);
   peer_wait_kernel<<<1, 32, 0, g.side>>>(mine, world, 1u, g.epoch, timeout_ns, g.d_error);
+  mark("all sums here", g.side);
   TAPES_CUDA_CHECK(cudaEventRecord(g.join, g.side));
   TAPES_CUDA_CHECK(cudaStreamWaitEvent(st, g.join, 0));
   TAPES_CUDA_CHECK(cudaGetLastError());
+  if (trace) {
+    // printed two calls later, when the events have completed anyway: the calls stay free-running
+    static std::vector<std::vector<std::pair<const char*, cudaEvent_t>>> pending;
+    static cudaEvent_t previous_end = nullptr;
+    pending.push_back(marks);
+    if (pending.size() > 2) {
+      auto done = pending.front();
+      pending.erase(pending.begin());
+      TAPES_CUDA_CHECK(cudaEventSynchronize(done.back().second));
+      if (rank == 0) std::fprintf(stderr, "[peer trace] rounds=%d:", g.rounds);
+      float ms = 0;
+      if (previous_end && cudaEventElapsedTime(&ms, previous_end, done.front().second) == cudaSuccess && rank == 0)
+        std::fprintf(stderr, " since the end of the call before %.3f;", ms);
+      for (auto& mk : done) {
+        const cudaError_t err = cudaEventElapsedTime(&ms, done.front().second, mk.second);
+        if (rank == 0) std::fprintf(stderr, " %s %.3f%s;", mk.first, ms, err == cudaSuccess ? "" : cudaGetErrorName(err));
+      }
+      if (rank == 0) std::fprintf(stderr, "\n");
+      if (previous_end) cudaEventDestroy(previous_end);
+      previous_end = done.back().second;
+      for (size_t i = 0; i + 1 < done.size(); ++i) cudaEventDestroy(done[i].second);
+    }
+  }
   end_use(m, st);  // the product kernels read the model's weights after weights_device's own record
 }
 
