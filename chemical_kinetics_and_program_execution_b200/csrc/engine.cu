@@ -1802,6 +1802,13 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   m.stats.device_expand_ms = ms_since(t_expand);
   m.stats.expand_alloc_ms = g_alloc_ms;
   auto t_lists = std::chrono::steady_clock::now();
+  auto trace_phase = [&](const char* what, std::chrono::steady_clock::time_point& since) {
+    if (!build_trace) return;
+    TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+    std::fprintf(stderr, "[tapes] %s: %.2f ms\n", what, ms_since(since));
+    since = std::chrono::steady_clock::now();
+  };
+  auto t_phase = t_lists;
   // ---- the sums of all prefix groups in one array; per-prefix lists of the groups (right-chain outflow) ----
   // A right child of group g with prefix q leaves row q * A + x with weight sum(g) * ratio[q * A + x]: all
   // right children of all groups with prefix q share the factor ratio[row], so the rows' outflow
@@ -1886,6 +1893,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     }
   }
 
+  trace_phase("per-prefix lists of the groups", t_phase);
   // seeds walk through p together (Level::block_order): sort the blocks of 256 groups of every
   // level by the prefix they start at; a level whose order comes out as the identity keeps none.
   // The same pass finds the regular blocks (Level::plane_blocks) and lists the others.
@@ -1939,6 +1947,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
   const double lists_and_blocks_ms = ms_since(t_lists);  // per-prefix lists, block order, plane blocks
 
+  trace_phase("block order and plane blocks", t_phase);
   // ---- CSR assembly: count per state, scan, fill, sort inside each row ----
   auto t_csr = std::chrono::steady_clock::now();
   const uint64_t n = m.n_states;
@@ -1952,7 +1961,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
     m.row_ptr = dkeep<uint64_t>(m, n + 1);
     uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(n), st);
     exclusive_scan_u32(cnt, n, m.row_ptr, scan_tmp, st);
+    trace_phase("CSR: count + scan", t_phase);
     m.entries = dtemp<uint32_t>(m.nnz_stored);
+    trace_phase("CSR: allocation of the entries", t_phase);
     TAPES_CUDA_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
     for (EdgeChunk& ec : edge_chunks) {
       group_fill_vals_kernel<<<grid_for(ec.n, kThreads), kThreads, 0, st>>>(ec.row, ec.val, ec.n, m.row_ptr, cnt, m.entries);
@@ -1960,7 +1971,9 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       cudaFree(ec.row);  // row and val share one allocation
       ec.row = ec.val = nullptr;
     }
+    trace_phase("CSR: fill, edge chunks freed", t_phase);
     sort_groups(m.row_ptr, n, m.entries, st);
+    trace_phase("CSR: sort inside the rows", t_phase);
     dfree(cnt, st); dfree(scan_tmp, st);
     TAPES_CUDA_CHECK(cudaGetLastError());
   }
