@@ -1900,6 +1900,7 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   {
     std::vector<Level::PlaneBlock> recs;
     std::vector<uint32_t> flags, order, general;
+    std::vector<uint64_t> keyed;
     std::vector<Level::PlaneBlock> planes;
     for (Level& lv : m.levels) {
       if (!lv.g_prefix || lv.n_groups <= (uint32_t)kThreads) continue;
@@ -1912,10 +1913,13 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
       TAPES_CUDA_CHECK(cudaMemcpyAsync(flags.data(), d_flag, n_blocks * 4, cudaMemcpyDeviceToHost, st));
       TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
       dfree(d_rec, st); dfree(d_flag, st);
+      // blocks by the prefix they start at, ties in block order: (prefix, block) pairs sort an order of
+      // magnitude faster than a stable sort of the block numbers through the records
+      keyed.resize(n_blocks);
+      for (size_t b = 0; b < n_blocks; ++b) keyed[b] = ((uint64_t)recs[b].prefix0 << 32) | (uint64_t)b;
+      std::sort(keyed.begin(), keyed.end());
       order.resize(n_blocks);
-      for (size_t b = 0; b < n_blocks; ++b) order[b] = (uint32_t)b;
-      std::stable_sort(order.begin(), order.end(),
-                       [&](uint32_t x, uint32_t y) { return recs[x].prefix0 < recs[y].prefix0; });
+      for (size_t b = 0; b < n_blocks; ++b) order[b] = (uint32_t)keyed[b];
       bool identity = true;
       for (size_t b = 0; b < n_blocks && identity; ++b) identity = order[b] == b;
       if (!identity) {
