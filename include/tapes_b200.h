@@ -161,7 +161,10 @@ int tapes_sync(void* model);
  * per-step ratio tables (0, 1: right extensions, 2: also left extensions to a full window), entries
  * the flux structure stores (nnz minus the entries of right children, whose flux is evaluated per
  * prefix group from the group sums), 1 when the weights of right children are written per step because
- * a later level reads them (else they exist only after tapes_export_node_weights).
+ * a later level reads them (else they exist only after tapes_export_node_weights), levels of the
+ * build whose table of prefixes was sized too small at first and redone with the safe size, table /
+ * ratio entries one step reads at most once per level (sum over the levels of min(nodes, states):
+ * what bench.py counts as the compulsory table reads of the level phase).
  * Returns how many were written. */
 int tapes_model_info(void* model, int64_t* out, int capacity);
 
