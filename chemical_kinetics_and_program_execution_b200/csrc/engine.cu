@@ -1071,6 +1071,43 @@ __global__ void __launch_bounds__(kThreads) classify_plane_blocks_kernel(Level l
   }
 }
 
+// Order of the blocks of 256 groups of a level and their split into plane blocks and the others, on
+// the device (the host used to fetch the records of every level, sort them and send three arrays back:
+// 14 ms of copies and synchronisation for 0.7 ms of kernels at the bench size).
+__global__ void plane_keys_kernel(const Level::PlaneBlock* __restrict__ rec, uint32_t n_blocks, uint64_t* __restrict__ keys) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_blocks) keys[b] = ((uint64_t)rec[b].prefix0 << 32) | b;  // by prefix, ties in block order
+}
+
+// order[i] = block at position i; taken[i] = whether that block is a plane block; facts[1] counts the
+// positions that are not their own block (0: the order is the identity).
+__global__ void plane_order_kernel(const uint64_t* __restrict__ sorted, uint32_t n_blocks, const uint32_t* __restrict__ is_plane,
+                                   uint32_t* __restrict__ order, uint32_t* __restrict__ taken,
+                                   unsigned long long* __restrict__ facts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool moved = false;
+  if (i < n_blocks) {
+    const uint32_t b = (uint32_t)sorted[i];
+    order[i] = b;
+    taken[i] = is_plane[b] ? 1u : 0u;
+    moved = b != i;
+  }
+  block_add(moved ? 1ull : 0ull, &facts[1]);
+}
+
+// Plane records and the numbers of the other blocks, both in the order of `order`; facts[0] = plane blocks.
+__global__ void plane_partition_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ taken,
+                                       const uint64_t* __restrict__ position, const Level::PlaneBlock* __restrict__ rec,
+                                       uint32_t n_blocks, Level::PlaneBlock* __restrict__ planes,
+                                       uint32_t* __restrict__ general, unsigned long long* __restrict__ facts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_blocks) return;
+  const uint64_t before = position[i];  // plane blocks before position i
+  if (taken[i]) planes[before] = rec[order[i]];
+  else general[i - before] = order[i];
+  if (i == 0) facts[0] = position[n_blocks];
+}
+
 // ---------------------------------------------------------------------------------------------
 // Small problems: the whole right-hand side in ONE launch.
 //
@@ -1896,54 +1933,64 @@ std::unique_ptr<Model> build_model(const RuleTable& table, cudaStream_t stream) 
   trace_phase("per-prefix lists of the groups", t_phase);
   // seeds walk through p together (Level::block_order): sort the blocks of 256 groups of every
   // level by the prefix they start at; a level whose order comes out as the identity keeps none.
-  // The same pass finds the regular blocks (Level::plane_blocks) and lists the others.
+  // The same pass finds the regular blocks (Level::plane_blocks) and lists the others.  Everything
+  // stays on the device; the host reads two numbers per level at the end.
   {
-    std::vector<Level::PlaneBlock> recs;
-    std::vector<uint32_t> flags, order, general;
-    std::vector<uint64_t> keyed;
-    std::vector<Level::PlaneBlock> planes;
-    for (Level& lv : m.levels) {
-      if (!lv.g_prefix || lv.n_groups <= (uint32_t)kThreads) continue;
+    std::vector<size_t> which;  // levels with more than one block
+    for (size_t l = 0; l < m.levels.size(); ++l)
+      if (m.levels[l].g_prefix && m.levels[l].n_groups > (uint32_t)kThreads) which.push_back(l);
+    unsigned long long* facts = which.empty() ? nullptr : dalloc<unsigned long long>(2 * which.size(), st);
+    if (facts) TAPES_CUDA_CHECK(cudaMemsetAsync(facts, 0, 16 * which.size(), st));
+    std::vector<uint32_t*> orders(which.size()), generals(which.size());
+    std::vector<Level::PlaneBlock*> planes(which.size());
+    for (size_t w = 0; w < which.size(); ++w) {
+      Level& lv = m.levels[which[w]];
       const size_t n_blocks = ((size_t)lv.n_groups + kThreads - 1) / kThreads;
+      const unsigned grid = grid_for(n_blocks, kThreads);
       Level::PlaneBlock* d_rec = dalloc<Level::PlaneBlock>(n_blocks, st);
       uint32_t* d_flag = dalloc<uint32_t>(n_blocks, st);
       classify_plane_blocks_kernel<<<(unsigned)n_blocks, kThreads, 0, st>>>(lv, c, (uint32_t)n_blocks, d_rec, d_flag);
-      recs.resize(n_blocks); flags.resize(n_blocks);
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(recs.data(), d_rec, n_blocks * sizeof(Level::PlaneBlock), cudaMemcpyDeviceToHost, st));
-      TAPES_CUDA_CHECK(cudaMemcpyAsync(flags.data(), d_flag, n_blocks * 4, cudaMemcpyDeviceToHost, st));
-      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
-      dfree(d_rec, st); dfree(d_flag, st);
-      // blocks by the prefix they start at, ties in block order: (prefix, block) pairs sort an order of
-      // magnitude faster than a stable sort of the block numbers through the records
-      keyed.resize(n_blocks);
-      for (size_t b = 0; b < n_blocks; ++b) keyed[b] = ((uint64_t)recs[b].prefix0 << 32) | (uint64_t)b;
-      std::sort(keyed.begin(), keyed.end());
-      order.resize(n_blocks);
-      for (size_t b = 0; b < n_blocks; ++b) order[b] = (uint32_t)keyed[b];
-      bool identity = true;
-      for (size_t b = 0; b < n_blocks && identity; ++b) identity = order[b] == b;
-      if (!identity) {
-        uint32_t* d_order = dkeep<uint32_t>(m, n_blocks);
-        TAPES_CUDA_CHECK(cudaMemcpyAsync(d_order, order.data(), n_blocks * 4, cudaMemcpyHostToDevice, st));
-        lv.block_order = d_order;
-      }
-      general.clear(); planes.clear();
-      for (uint32_t b : order) {
-        if (flags[b]) planes.push_back(recs[b]);
-        else general.push_back(b);
-      }
-      if (!planes.empty()) {
-        Level::PlaneBlock* d_planes = dkeep<Level::PlaneBlock>(m, planes.size());
-        uint32_t* d_general = dkeep<uint32_t>(m, general.size());
-        TAPES_CUDA_CHECK(cudaMemcpyAsync(d_planes, planes.data(), planes.size() * sizeof(Level::PlaneBlock), cudaMemcpyHostToDevice, st));
-        if (!general.empty())
-          TAPES_CUDA_CHECK(cudaMemcpyAsync(d_general, general.data(), general.size() * 4, cudaMemcpyHostToDevice, st));
-        lv.plane_blocks = d_planes; lv.n_plane_blocks = (uint32_t)planes.size();
-        lv.general_blocks = d_general; lv.n_general_blocks = (uint32_t)general.size();
-        m.stats.plane_groups += (int64_t)planes.size() * kThreads;
-      }
-      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));  // the host vectors are reused by the next level
+      const RadixPlan plan = radix_plan(n_blocks);
+      uint64_t* keys = dalloc<uint64_t>(n_blocks, st);
+      uint64_t* keys_alt = dalloc<uint64_t>(n_blocks, st);
+      uint32_t* hist = dalloc<uint32_t>(256ull * plan.blocks, st);
+      uint64_t* offsets = dalloc<uint64_t>(256ull * plan.blocks + 1, st);
+      uint64_t* scan_tmp = dalloc<uint64_t>(scan_tmp_elems(std::max<uint64_t>(n_blocks, 256ull * plan.blocks)), st);
+      plane_keys_kernel<<<grid, kThreads, 0, st>>>(d_rec, (uint32_t)n_blocks, keys);
+      uint64_t block_bits = 1;
+      while ((1ull << block_bits) < n_blocks) ++block_bits;
+      const uint64_t key_bits = ((1ull << block_bits) - 1) | (((prefix_bits ? ((1ull << prefix_bits) - 1) : 0ull)) << 32);
+      uint64_t* sorted = radix_sort_u64(keys, keys_alt, n_blocks, key_bits, hist, offsets, scan_tmp, st);
+      orders[w] = dkeep<uint32_t>(m, n_blocks);
+      planes[w] = dkeep<Level::PlaneBlock>(m, n_blocks);  // room for the case that every block is one
+      generals[w] = dkeep<uint32_t>(m, n_blocks);
+      uint32_t* taken = dalloc<uint32_t>(n_blocks, st);
+      uint64_t* position = dalloc<uint64_t>(n_blocks + 1, st);
+      plane_order_kernel<<<grid, kThreads, 0, st>>>(sorted, (uint32_t)n_blocks, d_flag, orders[w], taken, facts + 2 * w);
+      exclusive_scan_u32(taken, n_blocks, position, scan_tmp, st);
+      plane_partition_kernel<<<grid, kThreads, 0, st>>>(orders[w], taken, position, d_rec, (uint32_t)n_blocks, planes[w],
+                                                       generals[w], facts + 2 * w);
+      dfree(d_rec, st); dfree(d_flag, st); dfree(keys, st); dfree(keys_alt, st); dfree(hist, st); dfree(offsets, st);
+      dfree(scan_tmp, st); dfree(taken, st); dfree(position, st);
     }
+    if (facts) {
+      std::vector<unsigned long long> h_facts(2 * which.size());
+      TAPES_CUDA_CHECK(cudaMemcpyAsync(h_facts.data(), facts, 16 * which.size(), cudaMemcpyDeviceToHost, st));
+      TAPES_CUDA_CHECK(cudaStreamSynchronize(st));
+      dfree(facts, st);
+      for (size_t w = 0; w < which.size(); ++w) {
+        Level& lv = m.levels[which[w]];
+        const size_t n_blocks = ((size_t)lv.n_groups + kThreads - 1) / kThreads;
+        const uint64_t n_planes = h_facts[2 * w], moved = h_facts[2 * w + 1];
+        if (moved) lv.block_order = orders[w];
+        if (n_planes) {
+          lv.plane_blocks = planes[w]; lv.n_plane_blocks = (uint32_t)n_planes;
+          lv.general_blocks = generals[w]; lv.n_general_blocks = (uint32_t)(n_blocks - n_planes);
+          m.stats.plane_groups += (int64_t)n_planes * kThreads;
+        }
+      }
+    }
+    TAPES_CUDA_CHECK(cudaGetLastError());
   }
   m.n_nodes = cur_level.base;  // base of the (empty) level after the last
   m.stats.nodes = (int64_t)m.n_nodes;
