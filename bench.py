@@ -84,6 +84,7 @@ def parse_args():
   ap.add_argument('--cpu-rules', type=int, default=0,
                   help='rules in the CPU-baseline sample (0 = one per usable host core, at most all)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-prewarm', action='store_true', help='do not touch the device memory once before the structure build')
   ap.add_argument('--no-strong-leg', action='store_true', help='N > 1, weak scaling: skip the strong-scaling measurement the line carries')
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                   help='N > 1: weak = rules-per-gpu rules on every rank (work grows with N), strong = the '
@@ -471,6 +472,28 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------
 # CUDA path
 # --------------------------------------------------------------------------------------------
+def prewarm_device_memory(device, fraction=0.45):
+  """Warm-up of the driver's allocator, like the warm-up steps of the timed loop: the first process
+  that maps a large part of a fresh box's HBM pays the driver 0.7-3 s for it (seen as
+  build.expand_alloc_ms of 700-3000 ms in the first bench of a box and 20-30 ms in the second,
+  profiles/README.md), which says nothing about the structure build.  One allocation of `fraction` of
+  the free memory is written once and handed back before the build is timed; what it cost is reported
+  in build.prewarm."""
+  import torch
+  t0 = time.perf_counter()
+  free, _total = torch.cuda.mem_get_info(device)
+  n_bytes = int(free * fraction)
+  try:
+    block = torch.empty(n_bytes, dtype=torch.uint8, device=device)
+    block.zero_()
+    torch.cuda.synchronize(device)
+    del block
+    torch.cuda.empty_cache()
+  except RuntimeError as ex:  # out of memory on a shared device: the build will say so itself
+    return dict(bytes=0, seconds=time.perf_counter() - t0, error=str(ex)[:120])
+  return dict(bytes=n_bytes, seconds=time.perf_counter() - t0)
+
+
 def run_b200(args):
   import torch
   import torch.distributed as dist
@@ -493,6 +516,7 @@ def run_b200(args):
   n = args.size_a ** args.cl_k
   rules, local_rules, tag = make_workload(args, world, rank)
   mt.register_rule_set(tag, args.size_a, local_rules)
+  prewarm = None if args.no_prewarm else prewarm_device_memory(device)
   t0 = time.perf_counter()
   model = dev.DeviceModel(tag, args.cl_k)
   torch.cuda.synchronize()
@@ -864,7 +888,7 @@ def run_b200(args):
                 states_expanded_note=('forest nodes + program worlds of all ranks / (host enumeration + device expansion) of '
                                       'the slowest rank; the first figure leaves out the time inside cudaMalloc / cudaFree '
                                       '(build.expand_alloc_ms), the second includes it'),
-                build=dict(seconds=build_s, **timing, forest_levels=info['n_levels'],
+                build=dict(seconds=build_s, **timing, prewarm=prewarm, forest_levels=info['n_levels'],
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],
                            flux_slices={k: info.get(k) for k in ('n_slices', 'slice_words', 'runs', 'run_entries',
                                                                   'column_entries', 'column_slots')}))
