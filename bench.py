@@ -887,7 +887,9 @@ def run_b200(args):
                 states_expanded_per_s_incl_driver_alloc=expanded_total / max(expand_s, 1e-9),
                 states_expanded_note=('forest nodes + program worlds of all ranks / (host enumeration + device expansion) of '
                                       'the slowest rank; the first figure leaves out the time inside cudaMalloc / cudaFree '
-                                      '(build.expand_alloc_ms), the second includes it'),
+                                      '(build.expand_alloc_ms), the second includes it; before the build is timed the '
+                                      'device memory is touched once (build.prewarm; --no-prewarm to leave that out), '
+                                      'neither figure contains that'),
                 build=dict(seconds=build_s, **timing, prewarm=prewarm, forest_levels=info['n_levels'],
                            hash_inserts=info['hash_inserts'], hash_unique=info['hash_unique'],
                            flux_slices={k: info.get(k) for k in ('n_slices', 'slice_words', 'runs', 'run_entries',
